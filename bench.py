@@ -1,0 +1,373 @@
+#!/usr/bin/env python
+"""Benchmark of the jax-sgmc sampling hot path on B200 (BASELINE.json metric).
+
+Workload (configs[1], "C2"): Bayesian logistic regression, N = 1M synthetic
+observations x 1024 features resident in HBM, minibatch 1024 shared by all
+chains (the reference default: every chain's data key is PRNGKey(0)), 4096
+parallel pSGLD (SGLD + RMSprop) chains per GPU, chain c seeded PRNGKey(c).
+One "step" = one pass of the hot path over all chains of a rank:
+    minibatch draw (threefry randint)  ->  GLM potential + gradient
+    ->  fused pSGLD update with in-kernel jax.random noise.
+metric = chain-steps/sec (chains x steps / seconds), whole job over all GPUs.
+N > 1: chains are sharded over ranks (independent chains, no collective:
+"weak" scaling, 4096 chains per GPU).
+
+JSON keys follow the driver contract; see DESIGN.md "Measurement".
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "chain-steps/sec (BLR, 4096 chains)"
+UNIT = "chain-steps/s"
+BYTES_PER_PARAM = {"sgld": 12, "sgld_rms": 20}
+
+
+def parse():
+  p = argparse.ArgumentParser()
+  p.add_argument("--gpus", type=int, default=1)
+  p.add_argument("--steps", type=int, default=200)
+  p.add_argument("--warmup", type=int, default=10)
+  p.add_argument("--impl", default="b200", choices=["b200", "reference"])
+  p.add_argument("--chains", type=int, default=4096)
+  p.add_argument("--features", type=int, default=1024)
+  p.add_argument("--batch", type=int, default=1024)
+  p.add_argument("--observations", type=int, default=1_000_000)
+  p.add_argument("--path", default="auto",
+                 choices=["auto", "simt", "tc_parity", "tc_throughput"])
+  p.add_argument("--no-cpu-baseline", action="store_true")
+  p.add_argument("--cpu-seconds", type=float, default=15.0)
+  return p.parse_args()
+
+
+# ---------------------------------------------------------------------------
+class ClockSampler:
+  """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+
+  Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+       "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+       "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+  def __init__(self, gpu_index: int):
+    self.gpu, self.proc, self.lines = gpu_index, None, []
+
+  def start(self):
+    try:
+      self.proc = subprocess.Popen(
+          ["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}",
+           "--format=csv,noheader,nounits", "-lms", "100"],
+          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+      self.t = threading.Thread(target=self._read, daemon=True)
+      self.t.start()
+    except Exception:
+      self.proc = None
+
+  def _read(self):
+    for line in self.proc.stdout:
+      self.lines.append(line.strip())
+
+  def stop(self):
+    if self.proc is None:
+      return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+    time.sleep(0.15)
+    self.proc.terminate()
+    sm, mx, reasons = [], [], set()
+    names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+    for ln in self.lines:
+      f = [x.strip() for x in ln.split(",")]
+      if len(f) < 9:
+        continue
+      try:
+        sm.append(float(f[1])); mx.append(float(f[2]))
+      except ValueError:
+        continue
+      for name, val in zip(names, f[5:9]):
+        if val.lower().startswith("active"):
+          reasons.add(name)
+    return {"sm_mhz": float(np.median(sm)) if sm else None,
+            "sm_max_mhz": float(max(mx)) if mx else None,
+            "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def dist_env():
+  rank = int(os.environ.get("RANK", "0"))
+  world = int(os.environ.get("WORLD_SIZE", "1"))
+  local = int(os.environ.get("LOCAL_RANK", "0"))
+  return rank, world, local
+
+
+class Control:
+  """Barrier + max-over-ranks on the host control plane (torch.distributed,
+  gloo).  Plumbing only: no data-path collective exists for sharded chains."""
+
+  def __init__(self, world):
+    self.world = world
+    if world > 1:
+      import torch.distributed as dist
+      os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+      dist.init_process_group("gloo")
+      self.dist = dist
+
+  def barrier(self):
+    if self.world > 1:
+      self.dist.barrier()
+
+  def max(self, x: float) -> float:
+    if self.world == 1:
+      return x
+    import torch
+    t = torch.tensor([x], dtype=torch.float64)
+    self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+    return float(t[0])
+
+  def sum(self, x: float) -> float:
+    if self.world == 1:
+      return x
+    import torch
+    t = torch.tensor([x], dtype=torch.float64)
+    self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+    return float(t[0])
+
+  def close(self):
+    if self.world > 1:
+      self.dist.destroy_process_group()
+
+
+# ---------------------------------------------------------------------------
+def cpu_reference_run(args, seconds: float, max_chains: int = 64):
+  """The oracle port (NumPy f32 restatement of the reference, OpenBLAS on all
+  host cores) timed on a bounded sample of the same workload: `max_chains`
+  chains of the C2 model, same d / batch, as many steps as fit in `seconds`."""
+  from oracle import data as odata
+  from oracle import prng
+  from oracle import sgmc as osgmc
+  d, n = args.features, args.batch
+  Ns = 20000                                   # bounded data sample
+  rng = np.random.default_rng(0)
+  X = (rng.standard_normal((Ns, d)) / np.sqrt(d)).astype(np.float32)
+  w = rng.standard_normal(d).astype(np.float32)
+  y = (rng.random(Ns) < 1 / (1 + np.exp(-(X @ w)))).astype(np.float32)
+  C = max_chains
+  keys = np.stack([prng.PRNGKey(c) for c in range(C)])
+  st = osgmc.langevin_init(np.zeros((C, d), np.float32), keys, rms=True)
+  pot = osgmc.minibatch_potential(osgmc.Logistic(d, 0),
+                                  osgmc.Prior("gaussian", 0, d, 10.0))
+  dk = prng.PRNGKey(0)
+  steps, t0 = 0, time.perf_counter()
+  while True:
+    dk, idx = odata.device_draw(dk, n, Ns)
+    Xb, yb = X[idx], y[idx]
+    st = osgmc.langevin_update(st, lambda th: pot(th, (Xb, yb), args.observations),
+                               [d], 1e-3, 1.0)
+    steps += 1
+    el = time.perf_counter() - t0
+    if el >= seconds or steps >= 10000:
+      break
+  return {"value": C * steps / el, "unit": UNIT, "cores": os.cpu_count(),
+          "kind": "port",
+          "sample": f"{C} chains x {steps} pSGLD steps, d={d}, batch={n}, "
+                    f"NumPy f32 restatement of the reference (oracle/), "
+                    f"{el:.1f} s"}, steps, el
+
+
+def run_reference(args):
+  rank, world, _ = dist_env()
+  if rank != 0:
+    return
+  base, steps, el = cpu_reference_run(args, max(5.0, min(60.0, args.cpu_seconds)))
+  line = {
+      "impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT,
+      "n_gpus": args.gpus, "steps": steps, "warmup": 0,
+      "ms_per_step": 1e3 * el / steps, "higher_is_better": True,
+      "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+      "config": {"workload": "C2 Bayesian logistic regression pSGLD (bounded CPU sample)",
+                 "chains": 64, "features": args.features, "batch": args.batch},
+      "cpu_baseline": base,
+      "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0,
+              "d2h_bytes_per_step": 0},
+      "note": "jax is not installable in this image: the reference arm times "
+              "the NumPy restatement of the reference (oracle/), not jax-sgmc",
+  }
+  print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------
+def run_b200(args):
+  from jax_sgmc_b200 import _lib, device, ops
+  from jax_sgmc_b200.device import DeviceArray as DA, Event, Stream
+  rank, world, local = dist_env()
+  ctl = Control(world)
+  _lib.load()
+  device.set_device(local)
+  stream = Stream.create()
+  device.set_current_stream(stream)
+
+  C, d, n, N = args.chains, args.features, args.batch, args.observations
+  path = args.path
+  if path == "auto":
+    path = os.environ.get("SGMC_BENCH_PATH", "simt")
+  pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+  peaks = json.load(open(pk)) if os.path.exists(pk) else {}
+
+  # ---- resident state ------------------------------------------------------
+  X, y, _ = ops.synth_logistic_data(0, N, d)
+  theta = DA.zeros((C, d))
+  v = DA.full((C, d), 1.0)
+  grad = DA.zeros((C, d))
+  keys = [ops.prng_keys(range(rank * C, (rank + 1) * C)), DA((C, 2), np.uint32)]
+  dkey = [DA.from_numpy(ops.prng_key(0)), DA((2,), np.uint32)]
+  idx = DA((n,), np.int32)
+  U, var = DA((C,), np.float32), DA((C,), np.float32)
+  spec = ops.glm_spec("logistic", d, 0, prior="gaussian", prior_off=0,
+                      prior_size=d, prior_scale=10.0)
+  ws = ops.glm_workspace(C, n, d, path)
+  eps = 1e-3
+  state = {"k": 0}
+
+  def step():
+    k = state["k"]
+    ops.minibatch_draw(dkey[k % 2], dkey[(k + 1) % 2], idx, N)
+    ops.glm_potential_grad(spec, theta, X, y, idx, N, U, var, grad,
+                           workspace=ws, path=path)
+    ops.sgld_update(theta, grad, keys[k % 2], keys[(k + 1) % 2], [d], eps, 1.0,
+                    v=v, alpha=0.9, lmbd=1e-5)
+    state["k"] = k + 1
+
+  for _ in range(max(3, args.warmup)):
+    step()
+  stream.sync()
+
+  # ---- timed region: exactly K steps ----------------------------------------
+  sampler = ClockSampler(local)
+  sampler.start()
+  ctl.barrier()
+  device.synchronize()
+  e0, e1 = Event(), Event()
+  l0 = ops.launch_count()
+  e0.record(stream)
+  for _ in range(args.steps):
+    step()
+  e1.record(stream)
+  e1.sync()
+  device.synchronize()
+  launches = ops.launch_count() - l0
+  ms = e0.elapsed_ms(e1)
+  ctl.barrier()
+  clocks = sampler.stop()
+  ms = ctl.max(ms)
+  value = world * C * args.steps / (ms * 1e-3)
+
+  # ---- roofline of the dominant HBM kernel (fused pSGLD update) --------------
+  # rotating state sets so the working set (R x 67 MB) exceeds the 126 MB L2
+  R = 6
+  sets = [(DA.zeros((C, d)), DA.full((C, d), 1.0), DA.full((C, d), 0.01))
+          for _ in range(R)]
+  kk = [ops.prng_keys(range(C)), DA((C, 2), np.uint32)]
+  for r in range(R):
+    ops.sgld_update(sets[r][0], sets[r][2], kk[0], kk[1], [d], eps, 1.0, v=sets[r][1])
+  stream.sync()
+  reps = 20
+  e0.record(stream)
+  for i in range(reps * R):
+    t_, v_, g_ = sets[i % R]
+    ops.sgld_update(t_, g_, kk[i % 2], kk[(i + 1) % 2], [d], eps, 1.0, v=v_)
+  e1.record(stream)
+  e1.sync()
+  upd_ms = e0.elapsed_ms(e1) / (reps * R)
+  alg_bytes = C * d * BYTES_PER_PARAM["sgld_rms"]
+  achieved = alg_bytes / (upd_ms * 1e-3) / 1e9
+  peak = peaks.get("hbm_gbs", 6650.0)
+  roofline = {"bound": "hbm", "kernel": "k_noise_pass<SgldOp<rms>>",
+              "achieved": achieved, "peak": peak, "unit": "GB/s",
+              "frac": achieved / peak, "traffic": None,
+              "us_per_launch": upd_ms * 1e3,
+              "peak_source": "measured" if "hbm_gbs" in peaks else "fallback",
+              "algorithmic_bytes_per_launch": alg_bytes}
+
+  # ---- e2e: host data loader path (minibatch from pinned host memory) ---------
+  import ctypes as Ct
+  hX, hy, hU = Ct.c_void_p(), Ct.c_void_p(), Ct.c_void_p()
+  _lib.call("sgmc_host_alloc", Ct.byref(hX), n * d * 4)
+  _lib.call("sgmc_host_alloc", Ct.byref(hy), n * 4)
+  _lib.call("sgmc_host_alloc", Ct.byref(hU), C * 4 * 2)
+  Xb = ops.gather_rows(X, idx)
+  yb = ops.gather_rows(y.reshape(N, 1), idx)
+  _lib.call("sgmc_memcpy_d2h", hX, Ct.c_void_p(Xb.ptr), n * d * 4, stream.handle)
+  _lib.call("sgmc_memcpy_d2h", hy, Ct.c_void_p(yb.ptr), n * 4, stream.handle)
+  stream.sync()
+
+  def e2e_step():
+    k = state["k"]
+    _lib.call("sgmc_memcpy_h2d", Ct.c_void_p(Xb.ptr), hX, n * d * 4, stream.handle)
+    _lib.call("sgmc_memcpy_h2d", Ct.c_void_p(yb.ptr), hy, n * 4, stream.handle)
+    ops.glm_potential_grad(spec, theta, Xb, yb, None, N, U, var, grad,
+                           workspace=ws, path=path, batch_size=n)
+    ops.sgld_update(theta, grad, keys[k % 2], keys[(k + 1) % 2], [d], eps, 1.0,
+                    v=v, alpha=0.9, lmbd=1e-5)
+    _lib.call("sgmc_memcpy_d2h", hU, Ct.c_void_p(U.ptr), C * 4, stream.handle)
+    _lib.call("sgmc_memcpy_d2h", Ct.c_void_p(hU.value + C * 4), Ct.c_void_p(var.ptr),
+              C * 4, stream.handle)
+    stream.sync()                    # the host consumes the step's result
+    state["k"] = k + 1
+
+  for _ in range(3):
+    e2e_step()
+  ctl.barrier()
+  e2e_steps = max(10, args.steps // 4)
+  t0 = time.perf_counter()
+  for _ in range(e2e_steps):
+    e2e_step()
+  e2e_s = ctl.max(time.perf_counter() - t0)
+  e2e = {"value": world * C * e2e_steps / e2e_s, "unit": UNIT,
+         "h2d_bytes_per_step": n * d * 4 + n * 4, "d2h_bytes_per_step": C * 8,
+         "steps": e2e_steps,
+         "what": "host data loader: minibatch from pinned host memory each step, "
+                 "potential+variance read back each step"}
+
+  cpu_base = None
+  if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    cpu_base, _, _ = cpu_reference_run(args, args.cpu_seconds)
+
+  if rank == 0:
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
+        "steps": args.steps, "warmup": max(3, args.warmup),
+        "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": "C2: Bayesian logistic regression, pSGLD "
+                               "(alias.sgld rms_prop=True), chains sharded over GPUs",
+                   "chains_per_gpu": C, "features": d, "batch": n,
+                   "observations": N, "potential_path": path,
+                   "l2": "state (theta,v,grad = 50 MB/GPU) is reused every step by "
+                         "the algorithm itself; the roofline kernel is timed on "
+                         f"{R} rotating state sets ({R * 3 * C * d * 4 / 1e6:.0f} MB > L2)",
+                   "parallelism": f"chains x{world}"},
+        "clocks": clocks, "gpu_launches": int(launches),
+        "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu_base,
+    }
+    print(json.dumps(line), flush=True)
+  ctl.close()
+
+
+def main():
+  args = parse()
+  if args.impl == "reference":
+    run_reference(args)
+  else:
+    run_b200(args)
+
+
+if __name__ == "__main__":
+  main()

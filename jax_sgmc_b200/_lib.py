@@ -1,0 +1,131 @@
+"""ctypes binding of libsgmc_b200.so (the C ABI declared in include/sgmc_b200.h).
+
+The product path has no CPU fallback: if the shared library is missing or an
+entry point fails, an exception is raised.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_C", "libsgmc_b200.so")
+
+
+class SgmcError(RuntimeError):
+  """Raised when a libsgmc_b200 entry point returns a nonzero status."""
+
+
+class GlmSpec(C.Structure):
+  """``sgmc_glm_spec`` (include/sgmc_b200.h)."""
+  _fields_ = [("family", C.c_int32), ("d", C.c_int32), ("w_off", C.c_int32),
+              ("aux_off", C.c_int32), ("prior", C.c_int32),
+              ("prior_off", C.c_int32), ("prior_size", C.c_int32),
+              ("prior_scale", C.c_float), ("temperature", C.c_float)]
+
+
+_vp, _i64, _i32, _f32, _sz = C.c_void_p, C.c_int64, C.c_int32, C.c_float, C.c_size_t
+_int = C.c_int
+
+# name -> argtypes   (every function returns int status unless listed below)
+PROTOTYPES = {
+    "sgmc_device_count": [C.POINTER(_int)],
+    "sgmc_set_device": [_int],
+    "sgmc_device_info": [_int, C.POINTER(_int), C.POINTER(_int),
+                         C.POINTER(_int), C.POINTER(_sz)],
+    "sgmc_malloc": [C.POINTER(_vp), _sz],
+    "sgmc_free": [_vp],
+    "sgmc_host_alloc": [C.POINTER(_vp), _sz],
+    "sgmc_host_free": [_vp],
+    "sgmc_memcpy_h2d": [_vp, _vp, _sz, _vp],
+    "sgmc_memcpy_d2h": [_vp, _vp, _sz, _vp],
+    "sgmc_memcpy_d2d": [_vp, _vp, _sz, _vp],
+    "sgmc_memset": [_vp, _int, _sz, _vp],
+    "sgmc_stream_create": [C.POINTER(_vp)],
+    "sgmc_stream_destroy": [_vp],
+    "sgmc_stream_sync": [_vp],
+    "sgmc_device_sync": [],
+    "sgmc_event_create": [C.POINTER(_vp)],
+    "sgmc_event_destroy": [_vp],
+    "sgmc_event_record": [_vp, _vp],
+    "sgmc_event_sync": [_vp],
+    "sgmc_event_elapsed_ms": [_vp, _vp, C.POINTER(_f32)],
+    "sgmc_prng_split": [_vp, _vp, _vp, _i64, _int, _int],
+    "sgmc_random_bits": [_vp, _vp, _vp, _i64, _i64, _int],
+    "sgmc_uniform": [_vp, _vp, _vp, _i64, _i64, _f32, _f32, _int],
+    "sgmc_normal": [_vp, _vp, _vp, _i64, _i64, _int],
+    "sgmc_normal_like": [_vp, _vp, _vp, _i64, C.POINTER(_i64), _int, _int],
+    "sgmc_randint": [_vp, _vp, _vp, _i64, _i32, _i32, _int],
+    "sgmc_minibatch_draw": [_vp, _vp, _vp, _vp, _i64, _i64, _int],
+    "sgmc_gather_rows": [_vp, _vp, _vp, _vp, _i64, _i64],
+    "sgmc_synth_logistic_data": [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _int],
+    "sgmc_sgld_update": [_vp, _vp, _vp, _vp, _vp, _i64, C.POINTER(_i64), _int,
+                         _f32, _f32, _vp, _int],
+    "sgmc_sgld_rms_update": [_vp, _vp, _vp, _vp, _vp, _vp, _i64,
+                             C.POINTER(_i64), _int, _f32, _f32, _vp, _f32,
+                             _f32, _int],
+    "sgmc_sghmc_begin": [_vp, _vp, _vp, _vp, _vp, _i64, C.POINTER(_i64), _int,
+                         _f32, _vp, _int],
+    "sgmc_sghmc_step": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, C.POINTER(_i64),
+                        _int, _f32, _f32, _vp, _vp, _int, _int],
+    "sgmc_obabo_pass_a": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64,
+                          C.POINTER(_i64), _int, _f32, _f32, _f32, _vp, _int],
+    "sgmc_obabo_pass_b": [_vp, _vp, _vp, _vp, _vp, _i64, C.POINTER(_i64), _int,
+                          _f32, _f32, _f32, _vp, _int],
+    "sgmc_glm_potential_grad": [_vp, C.POINTER(GlmSpec), _vp, _i64, _i64, _vp,
+                                _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp,
+                                _vp, _sz, _int],
+    "sgmc_resgld_decide": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _f32, _f32, _vp,
+                           _vp, _vp, _i64, _int],
+    "sgmc_swap_rows": [_vp, _vp, _vp, _vp, _i64, _i64],
+    "sgmc_nccl_unique_id": [_vp],
+    "sgmc_nccl_init": [C.POINTER(_vp), _vp, _int, _int],
+    "sgmc_nccl_destroy": [_vp],
+    "sgmc_nccl_allgather": [_vp, _vp, _vp, _vp, _sz],
+    "sgmc_nccl_allreduce_sum_f32": [_vp, _vp, _vp, _vp, _sz],
+}
+# functions whose return value is NOT a status code
+SPECIAL = {
+    "sgmc_last_error": ([], C.c_char_p),
+    "sgmc_version": ([], _int),
+    "sgmc_launch_count": ([], C.c_ulonglong),
+    "sgmc_nccl_available": ([], _int),
+    "sgmc_glm_workspace_bytes": ([_i64, _i64, _i64, _int], _sz),
+}
+
+_lib = None
+
+
+def load() -> C.CDLL:
+  """Load the shared library (once).  Raises if it has not been built."""
+  global _lib
+  if _lib is not None:
+    return _lib
+  if not os.path.exists(LIB_PATH):
+    raise SgmcError(
+        f"{LIB_PATH} is missing: build it with `python -m jax_sgmc_b200.build` "
+        "(there is no CPU fallback)")
+  lib = C.CDLL(LIB_PATH)
+  for name, argtypes in PROTOTYPES.items():
+    fn = getattr(lib, name)
+    fn.argtypes = argtypes
+    fn.restype = _int
+  for name, (argtypes, restype) in SPECIAL.items():
+    fn = getattr(lib, name)
+    fn.argtypes = argtypes
+    fn.restype = restype
+  _lib = lib
+  return lib
+
+
+def call(name: str, *args):
+  """Call a status-returning entry point; raise SgmcError on failure."""
+  lib = load()
+  status = getattr(lib, name)(*args)
+  if status != 0:
+    msg = lib.sgmc_last_error().decode(errors="replace")
+    raise SgmcError(f"{name} failed (status {status}): {msg}")
+
+
+def exported_names():
+  return sorted(list(PROTOTYPES) + list(SPECIAL))

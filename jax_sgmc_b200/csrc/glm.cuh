@@ -1,0 +1,48 @@
+// Argument block shared by the GLM potential kernels (glm_simt.cu, glm_tc.cu).
+#pragma once
+#include "common.cuh"
+#include "glm_math.cuh"
+
+namespace sgmc {
+
+struct GlmArgs {
+  sgmc_glm_spec spec;
+  const float* theta;     // f32[C][P]
+  int64_t C, P;
+  const float* X;         // f32[N_total][d]
+  const float* y;         // f32[N_total]
+  const int32_t* idx;     // int32[n] or null (rows 0..n-1)
+  const float* mask;      // f32[n] or null
+  int64_t n, N;
+  float cot;              // (-N/n)/T
+  float* potential;       // f32[C]
+  float* variance;        // f32[C] or null
+  float* grad;            // f32[C][P] or null
+  float* R;               // f32[C][n] scratch: cot * d ell/dz
+  float* ell;             // f32[C][n]
+  float* tc_ws;           // extra scratch of the tensor-core path
+};
+
+// -(d prior / d theta_p) / T for flat parameter index p of chain c.
+__device__ __forceinline__ float prior_grad_term(const GlmArgs& a, int64_t c, int p) {
+  const sgmc_glm_spec& s = a.spec;
+  if (s.prior == kPriorGaussian) {
+    if (p >= s.prior_off && p < s.prior_off + s.prior_size) {
+      const float inv = 1.0f / (s.prior_scale * s.prior_scale);
+      // grad(prior) = -theta*inv  ->  g -= (-theta*inv)/T
+      return (a.theta[c * a.P + p] * inv) / s.temperature;
+    }
+  } else if (s.prior == kPriorInvSigma) {
+    if (p == s.prior_off)
+      return (1.0f / expf(a.theta[c * a.P + p])) / s.temperature;
+  }
+  return 0.0f;
+}
+
+int glm_finalize(cudaStream_t stream, const GlmArgs& a);
+int glm_simt(cudaStream_t stream, const GlmArgs& a);
+int glm_tc(cudaStream_t stream, const GlmArgs& a, int path);
+size_t glm_tc_workspace_bytes(int64_t n_chains, int64_t batch_size, int64_t d,
+                              int path);
+
+}  // namespace sgmc

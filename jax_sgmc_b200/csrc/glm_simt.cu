@@ -1,0 +1,275 @@
+// GLM stochastic potential + gradient, fp32 SIMT path (path 0) and the shared
+// "finalize" reduction used by every path.
+//
+// Replaces, for the recognised GLM families, potential.minibatch_potential
+// (jax_sgmc/potential.py:94-216) together with the reverse-mode gradient the
+// integrators take of it (jax_sgmc/integrator.py:166, :593, :792), batched over
+// chains that share one minibatch:
+//   pass 1  Z = Theta_w . X_b^T  -> per-observation ell and residual
+//           R = cot * d ell/dz, cot = (-N/n)/T (* mask)     [GEMM-shaped, NT]
+//   final   U = (-N mean(ell) - prior)/T, var(ell), aux-parameter gradients
+//   pass 2  G = R . X_b - grad(prior)/T                     [GEMM-shaped, NN]
+// The minibatch gather (data/core.py:642-660) is fused: rows are read through
+// idx.  This path is the precise fp32 fallback for arbitrary shapes (e.g. the
+// quickstart's d=4); the tensor-core path lives in glm_tc.cu.
+#include "glm.cuh"
+
+namespace sgmc {
+
+constexpr int TM = 64, TN = 64, TK = 16;
+
+template <bool NT, class Epi>
+__global__ void __launch_bounds__(256)
+k_sgemm(const float* __restrict__ A, int64_t lda, const float* __restrict__ B,
+        int64_t ldb, const int32_t* __restrict__ bidx, int M, int N, int K,
+        const Epi epi) {
+  __shared__ float As[TK][TM + 4];
+  __shared__ float Bs[TK][TN + 4];
+  const int tid = threadIdx.x;
+  const int m0 = blockIdx.y * TM, n0 = blockIdx.x * TN;
+  const int tx = tid & 15, ty = tid >> 4;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  for (int k0 = 0; k0 < K; k0 += TK) {
+    {
+      const int r = tid >> 2, kq = (tid & 3) * 4, m = m0 + r;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int k = k0 + kq + q;
+        As[kq + q][r] = (m < M && k < K) ? A[(int64_t)m * lda + k] : 0.f;
+      }
+    }
+    if (NT) {
+      const int r = tid >> 2, kq = (tid & 3) * 4, nn = n0 + r;
+      const int64_t row = nn < N ? (bidx ? (int64_t)bidx[nn] : nn) : 0;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int k = k0 + kq + q;
+        Bs[kq + q][r] = (nn < N && k < K) ? B[row * ldb + k] : 0.f;
+      }
+    } else {
+      const int kr = tid >> 4, nq = (tid & 15) * 4, k = k0 + kr;
+      const int64_t row = k < K ? (bidx ? (int64_t)bidx[k] : k) : 0;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int nn = n0 + nq + q;
+        Bs[kr][nq + q] = (k < K && nn < N) ? B[row * ldb + nn] : 0.f;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < TK; ++kk) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int nn = n0 + tx * 4 + j;
+      if (nn < N) epi(m, nn, acc[i][j]);
+    }
+  }
+}
+
+// pass 1 epilogue: z -> (ell, R)
+struct LinkEpi {
+  GlmArgs a;
+  __device__ void operator()(int c, int i, float z) const {
+    const float* th = a.theta + (int64_t)c * a.P;
+    GaussConst gc{1.f, 0.f};
+    if (a.spec.family == kFamilyGaussian) gc = gauss_const(th[a.spec.aux_off]);
+    else if (a.spec.aux_off >= 0) z += th[a.spec.aux_off];
+    const float y = a.y[a.idx ? a.idx[i] : i];
+    float ell, dz;
+    glm_link(a.spec.family, z, y, gc, ell, dz);
+    float cot = a.cot;
+    if (a.mask) cot *= a.mask[i];
+    a.R[(int64_t)c * a.n + i] = dz * cot;
+    a.ell[(int64_t)c * a.n + i] = ell;
+  }
+};
+
+// pass 2 epilogue: G -> grad (adds -grad(prior)/T)
+struct GradEpi {
+  GlmArgs a;
+  __device__ void operator()(int c, int j, float g) const {
+    const int64_t p = (int64_t)c * a.P + a.spec.w_off + j;
+    a.grad[p] = g + prior_grad_term(a, c, a.spec.w_off + j);
+  }
+};
+
+// One CTA per chain: U, var(ell), aux-parameter gradient (log_sigma / bias).
+__global__ void __launch_bounds__(256) k_glm_finalize(const GlmArgs a) {
+  __shared__ float red[2][8];
+  const int c = blockIdx.x;
+  const float* ell = a.ell + (int64_t)c * a.n;
+  const float* R = a.R + (int64_t)c * a.n;
+  const float* th = a.theta + (int64_t)c * a.P;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  auto block_sum2 = [&](float x, float y2, float& ox, float& oy) {
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) {
+      x += __shfl_xor_sync(0xffffffffu, x, s);
+      y2 += __shfl_xor_sync(0xffffffffu, y2, s);
+    }
+    __syncthreads();
+    if (lane == 0) { red[0][warp] = x; red[1][warp] = y2; }
+    __syncthreads();
+    ox = 0.f; oy = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) { ox += red[0][w]; oy += red[1][w]; }
+  };
+
+  // sum(ell) [masked sum when mask given], aux gradient
+  GaussConst gc{1.f, 0.f};
+  const bool gauss = a.spec.family == kFamilyGaussian;
+  if (gauss) gc = gauss_const(th[a.spec.aux_off]);
+  float s_ell = 0.f, s_aux = 0.f;
+  for (int i = tid; i < a.n; i += 256) {
+    const float l = ell[i];
+    const float m = a.mask ? a.mask[i] : 1.0f;
+    s_ell += l * m;
+    if (gauss) {
+      // d ell / d log_sigma = r^2/s2 - 1 = (-2 ell - ln) - 1
+      s_aux += (a.cot * m) * ((-2.0f * l - gc.ln) - 1.0f);
+    } else if (a.spec.aux_off >= 0) {
+      s_aux += R[i];
+    }
+  }
+  float sum_ell, sum_aux;
+  block_sum2(s_ell, s_aux, sum_ell, sum_aux);
+  const float mean = sum_ell / (float)a.n;
+
+  // population variance of ell (integrator.py:880: jnp.var), two-pass
+  float s_var = 0.f, s_prior = 0.f;
+  {
+    float plain = 0.f;
+    if (a.mask) {   // variance is over the unmasked likelihoods
+      for (int i = tid; i < a.n; i += 256) plain += ell[i];
+    }
+    float psum, dummy;
+    if (a.mask) block_sum2(plain, 0.f, psum, dummy); else psum = sum_ell;
+    const float mu = psum / (float)a.n;
+    for (int i = tid; i < a.n; i += 256) {
+      const float dv = ell[i] - mu;
+      s_var += dv * dv;
+    }
+    if (a.spec.prior == kPriorGaussian) {
+      for (int p = a.spec.prior_off + tid; p < a.spec.prior_off + a.spec.prior_size;
+           p += 256)
+        s_prior += th[p] * th[p];
+    }
+  }
+  float sum_var, sum_prior;
+  block_sum2(s_var, s_prior, sum_var, sum_prior);
+
+  if (tid == 0) {
+    float L;
+    if (a.mask) L = (-(float)a.N / (float)a.n) * sum_ell;      // potential.py:185
+    else L = -(float)a.N * mean;                               // potential.py:183
+    float prior = 0.f;
+    if (a.spec.prior == kPriorGaussian)
+      prior = -0.5f * (1.0f / (a.spec.prior_scale * a.spec.prior_scale)) * sum_prior;
+    else if (a.spec.prior == kPriorInvSigma)
+      prior = 1.0f / expf(th[a.spec.prior_off]);
+    a.potential[c] = (L - prior) / a.spec.temperature;         // potential.py:210
+    if (a.variance) a.variance[c] = sum_var / (float)a.n;
+    if (a.spec.aux_off >= 0 && a.grad)
+      a.grad[(int64_t)c * a.P + a.spec.aux_off] =
+          sum_aux + prior_grad_term(a, c, a.spec.aux_off);
+  }
+}
+
+int glm_finalize(cudaStream_t stream, const GlmArgs& a) {
+  k_glm_finalize<<<(unsigned)a.C, 256, 0, stream>>>(a);
+  return post_launch("k_glm_finalize");
+}
+
+int glm_simt(cudaStream_t stream, const GlmArgs& a) {
+  const int C = (int)a.C, n = (int)a.n, d = a.spec.d;
+  {
+    dim3 grid((n + TN - 1) / TN, (C + TM - 1) / TM);
+    k_sgemm<true, LinkEpi><<<grid, 256, 0, stream>>>(
+        a.theta + a.spec.w_off, a.P, a.X, d, a.idx, C, n, d, LinkEpi{a});
+    if (post_launch("k_sgemm<link>")) return 1;
+  }
+  if (glm_finalize(stream, a)) return 1;
+  if (a.grad) {
+    dim3 grid((d + TN - 1) / TN, (C + TM - 1) / TM);
+    k_sgemm<false, GradEpi><<<grid, 256, 0, stream>>>(
+        a.R, a.n, a.X, d, a.idx, C, d, n, GradEpi{a});
+    if (post_launch("k_sgemm<grad>")) return 1;
+  }
+  return 0;
+}
+
+}  // namespace sgmc
+
+using namespace sgmc;
+
+extern "C" {
+
+size_t sgmc_glm_workspace_bytes(int64_t n_chains, int64_t batch_size, int64_t d,
+                                int path) {
+  size_t base = (size_t)n_chains * batch_size * sizeof(float) * 2;  // R + ell
+  if (path != 0) base += glm_tc_workspace_bytes(n_chains, batch_size, d, path);
+  return base + 256;
+}
+
+int sgmc_glm_potential_grad(void* stream, const sgmc_glm_spec* spec,
+                            const float* theta, int64_t n_chains, int64_t P,
+                            const float* X, const float* y, const int32_t* idx,
+                            const float* mask, int64_t batch_size,
+                            int64_t observation_count, float* potential,
+                            float* variance, float* grad, float* ell,
+                            void* workspace, size_t workspace_bytes, int path) {
+  SGMC_REQUIRE(spec && theta && X && y && potential, "null argument");
+  SGMC_REQUIRE(spec->family == kFamilyGaussian || spec->family == kFamilyLogistic,
+               "unknown GLM family %d", spec->family);
+  SGMC_REQUIRE(spec->family != kFamilyGaussian || spec->aux_off >= 0,
+               "gaussian family needs aux_off (log_sigma)");
+  SGMC_REQUIRE(spec->d > 0 && spec->w_off >= 0 && spec->w_off + spec->d <= P,
+               "weight range outside the sample");
+  SGMC_REQUIRE(P == spec->d + (spec->aux_off >= 0 ? 1 : 0),
+               "sample size %lld != d + aux", (long long)P);
+  SGMC_REQUIRE(n_chains > 0 && batch_size > 0 && n_chains < (1ll << 31) &&
+               batch_size < (1ll << 31), "bad sizes");
+  SGMC_REQUIRE(workspace_bytes >=
+               sgmc_glm_workspace_bytes(n_chains, batch_size, spec->d, path),
+               "workspace too small");
+  SGMC_REQUIRE(path >= 0 && path <= 2, "unknown path %d", path);
+  GlmArgs a;
+  a.spec = *spec;
+  a.theta = theta; a.C = n_chains; a.P = P;
+  a.X = X; a.y = y; a.idx = idx; a.mask = mask;
+  a.n = batch_size; a.N = observation_count;
+  a.potential = potential; a.variance = variance; a.grad = grad;
+  float* ws = reinterpret_cast<float*>(
+      (reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255);
+  a.R = ws;
+  a.ell = ell ? ell : ws + (size_t)n_chains * batch_size;
+  a.tc_ws = ws + 2 * (size_t)n_chains * batch_size;
+  // cotangent of every ell_i: (1/T) * (-N) / n    (potential.py:183,210)
+  a.cot = (-(float)observation_count / (float)batch_size) / spec->temperature;
+  if (path == 0) return glm_simt((cudaStream_t)stream, a);
+  return glm_tc((cudaStream_t)stream, a, path);
+}
+
+}  // extern "C"

@@ -1,0 +1,90 @@
+// reSGLD swap step of solver.parallel_tempering.update
+// (jax_sgmc/solver.py:273-291), batched over S
+// independent two-temperature systems.
+#include "common.cuh"
+#include "rng.cuh"
+
+namespace sgmc {
+
+__global__ void k_resgld_decide(const float* __restrict__ U_n,
+                                const float* __restrict__ U_h,
+                                const float* __restrict__ var_n,
+                                float* __restrict__ ssq,
+                                const float* __restrict__ F, float eta,
+                                float temps, const uint32_t* __restrict__ keys_in,
+                                uint32_t* __restrict__ keys_out,
+                                int32_t* __restrict__ exchange, int64_t S,
+                                int layout) {
+  const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= S) return;
+  // ssq' = ((1-eta)*ssq) + (eta*var_n)                      solver.py:275-276
+  const float q = __fadd_rn(__fmul_rn(__fadd_rn(1.0f, -eta), ssq[s]),
+                            __fmul_rn(eta, var_n[s]));
+  ssq[s] = q;
+  // log_s = temps * (U_n - U_h - temps*ssq'/F)              solver.py:280-281
+  const float corr = __fdiv_rn(__fmul_rn(temps, q), F[s]);
+  const float log_s =
+      __fmul_rn(temps, __fadd_rn(__fadd_rn(U_n[s], -U_h[s]), -corr));
+  Key k{keys_in[2 * s], keys_in[2 * s + 1]}, nk, sub;
+  split2(k, layout, nk, sub);                               // solver.py:283
+  keys_out[2 * s] = nk.k0;
+  keys_out[2 * s + 1] = nk.k1;
+  const uint32_t w = random_word(sub, 0, 1, layout);        // uniform(split), shape ()
+  const float u = bits_to_uniform(w, 0.0f, 1.0f);
+  const float log_u = log_libdevice(u);                     // solver.py:284
+  // lax.cond(log_u < log_s, keep, swap): exchange iff NOT (log_u < log_s)
+  exchange[s] = (log_u < log_s) ? 0 : 1;                    // solver.py:287-291
+}
+
+__global__ void k_swap_rows(uint32_t* __restrict__ a, uint32_t* __restrict__ b,
+                            const int32_t* __restrict__ exchange,
+                            int64_t n_rows, int64_t row_words) {
+  const int64_t row = blockIdx.y;
+  if (row >= n_rows || exchange[row] == 0) return;
+  uint32_t* pa = a + row * row_words;
+  uint32_t* pb = b + row * row_words;
+  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < row_words;
+       j += (int64_t)gridDim.x * blockDim.x) {
+    const uint32_t t = pa[j];
+    pa[j] = pb[j];
+    pb[j] = t;
+  }
+}
+
+}  // namespace sgmc
+
+using namespace sgmc;
+
+extern "C" {
+
+int sgmc_resgld_decide(void* stream, const float* U_normal, const float* U_hot,
+                       const float* var_normal, float* ssq, const float* F,
+                       int64_t step, float T_normal, float T_hot,
+                       const uint32_t* keys_in, uint32_t* keys_out,
+                       int32_t* exchange, int64_t n_systems, int prng_layout) {
+  SGMC_REQUIRE(keys_in != keys_out, "keys_out must not alias keys_in");
+  SGMC_REQUIRE(step >= 1, "step must be >= 1 (already incremented)");
+  if (n_systems == 0) return 0;
+  const float eta = 1.0f / (float)step;                     // sa_schedule, :221
+  const float temps = 1.0f / T_normal - 1.0f / T_hot;       // :279
+  k_resgld_decide<<<(unsigned)((n_systems + 127) / 128), 128, 0,
+                    (cudaStream_t)stream>>>(
+      U_normal, U_hot, var_normal, ssq, F, eta, temps, keys_in, keys_out,
+      exchange, n_systems, prng_layout);
+  return post_launch("sgmc_resgld_decide");
+}
+
+int sgmc_swap_rows(void* stream, void* a, void* b, const int32_t* exchange,
+                   int64_t n_rows, int64_t row_bytes) {
+  SGMC_REQUIRE(row_bytes % 4 == 0, "row_bytes must be a multiple of 4");
+  if (n_rows == 0 || row_bytes == 0) return 0;
+  SGMC_REQUIRE(n_rows <= 65535, "too many rows for one launch");
+  const int64_t words = row_bytes / 4;
+  unsigned gx = (unsigned)((words + 255) / 256);
+  if (gx > 64) gx = 64;
+  k_swap_rows<<<dim3(gx, (unsigned)n_rows), 256, 0, (cudaStream_t)stream>>>(
+      (uint32_t*)a, (uint32_t*)b, exchange, n_rows, words);
+  return post_launch("sgmc_swap_rows");
+}
+
+}  // extern "C"

@@ -1,0 +1,557 @@
+// Fused integrator / preconditioner updates with in-kernel jax.random noise.
+//
+//   sgmc_sgld_update, sgmc_sgld_rms_update   integrator.py:860-922,
+//                                            adaption.py:254-291
+//   sgmc_sghmc_begin, sgmc_sghmc_step        integrator.py:603-666, :716-757
+//   sgmc_obabo_pass_a, sgmc_obabo_pass_b     integrator.py:177-273
+//   sgmc_normal_like                         integrator.py:119-135
+//
+// All are instances of k_noise_pass (noise_pass.cuh).  The elementwise
+// arithmetic follows SURVEY.md Appendix A operation by operation with explicit
+// round-to-nearest intrinsics (no FMA contraction), so that given the same
+// gradient the result equals the NumPy oracle bit for bit.
+// Roofline: HBM.  Algorithmic bytes per parameter: SGLD 12, pSGLD 20,
+// SGHMC step 20, OBABO pass A 20 + pass B 12.
+#include "noise_pass.cuh"
+
+#include <cmath>
+
+namespace sgmc {
+
+int build_leaf_table(LeafTable* t, const int64_t* leaf_sizes, int n_leaves,
+                     int64_t n_chains, bool ptrs_aligned16) {
+  SGMC_REQUIRE(n_leaves >= 1 && n_leaves <= SGMC_MAX_LEAVES,
+               "n_leaves=%d outside [1,%d]", n_leaves, SGMC_MAX_LEAVES);
+  SGMC_REQUIRE(n_chains >= 0, "n_chains < 0");
+  int64_t off = 0, g = 0;
+  for (int l = 0; l < n_leaves; ++l) {
+    SGMC_REQUIRE(leaf_sizes[l] >= 0 && leaf_sizes[l] < (1ll << 31),
+                 "leaf %d size %lld unsupported", l, (long long)leaf_sizes[l]);
+    off += leaf_sizes[l];
+  }
+  SGMC_REQUIRE(off < (1ll << 31), "flat sample too large (%lld)", (long long)off);
+  const int64_t P = off;
+  off = 0;
+  for (int l = 0; l < n_leaves; ++l) {
+    const int64_t size = leaf_sizes[l], half = (size + 1) / 2;
+    t->off[l] = (uint32_t)off;
+    t->size[l] = (uint32_t)size;
+    t->gstart[l] = (uint32_t)g;
+    t->vec_ok[l] = (ptrs_aligned16 && P % 4 == 0 && off % 4 == 0 &&
+                    half % 4 == 0 && size % 2 == 0) ? 1 : 0;
+    g += (half + 3) / 4;
+    off += size;
+  }
+  t->gstart[n_leaves] = (uint32_t)g;
+  t->n_leaves = n_leaves;
+  t->P = (uint32_t)P;
+  t->groups = (uint32_t)g;
+  t->tiles_per_chain = (uint32_t)((g + 31) / 32);
+  return 0;
+}
+
+int plan_noise_launch(const LeafTable& t, int64_t n_chains, const void* kernel,
+                      NoiseLaunch* out) {
+  out->tiles_total = n_chains * (int64_t)t.tiles_per_chain;
+  out->grid = 0;
+  out->smem = 0;
+  if (out->tiles_total == 0) return 0;
+  // persistent grid: a multiple of the SM count, bounded by the work
+  const int sms = sm_count();
+  int per_sm = 8;
+  int64_t grid = (int64_t)sms * per_sm;
+  if (grid > out->tiles_total) grid = out->tiles_total;
+  for (;;) {
+    const int64_t tiles_per_cta = (out->tiles_total + grid - 1) / grid;
+    const int64_t chains = tiles_per_cta / t.tiles_per_chain + 2;
+    const size_t smem = (size_t)chains * t.n_leaves * sizeof(Key);
+    if (smem <= 40 * 1024 || grid >= out->tiles_total) {
+      SGMC_REQUIRE(smem <= 40 * 1024, "key cache too large (%zu B)", smem);
+      out->smem = smem;
+      out->max_chains_per_cta = (int)chains;
+      break;
+    }
+    grid = grid * 2 > out->tiles_total ? out->tiles_total : grid * 2;
+  }
+  out->grid = (int)grid;
+  (void)kernel;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ float4 ld4(const float* p, int64_t i) {
+  return *reinterpret_cast<const float4*>(p + i);
+}
+__device__ __forceinline__ void st4(float* p, int64_t i, float4 v) {
+  *reinterpret_cast<float4*>(p + i) = v;
+}
+#define SGMC_F4_MAP(dst, expr)                          \
+  {                                                     \
+    float4 _o;                                          \
+    { const int k = 0; _o.x = (expr); }                 \
+    { const int k = 1; _o.y = (expr); }                 \
+    { const int k = 2; _o.z = (expr); }                 \
+    { const int k = 3; _o.w = (expr); }                 \
+    dst = _o;                                           \
+  }
+__device__ __forceinline__ float f4get(const float4& v, int k) {
+  return k == 0 ? v.x : (k == 1 ? v.y : (k == 2 ? v.z : v.w));
+}
+
+// ---- random_tree only -----------------------------------------------------
+struct NormalLikeOp {
+  float* out;
+  static constexpr bool kReduce = false;
+  struct Regs {};
+  __device__ void load_vec(Regs&, int64_t, int64_t) const {}
+  __device__ float apply_vec(Regs&, const float nA[4], const float nB[4],
+                             int64_t iA, int64_t iB, int64_t, uint32_t,
+                             uint32_t) const {
+    st4(out, iA, make_float4(nA[0], nA[1], nA[2], nA[3]));
+    st4(out, iB, make_float4(nB[0], nB[1], nB[2], nB[3]));
+    return 0.f;
+  }
+  __device__ float apply_one(int64_t i, float n, int64_t, uint32_t) const {
+    out[i] = n;
+    return 0.f;
+  }
+  __device__ void reduce(int64_t, float) const {}
+};
+
+// ---- SGLD / pSGLD -----------------------------------------------------------
+// integrator.py:882-912; adaption.py:270-272, :289-291.
+template <bool RMS>
+struct SgldOp {
+  float* theta;
+  float* v;
+  const float* grad;
+  const float* temp_per_chain;
+  float eps, neg_eps, noise_scale, alpha, one_m_alpha, lmbd;
+  static constexpr bool kReduce = false;
+  struct Regs {
+    float4 tA, tB, gA, gB, vA, vB;
+  };
+  __device__ __forceinline__ float scale_for(int64_t c) const {
+    if (temp_per_chain == nullptr) return noise_scale;
+    return __fsqrt_rn(__fmul_rn(__fmul_rn(2.0f, temp_per_chain[c]), eps));
+  }
+  __device__ __forceinline__ float one(float t, float g, float& vv, float xi,
+                                       float ns) const {
+    const float sg = __fmul_rn(neg_eps, g);
+    const float sn = __fmul_rn(ns, xi);
+    float delta;
+    if (RMS) {
+      vv = __fadd_rn(__fmul_rn(alpha, vv),
+                     __fmul_rn(one_m_alpha, __fmul_rn(g, g)));
+      const float G = __frcp_rn(__fadd_rn(lmbd, __fsqrt_rn(vv)));
+      const float S = __fsqrt_rn(G);
+      delta = __fadd_rn(__fadd_rn(0.0f, __fmul_rn(G, sg)), __fmul_rn(S, sn));
+    } else {
+      delta = __fadd_rn(sg, sn);
+    }
+    return __fadd_rn(t, delta);
+  }
+  __device__ void load_vec(Regs& r, int64_t iA, int64_t iB) const {
+    r.tA = ld4(theta, iA);
+    r.tB = ld4(theta, iB);
+    r.gA = ld4(grad, iA);
+    r.gB = ld4(grad, iB);
+    if (RMS) {
+      r.vA = ld4(v, iA);
+      r.vB = ld4(v, iB);
+    }
+  }
+  __device__ float apply_vec(Regs& r, const float nA[4], const float nB[4],
+                             int64_t iA, int64_t iB, int64_t c, uint32_t,
+                             uint32_t) const {
+    const float ns = scale_for(c);
+    float va[4] = {r.vA.x, r.vA.y, r.vA.z, r.vA.w};
+    float vb[4] = {r.vB.x, r.vB.y, r.vB.z, r.vB.w};
+    float4 oA, oB;
+    SGMC_F4_MAP(oA, one(f4get(r.tA, k), f4get(r.gA, k), va[k], nA[k], ns));
+    SGMC_F4_MAP(oB, one(f4get(r.tB, k), f4get(r.gB, k), vb[k], nB[k], ns));
+    st4(theta, iA, oA);
+    st4(theta, iB, oB);
+    if (RMS) {
+      st4(v, iA, make_float4(va[0], va[1], va[2], va[3]));
+      st4(v, iB, make_float4(vb[0], vb[1], vb[2], vb[3]));
+    }
+    return 0.f;
+  }
+  __device__ float apply_one(int64_t i, float n, int64_t c, uint32_t) const {
+    float vv = RMS ? v[i] : 0.f;
+    theta[i] = one(theta[i], grad[i], vv, n, scale_for(c));
+    if (RMS) v[i] = vv;
+    return 0.f;
+  }
+  __device__ void reduce(int64_t, float) const {}
+};
+
+// ---- SGHMC ------------------------------------------------------------------
+// begin: p = sqrt(m) * xi (integrator.py:737-738); theta += eps*(inv_m*p) (:610-612)
+struct SghmcBeginOp {
+  float* theta;
+  float* mom;
+  const float* mass;   // f32[P] or null
+  float eps;
+  static constexpr bool kReduce = false;
+  struct Regs {
+    float4 tA, tB;
+  };
+  __device__ __forceinline__ float one(float t, float xi, uint32_t e, float& p) const {
+    float inv_m = 1.0f, sqrt_m = 1.0f;
+    if (mass) {
+      const float m = mass[e];
+      inv_m = __frcp_rn(m);
+      sqrt_m = __fsqrt_rn(m);
+    }
+    p = __fmul_rn(sqrt_m, xi);
+    return __fadd_rn(t, __fmul_rn(eps, __fmul_rn(inv_m, p)));
+  }
+  __device__ void load_vec(Regs& r, int64_t iA, int64_t iB) const {
+    r.tA = ld4(theta, iA);
+    r.tB = ld4(theta, iB);
+  }
+  __device__ float apply_vec(Regs& r, const float nA[4], const float nB[4],
+                             int64_t iA, int64_t iB, int64_t, uint32_t eA,
+                             uint32_t eB) const {
+    float pa[4], pb[4];
+    float4 oA, oB;
+    SGMC_F4_MAP(oA, one(f4get(r.tA, k), nA[k], eA + k, pa[k]));
+    SGMC_F4_MAP(oB, one(f4get(r.tB, k), nB[k], eB + k, pb[k]));
+    st4(theta, iA, oA);
+    st4(theta, iB, oB);
+    st4(mom, iA, make_float4(pa[0], pa[1], pa[2], pa[3]));
+    st4(mom, iB, make_float4(pb[0], pb[1], pb[2], pb[3]));
+    return 0.f;
+  }
+  __device__ float apply_one(int64_t i, float n, int64_t, uint32_t e) const {
+    float p;
+    theta[i] = one(theta[i], n, e, p);
+    mom[i] = p;
+    return 0.f;
+  }
+  __device__ void reduce(int64_t, float) const {}
+};
+
+// step: integrator.py:616-655 (+ next position update :610-612 unless last)
+struct SghmcStepOp {
+  float* theta;
+  float* mom;
+  const float* grad;
+  const float* friction;  // f32[P] or null -> friction_scalar
+  const float* mass;      // f32[P] or null
+  float eps, neg_eps, noise_scale, friction_scalar;
+  int last;
+  static constexpr bool kReduce = false;
+  struct Regs {
+    float4 tA, tB, pA, pB, gA, gB;
+  };
+  __device__ __forceinline__ float one(float t, float& p, float g, float xi,
+                                       uint32_t e) const {
+    const float C = friction ? friction[e] : friction_scalar;
+    const float inv_m = mass ? __frcp_rn(mass[e]) : 1.0f;
+    const float m = __fmul_rn(inv_m, p);
+    const float p1 = __fadd_rn(p, __fmul_rn(__fmul_rn(neg_eps, C), m));
+    const float p2 = __fadd_rn(p1, __fmul_rn(neg_eps, g));
+    const float p3 = __fadd_rn(p2, __fmul_rn(C, __fmul_rn(noise_scale, xi)));
+    p = p3;
+    if (last) return t;
+    return __fadd_rn(t, __fmul_rn(eps, __fmul_rn(inv_m, p3)));
+  }
+  __device__ void load_vec(Regs& r, int64_t iA, int64_t iB) const {
+    if (!last) {
+      r.tA = ld4(theta, iA);
+      r.tB = ld4(theta, iB);
+    }
+    r.pA = ld4(mom, iA);
+    r.pB = ld4(mom, iB);
+    r.gA = ld4(grad, iA);
+    r.gB = ld4(grad, iB);
+  }
+  __device__ float apply_vec(Regs& r, const float nA[4], const float nB[4],
+                             int64_t iA, int64_t iB, int64_t, uint32_t eA,
+                             uint32_t eB) const {
+    float pa[4] = {r.pA.x, r.pA.y, r.pA.z, r.pA.w};
+    float pb[4] = {r.pB.x, r.pB.y, r.pB.z, r.pB.w};
+    float4 oA, oB;
+    SGMC_F4_MAP(oA, one(f4get(r.tA, k), pa[k], f4get(r.gA, k), nA[k], eA + k));
+    SGMC_F4_MAP(oB, one(f4get(r.tB, k), pb[k], f4get(r.gB, k), nB[k], eB + k));
+    if (!last) {
+      st4(theta, iA, oA);
+      st4(theta, iB, oB);
+    }
+    st4(mom, iA, make_float4(pa[0], pa[1], pa[2], pa[3]));
+    st4(mom, iB, make_float4(pb[0], pb[1], pb[2], pb[3]));
+    return 0.f;
+  }
+  __device__ float apply_one(int64_t i, float n, int64_t, uint32_t e) const {
+    float p = mom[i];
+    const float t = one(last ? 0.f : theta[i], p, grad[i], n, e);
+    if (!last) theta[i] = t;
+    mom[i] = p;
+    return 0.f;
+  }
+  __device__ void reduce(int64_t, float) const {}
+};
+
+// ---- OBABO --------------------------------------------------------------------
+// O(p, xi) = (sqrt(a) p) + (sqrt((1-a)T) * (sqrt(m) xi))   integrator.py:192-200
+struct ObaboAOp {   // integrator.py:210-240
+  float* theta;
+  float* mom;
+  const float* grad;
+  float* ke;           // f32[C] accumulator (kinetic_energy_start)
+  const float* mass;
+  float eps, sqrt_a, o_noise, neg_half_eps;
+  static constexpr bool kReduce = true;
+  struct Regs {
+    float4 tA, tB, pA, pB, gA, gB;
+  };
+  __device__ __forceinline__ float one(float& t, float& p, float g, float xi,
+                                       uint32_t e) const {
+    float inv_m = 1.0f, sqrt_m = 1.0f;
+    if (mass) {
+      const float m = mass[e];
+      inv_m = __frcp_rn(m);
+      sqrt_m = __fsqrt_rn(m);
+    }
+    const float p1 = __fadd_rn(__fmul_rn(sqrt_a, p),
+                               __fmul_rn(o_noise, __fmul_rn(sqrt_m, xi)));
+    const float ke1 = __fmul_rn(p1, __fmul_rn(inv_m, p1));
+    const float p2 = __fadd_rn(__fmul_rn(neg_half_eps, g), p1);
+    t = __fadd_rn(t, __fmul_rn(eps, __fmul_rn(inv_m, p2)));
+    p = p2;
+    return ke1;
+  }
+  __device__ void load_vec(Regs& r, int64_t iA, int64_t iB) const {
+    r.tA = ld4(theta, iA); r.tB = ld4(theta, iB);
+    r.pA = ld4(mom, iA);   r.pB = ld4(mom, iB);
+    r.gA = ld4(grad, iA);  r.gB = ld4(grad, iB);
+  }
+  __device__ float apply_vec(Regs& r, const float nA[4], const float nB[4],
+                             int64_t iA, int64_t iB, int64_t, uint32_t eA,
+                             uint32_t eB) const {
+    float ta[4] = {r.tA.x, r.tA.y, r.tA.z, r.tA.w};
+    float tb[4] = {r.tB.x, r.tB.y, r.tB.z, r.tB.w};
+    float pa[4] = {r.pA.x, r.pA.y, r.pA.z, r.pA.w};
+    float pb[4] = {r.pB.x, r.pB.y, r.pB.z, r.pB.w};
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      s += one(ta[k], pa[k], f4get(r.gA, k), nA[k], eA + k);
+      s += one(tb[k], pb[k], f4get(r.gB, k), nB[k], eB + k);
+    }
+    st4(theta, iA, make_float4(ta[0], ta[1], ta[2], ta[3]));
+    st4(theta, iB, make_float4(tb[0], tb[1], tb[2], tb[3]));
+    st4(mom, iA, make_float4(pa[0], pa[1], pa[2], pa[3]));
+    st4(mom, iB, make_float4(pb[0], pb[1], pb[2], pb[3]));
+    return s;
+  }
+  __device__ float apply_one(int64_t i, float n, int64_t, uint32_t e) const {
+    float t = theta[i], p = mom[i];
+    const float s = one(t, p, grad[i], n, e);
+    theta[i] = t;
+    mom[i] = p;
+    return s;
+  }
+  __device__ void reduce(int64_t c, float s) const {
+    atomicAdd(&ke[c], 0.5f * s);
+  }
+};
+
+struct ObaboBOp {   // integrator.py:248-261
+  float* mom;
+  const float* grad;
+  float* ke;           // kinetic_energy_end
+  const float* mass;
+  float sqrt_a, o_noise, neg_half_eps;
+  static constexpr bool kReduce = true;
+  struct Regs {
+    float4 pA, pB, gA, gB;
+  };
+  __device__ __forceinline__ float one(float& p, float g, float xi, uint32_t e) const {
+    float inv_m = 1.0f, sqrt_m = 1.0f;
+    if (mass) {
+      const float m = mass[e];
+      inv_m = __frcp_rn(m);
+      sqrt_m = __fsqrt_rn(m);
+    }
+    const float p3 = __fadd_rn(__fmul_rn(neg_half_eps, g), p);
+    const float ke3 = __fmul_rn(p3, __fmul_rn(inv_m, p3));
+    p = __fadd_rn(__fmul_rn(sqrt_a, p3),
+                  __fmul_rn(o_noise, __fmul_rn(sqrt_m, xi)));
+    return ke3;
+  }
+  __device__ void load_vec(Regs& r, int64_t iA, int64_t iB) const {
+    r.pA = ld4(mom, iA);  r.pB = ld4(mom, iB);
+    r.gA = ld4(grad, iA); r.gB = ld4(grad, iB);
+  }
+  __device__ float apply_vec(Regs& r, const float nA[4], const float nB[4],
+                             int64_t iA, int64_t iB, int64_t, uint32_t eA,
+                             uint32_t eB) const {
+    float pa[4] = {r.pA.x, r.pA.y, r.pA.z, r.pA.w};
+    float pb[4] = {r.pB.x, r.pB.y, r.pB.z, r.pB.w};
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      s += one(pa[k], f4get(r.gA, k), nA[k], eA + k);
+      s += one(pb[k], f4get(r.gB, k), nB[k], eB + k);
+    }
+    st4(mom, iA, make_float4(pa[0], pa[1], pa[2], pa[3]));
+    st4(mom, iB, make_float4(pb[0], pb[1], pb[2], pb[3]));
+    return s;
+  }
+  __device__ float apply_one(int64_t i, float n, int64_t, uint32_t e) const {
+    float p = mom[i];
+    const float s = one(p, grad[i], n, e);
+    mom[i] = p;
+    return s;
+  }
+  __device__ void reduce(int64_t c, float s) const {
+    atomicAdd(&ke[c], 0.5f * s);
+  }
+};
+
+static bool aligned16(std::initializer_list<const void*> ps) {
+  for (const void* p : ps)
+    if (p && (reinterpret_cast<uintptr_t>(p) & 15u)) return false;
+  return true;
+}
+
+}  // namespace sgmc
+
+using namespace sgmc;
+
+extern "C" {
+
+int sgmc_normal_like(void* stream, const uint32_t* keys, float* noise,
+                     int64_t n_chains, const int64_t* leaf_sizes, int n_leaves,
+                     int prng_layout) {
+  LeafTable tab;
+  if (int e = build_leaf_table(&tab, leaf_sizes, n_leaves, n_chains,
+                               aligned16({noise}))) return e;
+  NormalLikeOp op{noise};
+  return launch_noise_pass((cudaStream_t)stream, tab, keys, nullptr, n_chains,
+                           kKeyDirect, prng_layout, op, "sgmc_normal_like");
+}
+
+static int sgld_common(void* stream, float* theta, float* v, const float* grad,
+                       const uint32_t* keys_in, uint32_t* keys_out,
+                       int64_t n_chains, const int64_t* leaf_sizes,
+                       int n_leaves, float step_size, float temperature,
+                       const float* temp_per_chain, float alpha, float lmbd,
+                       int prng_layout, bool rms) {
+  SGMC_REQUIRE(keys_in != keys_out, "keys_out must not alias keys_in");
+  LeafTable tab;
+  if (int e = build_leaf_table(&tab, leaf_sizes, n_leaves, n_chains,
+                               aligned16({theta, v, grad}))) return e;
+  // integrator.py:882-884: (-eps), sqrt(2*T*eps) in f32
+  const float eps = step_size;
+  const float ns = sqrtf((2.0f * temperature) * eps);
+  if (rms) {
+    SgldOp<true> op{theta, v, grad, temp_per_chain, eps, -eps, ns,
+                    alpha, 1.0f - alpha, lmbd};
+    return launch_noise_pass((cudaStream_t)stream, tab, keys_in, keys_out,
+                             n_chains, kKeySplit2, prng_layout, op,
+                             "sgmc_sgld_rms_update");
+  }
+  SgldOp<false> op{theta, nullptr, grad, temp_per_chain, eps, -eps, ns,
+                   0.f, 0.f, 0.f};
+  return launch_noise_pass((cudaStream_t)stream, tab, keys_in, keys_out,
+                           n_chains, kKeySplit2, prng_layout, op,
+                           "sgmc_sgld_update");
+}
+
+int sgmc_sgld_update(void* stream, float* theta, const float* grad,
+                     const uint32_t* keys_in, uint32_t* keys_out,
+                     int64_t n_chains, const int64_t* leaf_sizes, int n_leaves,
+                     float step_size, float temperature,
+                     const float* temp_per_chain, int prng_layout) {
+  return sgld_common(stream, theta, nullptr, grad, keys_in, keys_out, n_chains,
+                     leaf_sizes, n_leaves, step_size, temperature,
+                     temp_per_chain, 0.f, 0.f, prng_layout, false);
+}
+
+int sgmc_sgld_rms_update(void* stream, float* theta, float* v,
+                         const float* grad, const uint32_t* keys_in,
+                         uint32_t* keys_out, int64_t n_chains,
+                         const int64_t* leaf_sizes, int n_leaves,
+                         float step_size, float temperature,
+                         const float* temp_per_chain, float alpha, float lmbd,
+                         int prng_layout) {
+  return sgld_common(stream, theta, v, grad, keys_in, keys_out, n_chains,
+                     leaf_sizes, n_leaves, step_size, temperature,
+                     temp_per_chain, alpha, lmbd, prng_layout, true);
+}
+
+int sgmc_sghmc_begin(void* stream, float* theta, float* momentum,
+                     const uint32_t* keys_in, uint32_t* keys_out,
+                     int64_t n_chains, const int64_t* leaf_sizes, int n_leaves,
+                     float step_size, const float* mass, int prng_layout) {
+  SGMC_REQUIRE(keys_in != keys_out, "keys_out must not alias keys_in");
+  LeafTable tab;
+  if (int e = build_leaf_table(&tab, leaf_sizes, n_leaves, n_chains,
+                               aligned16({theta, momentum}))) return e;
+  SghmcBeginOp op{theta, momentum, mass, step_size};
+  return launch_noise_pass((cudaStream_t)stream, tab, keys_in, keys_out,
+                           n_chains, kKeySplit2, prng_layout, op,
+                           "sgmc_sghmc_begin");
+}
+
+int sgmc_sghmc_step(void* stream, float* theta, float* momentum,
+                    const float* grad, const uint32_t* keys_in,
+                    uint32_t* keys_out, int64_t n_chains,
+                    const int64_t* leaf_sizes, int n_leaves, float step_size,
+                    float friction_scalar, const float* friction,
+                    const float* mass, int last, int prng_layout) {
+  SGMC_REQUIRE(keys_in != keys_out, "keys_out must not alias keys_in");
+  LeafTable tab;
+  if (int e = build_leaf_table(&tab, leaf_sizes, n_leaves, n_chains,
+                               aligned16({theta, momentum, grad}))) return e;
+  const float eps = step_size;
+  SghmcStepOp op{theta, momentum, grad, friction, mass, eps, -eps,
+                 sqrtf(2.0f * eps), friction_scalar, last};
+  return launch_noise_pass((cudaStream_t)stream, tab, keys_in, keys_out,
+                           n_chains, kKeySplit2, prng_layout, op,
+                           "sgmc_sghmc_step");
+}
+
+int sgmc_obabo_pass_a(void* stream, float* theta, float* momentum,
+                      const float* grad, float* ke_start,
+                      const uint32_t* keys_in, uint32_t* keys_out,
+                      int64_t n_chains, const int64_t* leaf_sizes, int n_leaves,
+                      float step_size, float temperature, float friction,
+                      const float* mass, int prng_layout) {
+  SGMC_REQUIRE(keys_in != keys_out, "keys_out must not alias keys_in");
+  LeafTable tab;
+  if (int e = build_leaf_table(&tab, leaf_sizes, n_leaves, n_chains,
+                               aligned16({theta, momentum, grad}))) return e;
+  // integrator.py:195-199
+  const float a = (float)exp((double)(-friction * step_size));  // f64 libm, rounded once
+  const float o_noise = sqrtf((1.0f - a) * temperature);
+  ObaboAOp op{theta, momentum, grad, ke_start, mass, step_size, sqrtf(a),
+              o_noise, -1.0f * (0.5f * step_size)};
+  return launch_noise_pass((cudaStream_t)stream, tab, keys_in, keys_out,
+                           n_chains, kKeySplit3A, prng_layout, op,
+                           "sgmc_obabo_pass_a");
+}
+
+int sgmc_obabo_pass_b(void* stream, float* momentum, const float* grad,
+                      float* ke_end, const uint32_t* keys_in,
+                      int64_t n_chains, const int64_t* leaf_sizes, int n_leaves,
+                      float step_size, float temperature, float friction,
+                      const float* mass, int prng_layout) {
+  LeafTable tab;
+  if (int e = build_leaf_table(&tab, leaf_sizes, n_leaves, n_chains,
+                               aligned16({momentum, grad}))) return e;
+  const float a = (float)exp((double)(-friction * step_size));  // f64 libm, rounded once
+  const float o_noise = sqrtf((1.0f - a) * temperature);
+  ObaboBOp op{momentum, grad, ke_end, mass, sqrtf(a), o_noise,
+              -1.0f * (0.5f * step_size)};
+  return launch_noise_pass((cudaStream_t)stream, tab, keys_in, nullptr,
+                           n_chains, kKeySplit3B, prng_layout, op,
+                           "sgmc_obabo_pass_b");
+}
+
+}  // extern "C"

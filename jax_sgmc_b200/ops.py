@@ -1,0 +1,232 @@
+"""Array-level wrappers of the libsgmc_b200 entry points.
+
+One Python function per C-ABI op (include/sgmc_b200.h), taking
+``DeviceArray``s.  The operator-API modules (``potential``, ``integrator``,
+``adaption``, ``solver``) are built on these; tests and ``bench.py`` call them
+directly as "the C ABI".  Nothing here computes on the host.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+from .device import DeviceArray, Stream, current_stream, vp, i64_array
+
+ORIGINAL, PARTITIONABLE = 0, 1
+_LAYOUTS = {"original": 0, "partitionable": 1, 0: 0, 1: 1}
+
+
+def _layout(layout) -> int:
+  return _LAYOUTS[layout]
+
+
+def _s(stream: Optional[Stream]):
+  return (stream or current_stream()).handle
+
+
+# ---- PRNG ---------------------------------------------------------------------
+
+def prng_key(seed: int) -> np.ndarray:
+  """``jax.random.PRNGKey`` (x64 off): uint32[2] = [hi32, lo32] of the seed.
+  Pure bit packing of a Python int; host-side by nature."""
+  seed = int(seed)
+  return np.array([(seed >> 32) & 0xFFFFFFFF, seed & 0xFFFFFFFF], np.uint32)
+
+
+def prng_keys(seeds: Sequence[int]) -> DeviceArray:
+  return DeviceArray.from_numpy(np.stack([prng_key(s) for s in seeds]))
+
+
+def split(keys: DeviceArray, num: int = 2, layout=0, stream=None) -> DeviceArray:
+  """random.split for every key: uint32[..., 2] -> uint32[..., num, 2]."""
+  n_keys = keys.size // 2
+  out = DeviceArray(keys.shape[:-1] + (num, 2), np.uint32)
+  _lib.call("sgmc_prng_split", _s(stream), vp(keys), vp(out), n_keys, num,
+            _layout(layout))
+  return out
+
+
+def random_bits(keys: DeviceArray, n: int, layout=0, stream=None) -> DeviceArray:
+  n_keys = keys.size // 2
+  out = DeviceArray(keys.shape[:-1] + (n,), np.uint32)
+  _lib.call("sgmc_random_bits", _s(stream), vp(keys), vp(out), n_keys, n,
+            _layout(layout))
+  return out
+
+
+def uniform(keys: DeviceArray, n: int, minval=0.0, maxval=1.0, layout=0,
+            stream=None) -> DeviceArray:
+  n_keys = keys.size // 2
+  out = DeviceArray(keys.shape[:-1] + (n,), np.float32)
+  _lib.call("sgmc_uniform", _s(stream), vp(keys), vp(out), n_keys, n,
+            float(minval), float(maxval), _layout(layout))
+  return out
+
+
+def normal(keys: DeviceArray, n: int, layout=0, stream=None) -> DeviceArray:
+  n_keys = keys.size // 2
+  out = DeviceArray(keys.shape[:-1] + (n,), np.float32)
+  _lib.call("sgmc_normal", _s(stream), vp(keys), vp(out), n_keys, n,
+            _layout(layout))
+  return out
+
+
+def normal_like(keys: DeviceArray, leaf_sizes: Sequence[int], layout=0,
+                stream=None, out: Optional[DeviceArray] = None) -> DeviceArray:
+  """integrator.random_tree for every chain: f32[C, P]."""
+  C_ = keys.size // 2
+  P = int(sum(leaf_sizes))
+  if out is None:
+    out = DeviceArray((C_, P), np.float32)
+  _lib.call("sgmc_normal_like", _s(stream), vp(keys), vp(out), C_,
+            i64_array(leaf_sizes), len(leaf_sizes), _layout(layout))
+  return out
+
+
+def randint(key: DeviceArray, n: int, minval: int, maxval: int, layout=0,
+            stream=None) -> DeviceArray:
+  out = DeviceArray((n,), np.int32)
+  _lib.call("sgmc_randint", _s(stream), vp(key), vp(out), n, int(minval),
+            int(maxval), _layout(layout))
+  return out
+
+
+def minibatch_draw(key_in: DeviceArray, key_out: DeviceArray, idx: DeviceArray,
+                   observation_count: int, layout=0, stream=None):
+  _lib.call("sgmc_minibatch_draw", _s(stream), vp(key_in), vp(key_out), vp(idx),
+            idx.size, int(observation_count), _layout(layout))
+
+
+def gather_rows(src: DeviceArray, idx: DeviceArray, stream=None,
+                out: Optional[DeviceArray] = None) -> DeviceArray:
+  row = int(np.prod(src.shape[1:], dtype=np.int64))
+  if out is None:
+    out = DeviceArray((idx.size,) + src.shape[1:], np.float32)
+  _lib.call("sgmc_gather_rows", _s(stream), vp(src), vp(idx), vp(out), idx.size,
+            row)
+  return out
+
+
+def synth_logistic_data(seed: int, N: int, d: int, layout=0, stream=None):
+  """Generate the C2 synthetic data set in HBM: returns (X, y, w_true)."""
+  X = DeviceArray((N, d), np.float32)
+  y = DeviceArray((N,), np.float32)
+  w = DeviceArray((d,), np.float32)
+  key = prng_key(seed)
+  _lib.call("sgmc_synth_logistic_data", _s(stream),
+            key.ctypes.data_as(C.c_void_p), vp(X), vp(y), vp(w), N, d,
+            _layout(layout))
+  return X, y, w
+
+
+# ---- fused updates ----------------------------------------------------------------
+
+def sgld_update(theta, grad, keys_in, keys_out, leaf_sizes, step_size,
+                temperature=1.0, temp_per_chain=None, v=None, alpha=0.9,
+                lmbd=1e-5, layout=0, stream=None):
+  """One fused SGLD (v is None) or pSGLD step; theta / v updated in place."""
+  C_ = theta.shape[0]
+  ls = i64_array(leaf_sizes)
+  if v is None:
+    _lib.call("sgmc_sgld_update", _s(stream), vp(theta), vp(grad), vp(keys_in),
+              vp(keys_out), C_, ls, len(leaf_sizes), float(step_size),
+              float(temperature), vp(temp_per_chain), _layout(layout))
+  else:
+    _lib.call("sgmc_sgld_rms_update", _s(stream), vp(theta), vp(v), vp(grad),
+              vp(keys_in), vp(keys_out), C_, ls, len(leaf_sizes),
+              float(step_size), float(temperature), vp(temp_per_chain),
+              float(alpha), float(lmbd), _layout(layout))
+
+
+def sghmc_begin(theta, momentum, keys_in, keys_out, leaf_sizes, step_size,
+                mass=None, layout=0, stream=None):
+  _lib.call("sgmc_sghmc_begin", _s(stream), vp(theta), vp(momentum),
+            vp(keys_in), vp(keys_out), theta.shape[0], i64_array(leaf_sizes),
+            len(leaf_sizes), float(step_size), vp(mass), _layout(layout))
+
+
+def sghmc_step(theta, momentum, grad, keys_in, keys_out, leaf_sizes, step_size,
+               friction=0.25, friction_vec=None, mass=None, last=False,
+               layout=0, stream=None):
+  _lib.call("sgmc_sghmc_step", _s(stream), vp(theta), vp(momentum), vp(grad),
+            vp(keys_in), vp(keys_out), theta.shape[0], i64_array(leaf_sizes),
+            len(leaf_sizes), float(step_size), float(friction),
+            vp(friction_vec), vp(mass), int(bool(last)), _layout(layout))
+
+
+def obabo_pass_a(theta, momentum, grad, ke_start, keys_in, keys_out,
+                 leaf_sizes, step_size, temperature=1.0, friction=1.0,
+                 mass=None, layout=0, stream=None):
+  _lib.call("sgmc_obabo_pass_a", _s(stream), vp(theta), vp(momentum), vp(grad),
+            vp(ke_start), vp(keys_in), vp(keys_out), theta.shape[0],
+            i64_array(leaf_sizes), len(leaf_sizes), float(step_size),
+            float(temperature), float(friction), vp(mass), _layout(layout))
+
+
+def obabo_pass_b(momentum, grad, ke_end, keys_in, leaf_sizes, step_size,
+                 temperature=1.0, friction=1.0, mass=None, layout=0,
+                 stream=None):
+  _lib.call("sgmc_obabo_pass_b", _s(stream), vp(momentum), vp(grad), vp(ke_end),
+            vp(keys_in), momentum.shape[0], i64_array(leaf_sizes),
+            len(leaf_sizes), float(step_size), float(temperature),
+            float(friction), vp(mass), _layout(layout))
+
+
+# ---- GLM potential -----------------------------------------------------------------
+
+FAMILY = {"gaussian": 0, "logistic": 1}
+PRIOR = {"flat": 0, "gaussian": 1, "inv_sigma": 2}
+PATH = {"simt": 0, "tc_parity": 1, "tc_throughput": 2, 0: 0, 1: 1, 2: 2}
+
+
+def glm_spec(family, d, w_off, aux_off=-1, prior="flat", prior_off=0,
+             prior_size=0, prior_scale=1.0, temperature=1.0) -> _lib.GlmSpec:
+  return _lib.GlmSpec(FAMILY[family], int(d), int(w_off), int(aux_off),
+                      PRIOR[prior], int(prior_off), int(prior_size),
+                      float(prior_scale), float(temperature))
+
+
+def glm_workspace(n_chains: int, batch_size: int, d: int, path=0) -> DeviceArray:
+  nbytes = _lib.load().sgmc_glm_workspace_bytes(n_chains, batch_size, d,
+                                                PATH[path])
+  return DeviceArray((int(nbytes),), np.uint8)
+
+
+def glm_potential_grad(spec, theta, X, y, idx, observation_count, potential,
+                       variance=None, grad=None, ell=None, mask=None,
+                       workspace=None, path=0, batch_size=None, stream=None):
+  """U, var(ell), dU/dtheta for all chains on one shared minibatch."""
+  C_, P = theta.shape
+  n = int(batch_size if batch_size is not None
+          else (idx.size if idx is not None else X.shape[0]))
+  if workspace is None:
+    workspace = glm_workspace(C_, n, spec.d, path)
+  _lib.call("sgmc_glm_potential_grad", _s(stream), C.byref(spec), vp(theta), C_,
+            P, vp(X), vp(y), vp(idx), vp(mask), n, int(observation_count),
+            vp(potential), vp(variance), vp(grad), vp(ell), vp(workspace),
+            workspace.nbytes, PATH[path])
+  return workspace
+
+
+# ---- reSGLD ------------------------------------------------------------------------
+
+def resgld_decide(U_n, U_h, var_n, ssq, F, step, T_normal, T_hot, keys_in,
+                  keys_out, exchange, layout=0, stream=None):
+  _lib.call("sgmc_resgld_decide", _s(stream), vp(U_n), vp(U_h), vp(var_n),
+            vp(ssq), vp(F), int(step), float(T_normal), float(T_hot),
+            vp(keys_in), vp(keys_out), vp(exchange), exchange.size,
+            _layout(layout))
+
+
+def swap_rows(a: DeviceArray, b: DeviceArray, exchange: DeviceArray, stream=None):
+  n_rows = exchange.size
+  row_bytes = a.nbytes // max(n_rows, 1)
+  _lib.call("sgmc_swap_rows", _s(stream), vp(a), vp(b), vp(exchange), n_rows,
+            row_bytes)
+
+
+def launch_count() -> int:
+  return int(_lib.load().sgmc_launch_count())

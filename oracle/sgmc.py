@@ -1,0 +1,542 @@
+"""NumPy f32 restatement of the jax-sgmc sampling hot path (oracle).
+
+TEST INFRASTRUCTURE (see ``oracle/__init__.py``): never imported by the
+product package.  Every function cites the reference lines it follows.
+Arrays are chain-batched and flat: ``theta`` is f32[C, P] where P is the
+raveled sample (``jax.flatten_util.ravel_pytree`` order, oracle/tree.py) and C
+the number of independent chains (the reference's leading ``list_vmap`` axis,
+util/list_map.py:53-56).  Evaluation order of every update follows SURVEY.md
+Appendix A; all arithmetic is f32 with one rounding per operation (no FMA) so
+the CUDA update kernels, which use explicit ``__fmul_rn``/``__fadd_rn``, can be
+compared bit for bit when they are fed the same gradient.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Callable, NamedTuple, Optional, Sequence
+
+import math
+
+import numpy as np
+
+from . import prng
+
+F32 = np.float32
+
+
+# ----------------------------------------------------------------------------
+# noise:  integrator.random_tree  (integrator.py:119-135)
+# ----------------------------------------------------------------------------
+
+def random_tree_flat(keys, sizes: Sequence[int], layout="original"):
+  """Noise shaped like the raveled sample for every chain.
+
+  ``splits = random.split(key, n_leaves)`` (integrator.py:131) and leaf l gets
+  ``random.normal(splits[l], leaf.shape)`` (integrator.py:132); leaves are in
+  tree_flatten order, so the flat noise is their concatenation.
+  keys: uint32[C, 2] -> f32[C, P].
+  """
+  keys = np.asarray(keys, dtype=np.uint32)
+  leaf_keys = prng.split(keys, len(sizes), layout)           # [C, L, 2]
+  parts = [prng.normal(leaf_keys[..., l, :], (sz,), layout)
+           for l, sz in enumerate(sizes)]
+  return np.concatenate(parts, axis=-1).astype(F32)
+
+
+# ----------------------------------------------------------------------------
+# GLM likelihoods and priors (the "recognised" families of the north star)
+# ----------------------------------------------------------------------------
+
+@dataclass
+class GaussianLinear:
+  """Quickstart model (examples/quickstart.md:158-176).
+
+  ``ell_i = norm.logpdf(y_i - x_i.w, scale=exp(log_sigma))`` with
+  jax.scipy.stats.norm.logpdf's operation order:
+  ``(log(2 pi s^2) + r^2 / s^2) / -2``.
+  """
+  d: int
+  w_off: int
+  log_sigma_off: int
+
+  def loglik(self, theta, X, y):
+    w = theta[:, self.w_off:self.w_off + self.d]
+    sigma = np.exp(theta[:, self.log_sigma_off]).astype(F32)[:, None]
+    r = (y[None, :] - (w @ X.T).astype(F32)).astype(F32)
+    s2 = (sigma * sigma).astype(F32)
+    ln = np.log((F32(2 * np.pi) * s2).astype(F32)).astype(F32)
+    q = ((r * r).astype(F32) / s2).astype(F32)
+    ell = ((ln + q).astype(F32) / F32(-2.0)).astype(F32)
+    return ell, (r, s2)
+
+  def vjp(self, theta, X, y, aux, cot):
+    """sum_i cot[c,i] * d ell_i / d theta  -> f32[C, P]."""
+    r, s2 = aux
+    g = np.zeros_like(theta)
+    dz = ((r / s2).astype(F32) * cot).astype(F32)              # d ell/d(x.w)
+    g[:, self.w_off:self.w_off + self.d] = (dz @ X).astype(F32)
+    dls = (((r * r).astype(F32) / s2).astype(F32) - F32(1.0)).astype(F32)
+    g[:, self.log_sigma_off] = np.sum((dls * cot).astype(F32), axis=1,
+                                      dtype=F32)
+    return g
+
+
+@dataclass
+class Logistic:
+  """Bayesian logistic regression (BASELINE.json configs[1]).
+
+  ``ell_i = y_i z_i - softplus(z_i)``, ``z = x.w (+ b)``, which equals
+  ``y log sigmoid(z) + (1-y) log(1-sigmoid(z))`` for y in {0,1};
+  ``softplus(z) = max(z,0) + log1p(exp(-|z|))``.
+  """
+  d: int
+  w_off: int
+  b_off: int = -1
+
+  def loglik(self, theta, X, y):
+    w = theta[:, self.w_off:self.w_off + self.d]
+    z = (w @ X.T).astype(F32)
+    if self.b_off >= 0:
+      z = (z + theta[:, self.b_off][:, None]).astype(F32)
+    e = np.exp(-np.abs(z)).astype(F32)
+    sp = (np.maximum(z, F32(0)) + np.log1p(e).astype(F32)).astype(F32)
+    ell = ((y[None, :] * z).astype(F32) - sp).astype(F32)
+    # sigmoid(z) = where(z>=0, 1/(1+e), e/(1+e))
+    den = (F32(1.0) + e).astype(F32)
+    sig = np.where(z >= 0, F32(1.0) / den, e / den).astype(F32)
+    return ell, (sig,)
+
+  def vjp(self, theta, X, y, aux, cot):
+    (sig,) = aux
+    g = np.zeros_like(theta)
+    dz = ((y[None, :] - sig).astype(F32) * cot).astype(F32)
+    g[:, self.w_off:self.w_off + self.d] = (dz @ X).astype(F32)
+    if self.b_off >= 0:
+      g[:, self.b_off] = np.sum(dz, axis=1, dtype=F32)
+    return g
+
+
+@dataclass
+class Prior:
+  """Log-priors used by the reference examples.
+
+  kind ``"gaussian"``: sum over [off, off+size) of ``-0.5 (theta/scale)^2``
+  (normalising constant dropped -- it has no gradient; the reference's
+  examples/cifar.md:214-219 uses ``norm.logpdf`` sums, whose constant only
+  shifts U).  kind ``"inv_sigma"``: ``1/exp(theta[off])`` -- the quickstart's
+  (unusual) log-prior, examples/quickstart.md:172-173.  kind ``"flat"``: 0.
+  """
+  kind: str = "flat"
+  off: int = 0
+  size: int = 0
+  scale: float = 1.0
+
+  def value(self, theta):
+    C = theta.shape[0]
+    if self.kind == "flat":
+      return np.zeros(C, F32)
+    if self.kind == "gaussian":
+      t = theta[:, self.off:self.off + self.size]
+      inv = F32(1.0) / F32(self.scale * self.scale)
+      return (F32(-0.5) * inv * np.sum((t * t).astype(F32), axis=1,
+                                       dtype=F32)).astype(F32)
+    if self.kind == "inv_sigma":
+      return (F32(1.0) / np.exp(theta[:, self.off]).astype(F32)).astype(F32)
+    raise ValueError(self.kind)
+
+  def grad(self, theta):
+    g = np.zeros_like(theta)
+    if self.kind == "gaussian":
+      inv = F32(1.0) / F32(self.scale * self.scale)
+      g[:, self.off:self.off + self.size] = (
+          -theta[:, self.off:self.off + self.size] * inv).astype(F32)
+    elif self.kind == "inv_sigma":
+      g[:, self.off] = (-(F32(1.0) / np.exp(theta[:, self.off]).astype(F32))
+                        ).astype(F32)
+    return g
+
+
+# ----------------------------------------------------------------------------
+# potential.minibatch_potential / full_potential   (potential.py:94-293)
+# ----------------------------------------------------------------------------
+
+def minibatch_potential(model, prior: Prior, temperature: float = 1.0):
+  """``potential_fn(theta, (X_b, y_b), N, mask=None) -> (U, ell, grad)``.
+
+  potential.py:159-214: ``L = -N * mean(ell)`` (:183) or
+  ``-N/n * dot(ell, mask)`` (:185); ``U = (L - prior) / T`` (:210).  The
+  gradient is the reverse-mode derivative of exactly that expression
+  (integrator.py:166,593,792 call ``value_and_grad``): cotangent
+  ``(1/T) * (-N) / n`` on every ell_i, ``-(1/T)`` on the prior.
+  """
+  T = F32(temperature)
+
+  def potential_fn(theta, batch, N, mask=None):
+    X, y = batch
+    n = X.shape[0]
+    theta = np.asarray(theta, F32)
+    ell, aux = model.loglik(theta, X, y)
+    if mask is None:
+      L = (F32(-N) * (np.sum(ell, axis=1, dtype=F32) / F32(n))).astype(F32)
+      cot = np.full(ell.shape, (F32(-N) / F32(n)) / T, dtype=F32)
+    else:
+      m = np.asarray(mask, F32)
+      L = ((F32(-N) / F32(n)) * (ell @ m).astype(F32)).astype(F32)
+      cot = (((F32(-N) / F32(n)) / T) * m)[None, :].astype(F32)
+      cot = np.broadcast_to(cot, ell.shape)
+    pv = prior.value(theta)
+    U = ((L - pv).astype(F32) / T).astype(F32)
+    g = model.vjp(theta, X, y, aux, cot)
+    g = (g - (prior.grad(theta) / T).astype(F32)).astype(F32)
+    return U, ell, g
+
+  return potential_fn
+
+
+def full_potential(model, prior: Prior, temperature: float = 1.0):
+  """potential.py:219-293: ``U = (sum_b -dot(ell_b, mask_b) - prior) / T``.
+
+  ``batches`` is an iterable of ``(X_b, y_b, mask_b)`` as produced by
+  ``full_reference_data`` (data/core.py:586-627): the last batch wraps indices
+  modulo N and masks the overhang (core.py:571-572).  The inner potential has
+  zero prior and T=1 and is un-scaled by n/N (potential.py:258-271).
+  """
+  inner = minibatch_potential(model, Prior("flat"), 1.0)
+  T = F32(temperature)
+
+  def full_fn(theta, batches, N):
+    theta = np.asarray(theta, F32)
+    total = np.zeros(theta.shape[0], F32)
+    for X, y, mask in batches:
+      n = X.shape[0]
+      u, _, _ = inner(theta, (X, y), N, mask=mask)
+      total = (total + (u * F32(n) / F32(N)).astype(F32)).astype(F32)
+    return ((total - prior.value(theta)).astype(F32) / T).astype(F32)
+
+  return full_fn
+
+
+# ----------------------------------------------------------------------------
+# adaption.rms_prop   (adaption.py:225-293)
+# ----------------------------------------------------------------------------
+
+def rms_prop_init(theta, alpha=0.9, lmbd=1e-5):
+  """adaption.py:238-252: v = ones_like(sample)."""
+  return np.ones_like(theta, dtype=F32), F32(alpha), F32(lmbd)
+
+
+def rms_prop_update(state, grad):
+  """adaption.py:270-272: v' = alpha v + (1 - alpha) g^2 (raw gradient)."""
+  v, alpha, lmbd = state
+  one_m = (F32(1.0) - alpha).astype(F32)
+  new_v = ((alpha * v).astype(F32)
+           + (one_m * (grad * grad).astype(F32)).astype(F32)).astype(F32)
+  return new_v, alpha, lmbd
+
+
+def rms_prop_get(state):
+  """adaption.py:289-291: G = (lmbd + sqrt(v))^-1, sqrt(G), Gamma = 0."""
+  v, _, lmbd = state
+  g = (F32(1.0) / (lmbd + np.sqrt(v).astype(F32)).astype(F32)).astype(F32)
+  return g, np.sqrt(g).astype(F32), np.zeros_like(g)
+
+
+# ----------------------------------------------------------------------------
+# integrator.langevin_diffusion   (integrator.py:767-924)
+# ----------------------------------------------------------------------------
+
+class LangevinState(NamedTuple):
+  theta: np.ndarray            # f32[C, P]
+  key: np.ndarray              # u32[C, 2]
+  v: Optional[np.ndarray]      # rms_prop second moment or None
+  potential: np.ndarray        # f32[C]
+  variance: np.ndarray         # f32[C]
+
+
+def langevin_init(theta, keys=None, rms=False):
+  """integrator.py:803-846.  Default key PRNGKey(0) for every chain (:804)."""
+  theta = np.array(theta, dtype=F32)
+  C = theta.shape[0]
+  if keys is None:
+    keys = np.tile(prng.PRNGKey(0), (C, 1))
+  return LangevinState(theta, np.array(keys, dtype=np.uint32),
+                       np.ones_like(theta) if rms else None,
+                       np.zeros(C, F32), np.ones(C, F32))
+
+
+def sgld_scales(step_size, temperature):
+  """integrator.py:882-884: (-eps), sqrt(2*T*eps) as f32 scalars."""
+  eps = F32(step_size)
+  neg_eps = F32(-eps)
+  noise_scale = np.sqrt(F32(F32(F32(2.0) * F32(temperature)) * eps)).astype(F32)
+  return neg_eps, F32(noise_scale)
+
+
+def sgld_apply(theta, grad, xi, step_size, temperature, v=None,
+               alpha=0.9, lmbd=1e-5):
+  """Elementwise part of one SGLD / pSGLD step.
+
+  Returns (theta', v').  integrator.py:882-912, adaption.py:254-291.
+  """
+  neg_eps, ns = sgld_scales(step_size, temperature)
+  sg = (neg_eps * grad).astype(F32)
+  sn = (ns * xi).astype(F32)
+  if v is None:
+    delta = (sg + sn).astype(F32)
+    new_v = None
+  else:
+    new_v, _, _ = rms_prop_update((v, F32(alpha), F32(lmbd)), grad)
+    G, S, _ = rms_prop_get((new_v, F32(alpha), F32(lmbd)))
+    # ((eps*Gamma) + (G*sg)) + (S*sn), Gamma == 0     (integrator.py:903-909)
+    delta = ((F32(0.0) + (G * sg).astype(F32)).astype(F32)
+             + (S * sn).astype(F32)).astype(F32)
+  return (theta + delta).astype(F32), new_v
+
+
+def langevin_update(state: LangevinState, grad_fn: Callable, sizes,
+                    step_size, temperature, alpha=0.9, lmbd=1e-5,
+                    layout="original"):
+  """One ``langevin_diffusion.update_fn`` (integrator.py:860-922).
+
+  ``grad_fn(theta) -> (U[C], ell[C,n], grad[C,P])`` is the value_and_grad of
+  the stochastic potential on this step's minibatch (:875-879).
+  """
+  ks = prng.split(state.key, 2, layout)                     # :871
+  new_key, sub = ks[..., 0, :], ks[..., 1, :]
+  xi = random_tree_flat(sub, sizes, layout)                 # :874
+  U, ell, g = grad_fn(state.theta)
+  mean = (np.sum(ell, axis=1, dtype=F32) / F32(ell.shape[1])).astype(F32)
+  dev = (ell - mean[:, None]).astype(F32)
+  var = (np.sum((dev * dev).astype(F32), axis=1, dtype=F32)
+         / F32(ell.shape[1])).astype(F32)                   # jnp.var  :880
+  theta, v = sgld_apply(state.theta, g, xi, step_size, temperature,
+                        state.v, alpha, lmbd)
+  return LangevinState(theta, new_key, v, U.astype(F32), var)
+
+
+# ----------------------------------------------------------------------------
+# integrator.friction_leapfrog (SGHMC)   (integrator.py:563-765)
+# ----------------------------------------------------------------------------
+
+class LeapfrogState(NamedTuple):
+  theta: np.ndarray
+  momentum: np.ndarray
+  key: np.ndarray
+  potential: np.ndarray
+
+
+def leapfrog_init(theta, keys=None):
+  """integrator.py:668-713: momentum placeholder = the sample (:702)."""
+  theta = np.array(theta, dtype=F32)
+  C = theta.shape[0]
+  if keys is None:
+    keys = np.tile(prng.PRNGKey(0), (C, 1))
+  return LeapfrogState(theta, theta.copy(), np.array(keys, np.uint32),
+                       np.zeros(C, F32))
+
+
+def sghmc_inner_apply(theta_new, p, m, grad, xi, step_size, friction):
+  """Momentum part of ``_body_fun`` after the gradient (integrator.py:616-655).
+
+  m = M^-1 p (computed by the caller from the *old* momentum, :610).
+  p1 = p + ((-eps*C) * m); p2 = p1 + ((-eps)*g); p3 = p2 + (C*(sqrt(2 eps)*xi)).
+  """
+  eps = F32(step_size)
+  C = np.asarray(friction, F32)
+  p1 = (p + ((F32(-eps) * C).astype(F32) * m).astype(F32)).astype(F32)
+  p2 = (p1 + (F32(-eps) * grad).astype(F32)).astype(F32)
+  ns = np.sqrt(F32(F32(2.0) * eps)).astype(F32)
+  p3 = (p2 + (C * (ns * xi).astype(F32)).astype(F32)).astype(F32)
+  return p3
+
+
+def friction_leapfrog_integrate(state: LeapfrogState, grad_fns, sizes,
+                                step_size, friction=0.25, mass=None,
+                                layout="original"):
+  """``friction_leapfrog.integrate`` (integrator.py:716-757).
+
+  ``grad_fns`` is a sequence of ``steps`` callables, one per inner step (each
+  inner step draws a fresh minibatch, :621).  ``mass`` is the flat diagonal
+  mass (f32[P]) or None for unit mass (:722-726).
+  """
+  P = state.theta.shape[1]
+  mass = np.ones(P, F32) if mass is None else np.asarray(mass, F32)
+  inv_m = (F32(1.0) / mass).astype(F32)                      # :108-110
+  sqrt_m = np.sqrt(mass).astype(F32)                         # :111-113
+  fr = np.asarray(friction, F32)
+  fr = np.full(P, fr, F32) if fr.ndim == 0 else fr           # :729-733
+  ks = prng.split(state.key, 2, layout)                      # :736
+  key, sub = ks[..., 0, :], ks[..., 1, :]
+  p = (sqrt_m * random_tree_flat(sub, sizes, layout)).astype(F32)  # :737-738
+  theta = state.theta
+  U = np.zeros(theta.shape[0], F32)
+  eps = F32(step_size)
+  for grad_fn in grad_fns:                                   # :749-755
+    m = (inv_m * p).astype(F32)                              # :610
+    theta = (theta + (eps * m).astype(F32)).astype(F32)      # :611-612
+    U, _, g = grad_fn(theta)                                 # :621-625
+    ks = prng.split(key, 2, layout)                          # :630
+    key, sub = ks[..., 0, :], ks[..., 1, :]
+    xi = random_tree_flat(sub, sizes, layout)                # :631
+    p = sghmc_inner_apply(theta, p, m, g, xi, eps, fr)
+  return LeapfrogState(theta, p, key, U.astype(F32))
+
+
+# ----------------------------------------------------------------------------
+# integrator.obabo   (integrator.py:138-346)
+# ----------------------------------------------------------------------------
+
+class ObaboState(NamedTuple):
+  theta: np.ndarray
+  momentum: np.ndarray
+  key: np.ndarray
+  potential: np.ndarray
+  kinetic_energy_start: np.ndarray
+  kinetic_energy_end: np.ndarray
+
+
+def obabo_init(theta, keys=None):
+  """integrator.py:275-315: zero momentum (:303), zero KE accumulators."""
+  theta = np.array(theta, dtype=F32)
+  C = theta.shape[0]
+  if keys is None:
+    keys = np.tile(prng.PRNGKey(0), (C, 1))
+  z = np.zeros(C, F32)
+  return ObaboState(theta, np.zeros_like(theta), np.array(keys, np.uint32),
+                    z, z.copy(), z.copy())
+
+
+def _tree_dot(a, b, sizes):
+  """util/tree_util.py:131-133: Python sum over per-leaf jnp.sum(a*b)."""
+  total = None
+  off = 0
+  for sz in sizes:
+    s = np.sum((a[:, off:off + sz] * b[:, off:off + sz]).astype(F32), axis=1,
+               dtype=F32)
+    total = s if total is None else (total + s).astype(F32)
+    off += sz
+  return total
+
+
+def obabo_o_step(p, xi, step_size, temperature, friction, sqrt_m):
+  """``_momentum_resampling`` (integrator.py:192-200)."""
+  # exp evaluated in f64 libm and rounded once (same as the C host code)
+  a = F32(math.exp(float(F32(-F32(friction) * F32(step_size)))))
+  ns = np.sqrt(F32(F32(F32(1.0) - a) * F32(temperature))).astype(F32)
+  sa = np.sqrt(a).astype(F32)
+  return ((sa * p).astype(F32)
+          + (ns * (sqrt_m * xi).astype(F32)).astype(F32)).astype(F32)
+
+
+def obabo_integrate(state: ObaboState, grad_fn_pairs, sizes, step_size,
+                    temperature=1.0, friction=1.0, mass=None,
+                    layout="original"):
+  """``obabo.integrate`` (integrator.py:318-338; step :203-273).
+
+  ``grad_fn_pairs``: one ``(grad_fn_1, grad_fn_2)`` per step -- two minibatch
+  draws and two gradient evaluations per step (:225, :243).
+  """
+  P = state.theta.shape[1]
+  mass = np.ones(P, F32) if mass is None else np.asarray(mass, F32)
+  inv_m = (F32(1.0) / mass).astype(F32)
+  sqrt_m = np.sqrt(mass).astype(F32)
+  eps = F32(step_size)
+  theta, p, key = state.theta, state.momentum, state.key
+  ke_s, ke_e = state.kinetic_energy_start, state.kinetic_energy_end
+  U = state.potential
+  for g1_fn, g2_fn in grad_fn_pairs:
+    ks = prng.split(key, 3, layout)                          # :208
+    key, k1, k2 = ks[..., 0, :], ks[..., 1, :], ks[..., 2, :]
+    p1 = obabo_o_step(p, random_tree_flat(k1, sizes, layout), eps,
+                      temperature, friction, sqrt_m)         # :210-214
+    ke_s = (ke_s + (F32(0.5) * _tree_dot(p1, (inv_m * p1).astype(F32), sizes)
+                    ).astype(F32)).astype(F32)               # :222
+    U1, _, g1 = g1_fn(theta)                                 # :225-229
+    half = F32(F32(-1.0) * F32(F32(0.5) * eps))              # :188
+    p2 = ((half * g1).astype(F32) + p1).astype(F32)          # :230-233
+    theta = (theta + (eps * (inv_m * p2).astype(F32)).astype(F32)
+             ).astype(F32)                                   # :236-240
+    U2, _, g2 = g2_fn(theta)                                 # :243-247
+    p3 = ((half * g2).astype(F32) + p2).astype(F32)          # :248-251
+    p4 = obabo_o_step(p3, random_tree_flat(k2, sizes, layout), eps,
+                      temperature, friction, sqrt_m)         # :253-257
+    ke_e = (ke_e + (F32(0.5) * _tree_dot(p3, (inv_m * p3).astype(F32), sizes)
+                    ).astype(F32)).astype(F32)               # :261
+    U = (F32(0.5) * (U1 + U2).astype(F32)).astype(F32)       # :264
+    p = p4
+  return ObaboState(theta, p, key, U, ke_s, ke_e)
+
+
+# ----------------------------------------------------------------------------
+# solver.parallel_tempering (reSGLD)   (solver.py:220-299)
+# ----------------------------------------------------------------------------
+
+class TemperingState(NamedTuple):
+  normal: LangevinState
+  hot: LangevinState
+  ssq: np.ndarray      # f32[S]   one entry per reSGLD system
+  F: np.ndarray        # f32[S]
+  step: int
+  key: np.ndarray      # u32[S, 2]
+
+
+def parallel_tempering_init(normal_theta, hot_theta, ssq_init=0.0, keys=None,
+                            F=1.0, rms=False, layout="original"):
+  """solver.py:248-259: ``key, split1, split2 = split(key, 3)``."""
+  normal_theta = np.asarray(normal_theta, F32)
+  S = normal_theta.shape[0]
+  if keys is None:
+    keys = np.tile(prng.PRNGKey(0), (S, 1))
+  ks = prng.split(np.asarray(keys, np.uint32), 3, layout)
+  key, s1, s2 = ks[..., 0, :], ks[..., 1, :], ks[..., 2, :]
+  return TemperingState(langevin_init(normal_theta, s1, rms),
+                        langevin_init(hot_theta, s2, rms),
+                        np.full(S, ssq_init, F32), np.full(S, F, F32), 0, key)
+
+
+def resgld_swap_decision(U_n, U_h, var_n, ssq, F, step, T_n, T_h, keys,
+                         layout="original"):
+  """Swap arithmetic of solver.py:273-291.
+
+  Returns (exchange[S] bool, ssq'[S], key'[S,2], log_s, log_u).  The reference
+  exchanges the chains iff ``not (log_u < log_s)`` (:287-291) -- inverted
+  with respect to the paper; reproduced as is.
+  """
+  eta = F32(1.0) / F32(step)                                 # sa_schedule :221
+  ssq = (((F32(1.0) - eta).astype(F32) * ssq).astype(F32)
+         + (eta * var_n).astype(F32)).astype(F32)            # :275-276
+  temps = (F32(1.0) / F32(T_n) - F32(1.0) / F32(T_h)).astype(F32)   # :279
+  corr = ((temps * ssq).astype(F32) / F).astype(F32)         # :280
+  log_s = (temps * ((U_n - U_h).astype(F32) - corr).astype(F32)).astype(F32)
+  ks = prng.split(keys, 2, layout)                           # :283
+  key, sub = ks[..., 0, :], ks[..., 1, :]
+  u = prng.uniform(sub, (), layout=layout)                   # :284
+  log_u = prng.log_libdevice(u)
+  exchange = ~(log_u < log_s)
+  return exchange, ssq, key, log_s, log_u
+
+
+def parallel_tempering_update(state: TemperingState, grad_fn_normal,
+                              grad_fn_hot, sizes, step_size, T_normal, T_hot,
+                              step_size_hot=None, layout="original"):
+  """solver.py:264-293: update both chains, then maybe exchange whole states."""
+  step = state.step + 1                                      # :267
+  eps_h = step_size if step_size_hot is None else step_size_hot
+  normal = langevin_update(state.normal, grad_fn_normal, sizes, step_size,
+                           T_normal, layout=layout)          # :270
+  hot = langevin_update(state.hot, grad_fn_hot, sizes, eps_h, T_hot,
+                        layout=layout)                       # :271
+  exchange, ssq, key, _, _ = resgld_swap_decision(
+      normal.potential, hot.potential, normal.variance, state.ssq, state.F,
+      step, T_normal, T_hot, state.key, layout)
+
+  def pick(a, b):
+    if a is None:
+      return None, None
+    m = exchange.reshape((-1,) + (1,) * (a.ndim - 1))
+    return np.where(m, b, a), np.where(m, a, b)
+
+  fields = [pick(a, b) for a, b in zip(normal, hot)]
+  normal = LangevinState(*[f[0] for f in fields])
+  hot = LangevinState(*[f[1] for f in fields])
+  return TemperingState(normal, hot, ssq, state.F, step, key), exchange

@@ -1,0 +1,166 @@
+"""GPU parity of the GLM stochastic potential + gradient (all paths) against
+the oracle's restatement of potential.minibatch_potential and its reverse-mode
+gradient.  Floating point: rtol 1e-5 on potentials / variances, and gradients
+within 1e-5 of the gradient's scale (north-star tolerance, fp32)."""
+import numpy as np
+import pytest
+
+from oracle import data as odata
+from oracle import prng
+from oracle import sgmc as osgmc
+
+pytestmark = pytest.mark.gpu
+
+
+def _grad_close(got, want, tol=1e-5):
+  scale = np.abs(want).max(axis=1, keepdims=True) + 1e-30
+  err = np.abs(got - want) / scale
+  assert err.max() < tol, f"max scaled gradient error {err.max():.3e}"
+
+
+def _run(ops, DA, spec, theta, X, y, idx, N, mask=None, path="simt"):
+  C, P = theta.shape
+  n = len(idx)
+  d_U, d_var = DA((C,), np.float32), DA((C,), np.float32)
+  d_g, d_ell = DA((C, P), np.float32), DA((C, n), np.float32)
+  ops.glm_potential_grad(spec, DA.from_numpy(theta), DA.from_numpy(X),
+                         DA.from_numpy(y), DA.from_numpy(idx.astype(np.int32)),
+                         N, d_U, d_var, d_g, d_ell,
+                         mask=None if mask is None else DA.from_numpy(mask),
+                         path=path)
+  return d_U.numpy(), d_var.numpy(), d_g.numpy(), d_ell.numpy()
+
+
+@pytest.mark.parametrize("C,n,d", [(1, 10, 4), (5, 33, 7), (64, 128, 64),
+                                   (130, 257, 100)])
+@pytest.mark.parametrize("masked", [False, True])
+def test_gaussian_family_simt(gpu, C, n, d, masked):
+  from jax_sgmc_b200 import ops
+  from jax_sgmc_b200.device import DeviceArray as DA
+  rng = np.random.default_rng(C * 1000 + n)
+  N = 1000
+  X = rng.standard_normal((N, d)).astype(np.float32)
+  w_true = rng.standard_normal(d).astype(np.float32)
+  y = (X @ w_true + 0.5 * rng.standard_normal(N)).astype(np.float32)
+  theta = np.concatenate([rng.standard_normal((C, 1)) * 0.3 + 0.5,
+                          rng.standard_normal((C, d)) * 0.3], axis=1).astype(np.float32)
+  idx = rng.integers(0, N, n)
+  mask = (rng.random(n) < 0.7).astype(np.float32) if masked else None
+  spec = ops.glm_spec("gaussian", d, w_off=1, aux_off=0, prior="inv_sigma",
+                      prior_off=0, temperature=1.0)
+  U, var, g, ell = _run(ops, DA, spec, theta, X, y, idx, N, mask)
+  pot = osgmc.minibatch_potential(osgmc.GaussianLinear(d, 1, 0),
+                                  osgmc.Prior("inv_sigma", 0))
+  wU, well, wg = pot(theta, (X[idx], y[idx]), N, mask)
+  np.testing.assert_allclose(ell, well, rtol=2e-5, atol=1e-5)
+  np.testing.assert_allclose(U, wU, rtol=1e-5)
+  np.testing.assert_allclose(var, well.astype(np.float64).var(axis=1), rtol=1e-4)
+  _grad_close(g, wg)
+
+
+@pytest.mark.parametrize("C,n,d", [(3, 16, 8), (64, 256, 128), (97, 100, 33)])
+@pytest.mark.parametrize("temperature", [1.0, 2.5])
+def test_logistic_family_simt(gpu, C, n, d, temperature):
+  from jax_sgmc_b200 import ops
+  from jax_sgmc_b200.device import DeviceArray as DA
+  X, y, _ = odata.logistic_dataset(2000, d, seed=3)
+  rng = np.random.default_rng(n)
+  theta = (rng.standard_normal((C, d)) * 0.7).astype(np.float32)
+  idx = rng.integers(0, 2000, n)
+  spec = ops.glm_spec("logistic", d, w_off=0, prior="gaussian", prior_off=0,
+                      prior_size=d, prior_scale=10.0, temperature=temperature)
+  U, var, g, ell = _run(ops, DA, spec, theta, X, y, idx, 2000)
+  pot = osgmc.minibatch_potential(osgmc.Logistic(d, 0),
+                                  osgmc.Prior("gaussian", 0, d, 10.0), temperature)
+  wU, well, wg = pot(theta, (X[idx], y[idx]), 2000)
+  np.testing.assert_allclose(ell, well, rtol=2e-5, atol=2e-6)
+  np.testing.assert_allclose(U, wU, rtol=1e-5)
+  np.testing.assert_allclose(var, well.astype(np.float64).var(axis=1), rtol=1e-4)
+  _grad_close(g, wg)
+
+
+def test_logistic_with_bias(gpu):
+  from jax_sgmc_b200 import ops
+  from jax_sgmc_b200.device import DeviceArray as DA
+  d, C, n = 12, 9, 40
+  X, y, _ = odata.logistic_dataset(500, d, seed=1)
+  rng = np.random.default_rng(0)
+  theta = (rng.standard_normal((C, d + 1)) * 0.5).astype(np.float32)
+  idx = rng.integers(0, 500, n)
+  spec = ops.glm_spec("logistic", d, w_off=0, aux_off=d, prior="gaussian",
+                      prior_off=0, prior_size=d + 1, prior_scale=3.0)
+  U, var, g, ell = _run(ops, DA, spec, theta, X, y, idx, 500)
+  pot = osgmc.minibatch_potential(osgmc.Logistic(d, 0, d),
+                                  osgmc.Prior("gaussian", 0, d + 1, 3.0))
+  wU, well, wg = pot(theta, (X[idx], y[idx]), 500)
+  np.testing.assert_allclose(U, wU, rtol=1e-5)
+  _grad_close(g, wg)
+
+
+def test_full_potential_equals_minibatch_on_whole_set(gpu):
+  """tests/test_potential.py:299-333: summing masked batches over the whole
+  data set equals the potential of the whole set."""
+  from jax_sgmc_b200 import ops
+  from jax_sgmc_b200.device import DeviceArray as DA
+  d, C, N = 6, 4, 10
+  X, y, _ = odata.logistic_dataset(N, d, seed=5)
+  rng = np.random.default_rng(0)
+  theta = rng.standard_normal((C, d)).astype(np.float32)
+  spec = ops.glm_spec("logistic", d, w_off=0, prior="flat")
+  whole, _, _, _ = _run(ops, DA, spec, theta, X, y, np.arange(N), N)
+  for mb in (2, 3):
+    total = np.zeros(C)
+    for s in range(0, N, mb):
+      ids = np.arange(s, s + mb)
+      mask = (ids < N).astype(np.float32)
+      U, _, _, _ = _run(ops, DA, spec, theta, X, y, ids % N, N, mask)
+      total += U.astype(np.float64) * mb / N          # potential.py:264-271
+    np.testing.assert_allclose(total, whole, rtol=1e-5)
+
+
+@pytest.mark.parametrize("rms", [False, True])
+def test_sgld_logistic_trajectory_1000_steps(gpu, rms):
+  """1 000 SGLD(-rms) steps, minibatch indices + noise from the same keys on
+  both sides: trajectories, potentials agree within rtol 1e-5 (scaled)."""
+  from jax_sgmc_b200 import ops
+  from jax_sgmc_b200.device import DeviceArray as DA
+  from oracle import scheduler as osched
+  d, C, n, N, K = 32, 16, 64, 5000, 1000
+  X, y, _ = odata.logistic_dataset(N, d, seed=0)
+  theta0 = np.zeros((C, d), np.float32)
+  keys = np.stack([prng.PRNGKey(c) for c in range(C)])
+  eps = osched.polynomial_step_size_first_last(K, 1e-3 if not rms else 2e-2,
+                                               1e-4 if not rms else 2e-3)
+  spec = ops.glm_spec("logistic", d, w_off=0, prior="gaussian", prior_off=0,
+                      prior_size=d, prior_scale=10.0)
+  pot = osgmc.minibatch_potential(osgmc.Logistic(d, 0),
+                                  osgmc.Prior("gaussian", 0, d, 10.0))
+  # device side
+  dX, dy = DA.from_numpy(X), DA.from_numpy(y)
+  d_theta = DA.from_numpy(theta0)
+  d_v = DA.from_numpy(np.ones_like(theta0)) if rms else None
+  d_k = [DA.from_numpy(keys), DA((C, 2), np.uint32)]
+  d_dk = [DA.from_numpy(prng.PRNGKey(0)), DA((2,), np.uint32)]
+  d_idx = DA((n,), np.int32)
+  d_U, d_var, d_g = DA((C,), np.float32), DA((C,), np.float32), DA((C, d), np.float32)
+  ws = ops.glm_workspace(C, n, d, "simt")
+  for k in range(K):
+    ops.minibatch_draw(d_dk[k % 2], d_dk[(k + 1) % 2], d_idx, N)
+    ops.glm_potential_grad(spec, d_theta, dX, dy, d_idx, N, d_U, d_var, d_g,
+                           workspace=ws)
+    ops.sgld_update(d_theta, d_g, d_k[k % 2], d_k[(k + 1) % 2], [d], eps[k], 1.0,
+                    v=d_v)
+  # oracle side
+  st = osgmc.langevin_init(theta0, keys, rms=rms)
+  dk = prng.PRNGKey(0)
+  for k in range(K):
+    dk, idx = odata.device_draw(dk, n, N)
+    Xb, yb = X[idx], y[idx]
+    st = osgmc.langevin_update(st, lambda th: pot(th, (Xb, yb), N), [d], eps[k], 1.0)
+  got = d_theta.numpy()
+  scale = np.abs(st.theta).max()
+  assert np.abs(got - st.theta).max() / scale < 1e-5
+  np.testing.assert_allclose(d_U.numpy(), st.potential, rtol=1e-5)
+  np.testing.assert_allclose(d_var.numpy(), st.variance, rtol=1e-4)
+  assert np.array_equal(d_k[K % 2].numpy(), st.key)
+  assert np.array_equal(d_dk[K % 2].numpy(), dk)
