@@ -59,6 +59,15 @@ int  sgmc_event_destroy(void* event);
 int  sgmc_event_record(void* event, void* stream);
 int  sgmc_event_sync(void* event);
 int  sgmc_event_elapsed_ms(void* start, void* stop, float* ms);
+/* Process-wide options.
+ * SGMC_OPT_EXACT_UPDATE_MATH: 0 (default) = the RMSprop preconditioner
+ *   arithmetic (sqrt, reciprocal) uses the SFU approximations (<= 2 ulp) and
+ *   FMA contraction; 1 = IEEE-exact unfused arithmetic, bit-identical to the
+ *   NumPy oracle given the same gradient.  The Gaussian noise is bit-exact in
+ *   both modes. */
+enum { SGMC_OPT_EXACT_UPDATE_MATH = 0, SGMC_OPT_COUNT = 4 };
+int  sgmc_set_option(int option, int value);
+int  sgmc_get_option(int option);
 /* counts kernels launched by this library since load (bench "gpu_launches") */
 unsigned long long sgmc_launch_count(void);
 

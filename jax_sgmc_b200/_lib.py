@@ -29,6 +29,7 @@ _int = C.c_int
 
 # name -> argtypes   (every function returns int status unless listed below)
 PROTOTYPES = {
+    "sgmc_set_option": [_int, _int],
     "sgmc_device_count": [C.POINTER(_int)],
     "sgmc_set_device": [_int],
     "sgmc_device_info": [_int, C.POINTER(_int), C.POINTER(_int),
@@ -88,6 +89,7 @@ PROTOTYPES = {
 SPECIAL = {
     "sgmc_last_error": ([], C.c_char_p),
     "sgmc_version": ([], _int),
+    "sgmc_get_option": ([_int], _int),
     "sgmc_launch_count": ([], C.c_ulonglong),
     "sgmc_nccl_available": ([], _int),
     "sgmc_glm_workspace_bytes": ([_i64, _i64, _i64, _int], _sz),

@@ -12,6 +12,7 @@ namespace sgmc {
 
 void set_error(const char* fmt, ...);
 extern std::atomic<unsigned long long> g_launches;
+int option(int which);
 
 inline int check_cuda(cudaError_t e, const char* what) {
   if (e != cudaSuccess) {

@@ -63,25 +63,38 @@ int plan_noise_launch(const LeafTable& t, int64_t n_chains, const void* kernel,
 // nA[q] belongs to element j0+q (valid if j0+q < half), nB[q] to element
 // half + j0 + q (valid if that is < size).
 template <int LAYOUT>
+__device__ __forceinline__ void pair_bits(Key lk, uint32_t j, uint32_t half,
+                                          uint32_t size, uint32_t& wa,
+                                          uint32_t& wb) {
+  if (LAYOUT == 0) {
+    wa = j;
+    wb = (j + half < size) ? j + half : 0u;
+    threefry2x32(lk, wa, wb);
+  } else {
+    uint32_t a0 = 0u, a1 = j;
+    threefry2x32(lk, a0, a1);
+    wa = a0 ^ a1;
+    uint32_t b0 = 0u, b1 = j + half;
+    threefry2x32(lk, b0, b1);
+    wb = b0 ^ b1;
+  }
+}
+
+template <int LAYOUT>
 __device__ __forceinline__ void group_noise(Key lk, uint32_t j0, uint32_t half,
                                             uint32_t size, float nA[4],
                                             float nB[4]) {
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
-    const uint32_t j = j0 + q;
-    if (LAYOUT == 0) {
-      uint32_t x0 = j;
-      uint32_t x1 = (j + half < size) ? j + half : 0u;
-      threefry2x32(lk, x0, x1);
-      nA[q] = bits_to_normal(x0);
-      nB[q] = bits_to_normal(x1);
-    } else {
-      uint32_t a0 = 0u, a1 = j;
-      threefry2x32(lk, a0, a1);
-      nA[q] = bits_to_normal(a0 ^ a1);
-      uint32_t b0 = 0u, b1 = j + half;
-      threefry2x32(lk, b0, b1);
-      nB[q] = bits_to_normal(b0 ^ b1);
+    NormalPartial pa, pb;
+    uint32_t wa, wb;
+    pair_bits<LAYOUT>(lk, j0 + q, half, size, wa, wb);
+    nA[q] = normal_main(wa, pa);
+    nB[q] = normal_main(wb, pb);
+    // 0.34 % of the draws need erf_inv's w >= 5 polynomial
+    if (normal_is_tail(pa) | normal_is_tail(pb)) {
+      if (normal_is_tail(pa)) nA[q] = normal_tail(pa);
+      if (normal_is_tail(pb)) nB[q] = normal_tail(pb);
     }
   }
 }
@@ -100,7 +113,7 @@ __device__ __forceinline__ void group_noise(Key lk, uint32_t j0, uint32_t half,
 // eA/eB/e are element offsets inside the chain (for per-parameter vectors such
 // as mass or friction).
 template <int LAYOUT, class Op>
-__global__ void __launch_bounds__(kNoiseThreads)
+__global__ void __launch_bounds__(kNoiseThreads, 8)
 k_noise_pass(const __grid_constant__ LeafTable tab,
              const uint32_t* __restrict__ keys_in,
              uint32_t* __restrict__ keys_out, int64_t n_chains,
@@ -142,7 +155,10 @@ k_noise_pass(const __grid_constant__ LeafTable tab,
   __syncthreads();
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int64_t tile = t0 + warp; tile < t1; tile += kNoiseWarps) {
+  // rotate the first warp per CTA so the odd tiles of the CTAs spread evenly
+  // over the four SM sub-partitions (warp w runs on sub-partition w % 4)
+  const int wrot = (warp + blockIdx.x) & (kNoiseWarps - 1);
+  for (int64_t tile = t0 + wrot; tile < t1; tile += kNoiseWarps) {
     const int64_t c = tile / tab.tiles_per_chain;
     const uint32_t g = (uint32_t)(tile - c * tab.tiles_per_chain) * 32u + lane;
     float partial = 0.0f;

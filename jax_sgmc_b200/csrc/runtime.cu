@@ -10,6 +10,11 @@ namespace sgmc {
 static thread_local char g_err[512] = "";
 std::atomic<unsigned long long> g_launches{0};
 
+static std::atomic<int> g_options[SGMC_OPT_COUNT];
+int option(int which) {
+  return (which >= 0 && which < SGMC_OPT_COUNT) ? g_options[which].load() : 0;
+}
+
 void set_error(const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);
@@ -25,6 +30,12 @@ extern "C" {
 
 const char* sgmc_last_error(void) { return g_err; }
 int sgmc_version(void) { return 100; }
+int sgmc_set_option(int option, int value) {
+  SGMC_REQUIRE(option >= 0 && option < SGMC_OPT_COUNT, "unknown option %d", option);
+  g_options[option].store(value);
+  return 0;
+}
+int sgmc_get_option(int option) { return sgmc::option(option); }
 unsigned long long sgmc_launch_count(void) { return g_launches.load(); }
 
 int sgmc_device_count(int* count) {

@@ -58,7 +58,15 @@ int plan_noise_launch(const LeafTable& t, int64_t n_chains, const void* kernel,
   if (out->tiles_total == 0) return 0;
   // persistent grid: a multiple of the SM count, bounded by the work
   const int sms = sm_count();
-  int per_sm = 8;
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kNoiseThreads,
+                                                    2048) != cudaSuccess ||
+      per_sm < 1) {
+    cudaGetLastError();
+    per_sm = 4;
+  }
+  // one resident wave exactly: every CTA is live from the start, tiles are
+  // dealt evenly, nothing is left for a ragged second wave
   int64_t grid = (int64_t)sms * per_sm;
   if (grid > out->tiles_total) grid = out->tiles_total;
   for (;;) {
@@ -74,7 +82,6 @@ int plan_noise_launch(const LeafTable& t, int64_t n_chains, const void* kernel,
     grid = grid * 2 > out->tiles_total ? out->tiles_total : grid * 2;
   }
   out->grid = (int)grid;
-  (void)kernel;
   return 0;
 }
 
@@ -120,7 +127,12 @@ struct NormalLikeOp {
 
 // ---- SGLD / pSGLD -----------------------------------------------------------
 // integrator.py:882-912; adaption.py:270-272, :289-291.
-template <bool RMS>
+// FAST = false: IEEE sqrt / reciprocal and unfused mul/add, bit-identical to the
+// oracle given the same gradient.  FAST = true (default at run time, see
+// sgmc_set_option): MUFU rsqrt / rcp / sqrt approximations (<= 2 ulp) and FMA
+// contraction in the preconditioner arithmetic only -- the noise stays
+// bit-exact; trajectories stay within the 1e-5 parity tolerance.
+template <bool RMS, bool FAST>
 struct SgldOp {
   float* theta;
   float* v;
@@ -140,12 +152,22 @@ struct SgldOp {
     const float sg = __fmul_rn(neg_eps, g);
     const float sn = __fmul_rn(ns, xi);
     float delta;
-    if (RMS) {
+    if (RMS && FAST) {
+      vv = fmaf(alpha, vv, one_m_alpha * (g * g));
+      float s, G, S;
+      asm("sqrt.approx.f32 %0, %1;" : "=f"(s) : "f"(vv));
+      const float den = lmbd + s;
+      asm("rcp.approx.f32 %0, %1;" : "=f"(G) : "f"(den));
+      asm("rsqrt.approx.f32 %0, %1;" : "=f"(S) : "f"(den));   // sqrt(1/den)
+      delta = fmaf(S, sn, G * sg);
+    } else if (RMS) {
       vv = __fadd_rn(__fmul_rn(alpha, vv),
                      __fmul_rn(one_m_alpha, __fmul_rn(g, g)));
       const float G = __frcp_rn(__fadd_rn(lmbd, __fsqrt_rn(vv)));
       const float S = __fsqrt_rn(G);
-      delta = __fadd_rn(__fadd_rn(0.0f, __fmul_rn(G, sg)), __fmul_rn(S, sn));
+      // (eps*Gamma + G*sg) + S*sn with Gamma == 0; the "0 +" only affects the
+      // sign of an exact zero and is dropped.
+      delta = __fadd_rn(__fmul_rn(G, sg), __fmul_rn(S, sn));
     } else {
       delta = __fadd_rn(sg, sn);
     }
@@ -449,15 +471,22 @@ static int sgld_common(void* stream, float* theta, float* v, const float* grad,
   // integrator.py:882-884: (-eps), sqrt(2*T*eps) in f32
   const float eps = step_size;
   const float ns = sqrtf((2.0f * temperature) * eps);
-  if (rms) {
-    SgldOp<true> op{theta, v, grad, temp_per_chain, eps, -eps, ns,
-                    alpha, 1.0f - alpha, lmbd};
+  if (rms && option(SGMC_OPT_EXACT_UPDATE_MATH)) {
+    SgldOp<true, false> op{theta, v, grad, temp_per_chain, eps, -eps, ns,
+                           alpha, 1.0f - alpha, lmbd};
     return launch_noise_pass((cudaStream_t)stream, tab, keys_in, keys_out,
                              n_chains, kKeySplit2, prng_layout, op,
                              "sgmc_sgld_rms_update");
   }
-  SgldOp<false> op{theta, nullptr, grad, temp_per_chain, eps, -eps, ns,
-                   0.f, 0.f, 0.f};
+  if (rms) {
+    SgldOp<true, true> op{theta, v, grad, temp_per_chain, eps, -eps, ns,
+                          alpha, 1.0f - alpha, lmbd};
+    return launch_noise_pass((cudaStream_t)stream, tab, keys_in, keys_out,
+                             n_chains, kKeySplit2, prng_layout, op,
+                             "sgmc_sgld_rms_update");
+  }
+  SgldOp<false, false> op{theta, nullptr, grad, temp_per_chain, eps, -eps, ns,
+                          0.f, 0.f, 0.f};
   return launch_noise_pass((cudaStream_t)stream, tab, keys_in, keys_out,
                            n_chains, kKeySplit2, prng_layout, op,
                            "sgmc_sgld_update");

@@ -228,5 +228,12 @@ def swap_rows(a: DeviceArray, b: DeviceArray, exchange: DeviceArray, stream=None
             row_bytes)
 
 
+OPT_EXACT_UPDATE_MATH = 0
+
+
+def set_option(option: int, value: int):
+  _lib.call("sgmc_set_option", int(option), int(value))
+
+
 def launch_count() -> int:
   return int(_lib.load().sgmc_launch_count())

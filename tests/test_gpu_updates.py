@@ -20,6 +20,16 @@ def _bits(a):
   return np.ascontiguousarray(a).view(np.uint32)
 
 
+@pytest.fixture
+def exact_math(gpu):
+  """IEEE-exact preconditioner arithmetic (SGMC_OPT_EXACT_UPDATE_MATH=1): the
+  mode in which pSGLD is bit-identical to the oracle."""
+  from jax_sgmc_b200 import ops
+  ops.set_option(ops.OPT_EXACT_UPDATE_MATH, 1)
+  yield
+  ops.set_option(ops.OPT_EXACT_UPDATE_MATH, 0)
+
+
 def _setup(C, sizes, seed=0):
   rng = np.random.default_rng(seed)
   P = sum(sizes)
@@ -32,7 +42,7 @@ def _setup(C, sizes, seed=0):
 @pytest.mark.parametrize("layout", LAYOUTS)
 @pytest.mark.parametrize("sizes", SIZES)
 @pytest.mark.parametrize("rms", [False, True])
-def test_sgld_step_bit_exact(gpu, sizes, rms, layout):
+def test_sgld_step_bit_exact(gpu, exact_math, sizes, rms, layout):
   from jax_sgmc_b200 import ops
   from jax_sgmc_b200.device import DeviceArray as DA
   C = 11
@@ -52,6 +62,29 @@ def test_sgld_step_bit_exact(gpu, sizes, rms, layout):
   assert np.array_equal(_bits(d_theta.numpy()), _bits(want_theta))
   if rms:
     assert np.array_equal(_bits(d_v.numpy()), _bits(want_v))
+
+
+@pytest.mark.parametrize("sizes", SIZES)
+def test_psgld_fast_math_within_tolerance(gpu, sizes):
+  """Default mode: SFU sqrt/rcp approximations in the RMSprop arithmetic.
+  v' stays within 1 ulp, theta' within rtol 2e-6 of the oracle; keys exact."""
+  from jax_sgmc_b200 import ops
+  from jax_sgmc_b200.device import DeviceArray as DA
+  assert ops._lib.load().sgmc_get_option(ops.OPT_EXACT_UPDATE_MATH) == 0
+  C = 11
+  theta, grad, keys = _setup(C, sizes)
+  v = np.abs(np.random.default_rng(1).standard_normal(theta.shape)).astype(np.float32) + 0.1
+  d_theta, d_v = DA.from_numpy(theta), DA.from_numpy(v)
+  d_kout = DA((C, 2), np.uint32)
+  ops.sgld_update(d_theta, DA.from_numpy(grad), DA.from_numpy(keys), d_kout,
+                  sizes, 0.0123, 1.7, v=d_v)
+  ks = prng.split(keys, 2)
+  xi = osgmc.random_tree_flat(ks[:, 1], sizes)
+  want_theta, want_v = osgmc.sgld_apply(theta, grad, xi, 0.0123, 1.7, v)
+  assert np.array_equal(d_kout.numpy(), ks[:, 0])
+  np.testing.assert_allclose(d_v.numpy(), want_v, rtol=2.5e-7)
+  delta = np.abs(want_theta - theta).max()
+  assert np.abs(d_theta.numpy() - want_theta).max() <= 2e-6 * delta + 1e-7
 
 
 def test_sgld_per_chain_temperature(gpu):
@@ -75,7 +108,7 @@ def test_sgld_per_chain_temperature(gpu):
 
 
 @pytest.mark.parametrize("rms", [False, True])
-def test_sgld_trajectory_bit_exact(gpu, rms):
+def test_sgld_trajectory_bit_exact(gpu, exact_math, rms):
   """200 chained steps with a decaying step size and a gradient that depends on
   the current position (computed on the host from the device state, so both
   sides see identical gradients): the whole trajectory must stay bit-exact."""
