@@ -1,14 +1,679 @@
-// Tensor-core (tcgen05) GLM potential path -- placeholder until the tcgen05
-// kernels land; fails loudly (no silent fallback to the SIMT path).
+// GLM stochastic potential + gradient on the 5th-generation tensor cores
+// (tcgen05 / TMEM / TMA), paths 1 and 2 of sgmc_glm_potential_grad.
+//
+// Replaces potential.minibatch_potential + its reverse-mode gradient
+// (jax_sgmc/potential.py:159-214; integrator.py:166,593,792) for the logistic
+// family when many chains share one minibatch (the reference default: every
+// chain's data key is PRNGKey(0), data/numpy_loader.py:124).  The work is two
+// dense contractions chains x features x batch:
+//     GEMM1  Z[C,n] = Theta[C,d] . Xb[n,d]^T     epilogue: ell, R = cot*dl/dz
+//     GEMM2  G[C,d] = R[C,n]     . Xb[n,d]       epilogue: + prior gradient
+// path 1 ("parity"): every f32 operand x is split as x*s = hi + lo with fp16
+//   hi, lo (s a power of two: per chain row for Theta, per tensor for Xb and
+//   R); three MMAs per k-step (hi*hi + hi*lo + lo*hi) accumulate in fp32 in
+//   TMEM -> ~2^-22 relative accuracy (the dropped lo*lo term), i.e. fp32-level
+//   parity with the reference at 3 tensor-core passes.
+// path 2 ("throughput"): single bf16 pass.
+//
+// Kernel anatomy (one 128x256 output tile per CTA, K streamed in 64-element
+// blocks): warp 0 = TMA producer (cp.async.bulk.tensor, 128B swizzle, mbarrier
+// expect_tx), warp 1 = single-thread tcgen05.mma issuer (accumulator 128 lanes
+// x 256 fp32 columns in TMEM), warp 2 = TMEM allocator; afterwards all 8 warps
+// run the epilogue (tcgen05.ld 32x32b.x32 -> registers -> link function ->
+// global).  Roofline: tensor pipe; algorithmic FLOPs 2*C*n*d per GEMM.
 #include "glm.cuh"
+
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+#include <mutex>
 
 namespace sgmc {
 
-size_t glm_tc_workspace_bytes(int64_t, int64_t, int64_t, int) { return 0; }
+constexpr int BM = 128, BN = 256, BK = 64;       // tile (elements)
+constexpr int kTcThreads = 256;
+constexpr uint32_t kTmemCols = 256;
 
-int glm_tc(cudaStream_t, const GlmArgs&, int path) {
-  set_error("GLM tensor-core path %d is not built in this library", path);
-  return 3;
+// ---------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map,
+                                            uint64_t* bar, int c_inner, int c_outer) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c_inner), "r"(c_outer)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                   smem_u32(smem_dst)), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols)
+               : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+// D[tmem] (+)= A[smem] . B[smem]^T, kind::f16 (fp16 / bf16 operands, fp32 acc)
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
+                                         uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on an mbarrier when all previously issued MMAs have completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::
+                   "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+        "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
+        "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]),
+        "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]),
+        "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, 128B-swizzled operand tile (rows x 64 two-byte elements = rows x 128 B):
+// canonical layout Swizzle<3,4,3> o ((8,m),(8,2)):((8,SBO),(1,1)) in 16 B units,
+// SBO = 1024 B between 8-row groups, LBO = 1 (ignored), version 1 (sm_100),
+// layout type 2 (SWIZZLE_128B).  cute/arch/mma_sm100_desc.hpp SmemDescriptor.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// kind::f16 instruction descriptor: fp32 accumulate, A/B format (0 fp16, 1 bf16),
+// both K-major, N>>3 at [17,23), M>>4 at [24,29).
+__host__ __device__ constexpr uint32_t make_idesc(int ab_format, int M, int N) {
+  return (1u << 4) | ((uint32_t)ab_format << 7) | ((uint32_t)ab_format << 10) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ---------------------------------------------------------------------------
+// Epilogues
+// ---------------------------------------------------------------------------
+struct TcLinkEpi {      // GEMM1: z -> ell (f32), R = cot*mask*dl/dz split to fp16
+  const float* theta; int64_t P; int aux_off;
+  const float* y; const int32_t* idx; const float* mask;
+  const float* row_scale;   // f32[C]: scale applied to Theta rows (1 for bf16)
+  const float* b_scale;     // device scalar: scale applied to Xb
+  float cot;
+  float r_scale;            // scale applied to R before the fp16 split
+  float* ell;               // f32[C][n]
+  __half* r_hi; __half* r_lo;          // fp16[C][n]  (path 1)
+  __nv_bfloat16* r_bf;                 // bf16[C][n]  (path 2)
+  int C, n;
+};
+
+struct TcGradEpi {      // GEMM2: G -> grad (adds -grad(prior)/T)
+  GlmArgs a;
+  const float* xt_scale;  // device scalar: scale applied to XbT
+  float r_scale;          // scale applied to R
+};
+
+template <bool SPLIT>
+__device__ __forceinline__ void epi_link_chunk(const TcLinkEpi& e, int row, int col0,
+                                               const uint32_t (&acc)[32],
+                                               const float* s_y, const float* s_mask,
+                                               int col_in_tile) {
+  if (row >= e.C) return;
+  const float inv = 1.0f / (e.row_scale[row] * __ldg(e.b_scale));
+  const float bias = e.aux_off >= 0 ? e.theta[(int64_t)row * e.P + e.aux_off] : 0.0f;
+  const GaussConst gc{1.f, 0.f};
+  float ellv[32], rv[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    const float z = __uint_as_float(acc[j]) * inv + bias;
+    float l, dz;
+    glm_link(kFamilyLogistic, z, s_y[col_in_tile + j], gc, l, dz);
+    ellv[j] = l;
+    rv[j] = dz * (e.cot * s_mask[col_in_tile + j]);
+  }
+  const int64_t base = (int64_t)row * e.n + col0;
+  const int valid = e.n - col0;            // columns of this chunk inside the matrix
+  if (valid >= 32) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 4)
+      *reinterpret_cast<float4*>(e.ell + base + j) =
+          make_float4(ellv[j], ellv[j + 1], ellv[j + 2], ellv[j + 3]);
+    if (SPLIT) {
+      __align__(16) __half hi[32], lo[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float s = rv[j] * e.r_scale;
+        hi[j] = __float2half_rn(s);
+        lo[j] = __float2half_rn(s - __half2float(hi[j]));
+      }
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) {
+        *reinterpret_cast<uint4*>(e.r_hi + base + j) = *reinterpret_cast<uint4*>(hi + j);
+        *reinterpret_cast<uint4*>(e.r_lo + base + j) = *reinterpret_cast<uint4*>(lo + j);
+      }
+    } else {
+      __align__(16) __nv_bfloat16 b[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) b[j] = __float2bfloat16_rn(rv[j]);
+#pragma unroll
+      for (int j = 0; j < 32; j += 8)
+        *reinterpret_cast<uint4*>(e.r_bf + base + j) = *reinterpret_cast<uint4*>(b + j);
+    }
+  } else {
+    for (int j = 0; j < valid; ++j) {
+      e.ell[base + j] = ellv[j];
+      if (SPLIT) {
+        const float s = rv[j] * e.r_scale;
+        const __half h = __float2half_rn(s);
+        e.r_hi[base + j] = h;
+        e.r_lo[base + j] = __float2half_rn(s - __half2float(h));
+      } else {
+        e.r_bf[base + j] = __float2bfloat16_rn(rv[j]);
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ void epi_grad_chunk(const TcGradEpi& e, int row, int col0,
+                                               const uint32_t (&acc)[32]) {
+  const GlmArgs& a = e.a;
+  if (row >= a.C) return;
+  const int d = a.spec.d;
+  const int64_t base = (int64_t)row * a.P + a.spec.w_off + col0;
+  const int valid = d - col0;
+  const float inv_scale = 1.0f / (e.r_scale * __ldg(e.xt_scale));
+  float g[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    g[j] = __uint_as_float(acc[j]) * inv_scale;
+    if (col0 + j < d) g[j] += prior_grad_term(a, row, a.spec.w_off + col0 + j);
+  }
+  if (valid >= 32 && ((a.P | a.spec.w_off) & 3) == 0 &&
+      (reinterpret_cast<uintptr_t>(a.grad) & 15u) == 0) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 4)
+      *reinterpret_cast<float4*>(a.grad + base + j) = make_float4(g[j], g[j + 1], g[j + 2], g[j + 3]);
+  } else {
+    for (int j = 0; j < 32 && j < valid; ++j) a.grad[base + j] = g[j];
+  }
+}
+
+// ---------------------------------------------------------------------------
+// The GEMM kernel.  TERMS = 3: operands (A_hi, A_lo) x (B_hi, B_lo), MMAs
+// hi*hi + hi*lo + lo*hi.  TERMS = 1: single operand pair.
+// EPI = 0: link epilogue, EPI = 1: gradient epilogue.
+// ---------------------------------------------------------------------------
+template <int TERMS>
+struct TcSmem {
+  static constexpr int kNA = TERMS == 3 ? 2 : 1;
+  static constexpr int kStageBytes = kNA * (BM * BK * 2) + kNA * (BN * BK * 2);
+  static constexpr int kStages = TERMS == 3 ? 2 : 4;
+  static constexpr int kBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ +
+                                2 * BN * 4 /*y, mask*/;
+};
+
+template <int TERMS, int EPI, int ABFMT>
+__global__ void __launch_bounds__(kTcThreads, 1)
+k_glm_tc_gemm(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+              const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1,
+              int num_k_blocks, const TcLinkEpi link, const TcGradEpi gradp) {
+  using S = TcSmem<TERMS>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(
+      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* tiles = smem;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::kStages * S::kStageBytes);
+  uint64_t* empty_bar = full_bar + S::kStages;
+  uint64_t* tmem_full_bar = empty_bar + S::kStages;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  float* s_y = reinterpret_cast<float*>(smem + S::kStages * S::kStageBytes + 256);
+  float* s_mask = s_y + BN;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA0);
+    tma_prefetch_desc(&tmB0);
+    if (TERMS == 3) {
+      tma_prefetch_desc(&tmA1);
+      tma_prefetch_desc(&tmB1);
+    }
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < S::kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_ptr, kTmemCols);
+  if (EPI == 0) {   // per-column observation data of this tile
+    const int col = n0 + threadIdx.x;
+    float yv = 0.f, mv = 0.f;
+    if (threadIdx.x < BN && col < link.n) {
+      yv = link.y[link.idx ? link.idx[col] : col];
+      mv = link.mask ? link.mask[col] : 1.0f;
+    }
+    if (threadIdx.x < BN) {
+      s_y[threadIdx.x] = yv;
+      s_mask[threadIdx.x] = mv;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0 && lane == 0) {
+    // ===== TMA producer =====
+    for (int kb = 0; kb < num_k_blocks; ++kb) {
+      const int s = kb % S::kStages;
+      const uint32_t ph = (kb / S::kStages) & 1;
+      mbar_wait(&empty_bar[s], ph ^ 1);
+      uint8_t* st = tiles + s * S::kStageBytes;
+      mbar_expect_tx(&full_bar[s], S::kStageBytes);
+      tma_load_2d(st, &tmA0, &full_bar[s], kb * BK, m0);
+      if (TERMS == 3) tma_load_2d(st + BM * BK * 2, &tmA1, &full_bar[s], kb * BK, m0);
+      uint8_t* sb = st + S::kNA * BM * BK * 2;
+      tma_load_2d(sb, &tmB0, &full_bar[s], kb * BK, n0);
+      if (TERMS == 3) tma_load_2d(sb + BN * BK * 2, &tmB1, &full_bar[s], kb * BK, n0);
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ===== MMA issuer =====
+    constexpr uint32_t idesc = make_idesc(ABFMT, BM, BN);
+    for (int kb = 0; kb < num_k_blocks; ++kb) {
+      const int s = kb % S::kStages;
+      const uint32_t ph = (kb / S::kStages) & 1;
+      mbar_wait(&full_bar[s], ph);
+      tc_fence_after();
+      const uint32_t a0 = smem_u32(tiles + s * S::kStageBytes);
+      const uint32_t a1 = a0 + BM * BK * 2;
+      const uint32_t b0 = a0 + S::kNA * BM * BK * 2;
+      const uint32_t b1 = b0 + BN * BK * 2;
+#pragma unroll
+      for (int k = 0; k < BK / 16; ++k) {
+        // advancing K by 16 elements (32 B) inside the 128 B swizzle atom
+        const uint64_t da0 = make_smem_desc(a0 + k * 32), db0 = make_smem_desc(b0 + k * 32);
+        if (TERMS == 3) {
+          const uint64_t da1 = make_smem_desc(a1 + k * 32), db1 = make_smem_desc(b1 + k * 32);
+          umma_f16(tmem_base, da1, db0, idesc, (kb | k) != 0);   // lo*hi
+          umma_f16(tmem_base, da0, db1, idesc, 1);               // hi*lo
+          umma_f16(tmem_base, da0, db0, idesc, 1);               // hi*hi
+        } else {
+          umma_f16(tmem_base, da0, db0, idesc, (kb | k) != 0);
+        }
+      }
+      umma_commit(&empty_bar[s]);          // frees the smem stage when the MMAs retire
+    }
+    umma_commit(tmem_full_bar);            // accumulator complete
+  }
+
+  // ===== epilogue: all 8 warps =====
+  __syncwarp();
+  mbar_wait(tmem_full_bar, 0);
+  tc_fence_after();
+  {
+    const int q = warp & 3;                 // TMEM lane quarter this warp may access
+    const int hcol = (warp >> 2) * (BN / 2);
+    const int row = m0 + q * 32 + lane;
+#pragma unroll 1
+    for (int c = 0; c < BN / 2; c += 32) {
+      uint32_t acc[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(hcol + c), acc);
+      const int col0 = n0 + hcol + c;
+      if (EPI == 0) {
+        if (col0 < link.n)
+          epi_link_chunk<TERMS == 3>(link, row, col0, acc, s_y, s_mask, hcol + c);
+      } else {
+        if (col0 < gradp.a.spec.d) epi_grad_chunk(gradp, row, col0, acc);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+// ---------------------------------------------------------------------------
+// Operand preparation kernels
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ float pow2_scale_for(float absmax) {
+  // power of two s with absmax*s in [2^12, 2^13); 1 for absmax == 0 / non-finite
+  if (!(absmax > 0.0f) || isinf(absmax)) return 1.0f;
+  int e;
+  frexpf(absmax, &e);                     // absmax = m * 2^e, m in [0.5, 1)
+  return ldexpf(1.0f, 13 - e);
+}
+
+// One warp per chain row: row absmax -> power-of-two scale -> fp16 hi/lo split
+// (SPLIT) or plain bf16 conversion.  Theta row = theta[c*P + w_off .. + d).
+template <bool SPLIT>
+__global__ void k_theta_prepare(const float* __restrict__ theta, int64_t P, int w_off, int d,
+                                int C, void* __restrict__ out_hi, __half* __restrict__ out_lo,
+                                float* __restrict__ row_scale) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= C) return;
+  const float* src = theta + (int64_t)warp * P + w_off;
+  float s = 1.0f;
+  if (SPLIT) {
+    float m = 0.f;
+    for (int j = lane; j < d; j += 32) m = fmaxf(m, fabsf(src[j]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    s = pow2_scale_for(m);
+  }
+  if (lane == 0) row_scale[warp] = s;
+  for (int j = lane; j < d; j += 32) {
+    const float x = src[j] * s;
+    if (SPLIT) {
+      const __half h = __float2half_rn(x);
+      reinterpret_cast<__half*>(out_hi)[(int64_t)warp * d + j] = h;
+      out_lo[(int64_t)warp * d + j] = __float2half_rn(x - __half2float(h));
+    } else {
+      reinterpret_cast<__nv_bfloat16*>(out_hi)[(int64_t)warp * d + j] = __float2bfloat16_rn(x);
+    }
+  }
+}
+
+__global__ void k_absmax_gather(const float* __restrict__ X, const int32_t* __restrict__ idx,
+                                int n, int d, uint32_t* __restrict__ out_bits) {
+  float m = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < (int64_t)n * d;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i / d), c = (int)(i - (int64_t)r * d);
+    const int64_t row = idx ? idx[r] : r;
+    m = fmaxf(m, fabsf(X[row * d + c]));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(out_bits, __float_as_uint(m));  // m >= 0
+}
+
+// Gather minibatch rows, scale, split, and write both Xb [n][d] and its
+// transpose XbT [d][n] (32x32 tiles through shared memory).
+template <bool SPLIT>
+__global__ void k_x_prepare(const float* __restrict__ X, const int32_t* __restrict__ idx, int n,
+                            int d, const uint32_t* __restrict__ absmax_bits, float static_absmax,
+                            void* __restrict__ xb_hi, __half* __restrict__ xb_lo,
+                            void* __restrict__ xt_hi, __half* __restrict__ xt_lo,
+                            float* __restrict__ scale_out) {
+  __shared__ float tile[32][33];
+  float s = 1.0f;
+  if (SPLIT)
+    s = pow2_scale_for(static_absmax > 0.f ? static_absmax : __uint_as_float(*absmax_bits));
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 && threadIdx.y == 0) *scale_out = s;
+  const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    float v = 0.f;
+    if (r < n && c < d) {
+      const int64_t row = idx ? idx[r] : r;
+      v = X[row * d + c] * s;
+      if (SPLIT) {
+        const __half h = __float2half_rn(v);
+        reinterpret_cast<__half*>(xb_hi)[(int64_t)r * d + c] = h;
+        xb_lo[(int64_t)r * d + c] = __float2half_rn(v - __half2float(h));
+      } else {
+        reinterpret_cast<__nv_bfloat16*>(xb_hi)[(int64_t)r * d + c] = __float2bfloat16_rn(v);
+      }
+    }
+    tile[i][threadIdx.x] = v;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, r = r0 + threadIdx.x;      // transposed: row = feature c
+    if (c < d && r < n) {
+      const float v = tile[threadIdx.x][i];
+      if (SPLIT) {
+        const __half h = __float2half_rn(v);
+        reinterpret_cast<__half*>(xt_hi)[(int64_t)c * n + r] = h;
+        xt_lo[(int64_t)c * n + r] = __float2half_rn(v - __half2float(h));
+      } else {
+        reinterpret_cast<__nv_bfloat16*>(xt_hi)[(int64_t)c * n + r] = __float2bfloat16_rn(v);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Host side
+// ---------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) ==
+            cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  });
+  return fn;
+}
+
+// 2-D row-major [rows][cols] matrix of 2-byte elements, box = [box_rows][64].
+static int make_map(CUtensorMap* m, const void* ptr, int bf16, int64_t rows, int64_t cols,
+                    int box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  SGMC_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled unavailable");
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)cols * 2};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16,
+                  2, const_cast<void*>(ptr), gdim, gstr, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  SGMC_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return 0;
+}
+
+struct TcWorkspace {
+  void* th_hi; __half* th_lo; float* row_scale;
+  void* xb_hi; __half* xb_lo; void* xt_hi; __half* xt_lo;
+  void* r_hi; __half* r_lo;
+  uint32_t* absmax_bits; float* x_scale;
+};
+
+static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+static size_t carve(TcWorkspace* w, uint8_t* base, int64_t C, int64_t n, int64_t d) {
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    uint8_t* p = base ? base + off : nullptr;
+    off += align256(bytes);
+    return p;
+  };
+  void* th_hi = take((size_t)C * d * 2);
+  void* th_lo = take((size_t)C * d * 2);
+  void* rs = take((size_t)C * 4);
+  void* xb_hi = take((size_t)n * d * 2);
+  void* xb_lo = take((size_t)n * d * 2);
+  void* xt_hi = take((size_t)n * d * 2);
+  void* xt_lo = take((size_t)n * d * 2);
+  void* r_hi = take((size_t)C * n * 2);
+  void* r_lo = take((size_t)C * n * 2);
+  void* am = take(256);
+  if (w) {
+    w->th_hi = th_hi; w->th_lo = (__half*)th_lo; w->row_scale = (float*)rs;
+    w->xb_hi = xb_hi; w->xb_lo = (__half*)xb_lo; w->xt_hi = xt_hi; w->xt_lo = (__half*)xt_lo;
+    w->r_hi = r_hi; w->r_lo = (__half*)r_lo;
+    w->absmax_bits = (uint32_t*)am; w->x_scale = (float*)am + 1;
+  }
+  return off;
+}
+
+size_t glm_tc_workspace_bytes(int64_t n_chains, int64_t batch_size, int64_t d, int) {
+  return carve(nullptr, nullptr, n_chains, batch_size, d) + 256;
+}
+
+template <int TERMS, int EPI, int ABFMT>
+static int launch_gemm(cudaStream_t stream, const CUtensorMap& a0, const CUtensorMap& a1,
+                       const CUtensorMap& b0, const CUtensorMap& b1, int M, int N, int K,
+                       const TcLinkEpi& link, const TcGradEpi& gradp, const char* name) {
+  using S = TcSmem<TERMS>;
+  auto kfn = k_glm_tc_gemm<TERMS, EPI, ABFMT>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (check_cuda(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        S::kBytes), "cudaFuncSetAttribute"))
+      return 1;
+    attr_set = true;
+  }
+  dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM);
+  kfn<<<grid, kTcThreads, S::kBytes, stream>>>(a0, a1, b0, b1, (K + BK - 1) / BK, link, gradp);
+  return post_launch(name);
+}
+
+int glm_tc(cudaStream_t stream, const GlmArgs& a, int path) {
+  const int64_t C = a.C, n = a.n;
+  const int d = a.spec.d;
+  SGMC_REQUIRE(a.spec.family == kFamilyLogistic,
+               "tensor-core path supports the logistic family (use path 0)");
+  SGMC_REQUIRE(a.spec.aux_off < 0, "tensor-core path: bias term not supported (use path 0)");
+  SGMC_REQUIRE(d % 8 == 0 && n % 8 == 0, "tensor-core path needs d %% 8 == 0 and n %% 8 == 0");
+  const bool split = path == 1;
+  TcWorkspace w;
+  uint8_t* base = reinterpret_cast<uint8_t*>(
+      (reinterpret_cast<uintptr_t>(a.tc_ws) + 255) & ~(uintptr_t)255);
+  carve(&w, base, C, n, d);
+
+  // ---- operand preparation ------------------------------------------------
+  {
+    const int wpb = 8;
+    dim3 grid((unsigned)((C + wpb - 1) / wpb));
+    if (split)
+      k_theta_prepare<true><<<grid, wpb * 32, 0, stream>>>(a.theta, a.P, a.spec.w_off, d, (int)C,
+                                                           w.th_hi, w.th_lo, w.row_scale);
+    else
+      k_theta_prepare<false><<<grid, wpb * 32, 0, stream>>>(a.theta, a.P, a.spec.w_off, d, (int)C,
+                                                            w.th_hi, w.th_lo, w.row_scale);
+    if (post_launch("k_theta_prepare")) return 1;
+  }
+  if (split) {
+    if (check_cuda(cudaMemsetAsync(w.absmax_bits, 0, 4, stream), "memset")) return 1;
+    k_absmax_gather<<<sm_count(), 256, 0, stream>>>(a.X, a.idx, (int)n, d, w.absmax_bits);
+    if (post_launch("k_absmax_gather")) return 1;
+  }
+  {
+    dim3 grid((d + 31) / 32, (unsigned)((n + 31) / 32)), block(32, 8);
+    if (split)
+      k_x_prepare<true><<<grid, block, 0, stream>>>(a.X, a.idx, (int)n, d, w.absmax_bits, 0.f,
+                                                    w.xb_hi, w.xb_lo, w.xt_hi, w.xt_lo, w.x_scale);
+    else
+      k_x_prepare<false><<<grid, block, 0, stream>>>(a.X, a.idx, (int)n, d, w.absmax_bits, 0.f,
+                                                     w.xb_hi, w.xb_lo, w.xt_hi, w.xt_lo, w.x_scale);
+    if (post_launch("k_x_prepare")) return 1;
+  }
+  // The Xb scale is computed on the device (k_x_prepare) and read by the
+  // epilogues through a device scalar, so the whole op stays sync-free.
+  // R scale: |R| <= |cot| for the logistic family (|dl/dz| <= 1, mask in [0,1]).
+  float r_scale = 1.0f;
+  if (split) {
+    int e;
+    frexpf(fabsf(a.cot) > 0.f ? fabsf(a.cot) : 1.0f, &e);
+    r_scale = ldexpf(1.0f, 12 - e);
+  }
+
+  TcLinkEpi link{};
+  link.theta = a.theta; link.P = a.P; link.aux_off = a.spec.aux_off;
+  link.y = a.y; link.idx = a.idx; link.mask = a.mask;
+  link.row_scale = w.row_scale; link.b_scale = w.x_scale;
+  link.cot = a.cot; link.r_scale = r_scale;
+  link.ell = a.ell;
+  link.r_hi = (__half*)w.r_hi; link.r_lo = w.r_lo; link.r_bf = (__nv_bfloat16*)w.r_hi;
+  link.C = (int)C; link.n = (int)n;
+  TcGradEpi gradp{};
+  gradp.a = a;
+  gradp.xt_scale = w.x_scale;
+  gradp.r_scale = r_scale;
+
+  CUtensorMap mA0, mA1, mB0, mB1;
+  // ---- GEMM1: Z[C,n] = Theta[C,d] . Xb[n,d]^T ------------------------------
+  if (make_map(&mA0, w.th_hi, !split, C, d, BM)) return 2;
+  if (make_map(&mB0, w.xb_hi, !split, n, d, BN)) return 2;
+  if (split) {
+    if (make_map(&mA1, w.th_lo, 0, C, d, BM)) return 2;
+    if (make_map(&mB1, w.xb_lo, 0, n, d, BN)) return 2;
+    if (launch_gemm<3, 0, 0>(stream, mA0, mA1, mB0, mB1, (int)C, (int)n, d, link, gradp,
+                             "k_glm_tc_gemm<split,link>")) return 1;
+  } else {
+    if (launch_gemm<1, 0, 1>(stream, mA0, mA0, mB0, mB0, (int)C, (int)n, d, link, gradp,
+                             "k_glm_tc_gemm<bf16,link>")) return 1;
+  }
+  // ---- U, var(ell) ------------------------------------------------------------
+  if (glm_finalize(stream, a)) return 1;
+  if (!a.grad) return 0;
+  // ---- GEMM2: G[C,d] = R[C,n] . XbT[d,n]^T ---------------------------------------
+  if (make_map(&mA0, w.r_hi, !split, C, n, BM)) return 2;
+  if (make_map(&mB0, w.xt_hi, !split, d, n, BN)) return 2;
+  if (split) {
+    if (make_map(&mA1, w.r_lo, 0, C, n, BM)) return 2;
+    if (make_map(&mB1, w.xt_lo, 0, d, n, BN)) return 2;
+    if (launch_gemm<3, 1, 0>(stream, mA0, mA1, mB0, mB1, (int)C, d, (int)n, link, gradp,
+                             "k_glm_tc_gemm<split,grad>")) return 1;
+  } else {
+    if (launch_gemm<1, 1, 1>(stream, mA0, mA0, mB0, mB0, (int)C, d, (int)n, link, gradp,
+                             "k_glm_tc_gemm<bf16,grad>")) return 1;
+  }
+  return 0;
 }
 
 }  // namespace sgmc

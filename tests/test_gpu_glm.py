@@ -164,3 +164,65 @@ def test_sgld_logistic_trajectory_1000_steps(gpu, rms):
   np.testing.assert_allclose(d_var.numpy(), st.variance, rtol=1e-4)
   assert np.array_equal(d_k[K % 2].numpy(), st.key)
   assert np.array_equal(d_dk[K % 2].numpy(), dk)
+
+
+# ---- tensor-core (tcgen05) paths ------------------------------------------------
+
+def _tc_case(C, n, d, seed=0):
+  X, y, _ = odata.logistic_dataset(3000, d, seed=seed)
+  rng = np.random.default_rng(C + n + d)
+  theta = (rng.standard_normal((C, d)) * 0.7).astype(np.float32)
+  theta[0] *= 1e-3          # rows of very different magnitude (per-row scaling)
+  theta[-1] *= 30.0
+  idx = rng.integers(0, 3000, n)
+  return X, y, theta, idx
+
+
+@pytest.mark.parametrize("C,n,d", [(128, 256, 64), (256, 512, 256), (130, 264, 72),
+                                   (512, 1024, 1024)])
+def test_logistic_tc_parity_path(gpu, C, n, d):
+  """path 1: fp16 hi/lo split operands, 3 MMAs per k-step, fp32 accumulation in
+  TMEM: fp32-level agreement with the oracle (rtol 1e-5)."""
+  from jax_sgmc_b200 import ops
+  from jax_sgmc_b200.device import DeviceArray as DA
+  X, y, theta, idx = _tc_case(C, n, d)
+  spec = ops.glm_spec("logistic", d, w_off=0, prior="gaussian", prior_off=0,
+                      prior_size=d, prior_scale=10.0)
+  U, var, g, ell = _run(ops, DA, spec, theta, X, y, idx, 3000, path="tc_parity")
+  pot = osgmc.minibatch_potential(osgmc.Logistic(d, 0),
+                                  osgmc.Prior("gaussian", 0, d, 10.0))
+  wU, well, wg = pot(theta, (X[idx], y[idx]), 3000)
+  np.testing.assert_allclose(ell, well, rtol=2e-5, atol=2e-5)
+  np.testing.assert_allclose(U, wU, rtol=1e-5)
+  np.testing.assert_allclose(var, well.astype(np.float64).var(axis=1), rtol=1e-4)
+  _grad_close(g, wg, 1e-5)
+  # and against the fp32 SIMT path on the device
+  U0, var0, g0, ell0 = _run(ops, DA, spec, theta, X, y, idx, 3000, path="simt")
+  np.testing.assert_allclose(U, U0, rtol=1e-5)
+  _grad_close(g, g0, 1e-5)
+
+
+@pytest.mark.parametrize("C,n,d", [(128, 256, 64), (512, 1024, 1024)])
+def test_logistic_tc_throughput_path(gpu, C, n, d):
+  """path 2: single bf16 pass -- graded on posterior moments, not on rtol 1e-5;
+  here only a sanity bound (bf16 operand rounding ~ 2^-9)."""
+  from jax_sgmc_b200 import ops
+  from jax_sgmc_b200.device import DeviceArray as DA
+  X, y, theta, idx = _tc_case(C, n, d)
+  spec = ops.glm_spec("logistic", d, w_off=0, prior="gaussian", prior_off=0,
+                      prior_size=d, prior_scale=10.0)
+  U, var, g, ell = _run(ops, DA, spec, theta, X, y, idx, 3000, path="tc_throughput")
+  pot = osgmc.minibatch_potential(osgmc.Logistic(d, 0),
+                                  osgmc.Prior("gaussian", 0, d, 10.0))
+  wU, well, wg = pot(theta, (X[idx], y[idx]), 3000)
+  np.testing.assert_allclose(U, wU, rtol=2e-2)
+  _grad_close(g, wg, 3e-2)
+
+
+def test_tc_path_rejects_unsupported(gpu):
+  from jax_sgmc_b200 import _lib, ops
+  from jax_sgmc_b200.device import DeviceArray as DA
+  X, y, theta, idx = _tc_case(16, 24, 12)          # d % 8 != 0
+  spec = ops.glm_spec("logistic", 12, w_off=0)
+  with pytest.raises(_lib.SgmcError):
+    _run(ops, DA, spec, theta, X, y, idx, 3000, path="tc_parity")
