@@ -20,6 +20,7 @@ struct GlmArgs {
   float* grad;            // f32[C][P] or null
   float* R;               // f32[C][n] scratch: cot * d ell/dz
   float* ell;             // f32[C][n]
+  bool ell_requested;     // the caller passed an ell output buffer
   float* tc_ws;           // extra scratch of the tensor-core path
 };
 

@@ -265,6 +265,7 @@ int sgmc_glm_potential_grad(void* stream, const sgmc_glm_spec* spec,
       (reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255);
   a.R = ws;
   a.ell = ell ? ell : ws + (size_t)n_chains * batch_size;
+  a.ell_requested = ell != nullptr;
   a.tc_ws = ws + 2 * (size_t)n_chains * batch_size;
   // cotangent of every ell_i: (1/T) * (-N) / n    (potential.py:183,210)
   a.cot = (-(float)observation_count / (float)batch_size) / spec->temperature;

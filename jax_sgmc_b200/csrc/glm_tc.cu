@@ -18,9 +18,11 @@
 // Kernel anatomy (one 128x256 output tile per CTA, K streamed in 64-element
 // blocks): warp 0 = TMA producer (cp.async.bulk.tensor, 128B swizzle, mbarrier
 // expect_tx), warp 1 = single-thread tcgen05.mma issuer (accumulator 128 lanes
-// x 256 fp32 columns in TMEM), warp 2 = TMEM allocator; afterwards all 8 warps
-// run the epilogue (tcgen05.ld 32x32b.x32 -> registers -> link function ->
-// global).  Roofline: tensor pipe; algorithmic FLOPs 2*C*n*d per GEMM.
+// x 256 fp32 columns in TMEM), warp 2 = TMEM allocator; afterwards all 16 warps
+// run the epilogue: tcgen05.ld 32x32b.x32 -> registers -> link function /
+// per-row likelihood statistics -> 32x32 transpose through the (now idle)
+// pipeline shared memory -> fully coalesced global stores.
+// Roofline: tensor pipe; algorithmic FLOPs 2*C*n*d per GEMM.
 #include "glm.cuh"
 
 #include <cuda.h>
@@ -32,7 +34,8 @@
 namespace sgmc {
 
 constexpr int BM = 128, BN = 256, BK = 64;       // tile (elements)
-constexpr int kTcThreads = 256;
+constexpr int kTcThreads = 512;               // 16 warps
+constexpr int kTcWarps = kTcThreads / 32;
 constexpr uint32_t kTmemCols = 256;
 
 // ---------------------------------------------------------------------------
@@ -144,113 +147,48 @@ __host__ __device__ constexpr uint32_t make_idesc(int ab_format, int M, int N) {
 // ---------------------------------------------------------------------------
 // Epilogues
 // ---------------------------------------------------------------------------
-struct TcLinkEpi {      // GEMM1: z -> ell (f32), R = cot*mask*dl/dz split to fp16
+// Per-row partial likelihood statistics of one CTA tile (combined by
+// k_glm_finalize_parts): {count, mean, M2, masked_sum}.
+constexpr int kStatFields = 4;
+
+struct TcLinkEpi {      // GEMM1: z -> ell statistics, R = cot*mask*dl/dz as fp16 hi/lo
   const float* theta; int64_t P; int aux_off;
   const float* y; const int32_t* idx; const float* mask;
   const float* row_scale;   // f32[C]: scale applied to Theta rows (1 for bf16)
   const float* b_scale;     // device scalar: scale applied to Xb
   float cot;
   float r_scale;            // scale applied to R before the fp16 split
-  float* ell;               // f32[C][n]
+  float* ell;               // f32[C][n] or null (only when the caller wants it)
+  float* stats;             // f32[C][parts][4]
+  int parts;
   __half* r_hi; __half* r_lo;          // fp16[C][n]  (path 1)
   __nv_bfloat16* r_bf;                 // bf16[C][n]  (path 2)
   int C, n;
 };
 
 struct TcGradEpi {      // GEMM2: G -> grad (adds -grad(prior)/T)
-  GlmArgs a;
-  const float* xt_scale;  // device scalar: scale applied to XbT
-  float r_scale;          // scale applied to R
+  const float* theta; float* grad; int64_t P; int w_off; int d; int C;
+  int prior_lo, prior_hi;   // flat index range of the gaussian prior (empty if none)
+  float prior_coef;         // 1 / (scale^2 * T)
+  const float* xt_scale;    // device scalar: scale applied to XbT
+  float r_scale;            // scale applied to R
 };
 
-template <bool SPLIT>
-__device__ __forceinline__ void epi_link_chunk(const TcLinkEpi& e, int row, int col0,
-                                               const uint32_t (&acc)[32],
-                                               const float* s_y, const float* s_mask,
-                                               int col_in_tile) {
-  if (row >= e.C) return;
-  const float inv = 1.0f / (e.row_scale[row] * __ldg(e.b_scale));
-  const float bias = e.aux_off >= 0 ? e.theta[(int64_t)row * e.P + e.aux_off] : 0.0f;
-  const GaussConst gc{1.f, 0.f};
-  float ellv[32], rv[32];
-#pragma unroll
-  for (int j = 0; j < 32; ++j) {
-    const float z = __uint_as_float(acc[j]) * inv + bias;
-    float l, dz;
-    glm_link(kFamilyLogistic, z, s_y[col_in_tile + j], gc, l, dz);
-    ellv[j] = l;
-    rv[j] = dz * (e.cot * s_mask[col_in_tile + j]);
-  }
-  const int64_t base = (int64_t)row * e.n + col0;
-  const int valid = e.n - col0;            // columns of this chunk inside the matrix
-  if (valid >= 32) {
-#pragma unroll
-    for (int j = 0; j < 32; j += 4)
-      *reinterpret_cast<float4*>(e.ell + base + j) =
-          make_float4(ellv[j], ellv[j + 1], ellv[j + 2], ellv[j + 3]);
-    if (SPLIT) {
-      __align__(16) __half hi[32], lo[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const float s = rv[j] * e.r_scale;
-        hi[j] = __float2half_rn(s);
-        lo[j] = __float2half_rn(s - __half2float(hi[j]));
-      }
-#pragma unroll
-      for (int j = 0; j < 32; j += 8) {
-        *reinterpret_cast<uint4*>(e.r_hi + base + j) = *reinterpret_cast<uint4*>(hi + j);
-        *reinterpret_cast<uint4*>(e.r_lo + base + j) = *reinterpret_cast<uint4*>(lo + j);
-      }
-    } else {
-      __align__(16) __nv_bfloat16 b[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) b[j] = __float2bfloat16_rn(rv[j]);
-#pragma unroll
-      for (int j = 0; j < 32; j += 8)
-        *reinterpret_cast<uint4*>(e.r_bf + base + j) = *reinterpret_cast<uint4*>(b + j);
-    }
-  } else {
-    for (int j = 0; j < valid; ++j) {
-      e.ell[base + j] = ellv[j];
-      if (SPLIT) {
-        const float s = rv[j] * e.r_scale;
-        const __half h = __float2half_rn(s);
-        e.r_hi[base + j] = h;
-        e.r_lo[base + j] = __float2half_rn(s - __half2float(h));
-      } else {
-        e.r_bf[base + j] = __float2bfloat16_rn(rv[j]);
-      }
-    }
-  }
-}
-
-__device__ __forceinline__ void epi_grad_chunk(const TcGradEpi& e, int row, int col0,
-                                               const uint32_t (&acc)[32]) {
-  const GlmArgs& a = e.a;
-  if (row >= a.C) return;
-  const int d = a.spec.d;
-  const int64_t base = (int64_t)row * a.P + a.spec.w_off + col0;
-  const int valid = d - col0;
-  const float inv_scale = 1.0f / (e.r_scale * __ldg(e.xt_scale));
-  float g[32];
-#pragma unroll
-  for (int j = 0; j < 32; ++j) {
-    g[j] = __uint_as_float(acc[j]) * inv_scale;
-    if (col0 + j < d) g[j] += prior_grad_term(a, row, a.spec.w_off + col0 + j);
-  }
-  if (valid >= 32 && ((a.P | a.spec.w_off) & 3) == 0 &&
-      (reinterpret_cast<uintptr_t>(a.grad) & 15u) == 0) {
-#pragma unroll
-    for (int j = 0; j < 32; j += 4)
-      *reinterpret_cast<float4*>(a.grad + base + j) = make_float4(g[j], g[j + 1], g[j + 2], g[j + 3]);
-  } else {
-    for (int j = 0; j < 32 && j < valid; ++j) a.grad[base + j] = g[j];
-  }
+// logistic link with SFU-based exp / log / reciprocal (abs. error ~1e-7):
+//   ell = y z - softplus(z),  dz = y - sigmoid(z)
+__device__ __forceinline__ void logistic_link_fast(float z, float y, float& ell, float& dz) {
+  const float e = __expf(-fabsf(z));
+  const float den = 1.0f + e;
+  // log1p(e): log(1+e) loses e below 2^-24; the series e - e^2/2 covers small e
+  const float lp = e > 1e-3f ? __logf(den) : e * (1.0f - 0.5f * e);
+  ell = y * z - (fmaxf(z, 0.0f) + lp);
+  const float rden = __fdividef(1.0f, den);
+  dz = y - (z >= 0.0f ? rden : e * rden);
 }
 
 // ---------------------------------------------------------------------------
 // The GEMM kernel.  TERMS = 3: operands (A_hi, A_lo) x (B_hi, B_lo), MMAs
-// hi*hi + hi*lo + lo*hi.  TERMS = 1: single operand pair.
+// lo*hi + hi*lo + hi*hi.  TERMS = 1: single operand pair.
 // EPI = 0: link epilogue, EPI = 1: gradient epilogue.
 // ---------------------------------------------------------------------------
 template <int TERMS>
@@ -258,8 +196,11 @@ struct TcSmem {
   static constexpr int kNA = TERMS == 3 ? 2 : 1;
   static constexpr int kStageBytes = kNA * (BM * BK * 2) + kNA * (BN * BK * 2);
   static constexpr int kStages = TERMS == 3 ? 2 : 4;
-  static constexpr int kBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ +
-                                2 * BN * 4 /*y, mask*/;
+  static constexpr int kPipeBytes = kStages * kStageBytes;
+  static constexpr int kAuxBytes = 256 /*barriers*/ + 2 * BN * 4 /*y, mask*/ +
+                                   4 * BM * kStatFields * 4 /*row stats*/;
+  static constexpr int kBytes = kPipeBytes + kAuxBytes + 1024 /*alignment slack*/;
+  static_assert(kPipeBytes >= kTcWarps * 32 * 33 * 4, "staging must fit in the pipeline smem");
 };
 
 template <int TERMS, int EPI, int ABFMT>
@@ -272,12 +213,13 @@ k_glm_tc_gemm(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
   uint8_t* smem = reinterpret_cast<uint8_t*>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* tiles = smem;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::kStages * S::kStageBytes);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::kPipeBytes);
   uint64_t* empty_bar = full_bar + S::kStages;
   uint64_t* tmem_full_bar = empty_bar + S::kStages;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
-  float* s_y = reinterpret_cast<float*>(smem + S::kStages * S::kStageBytes + 256);
+  float* s_y = reinterpret_cast<float*>(smem + S::kPipeBytes + 256);
   float* s_mask = s_y + BN;
+  float* s_stats = s_mask + BN;                    // [4 col groups][BM][4]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
@@ -299,17 +241,15 @@ k_glm_tc_gemm(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_ptr, kTmemCols);
-  if (EPI == 0) {   // per-column observation data of this tile
+  if (EPI == 0 && threadIdx.x < BN) {   // per-column observation data of this tile
     const int col = n0 + threadIdx.x;
     float yv = 0.f, mv = 0.f;
-    if (threadIdx.x < BN && col < link.n) {
+    if (col < link.n) {
       yv = link.y[link.idx ? link.idx[col] : col];
       mv = link.mask ? link.mask[col] : 1.0f;
     }
-    if (threadIdx.x < BN) {
-      s_y[threadIdx.x] = yv;
-      s_mask[threadIdx.x] = mv;
-    }
+    s_y[threadIdx.x] = yv;
+    s_mask[threadIdx.x] = mv;
   }
   tc_fence_before();
   __syncthreads();
@@ -360,25 +300,131 @@ k_glm_tc_gemm(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
     umma_commit(tmem_full_bar);            // accumulator complete
   }
 
-  // ===== epilogue: all 8 warps =====
+  // ===== epilogue: all 16 warps =====
   __syncwarp();
   mbar_wait(tmem_full_bar, 0);
   tc_fence_after();
-  {
-    const int q = warp & 3;                 // TMEM lane quarter this warp may access
-    const int hcol = (warp >> 2) * (BN / 2);
-    const int row = m0 + q * 32 + lane;
+  // All TMA writes have landed and all MMAs have read them: the pipeline smem
+  // is free and becomes 16 private 32x33 f32 transpose buffers.
+  float* stage = reinterpret_cast<float*>(tiles) + warp * (32 * 33);
+  const int q = warp & 3;                  // TMEM lane quarter this warp may access
+  const int cg = warp >> 2;                // column group: 64 columns
+  const int row = m0 + q * 32 + lane;      // this thread's accumulator row
+  const int rsub = lane >> 4, csub = (lane & 15) * 2;   // packed 2-row store mapping
+
+  if (EPI == 0) {
+    const float inv = row < link.C ? 1.0f / (link.row_scale[row] * __ldg(link.b_scale)) : 0.f;
+    const float bias = (link.aux_off >= 0 && row < link.C)
+                           ? link.theta[(int64_t)row * link.P + link.aux_off] : 0.0f;
+    float cnt = 0.f, shift = 0.f, s1 = 0.f, s2 = 0.f, sm = 0.f;
 #pragma unroll 1
-    for (int c = 0; c < BN / 2; c += 32) {
+    for (int c = 0; c < 64; c += 32) {
+      const int ct = cg * 64 + c;                       // column inside the tile
+      const int col0 = n0 + ct;
       uint32_t acc[32];
-      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(hcol + c), acc);
-      const int col0 = n0 + hcol + c;
-      if (EPI == 0) {
-        if (col0 < link.n)
-          epi_link_chunk<TERMS == 3>(link, row, col0, acc, s_y, s_mask, hcol + c);
-      } else {
-        if (col0 < gradp.a.spec.d) epi_grad_chunk(gradp, row, col0, acc);
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)ct, acc);
+      if (col0 >= link.n) continue;                      // warp-uniform
+      float ellv[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float z = fmaf(__uint_as_float(acc[j]), inv, bias);
+        float l, dz;
+        logistic_link_fast(z, s_y[ct + j], l, dz);
+        const float m = s_mask[ct + j];
+        ellv[j] = l;
+        stage[lane * 33 + j] = dz * (link.cot * m) * link.r_scale;
+        if (col0 + j < link.n) {
+          if (cnt == 0.f) shift = l;
+          const float dl = l - shift;
+          cnt += 1.f; s1 += dl; s2 = fmaf(dl, dl, s2); sm = fmaf(l, m, sm);
+        }
       }
+      __syncwarp();
+      // coalesced R stores: two rows per instruction, two columns per lane
+#pragma unroll 4
+      for (int r = 0; r < 32; r += 2) {
+        const int rr = r + rsub, grow = m0 + q * 32 + rr, gcol = col0 + csub;
+        const float v0 = stage[rr * 33 + csub], v1 = stage[rr * 33 + csub + 1];
+        if (grow < link.C && gcol < link.n) {      // n % 8 == 0: pairs never straddle
+          const int64_t o = (int64_t)grow * link.n + gcol;
+          if (TERMS == 3) {
+            const __half2 h = __floats2half2_rn(v0, v1);
+            const float2 hf = __half22float2(h);
+            *reinterpret_cast<__half2*>(link.r_hi + o) = h;
+            *reinterpret_cast<__half2*>(link.r_lo + o) = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
+          } else {
+            *reinterpret_cast<__nv_bfloat162*>(link.r_bf + o) = __floats2bfloat162_rn(v0, v1);
+          }
+        }
+      }
+      if (link.ell) {                                    // optional per-observation output
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) stage[lane * 33 + j] = ellv[j];
+        __syncwarp();
+#pragma unroll 4
+        for (int r = 0; r < 32; ++r) {
+          const int grow = m0 + q * 32 + r;
+          if (grow < link.C && col0 + lane < link.n)
+            link.ell[(int64_t)grow * link.n + col0 + lane] = stage[r * 33 + lane];
+        }
+      }
+      __syncwarp();
+    }
+    // per-row statistics of this warp's 64 columns -> smem -> combine 4 groups
+    {
+      float mean = 0.f, m2 = 0.f;
+      if (cnt > 0.f) {
+        mean = shift + s1 / cnt;
+        m2 = fmaxf(s2 - s1 * s1 / cnt, 0.f);
+      }
+      float* st = s_stats + ((cg * BM) + q * 32 + lane) * kStatFields;
+      st[0] = cnt; st[1] = mean; st[2] = m2; st[3] = sm;
+    }
+    __syncthreads();
+    if (threadIdx.x < BM && m0 + threadIdx.x < link.C) {
+      float n_t = 0.f, mean_t = 0.f, m2_t = 0.f, sm_t = 0.f;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {                      // Chan et al. pairwise update
+        const float* st = s_stats + ((g * BM) + threadIdx.x) * kStatFields;
+        const float nb = st[0];
+        if (nb > 0.f) {
+          const float nn = n_t + nb, delta = st[1] - mean_t;
+          mean_t += delta * (nb / nn);
+          m2_t += st[2] + delta * delta * (n_t * nb / nn);
+          n_t = nn;
+        }
+        sm_t += st[3];
+      }
+      float* o = link.stats + ((int64_t)(m0 + threadIdx.x) * link.parts + blockIdx.x) * kStatFields;
+      o[0] = n_t; o[1] = mean_t; o[2] = m2_t; o[3] = sm_t;
+    }
+  } else {
+    const float inv_scale = 1.0f / (gradp.r_scale * __ldg(gradp.xt_scale));
+#pragma unroll 1
+    for (int c = 0; c < 64; c += 32) {
+      const int ct = cg * 64 + c;
+      const int col0 = n0 + ct;
+      uint32_t acc[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)ct, acc);
+      if (col0 >= gradp.d) continue;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) stage[lane * 33 + j] = __uint_as_float(acc[j]) * inv_scale;
+      __syncwarp();
+      const int gcol = col0 + lane;
+      const int p = gradp.w_off + gcol;
+      const bool in_prior = p >= gradp.prior_lo && p < gradp.prior_hi;
+#pragma unroll 4
+      for (int r = 0; r < 32; ++r) {
+        const int grow = m0 + q * 32 + r;
+        if (grow < gradp.C && gcol < gradp.d) {
+          const int64_t o = (int64_t)grow * gradp.P + p;
+          float g = stage[r * 33 + lane];
+          if (in_prior) g = fmaf(gradp.theta[o], gradp.prior_coef, g);
+          gradp.grad[o] = g;
+        }
+      }
+      __syncwarp();
     }
   }
   tc_fence_before();
@@ -387,7 +433,7 @@ k_glm_tc_gemm(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
 }
 
 // ---------------------------------------------------------------------------
-// Operand preparation kernels
+// Operand preparation / finalisation kernels
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ float pow2_scale_for(float absmax) {
   // power of two s with absmax*s in [2^12, 2^13); 1 for absmax == 0 / non-finite
@@ -398,23 +444,32 @@ __device__ __forceinline__ float pow2_scale_for(float absmax) {
 }
 
 // One warp per chain row: row absmax -> power-of-two scale -> fp16 hi/lo split
-// (SPLIT) or plain bf16 conversion.  Theta row = theta[c*P + w_off .. + d).
+// (SPLIT) or plain bf16 conversion; also sum(theta^2) over the gaussian-prior
+// range of the row (for the prior value).  Theta row = theta[c*P + w_off ..+d).
 template <bool SPLIT>
 __global__ void k_theta_prepare(const float* __restrict__ theta, int64_t P, int w_off, int d,
-                                int C, void* __restrict__ out_hi, __half* __restrict__ out_lo,
-                                float* __restrict__ row_scale) {
+                                int C, int prior_lo, int prior_hi, void* __restrict__ out_hi,
+                                __half* __restrict__ out_lo, float* __restrict__ row_scale,
+                                float* __restrict__ row_sumsq) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= C) return;
   const float* src = theta + (int64_t)warp * P + w_off;
-  float s = 1.0f;
-  if (SPLIT) {
-    float m = 0.f;
-    for (int j = lane; j < d; j += 32) m = fmaxf(m, fabsf(src[j]));
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-    s = pow2_scale_for(m);
+  float m = 0.f, sq = 0.f;
+  for (int j = lane; j < d; j += 32) {
+    const float x = src[j];
+    m = fmaxf(m, fabsf(x));
+    if (w_off + j >= prior_lo && w_off + j < prior_hi) sq = fmaf(x, x, sq);
   }
-  if (lane == 0) row_scale[warp] = s;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    sq += __shfl_xor_sync(0xffffffffu, sq, o);
+  }
+  const float s = SPLIT ? pow2_scale_for(m) : 1.0f;
+  if (lane == 0) {
+    row_scale[warp] = s;
+    row_sumsq[warp] = sq;
+  }
   for (int j = lane; j < d; j += 32) {
     const float x = src[j] * s;
     if (SPLIT) {
@@ -427,18 +482,17 @@ __global__ void k_theta_prepare(const float* __restrict__ theta, int64_t P, int 
   }
 }
 
+// |X[idx]| max over the minibatch: one warp per gathered row.
 __global__ void k_absmax_gather(const float* __restrict__ X, const int32_t* __restrict__ idx,
                                 int n, int d, uint32_t* __restrict__ out_bits) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= n) return;
+  const float* src = X + (int64_t)(idx ? idx[warp] : warp) * d;
   float m = 0.f;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < (int64_t)n * d;
-       i += (int64_t)gridDim.x * blockDim.x) {
-    const int r = (int)(i / d), c = (int)(i - (int64_t)r * d);
-    const int64_t row = idx ? idx[r] : r;
-    m = fmaxf(m, fabsf(X[row * d + c]));
-  }
+  for (int j = lane; j < d; j += 32) m = fmaxf(m, fabsf(src[j]));
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-  if ((threadIdx.x & 31) == 0) atomicMax(out_bits, __float_as_uint(m));  // m >= 0
+  if (lane == 0) atomicMax(out_bits, __float_as_uint(m));  // m >= 0: uint order == float order
 }
 
 // Gather minibatch rows, scale, split, and write both Xb [n][d] and its
@@ -487,6 +541,34 @@ __global__ void k_x_prepare(const float* __restrict__ X, const int32_t* __restri
   }
 }
 
+// One thread per chain: combine the per-tile likelihood statistics into
+// U = (L - prior)/T (potential.py:183-185, :210) and var(ell) (integrator.py:880).
+__global__ void k_glm_finalize_parts(const float* __restrict__ stats, int parts,
+                                     const float* __restrict__ row_sumsq, const GlmArgs a) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= a.C) return;
+  float n_t = 0.f, mean_t = 0.f, m2_t = 0.f, sm_t = 0.f;
+  for (int g = 0; g < parts; ++g) {
+    const float* st = stats + ((int64_t)c * parts + g) * kStatFields;
+    const float nb = st[0];
+    if (nb > 0.f) {
+      const float nn = n_t + nb, delta = st[1] - mean_t;
+      mean_t += delta * (nb / nn);
+      m2_t += st[2] + delta * delta * (n_t * nb / nn);
+      n_t = nn;
+    }
+    sm_t += st[3];
+  }
+  float L;
+  if (a.mask) L = (-(float)a.N / (float)a.n) * sm_t;
+  else L = -(float)a.N * mean_t;
+  float prior = 0.f;
+  if (a.spec.prior == kPriorGaussian)
+    prior = -0.5f * (1.0f / (a.spec.prior_scale * a.spec.prior_scale)) * row_sumsq[c];
+  a.potential[c] = (L - prior) / a.spec.temperature;
+  if (a.variance) a.variance[c] = m2_t / (float)a.n;
+}
+
 // ---------------------------------------------------------------------------
 // Host side
 // ---------------------------------------------------------------------------
@@ -526,9 +608,10 @@ static int make_map(CUtensorMap* m, const void* ptr, int bf16, int64_t rows, int
 }
 
 struct TcWorkspace {
-  void* th_hi; __half* th_lo; float* row_scale;
+  void* th_hi; __half* th_lo; float* row_scale; float* row_sumsq;
   void* xb_hi; __half* xb_lo; void* xt_hi; __half* xt_lo;
   void* r_hi; __half* r_lo;
+  float* stats;
   uint32_t* absmax_bits; float* x_scale;
 };
 
@@ -541,20 +624,25 @@ static size_t carve(TcWorkspace* w, uint8_t* base, int64_t C, int64_t n, int64_t
     off += align256(bytes);
     return p;
   };
+  const int64_t parts = (n + BN - 1) / BN;
   void* th_hi = take((size_t)C * d * 2);
   void* th_lo = take((size_t)C * d * 2);
   void* rs = take((size_t)C * 4);
+  void* rq = take((size_t)C * 4);
   void* xb_hi = take((size_t)n * d * 2);
   void* xb_lo = take((size_t)n * d * 2);
   void* xt_hi = take((size_t)n * d * 2);
   void* xt_lo = take((size_t)n * d * 2);
   void* r_hi = take((size_t)C * n * 2);
   void* r_lo = take((size_t)C * n * 2);
+  void* stats = take((size_t)C * parts * kStatFields * 4);
   void* am = take(256);
   if (w) {
-    w->th_hi = th_hi; w->th_lo = (__half*)th_lo; w->row_scale = (float*)rs;
+    w->th_hi = th_hi; w->th_lo = (__half*)th_lo;
+    w->row_scale = (float*)rs; w->row_sumsq = (float*)rq;
     w->xb_hi = xb_hi; w->xb_lo = (__half*)xb_lo; w->xt_hi = xt_hi; w->xt_lo = (__half*)xt_lo;
     w->r_hi = r_hi; w->r_lo = (__half*)r_lo;
+    w->stats = (float*)stats;
     w->absmax_bits = (uint32_t*)am; w->x_scale = (float*)am + 1;
   }
   return off;
@@ -588,28 +676,35 @@ int glm_tc(cudaStream_t stream, const GlmArgs& a, int path) {
   SGMC_REQUIRE(a.spec.family == kFamilyLogistic,
                "tensor-core path supports the logistic family (use path 0)");
   SGMC_REQUIRE(a.spec.aux_off < 0, "tensor-core path: bias term not supported (use path 0)");
+  SGMC_REQUIRE(a.spec.prior != kPriorInvSigma, "tensor-core path: prior not supported");
   SGMC_REQUIRE(d % 8 == 0 && n % 8 == 0, "tensor-core path needs d %% 8 == 0 and n %% 8 == 0");
   const bool split = path == 1;
   TcWorkspace w;
   uint8_t* base = reinterpret_cast<uint8_t*>(
       (reinterpret_cast<uintptr_t>(a.tc_ws) + 255) & ~(uintptr_t)255);
   carve(&w, base, C, n, d);
+  const bool gauss_prior = a.spec.prior == kPriorGaussian;
+  const int prior_lo = gauss_prior ? a.spec.prior_off : 0;
+  const int prior_hi = gauss_prior ? a.spec.prior_off + a.spec.prior_size : 0;
 
   // ---- operand preparation ------------------------------------------------
   {
     const int wpb = 8;
     dim3 grid((unsigned)((C + wpb - 1) / wpb));
     if (split)
-      k_theta_prepare<true><<<grid, wpb * 32, 0, stream>>>(a.theta, a.P, a.spec.w_off, d, (int)C,
-                                                           w.th_hi, w.th_lo, w.row_scale);
+      k_theta_prepare<true><<<grid, wpb * 32, 0, stream>>>(
+          a.theta, a.P, a.spec.w_off, d, (int)C, prior_lo, prior_hi, w.th_hi, w.th_lo,
+          w.row_scale, w.row_sumsq);
     else
-      k_theta_prepare<false><<<grid, wpb * 32, 0, stream>>>(a.theta, a.P, a.spec.w_off, d, (int)C,
-                                                            w.th_hi, w.th_lo, w.row_scale);
+      k_theta_prepare<false><<<grid, wpb * 32, 0, stream>>>(
+          a.theta, a.P, a.spec.w_off, d, (int)C, prior_lo, prior_hi, w.th_hi, w.th_lo,
+          w.row_scale, w.row_sumsq);
     if (post_launch("k_theta_prepare")) return 1;
   }
   if (split) {
     if (check_cuda(cudaMemsetAsync(w.absmax_bits, 0, 4, stream), "memset")) return 1;
-    k_absmax_gather<<<sm_count(), 256, 0, stream>>>(a.X, a.idx, (int)n, d, w.absmax_bits);
+    k_absmax_gather<<<(unsigned)((n + 7) / 8), 256, 0, stream>>>(a.X, a.idx, (int)n, d,
+                                                                w.absmax_bits);
     if (post_launch("k_absmax_gather")) return 1;
   }
   {
@@ -637,11 +732,16 @@ int glm_tc(cudaStream_t stream, const GlmArgs& a, int path) {
   link.y = a.y; link.idx = a.idx; link.mask = a.mask;
   link.row_scale = w.row_scale; link.b_scale = w.x_scale;
   link.cot = a.cot; link.r_scale = r_scale;
-  link.ell = a.ell;
+  link.ell = a.ell_requested ? a.ell : nullptr;
+  link.stats = w.stats; link.parts = (int)((n + BN - 1) / BN);
   link.r_hi = (__half*)w.r_hi; link.r_lo = w.r_lo; link.r_bf = (__nv_bfloat16*)w.r_hi;
   link.C = (int)C; link.n = (int)n;
   TcGradEpi gradp{};
-  gradp.a = a;
+  gradp.theta = a.theta; gradp.grad = a.grad; gradp.P = a.P; gradp.w_off = a.spec.w_off;
+  gradp.d = d; gradp.C = (int)C;
+  gradp.prior_lo = prior_lo; gradp.prior_hi = prior_hi;
+  gradp.prior_coef = gauss_prior
+      ? (1.0f / (a.spec.prior_scale * a.spec.prior_scale)) / a.spec.temperature : 0.f;
   gradp.xt_scale = w.x_scale;
   gradp.r_scale = r_scale;
 
@@ -658,8 +758,10 @@ int glm_tc(cudaStream_t stream, const GlmArgs& a, int path) {
     if (launch_gemm<1, 0, 1>(stream, mA0, mA0, mB0, mB0, (int)C, (int)n, d, link, gradp,
                              "k_glm_tc_gemm<bf16,link>")) return 1;
   }
-  // ---- U, var(ell) ------------------------------------------------------------
-  if (glm_finalize(stream, a)) return 1;
+  // ---- U, var(ell) from the per-tile statistics ---------------------------------
+  k_glm_finalize_parts<<<(unsigned)((C + 127) / 128), 128, 0, stream>>>(w.stats, link.parts,
+                                                                       w.row_sumsq, a);
+  if (post_launch("k_glm_finalize_parts")) return 1;
   if (!a.grad) return 0;
   // ---- GEMM2: G[C,d] = R[C,n] . XbT[d,n]^T ---------------------------------------
   if (make_map(&mA0, w.r_hi, !split, C, n, BM)) return 2;

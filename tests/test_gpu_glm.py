@@ -192,7 +192,10 @@ def test_logistic_tc_parity_path(gpu, C, n, d):
   pot = osgmc.minibatch_potential(osgmc.Logistic(d, 0),
                                   osgmc.Prior("gaussian", 0, d, 10.0))
   wU, well, wg = pot(theta, (X[idx], y[idx]), 3000)
-  np.testing.assert_allclose(ell, well, rtol=2e-5, atol=2e-5)
+  # per-observation log-likelihoods: 1e-5 of the row's scale (the tensor-core
+  # accumulator truncates, which biases z by ~0.5 ulp per 16-element k-step)
+  scale = np.abs(well).max(axis=1, keepdims=True)
+  assert (np.abs(ell - well) / scale).max() < 1e-5
   np.testing.assert_allclose(U, wU, rtol=1e-5)
   np.testing.assert_allclose(var, well.astype(np.float64).var(axis=1), rtol=1e-4)
   _grad_close(g, wg, 1e-5)
