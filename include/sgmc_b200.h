@@ -138,6 +138,19 @@ int sgmc_sgld_rms_update(void* stream, float* theta, float* v,
                          const float* temp_per_chain, float alpha, float lmbd,
                          int prng_layout);
 
+/* Stand-alone adaption.rms_prop (adaption.py:225-293) for users of the
+ * (init, update, get) triplet outside the fused update:
+ * update: v' = alpha v + (1-alpha) g^2 (in place, :270-272);
+ * get   : g_inv = 1/(lmbd + sqrt(v)), sqrt_g_inv = sqrt(g_inv) (:289-291). */
+int sgmc_rms_prop_update(void* stream, float* v, const float* grad, int64_t n,
+                         float alpha);
+int sgmc_rms_prop_get(void* stream, const float* v, float* g_inv,
+                      float* sqrt_g_inv, int64_t n, float lmbd);
+/* out = a*x + b*y on per-chain scalars (e.g. obabo's potential =
+ * 0.5*(U1+U2), integrator.py:264). */
+int sgmc_axpby(void* stream, float* out, float a, const float* x, float b,
+               const float* y, int64_t n);
+
 /* integrator.friction_leapfrog (integrator.py:563-765).
  * begin: key', split = split(key); p = sqrt(m) * random_tree(split)  (:736-738)
  *        fused with the first position update theta += eps * (p / m) (:610-612).

@@ -65,6 +65,9 @@ PROTOTYPES = {
     "sgmc_sgld_rms_update": [_vp, _vp, _vp, _vp, _vp, _vp, _i64,
                              C.POINTER(_i64), _int, _f32, _f32, _vp, _f32,
                              _f32, _int],
+    "sgmc_rms_prop_update": [_vp, _vp, _vp, _i64, _f32],
+    "sgmc_rms_prop_get": [_vp, _vp, _vp, _vp, _i64, _f32],
+    "sgmc_axpby": [_vp, _vp, _f32, _vp, _f32, _vp, _i64],
     "sgmc_sghmc_begin": [_vp, _vp, _vp, _vp, _vp, _i64, C.POINTER(_i64), _int,
                          _f32, _vp, _int],
     "sgmc_sghmc_step": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, C.POINTER(_i64),

@@ -1,0 +1,157 @@
+"""Ready-to-use solvers, mirroring ``jax_sgmc.alias`` for the hot path.
+
+``sgld`` (reference alias.py:30-120), ``re_sgld`` (:122-208), ``sghmc``
+(:451-540) and ``obabo`` (:542-619) keep signatures and defaults; each returns
+``run_fn(*init_samples, init_model_state=None, iterations=1000)`` producing one
+result dict per chain.  All chains of a call advance together through the
+batched kernels; with the reference's defaults (every chain on PRNGKey(0),
+integrator.py:804) the per-chain results equal the reference's sequential
+``strategy='map'`` runs.  ``keys=`` (not in the reference) seeds chains
+individually.
+"""
+from __future__ import annotations
+
+from functools import partial
+from typing import Any, Union
+
+import numpy as np
+
+from . import adaption, data, integrator, io, scheduler, solver
+from .tree_util import ChainTree
+
+Pytree = Any
+
+
+def _schedule(first_step_size, last_step_size, burn_in, accepted_samples,
+              progress_bar, temperature=None):
+  step_size_schedule = scheduler.polynomial_step_size_first_last(
+      first=first_step_size, last=last_step_size)
+  burn_in_schedule = scheduler.initial_burn_in(burn_in)
+  thinning = scheduler.random_thinning(step_size_schedule, burn_in_schedule,
+                                       selections=accepted_samples)
+  kw = {} if temperature is None else {"temperature": temperature}
+  return scheduler.init_scheduler(step_size=step_size_schedule,
+                                  burn_in=burn_in_schedule, thinning=thinning,
+                                  progress_bar=progress_bar, **kw)
+
+
+def _saving(save_to_numpy):
+  return io.save(io.MemoryCollector()) if save_to_numpy else None
+
+
+def sgld(potential_fn, data_loader, cache_size: int = 512, batch_size: int = 32,
+         first_step_size: float = 0.05, last_step_size: float = 0.001,
+         burn_in: int = 0, accepted_samples: int = 1000, rms_prop: bool = False,
+         alpha: float = 0.9, lmbd: float = 1e-5, save_to_numpy: bool = True,
+         progress_bar: bool = True):
+  """alias.py:30-120: SGLD with polynomial step size and optional RMSprop."""
+  random_data = data.random_reference_data(data_loader, cache_size, batch_size)
+  rms = adaption.rms_prop() if rms_prop else None
+  rms_integrator = integrator.langevin_diffusion(potential_fn, random_data,
+                                                 adaption=rms)
+  schedule = _schedule(first_step_size, last_step_size, burn_in, accepted_samples,
+                       progress_bar)
+  sgld_solver = solver.sgmc(rms_integrator)
+  mcmc = solver.mcmc(sgld_solver, schedule, strategy="map",
+                     saving=_saving(save_to_numpy))
+
+  def run_fn(*init_samples, init_model_state: Pytree = None, iterations=1000,
+             keys=None):
+    state = sgld_solver[0](ChainTree.from_trees(list(init_samples)), key=keys,
+                           adaption_kwargs={"alpha": alpha, "lmbd": lmbd},
+                           init_model_state=init_model_state)
+    return mcmc(state, iterations=iterations)
+
+  return run_fn
+
+
+def re_sgld(potential_fn, data_loader, cache_size: int = 512, batch_size: int = 32,
+            temperature: float = 1000.0, first_step_size: float = 0.05,
+            last_step_size: float = 0.001, burn_in: int = 0,
+            accepted_samples: int = 100, save_to_numpy: bool = True,
+            progress_bar: bool = True):
+  """alias.py:122-208: replica exchange SGLD; ``init_samples`` are
+  ``(normal, tempered)`` tuples."""
+  del progress_bar                                                  # :171
+  random_data = data.random_reference_data(data_loader, cache_size, batch_size)
+  resgld_integrator = integrator.langevin_diffusion(potential_fn, random_data)
+  schedule = _schedule(first_step_size, last_step_size, burn_in, accepted_samples,
+                       False, temperature=scheduler.constant_temperature(1.0))
+  resgld_solver = solver.parallel_tempering(resgld_integrator)
+  mcmc = solver.mcmc(resgld_solver, schedule, strategy="map",
+                     saving=_saving(save_to_numpy))
+
+  def run_fn(*init_samples, init_model_state: Pytree = None, iterations=1000,
+             keys=None):
+    normal, tempered = zip(*init_samples)
+    state = resgld_solver[0](ChainTree.from_trees(list(normal)),
+                             ChainTree.from_trees(list(tempered)), key=keys,
+                             init_model_state=init_model_state)
+    return mcmc(state, iterations=iterations,
+                schedulers=[{"temperature": {"tau": temperature}}])   # :205-207
+
+  return run_fn
+
+
+def sghmc(potential_fn, data_loader, cache_size: int = 512, batch_size: int = 32,
+          integration_steps: int = 10, friction: Union[float, Pytree] = 1.0,
+          mass: Pytree = None, first_step_size: float = 0.05,
+          last_step_size: float = 0.001, burn_in: int = 0,
+          accepted_samples: int = 1000, adapt_noise_model: bool = False,
+          diagonal_noise: bool = True, save_to_numpy: bool = True,
+          progress_bar: bool = True):
+  """alias.py:451-540."""
+  del diagonal_noise
+  if adapt_noise_model:
+    raise NotImplementedError("adaption.fisher_information is outside this path")
+  random_data = data.random_reference_data(data_loader, cache_size, batch_size)
+  leapfrog = integrator.friction_leapfrog(potential_fn, random_data,
+                                          friction=friction, const_mass=mass,
+                                          steps=integration_steps)
+  schedule = _schedule(first_step_size, last_step_size, burn_in, accepted_samples,
+                       progress_bar)
+  sghmc_solver = solver.sgmc(leapfrog)
+  mcmc = solver.mcmc(sghmc_solver, schedule, strategy="map",
+                     saving=_saving(save_to_numpy))
+
+  def run_fn(*init_samples, init_model_state: Pytree = None, iterations=1000,
+             keys=None):
+    state = sghmc_solver[0](ChainTree.from_trees(list(init_samples)), key=keys,
+                            init_model_state=init_model_state)
+    return mcmc(state, iterations=iterations)
+
+  return run_fn
+
+
+def obabo(potential_fn, data_loader, cache_size: int = 512, batch_size: int = 32,
+          integration_steps: int = 10, friction: Union[float, Pytree] = 1.0,
+          mass: Pytree = None, first_step_size: float = 0.05,
+          last_step_size: float = 0.001, burn_in: int = 0,
+          accepted_samples: int = 1000, save_to_numpy: bool = True,
+          progress_bar: bool = True):
+  """alias.py:542-619."""
+  random_data = data.random_reference_data(data_loader, cache_size, batch_size)
+  obabo_integrator = integrator.obabo(potential_fn=potential_fn, batch_fn=random_data,
+                                      steps=integration_steps, friction=friction,
+                                      const_mass=mass)
+  schedule = _schedule(first_step_size, last_step_size, burn_in, accepted_samples,
+                       progress_bar)
+  obabo_solver = solver.sgmc(obabo_integrator)
+  mcmc = solver.mcmc(obabo_solver, schedule, strategy="map",
+                     saving=_saving(save_to_numpy))
+
+  def run_fn(*init_samples, init_model_state: Pytree = None, iterations=1000,
+             keys=None):
+    state = obabo_solver[0](ChainTree.from_trees(list(init_samples)), key=keys,
+                            init_model_state=init_model_state)
+    return mcmc(state, iterations=iterations)
+
+  return run_fn
+
+
+def amagold(*args, **kwargs):
+  raise NotImplementedError("alias.amagold is the next tier (SURVEY.md 8f)")
+
+
+def sggmc(*args, **kwargs):
+  raise NotImplementedError("alias.sggmc is the next tier (SURVEY.md 8f)")

@@ -414,15 +414,21 @@ k_glm_tc_gemm(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
       const int gcol = col0 + lane;
       const int p = gradp.w_off + gcol;
       const bool in_prior = p >= gradp.prior_lo && p < gradp.prior_hi;
-#pragma unroll 4
+      const bool col_ok = gcol < gradp.d;
+      // all 32 theta loads are issued before the first dependent store
+      float th[32];
+#pragma unroll
       for (int r = 0; r < 32; ++r) {
         const int grow = m0 + q * 32 + r;
-        if (grow < gradp.C && gcol < gradp.d) {
-          const int64_t o = (int64_t)grow * gradp.P + p;
-          float g = stage[r * 33 + lane];
-          if (in_prior) g = fmaf(gradp.theta[o], gradp.prior_coef, g);
-          gradp.grad[o] = g;
-        }
+        th[r] = (in_prior && col_ok && grow < gradp.C)
+                    ? __ldg(gradp.theta + (int64_t)grow * gradp.P + p) : 0.f;
+      }
+#pragma unroll
+      for (int r = 0; r < 32; ++r) {
+        const int grow = m0 + q * 32 + r;
+        if (grow < gradp.C && col_ok)
+          gradp.grad[(int64_t)grow * gradp.P + p] =
+              fmaf(th[r], gradp.prior_coef, stage[r * 33 + lane]);
       }
       __syncwarp();
     }

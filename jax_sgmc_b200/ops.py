@@ -141,6 +141,21 @@ def sgld_update(theta, grad, keys_in, keys_out, leaf_sizes, step_size,
               float(alpha), float(lmbd), _layout(layout))
 
 
+def rms_prop_update(v, grad, alpha=0.9, stream=None):
+  _lib.call("sgmc_rms_prop_update", _s(stream), vp(v), vp(grad), v.size,
+            float(alpha))
+
+
+def rms_prop_get(v, g_inv, sqrt_g_inv, lmbd=1e-5, stream=None):
+  _lib.call("sgmc_rms_prop_get", _s(stream), vp(v), vp(g_inv), vp(sqrt_g_inv),
+            v.size, float(lmbd))
+
+
+def axpby(out, a, x, b, y, stream=None):
+  _lib.call("sgmc_axpby", _s(stream), vp(out), float(a), vp(x), float(b), vp(y),
+            out.size)
+
+
 def sghmc_begin(theta, momentum, keys_in, keys_out, leaf_sizes, step_size,
                 mass=None, layout=0, stream=None):
   _lib.call("sgmc_sghmc_begin", _s(stream), vp(theta), vp(momentum),

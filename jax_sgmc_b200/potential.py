@@ -1,0 +1,184 @@
+"""Stochastic / full potential, mirroring ``jax_sgmc.potential``.
+
+``minibatch_potential`` (reference potential.py:94-216) and ``full_potential``
+(:219-293) keep their signatures.  The returned callables evaluate
+``U = (-N mean(ell) - prior) / T`` (or the masked form) for *all chains at
+once* on the device; ``value_and_grad(potential_fn)`` is what the integrators
+call in place of ``jax.value_and_grad(potential_fn, argnums=0, has_aux=True)``
+(integrator.py:166, :593, :792) and returns the gradient produced by the fused
+GLM kernels (tcgen05 tensor-core path when the shape allows, fp32 SIMT
+otherwise).
+"""
+from __future__ import annotations
+
+import os
+from typing import Any, Callable, Optional
+
+import numpy as np
+
+from . import glm, ops
+from .data import BatchRef, MiniBatchInformation
+from .device import DeviceArray
+from .tree_util import ChainTree
+
+# 'auto': tensor cores whenever the shape qualifies; override with
+# SGMC_GLM_PATH=simt|tc_parity|tc_throughput
+DEFAULT_PATH = os.environ.get("SGMC_GLM_PATH", "auto")
+
+
+def _select_path(path: str, spec, n_chains: int, n: int) -> str:
+  if path != "auto":
+    return path
+  tc_ok = (spec.family == ops.FAMILY["logistic"] and spec.aux_off < 0
+           and spec.d % 8 == 0 and n % 8 == 0 and spec.d >= 64 and n >= 64
+           and n_chains >= 64 and spec.prior != ops.PRIOR["inv_sigma"])
+  return "tc_parity" if tc_ok else "simt"
+
+
+class _PotentialFn:
+  """Callable with the reference's StochasticPotential protocol
+  (potential.py:42-66)."""
+
+  def __init__(self, prior, likelihood, temperature, path):
+    self.prior, self.likelihood = prior, likelihood
+    self.temperature, self.path = float(temperature), path
+    self._buffers = {}
+
+  # -- internal ------------------------------------------------------------------
+  def _run(self, sample: ChainTree, reference_data, mask, want_grad, want_ell,
+           grad_out: Optional[DeviceArray] = None,
+           U_out: Optional[DeviceArray] = None,
+           var_out: Optional[DeviceArray] = None):
+    batch, info = reference_data
+    assert isinstance(batch, BatchRef), "reference_data must come from jax_sgmc_b200.data"
+    spec = glm.resolve(self.likelihood, self.prior, sample, self.temperature)
+    C, P, n = sample.n_chains, sample.n_params, batch.n
+    N = int(info.observation_count)
+    X = batch.loader.device_data[self.likelihood.x]
+    y = batch.loader.device_data[self.likelihood.y]
+    if mask is None:
+      mask = batch.mask
+    path = _select_path(self.path, spec, C, n)
+    key = (C, P, n, path)
+    buf = self._buffers.get(key)
+    if buf is None:
+      buf = {"U": DeviceArray((C,), np.float32), "var": DeviceArray((C,), np.float32),
+             "ws": ops.glm_workspace(C if not batch.per_chain else 1, n, spec.d, path),
+             "ell": None}
+      self._buffers[key] = buf
+    grad = None
+    if want_grad:
+      grad = grad_out if grad_out is not None else DeviceArray((C, P), np.float32)
+    ell = None
+    if want_ell:
+      if buf["ell"] is None:
+        buf["ell"] = DeviceArray((C, n), np.float32)
+      ell = buf["ell"]
+    U_buf = U_out if U_out is not None else buf["U"]
+    var_buf = var_out if var_out is not None else buf["var"]
+    if not batch.per_chain:
+      ops.glm_potential_grad(spec, sample.flat, X, y, batch.idx, N, U_buf,
+                             var_buf, grad, ell, mask=mask, workspace=buf["ws"],
+                             path=path, batch_size=n)
+    else:
+      # one minibatch per chain (host loader with per-chain seeds): no sharing,
+      # evaluate chain by chain
+      for c in range(C):
+        ops.glm_potential_grad(
+            spec, sample.flat.row_slice(c, c + 1), X, y,
+            batch.idx.row_slice(c, c + 1).reshape(n), N,
+            U_buf.row_slice(c, c + 1), var_buf.row_slice(c, c + 1),
+            None if grad is None else grad.row_slice(c, c + 1),
+            None if ell is None else ell.row_slice(c, c + 1), mask=mask,
+            workspace=buf["ws"], path="simt", batch_size=n)
+    return U_buf, var_buf, grad, ell
+
+  # -- public protocol --------------------------------------------------------------
+  def __call__(self, sample: ChainTree, reference_data, state: Any = None,
+               mask=None, likelihoods: bool = False):
+    U, _, _, ell = self._run(sample, reference_data, mask, False, likelihoods)
+    if likelihoods:
+      return U, (ell, state)
+    return U, state
+
+  def value_and_grad(self, sample: ChainTree, reference_data, state: Any = None,
+                     mask=None, likelihoods: bool = False,
+                     grad_out: Optional[DeviceArray] = None,
+                     U_out: Optional[DeviceArray] = None,
+                     var_out: Optional[DeviceArray] = None):
+    """((U, aux), grad) with aux = state or (var(ell), state).  ``grad_out`` /
+    ``U_out`` / ``var_out`` let the caller own the output buffers."""
+    U, var, grad, ell = self._run(sample, reference_data, mask, True, False,
+                                  grad_out, U_out, var_out)
+    self.last_variance = var
+    g = ChainTree.like(sample, grad)
+    if likelihoods:
+      return (U, (var, state)), g
+    return (U, state), g
+
+
+def value_and_grad(potential_fn: _PotentialFn) -> Callable:
+  """Stand-in for ``jax.value_and_grad(potential_fn, argnums=0, has_aux=True)``.
+
+  With ``likelihoods=True`` the aux carries ``var(ell)`` per chain (what the
+  only caller, ``langevin_diffusion``, reduces the likelihoods to,
+  integrator.py:880) instead of the raw per-observation values.
+  """
+  return potential_fn.value_and_grad
+
+
+def minibatch_potential(prior, likelihood, strategy: str = "map",
+                        has_state: bool = False, is_batched: bool = False,
+                        temperature: float = 1., path: str = None):
+  """potential.py:94-216.  ``prior`` / ``likelihood`` are ``jax_sgmc_b200.glm``
+  specifications; ``strategy`` is accepted for API compatibility (the fused
+  kernels always evaluate the whole minibatch in parallel)."""
+  del is_batched
+  if strategy not in ("map", "vmap", "pmap"):
+    raise NotImplementedError(f"Strategy {strategy} is unknown")
+  if has_state:
+    raise NotImplementedError(
+        "stateful likelihoods are outside the fused GLM path")
+  if not isinstance(likelihood, (glm.GaussianRegression, glm.LogisticRegression)):
+    raise TypeError(
+        "likelihood must be a jax_sgmc_b200.glm specification (GaussianRegression, "
+        "LogisticRegression); arbitrary callables need the JAX route, see "
+        "INTEGRATION.md")
+  if not isinstance(prior, (glm.FlatPrior, glm.GaussianPrior, glm.InvSigmaPrior)):
+    raise TypeError("prior must be a jax_sgmc_b200.glm prior specification")
+  return _PotentialFn(prior, likelihood, temperature, path or DEFAULT_PATH)
+
+
+def full_potential(prior, likelihood, strategy: str = "map", has_state: bool = False,
+                   is_batched: bool = False, temperature: float = 1.,
+                   path: str = None):
+  """potential.py:219-293: ``U = (sum_b -dot(ell_b, mask_b) - prior) / T``."""
+  assert strategy != "pmap", "Pmap is currently not supported"
+  batch_potential = minibatch_potential(glm.FlatPrior(), likelihood, strategy,
+                                        has_state, is_batched, 1.0, path)
+  prior_only = minibatch_potential(prior, likelihood, strategy, has_state,
+                                   is_batched, 1.0, path)
+
+  def sum_batched_evaluations(sample: ChainTree, data_state, full_data_map_fn,
+                              state: Any = None):
+    first = []
+
+    def body(reference_data, mask, carry):
+      if not first:
+        first.append(reference_data)
+      U, _ = batch_potential(sample, reference_data, carry, mask)
+      _, info = reference_data
+      # undo the N/n scaling (potential.py:264-271)
+      return U.numpy().astype(np.float64) * info.batch_size / info.observation_count, carry
+
+    data_state, (results, new_state) = full_data_map_fn(
+        body, data_state, state, masking=True, information=True)
+    total = np.sum(results, axis=0)
+    # prior value: evaluate the potential on an all-masked batch (L = 0)
+    ref = first[0]
+    zero_mask = DeviceArray.zeros((ref[0].n,))
+    Up, _ = prior_only(sample, ref, None, zero_mask)       # = -prior
+    prior_val = -Up.numpy().astype(np.float64)
+    return ((total - prior_val) / temperature).astype(np.float32), (data_state, new_state)
+
+  return sum_batched_evaluations

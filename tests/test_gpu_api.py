@@ -1,0 +1,168 @@
+"""GPU tests of the operator API (potential / integrator / adaption / solver /
+alias mirrors): trajectories against the oracle driven through the API, and
+the reference's own statistical acceptance tests (tests/test_alias.py:
+Kolmogorov-Smirnov p > 0.05 for every solver; linear-regression sigma)."""
+import numpy as np
+import pytest
+from scipy import stats as scpstats
+
+from oracle import data as odata
+from oracle import prng
+from oracle import scheduler as osched
+from oracle import sgmc as osgmc
+
+pytestmark = pytest.mark.gpu
+
+
+def _ks_problem():
+  """tests/test_alias.py:32-65: target N(0, 0.5^2); the potential does not
+  depend on the data.  Expressed with the recognised families: logistic
+  likelihood on all-zero features (constant) + GaussianPrior(0.5)."""
+  from jax_sgmc_b200 import data, glm, potential
+  x = 0.5 * prng.normal(prng.PRNGKey(11), (100,))
+  loader = data.DeviceNumpyDataLoader(x=np.zeros((2, 1), np.float32),
+                                      y=np.zeros((2,), np.float32))
+  pot = potential.minibatch_potential(glm.GaussianPrior(0.5),
+                                      glm.LogisticRegression(), strategy="vmap")
+  init = {"w": np.array([x[0]], np.float32)}
+
+  def check(samples):
+    st = scpstats.kstest(np.ravel(samples), x)
+    assert st.pvalue > 0.05, f"KS p-value {st.pvalue}"
+
+  return loader, pot, init, check
+
+
+def test_ks_sgld_rms(gpu):
+  """tests/test_alias.py:121-142."""
+  from jax_sgmc_b200 import alias
+  loader, pot, init, check = _ks_problem()
+  run = alias.sgld(pot, loader, cache_size=1, batch_size=1, first_step_size=0.5,
+                   last_step_size=0.1, burn_in=100, accepted_samples=100,
+                   rms_prop=True, progress_bar=False)
+  res = run(init, iterations=2000)
+  assert res[0]["sample_count"] == 100
+  check(res[0]["samples"]["variables"]["w"])
+
+
+def test_ks_re_sgld(gpu):
+  """tests/test_alias.py:144-165."""
+  from jax_sgmc_b200 import alias
+  loader, pot, init, check = _ks_problem()
+  run = alias.re_sgld(pot, loader, cache_size=1, batch_size=1, first_step_size=0.1,
+                      last_step_size=0.05, burn_in=100, accepted_samples=100,
+                      temperature=1.5, progress_bar=False)
+  res = run((init, init), iterations=1500)
+  check(res[0]["samples"]["variables"]["w"])
+
+
+def test_ks_sghmc_and_obabo(gpu):
+  """tests/test_alias.py:205-244."""
+  from jax_sgmc_b200 import alias
+  loader, pot, init, check = _ks_problem()
+  run = alias.sghmc(pot, loader, cache_size=1, batch_size=1, first_step_size=0.1,
+                    last_step_size=0.05, burn_in=100, accepted_samples=100,
+                    integration_steps=5, friction=1.0, progress_bar=False)
+  check(run(init, iterations=1500)[0]["samples"]["variables"]["w"])
+  run = alias.obabo(pot, loader, cache_size=1, batch_size=1, first_step_size=0.2,
+                    last_step_size=0.1, burn_in=100, accepted_samples=100,
+                    integration_steps=5, friction=1.0, progress_bar=False)
+  check(run(init, iterations=1500)[0]["samples"]["variables"]["w"])
+
+
+def test_quickstart_sgld_posterior(gpu):
+  """BASELINE.json configs[0]: examples/quickstart Bayesian linear regression
+  with alias.sgld (rms_prop), single chain -- the setting the reference tests on
+  this data (tests/test_alias.py:250-265), shortened; posterior means must sit
+  on the least-squares solution / the notebook's NumPyro posterior."""
+  from jax_sgmc_b200 import alias, data, glm, potential
+  x, y, _ = odata.quickstart_dataset()
+  loader = data.NumpyDataLoader(x=x, y=y[:, 0])
+  pot = potential.minibatch_potential(prior=glm.InvSigmaPrior("log_sigma"),
+                                      likelihood=glm.GaussianRegression(
+                                          weights="w", log_sigma="log_sigma"),
+                                      strategy="vmap")
+  run = alias.sgld(pot, loader, cache_size=512, batch_size=10, first_step_size=0.05,
+                   last_step_size=0.001, burn_in=6000, accepted_samples=2000,
+                   rms_prop=True, progress_bar=False)
+  init = {"w": np.zeros((4, 1), np.float32), "log_sigma": np.array(2.5, np.float32)}
+  res = run(init, iterations=12000)[0]["samples"]["variables"]
+  w = res["w"].mean(axis=0).ravel()
+  sigma = np.exp(res["log_sigma"]).mean()
+  w_ls = np.linalg.lstsq(x.astype(np.float64), y.astype(np.float64), rcond=None)[0].ravel()
+  assert np.abs(w - w_ls).max() < 0.08, (w, w_ls)
+  assert abs(sigma - 0.5) < 0.1, sigma
+
+
+def test_langevin_api_matches_oracle_trajectory(gpu):
+  """integrator.langevin_diffusion + adaption.rms_prop + solver.sgmc driven
+  through the API for 300 steps == the oracle, same keys, same minibatches."""
+  from jax_sgmc_b200 import adaption, data, glm, integrator, potential, scheduler, solver
+  d, C, n, N, K = 16, 6, 32, 400, 300
+  X, y, _ = odata.logistic_dataset(N, d, seed=2)
+  loader = data.DeviceNumpyDataLoader(x=X, y=y)
+  pot = potential.minibatch_potential(glm.GaussianPrior(10.0), glm.LogisticRegression(),
+                                      path="simt")
+  batch_fn = data.random_reference_data(loader, 1, n)
+  integ = integrator.langevin_diffusion(pot, batch_fn, adaption=adaption.rms_prop())
+  init_fn, update_fn, get_fn = solver.sgmc(integ)
+  keys = np.stack([prng.PRNGKey(c) for c in range(C)])
+  state = init_fn([{"w": np.zeros(d, np.float32)} for _ in range(C)], key=keys,
+                  adaption_kwargs={"alpha": 0.9, "lmbd": 1e-5})
+  eps = osched.polynomial_step_size_first_last(K, 2e-2, 2e-3)
+  for k in range(K):
+    state, _ = update_fn(state, scheduler.schedule(eps[k], 1.0, 1.0, True))
+  # oracle
+  opot = osgmc.minibatch_potential(osgmc.Logistic(d, 0),
+                                   osgmc.Prior("gaussian", 0, d, 10.0))
+  st = osgmc.langevin_init(np.zeros((C, d), np.float32), keys, rms=True)
+  dk = prng.PRNGKey(0)
+  for k in range(K):
+    dk, idx = odata.device_draw(dk, n, N)
+    Xb, yb = X[idx], y[idx]
+    st = osgmc.langevin_update(st, lambda th: opot(th, (Xb, yb), N), [d], eps[k], 1.0)
+  got = get_fn(state)["variables"].to_host()["w"]
+  assert np.abs(got - st.theta).max() / np.abs(st.theta).max() < 1e-5
+  np.testing.assert_allclose(get_fn(state)["likelihood"].numpy(), -st.potential, rtol=1e-5)
+  assert np.array_equal(state.key.numpy(), st.key)
+
+
+def test_adaption_triplet_matches_oracle(gpu):
+  """adaption.rms_prop (init, update, get) stand-alone == adaption.py:238-291."""
+  from jax_sgmc_b200 import adaption
+  from jax_sgmc_b200.device import DeviceArray
+  from jax_sgmc_b200.tree_util import ChainTree
+  rng = np.random.default_rng(0)
+  sample = ChainTree.from_trees([{"a": rng.standard_normal(5), "b": rng.standard_normal((2, 3))}
+                                 for _ in range(3)])
+  g = rng.standard_normal((3, 11)).astype(np.float32)
+  init, update, get = adaption.rms_prop()
+  st = init(sample, alpha=0.8, lmbd=1e-3)
+  st = update(st, sample, ChainTree.like(sample, DeviceArray.from_numpy(g)))
+  man = get(st)
+  ov = osgmc.rms_prop_update(osgmc.rms_prop_init(np.zeros((3, 11)), 0.8, 1e-3), g)
+  oG, oS, _ = osgmc.rms_prop_get(ov)
+  assert man.g_inv.ndim == 1
+  assert np.array_equal(st.v.flat.numpy(), ov[0])
+  assert np.array_equal(man.g_inv.tensor.flat.numpy(), oG)
+  assert np.array_equal(man.sqrt_g_inv.tensor.flat.numpy(), oS)
+  assert set(man.g_inv.tensor.to_host()) == {"a", "b"}
+
+
+def test_host_loader_gives_each_chain_its_own_stream(gpu):
+  """Reference semantics: NumpyDataLoader chains are seeded by the chain id
+  (numpy_loader.py:263), so two chains of one run see different minibatches."""
+  from jax_sgmc_b200 import data, glm, integrator, potential, scheduler
+  X, y, _ = odata.logistic_dataset(50, 8, seed=4)
+  loader = data.NumpyDataLoader(x=X, y=y)
+  batch_fn = data.random_reference_data(loader, 4, 5)
+  pot = potential.minibatch_potential(glm.FlatPrior(), glm.LogisticRegression())
+  init_fn, update_fn, get_fn = integrator.langevin_diffusion(pot, batch_fn)
+  state = init_fn([{"w": np.zeros(8, np.float32)}] * 2)
+  state = update_fn(state, scheduler.schedule(0.01, 1.0, 1.0, True))
+  U = state.potential.numpy()
+  opot = osgmc.minibatch_potential(osgmc.Logistic(8, 0), osgmc.Prior("flat"))
+  for c in range(2):
+    idx = odata.HostDraws(50, 5, seed=c).draw()
+    wU, _, _ = opot(np.zeros((1, 8), np.float32), (X[idx], y[idx]), 50)
+    np.testing.assert_allclose(U[c], wU[0], rtol=1e-5)

@@ -1,0 +1,116 @@
+"""Host-side glue of the product package (no GPU): pytree ordering, schedules,
+host-loader index draws, argument validation -- checked against the oracle and
+the values the reference's own docs print."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import data as odata
+from oracle import scheduler as osched
+from oracle import tree as otree
+
+GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden",
+                                   "reference_values.json")))
+
+
+def test_tree_flatten_order_matches_jax_convention():
+  from jax_sgmc_b200 import tree_util
+  tree = {"w": np.zeros((4, 1)), "log_sigma": np.array(2.5),
+          "nested": (np.ones(2), [np.ones(3), None])}
+  leaves, treedef = tree_util.tree_flatten(tree)
+  # dict keys sorted: log_sigma, nested(...), w
+  assert [np.shape(l) for l in leaves] == [(), (2,), (3,), (4, 1)]
+  back = tree_util.tree_unflatten(treedef, leaves)
+  assert sorted(back) == sorted(tree) and back["nested"][1][1] is None
+  o_leaves, _ = otree.tree_flatten(tree)
+  assert [l.shape for l in o_leaves] == [np.shape(l) for l in leaves]
+
+
+def test_schedules_match_oracle_and_doc_values():
+  from jax_sgmc_b200 import scheduler
+  s = scheduler.polynomial_step_size_first_last(first=0.05, last=0.001)
+  st = s.init(1000)
+  assert np.array_equal(st, osched.polynomial_step_size_first_last(1000, 0.05, 0.001))
+  g = GOLD["scheduler"]
+  p = scheduler.polynomial_step_size(a=g["a"], b=g["b"], gamma=0.1)
+  assert round(float(p.get(p.init(5), 1)), 2) == g["gamma_0.1"]["step1"]
+  b = scheduler.initial_burn_in(3)
+  state, collected = b.init(10)
+  assert collected == 7
+  assert [float(b.get(state, i)) for i in range(5)] == [0, 0, 0, 1, 1]
+
+
+def test_init_scheduler_defaults_and_composition():
+  """tests/test_scheduler.py:28-78: default step size 1.0, temperature 1.0,
+  no burn-in, accept everything."""
+  from jax_sgmc_b200 import scheduler
+  init_fn, next_fn, get_fn = scheduler.init_scheduler(progress_bar=False)
+  st, static = init_fn(10)
+  assert static.samples_collected == 10
+  sch = get_fn(st)
+  assert float(sch.step_size) == 1.0 and float(sch.temperature) == 1.0
+  assert float(sch.burn_in) == 1.0 and sch.accept is True
+  st = next_fn(st)
+  assert st.state == (1, 10)
+
+
+def test_host_loader_draws_match_reference_docs():
+  from jax_sgmc_b200 import data
+  pytest.importorskip("ctypes")
+  g = GOLD["host_loader_draws"]
+
+  class _Fake(data.NumpyDataLoader):     # no device upload needed for index draws
+    def __init__(self, n):
+      self._observation_count = n
+      self._chains = []
+
+  dl = _Fake(g["N"])
+  c = dl.register_random_pipeline(cache_size=1, mb_size=2, seed=0)
+  assert dl.get_indices(c)[0][0].tolist() == g["seed0_mb2_first"]
+  dl = _Fake(g["N"])
+  c = dl.register_random_pipeline(cache_size=2, mb_size=3)       # seed = chain id 0
+  draws = np.concatenate([dl.get_indices(c)[0], dl.get_indices(c)[0]])
+  assert draws[3].tolist() == g["seed0_mb3_fourth_random"]
+  # same stream as the oracle
+  h = odata.HostDraws(g["N"], 3, seed=0)
+  for row in draws:
+    assert row.tolist() == h.draw().tolist()
+
+
+def test_shuffle_modes_cover_the_data_set():
+  """tests/test_data.py shuffle coverage: every observation once per epoch."""
+  from jax_sgmc_b200 import data
+
+  class _Fake(data.NumpyDataLoader):
+    def __init__(self, n):
+      self._observation_count = n
+      self._chains = []
+
+  dl = _Fake(10)
+  c = dl.register_random_pipeline(cache_size=5, mb_size=2, shuffle=True)
+  idx, mask = dl.get_indices(c)
+  assert sorted(idx.ravel().tolist()) == list(range(10)) and mask.all()
+  dl = _Fake(10)
+  c = dl.register_random_pipeline(cache_size=4, mb_size=3, shuffle=True, in_epochs=True)
+  idx, mask = dl.get_indices(c)
+  assert sorted(idx[mask].tolist()) == list(range(10))
+  assert mask.sum() == 10
+  with pytest.raises(ValueError):
+    dl.register_random_pipeline(cache_size=1, mb_size=2, in_epochs=True)
+  with pytest.raises(ValueError):
+    dl.register_random_pipeline(cache_size=1, mb_size=11)
+
+
+def test_potential_rejects_unknown_callables_and_strategies():
+  from jax_sgmc_b200 import glm, potential
+  lk, pr = glm.LogisticRegression(), glm.FlatPrior()
+  with pytest.raises(NotImplementedError):
+    potential.minibatch_potential(pr, lk, strategy="bogus")      # potential.py:156
+  with pytest.raises(TypeError):
+    potential.minibatch_potential(pr, lambda s, o: 0.0)
+  with pytest.raises(AssertionError):
+    potential.full_potential(pr, lk, strategy="pmap")            # potential.py:254
+  with pytest.raises(NotImplementedError):
+    lk({}, {})
