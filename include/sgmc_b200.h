@@ -249,6 +249,29 @@ int sgmc_resgld_decide(void* stream, const float* U_normal, const float* U_hot,
 int sgmc_swap_rows(void* stream, void* a, void* b, const int32_t* exchange,
                    int64_t n_rows, int64_t row_bytes);
 
+/* reSGLD with a ladder of n_replicas temperatures sharded over GPUs
+ * (BASELINE.json configs[3]); extends solver.py:273-291 from 2 to R replicas
+ * by exchanging temperature LABELS instead of chain states, so that only the
+ * all-gathered (U, var) scalars cross NVLink and every rank replays the same
+ * decisions from the same keys.
+ *   gathered f32[R][2][B]: potential row and variance row of replica r
+ *            (the all-gather of every rank's local values, rank-major);
+ *   holder   int32[R][B]: replica running system b at temperature index t
+ *            (in/out, replicated on every rank);
+ *   ssq f32[R-1][B] (in/out), F f32[B], temps f32[R], keys uint32[R-1][B][2];
+ *   exchange int32[R-1][B] (out): pair (t, t+1) of system b swapped labels;
+ *   temp_per_chain f32[n_local][B], temp_index int32[n_local][B] (out): the
+ *            temperature each local replica's systems run at next step.
+ * Pair p is attempted every step when R == 2 (the reference), else iff
+ * p % 2 == step % 2.  `step` is the already incremented counter (>= 1). */
+int sgmc_resgld_ladder_step(void* stream, const float* gathered, int32_t* holder,
+                            float* ssq, const float* F, const float* temps,
+                            const uint32_t* keys_in, uint32_t* keys_out,
+                            int32_t* exchange, int n_replicas, int64_t n_systems,
+                            int64_t step, int first_local_replica,
+                            int n_local_replicas, float* temp_per_chain,
+                            int32_t* temp_index, int prng_layout);
+
 /* ---- NCCL over NVLink (multi-GPU exchange steps).  libnccl.so.2 is resolved
  *      with dlopen at first use; no link-time dependency.  Used by the reSGLD
  *      replica exchange (all-gather of per-replica (U, var), solver.py:273-291

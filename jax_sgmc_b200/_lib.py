@@ -82,6 +82,8 @@ PROTOTYPES = {
     "sgmc_resgld_decide": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _f32, _f32, _vp,
                            _vp, _vp, _i64, _int],
     "sgmc_swap_rows": [_vp, _vp, _vp, _vp, _i64, _i64],
+    "sgmc_resgld_ladder_step": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _int,
+                                _i64, _i64, _int, _int, _vp, _vp, _int],
     "sgmc_nccl_unique_id": [_vp],
     "sgmc_nccl_init": [C.POINTER(_vp), _vp, _int, _int],
     "sgmc_nccl_destroy": [_vp],

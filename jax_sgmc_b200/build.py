@@ -17,7 +17,8 @@ OUT_DIR = os.path.join(HERE, "_C")
 LIB = os.path.join(OUT_DIR, "libsgmc_b200.so")
 
 SOURCES = ["runtime.cu", "prng_kernels.cu", "update_kernels.cu", "glm_simt.cu",
-           "glm_tc.cu", "resgld.cu", "nccl_shim.cu", "adaption_kernels.cu"]
+           "glm_tc.cu", "resgld.cu", "nccl_shim.cu", "adaption_kernels.cu",
+           "resgld_ladder.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3",

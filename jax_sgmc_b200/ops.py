@@ -236,6 +236,15 @@ def resgld_decide(U_n, U_h, var_n, ssq, F, step, T_normal, T_hot, keys_in,
             _layout(layout))
 
 
+def resgld_ladder_step(gathered, holder, ssq, F, temps, keys_in, keys_out, exchange,
+                       n_replicas, n_systems, step, first_local, n_local,
+                       temp_per_chain, temp_index, layout=0, stream=None):
+  _lib.call("sgmc_resgld_ladder_step", _s(stream), vp(gathered), vp(holder), vp(ssq),
+            vp(F), vp(temps), vp(keys_in), vp(keys_out), vp(exchange),
+            int(n_replicas), int(n_systems), int(step), int(first_local),
+            int(n_local), vp(temp_per_chain), vp(temp_index), _layout(layout))
+
+
 def swap_rows(a: DeviceArray, b: DeviceArray, exchange: DeviceArray, stream=None):
   n_rows = exchange.size
   row_bytes = a.nbytes // max(n_rows, 1)
