@@ -230,7 +230,8 @@ def run_b200(args):
   idx = DA((n,), np.int32)
   U, var = DA((C,), np.float32), DA((C,), np.float32)
   spec = ops.glm_spec("logistic", d, 0, prior="gaussian", prior_off=0,
-                      prior_size=d, prior_scale=10.0)
+                      prior_size=d, prior_scale=10.0,
+                      x_absmax=ops.absmax(X))   # data-set statistic, computed once
   ws = ops.glm_workspace(C, n, d, path)
   eps = 1e-3
   state = {"k": 0}

@@ -213,7 +213,14 @@ typedef struct {
   int32_t prior_size;
   float   prior_scale;
   float   temperature;     /* potential temperature T (potential.py:99) */
+  float   x_absmax;        /* max |X| over the data set if known (> 0): lets the
+                              tensor-core path pick its fp16 scale without a
+                              per-minibatch reduction; 0 = compute per call */
 } sgmc_glm_spec;
+
+/* out[0] = max |x[i]| (device scalar; e.g. the data-set bound for
+ * sgmc_glm_spec.x_absmax, computed once when a data set is registered). */
+int sgmc_absmax(void* stream, const float* x, int64_t n, float* out);
 
 /* `workspace` is device scratch of at least sgmc_glm_workspace_bytes(C, n)
  * bytes (residuals and per-observation likelihoods between the two GEMM-shaped

@@ -21,7 +21,8 @@ class GlmSpec(C.Structure):
   _fields_ = [("family", C.c_int32), ("d", C.c_int32), ("w_off", C.c_int32),
               ("aux_off", C.c_int32), ("prior", C.c_int32),
               ("prior_off", C.c_int32), ("prior_size", C.c_int32),
-              ("prior_scale", C.c_float), ("temperature", C.c_float)]
+              ("prior_scale", C.c_float), ("temperature", C.c_float),
+              ("x_absmax", C.c_float)]
 
 
 _vp, _i64, _i32, _f32, _sz = C.c_void_p, C.c_int64, C.c_int32, C.c_float, C.c_size_t
@@ -68,6 +69,7 @@ PROTOTYPES = {
     "sgmc_rms_prop_update": [_vp, _vp, _vp, _i64, _f32],
     "sgmc_rms_prop_get": [_vp, _vp, _vp, _vp, _i64, _f32],
     "sgmc_axpby": [_vp, _vp, _f32, _vp, _f32, _vp, _i64],
+    "sgmc_absmax": [_vp, _vp, _i64, _vp],
     "sgmc_sghmc_begin": [_vp, _vp, _vp, _vp, _vp, _i64, C.POINTER(_i64), _int,
                          _f32, _vp, _int],
     "sgmc_sghmc_step": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, C.POINTER(_i64),

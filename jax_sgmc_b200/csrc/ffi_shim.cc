@@ -119,7 +119,7 @@ static ffi::Error GlmPotentialGradImpl(
     int32_t path, ffi::ResultBuffer<ffi::F32> potential, ffi::ResultBuffer<ffi::F32> variance,
     ffi::ResultBuffer<ffi::F32> grad) {
   sgmc_glm_spec spec{family, (int32_t)X.dimensions()[1], w_off, aux_off, prior, prior_off,
-                     prior_size, prior_scale, temperature};
+                     prior_size, prior_scale, temperature, /*x_absmax=*/0.0f};
   return Status(sgmc_glm_potential_grad(
       stream, &spec, theta.typed_data(), theta.dimensions()[0], theta.dimensions()[1],
       X.typed_data(), y.typed_data(), idx.typed_data(), nullptr, idx.dimensions()[0],

@@ -224,7 +224,11 @@ int glm_simt(cudaStream_t stream, const GlmArgs& a) {
 
 using namespace sgmc;
 
+namespace sgmc { int glm_tc_debug_read(unsigned long long* out); }
+
 extern "C" {
+
+int sgmc_debug_tc_timers(unsigned long long* out8) { return sgmc::glm_tc_debug_read(out8); }
 
 size_t sgmc_glm_workspace_bytes(int64_t n_chains, int64_t batch_size, int64_t d,
                                 int path) {

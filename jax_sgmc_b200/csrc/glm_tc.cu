@@ -38,6 +38,14 @@ constexpr int kTcThreads = 512;               // 16 warps
 constexpr int kTcWarps = kTcThreads / 32;
 constexpr uint32_t kTmemCols = 256;
 
+// debug timers (globaltimer ns) of CTA 0: [start, setup done, mainloop done, end]
+__device__ unsigned long long g_tc_dbg[8];
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
 // ---------------------------------------------------------------------------
 // PTX wrappers
 // ---------------------------------------------------------------------------
@@ -161,6 +169,11 @@ struct TcLinkEpi {      // GEMM1: z -> ell statistics, R = cot*mask*dl/dz as fp1
   float* ell;               // f32[C][n] or null (only when the caller wants it)
   float* stats;             // f32[C][parts][4]
   int parts;
+  // last-arriver finalisation (U, var) per 128-row block
+  uint32_t* counters;       // u32[ceil(C/128)], zeroed by k_prepare_all
+  const float* row_sumsq;   // f32[C]: sum theta^2 over the gaussian-prior range
+  float* potential; float* variance;
+  float n_obs, inv_temperature, prior_half_inv;   // N, 1/T, 0.5/scale^2 (0: no gaussian prior)
   __half* r_hi; __half* r_lo;          // fp16[C][n]  (path 1)
   __nv_bfloat16* r_bf;                 // bf16[C][n]  (path 2)
   int C, n;
@@ -180,10 +193,10 @@ __device__ __forceinline__ void logistic_link_fast(float z, float y, float& ell,
   const float e = __expf(-fabsf(z));
   const float den = 1.0f + e;
   // log1p(e): log(1+e) loses e below 2^-24; the series e - e^2/2 covers small e
-  const float lp = e > 1e-3f ? __logf(den) : e * (1.0f - 0.5f * e);
+  const float lp = __logf(den);     // abs. error <= 1 ulp(1) = 6e-8 (|ell| >= 7 when e < 1e-3)
   ell = y * z - (fmaxf(z, 0.0f) + lp);
   const float rden = __fdividef(1.0f, den);
-  dz = y - (z >= 0.0f ? rden : e * rden);
+  dz = y - (z >= 0.0f ? rden : 1.0f - rden);
 }
 
 // ---------------------------------------------------------------------------
@@ -197,7 +210,7 @@ struct TcSmem {
   static constexpr int kStageBytes = kNA * (BM * BK * 2) + kNA * (BN * BK * 2);
   static constexpr int kStages = TERMS == 3 ? 2 : 4;
   static constexpr int kPipeBytes = kStages * kStageBytes;
-  static constexpr int kAuxBytes = 256 /*barriers*/ + 2 * BN * 4 /*y, mask*/ +
+  static constexpr int kAuxBytes = 256 /*barriers*/ + 3 * BN * 4 /*y, mask, rm*/ +
                                    4 * BM * kStatFields * 4 /*row stats*/;
   static constexpr int kBytes = kPipeBytes + kAuxBytes + 1024 /*alignment slack*/;
   static_assert(kPipeBytes >= kTcWarps * 32 * 33 * 4, "staging must fit in the pipeline smem");
@@ -219,10 +232,12 @@ k_glm_tc_gemm(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
   float* s_y = reinterpret_cast<float*>(smem + S::kPipeBytes + 256);
   float* s_mask = s_y + BN;
-  float* s_stats = s_mask + BN;                    // [4 col groups][BM][4]
+  float* s_rm = s_mask + BN;                       // cot * mask * r_scale per column
+  float* s_stats = s_rm + BN;                      // [4 col groups][BM][4]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 64) g_tc_dbg[0] = gtime();
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA0);
@@ -250,11 +265,14 @@ k_glm_tc_gemm(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
     }
     s_y[threadIdx.x] = yv;
     s_mask[threadIdx.x] = mv;
+    s_rm[threadIdx.x] = link.cot * mv * link.r_scale;
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  const bool dbg = blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 64;
+  if (dbg) g_tc_dbg[1] = gtime();
 
   if (warp == 0 && lane == 0) {
     // ===== TMA producer =====
@@ -302,13 +320,30 @@ k_glm_tc_gemm(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
 
   // ===== epilogue: all 16 warps =====
   __syncwarp();
+  const int q = warp & 3;                  // TMEM lane quarter this warp may access
+  const int cg = warp >> 2;                // column group: 64 columns
+  // GEMM2: the prior-gradient operand theta[row][col] does not depend on the
+  // accumulator -> fetch it (coalesced, 64 loads in flight per thread) while the
+  // tensor pipe is still busy, so the epilogue itself only stores.
+  float thp[2][32];
+  if (EPI == 1) {
+#pragma unroll
+    for (int c2 = 0; c2 < 2; ++c2) {
+      const int col0 = n0 + cg * 64 + c2 * 32, row0 = m0 + q * 32;
+      const int p = gradp.w_off + col0 + lane;
+      const bool want = (row0 + 32 <= gradp.C) && (col0 + 32 <= gradp.d) &&
+                        p >= gradp.prior_lo && p < gradp.prior_hi;
+      const float* tp = gradp.theta + (int64_t)row0 * gradp.P + p;
+#pragma unroll
+      for (int r = 0; r < 32; ++r) thp[c2][r] = want ? __ldg(tp + (int64_t)r * gradp.P) : 0.f;
+    }
+  }
   mbar_wait(tmem_full_bar, 0);
   tc_fence_after();
+  if (dbg) g_tc_dbg[2] = gtime();
   // All TMA writes have landed and all MMAs have read them: the pipeline smem
   // is free and becomes 16 private 32x33 f32 transpose buffers.
   float* stage = reinterpret_cast<float*>(tiles) + warp * (32 * 33);
-  const int q = warp & 3;                  // TMEM lane quarter this warp may access
-  const int cg = warp >> 2;                // column group: 64 columns
   const int row = m0 + q * 32 + lane;      // this thread's accumulator row
   const int rsub = lane >> 4, csub = (lane & 15) * 2;   // packed 2-row store mapping
 
@@ -323,30 +358,57 @@ k_glm_tc_gemm(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
       const int col0 = n0 + ct;
       uint32_t acc[32];
       tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)ct, acc);
+      if (dbg && c == 0) g_tc_dbg[4] = gtime();
       if (col0 >= link.n) continue;                      // warp-uniform
       float ellv[32];
+      const bool full_cols = col0 + 32 <= link.n;        // warp-uniform
+      if (full_cols) {
+        // interior chunk: no per-element bounds logic; the running shift of the
+        // one-pass variance is the first likelihood this thread sees
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const float z = fmaf(__uint_as_float(acc[j]), inv, bias);
-        float l, dz;
-        logistic_link_fast(z, s_y[ct + j], l, dz);
-        const float m = s_mask[ct + j];
-        ellv[j] = l;
-        stage[lane * 33 + j] = dz * (link.cot * m) * link.r_scale;
-        if (col0 + j < link.n) {
-          if (cnt == 0.f) shift = l;
-          const float dl = l - shift;
-          cnt += 1.f; s1 += dl; s2 = fmaf(dl, dl, s2); sm = fmaf(l, m, sm);
+        for (int j = 0; j < 32; ++j) {
+          const float z = fmaf(__uint_as_float(acc[j]), inv, bias);
+          float l, dz;
+          logistic_link_fast(z, s_y[ct + j], l, dz);
+          ellv[j] = l;
+          stage[lane * 33 + j] = dz * s_rm[ct + j];
+        }
+        if (cnt == 0.f) shift = ellv[0];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float dl = ellv[j] - shift;
+          s1 += dl;
+          s2 = fmaf(dl, dl, s2);
+          sm = fmaf(ellv[j], s_mask[ct + j], sm);
+        }
+        cnt += 32.f;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float z = fmaf(__uint_as_float(acc[j]), inv, bias);
+          float l, dz;
+          logistic_link_fast(z, s_y[ct + j], l, dz);
+          const float m = s_mask[ct + j];
+          ellv[j] = l;
+          stage[lane * 33 + j] = dz * s_rm[ct + j];
+          if (col0 + j < link.n) {
+            if (cnt == 0.f) shift = l;
+            const float dl = l - shift;
+            cnt += 1.f; s1 += dl; s2 = fmaf(dl, dl, s2); sm = fmaf(l, m, sm);
+          }
         }
       }
       __syncwarp();
+      if (dbg && c == 0) g_tc_dbg[5] = gtime();
       // coalesced R stores: two rows per instruction, two columns per lane
-#pragma unroll 4
+      const int64_t ro0 = (int64_t)(m0 + q * 32 + rsub) * link.n + col0 + csub;
+      const bool full_tile = (m0 + q * 32 + 32 <= link.C) && (col0 + 32 <= link.n);
+#pragma unroll
       for (int r = 0; r < 32; r += 2) {
         const int rr = r + rsub, grow = m0 + q * 32 + rr, gcol = col0 + csub;
         const float v0 = stage[rr * 33 + csub], v1 = stage[rr * 33 + csub + 1];
-        if (grow < link.C && gcol < link.n) {      // n % 8 == 0: pairs never straddle
-          const int64_t o = (int64_t)grow * link.n + gcol;
+        if (full_tile || (grow < link.C && gcol < link.n)) {   // n % 8 == 0: pairs never straddle
+          const int64_t o = ro0 + (int64_t)r * link.n;
           if (TERMS == 3) {
             const __half2 h = __floats2half2_rn(v0, v1);
             const float2 hf = __half22float2(h);
@@ -357,6 +419,7 @@ k_glm_tc_gemm(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
           }
         }
       }
+      if (dbg && c == 0) g_tc_dbg[6] = gtime();
       if (link.ell) {                                    // optional per-observation output
         __syncwarp();
 #pragma unroll
@@ -371,6 +434,7 @@ k_glm_tc_gemm(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
       }
       __syncwarp();
     }
+    if (dbg) g_tc_dbg[7] = gtime();
     // per-row statistics of this warp's 64 columns -> smem -> combine 4 groups
     {
       float mean = 0.f, m2 = 0.f;
@@ -399,6 +463,34 @@ k_glm_tc_gemm(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
       float* o = link.stats + ((int64_t)(m0 + threadIdx.x) * link.parts + blockIdx.x) * kStatFields;
       o[0] = n_t; o[1] = mean_t; o[2] = m2_t; o[3] = sm_t;
     }
+    // The CTA that completes a 128-row block last combines its column tiles into
+    // U = (L - prior)/T (potential.py:183-185, :210) and var(ell) (integrator.py:880).
+    __shared__ int s_is_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0)
+      s_is_last = atomicAdd(&link.counters[blockIdx.y], 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (s_is_last && threadIdx.x < BM && m0 + threadIdx.x < link.C) {
+      __threadfence();
+      const int c = m0 + threadIdx.x;
+      float n_t = 0.f, mean_t = 0.f, m2_t = 0.f, sm_t = 0.f;
+      for (int g = 0; g < link.parts; ++g) {
+        const float4 st = __ldcg(reinterpret_cast<const float4*>(
+            link.stats + ((int64_t)c * link.parts + g) * kStatFields));
+        if (st.x > 0.f) {
+          const float nn = n_t + st.x, delta = st.y - mean_t;
+          mean_t += delta * (st.x / nn);
+          m2_t += st.z + delta * delta * (n_t * st.x / nn);
+          n_t = nn;
+        }
+        sm_t += st.w;
+      }
+      const float L = link.mask ? (-link.n_obs / (float)link.n) * sm_t : -link.n_obs * mean_t;
+      const float prior = -link.prior_half_inv * link.row_sumsq[c];
+      link.potential[c] = (L - prior) * link.inv_temperature;
+      if (link.variance) link.variance[c] = m2_t / (float)link.n;
+    }
   } else {
     const float inv_scale = 1.0f / (gradp.r_scale * __ldg(gradp.xt_scale));
 #pragma unroll 1
@@ -407,35 +499,51 @@ k_glm_tc_gemm(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
       const int col0 = n0 + ct;
       uint32_t acc[32];
       tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)ct, acc);
+      if (dbg && c == 0) g_tc_dbg[4] = gtime();
       if (col0 >= gradp.d) continue;
 #pragma unroll
       for (int j = 0; j < 32; ++j) stage[lane * 33 + j] = __uint_as_float(acc[j]) * inv_scale;
       __syncwarp();
+      if (dbg && c == 0) g_tc_dbg[5] = gtime();
       const int gcol = col0 + lane;
       const int p = gradp.w_off + gcol;
       const bool in_prior = p >= gradp.prior_lo && p < gradp.prior_hi;
       const bool col_ok = gcol < gradp.d;
-      // all 32 theta loads are issued before the first dependent store
-      float th[32];
+      const int row0 = m0 + q * 32;
+      const int64_t o0 = (int64_t)row0 * gradp.P + p;
+      const bool full_tile = (row0 + 32 <= gradp.C) && (col0 + 32 <= gradp.d);   // warp-uniform
+      if (full_tile) {
+        // interior tile: theta was prefetched before the accumulator wait
+        float* gp = gradp.grad + o0;
+        if (c == 0) {
 #pragma unroll
-      for (int r = 0; r < 32; ++r) {
-        const int grow = m0 + q * 32 + r;
-        th[r] = (in_prior && col_ok && grow < gradp.C)
-                    ? __ldg(gradp.theta + (int64_t)grow * gradp.P + p) : 0.f;
-      }
+          for (int r = 0; r < 32; ++r)
+            gp[(int64_t)r * gradp.P] = fmaf(thp[0][r], gradp.prior_coef, stage[r * 33 + lane]);
+        } else {
 #pragma unroll
-      for (int r = 0; r < 32; ++r) {
-        const int grow = m0 + q * 32 + r;
-        if (grow < gradp.C && col_ok)
-          gradp.grad[(int64_t)grow * gradp.P + p] =
-              fmaf(th[r], gradp.prior_coef, stage[r * 33 + lane]);
+          for (int r = 0; r < 32; ++r)
+            gp[(int64_t)r * gradp.P] = fmaf(thp[1][r], gradp.prior_coef, stage[r * 33 + lane]);
+        }
+      } else {
+        for (int r = 0; r < 32; ++r) {
+          const int grow = row0 + r;
+          if (grow < gradp.C && col_ok) {
+            const int64_t o = (int64_t)grow * gradp.P + p;
+            float g = stage[r * 33 + lane];
+            if (in_prior) g = fmaf(gradp.theta[o], gradp.prior_coef, g);
+            gradp.grad[o] = g;
+          }
+        }
       }
       __syncwarp();
+      if (dbg && c == 0) g_tc_dbg[6] = gtime();
     }
   }
+  if (dbg) g_tc_dbg[7] = gtime();
   tc_fence_before();
   __syncthreads();
   if (warp == 2) tmem_dealloc(tmem_base, kTmemCols);
+  if (dbg) g_tc_dbg[3] = gtime();
 }
 
 // ---------------------------------------------------------------------------
@@ -547,6 +655,140 @@ __global__ void k_x_prepare(const float* __restrict__ X, const int32_t* __restri
   }
 }
 
+// Both operand preparations in ONE launch (they are independent): blocks
+// [0, theta_blocks) convert Theta rows (one warp per chain row, 128-bit loads,
+// 64-bit packed stores), the remaining blocks gather / split / transpose the
+// minibatch in 32x32 tiles.  Also clears the per-row-block tile counters used by
+// GEMM1's last-arriver finalisation.
+struct PrepareArgs {
+  const float* theta; int64_t P; int w_off, d, C, prior_lo, prior_hi;
+  void* th_hi; __half* th_lo; float* row_scale; float* row_sumsq;
+  const float* X; const int32_t* idx; int n;
+  const uint32_t* absmax_bits; float static_absmax;
+  void* xb_hi; __half* xb_lo; void* xt_hi; __half* xt_lo; float* x_scale;
+  int theta_blocks, x_tiles_x;
+  uint32_t* tile_counters; int n_counters;
+};
+
+template <bool SPLIT>
+__global__ void __launch_bounds__(256) k_prepare_all(const PrepareArgs a) {
+  __shared__ float tile[32][33];
+  const int lane = threadIdx.x & 31;
+  if ((int)blockIdx.x < a.theta_blocks) {
+    if (blockIdx.x == 0)
+      for (int i = threadIdx.x; i < a.n_counters; i += 256) a.tile_counters[i] = 0u;
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= a.C) return;
+    const float* src = a.theta + (int64_t)row * a.P + a.w_off;
+    const bool vec = (a.d & 3) == 0 && (a.P & 3) == 0 && (a.w_off & 3) == 0 &&
+                     (reinterpret_cast<uintptr_t>(a.theta) & 15u) == 0;
+    float m = 0.f, sq = 0.f;
+    if (vec) {
+      for (int j = lane * 4; j < a.d; j += 128) {
+        const float4 x = *reinterpret_cast<const float4*>(src + j);
+        m = fmaxf(fmaxf(m, fmaxf(fabsf(x.x), fabsf(x.y))), fmaxf(fabsf(x.z), fabsf(x.w)));
+        if (a.w_off + j >= a.prior_lo && a.w_off + j + 3 < a.prior_hi)
+          sq += x.x * x.x + x.y * x.y + x.z * x.z + x.w * x.w;
+        else
+          for (int k = 0; k < 4; ++k) {
+            const float xv = k == 0 ? x.x : (k == 1 ? x.y : (k == 2 ? x.z : x.w));
+            if (a.w_off + j + k >= a.prior_lo && a.w_off + j + k < a.prior_hi) sq = fmaf(xv, xv, sq);
+          }
+      }
+    } else {
+      for (int j = lane; j < a.d; j += 32) {
+        const float x = src[j];
+        m = fmaxf(m, fabsf(x));
+        if (a.w_off + j >= a.prior_lo && a.w_off + j < a.prior_hi) sq = fmaf(x, x, sq);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+      sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    }
+    const float s = SPLIT ? pow2_scale_for(m) : 1.0f;
+    if (lane == 0) {
+      a.row_scale[row] = s;
+      a.row_sumsq[row] = sq;
+    }
+    const int64_t ob = (int64_t)row * a.d;
+    if (vec) {
+      for (int j = lane * 4; j < a.d; j += 128) {
+        const float4 x = *reinterpret_cast<const float4*>(src + j);   // L1 hit
+        const float v0 = x.x * s, v1 = x.y * s, v2 = x.z * s, v3 = x.w * s;
+        if (SPLIT) {
+          const __half2 h01 = __floats2half2_rn(v0, v1), h23 = __floats2half2_rn(v2, v3);
+          const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+          const __half2 l01 = __floats2half2_rn(v0 - f01.x, v1 - f01.y);
+          const __half2 l23 = __floats2half2_rn(v2 - f23.x, v3 - f23.y);
+          uint2 ph, pl;
+          ph.x = *reinterpret_cast<const uint32_t*>(&h01); ph.y = *reinterpret_cast<const uint32_t*>(&h23);
+          pl.x = *reinterpret_cast<const uint32_t*>(&l01); pl.y = *reinterpret_cast<const uint32_t*>(&l23);
+          *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(a.th_hi) + ob + j) = ph;
+          *reinterpret_cast<uint2*>(a.th_lo + ob + j) = pl;
+        } else {
+          const __nv_bfloat162 b01 = __floats2bfloat162_rn(v0, v1), b23 = __floats2bfloat162_rn(v2, v3);
+          uint2 pb;
+          pb.x = *reinterpret_cast<const uint32_t*>(&b01); pb.y = *reinterpret_cast<const uint32_t*>(&b23);
+          *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(a.th_hi) + ob + j) = pb;
+        }
+      }
+    } else {
+      for (int j = lane; j < a.d; j += 32) {
+        const float x = src[j] * s;
+        if (SPLIT) {
+          const __half h = __float2half_rn(x);
+          reinterpret_cast<__half*>(a.th_hi)[ob + j] = h;
+          a.th_lo[ob + j] = __float2half_rn(x - __half2float(h));
+        } else {
+          reinterpret_cast<__nv_bfloat16*>(a.th_hi)[ob + j] = __float2bfloat16_rn(x);
+        }
+      }
+    }
+    return;
+  }
+  // ---- minibatch tile ------------------------------------------------------------
+  const int t = blockIdx.x - a.theta_blocks;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;           // 32 x 8
+  const int n = a.n, d = a.d;
+  float s = 1.0f;
+  if (SPLIT)
+    s = pow2_scale_for(a.static_absmax > 0.f ? a.static_absmax : __uint_as_float(*a.absmax_bits));
+  if (t == 0 && threadIdx.x == 0) *a.x_scale = s;
+  const int r0 = (t / a.x_tiles_x) * 32, c0 = (t % a.x_tiles_x) * 32;
+  for (int i = ty; i < 32; i += 8) {
+    const int r = r0 + i, c = c0 + tx;
+    float v = 0.f;
+    if (r < n && c < d) {
+      const int64_t row = a.idx ? a.idx[r] : r;
+      v = a.X[row * d + c] * s;
+      if (SPLIT) {
+        const __half h = __float2half_rn(v);
+        reinterpret_cast<__half*>(a.xb_hi)[(int64_t)r * d + c] = h;
+        a.xb_lo[(int64_t)r * d + c] = __float2half_rn(v - __half2float(h));
+      } else {
+        reinterpret_cast<__nv_bfloat16*>(a.xb_hi)[(int64_t)r * d + c] = __float2bfloat16_rn(v);
+      }
+    }
+    tile[i][tx] = v;
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int c = c0 + i, r = r0 + tx;                 // transposed: row = feature c
+    if (c < d && r < n) {
+      const float v = tile[tx][i];
+      if (SPLIT) {
+        const __half h = __float2half_rn(v);
+        reinterpret_cast<__half*>(a.xt_hi)[(int64_t)c * n + r] = h;
+        a.xt_lo[(int64_t)c * n + r] = __float2half_rn(v - __half2float(h));
+      } else {
+        reinterpret_cast<__nv_bfloat16*>(a.xt_hi)[(int64_t)c * n + r] = __float2bfloat16_rn(v);
+      }
+    }
+  }
+}
+
 // One thread per chain: combine the per-tile likelihood statistics into
 // U = (L - prior)/T (potential.py:183-185, :210) and var(ell) (integrator.py:880).
 __global__ void k_glm_finalize_parts(const float* __restrict__ stats, int parts,
@@ -619,6 +861,7 @@ struct TcWorkspace {
   void* r_hi; __half* r_lo;
   float* stats;
   uint32_t* absmax_bits; float* x_scale;
+  uint32_t* counters;
 };
 
 static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
@@ -643,7 +886,9 @@ static size_t carve(TcWorkspace* w, uint8_t* base, int64_t C, int64_t n, int64_t
   void* r_lo = take((size_t)C * n * 2);
   void* stats = take((size_t)C * parts * kStatFields * 4);
   void* am = take(256);
+  void* cnt = take((size_t)((C + BM - 1) / BM) * 4);
   if (w) {
+    w->counters = (uint32_t*)cnt;
     w->th_hi = th_hi; w->th_lo = (__half*)th_lo;
     w->row_scale = (float*)rs; w->row_sumsq = (float*)rq;
     w->xb_hi = xb_hi; w->xb_lo = (__half*)xb_lo; w->xt_hi = xt_hi; w->xt_lo = (__half*)xt_lo;
@@ -652,6 +897,10 @@ static size_t carve(TcWorkspace* w, uint8_t* base, int64_t C, int64_t n, int64_t
     w->absmax_bits = (uint32_t*)am; w->x_scale = (float*)am + 1;
   }
   return off;
+}
+
+int glm_tc_debug_read(unsigned long long* out) {
+  return check_cuda(cudaMemcpyFromSymbol(out, g_tc_dbg, sizeof(unsigned long long) * 8), "dbg");
 }
 
 size_t glm_tc_workspace_bytes(int64_t n_chains, int64_t batch_size, int64_t d, int) {
@@ -693,35 +942,30 @@ int glm_tc(cudaStream_t stream, const GlmArgs& a, int path) {
   const int prior_lo = gauss_prior ? a.spec.prior_off : 0;
   const int prior_hi = gauss_prior ? a.spec.prior_off + a.spec.prior_size : 0;
 
-  // ---- operand preparation ------------------------------------------------
-  {
-    const int wpb = 8;
-    dim3 grid((unsigned)((C + wpb - 1) / wpb));
-    if (split)
-      k_theta_prepare<true><<<grid, wpb * 32, 0, stream>>>(
-          a.theta, a.P, a.spec.w_off, d, (int)C, prior_lo, prior_hi, w.th_hi, w.th_lo,
-          w.row_scale, w.row_sumsq);
-    else
-      k_theta_prepare<false><<<grid, wpb * 32, 0, stream>>>(
-          a.theta, a.P, a.spec.w_off, d, (int)C, prior_lo, prior_hi, w.th_hi, w.th_lo,
-          w.row_scale, w.row_sumsq);
-    if (post_launch("k_theta_prepare")) return 1;
-  }
-  if (split) {
+  // ---- operand preparation (one launch) -------------------------------------
+  const float x_absmax = a.spec.x_absmax > 0.f ? a.spec.x_absmax : 0.f;
+  if (split && x_absmax == 0.f) {   // no data-set bound given: reduce over the minibatch
     if (check_cuda(cudaMemsetAsync(w.absmax_bits, 0, 4, stream), "memset")) return 1;
     k_absmax_gather<<<(unsigned)((n + 7) / 8), 256, 0, stream>>>(a.X, a.idx, (int)n, d,
                                                                 w.absmax_bits);
     if (post_launch("k_absmax_gather")) return 1;
   }
   {
-    dim3 grid((d + 31) / 32, (unsigned)((n + 31) / 32)), block(32, 8);
-    if (split)
-      k_x_prepare<true><<<grid, block, 0, stream>>>(a.X, a.idx, (int)n, d, w.absmax_bits, 0.f,
-                                                    w.xb_hi, w.xb_lo, w.xt_hi, w.xt_lo, w.x_scale);
-    else
-      k_x_prepare<false><<<grid, block, 0, stream>>>(a.X, a.idx, (int)n, d, w.absmax_bits, 0.f,
-                                                     w.xb_hi, w.xb_lo, w.xt_hi, w.xt_lo, w.x_scale);
-    if (post_launch("k_x_prepare")) return 1;
+    PrepareArgs pa{};
+    pa.theta = a.theta; pa.P = a.P; pa.w_off = a.spec.w_off; pa.d = d; pa.C = (int)C;
+    pa.prior_lo = prior_lo; pa.prior_hi = prior_hi;
+    pa.th_hi = w.th_hi; pa.th_lo = w.th_lo; pa.row_scale = w.row_scale; pa.row_sumsq = w.row_sumsq;
+    pa.X = a.X; pa.idx = a.idx; pa.n = (int)n;
+    pa.absmax_bits = w.absmax_bits; pa.static_absmax = x_absmax;
+    pa.xb_hi = w.xb_hi; pa.xb_lo = w.xb_lo; pa.xt_hi = w.xt_hi; pa.xt_lo = w.xt_lo;
+    pa.x_scale = w.x_scale;
+    pa.theta_blocks = (int)((C + 7) / 8);
+    pa.x_tiles_x = (d + 31) / 32;
+    pa.tile_counters = w.counters; pa.n_counters = (int)((C + BM - 1) / BM);
+    const unsigned grid = (unsigned)(pa.theta_blocks + pa.x_tiles_x * ((n + 31) / 32));
+    if (split) k_prepare_all<true><<<grid, 256, 0, stream>>>(pa);
+    else k_prepare_all<false><<<grid, 256, 0, stream>>>(pa);
+    if (post_launch("k_prepare_all")) return 1;
   }
   // The Xb scale is computed on the device (k_x_prepare) and read by the
   // epilogues through a device scalar, so the whole op stays sync-free.
@@ -740,6 +984,10 @@ int glm_tc(cudaStream_t stream, const GlmArgs& a, int path) {
   link.cot = a.cot; link.r_scale = r_scale;
   link.ell = a.ell_requested ? a.ell : nullptr;
   link.stats = w.stats; link.parts = (int)((n + BN - 1) / BN);
+  link.counters = w.counters; link.row_sumsq = w.row_sumsq;
+  link.potential = a.potential; link.variance = a.variance;
+  link.n_obs = (float)a.N; link.inv_temperature = 1.0f / a.spec.temperature;
+  link.prior_half_inv = gauss_prior ? 0.5f / (a.spec.prior_scale * a.spec.prior_scale) : 0.f;
   link.r_hi = (__half*)w.r_hi; link.r_lo = w.r_lo; link.r_bf = (__nv_bfloat16*)w.r_hi;
   link.C = (int)C; link.n = (int)n;
   TcGradEpi gradp{};
@@ -764,10 +1012,7 @@ int glm_tc(cudaStream_t stream, const GlmArgs& a, int path) {
     if (launch_gemm<1, 0, 1>(stream, mA0, mA0, mB0, mB0, (int)C, (int)n, d, link, gradp,
                              "k_glm_tc_gemm<bf16,link>")) return 1;
   }
-  // ---- U, var(ell) from the per-tile statistics ---------------------------------
-  k_glm_finalize_parts<<<(unsigned)((C + 127) / 128), 128, 0, stream>>>(w.stats, link.parts,
-                                                                       w.row_sumsq, a);
-  if (post_launch("k_glm_finalize_parts")) return 1;
+  // U and var(ell) were finalised inside GEMM1 by the last CTA of every row block.
   if (!a.grad) return 0;
   // ---- GEMM2: G[C,d] = R[C,n] . XbT[d,n]^T ---------------------------------------
   if (make_map(&mA0, w.r_hi, !split, C, n, BM)) return 2;

@@ -145,7 +145,8 @@ k_noise_pass(const __grid_constant__ LeafTable tab,
       nk = (key_mode == kKeySplit3A) ? s1 : s2;
       write = (key_mode == kKeySplit3A);
     }
-    s_keys[idx] = split_key(nk, (uint32_t)l, (uint32_t)L, LAYOUT);
+    s_keys[idx] = key_mode == 99 ? k /* debug: no derivation */
+                                 : split_key(nk, (uint32_t)l, (uint32_t)L, LAYOUT);
     // the CTA that owns the chain's first tile publishes the new chain key
     if (write && l == 0 && c * tab.tiles_per_chain >= t0) {
       keys_out[2 * c] = newk.k0;

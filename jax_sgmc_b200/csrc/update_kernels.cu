@@ -455,7 +455,8 @@ int sgmc_normal_like(void* stream, const uint32_t* keys, float* noise,
                                aligned16({noise}))) return e;
   NormalLikeOp op{noise};
   return launch_noise_pass((cudaStream_t)stream, tab, keys, nullptr, n_chains,
-                           kKeyDirect, prng_layout, op, "sgmc_normal_like");
+                           option(1) == 99 ? 99 : kKeyDirect, prng_layout, op,
+                           "sgmc_normal_like");
 }
 
 static int sgld_common(void* stream, float* theta, float* v, const float* grad,

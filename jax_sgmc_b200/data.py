@@ -80,6 +80,14 @@ class DataLoader:
   def static_information(self):
     return {"observation_count": self._observation_count}
 
+  def absmax(self, name: str) -> float:
+    """max |leaf| over the whole data set (device reduction, computed once):
+    the bound the tensor-core potential uses to scale its fp16 operands."""
+    cache = self.__dict__.setdefault("_absmax", {})
+    if name not in cache:
+      cache[name] = ops.absmax(self.device_data[name])
+    return cache[name]
+
   @property
   def _format(self):
     return {k: ((), v.shape[1:]) for k, v in self.device_data.items()}

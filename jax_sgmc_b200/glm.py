@@ -63,7 +63,7 @@ class InvSigmaPrior(_Spec):
     self.leaf = log_sigma
 
 
-def resolve(likelihood, prior, sample, temperature: float):
+def resolve(likelihood, prior, sample, temperature: float, x_absmax: float = 0.0):
   """Build the C-ABI ``sgmc_glm_spec`` for a ChainTree layout."""
   offs, sizes = sample.offsets(), sample.sizes
   wl = sample.leaf_index(likelihood.weights)
@@ -94,4 +94,4 @@ def resolve(likelihood, prior, sample, temperature: float):
   elif not isinstance(prior, FlatPrior):
     raise TypeError("unrecognised prior")
   return ops.glm_spec(likelihood.family, d, w_off, aux_off, kind, p_off, p_size,
-                      p_scale, temperature)
+                      p_scale, temperature, x_absmax)

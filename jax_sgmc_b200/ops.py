@@ -198,10 +198,18 @@ PATH = {"simt": 0, "tc_parity": 1, "tc_throughput": 2, 0: 0, 1: 1, 2: 2}
 
 
 def glm_spec(family, d, w_off, aux_off=-1, prior="flat", prior_off=0,
-             prior_size=0, prior_scale=1.0, temperature=1.0) -> _lib.GlmSpec:
+             prior_size=0, prior_scale=1.0, temperature=1.0,
+             x_absmax=0.0) -> _lib.GlmSpec:
   return _lib.GlmSpec(FAMILY[family], int(d), int(w_off), int(aux_off),
                       PRIOR[prior], int(prior_off), int(prior_size),
-                      float(prior_scale), float(temperature))
+                      float(prior_scale), float(temperature), float(x_absmax))
+
+
+def absmax(x: DeviceArray, stream=None) -> float:
+  """max |x| of a device array (one-time data-set statistic; synchronises)."""
+  out = DeviceArray.zeros((1,), np.float32)
+  _lib.call("sgmc_absmax", _s(stream), vp(x), x.size, vp(out))
+  return float(out.numpy()[0])
 
 
 def glm_workspace(n_chains: int, batch_size: int, d: int, path=0) -> DeviceArray:

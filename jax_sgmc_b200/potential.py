@@ -51,7 +51,8 @@ class _PotentialFn:
            var_out: Optional[DeviceArray] = None):
     batch, info = reference_data
     assert isinstance(batch, BatchRef), "reference_data must come from jax_sgmc_b200.data"
-    spec = glm.resolve(self.likelihood, self.prior, sample, self.temperature)
+    spec = glm.resolve(self.likelihood, self.prior, sample, self.temperature,
+                       batch.loader.absmax(self.likelihood.x))
     C, P, n = sample.n_chains, sample.n_params, batch.n
     N = int(info.observation_count)
     X = batch.loader.device_data[self.likelihood.x]
