@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_C", "libsgmc_b200.so")
+LIB_PATH = os.environ.get("SGMC_LIB_PATH",
+                          os.path.join(_HERE, "_C", "libsgmc_b200.so"))
 
 
 class SgmcError(RuntimeError):

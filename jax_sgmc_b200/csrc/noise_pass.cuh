@@ -24,7 +24,7 @@
 
 namespace sgmc {
 
-constexpr int kNoiseThreads = 128;
+constexpr int kNoiseThreads = 512;
 constexpr int kNoiseWarps = kNoiseThreads / 32;
 
 struct LeafTable {
@@ -62,13 +62,13 @@ int plan_noise_launch(const LeafTable& t, int64_t n_chains, const void* kernel,
 // Noise for one group: pairs j0..j0+3 of a leaf with `size` elements.
 // nA[q] belongs to element j0+q (valid if j0+q < half), nB[q] to element
 // half + j0 + q (valid if that is < size).
-template <int LAYOUT>
+template <int LAYOUT, bool FULL = false>
 __device__ __forceinline__ void pair_bits(Key lk, uint32_t j, uint32_t half,
                                           uint32_t size, uint32_t& wa,
                                           uint32_t& wb) {
   if (LAYOUT == 0) {
     wa = j;
-    wb = (j + half < size) ? j + half : 0u;
+    wb = (FULL || j + half < size) ? j + half : 0u;   // FULL: partner known valid
     threefry2x32(lk, wa, wb);
   } else {
     uint32_t a0 = 0u, a1 = j;
@@ -80,7 +80,7 @@ __device__ __forceinline__ void pair_bits(Key lk, uint32_t j, uint32_t half,
   }
 }
 
-template <int LAYOUT>
+template <int LAYOUT, bool FULL = false>
 __device__ __forceinline__ void group_noise(Key lk, uint32_t j0, uint32_t half,
                                             uint32_t size, float nA[4],
                                             float nB[4]) {
@@ -88,7 +88,7 @@ __device__ __forceinline__ void group_noise(Key lk, uint32_t j0, uint32_t half,
   for (int q = 0; q < 4; ++q) {
     NormalPartial pa, pb;
     uint32_t wa, wb;
-    pair_bits<LAYOUT>(lk, j0 + q, half, size, wa, wb);
+    pair_bits<LAYOUT, FULL>(lk, j0 + q, half, size, wa, wb);
     nA[q] = normal_main(wa, pa);
     nB[q] = normal_main(wb, pb);
     // 0.34 % of the draws need erf_inv's w >= 5 polynomial
@@ -113,7 +113,7 @@ __device__ __forceinline__ void group_noise(Key lk, uint32_t j0, uint32_t half,
 // eA/eB/e are element offsets inside the chain (for per-parameter vectors such
 // as mass or friction).
 template <int LAYOUT, class Op>
-__global__ void __launch_bounds__(kNoiseThreads, 8)
+__global__ void __launch_bounds__(kNoiseThreads, 2)
 k_noise_pass(const __grid_constant__ LeafTable tab,
              const uint32_t* __restrict__ keys_in,
              uint32_t* __restrict__ keys_out, int64_t n_chains,
@@ -159,9 +159,13 @@ k_noise_pass(const __grid_constant__ LeafTable tab,
   // rotate the first warp per CTA so the odd tiles of the CTAs spread evenly
   // over the four SM sub-partitions (warp w runs on sub-partition w % 4)
   const int wrot = (warp + blockIdx.x) & (kNoiseWarps - 1);
-  for (int64_t tile = t0 + wrot; tile < t1; tile += kNoiseWarps) {
-    const int64_t c = tile / tab.tiles_per_chain;
-    const uint32_t g = (uint32_t)(tile - c * tab.tiles_per_chain) * 32u + lane;
+  // (chain, tile-in-chain) advance incrementally: no division in the loop
+  const uint32_t tpc = tab.tiles_per_chain;
+  int64_t c = (t0 + wrot) / tpc;
+  uint32_t lt = (uint32_t)((t0 + wrot) - c * tpc);
+  for (int64_t tile = t0 + wrot; tile < t1; tile += kNoiseWarps, lt += kNoiseWarps) {
+    while (lt >= tpc) { lt -= tpc; ++c; }
+    const uint32_t g = lt * 32u + lane;
     float partial = 0.0f;
     if (g < tab.groups) {
       int l = 0;
@@ -176,7 +180,7 @@ k_noise_pass(const __grid_constant__ LeafTable tab,
       if (tab.vec_ok[l] && j0 + 4u <= half) {
         typename Op::Regs r;
         op.load_vec(r, base + j0, base + half + j0);   // loads first ...
-        group_noise<LAYOUT>(lk, j0, half, size, nA, nB);  // ... then ALU work
+        group_noise<LAYOUT, true>(lk, j0, half, size, nA, nB);  // ... then ALU work
         partial = op.apply_vec(r, nA, nB, base + j0, base + half + j0, c, eA, eB);
       } else {
         group_noise<LAYOUT>(lk, j0, half, size, nA, nB);
