@@ -151,6 +151,15 @@ int sgmc_rms_prop_get(void* stream, const float* v, float* g_inv,
 int sgmc_axpby(void* stream, float* out, float a, const float* x, float b,
                const float* y, int64_t n);
 
+/* util.tree_scale / tree_add / tree_multiply / tree_dot
+ * (util/tree_util.py:58-133) on the flat chain-batched layout.
+ * op 0: out = alpha*x (tree_scale), 1: out = x + y (tree_add),
+ * 2: out = x*y (tree_multiply); tree_dot: out[c] = <x[c,:], y[c,:]>. */
+int sgmc_tree_ewise(void* stream, int op, float* out, float alpha,
+                    const float* x, const float* y, int64_t n);
+int sgmc_tree_dot(void* stream, float* out, const float* x, const float* y,
+                  int64_t n_chains, int64_t P);
+
 /* integrator.friction_leapfrog (integrator.py:563-765).
  * begin: key', split = split(key); p = sqrt(m) * random_tree(split)  (:736-738)
  *        fused with the first position update theta += eps * (p / m) (:610-612).

@@ -71,6 +71,8 @@ PROTOTYPES = {
     "sgmc_rms_prop_get": [_vp, _vp, _vp, _vp, _i64, _f32],
     "sgmc_axpby": [_vp, _vp, _f32, _vp, _f32, _vp, _i64],
     "sgmc_absmax": [_vp, _vp, _i64, _vp],
+    "sgmc_tree_ewise": [_vp, _int, _vp, _f32, _vp, _vp, _i64],
+    "sgmc_tree_dot": [_vp, _vp, _vp, _vp, _i64, _i64],
     "sgmc_sghmc_begin": [_vp, _vp, _vp, _vp, _vp, _i64, C.POINTER(_i64), _int,
                          _f32, _vp, _int],
     "sgmc_sghmc_step": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, C.POINTER(_i64),

@@ -18,13 +18,13 @@ LIB = os.path.join(OUT_DIR, "libsgmc_b200.so")
 
 SOURCES = ["runtime.cu", "prng_kernels.cu", "update_kernels.cu", "glm_simt.cu",
            "glm_tc.cu", "resgld.cu", "nccl_shim.cu", "adaption_kernels.cu",
-           "resgld_ladder.cu", "misc_kernels.cu"]
+           "resgld_ladder.cu", "misc_kernels.cu", "tree_kernels.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3",
     "-std=c++17", "-Xcompiler", "-fPIC",
     "--expt-relaxed-constexpr",
-]
+] + ([f"-DSGMC_TC_BK={os.environ['SGMC_TC_BK']}"] if os.environ.get("SGMC_TC_BK") else [])
 
 
 def _nvcc() -> str:

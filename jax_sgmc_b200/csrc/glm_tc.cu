@@ -33,7 +33,11 @@
 
 namespace sgmc {
 
-constexpr int BM = 128, BN = 256, BK = 64;       // tile (elements)
+#ifndef SGMC_TC_BK
+#define SGMC_TC_BK 64
+#endif
+constexpr int BM = 128, BN = 256, BK = SGMC_TC_BK;   // tile (elements); BK*2 B = swizzle span
+static_assert(BK == 64 || BK == 32, "BK must be 64 (128B swizzle) or 32 (64B swizzle)");
 constexpr int kTcThreads = 512;               // 16 warps
 constexpr int kTcWarps = kTcThreads / 32;
 constexpr uint32_t kTmemCols = 256;
@@ -140,9 +144,9 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
   d |= (uint64_t)1 << 16;
-  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)((8 * BK * 2) >> 4) << 32;            // SBO: 8 rows of BK*2 bytes
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
+  d |= (uint64_t)(BK == 64 ? 2 : 4) << 61;             // SWIZZLE_128B / SWIZZLE_64B
   return d;
 }
 // kind::f16 instruction descriptor: fp32 accumulate, A/B format (0 fp16, 1 bf16),
@@ -208,7 +212,7 @@ template <int TERMS>
 struct TcSmem {
   static constexpr int kNA = TERMS == 3 ? 2 : 1;
   static constexpr int kStageBytes = kNA * (BM * BK * 2) + kNA * (BN * BK * 2);
-  static constexpr int kStages = TERMS == 3 ? 2 : 4;
+  static constexpr int kStages = (TERMS == 3 ? 2 : 4) * (64 / BK);
   static constexpr int kPipeBytes = kStages * kStageBytes;
   static constexpr int kAuxBytes = 256 /*barriers*/ + 3 * BN * 4 /*y, mask, rm*/ +
                                    4 * BM * kStatFields * 4 /*row stats*/;
@@ -849,7 +853,8 @@ static int make_map(CUtensorMap* m, const void* ptr, int bf16, int64_t rows, int
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(m, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16,
                   2, const_cast<void*>(ptr), gdim, gstr, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  BK == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   SGMC_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d)", (int)r);
   return 0;

@@ -151,6 +151,17 @@ def rms_prop_get(v, g_inv, sqrt_g_inv, lmbd=1e-5, stream=None):
             v.size, float(lmbd))
 
 
+def tree_ewise(op: int, out, alpha, x, y=None, stream=None):
+  """op 0: alpha*x, 1: x+y, 2: x*y (flat chain-batched buffers)."""
+  _lib.call("sgmc_tree_ewise", _s(stream), int(op), vp(out), float(alpha), vp(x),
+            vp(y if y is not None else x), out.size)
+
+
+def tree_dot(out, x, y, stream=None):
+  C_, P = x.shape
+  _lib.call("sgmc_tree_dot", _s(stream), vp(out), vp(x), vp(y), C_, P)
+
+
 def axpby(out, a, x, b, y, stream=None):
   _lib.call("sgmc_axpby", _s(stream), vp(out), float(a), vp(x), float(b), vp(y),
             out.size)

@@ -179,6 +179,50 @@ class ChainTree:
     return f"ChainTree(chains={self.n_chains}, params={self.n_params}, leaves={len(self.sizes)})"
 
 
+# -- pytree vector-space operations (util/tree_util.py:38-133) --------------------
+# Every ChainTree operand is a flat f32[C, P] device buffer, so the leaf-wise
+# tree_map of the reference becomes one elementwise kernel.
+
+def _ewise(op: int, alpha, a: "ChainTree", b: "ChainTree" = None) -> "ChainTree":
+  from . import ops
+  out = DeviceArray(a.flat.shape, np.float32)
+  ops.tree_ewise(op, out, alpha, a.flat, None if b is None else b.flat)
+  return ChainTree.like(a, out)
+
+
+def tree_scale(alpha, tree: "ChainTree") -> "ChainTree":
+  """util/tree_util.py:83-96: ``alpha * x`` on every leaf."""
+  return _ewise(0, float(alpha), tree)
+
+
+def tree_add(tree_a: "ChainTree", tree_b: "ChainTree") -> "ChainTree":
+  """util/tree_util.py:99-110."""
+  return _ewise(1, 0.0, tree_a, tree_b)
+
+
+def tree_multiply(tree_a: "ChainTree", tree_b: "ChainTree") -> "ChainTree":
+  """util/tree_util.py:58-80."""
+  return _ewise(2, 0.0, tree_a, tree_b)
+
+
+def tree_dot(tree_a: "ChainTree", tree_b: "ChainTree") -> DeviceArray:
+  """util/tree_util.py:120-133, one scalar per chain: ``f32[C]``."""
+  from . import ops
+  out = DeviceArray((tree_a.n_chains,), np.float32)
+  ops.tree_dot(out, tree_a.flat, tree_b.flat)
+  return out
+
+
+def tensor_matmul(matrix: Tensor, vector: "ChainTree") -> "ChainTree":
+  """util/tree_util.py:38-56: scalar (ndim 0) and diagonal (ndim 1) tensors;
+  dense matrices (ndim 2) are outside the fused path."""
+  if matrix.ndim == 0:
+    return tree_scale(matrix.tensor, vector)
+  if matrix.ndim == 1:
+    return tree_multiply(matrix.tensor, vector)
+  raise NotImplementedError(f"Cannot multiply matrix with dimension {matrix.ndim}")
+
+
 def unravel_rows(flat: np.ndarray, treedef, shapes) -> PyTree:
   """Inverse of the chain-wise ravel for a host array ``[..., P]``."""
   out, off = [], 0
