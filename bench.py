@@ -37,7 +37,7 @@ BYTES_PER_PARAM = {"sgld": 12, "sgld_rms": 20}
 def parse():
   p = argparse.ArgumentParser()
   p.add_argument("--gpus", type=int, default=1)
-  p.add_argument("--steps", type=int, default=200)
+  p.add_argument("--steps", type=int, default=2000)
   p.add_argument("--warmup", type=int, default=10)
   p.add_argument("--impl", default="b200", choices=["b200", "reference"])
   p.add_argument("--chains", type=int, default=4096)
@@ -66,7 +66,7 @@ class ClockSampler:
     try:
       self.proc = subprocess.Popen(
           ["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}",
-           "--format=csv,noheader,nounits", "-lms", "100"],
+           "--format=csv,noheader,nounits", "-lms", "50"],
           stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
       self.t = threading.Thread(target=self._read, daemon=True)
       self.t.start()
@@ -145,10 +145,15 @@ class Control:
 
 
 # ---------------------------------------------------------------------------
-def cpu_reference_run(args, seconds: float, max_chains: int = 64):
-  """The oracle port (NumPy f32 restatement of the reference, OpenBLAS on all
-  host cores) timed on a bounded sample of the same workload: `max_chains`
-  chains of the C2 model, same d / batch, as many steps as fit in `seconds`."""
+def cpu_reference_run(args, seconds: float, max_chains: int = 256, max_steps: int = 10000,
+                      warmup: int = 0):
+  """The oracle port timed on a bounded sample of the same workload on all host
+  cores: `max_chains` chains of the C2 model, same d / batch; one step = draw
+  the minibatch, potential + gradient (NumPy f32 on the threaded BLAS), noise +
+  pSGLD update (the oracle's C restatement, threaded over chain slices).  At
+  most `max_steps` steps and at most `seconds` of CPU time."""
+  from concurrent.futures import ThreadPoolExecutor
+  from oracle import cnative
   from oracle import data as odata
   from oracle import prng
   from oracle import sgmc as osgmc
@@ -159,40 +164,56 @@ def cpu_reference_run(args, seconds: float, max_chains: int = 64):
   w = rng.standard_normal(d).astype(np.float32)
   y = (rng.random(Ns) < 1 / (1 + np.exp(-(X @ w)))).astype(np.float32)
   C = max_chains
-  keys = np.stack([prng.PRNGKey(c) for c in range(C)])
-  st = osgmc.langevin_init(np.zeros((C, d), np.float32), keys, rms=True)
+  cores = os.cpu_count() or 1
+  keys = np.ascontiguousarray(np.stack([prng.PRNGKey(c) for c in range(C)]))
+  theta = np.zeros((C, d), np.float32)
+  v = np.ones((C, d), np.float32)
   pot = osgmc.minibatch_potential(osgmc.Logistic(d, 0),
                                   osgmc.Prior("gaussian", 0, d, 10.0))
-  dk = prng.PRNGKey(0)
+  cnative.load()
+  bounds = np.linspace(0, C, min(cores, C) + 1).astype(int)
+  slices = [(a, b) for a, b in zip(bounds[:-1], bounds[1:]) if b > a]
+  pool = ThreadPoolExecutor(max_workers=len(slices))
+  state = {"dk": prng.PRNGKey(0)}
+
+  def one_step():
+    state["dk"], idx = odata.device_draw(state["dk"], n, Ns)
+    _, _, g = pot(theta, (X[idx], y[idx]), args.observations)
+    g = np.ascontiguousarray(g)
+    list(pool.map(lambda ab: cnative.sgld_step(theta[ab[0]:ab[1]], v[ab[0]:ab[1]],
+                                               g[ab[0]:ab[1]], keys[ab[0]:ab[1]], [d],
+                                               1e-3, 1.0), slices))
+
+  for _ in range(warmup):
+    one_step()
   steps, t0 = 0, time.perf_counter()
   while True:
-    dk, idx = odata.device_draw(dk, n, Ns)
-    Xb, yb = X[idx], y[idx]
-    st = osgmc.langevin_update(st, lambda th: pot(th, (Xb, yb), args.observations),
-                               [d], 1e-3, 1.0)
+    one_step()
     steps += 1
     el = time.perf_counter() - t0
-    if el >= seconds or steps >= 10000:
+    if el >= seconds or steps >= max_steps:
       break
-  return {"value": C * steps / el, "unit": UNIT, "cores": os.cpu_count(),
-          "kind": "port",
-          "sample": f"{C} chains x {steps} pSGLD steps, d={d}, batch={n}, "
-                    f"NumPy f32 restatement of the reference (oracle/), "
-                    f"{el:.1f} s"}, steps, el
+  pool.shutdown()
+  return {"value": C * steps / el, "unit": UNIT, "cores": cores, "kind": "port",
+          "sample": f"{C} chains x {steps} pSGLD steps, d={d}, batch={n}: oracle port "
+                    f"(NumPy f32 + threaded BLAS potential, C noise/update on {len(slices)} "
+                    f"threads), {el:.1f} s"}, steps, el
 
 
 def run_reference(args):
   rank, world, _ = dist_env()
   if rank != 0:
     return
-  base, steps, el = cpu_reference_run(args, max(5.0, min(60.0, args.cpu_seconds)))
+  # K timed steps after W warm-up steps of the bounded sample, capped at 150 s
+  base, steps, el = cpu_reference_run(args, 150.0, max_steps=args.steps,
+                                      warmup=min(args.warmup, 20))
   line = {
       "impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT,
-      "n_gpus": args.gpus, "steps": steps, "warmup": 0,
+      "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 20),
       "ms_per_step": 1e3 * el / steps, "higher_is_better": True,
       "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
       "config": {"workload": "C2 Bayesian logistic regression pSGLD (bounded CPU sample)",
-                 "chains": 64, "features": args.features, "batch": args.batch},
+                 "chains": 256, "features": args.features, "batch": args.batch},
       "cpu_baseline": base,
       "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0,
               "d2h_bytes_per_step": 0},
@@ -246,13 +267,21 @@ def run_b200(args):
                     v=v, alpha=0.9, lmbd=1e-5)
     state["k"] = k + 1
 
-  for _ in range(max(3, args.warmup)):
+  # Clock sampler runs from the warm-up on, so that every nvidia-smi sample is
+  # taken under the same load as the timed region that follows immediately; the
+  # warm-up is W steps, extended to ~0.4 s so the sampler is up before timing.
+  sampler = ClockSampler(local)
+  sampler.start()
+  t_w = time.perf_counter()
+  n_w = 0
+  while n_w < max(3, args.warmup) or time.perf_counter() - t_w < 0.4:
     step()
+    n_w += 1
+    if n_w % 50 == 0:
+      stream.sync()
   stream.sync()
 
   # ---- timed region: exactly K steps ----------------------------------------
-  sampler = ClockSampler(local)
-  sampler.start()
   ctl.barrier()
   device.synchronize()
   e0, e1 = Event(), Event()
@@ -318,45 +347,77 @@ def run_b200(args):
         "note": "peak = measured sustained bf16 GEMM; the parity path spends 3 "
                 "fp16 MMA passes per algorithmic FLOP (fp32-level accuracy)"}
 
-  # ---- e2e: host data loader path (minibatch from pinned host memory) ---------
+  # ---- e2e: host data loader path ---------------------------------------------
+  # Every step's minibatch rows travel host -> device from pinned memory and the
+  # step's result (U, var per chain) travels device -> host, all inside the timed
+  # region.  The loader prefetches: the copy of batch k+1 runs on a copy stream
+  # while step k computes (double-buffered), and the host reads step k's result
+  # after launching step k+1 -- the minibatch sequence does not depend on the
+  # chain state, so this is the natural pipelining of the reference's host cache
+  # (data/core.py:664-791).
   import ctypes as Ct
-  hX, hy, hU = Ct.c_void_p(), Ct.c_void_p(), Ct.c_void_p()
-  _lib.call("sgmc_host_alloc", Ct.byref(hX), n * d * 4)
-  _lib.call("sgmc_host_alloc", Ct.byref(hy), n * 4)
-  _lib.call("sgmc_host_alloc", Ct.byref(hU), C * 4 * 2)
-  Xb = ops.gather_rows(X, idx)
-  yb = ops.gather_rows(y.reshape(N, 1), idx)
-  _lib.call("sgmc_memcpy_d2h", hX, Ct.c_void_p(Xb.ptr), n * d * 4, stream.handle)
-  _lib.call("sgmc_memcpy_d2h", hy, Ct.c_void_p(yb.ptr), n * 4, stream.handle)
+  copy_stream = Stream.create()
+  hX = [Ct.c_void_p(), Ct.c_void_p()]
+  hy = [Ct.c_void_p(), Ct.c_void_p()]
+  hU = [Ct.c_void_p(), Ct.c_void_p()]
+  Xb = [ops.gather_rows(X, idx), DA((n, d), np.float32)]
+  yb = [ops.gather_rows(y.reshape(N, 1), idx), DA((n, 1), np.float32)]
+  for b in range(2):
+    _lib.call("sgmc_host_alloc", Ct.byref(hX[b]), n * d * 4)
+    _lib.call("sgmc_host_alloc", Ct.byref(hy[b]), n * 4)
+    _lib.call("sgmc_host_alloc", Ct.byref(hU[b]), C * 4 * 2)
+    _lib.call("sgmc_memcpy_d2h", hX[b], Ct.c_void_p(Xb[0].ptr), n * d * 4, stream.handle)
+    _lib.call("sgmc_memcpy_d2h", hy[b], Ct.c_void_p(yb[0].ptr), n * 4, stream.handle)
   stream.sync()
+  copied = [Event(), Event()]
+  computed = [Event(), Event()]
+  result = [Event(), Event()]
 
-  def e2e_step():
-    k = state["k"]
-    _lib.call("sgmc_memcpy_h2d", Ct.c_void_p(Xb.ptr), hX, n * d * 4, stream.handle)
-    _lib.call("sgmc_memcpy_h2d", Ct.c_void_p(yb.ptr), hy, n * 4, stream.handle)
-    ops.glm_potential_grad(spec, theta, Xb, yb, None, N, U, var, grad,
+  def enqueue_copy(j):
+    b = j % 2
+    copy_stream.wait_event(computed[b])          # buffer b free again (step j-2 done)
+    _lib.call("sgmc_memcpy_h2d", Ct.c_void_p(Xb[b].ptr), hX[b], n * d * 4, copy_stream.handle)
+    _lib.call("sgmc_memcpy_h2d", Ct.c_void_p(yb[b].ptr), hy[b], n * 4, copy_stream.handle)
+    copied[b].record(copy_stream)
+
+  def enqueue_step(j):
+    b, k = j % 2, state["k"]
+    stream.wait_event(copied[b])
+    ops.glm_potential_grad(spec, theta, Xb[b], yb[b], None, N, U, var, grad,
                            workspace=ws, path=path, batch_size=n)
     ops.sgld_update(theta, grad, keys[k % 2], keys[(k + 1) % 2], [d], eps, 1.0,
                     v=v, alpha=0.9, lmbd=1e-5)
-    _lib.call("sgmc_memcpy_d2h", hU, Ct.c_void_p(U.ptr), C * 4, stream.handle)
-    _lib.call("sgmc_memcpy_d2h", Ct.c_void_p(hU.value + C * 4), Ct.c_void_p(var.ptr),
+    computed[b].record(stream)
+    _lib.call("sgmc_memcpy_d2h", hU[b], Ct.c_void_p(U.ptr), C * 4, stream.handle)
+    _lib.call("sgmc_memcpy_d2h", Ct.c_void_p(hU[b].value + C * 4), Ct.c_void_p(var.ptr),
               C * 4, stream.handle)
-    stream.sync()                    # the host consumes the step's result
+    result[b].record(stream)
     state["k"] = k + 1
 
-  for _ in range(3):
-    e2e_step()
+  def run_e2e(steps):
+    for b in range(2):
+      computed[b].record(stream)
+    enqueue_copy(0)
+    for j in range(steps):
+      if j + 1 < steps:
+        enqueue_copy(j + 1)                      # prefetch the next batch
+      enqueue_step(j)
+      if j >= 1:
+        result[(j - 1) % 2].sync()               # host consumes step j-1's result
+    result[(steps - 1) % 2].sync()
+
+  run_e2e(4)
   ctl.barrier()
-  e2e_steps = max(10, args.steps // 4)
+  e2e_steps = max(10, args.steps // 2)
   t0 = time.perf_counter()
-  for _ in range(e2e_steps):
-    e2e_step()
+  run_e2e(e2e_steps)
   e2e_s = ctl.max(time.perf_counter() - t0)
   e2e = {"value": world * C * e2e_steps / e2e_s, "unit": UNIT,
          "h2d_bytes_per_step": n * d * 4 + n * 4, "d2h_bytes_per_step": C * 8,
          "steps": e2e_steps,
-         "what": "host data loader: minibatch from pinned host memory each step, "
-                 "potential+variance read back each step"}
+         "what": "host data loader: every step's minibatch rows H2D from pinned host "
+                 "memory (prefetched one step ahead on a copy stream), potential + "
+                 "variance of every chain D2H and read by the host every step"}
 
   cpu_base = None
   if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -58,6 +58,7 @@ int  sgmc_event_create(void** event);
 int  sgmc_event_destroy(void* event);
 int  sgmc_event_record(void* event, void* stream);
 int  sgmc_event_sync(void* event);
+int  sgmc_stream_wait_event(void* stream, void* event);
 int  sgmc_event_elapsed_ms(void* start, void* stop, float* ms);
 /* Process-wide options.
  * SGMC_OPT_EXACT_UPDATE_MATH: 0 (default) = the RMSprop preconditioner

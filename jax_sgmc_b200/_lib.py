@@ -53,6 +53,7 @@ PROTOTYPES = {
     "sgmc_event_record": [_vp, _vp],
     "sgmc_event_sync": [_vp],
     "sgmc_event_elapsed_ms": [_vp, _vp, C.POINTER(_f32)],
+    "sgmc_stream_wait_event": [_vp, _vp],
     "sgmc_prng_split": [_vp, _vp, _vp, _i64, _int, _int],
     "sgmc_random_bits": [_vp, _vp, _vp, _i64, _i64, _int],
     "sgmc_uniform": [_vp, _vp, _vp, _i64, _i64, _f32, _f32, _int],

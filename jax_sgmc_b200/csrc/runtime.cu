@@ -116,6 +116,10 @@ int sgmc_event_sync(void* event) {
   return check_cuda(cudaEventSynchronize((cudaEvent_t)event),
                     "cudaEventSynchronize");
 }
+int sgmc_stream_wait_event(void* stream, void* event) {
+  return check_cuda(cudaStreamWaitEvent((cudaStream_t)stream, (cudaEvent_t)event, 0),
+                    "cudaStreamWaitEvent");
+}
 int sgmc_event_elapsed_ms(void* start, void* stop, float* ms) {
   return check_cuda(
       cudaEventElapsedTime(ms, (cudaEvent_t)start, (cudaEvent_t)stop),

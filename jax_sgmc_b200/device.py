@@ -35,6 +35,10 @@ class Stream:
   def sync(self):
     _lib.call("sgmc_stream_sync", self.handle)
 
+  def wait_event(self, event: "Event"):
+    """Make later work on this stream wait for ``event`` (no host blocking)."""
+    _lib.call("sgmc_stream_wait_event", self.handle, event.handle)
+
   def __del__(self):
     if getattr(self, "_owned", False) and self.handle.value:
       try:
