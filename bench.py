@@ -47,6 +47,8 @@ def parse():
   p.add_argument("--path", default="auto",
                  choices=["auto", "simt", "tc_parity", "tc_throughput"])
   p.add_argument("--no-cpu-baseline", action="store_true")
+  p.add_argument("--serial-launch", action="store_true",
+                 help="disable programmatic dependent launch (A/B of the launch overlap)")
   p.add_argument("--cpu-seconds", type=float, default=15.0)
   return p.parse_args()
 
@@ -233,6 +235,8 @@ def run_b200(args):
   device.set_device(local)
   stream = Stream.create()
   device.set_current_stream(stream)
+  if args.serial_launch:
+    ops.set_option(ops.OPT_SERIAL_LAUNCH, 1)
 
   C, d, n, N = args.chains, args.features, args.batch, args.observations
   path = args.path

@@ -65,8 +65,12 @@ int  sgmc_event_elapsed_ms(void* start, void* stop, float* ms);
  *   arithmetic (sqrt, reciprocal) uses the SFU approximations (<= 2 ulp) and
  *   FMA contraction; 1 = IEEE-exact unfused arithmetic, bit-identical to the
  *   NumPy oracle given the same gradient.  The Gaussian noise is bit-exact in
- *   both modes. */
-enum { SGMC_OPT_EXACT_UPDATE_MATH = 0, SGMC_OPT_COUNT = 4 };
+ *   both modes.
+ * SGMC_OPT_SERIAL_LAUNCH: 0 (default) = the step's kernels are launched with
+ *   programmatic dependent launch (each kernel's prologue and CTA ramp overlap
+ *   the previous kernel's tail; every kernel executes griddepcontrol.wait
+ *   before its first global access); 1 = plain stream-serialised launches. */
+enum { SGMC_OPT_EXACT_UPDATE_MATH = 0, SGMC_OPT_SERIAL_LAUNCH = 1, SGMC_OPT_COUNT = 4 };
 int  sgmc_set_option(int option, int value);
 int  sgmc_get_option(int option);
 /* counts kernels launched by this library since load (bench "gpu_launches") */

@@ -38,6 +38,35 @@ inline int sm_count() {
   return cached;
 }
 
+// Launch with programmatic dependent launch (PDL) unless disabled: the grid may
+// start while the previous kernel of the stream drains, so every kernel
+// launched through here calls pdl_wait() before its first global access.
+template <class... P, class... A>
+inline void launch_pdl(void (*kernel)(P...), dim3 grid, dim3 block, size_t smem,
+                       cudaStream_t stream, A&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = option(SGMC_OPT_SERIAL_LAUNCH) ? 0 : 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, kernel, static_cast<P>(args)...);
+}
+
+#ifdef __CUDACC__
+// Blocks until the grids this one depends on have completed and their writes
+// are visible (no-op when launched without the PDL attribute).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// Lets the next PDL grid of the stream start being scheduled.
+__device__ __forceinline__ void pdl_launch_dependents() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+#endif
+
 }  // namespace sgmc
 
 #define SGMC_REQUIRE(cond, ...)            \

@@ -260,6 +260,10 @@ k_glm_tc_gemm(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_ptr, kTmemCols);
+  // Everything above (descriptor prefetch, barrier init, TMEM allocation) overlaps
+  // the previous kernel's tail under programmatic dependent launch.
+  pdl_launch_dependents();
+  pdl_wait();
   if (EPI == 0 && threadIdx.x < BN) {   // per-column observation data of this tile
     const int col = n0 + threadIdx.x;
     float yv = 0.f, mv = 0.f;
@@ -678,6 +682,8 @@ template <bool SPLIT>
 __global__ void __launch_bounds__(256) k_prepare_all(const PrepareArgs a) {
   __shared__ float tile[32][33];
   const int lane = threadIdx.x & 31;
+  pdl_launch_dependents();
+  pdl_wait();
   if ((int)blockIdx.x < a.theta_blocks) {
     if (blockIdx.x == 0)
       for (int i = threadIdx.x; i < a.n_counters; i += 256) a.tile_counters[i] = 0u;
@@ -926,7 +932,8 @@ static int launch_gemm(cudaStream_t stream, const CUtensorMap& a0, const CUtenso
     attr_set = true;
   }
   dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM);
-  kfn<<<grid, kTcThreads, S::kBytes, stream>>>(a0, a1, b0, b1, (K + BK - 1) / BK, link, gradp);
+  launch_pdl(kfn, grid, dim3(kTcThreads), S::kBytes, stream, a0, a1, b0, b1,
+             (int)((K + BK - 1) / BK), link, gradp);
   return post_launch(name);
 }
 
@@ -968,8 +975,8 @@ int glm_tc(cudaStream_t stream, const GlmArgs& a, int path) {
     pa.x_tiles_x = (d + 31) / 32;
     pa.tile_counters = w.counters; pa.n_counters = (int)((C + BM - 1) / BM);
     const unsigned grid = (unsigned)(pa.theta_blocks + pa.x_tiles_x * ((n + 31) / 32));
-    if (split) k_prepare_all<true><<<grid, 256, 0, stream>>>(pa);
-    else k_prepare_all<false><<<grid, 256, 0, stream>>>(pa);
+    if (split) launch_pdl(k_prepare_all<true>, dim3(grid), dim3(256), 0, stream, pa);
+    else launch_pdl(k_prepare_all<false>, dim3(grid), dim3(256), 0, stream, pa);
     if (post_launch("k_prepare_all")) return 1;
   }
   // The Xb scale is computed on the device (k_x_prepare) and read by the

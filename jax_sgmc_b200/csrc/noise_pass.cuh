@@ -119,6 +119,8 @@ k_noise_pass(const __grid_constant__ LeafTable tab,
              uint32_t* __restrict__ keys_out, int64_t n_chains,
              int64_t tiles_total, int key_mode, const Op op) {
   extern __shared__ Key s_keys[];
+  pdl_launch_dependents();   // the next kernel may start ramping up behind this grid
+  pdl_wait();                // ... and this one waits here for the grids before it
   const int L = tab.n_leaves;
   const int64_t t0 = tiles_total * (int64_t)blockIdx.x / gridDim.x;
   const int64_t t1 = tiles_total * ((int64_t)blockIdx.x + 1) / gridDim.x;
@@ -214,11 +216,11 @@ int launch_noise_pass(cudaStream_t stream, const LeafTable& tab,
   if (plan_noise_launch(tab, n_chains, fn, &nl)) return 1;
   if (nl.tiles_total == 0) return 0;
   if (layout == 0)
-    k_noise_pass<0, Op><<<nl.grid, kNoiseThreads, nl.smem, stream>>>(
-        tab, keys_in, keys_out, n_chains, nl.tiles_total, key_mode, op);
+    launch_pdl(k_noise_pass<0, Op>, dim3(nl.grid), dim3(kNoiseThreads), nl.smem, stream, tab,
+               keys_in, keys_out, n_chains, nl.tiles_total, key_mode, op);
   else
-    k_noise_pass<1, Op><<<nl.grid, kNoiseThreads, nl.smem, stream>>>(
-        tab, keys_in, keys_out, n_chains, nl.tiles_total, key_mode, op);
+    launch_pdl(k_noise_pass<1, Op>, dim3(nl.grid), dim3(kNoiseThreads), nl.smem, stream, tab,
+               keys_in, keys_out, n_chains, nl.tiles_total, key_mode, op);
   return post_launch(name);
 }
 

@@ -76,6 +76,8 @@ __global__ void k_randint(const uint32_t* __restrict__ key_in,
                           uint32_t span, uint32_t mult, int draw_mode,
                           int layout) {
   // draw_mode 0: randint(key);  1: key', sub = split(key); randint(sub)
+  pdl_launch_dependents();
+  pdl_wait();
   Key k{key_in[0], key_in[1]};
   if (draw_mode == 1) {
     Key nk, sub;
@@ -191,8 +193,8 @@ int sgmc_minibatch_draw(void* stream, const uint32_t* key_in, uint32_t* key_out,
   randint_params(0, (int32_t)observation_count, &span, &mult);
   const unsigned grid =
       (unsigned)((batch_size + 255) / 256 > 1184 ? 1184 : (batch_size + 255) / 256);
-  k_randint<<<grid, 256, 0, (cudaStream_t)stream>>>(
-      key_in, key_out, idx, batch_size, 0, span, mult, 1, prng_layout);
+  launch_pdl(k_randint, dim3(grid), dim3(256), 0, (cudaStream_t)stream, key_in, key_out, idx,
+             batch_size, (int32_t)0, span, mult, 1, prng_layout);
   return post_launch("sgmc_minibatch_draw");
 }
 

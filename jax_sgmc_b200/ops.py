@@ -272,6 +272,7 @@ def swap_rows(a: DeviceArray, b: DeviceArray, exchange: DeviceArray, stream=None
 
 
 OPT_EXACT_UPDATE_MATH = 0
+OPT_SERIAL_LAUNCH = 1      # 1: disable programmatic dependent launch
 
 
 def set_option(option: int, value: int):
