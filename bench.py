@@ -49,6 +49,9 @@ def parse():
   p.add_argument("--no-cpu-baseline", action="store_true")
   p.add_argument("--serial-launch", action="store_true",
                  help="disable programmatic dependent launch (A/B of the launch overlap)")
+  p.add_argument("--fused-epilogue", action="store_true",
+                 help="experimental: pSGLD update inside the gradient GEMM's epilogue "
+                      "(SGMC_OPT_FUSED_STEP_EPILOGUE)")
   p.add_argument("--cpu-seconds", type=float, default=15.0)
   return p.parse_args()
 
@@ -237,6 +240,8 @@ def run_b200(args):
   device.set_current_stream(stream)
   if args.serial_launch:
     ops.set_option(ops.OPT_SERIAL_LAUNCH, 1)
+  if args.fused_epilogue:
+    ops.set_option(ops.OPT_FUSED_STEP_EPILOGUE, 1)
 
   C, d, n, N = args.chains, args.features, args.batch, args.observations
   path = args.path
@@ -265,10 +270,11 @@ def run_b200(args):
   def step():
     k = state["k"]
     ops.minibatch_draw(dkey[k % 2], dkey[(k + 1) % 2], idx, N)
-    ops.glm_potential_grad(spec, theta, X, y, idx, N, U, var, grad,
-                           workspace=ws, path=path)
-    ops.sgld_update(theta, grad, keys[k % 2], keys[(k + 1) % 2], [d], eps, 1.0,
-                    v=v, alpha=0.9, lmbd=1e-5)
+    # the whole langevin_diffusion step in one C call (operand prepare, two
+    # tcgen05 GEMMs, fused noise + pSGLD update)
+    ops.glm_sgld_step(spec, theta, X, y, idx, N, U, var, grad, keys[k % 2],
+                      keys[(k + 1) % 2], eps, 1.0, v=v, alpha=0.9, lmbd=1e-5,
+                      workspace=ws, path=path, write_grad=False)
     state["k"] = k + 1
 
   # Clock sampler runs from the warm-up on, so that every nvidia-smi sample is

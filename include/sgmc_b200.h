@@ -70,7 +70,12 @@ int  sgmc_event_elapsed_ms(void* start, void* stop, float* ms);
  *   programmatic dependent launch (each kernel's prologue and CTA ramp overlap
  *   the previous kernel's tail; every kernel executes griddepcontrol.wait
  *   before its first global access); 1 = plain stream-serialised launches. */
-enum { SGMC_OPT_EXACT_UPDATE_MATH = 0, SGMC_OPT_SERIAL_LAUNCH = 1, SGMC_OPT_COUNT = 4 };
+/* SGMC_OPT_FUSED_STEP_EPILOGUE: 1 = sgmc_glm_sgld_step applies the update inside
+ *   the gradient GEMM's epilogue when the shapes allow (same bits; measured
+ *   slower than the two-kernel sequence on B200 so far); 0
+ *   (default) = potential/gradient kernels followed by the fused update kernel. */
+enum { SGMC_OPT_EXACT_UPDATE_MATH = 0, SGMC_OPT_SERIAL_LAUNCH = 1,
+       SGMC_OPT_FUSED_STEP_EPILOGUE = 2, SGMC_OPT_COUNT = 4 };
 int  sgmc_set_option(int option, int value);
 int  sgmc_get_option(int option);
 /* counts kernels launched by this library since load (bench "gpu_launches") */
@@ -253,6 +258,30 @@ int sgmc_glm_potential_grad(void* stream, const sgmc_glm_spec* spec,
                             int64_t observation_count, float* potential,
                             float* variance, float* grad, float* ell,
                             void* workspace, size_t workspace_bytes, int path);
+
+/* One whole integrator.langevin_diffusion.update_fn step for the GLM potential
+ * (integrator.py:860-922): the minibatch potential + gradient at the current
+ * theta (sgmc_glm_potential_grad; `potential` / `variance` describe theta
+ * BEFORE the update, as LangevinState.potential / .variance do) followed by
+ * sgmc_sgld_rms_update (v != NULL) or sgmc_sgld_update (v == NULL) on that
+ * gradient.  With SGMC_OPT_FUSED_STEP_EPILOGUE on the tensor-core paths, when
+ * the sample is exactly the weight vector (P == d, d % 256 == 0, n_chains %
+ * 128 == 0, original threefry layout, SGMC_OPT_EXACT_UPDATE_MATH off), the
+ * update runs inside the epilogue of the gradient GEMM (the Gaussian noise is
+ * generated while the tensor pipe works and the gradient never goes to memory
+ * unless `grad` is wanted); every other case runs the kernels one after the
+ * other.  Same results either way (bit for bit).
+ * `grad` (f32[C][P]) must be a valid buffer; with write_grad != 0 it receives
+ * dU/dtheta, with write_grad == 0 its contents are unspecified afterwards (the
+ * fused kernel then skips the store). */
+int sgmc_glm_sgld_step(void* stream, const sgmc_glm_spec* spec, float* theta, float* v,
+                       int64_t n_chains, int64_t P, const float* X, const float* y,
+                       const int32_t* idx, const float* mask, int64_t batch_size,
+                       int64_t observation_count, float* potential, float* variance,
+                       float* grad, const uint32_t* keys_in, uint32_t* keys_out,
+                       float step_size, float temperature, float alpha, float lmbd,
+                       void* workspace, size_t workspace_bytes, int path, int prng_layout,
+                       int write_grad);
 
 /* ---- reSGLD: solver.parallel_tempering.update swap step
  *      (solver.py:273-291).  For S systems: ssq' = (1-1/k) ssq + var_n/k;

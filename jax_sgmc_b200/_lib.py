@@ -85,6 +85,9 @@ PROTOTYPES = {
     "sgmc_glm_potential_grad": [_vp, C.POINTER(GlmSpec), _vp, _i64, _i64, _vp,
                                 _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp,
                                 _vp, _sz, _int],
+    "sgmc_glm_sgld_step": [_vp, C.POINTER(GlmSpec), _vp, _vp, _i64, _i64, _vp, _vp, _vp,
+                           _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _f32, _f32, _f32,
+                           _f32, _vp, _sz, _int, _int, _int],
     "sgmc_resgld_decide": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _f32, _f32, _vp,
                            _vp, _vp, _i64, _int],
     "sgmc_swap_rows": [_vp, _vp, _vp, _vp, _i64, _i64],

@@ -5,6 +5,21 @@
 
 namespace sgmc {
 
+// The SGLD / pSGLD update the caller wants applied right after the gradient
+// (sgmc_glm_sgld_step).  The tensor-core path applies it inside GEMM2's
+// epilogue when the shapes allow and reports that through *applied.
+struct FusedSgld {
+  bool requested;
+  float* theta_rw;          // f32[C][P], updated in place
+  float* v;                 // RMSprop state or null
+  const uint32_t* keys_in;
+  uint32_t* keys_out;
+  float step_size, temperature, alpha, lmbd;
+  int layout;
+  bool write_grad;
+  bool* applied;
+};
+
 struct GlmArgs {
   sgmc_glm_spec spec;
   const float* theta;     // f32[C][P]
@@ -22,6 +37,7 @@ struct GlmArgs {
   float* ell;             // f32[C][n]
   bool ell_requested;     // the caller passed an ell output buffer
   float* tc_ws;           // extra scratch of the tensor-core path
+  FusedSgld fused;
 };
 
 // -(d prior / d theta_p) / T for flat parameter index p of chain c.

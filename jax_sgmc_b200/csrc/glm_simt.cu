@@ -237,13 +237,12 @@ size_t sgmc_glm_workspace_bytes(int64_t n_chains, int64_t batch_size, int64_t d,
   return base + 256;
 }
 
-int sgmc_glm_potential_grad(void* stream, const sgmc_glm_spec* spec,
-                            const float* theta, int64_t n_chains, int64_t P,
-                            const float* X, const float* y, const int32_t* idx,
-                            const float* mask, int64_t batch_size,
-                            int64_t observation_count, float* potential,
-                            float* variance, float* grad, float* ell,
-                            void* workspace, size_t workspace_bytes, int path) {
+static int glm_dispatch(void* stream, const sgmc_glm_spec* spec, const float* theta,
+                        int64_t n_chains, int64_t P, const float* X, const float* y,
+                        const int32_t* idx, const float* mask, int64_t batch_size,
+                        int64_t observation_count, float* potential, float* variance,
+                        float* grad, float* ell, void* workspace, size_t workspace_bytes,
+                        int path, const FusedSgld& fused) {
   SGMC_REQUIRE(spec && theta && X && y && potential, "null argument");
   SGMC_REQUIRE(spec->family == kFamilyGaussian || spec->family == kFamilyLogistic,
                "unknown GLM family %d", spec->family);
@@ -271,10 +270,54 @@ int sgmc_glm_potential_grad(void* stream, const sgmc_glm_spec* spec,
   a.ell = ell ? ell : ws + (size_t)n_chains * batch_size;
   a.ell_requested = ell != nullptr;
   a.tc_ws = ws + 2 * (size_t)n_chains * batch_size;
+  a.fused = fused;
   // cotangent of every ell_i: (1/T) * (-N) / n    (potential.py:183,210)
   a.cot = (-(float)observation_count / (float)batch_size) / spec->temperature;
   if (path == 0) return glm_simt((cudaStream_t)stream, a);
   return glm_tc((cudaStream_t)stream, a, path);
+}
+
+int sgmc_glm_potential_grad(void* stream, const sgmc_glm_spec* spec,
+                            const float* theta, int64_t n_chains, int64_t P,
+                            const float* X, const float* y, const int32_t* idx,
+                            const float* mask, int64_t batch_size,
+                            int64_t observation_count, float* potential,
+                            float* variance, float* grad, float* ell,
+                            void* workspace, size_t workspace_bytes, int path) {
+  FusedSgld none{};
+  return glm_dispatch(stream, spec, theta, n_chains, P, X, y, idx, mask, batch_size,
+                      observation_count, potential, variance, grad, ell, workspace,
+                      workspace_bytes, path, none);
+}
+
+int sgmc_glm_sgld_step(void* stream, const sgmc_glm_spec* spec, float* theta, float* v,
+                       int64_t n_chains, int64_t P, const float* X, const float* y,
+                       const int32_t* idx, const float* mask, int64_t batch_size,
+                       int64_t observation_count, float* potential, float* variance,
+                       float* grad, const uint32_t* keys_in, uint32_t* keys_out,
+                       float step_size, float temperature, float alpha, float lmbd,
+                       void* workspace, size_t workspace_bytes, int path, int prng_layout,
+                       int write_grad) {
+  SGMC_REQUIRE(grad && keys_in && keys_out, "null argument");
+  SGMC_REQUIRE(keys_in != keys_out, "keys_out must not alias keys_in");
+  bool applied = false;
+  FusedSgld fu{};
+  fu.requested = true;
+  fu.theta_rw = theta; fu.v = v; fu.keys_in = keys_in; fu.keys_out = keys_out;
+  fu.step_size = step_size; fu.temperature = temperature; fu.alpha = alpha; fu.lmbd = lmbd;
+  fu.layout = prng_layout; fu.applied = &applied; fu.write_grad = write_grad != 0;
+  if (int e = glm_dispatch(stream, spec, theta, n_chains, P, X, y, idx, mask, batch_size,
+                           observation_count, potential, variance, grad, nullptr, workspace,
+                           workspace_bytes, path, fu))
+    return e;
+  if (applied) return 0;
+  // not fusable for these shapes / options: the stand-alone fused update
+  const int64_t leaf = P;
+  if (v)
+    return sgmc_sgld_rms_update(stream, theta, v, grad, keys_in, keys_out, n_chains, &leaf, 1,
+                                step_size, temperature, nullptr, alpha, lmbd, prng_layout);
+  return sgmc_sgld_update(stream, theta, grad, keys_in, keys_out, n_chains, &leaf, 1, step_size,
+                          temperature, nullptr, prng_layout);
 }
 
 }  // extern "C"

@@ -24,6 +24,8 @@
 // pipeline shared memory -> fully coalesced global stores.
 // Roofline: tensor pipe; algorithmic FLOPs 2*C*n*d per GEMM.
 #include "glm.cuh"
+#include "rng.cuh"
+#include "sgld_math.cuh"
 
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -40,10 +42,14 @@ constexpr int BM = 128, BN = 256, BK = SGMC_TC_BK;   // tile (elements); BK*2 B 
 static_assert(BK == 64 || BK == 32, "BK must be 64 (128B swizzle) or 32 (64B swizzle)");
 constexpr int kTcThreads = 512;               // 16 warps
 constexpr int kTcWarps = kTcThreads / 32;
+// EPI 2 (gradient + fused SGLD update): the 16 warps generate the step's Gaussian
+// noise while the tensor pipe works, so the pipeline (TMA + MMA issue) moves to
+// one thread of a 17th warp.
+constexpr int kTcFusedThreads = kTcThreads + 32;
 constexpr uint32_t kTmemCols = 256;
 
 // debug timers (globaltimer ns) of CTA 0: [start, setup done, mainloop done, end]
-__device__ unsigned long long g_tc_dbg[8];
+__device__ unsigned long long g_tc_dbg[10];
 __device__ __forceinline__ unsigned long long gtime() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
@@ -189,6 +195,13 @@ struct TcGradEpi {      // GEMM2: G -> grad (adds -grad(prior)/T)
   float prior_coef;         // 1 / (scale^2 * T)
   const float* xt_scale;    // device scalar: scale applied to XbT
   float r_scale;            // scale applied to R
+  // EPI 2: the SGLD / pSGLD update of integrator.py:860-922 applied in the epilogue
+  float* theta_rw;          // f32[C][P], updated in place
+  float* v;                 // f32[C][P] RMSprop state or null (plain SGLD)
+  const uint32_t* keys_in;  // u32[C][2]
+  uint32_t* keys_out;       // u32[C][2]
+  float neg_eps, noise_scale, alpha, one_m_alpha, lmbd;
+  uint32_t half;            // d / 2: element j shares its threefry block with j + half
 };
 
 // logistic link with SFU-based exp / log / reciprocal (abs. error ~1e-7):
@@ -221,7 +234,7 @@ struct TcSmem {
 };
 
 template <int TERMS, int EPI, int ABFMT>
-__global__ void __launch_bounds__(kTcThreads, 1)
+__global__ void __launch_bounds__(EPI == 2 ? kTcFusedThreads : kTcThreads, 1)
 k_glm_tc_gemm(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
               const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1,
               int num_k_blocks, const TcLinkEpi link, const TcGradEpi gradp) {
@@ -241,6 +254,10 @@ k_glm_tc_gemm(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  // EPI 2 tiles pair feature j with j + d/2 (the two outputs of one threefry
+  // block): accumulator columns [0,128) = features n0a.., [128,256) = n0b..
+  const int n0a = blockIdx.x * (BN / 2), n0b = (int)gradp.half + n0a;
+  Key* s_lk = reinterpret_cast<Key*>(s_y);         // EPI 2: per-row noise keys
   if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 64) g_tc_dbg[0] = gtime();
 
   if (warp == 0 && lane == 0) {
@@ -275,6 +292,19 @@ k_glm_tc_gemm(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
     s_mask[threadIdx.x] = mv;
     s_rm[threadIdx.x] = link.cot * mv * link.r_scale;
   }
+  if (EPI == 2 && threadIdx.x < BM) {
+    // key', sub = split(key); noise key of the single leaf = split(sub, 1)[0]
+    // (integrator.py:871, :131-133)
+    const int64_t c = m0 + threadIdx.x;
+    const Key k{gradp.keys_in[2 * c], gradp.keys_in[2 * c + 1]};
+    Key newk, sub;
+    split2(k, 0, newk, sub);
+    s_lk[threadIdx.x] = split_key(sub, 0u, 1u, 0);
+    if (blockIdx.x == 0) {
+      gradp.keys_out[2 * c] = newk.k0;
+      gradp.keys_out[2 * c + 1] = newk.k1;
+    }
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -282,7 +312,79 @@ k_glm_tc_gemm(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
   const bool dbg = blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 64;
   if (dbg) g_tc_dbg[1] = gtime();
 
-  if (warp == 0 && lane == 0) {
+  float nzA[32], nzB[32];   // EPI 2: noise of (row q*32+r, feature n0a/n0b + cg*32 + lane)
+  if (EPI == 2) {
+    if (warp == kTcWarps) {
+      if (lane == 0) {
+        // ===== TMA producer + MMA issuer in one thread (both only enqueue work) =====
+        constexpr uint32_t idesc = make_idesc(ABFMT, BM, BN);
+        auto load_block = [&](int kb) {
+          const int s = kb % S::kStages;
+          uint8_t* st = tiles + s * S::kStageBytes;
+          mbar_expect_tx(&full_bar[s], S::kStageBytes);
+          tma_load_2d(st, &tmA0, &full_bar[s], kb * BK, m0);
+          if (TERMS == 3) tma_load_2d(st + BM * BK * 2, &tmA1, &full_bar[s], kb * BK, m0);
+          uint8_t* sb = st + S::kNA * BM * BK * 2;
+          tma_load_2d(sb, &tmB0, &full_bar[s], kb * BK, n0a);
+          tma_load_2d(sb + (BN / 2) * BK * 2, &tmB0, &full_bar[s], kb * BK, n0b);
+          if (TERMS == 3) {
+            tma_load_2d(sb + BN * BK * 2, &tmB1, &full_bar[s], kb * BK, n0a);
+            tma_load_2d(sb + BN * BK * 2 + (BN / 2) * BK * 2, &tmB1, &full_bar[s], kb * BK, n0b);
+          }
+        };
+        for (int kb = 0; kb < S::kStages && kb < num_k_blocks; ++kb) load_block(kb);
+        for (int kb = 0; kb < num_k_blocks; ++kb) {
+          const int s = kb % S::kStages;
+          mbar_wait(&full_bar[s], (kb / S::kStages) & 1);
+          tc_fence_after();
+          const uint32_t a0 = smem_u32(tiles + s * S::kStageBytes);
+          const uint32_t a1 = a0 + BM * BK * 2;
+          const uint32_t b0 = a0 + S::kNA * BM * BK * 2;
+          const uint32_t b1 = b0 + BN * BK * 2;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t da0 = make_smem_desc(a0 + k * 32), db0 = make_smem_desc(b0 + k * 32);
+            if (TERMS == 3) {
+              const uint64_t da1 = make_smem_desc(a1 + k * 32), db1 = make_smem_desc(b1 + k * 32);
+              umma_f16(tmem_base, da1, db0, idesc, (kb | k) != 0);
+              umma_f16(tmem_base, da0, db1, idesc, 1);
+              umma_f16(tmem_base, da0, db0, idesc, 1);
+            } else {
+              umma_f16(tmem_base, da0, db0, idesc, (kb | k) != 0);
+            }
+          }
+          umma_commit(&empty_bar[s]);
+          // refill the stage of the previous block once its MMAs have retired
+          const int kn = kb - 1 + S::kStages;
+          if (kb >= 1 && kn < num_k_blocks) {
+            mbar_wait(&empty_bar[(kb - 1) % S::kStages], ((kb - 1) / S::kStages) & 1);
+            load_block(kn);
+          }
+        }
+        umma_commit(tmem_full_bar);
+      }
+    } else {
+      // ===== the step's Gaussian noise, generated under the mainloop =====
+      // lane = feature inside the warp's 32-column slice, r = chain row: the
+      // layout the coalesced epilogue below consumes.
+      const int q_ = warp & 3, cg_ = warp >> 2;
+      const uint32_t jA = (uint32_t)(n0a + cg_ * 32 + lane);
+#pragma unroll
+      for (int r = 0; r < 32; ++r) {
+        const Key lk = s_lk[q_ * 32 + r];
+        uint32_t wa = jA, wb = jA + gradp.half;
+        threefry2x32(lk, wa, wb);
+        NormalPartial pa, pb;
+        nzA[r] = normal_main(wa, pa);
+        nzB[r] = normal_main(wb, pb);
+        if (normal_is_tail(pa) | normal_is_tail(pb)) {
+          if (normal_is_tail(pa)) nzA[r] = normal_tail(pa);
+          if (normal_is_tail(pb)) nzB[r] = normal_tail(pb);
+        }
+      }
+      if (dbg) g_tc_dbg[8] = gtime();
+    }
+  } else if (warp == 0 && lane == 0) {
     // ===== TMA producer =====
     for (int kb = 0; kb < num_k_blocks; ++kb) {
       const int s = kb % S::kStages;
@@ -328,6 +430,7 @@ k_glm_tc_gemm(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
 
   // ===== epilogue: all 16 warps =====
   __syncwarp();
+  if (EPI != 2 || warp < kTcWarps) {
   const int q = warp & 3;                  // TMEM lane quarter this warp may access
   const int cg = warp >> 2;                // column group: 64 columns
   // GEMM2: the prior-gradient operand theta[row][col] does not depend on the
@@ -499,6 +602,58 @@ k_glm_tc_gemm(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
       link.potential[c] = (L - prior) * link.inv_temperature;
       if (link.variance) link.variance[c] = m2_t / (float)link.n;
     }
+  } else if (EPI == 2) {
+    // Gradient tile -> SGLD / pSGLD update in place.  Per 32x32 block: accumulator
+    // -> transpose through smem -> lane = feature, loop over the 32 chain rows with
+    // coalesced theta / v accesses; the noise is already in registers.
+    const float inv_scale = 1.0f / (gradp.r_scale * __ldg(gradp.xt_scale));
+    const bool rms = gradp.v != nullptr;
+    const int row0 = m0 + q * 32;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int ct = h * (BN / 2) + cg * 32;                 // accumulator column
+      const int p = (h ? n0b : n0a) + cg * 32 + lane;        // flat parameter index (w_off = 0)
+      uint32_t acc[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)ct, acc);
+      if (dbg && h == 0) g_tc_dbg[4] = gtime();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) stage[lane * 33 + j] = __uint_as_float(acc[j]) * inv_scale;
+      __syncwarp();
+      if (dbg && h == 0) g_tc_dbg[5] = gtime();
+      const float coef = (p >= gradp.prior_lo && p < gradp.prior_hi) ? gradp.prior_coef : 0.f;
+      const int64_t o0 = (int64_t)row0 * gradp.P + p;
+      float* tp = gradp.theta_rw + o0;
+      float* vp = rms ? gradp.v + o0 : nullptr;
+      float* gp = gradp.grad ? gradp.grad + o0 : nullptr;
+#pragma unroll
+      for (int rb = 0; rb < 32; rb += 8) {
+        float t8[8], v8[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          t8[k] = tp[(int64_t)(rb + k) * gradp.P];
+          v8[k] = rms ? vp[(int64_t)(rb + k) * gradp.P] : 0.f;
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int r = rb + k;
+          const float g = fmaf(t8[k], coef, stage[r * 33 + lane]);
+          const float xi = h ? nzB[r] : nzA[r];
+          float tn;
+          if (rms) {
+            tn = sgld_one<true, true>(t8[k], g, v8[k], xi, gradp.noise_scale, gradp.neg_eps,
+                                      gradp.alpha, gradp.one_m_alpha, gradp.lmbd);
+            vp[(int64_t)r * gradp.P] = v8[k];
+          } else {
+            tn = sgld_one<false, false>(t8[k], g, v8[k], xi, gradp.noise_scale, gradp.neg_eps,
+                                        0.f, 0.f, 0.f);
+          }
+          tp[(int64_t)r * gradp.P] = tn;
+          if (gp) gp[(int64_t)r * gradp.P] = g;
+        }
+      }
+      __syncwarp();
+      if (dbg && h == 0) g_tc_dbg[6] = gtime();
+    }
   } else {
     const float inv_scale = 1.0f / (gradp.r_scale * __ldg(gradp.xt_scale));
 #pragma unroll 1
@@ -548,6 +703,7 @@ k_glm_tc_gemm(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
     }
   }
   if (dbg) g_tc_dbg[7] = gtime();
+  }  // epilogue warps
   tc_fence_before();
   __syncthreads();
   if (warp == 2) tmem_dealloc(tmem_base, kTmemCols);
@@ -678,9 +834,11 @@ struct PrepareArgs {
   uint32_t* tile_counters; int n_counters;
 };
 
+constexpr int kPrepTile = 64;   // minibatch tile: 64 observations x 64 features
+
 template <bool SPLIT>
 __global__ void __launch_bounds__(256) k_prepare_all(const PrepareArgs a) {
-  __shared__ float tile[32][33];
+  __shared__ float tile[kPrepTile][kPrepTile + 1];
   const int lane = threadIdx.x & 31;
   pdl_launch_dependents();
   pdl_wait();
@@ -692,18 +850,77 @@ __global__ void __launch_bounds__(256) k_prepare_all(const PrepareArgs a) {
     const float* src = a.theta + (int64_t)row * a.P + a.w_off;
     const bool vec = (a.d & 3) == 0 && (a.P & 3) == 0 && (a.w_off & 3) == 0 &&
                      (reinterpret_cast<uintptr_t>(a.theta) & 15u) == 0;
+    const int64_t ob = (int64_t)row * a.d;
+    auto in_prior4 = [&](int j) { return a.w_off + j >= a.prior_lo && a.w_off + j + 3 < a.prior_hi; };
+    auto sumsq4 = [&](const float4& x, int j, float sq) {
+      if (in_prior4(j)) return sq + (x.x * x.x + x.y * x.y + x.z * x.z + x.w * x.w);
+      const int p0 = a.w_off + j;
+      if (p0 >= a.prior_lo && p0 < a.prior_hi) sq = fmaf(x.x, x.x, sq);
+      if (p0 + 1 >= a.prior_lo && p0 + 1 < a.prior_hi) sq = fmaf(x.y, x.y, sq);
+      if (p0 + 2 >= a.prior_lo && p0 + 2 < a.prior_hi) sq = fmaf(x.z, x.z, sq);
+      if (p0 + 3 >= a.prior_lo && p0 + 3 < a.prior_hi) sq = fmaf(x.w, x.w, sq);
+      return sq;
+    };
+    auto store4 = [&](const float4& x, int j, float s) {
+      const float v0 = x.x * s, v1 = x.y * s, v2 = x.z * s, v3 = x.w * s;
+      if (SPLIT) {
+        const __half2 h01 = __floats2half2_rn(v0, v1), h23 = __floats2half2_rn(v2, v3);
+        const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+        const __half2 l01 = __floats2half2_rn(v0 - f01.x, v1 - f01.y);
+        const __half2 l23 = __floats2half2_rn(v2 - f23.x, v3 - f23.y);
+        uint2 ph, pl;
+        ph.x = *reinterpret_cast<const uint32_t*>(&h01); ph.y = *reinterpret_cast<const uint32_t*>(&h23);
+        pl.x = *reinterpret_cast<const uint32_t*>(&l01); pl.y = *reinterpret_cast<const uint32_t*>(&l23);
+        *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(a.th_hi) + ob + j) = ph;
+        *reinterpret_cast<uint2*>(a.th_lo + ob + j) = pl;
+      } else {
+        const __nv_bfloat162 b01 = __floats2bfloat162_rn(v0, v1), b23 = __floats2bfloat162_rn(v2, v3);
+        uint2 pb;
+        pb.x = *reinterpret_cast<const uint32_t*>(&b01); pb.y = *reinterpret_cast<const uint32_t*>(&b23);
+        *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(a.th_hi) + ob + j) = pb;
+      }
+    };
     float m = 0.f, sq = 0.f;
+    if (vec && a.d <= 1024) {
+      // the whole row lives in registers: 8 independent 128-bit loads per lane in
+      // flight, one pass over memory
+      float4 x[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int j = lane * 4 + k * 128;
+        x[k] = j < a.d ? *reinterpret_cast<const float4*>(src + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int j = lane * 4 + k * 128;
+        if (j < a.d) {
+          m = fmaxf(fmaxf(m, fmaxf(fabsf(x[k].x), fabsf(x[k].y))),
+                    fmaxf(fabsf(x[k].z), fabsf(x[k].w)));
+          sq = sumsq4(x[k], j, sq);
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        sq += __shfl_xor_sync(0xffffffffu, sq, o);
+      }
+      const float s = SPLIT ? pow2_scale_for(m) : 1.0f;
+      if (lane == 0) {
+        a.row_scale[row] = s;
+        a.row_sumsq[row] = sq;
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int j = lane * 4 + k * 128;
+        if (j < a.d) store4(x[k], j, s);
+      }
+      return;
+    }
     if (vec) {
       for (int j = lane * 4; j < a.d; j += 128) {
         const float4 x = *reinterpret_cast<const float4*>(src + j);
         m = fmaxf(fmaxf(m, fmaxf(fabsf(x.x), fabsf(x.y))), fmaxf(fabsf(x.z), fabsf(x.w)));
-        if (a.w_off + j >= a.prior_lo && a.w_off + j + 3 < a.prior_hi)
-          sq += x.x * x.x + x.y * x.y + x.z * x.z + x.w * x.w;
-        else
-          for (int k = 0; k < 4; ++k) {
-            const float xv = k == 0 ? x.x : (k == 1 ? x.y : (k == 2 ? x.z : x.w));
-            if (a.w_off + j + k >= a.prior_lo && a.w_off + j + k < a.prior_hi) sq = fmaf(xv, xv, sq);
-          }
+        sq = sumsq4(x, j, sq);
       }
     } else {
       for (int j = lane; j < a.d; j += 32) {
@@ -722,28 +939,9 @@ __global__ void __launch_bounds__(256) k_prepare_all(const PrepareArgs a) {
       a.row_scale[row] = s;
       a.row_sumsq[row] = sq;
     }
-    const int64_t ob = (int64_t)row * a.d;
     if (vec) {
-      for (int j = lane * 4; j < a.d; j += 128) {
-        const float4 x = *reinterpret_cast<const float4*>(src + j);   // L1 hit
-        const float v0 = x.x * s, v1 = x.y * s, v2 = x.z * s, v3 = x.w * s;
-        if (SPLIT) {
-          const __half2 h01 = __floats2half2_rn(v0, v1), h23 = __floats2half2_rn(v2, v3);
-          const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
-          const __half2 l01 = __floats2half2_rn(v0 - f01.x, v1 - f01.y);
-          const __half2 l23 = __floats2half2_rn(v2 - f23.x, v3 - f23.y);
-          uint2 ph, pl;
-          ph.x = *reinterpret_cast<const uint32_t*>(&h01); ph.y = *reinterpret_cast<const uint32_t*>(&h23);
-          pl.x = *reinterpret_cast<const uint32_t*>(&l01); pl.y = *reinterpret_cast<const uint32_t*>(&l23);
-          *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(a.th_hi) + ob + j) = ph;
-          *reinterpret_cast<uint2*>(a.th_lo + ob + j) = pl;
-        } else {
-          const __nv_bfloat162 b01 = __floats2bfloat162_rn(v0, v1), b23 = __floats2bfloat162_rn(v2, v3);
-          uint2 pb;
-          pb.x = *reinterpret_cast<const uint32_t*>(&b01); pb.y = *reinterpret_cast<const uint32_t*>(&b23);
-          *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(a.th_hi) + ob + j) = pb;
-        }
-      }
+      for (int j = lane * 4; j < a.d; j += 128)
+        store4(*reinterpret_cast<const float4*>(src + j), j, s);   // L1 / L2 hit
     } else {
       for (int j = lane; j < a.d; j += 32) {
         const float x = src[j] * s;
@@ -758,7 +956,8 @@ __global__ void __launch_bounds__(256) k_prepare_all(const PrepareArgs a) {
     }
     return;
   }
-  // ---- minibatch tile ------------------------------------------------------------
+  // ---- minibatch tile: gather, scale, split; row-major and transposed copies --------
+  // (n and d are multiples of 8 on this path: element pairs never straddle an edge)
   const int t = blockIdx.x - a.theta_blocks;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;           // 32 x 8
   const int n = a.n, d = a.d;
@@ -766,36 +965,48 @@ __global__ void __launch_bounds__(256) k_prepare_all(const PrepareArgs a) {
   if (SPLIT)
     s = pow2_scale_for(a.static_absmax > 0.f ? a.static_absmax : __uint_as_float(*a.absmax_bits));
   if (t == 0 && threadIdx.x == 0) *a.x_scale = s;
-  const int r0 = (t / a.x_tiles_x) * 32, c0 = (t % a.x_tiles_x) * 32;
-  for (int i = ty; i < 32; i += 8) {
-    const int r = r0 + i, c = c0 + tx;
-    float v = 0.f;
-    if (r < n && c < d) {
-      const int64_t row = a.idx ? a.idx[r] : r;
-      v = a.X[row * d + c] * s;
-      if (SPLIT) {
-        const __half h = __float2half_rn(v);
-        reinterpret_cast<__half*>(a.xb_hi)[(int64_t)r * d + c] = h;
-        a.xb_lo[(int64_t)r * d + c] = __float2half_rn(v - __half2float(h));
-      } else {
-        reinterpret_cast<__nv_bfloat16*>(a.xb_hi)[(int64_t)r * d + c] = __float2bfloat16_rn(v);
+  const int r0 = (t / a.x_tiles_x) * kPrepTile, c0 = (t % a.x_tiles_x) * kPrepTile;
+  const bool x8 = (reinterpret_cast<uintptr_t>(a.X) & 7u) == 0;
+  auto store2 = [&](void* hi, __half* lo, int64_t o, float v0, float v1) {
+    if (SPLIT) {
+      const __half2 h = __floats2half2_rn(v0, v1);
+      const float2 hf = __half22float2(h);
+      *reinterpret_cast<__half2*>(reinterpret_cast<__half*>(hi) + o) = h;
+      *reinterpret_cast<__half2*>(lo + o) = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
+    } else {
+      *reinterpret_cast<__nv_bfloat162*>(reinterpret_cast<__nv_bfloat16*>(hi) + o) =
+          __floats2bfloat162_rn(v0, v1);
+    }
+  };
+  {
+    const int c = c0 + 2 * tx;
+    float2 val[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {                   // 8 independent 64-bit loads in flight
+      const int r = r0 + ty + 8 * k;
+      val[k] = make_float2(0.f, 0.f);
+      if (r < n && c < d) {
+        const int64_t row = a.idx ? a.idx[r] : r;
+        const float* px = a.X + row * d + c;
+        if (x8) val[k] = *reinterpret_cast<const float2*>(px);
+        else val[k] = make_float2(px[0], px[1]);
       }
     }
-    tile[i][tx] = v;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int i = ty + 8 * k, r = r0 + i;
+      const float v0 = val[k].x * s, v1 = val[k].y * s;
+      if (r < n && c < d) store2(a.xb_hi, a.xb_lo, (int64_t)r * d + c, v0, v1);
+      tile[i][2 * tx] = v0;
+      tile[i][2 * tx + 1] = v1;
+    }
   }
   __syncthreads();
-  for (int i = ty; i < 32; i += 8) {
-    const int c = c0 + i, r = r0 + tx;                 // transposed: row = feature c
-    if (c < d && r < n) {
-      const float v = tile[tx][i];
-      if (SPLIT) {
-        const __half h = __float2half_rn(v);
-        reinterpret_cast<__half*>(a.xt_hi)[(int64_t)c * n + r] = h;
-        a.xt_lo[(int64_t)c * n + r] = __float2half_rn(v - __half2float(h));
-      } else {
-        reinterpret_cast<__nv_bfloat16*>(a.xt_hi)[(int64_t)c * n + r] = __float2bfloat16_rn(v);
-      }
-    }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int cc = ty + 8 * k, c = c0 + cc, r = r0 + 2 * tx;   // transposed: row = feature c
+    if (c < d && r < n)
+      store2(a.xt_hi, a.xt_lo, (int64_t)c * n + r, tile[2 * tx][cc], tile[2 * tx + 1][cc]);
   }
 }
 
@@ -911,7 +1122,7 @@ static size_t carve(TcWorkspace* w, uint8_t* base, int64_t C, int64_t n, int64_t
 }
 
 int glm_tc_debug_read(unsigned long long* out) {
-  return check_cuda(cudaMemcpyFromSymbol(out, g_tc_dbg, sizeof(unsigned long long) * 8), "dbg");
+  return check_cuda(cudaMemcpyFromSymbol(out, g_tc_dbg, sizeof(unsigned long long) * 10), "dbg");
 }
 
 size_t glm_tc_workspace_bytes(int64_t n_chains, int64_t batch_size, int64_t d, int) {
@@ -932,7 +1143,7 @@ static int launch_gemm(cudaStream_t stream, const CUtensorMap& a0, const CUtenso
     attr_set = true;
   }
   dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM);
-  launch_pdl(kfn, grid, dim3(kTcThreads), S::kBytes, stream, a0, a1, b0, b1,
+  launch_pdl(kfn, grid, dim3(EPI == 2 ? kTcFusedThreads : kTcThreads), S::kBytes, stream, a0, a1, b0, b1,
              (int)((K + BK - 1) / BK), link, gradp);
   return post_launch(name);
 }
@@ -972,9 +1183,10 @@ int glm_tc(cudaStream_t stream, const GlmArgs& a, int path) {
     pa.xb_hi = w.xb_hi; pa.xb_lo = w.xb_lo; pa.xt_hi = w.xt_hi; pa.xt_lo = w.xt_lo;
     pa.x_scale = w.x_scale;
     pa.theta_blocks = (int)((C + 7) / 8);
-    pa.x_tiles_x = (d + 31) / 32;
+    pa.x_tiles_x = (d + kPrepTile - 1) / kPrepTile;
     pa.tile_counters = w.counters; pa.n_counters = (int)((C + BM - 1) / BM);
-    const unsigned grid = (unsigned)(pa.theta_blocks + pa.x_tiles_x * ((n + 31) / 32));
+    const unsigned grid =
+        (unsigned)(pa.theta_blocks + pa.x_tiles_x * ((n + kPrepTile - 1) / kPrepTile));
     if (split) launch_pdl(k_prepare_all<true>, dim3(grid), dim3(256), 0, stream, pa);
     else launch_pdl(k_prepare_all<false>, dim3(grid), dim3(256), 0, stream, pa);
     if (post_launch("k_prepare_all")) return 1;
@@ -1025,6 +1237,34 @@ int glm_tc(cudaStream_t stream, const GlmArgs& a, int path) {
                              "k_glm_tc_gemm<bf16,link>")) return 1;
   }
   // U and var(ell) were finalised inside GEMM1 by the last CTA of every row block.
+  // ---- GEMM2 with the SGLD / pSGLD update in its epilogue -----------------------------
+  // Needs whole tiles, the sample to be exactly the weight vector (one leaf, so
+  // feature j shares its threefry block with j + d/2) and the default (fast)
+  // preconditioner arithmetic; otherwise the caller runs the stand-alone update.
+  const FusedSgld& fu = a.fused;
+  if (fu.requested && option(SGMC_OPT_FUSED_STEP_EPILOGUE) && fu.layout == 0 && a.P == d && a.spec.w_off == 0 && d % BN == 0 &&
+      C % BM == 0 && !option(SGMC_OPT_EXACT_UPDATE_MATH)) {
+    gradp.theta_rw = fu.theta_rw; gradp.v = fu.v;
+    gradp.keys_in = fu.keys_in; gradp.keys_out = fu.keys_out;
+    gradp.neg_eps = -fu.step_size;
+    gradp.noise_scale = sqrtf((2.0f * fu.temperature) * fu.step_size);   // integrator.py:882-884
+    gradp.alpha = fu.alpha; gradp.one_m_alpha = 1.0f - fu.alpha; gradp.lmbd = fu.lmbd;
+    gradp.half = (uint32_t)(d / 2);
+    if (!fu.write_grad) gradp.grad = nullptr;
+    if (make_map(&mA0, w.r_hi, !split, C, n, BM)) return 2;
+    if (make_map(&mB0, w.xt_hi, !split, d, n, BN / 2)) return 2;
+    if (split) {
+      if (make_map(&mA1, w.r_lo, 0, C, n, BM)) return 2;
+      if (make_map(&mB1, w.xt_lo, 0, d, n, BN / 2)) return 2;
+      if (launch_gemm<3, 2, 0>(stream, mA0, mA1, mB0, mB1, (int)C, d, (int)n, link, gradp,
+                               "k_glm_tc_gemm<split,grad+sgld>")) return 1;
+    } else {
+      if (launch_gemm<1, 2, 1>(stream, mA0, mA0, mB0, mB0, (int)C, d, (int)n, link, gradp,
+                               "k_glm_tc_gemm<bf16,grad+sgld>")) return 1;
+    }
+    *fu.applied = true;
+    return 0;
+  }
   if (!a.grad) return 0;
   // ---- GEMM2: G[C,d] = R[C,n] . XbT[d,n]^T ---------------------------------------
   if (make_map(&mA0, w.r_hi, !split, C, n, BM)) return 2;

@@ -13,6 +13,7 @@
 // Roofline: HBM.  Algorithmic bytes per parameter: SGLD 12, pSGLD 20,
 // SGHMC step 20, OBABO pass A 20 + pass B 12.
 #include "noise_pass.cuh"
+#include "sgld_math.cuh"
 
 #include <cmath>
 
@@ -149,29 +150,7 @@ struct SgldOp {
   }
   __device__ __forceinline__ float one(float t, float g, float& vv, float xi,
                                        float ns) const {
-    const float sg = __fmul_rn(neg_eps, g);
-    const float sn = __fmul_rn(ns, xi);
-    float delta;
-    if (RMS && FAST) {
-      vv = fmaf(alpha, vv, one_m_alpha * (g * g));
-      float s, G, S;
-      asm("sqrt.approx.f32 %0, %1;" : "=f"(s) : "f"(vv));
-      const float den = lmbd + s;
-      asm("rcp.approx.f32 %0, %1;" : "=f"(G) : "f"(den));
-      asm("rsqrt.approx.f32 %0, %1;" : "=f"(S) : "f"(den));   // sqrt(1/den)
-      delta = fmaf(S, sn, G * sg);
-    } else if (RMS) {
-      vv = __fadd_rn(__fmul_rn(alpha, vv),
-                     __fmul_rn(one_m_alpha, __fmul_rn(g, g)));
-      const float G = __frcp_rn(__fadd_rn(lmbd, __fsqrt_rn(vv)));
-      const float S = __fsqrt_rn(G);
-      // (eps*Gamma + G*sg) + S*sn with Gamma == 0; the "0 +" only affects the
-      // sign of an exact zero and is dropped.
-      delta = __fadd_rn(__fmul_rn(G, sg), __fmul_rn(S, sn));
-    } else {
-      delta = __fadd_rn(sg, sn);
-    }
-    return __fadd_rn(t, delta);
+    return sgld_one<RMS, FAST>(t, g, vv, xi, ns, neg_eps, alpha, one_m_alpha, lmbd);
   }
   __device__ void load_vec(Regs& r, int64_t iA, int64_t iB) const {
     r.tA = ld4(theta, iA);

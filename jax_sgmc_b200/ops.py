@@ -245,6 +245,27 @@ def glm_potential_grad(spec, theta, X, y, idx, observation_count, potential,
   return workspace
 
 
+def glm_sgld_step(spec, theta, X, y, idx, observation_count, potential, variance,
+                  grad, keys_in, keys_out, step_size, temperature=1.0, v=None,
+                  alpha=0.9, lmbd=1e-5, mask=None, workspace=None, path=0,
+                  batch_size=None, layout=0, write_grad=True, stream=None):
+  """One langevin_diffusion step on the GLM potential: potential / variance /
+  gradient at the current theta, then the SGLD (v None) or pSGLD update in
+  place -- inside the gradient GEMM's epilogue when the shapes allow."""
+  C_, P = theta.shape
+  n = int(batch_size if batch_size is not None
+          else (idx.size if idx is not None else X.shape[0]))
+  if workspace is None:
+    workspace = glm_workspace(C_, n, spec.d, path)
+  _lib.call("sgmc_glm_sgld_step", _s(stream), C.byref(spec), vp(theta), vp(v), C_, P,
+            vp(X), vp(y), vp(idx), vp(mask), n, int(observation_count),
+            vp(potential), vp(variance), vp(grad), vp(keys_in), vp(keys_out),
+            float(step_size), float(temperature), float(alpha), float(lmbd),
+            vp(workspace), workspace.nbytes, PATH[path], _layout(layout),
+            1 if write_grad else 0)
+  return workspace
+
+
 # ---- reSGLD ------------------------------------------------------------------------
 
 def resgld_decide(U_n, U_h, var_n, ssq, F, step, T_normal, T_hot, keys_in,
@@ -273,6 +294,7 @@ def swap_rows(a: DeviceArray, b: DeviceArray, exchange: DeviceArray, stream=None
 
 OPT_EXACT_UPDATE_MATH = 0
 OPT_SERIAL_LAUNCH = 1      # 1: disable programmatic dependent launch
+OPT_FUSED_STEP_EPILOGUE = 2  # 1: glm_sgld_step updates inside the gradient GEMM's epilogue
 
 
 def set_option(option: int, value: int):

@@ -17,6 +17,6 @@ for path in ("tc_parity","tc_throughput"):
   for rep in range(3):
     ops.glm_potential_grad(spec,theta,X,y,idx,N,U,var,(g if GR else None),workspace=ws,path=path)
     device.synchronize()
-    t=(C.c_ulonglong*8)(); lib.sgmc_debug_tc_timers(t)
+    t=(C.c_ulonglong*10)(); lib.sgmc_debug_tc_timers(t)
     a=[int(t[i])-int(t[0]) for i in range(8)]
   print(path,("GEMM2" if GR else "GEMM1")+" ns from start: setup",a[1],"mainloop_done",a[2],"tmem_ld",a[4],"staged",a[5],"chunk0 done",a[6],"loops done",a[7],"end",a[3])
