@@ -24,13 +24,14 @@
 // pipeline shared memory -> fully coalesced global stores.
 // Roofline: tensor pipe; algorithmic FLOPs 2*C*n*d per GEMM.
 #include "glm.cuh"
-#include "rng.cuh"
+#include "noise_pass.cuh"
 #include "sgld_math.cuh"
 
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
+#include <algorithm>
 #include <mutex>
 
 namespace sgmc {
@@ -204,6 +205,22 @@ struct TcGradEpi {      // GEMM2: G -> grad (adds -grad(prior)/T)
   uint32_t half;            // d / 2: element j shares its threefry block with j + half
 };
 
+// Side job of the GEMM kernels for sgmc_glm_sgld_step: while the tensor pipe
+// works, the otherwise idle warps 2..15 generate part of the step's Gaussian
+// noise (integrator.random_tree, single leaf of d elements per chain) into
+// xi[C][d]; k_sgld_apply then consumes it.  Work unit = a warp-tile of
+// k_noise_pass: 32 groups x 4 threefry pairs = 256 elements of one chain.
+struct TcNoiseJob {
+  float* xi;                // f32[C][d] or null (no job)
+  const uint32_t* keys_in;  // u32[C][2]
+  uint32_t* keys_out;       // u32[C][2]: split(key)[0], written by the tile owner
+  int tile0, tile_end;      // this launch's range of warp-tiles
+  int tiles_per_cta;
+  int d;
+};
+constexpr int kNoiseJobWarps = kTcWarps - 2;
+constexpr int kNoiseJobMaxChains = 128;
+
 // logistic link with SFU-based exp / log / reciprocal (abs. error ~1e-7):
 //   ell = y z - softplus(z),  dz = y - sigmoid(z)
 __device__ __forceinline__ void logistic_link_fast(float z, float y, float& ell, float& dz) {
@@ -228,7 +245,8 @@ struct TcSmem {
   static constexpr int kStages = (TERMS == 3 ? 2 : 4) * (64 / BK);
   static constexpr int kPipeBytes = kStages * kStageBytes;
   static constexpr int kAuxBytes = 256 /*barriers*/ + 3 * BN * 4 /*y, mask, rm*/ +
-                                   4 * BM * kStatFields * 4 /*row stats*/;
+                                   4 * BM * kStatFields * 4 /*row stats*/ +
+                                   kNoiseJobMaxChains * 8 /*noise-job keys*/;
   static constexpr int kBytes = kPipeBytes + kAuxBytes + 1024 /*alignment slack*/;
   static_assert(kPipeBytes >= kTcWarps * 32 * 33 * 4, "staging must fit in the pipeline smem");
 };
@@ -237,7 +255,8 @@ template <int TERMS, int EPI, int ABFMT>
 __global__ void __launch_bounds__(EPI == 2 ? kTcFusedThreads : kTcThreads, 1)
 k_glm_tc_gemm(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
               const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1,
-              int num_k_blocks, const TcLinkEpi link, const TcGradEpi gradp) {
+              int num_k_blocks, const TcLinkEpi link, const TcGradEpi gradp,
+              const TcNoiseJob job) {
   using S = TcSmem<TERMS>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(
@@ -251,6 +270,7 @@ k_glm_tc_gemm(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
   float* s_mask = s_y + BN;
   float* s_rm = s_mask + BN;                       // cot * mask * r_scale per column
   float* s_stats = s_rm + BN;                      // [4 col groups][BM][4]
+  Key* s_nk = reinterpret_cast<Key*>(s_stats + 4 * BM * kStatFields);   // noise-job keys
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
@@ -291,6 +311,29 @@ k_glm_tc_gemm(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
     s_y[threadIdx.x] = yv;
     s_mask[threadIdx.x] = mv;
     s_rm[threadIdx.x] = link.cot * mv * link.r_scale;
+  }
+  // noise job: tiles [jt0, jt1) of this CTA, keys of the chains they touch
+  int jt0 = 0, jt1 = 0, jtpc = 1, jc_lo = 0;
+  if (EPI != 2 && job.xi != nullptr) {
+    const int cta = blockIdx.y * gridDim.x + blockIdx.x;
+    jtpc = job.d / 256;
+    jt0 = min(job.tile0 + cta * job.tiles_per_cta, job.tile_end);
+    jt1 = min(jt0 + job.tiles_per_cta, job.tile_end);
+    if (jt0 < jt1) {
+      jc_lo = jt0 / jtpc;
+      const int n_ch = (jt1 - 1) / jtpc - jc_lo + 1;
+      if ((int)threadIdx.x < n_ch) {
+        const int64_t c = jc_lo + threadIdx.x;
+        const Key k{job.keys_in[2 * c], job.keys_in[2 * c + 1]};
+        Key newk, sub;
+        split2(k, 0, newk, sub);                       // integrator.py:871
+        s_nk[threadIdx.x] = split_key(sub, 0u, 1u, 0); // random_tree: split(sub, 1)[0]
+        if (c * jtpc >= jt0) {                         // owner of the chain's first tile
+          job.keys_out[2 * c] = newk.k0;
+          job.keys_out[2 * c + 1] = newk.k1;
+        }
+      }
+    }
   }
   if (EPI == 2 && threadIdx.x < BM) {
     // key', sub = split(key); noise key of the single leaf = split(sub, 1)[0]
@@ -426,6 +469,20 @@ k_glm_tc_gemm(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
       umma_commit(&empty_bar[s]);          // frees the smem stage when the MMAs retire
     }
     umma_commit(tmem_full_bar);            // accumulator complete
+  }
+
+  // ===== noise job of the idle warps, under the mainloop =====
+  if (EPI != 2 && warp >= 2 && jt0 < jt1) {
+    const uint32_t half = (uint32_t)job.d >> 1;
+    for (int t = jt0 + (warp - 2); t < jt1; t += kNoiseJobWarps) {
+      const int c = t / jtpc;
+      const uint32_t j0 = (uint32_t)((t - c * jtpc) * 32 + lane) * 4u;
+      float nA[4], nB[4];
+      group_noise<0, true>(s_nk[c - jc_lo], j0, half, (uint32_t)job.d, nA, nB);
+      float* row = job.xi + (int64_t)c * job.d;
+      *reinterpret_cast<float4*>(row + j0) = make_float4(nA[0], nA[1], nA[2], nA[3]);
+      *reinterpret_cast<float4*>(row + half + j0) = make_float4(nB[0], nB[1], nB[2], nB[3]);
+    }
   }
 
   // ===== epilogue: all 16 warps =====
@@ -1084,6 +1141,7 @@ struct TcWorkspace {
   float* stats;
   uint32_t* absmax_bits; float* x_scale;
   uint32_t* counters;
+  float* xi;                // f32[C][d]: noise of the pending update (sgmc_glm_sgld_step)
 };
 
 static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
@@ -1109,8 +1167,10 @@ static size_t carve(TcWorkspace* w, uint8_t* base, int64_t C, int64_t n, int64_t
   void* stats = take((size_t)C * parts * kStatFields * 4);
   void* am = take(256);
   void* cnt = take((size_t)((C + BM - 1) / BM) * 4);
+  void* xi = take((size_t)C * d * 4);
   if (w) {
     w->counters = (uint32_t*)cnt;
+    w->xi = (float*)xi;
     w->th_hi = th_hi; w->th_lo = (__half*)th_lo;
     w->row_scale = (float*)rs; w->row_sumsq = (float*)rq;
     w->xb_hi = xb_hi; w->xb_lo = (__half*)xb_lo; w->xt_hi = xt_hi; w->xt_lo = (__half*)xt_lo;
@@ -1119,6 +1179,34 @@ static size_t carve(TcWorkspace* w, uint8_t* base, int64_t C, int64_t n, int64_t
     w->absmax_bits = (uint32_t*)am; w->x_scale = (float*)am + 1;
   }
   return off;
+}
+
+// The update half of sgmc_glm_sgld_step when the noise was generated by the GEMM
+// kernels: one elementwise pass theta, v <- sgld(theta, v, grad, xi)
+// (integrator.py:882-914, adaption.py:254-291); 24 B per parameter, HBM/L2-bound.
+template <bool RMS>
+__global__ void __launch_bounds__(256) k_sgld_apply(float* __restrict__ theta, float* __restrict__ v,
+                                                    const float* __restrict__ grad,
+                                                    const float* __restrict__ xi, int64_t n4,
+                                                    float neg_eps, float ns, float alpha,
+                                                    float one_m_alpha, float lmbd) {
+  pdl_launch_dependents();
+  pdl_wait();
+  float4* t4 = reinterpret_cast<float4*>(theta);
+  float4* v4 = reinterpret_cast<float4*>(v);
+  const float4* g4 = reinterpret_cast<const float4*>(grad);
+  const float4* x4 = reinterpret_cast<const float4*>(xi);
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n4; i += (int64_t)gridDim.x * 256) {
+    float4 t = t4[i];
+    const float4 g = g4[i], x = x4[i];
+    float4 vv = RMS ? v4[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    t.x = sgld_one<RMS, RMS>(t.x, g.x, vv.x, x.x, ns, neg_eps, alpha, one_m_alpha, lmbd);
+    t.y = sgld_one<RMS, RMS>(t.y, g.y, vv.y, x.y, ns, neg_eps, alpha, one_m_alpha, lmbd);
+    t.z = sgld_one<RMS, RMS>(t.z, g.z, vv.z, x.z, ns, neg_eps, alpha, one_m_alpha, lmbd);
+    t.w = sgld_one<RMS, RMS>(t.w, g.w, vv.w, x.w, ns, neg_eps, alpha, one_m_alpha, lmbd);
+    t4[i] = t;
+    if (RMS) v4[i] = vv;
+  }
 }
 
 int glm_tc_debug_read(unsigned long long* out) {
@@ -1132,7 +1220,8 @@ size_t glm_tc_workspace_bytes(int64_t n_chains, int64_t batch_size, int64_t d, i
 template <int TERMS, int EPI, int ABFMT>
 static int launch_gemm(cudaStream_t stream, const CUtensorMap& a0, const CUtensorMap& a1,
                        const CUtensorMap& b0, const CUtensorMap& b1, int M, int N, int K,
-                       const TcLinkEpi& link, const TcGradEpi& gradp, const char* name) {
+                       const TcLinkEpi& link, const TcGradEpi& gradp, const char* name,
+                       TcNoiseJob job = TcNoiseJob{}) {
   using S = TcSmem<TERMS>;
   auto kfn = k_glm_tc_gemm<TERMS, EPI, ABFMT>;
   static bool attr_set = false;
@@ -1143,8 +1232,12 @@ static int launch_gemm(cudaStream_t stream, const CUtensorMap& a0, const CUtenso
     attr_set = true;
   }
   dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM);
+  if (job.xi != nullptr) {
+    const int ctas = (int)(grid.x * grid.y);
+    job.tiles_per_cta = (job.tile_end - job.tile0 + ctas - 1) / ctas;
+  }
   launch_pdl(kfn, grid, dim3(EPI == 2 ? kTcFusedThreads : kTcThreads), S::kBytes, stream, a0, a1, b0, b1,
-             (int)((K + BK - 1) / BK), link, gradp);
+             (int)((K + BK - 1) / BK), link, gradp, job);
   return post_launch(name);
 }
 
@@ -1223,6 +1316,27 @@ int glm_tc(cudaStream_t stream, const GlmArgs& a, int path) {
   gradp.xt_scale = w.x_scale;
   gradp.r_scale = r_scale;
 
+  // sgmc_glm_sgld_step: the update's Gaussian noise is generated by the idle warps
+  // of the two GEMMs (half each) and applied by k_sgld_apply afterwards.
+  const FusedSgld& fu = a.fused;
+  const bool aligned = ((reinterpret_cast<uintptr_t>(fu.theta_rw) | reinterpret_cast<uintptr_t>(fu.v) |
+                         reinterpret_cast<uintptr_t>(a.grad)) & 15u) == 0;
+  const bool fusable = fu.requested && fu.layout == 0 && a.P == d && a.spec.w_off == 0 &&
+                       d % 256 == 0 && a.grad != nullptr && !option(SGMC_OPT_EXACT_UPDATE_MATH);
+  const bool epilogue_update = fusable && option(SGMC_OPT_FUSED_STEP_EPILOGUE) && C % BM == 0;
+  const bool noise_job = fusable && !epilogue_update && aligned &&
+                         option(SGMC_OPT_STEP_NOISE_IN_GEMM);
+  TcNoiseJob job1{}, job2{};
+  if (noise_job) {
+    const int tiles = (int)(C * (d / 256));
+    job1.xi = job2.xi = w.xi;
+    job1.keys_in = job2.keys_in = fu.keys_in;
+    job1.keys_out = job2.keys_out = fu.keys_out;
+    job1.d = job2.d = d;
+    job1.tile0 = 0; job1.tile_end = tiles / 2;
+    job2.tile0 = tiles / 2; job2.tile_end = tiles;
+  }
+
   CUtensorMap mA0, mA1, mB0, mB1;
   // ---- GEMM1: Z[C,n] = Theta[C,d] . Xb[n,d]^T ------------------------------
   if (make_map(&mA0, w.th_hi, !split, C, d, BM)) return 2;
@@ -1231,19 +1345,17 @@ int glm_tc(cudaStream_t stream, const GlmArgs& a, int path) {
     if (make_map(&mA1, w.th_lo, 0, C, d, BM)) return 2;
     if (make_map(&mB1, w.xb_lo, 0, n, d, BN)) return 2;
     if (launch_gemm<3, 0, 0>(stream, mA0, mA1, mB0, mB1, (int)C, (int)n, d, link, gradp,
-                             "k_glm_tc_gemm<split,link>")) return 1;
+                             "k_glm_tc_gemm<split,link>", job1)) return 1;
   } else {
     if (launch_gemm<1, 0, 1>(stream, mA0, mA0, mB0, mB0, (int)C, (int)n, d, link, gradp,
-                             "k_glm_tc_gemm<bf16,link>")) return 1;
+                             "k_glm_tc_gemm<bf16,link>", job1)) return 1;
   }
   // U and var(ell) were finalised inside GEMM1 by the last CTA of every row block.
   // ---- GEMM2 with the SGLD / pSGLD update in its epilogue -----------------------------
   // Needs whole tiles, the sample to be exactly the weight vector (one leaf, so
   // feature j shares its threefry block with j + d/2) and the default (fast)
   // preconditioner arithmetic; otherwise the caller runs the stand-alone update.
-  const FusedSgld& fu = a.fused;
-  if (fu.requested && option(SGMC_OPT_FUSED_STEP_EPILOGUE) && fu.layout == 0 && a.P == d && a.spec.w_off == 0 && d % BN == 0 &&
-      C % BM == 0 && !option(SGMC_OPT_EXACT_UPDATE_MATH)) {
+  if (epilogue_update) {
     gradp.theta_rw = fu.theta_rw; gradp.v = fu.v;
     gradp.keys_in = fu.keys_in; gradp.keys_out = fu.keys_out;
     gradp.neg_eps = -fu.step_size;
@@ -1273,10 +1385,25 @@ int glm_tc(cudaStream_t stream, const GlmArgs& a, int path) {
     if (make_map(&mA1, w.r_lo, 0, C, n, BM)) return 2;
     if (make_map(&mB1, w.xt_lo, 0, d, n, BN)) return 2;
     if (launch_gemm<3, 1, 0>(stream, mA0, mA1, mB0, mB1, (int)C, d, (int)n, link, gradp,
-                             "k_glm_tc_gemm<split,grad>")) return 1;
+                             "k_glm_tc_gemm<split,grad>", job2)) return 1;
   } else {
     if (launch_gemm<1, 1, 1>(stream, mA0, mA0, mB0, mB0, (int)C, d, (int)n, link, gradp,
-                             "k_glm_tc_gemm<bf16,grad>")) return 1;
+                             "k_glm_tc_gemm<bf16,grad>", job2)) return 1;
+  }
+  if (noise_job) {
+    const int64_t n4 = C * (int64_t)d / 4;
+    const unsigned grid = (unsigned)std::min<int64_t>((n4 + 255) / 256, (int64_t)sm_count() * 8);
+    const float ns = sqrtf((2.0f * fu.temperature) * fu.step_size);   // integrator.py:882-884
+    if (fu.v)
+      launch_pdl(k_sgld_apply<true>, dim3(grid), dim3(256), 0, stream, fu.theta_rw, fu.v,
+                 (const float*)a.grad, (const float*)w.xi, n4, -fu.step_size, ns, fu.alpha,
+                 1.0f - fu.alpha, fu.lmbd);
+    else
+      launch_pdl(k_sgld_apply<false>, dim3(grid), dim3(256), 0, stream, fu.theta_rw,
+                 (float*)nullptr, (const float*)a.grad, (const float*)w.xi, n4, -fu.step_size,
+                 ns, 0.f, 0.f, 0.f);
+    if (post_launch("k_sgld_apply")) return 1;
+    *fu.applied = true;
   }
   return 0;
 }

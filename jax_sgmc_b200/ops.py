@@ -295,6 +295,7 @@ def swap_rows(a: DeviceArray, b: DeviceArray, exchange: DeviceArray, stream=None
 OPT_EXACT_UPDATE_MATH = 0
 OPT_SERIAL_LAUNCH = 1      # 1: disable programmatic dependent launch
 OPT_FUSED_STEP_EPILOGUE = 2  # 1: glm_sgld_step updates inside the gradient GEMM's epilogue
+OPT_STEP_NOISE_IN_GEMM = 3   # 1: glm_sgld_step generates the noise in the GEMMs' idle warps
 
 
 def set_option(option: int, value: int):
