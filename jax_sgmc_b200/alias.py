@@ -149,9 +149,79 @@ def obabo(potential_fn, data_loader, cache_size: int = 512, batch_size: int = 32
   return run_fn
 
 
-def amagold(*args, **kwargs):
-  raise NotImplementedError("alias.amagold is the next tier (SURVEY.md 8f)")
+def _mh_schedule(first_step_size, last_step_size, adaptive_step_size,
+                 stabilization_constant, decay_constant, speed_constant,
+                 target_acceptance_rate, burn_in, accepted_samples, progress_bar):
+  """alias.py:285-311 / :405-431."""
+  burn_in_schedule = scheduler.initial_burn_in(burn_in)
+  if adaptive_step_size:
+    step_size_schedule = scheduler.adaptive_step_size(
+        burn_in=burn_in, initial_step_size=first_step_size,
+        stabilization_constant=stabilization_constant, decay_constant=decay_constant,
+        speed_constant=speed_constant, target_acceptance_rate=target_acceptance_rate)
+    thinning = None
+    assert accepted_samples is None, ("Thinning currently not supported for"
+                                      " adaptive step size.")
+  else:
+    step_size_schedule = scheduler.polynomial_step_size_first_last(
+        first=first_step_size, last=last_step_size)
+    thinning = None if accepted_samples is None else scheduler.random_thinning(
+        step_size_schedule, burn_in_schedule, selections=accepted_samples)
+  return scheduler.init_scheduler(step_size=step_size_schedule, burn_in=burn_in_schedule,
+                                  thinning=thinning, progress_bar=progress_bar)
 
 
-def sggmc(*args, **kwargs):
-  raise NotImplementedError("alias.sggmc is the next tier (SURVEY.md 8f)")
+def amagold(stochastic_potential_fn, full_potential_fn, data_loader,
+            cache_size: int = 512, batch_size: int = 32, integration_steps: int = 10,
+            friction: float = 0.25, first_step_size: float = 0.001,
+            last_step_size: float = 0.001, adaptive_step_size: bool = False,
+            stabilization_constant: int = 10, decay_constant: float = 0.75,
+            speed_constant: float = 0.05, target_acceptance_rate: float = 0.25,
+            burn_in: int = 0, accepted_samples: Union[int, None] = None,
+            mass: Pytree = None, save_to_numpy: bool = True, progress_bar: bool = True):
+  """alias.py:210-328."""
+  random_data = data.random_reference_data(data_loader, cache_size, batch_size)
+  full_data_map = data.full_reference_data(data_loader, cache_size, batch_size)
+  reversible_leapfrog = integrator.reversible_leapfrog(
+      stochastic_potential_fn, random_data, integration_steps, friction, mass)
+  amagold_solver = solver.amagold(reversible_leapfrog, full_potential_fn, full_data_map)
+  schedule = _mh_schedule(first_step_size, last_step_size, adaptive_step_size,
+                          stabilization_constant, decay_constant, speed_constant,
+                          target_acceptance_rate, burn_in, accepted_samples, progress_bar)
+  mcmc = solver.mcmc(amagold_solver, schedule, strategy="map",
+                     saving=_saving(save_to_numpy))
+
+  def run_fn(*init_samples, init_model_state: Pytree = None, iterations=1000, keys=None):
+    state = amagold_solver[0](ChainTree.from_trees(list(init_samples)), key=keys,
+                              init_model_state=init_model_state)
+    return mcmc(state, iterations=iterations)
+
+  return run_fn
+
+
+def sggmc(stochastic_potential_fn, full_potential_fn, data_loader,
+          cache_size: int = 512, batch_size: int = 32, integration_steps: int = 10,
+          friction_coefficient: float = 1.0, first_step_size: float = 0.001,
+          last_step_size: float = 0.001, adaptive_step_size: bool = False,
+          stabilization_constant: int = 10, decay_constant: float = 0.75,
+          speed_constant: float = 0.05, target_acceptance_rate: float = 0.25,
+          burn_in: int = 0, accepted_samples: Union[int, None] = None,
+          mass: Pytree = None, save_to_numpy: bool = True, progress_bar: bool = True):
+  """alias.py:330-449."""
+  random_data = data.random_reference_data(data_loader, cache_size, batch_size)
+  full_data_map = data.full_reference_data(data_loader, cache_size, batch_size)
+  obabo_integrator = integrator.obabo(stochastic_potential_fn, random_data,
+                                      integration_steps, friction_coefficient, mass)
+  sggmc_solver = solver.sggmc(obabo_integrator, full_potential_fn, full_data_map)
+  schedule = _mh_schedule(first_step_size, last_step_size, adaptive_step_size,
+                          stabilization_constant, decay_constant, speed_constant,
+                          target_acceptance_rate, burn_in, accepted_samples, progress_bar)
+  mcmc = solver.mcmc(sggmc_solver, schedule, strategy="map",
+                     saving=_saving(save_to_numpy))
+
+  def run_fn(*init_samples, init_model_state: Pytree = None, iterations=1000, keys=None):
+    state = sggmc_solver[0](ChainTree.from_trees(list(init_samples)), key=keys,
+                            init_model_state=init_model_state)
+    return mcmc(state, iterations=iterations)
+
+  return run_fn

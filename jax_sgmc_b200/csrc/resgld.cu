@@ -36,6 +36,38 @@ __global__ void k_resgld_decide(const float* __restrict__ U_n,
   exchange[s] = (log_u < log_s) ? 0 : 1;                    // solver.py:287-291
 }
 
+// Metropolis-Hastings accept/reject of solver.sggmc (mode 0, solver.py:524-539)
+// and solver.amagold (mode 1, solver.py:381-395) for C chains.
+__global__ void k_mh_decide(int mode, float* __restrict__ U_state,
+                            const float* __restrict__ U_new, const float* __restrict__ e0,
+                            const float* __restrict__ e1, float neg_inv_T,
+                            const uint32_t* __restrict__ keys_in,
+                            uint32_t* __restrict__ keys_out, int32_t* __restrict__ reject,
+                            float* __restrict__ ratio, int64_t n, int layout) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n) return;
+  float la;
+  if (mode == 0) {
+    // -1/T * (U_new - U_old + ke_end - ke_start), capped at 0      solver.py:524-529
+    const float s = __fadd_rn(__fadd_rn(__fadd_rn(U_new[c], -U_state[c]), e1[c]), -e0[c]);
+    la = __fmul_rn(neg_inv_T, s);
+    la = (la <= 0.0f) ? la : 0.0f;
+  } else {
+    // U_old - U_new + accumulated energy, capped at 0               solver.py:381-383
+    la = __fadd_rn(__fadd_rn(U_state[c], -U_new[c]), e1[c]);
+    la = (la > 0.0f) ? 0.0f : la;
+  }
+  Key k{keys_in[2 * c], keys_in[2 * c + 1]}, nk, sub;
+  split2(k, layout, nk, sub);                               // key, split = split(key, 2)
+  keys_out[2 * c] = nk.k0;
+  keys_out[2 * c + 1] = nk.k1;
+  const float u = bits_to_uniform(random_word(sub, 0, 1, layout), 0.0f, 1.0f);
+  const bool accept = log_libdevice(u) < la;                // lax.cond(log(slice) < log_alpha
+  reject[c] = accept ? 0 : 1;
+  if (accept) U_state[c] = U_new[c];
+  ratio[c] = expf(la);                                      // acceptance_ratio statistic
+}
+
 __global__ void k_swap_rows(uint32_t* __restrict__ a, uint32_t* __restrict__ b,
                             const int32_t* __restrict__ exchange,
                             int64_t n_rows, int64_t row_words) {
@@ -72,6 +104,20 @@ int sgmc_resgld_decide(void* stream, const float* U_normal, const float* U_hot,
       U_normal, U_hot, var_normal, ssq, F, eta, temps, keys_in, keys_out,
       exchange, n_systems, prng_layout);
   return post_launch("sgmc_resgld_decide");
+}
+
+int sgmc_mh_decide(void* stream, int mode, float* U_state, const float* U_new,
+                   const float* e0, const float* e1, float temperature,
+                   const uint32_t* keys_in, uint32_t* keys_out, int32_t* reject,
+                   float* ratio, int64_t n_chains, int prng_layout) {
+  SGMC_REQUIRE(keys_in != keys_out, "keys_out must not alias keys_in");
+  SGMC_REQUIRE(mode == 0 || mode == 1, "unknown MH mode %d", mode);
+  SGMC_REQUIRE(e1 != nullptr && (mode == 1 || e0 != nullptr), "null energy argument");
+  if (n_chains == 0) return 0;
+  k_mh_decide<<<(unsigned)((n_chains + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+      mode, U_state, U_new, e0, e1, -1.0f / temperature, keys_in, keys_out, reject, ratio,
+      n_chains, prng_layout);
+  return post_launch("sgmc_mh_decide");
 }
 
 int sgmc_swap_rows(void* stream, void* a, void* b, const int32_t* exchange,

@@ -414,6 +414,76 @@ struct ObaboBOp {   // integrator.py:248-261
   }
 };
 
+// ---- reversible leapfrog (AMAGOLD) -------------------------------------------------
+// One _body_fun of integrator.reversible_leapfrog (integrator.py:395-466) after
+// the gradient, with the NEXT position update folded in:
+//   p' = (((1-eps*f) p) + (-eps g) + sqrt(4 f eps) (sqrt(m) xi)) * (1/(1+eps*f))
+//   energy[c] += (0.5 eps) * sum((p + p') * (inv_m g))                 (:395-400)
+//   theta  += pos_scale * (inv_m p')    pos_scale = eps (next body's :411-418) or
+//                                       0.5 eps (closing half step :545-546)
+struct RevLeapfrogOp {
+  float* theta;
+  float* mom;
+  const float* grad;
+  float* energy;       // f32[C] accumulator (LeapfrogState.potential)
+  const float* mass;   // f32[P] or null
+  float decay, neg_eps, noise_scale, inv_norm, half_eps, pos_scale;
+  static constexpr bool kReduce = true;
+  struct Regs {
+    float4 tA, tB, pA, pB, gA, gB;
+  };
+  __device__ __forceinline__ float one(float& t, float& p, float g, float xi,
+                                       uint32_t e) const {
+    float inv_m = 1.0f, sqrt_m = 1.0f;
+    if (mass) {
+      const float m = mass[e];
+      inv_m = __frcp_rn(m);
+      sqrt_m = __fsqrt_rn(m);
+    }
+    const float noise = __fmul_rn(noise_scale, __fmul_rn(sqrt_m, xi));
+    const float un = __fadd_rn(__fadd_rn(__fmul_rn(decay, p), __fmul_rn(neg_eps, g)), noise);
+    const float pn = __fmul_rn(inv_norm, un);
+    const float en = __fmul_rn(__fadd_rn(p, pn), __fmul_rn(inv_m, g));
+    t = __fadd_rn(t, __fmul_rn(pos_scale, __fmul_rn(inv_m, pn)));
+    p = pn;
+    return en;
+  }
+  __device__ void load_vec(Regs& r, int64_t iA, int64_t iB) const {
+    r.tA = ld4(theta, iA); r.tB = ld4(theta, iB);
+    r.pA = ld4(mom, iA);   r.pB = ld4(mom, iB);
+    r.gA = ld4(grad, iA);  r.gB = ld4(grad, iB);
+  }
+  __device__ float apply_vec(Regs& r, const float nA[4], const float nB[4],
+                             int64_t iA, int64_t iB, int64_t, uint32_t eA,
+                             uint32_t eB) const {
+    float ta[4] = {r.tA.x, r.tA.y, r.tA.z, r.tA.w};
+    float tb[4] = {r.tB.x, r.tB.y, r.tB.z, r.tB.w};
+    float pa[4] = {r.pA.x, r.pA.y, r.pA.z, r.pA.w};
+    float pb[4] = {r.pB.x, r.pB.y, r.pB.z, r.pB.w};
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      s += one(ta[k], pa[k], f4get(r.gA, k), nA[k], eA + k);
+      s += one(tb[k], pb[k], f4get(r.gB, k), nB[k], eB + k);
+    }
+    st4(theta, iA, make_float4(ta[0], ta[1], ta[2], ta[3]));
+    st4(theta, iB, make_float4(tb[0], tb[1], tb[2], tb[3]));
+    st4(mom, iA, make_float4(pa[0], pa[1], pa[2], pa[3]));
+    st4(mom, iB, make_float4(pb[0], pb[1], pb[2], pb[3]));
+    return s;
+  }
+  __device__ float apply_one(int64_t i, float n, int64_t, uint32_t e) const {
+    float t = theta[i], p = mom[i];
+    const float s = one(t, p, grad[i], n, e);
+    theta[i] = t;
+    mom[i] = p;
+    return s;
+  }
+  __device__ void reduce(int64_t c, float s) const {
+    atomicAdd(&energy[c], half_eps * s);
+  }
+};
+
 static bool aligned16(std::initializer_list<const void*> ps) {
   for (const void* p : ps)
     if (p && (reinterpret_cast<uintptr_t>(p) & 15u)) return false;
@@ -561,6 +631,25 @@ int sgmc_obabo_pass_b(void* stream, float* momentum, const float* grad,
   return launch_noise_pass((cudaStream_t)stream, tab, keys_in, nullptr,
                            n_chains, kKeySplit3B, prng_layout, op,
                            "sgmc_obabo_pass_b");
+}
+
+int sgmc_revleapfrog_step(void* stream, float* theta, float* momentum, const float* grad,
+                          float* energy, const uint32_t* keys_in, uint32_t* keys_out,
+                          int64_t n_chains, const int64_t* leaf_sizes, int n_leaves,
+                          float step_size, float friction, const float* mass, int last,
+                          int prng_layout) {
+  SGMC_REQUIRE(keys_in != keys_out, "keys_out must not alias keys_in");
+  LeafTable tab;
+  if (int e = build_leaf_table(&tab, leaf_sizes, n_leaves, n_chains,
+                               aligned16({theta, momentum, grad}))) return e;
+  // integrator.py:423-446: weak-typed python scalars times the f32 step size
+  const float ef = step_size * friction;
+  RevLeapfrogOp op{theta, momentum, grad, energy, mass,
+                   1.0f - ef, -1.0f * step_size, sqrtf((4.0f * friction) * step_size),
+                   1.0f / (1.0f + ef), 0.5f * step_size,
+                   last ? 0.5f * step_size : step_size};
+  return launch_noise_pass((cudaStream_t)stream, tab, keys_in, keys_out, n_chains,
+                           kKeySplit2, prng_layout, op, "sgmc_revleapfrog_step");
 }
 
 }  // extern "C"

@@ -160,6 +160,11 @@ class DeviceArray:
               self.nbytes, s.handle)
     return out
 
+  def zero_(self, stream: Optional[Stream] = None) -> "DeviceArray":
+    s = stream or current_stream()
+    _lib.call("sgmc_memset", C.c_void_p(self.ptr), 0, self.nbytes, s.handle)
+    return self
+
   def copy_from(self, other: "DeviceArray", stream: Optional[Stream] = None):
     assert other.nbytes == self.nbytes
     s = stream or current_stream()

@@ -331,6 +331,71 @@ def obabo(potential_fn, batch_fn, steps: int = 10, friction: float = 1.0,
   return init_fn, integrate, get_fn
 
 
-def reversible_leapfrog(*args, **kwargs):
-  raise NotImplementedError("reversible_leapfrog (AMAGOLD) is the next tier "
-                            "(SURVEY.md section 8f)")
+def reversible_leapfrog(potential_fn, batch_fn, steps: int = 10, friction=0.25,
+                        const_mass: PyTree = None) -> Tuple[Callable, Callable, Callable]:
+  """integrator.py:349-560 (the AMAGOLD integrator): half position step,
+  ``steps`` momentum updates with friction and accumulated energy difference,
+  half position step."""
+  init_data, get_data, _ = batch_fn
+  stochastic_gradient = _potential.value_and_grad(potential_fn)
+  scratch: Dict[int, Any] = {}
+
+  def _mass_vector(mass, theta):
+    m = mass if mass is not None else const_mass
+    return None if m is None else _flat_vector(m, theta)
+
+  def init_fn(init_sample, key=None, batch_kwargs: Dict = None,
+              init_model_state: PyTree = None, mass: PyTree = None) -> LeapfrogState:
+    batch_kwargs = batch_kwargs or {}
+    sample = _as_chain_tree(init_sample)
+    C = sample.n_chains
+    ks = ops.split(_keys_for(key, C).current, 2).numpy()            # :500
+    momentum = random_tree(ks[:, 1], sample)                        # :501, :383-386
+    m = _mass_vector(mass, sample)
+    if m is not None:
+      momentum.flat.copy_from_host(momentum.flat.numpy() * np.sqrt(m.numpy())[None, :])
+    return LeapfrogState(
+        potential=DeviceArray.zeros((C,)), key=KeyState(ks[:, 0]), positions=sample,
+        momentum=momentum, data_state=_init_data_state(init_data, batch_kwargs, C),
+        model_state=init_model_state, extra_fields=None)
+
+  def integrate(state: LeapfrogState, parameters, mass: PyTree = None) -> LeapfrogState:
+    theta, p = state.positions, state.momentum
+    eps = np.float32(parameters.step_size)
+    sc = scratch.get(id(theta.flat))
+    if sc is None:
+      m = _mass_vector(mass, theta)
+      inv_full = None
+      if m is not None:      # inv_m broadcast over the chains for the opening half step
+        inv_full = DeviceArray.from_numpy(
+            np.tile((np.float32(1.0) / m.numpy())[None, :], (theta.n_chains, 1)))
+      sc = scratch[id(theta.flat)] = {
+          "grad": DeviceArray(theta.flat.shape, np.float32), "mass": m,
+          "inv_full": inv_full, "tmp": None if m is None else DeviceArray(theta.flat.shape,
+                                                                         np.float32),
+          "U": DeviceArray((theta.n_chains,), np.float32)}
+    half = float(np.float32(0.5) * eps)
+    if sc["mass"] is None:                                           # :523-524
+      ops.axpby(theta.flat, 1.0, theta.flat, half, p.flat)
+    else:
+      ops.tree_ewise(2, sc["tmp"], 1.0, sc["inv_full"], p.flat)
+      ops.axpby(theta.flat, 1.0, theta.flat, half, sc["tmp"])
+    state.potential.zero_()                                          # :531
+    data_state, model_state = state.data_state, state.model_state
+    for s in range(steps):                                           # :538-541
+      data_state, mini_batch = get_data(data_state, information=True)   # :427
+      (_, model_state), grad = stochastic_gradient(
+          theta, mini_batch, state=model_state, grad_out=sc["grad"], U_out=sc["U"])
+      ops.revleapfrog_step(theta.flat, p.flat, grad.flat, state.potential,
+                           state.key.current, state.key.next, theta.sizes, float(eps),
+                           float(friction), sc["mass"], last=(s == steps - 1))
+      state.key.flip()
+    return LeapfrogState(positions=theta, momentum=p, key=state.key,
+                         potential=state.potential, model_state=model_state,
+                         data_state=data_state, extra_fields=state.extra_fields)
+
+  def get_fn(state: LeapfrogState) -> Dict[str, PyTree]:
+    return {"variables": state.positions, "energy": state.potential,
+            "model_state": state.model_state}
+
+  return init_fn, integrate, get_fn

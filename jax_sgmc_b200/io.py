@@ -55,6 +55,16 @@ class _SavingState:
     self.capacity = int(capacity)
     self.variables = DeviceArray((max(self.capacity, 1), C, P), np.float32)
     self.scalars = DeviceArray((max(self.capacity, 1), C), np.float32)
+    # further per-chain scalars of the solver's get() (acceptance_ratio, step_size,
+    # kinetic_energy, potential of the MH solvers; solver.py:426-431, :568-575)
+    self.extra = {}
+    for k, v in template.items():
+      if k in ("variables", "model_state", self.scalar_key):
+        continue
+      if isinstance(v, DeviceArray) and v.shape == (C,):
+        self.extra[k] = DeviceArray((max(self.capacity, 1), C), np.float32)
+      elif isinstance(v, np.ndarray) and v.shape == (C,):
+        self.extra[k] = np.zeros((max(self.capacity, 1), C), np.float32)
     self.count = 0
 
 
@@ -75,6 +85,11 @@ def _make(checkpoint_every: int = 0):
       state.negate = isinstance(sc, Negated)     # "likelihood" = -U, kept lazy
       state.scalars.row_slice(state.count, state.count + 1).copy_from(
           sc.array if state.negate else sc)
+      for k, buf in state.extra.items():
+        if isinstance(buf, DeviceArray):
+          buf.row_slice(state.count, state.count + 1).copy_from(sample[k])
+        else:
+          buf[state.count] = sample[k]
       state.count += 1
     return state, None
 
@@ -84,12 +99,14 @@ def _make(checkpoint_every: int = 0):
     sca = state.scalars.numpy()[:n]              # [n, C]
     if getattr(state, "negate", False):
       sca = -sca                                 # get_fn labels -U (integrator.py:853-855)
+    extra = {k: (b.numpy() if isinstance(b, DeviceArray) else b)[:n]
+             for k, b in state.extra.items()}
     out = []
     for c in range(var.shape[1]):
       tree = unravel_rows(var[:, c], state.template.treedef, state.template.shapes)
-      out.append({"sample_count": n,
-                  "samples": {"variables": tree, state.scalar_key: sca[:, c].copy(),
-                              "model_state": None}})
+      samples = {"variables": tree, state.scalar_key: sca[:, c].copy(), "model_state": None}
+      samples.update({k: b[:, c].copy() for k, b in extra.items()})
+      out.append({"sample_count": n, "samples": samples})
     return out
 
   return init_saving, save, postprocess

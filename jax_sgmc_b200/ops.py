@@ -266,6 +266,24 @@ def glm_sgld_step(spec, theta, X, y, idx, observation_count, potential, variance
   return workspace
 
 
+# ---- MH-corrected samplers ------------------------------------------------------------
+
+def revleapfrog_step(theta, momentum, grad, energy, keys_in, keys_out, leaf_sizes,
+                     step_size, friction, mass=None, last=False, layout=0, stream=None):
+  _lib.call("sgmc_revleapfrog_step", _s(stream), vp(theta), vp(momentum), vp(grad),
+            vp(energy), vp(keys_in), vp(keys_out), theta.shape[0], i64_array(leaf_sizes),
+            len(leaf_sizes), float(step_size), float(friction), vp(mass),
+            1 if last else 0, _layout(layout))
+
+
+def mh_decide(mode, U_state, U_new, e0, e1, temperature, keys_in, keys_out, reject,
+              ratio, layout=0, stream=None):
+  """mode 'sggmc' | 'amagold'; see sgmc_mh_decide."""
+  _lib.call("sgmc_mh_decide", _s(stream), {"sggmc": 0, "amagold": 1}[mode], vp(U_state),
+            vp(U_new), vp(e0), vp(e1), float(temperature), vp(keys_in), vp(keys_out),
+            vp(reject), vp(ratio), U_state.size, _layout(layout))
+
+
 # ---- reSGLD ------------------------------------------------------------------------
 
 def resgld_decide(U_n, U_h, var_n, ssq, F, step, T_normal, T_hot, keys_in,

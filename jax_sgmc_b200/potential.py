@@ -162,24 +162,28 @@ def full_potential(prior, likelihood, strategy: str = "map", has_state: bool = F
 
   def sum_batched_evaluations(sample: ChainTree, data_state, full_data_map_fn,
                               state: Any = None):
+    """Returns ``(U f32[C] on the device, (data_state, state))``; everything is
+    enqueued, nothing synchronises (the MH solvers consume U on the device)."""
     first = []
+    total = DeviceArray.zeros((sample.n_chains,))
 
     def body(reference_data, mask, carry):
       if not first:
         first.append(reference_data)
       U, _ = batch_potential(sample, reference_data, carry, mask)
       _, info = reference_data
-      # undo the N/n scaling (potential.py:264-271)
-      return U.numpy().astype(np.float64) * info.batch_size / info.observation_count, carry
+      # undo the N/n scaling and add up (potential.py:264-271, :290)
+      ops.axpby(total, 1.0, total, info.batch_size / info.observation_count, U)
+      return None, carry
 
-    data_state, (results, new_state) = full_data_map_fn(
+    data_state, (_, new_state) = full_data_map_fn(
         body, data_state, state, masking=True, information=True)
-    total = np.sum(results, axis=0)
-    # prior value: evaluate the potential on an all-masked batch (L = 0)
+    # prior value: the potential of an all-masked batch is -prior (L = 0)
     ref = first[0]
     zero_mask = DeviceArray.zeros((ref[0].n,))
-    Up, _ = prior_only(sample, ref, None, zero_mask)       # = -prior
-    prior_val = -Up.numpy().astype(np.float64)
-    return ((total - prior_val) / temperature).astype(np.float32), (data_state, new_state)
+    Up, _ = prior_only(sample, ref, None, zero_mask)
+    out = DeviceArray((sample.n_chains,), np.float32)
+    ops.axpby(out, 1.0 / temperature, total, 1.0 / temperature, Up)    # (sum - prior) / T
+    return out, (data_state, new_state)
 
   return sum_batched_evaluations

@@ -130,6 +130,45 @@ def polynomial_step_size_first_last(first: float = 1.0, last: float = 1.0,
                             lambda state, iteration, **kw: state[iteration])
 
 
+def adaptive_step_size(burn_in=0, initial_step_size=0.05, stabilization_constant=100,
+                       decay_constant=0.75, speed_constant=0.05,
+                       target_acceptance_rate=0.02) -> specific_scheduler:
+  """scheduler.py:376-444: dual averaging of log(step size) on the MH acceptance
+  ratio during burn in.  All chains of a call share one schedule here, so the
+  statistic is the MEAN acceptance ratio of the chains (for a single chain this
+  is the reference's update; the reference adapts every chain separately)."""
+
+  def init_fn(iterations: int, burn_in=burn_in, initial_step_size=initial_step_size,
+              stabilization_constant=stabilization_constant,
+              decay_constant=decay_constant, speed_constant=speed_constant,
+              target_acceptance_rate=target_acceptance_rate):
+    del iterations
+    x_bar = np.log(F32(initial_step_size)).astype(F32)
+    return (burn_in, x_bar, F32(0.0), F32(target_acceptance_rate),
+            F32(stabilization_constant), F32(decay_constant), F32(speed_constant),
+            np.log(F32(10 * initial_step_size)).astype(F32))
+
+  def update_fn(state, iteration: int, acceptance_ratio=0.0, **kw):
+    del kw
+    burn_in, x_bar, h_bar, alpha, t0, kappa, gamma, mu = state
+    acc = F32(np.mean(np.asarray(acceptance_ratio, dtype=np.float32)))
+    m = F32(iteration + 1)
+    # the reference uses the closed-over target_acceptance_rate (:423), not `alpha`
+    h_bar = F32(h_bar * F32(F32(1) - F32(1) / F32(m + t0)))
+    h_bar = F32(h_bar + F32(F32(1) / F32(m + t0)) * F32(F32(target_acceptance_rate) - acc))
+    x = F32(mu - F32(np.sqrt(m) / gamma) * h_bar)
+    lr = F32(np.power(m, -kappa))
+    x_new = F32(F32(x_bar * F32(F32(1) - lr)) + F32(lr * x))
+    x_bar = x_new if iteration < burn_in else x_bar             # only during burn in
+    return burn_in, x_bar, h_bar, alpha, t0, kappa, gamma, mu
+
+  def get_fn(state, iteration: int, **kw):
+    del iteration, kw
+    return F32(np.exp(state[1]))
+
+  return specific_scheduler(init_fn, update_fn, get_fn)
+
+
 def initial_burn_in(n: int = 0) -> specific_scheduler:
   """scheduler.py:567-596: discard the first n steps (returns 0.0 / 1.0)."""
   return specific_scheduler(

@@ -143,9 +143,110 @@ def parallel_tempering(integrator, sa_schedule: Callable = lambda n: 1 / n
   return init, update, get
 
 
-def amagold(*args, **kwargs):
-  raise NotImplementedError("solver.amagold is the next tier (SURVEY.md 8f)")
+class MHState:
+  """SGGMCState / AMAGOLDState (solver.py:45-62) for C chains advancing together.
+
+  ``potential`` is the full-data potential of the current sample; ``saved`` holds
+  the pre-proposal copies the rejected chains are restored from."""
+
+  def __init__(self, integrator_state, potential, full_data_state, key, C, P):
+    self.integrator_state = integrator_state
+    self.potential = potential
+    self.full_data_state = full_data_state
+    self.key = key
+    self.mass_state = None
+    self.reject = DeviceArray((C,), np.int32)
+    self.ratio = DeviceArray.zeros((C,))
+    self.kinetic = DeviceArray.zeros((C,))
+    self.step_size = 0.0
+    self.saved = {"theta": DeviceArray((C, P), np.float32),
+                  "momentum": DeviceArray((C, P), np.float32),
+                  "potential": DeviceArray((C,), np.float32)}
+
+  @property
+  def acceptance_ratio(self):
+    return self.ratio, self.step_size, self.kinetic
 
 
-def sggmc(*args, **kwargs):
-  raise NotImplementedError("solver.sggmc is the next tier (SURVEY.md 8f)")
+def _mh_solver(kind, integrator_fn, full_potential_fn, full_data_map, mass_adaption):
+  if mass_adaption is not None:
+    raise NotImplementedError("adaption.mass_matrix is outside this path")
+  init_integrator, update_integrator, get_integrator = integrator_fn
+  init_full_data, full_data_map_fn, _ = full_data_map
+
+  def init(init_sample, key=None, initial_mass=None, full_data_kwargs: dict = None,
+           **kwargs) -> MHState:
+    del initial_mass
+    sample = _as_chain_tree(init_sample)
+    C = sample.n_chains
+    full_data_state = init_full_data(**(full_data_kwargs or {}))
+    potential, (full_data_state, model_state) = full_potential_fn(    # :474-478 / :341-345
+        sample, full_data_state, full_data_map_fn, state=kwargs.get("init_model_state"))
+    kwargs["init_model_state"] = model_state
+    key = ops.prng_key(0) if key is None else np.asarray(key, np.uint32)
+    if key.ndim == 1:
+      key = np.tile(key, (C, 1))
+    ks = ops.split(DeviceArray.from_numpy(key), 2).numpy()            # :483 / :349
+    integrator_state = init_integrator(sample, key=ks[:, 0], **kwargs)
+    return MHState(integrator_state, potential, full_data_state, KeyState(ks[:, 1]),
+                   C, sample.n_params)
+
+  def update(state: MHState, schedule):
+    old = state.integrator_state
+    # the integrators update in place: keep what a rejected chain goes back to
+    state.saved["theta"].copy_from(old.positions.flat)
+    state.saved["momentum"].copy_from(old.momentum.flat)
+    state.saved["potential"].copy_from(old.potential)
+    proposal = update_integrator(old, schedule, mass=None)            # :512-515 / :372-375
+    new_potential, (full_data_state, _) = full_potential_fn(          # :518-522 / :378-382
+        proposal.positions, state.full_data_state, full_data_map_fn,
+        state=proposal.model_state)
+    if kind == "sggmc":
+      ops.mh_decide("sggmc", state.potential, new_potential,
+                    proposal.kinetic_energy_start, proposal.kinetic_energy_end,
+                    float(schedule.temperature), state.key.current, state.key.next,
+                    state.reject, state.ratio)                        # :524-539
+      ops.axpby(state.kinetic, 1.0, proposal.kinetic_energy_end, -1.0,
+                proposal.kinetic_energy_start)                        # :563
+    else:
+      ops.mh_decide("amagold", state.potential, new_potential, None, proposal.potential,
+                    1.0, state.key.current, state.key.next, state.reject,
+                    state.ratio)                                      # :381-395
+      # a rejected chain restarts from the old state with the momentum flipped (:392-399)
+      ops.tree_ewise(0, state.saved["momentum"], -1.0, state.saved["momentum"])
+    state.key.flip()
+    ops.swap_rows(proposal.positions.flat, state.saved["theta"], state.reject)
+    ops.swap_rows(proposal.momentum.flat, state.saved["momentum"], state.reject)
+    ops.swap_rows(proposal.potential, state.saved["potential"], state.reject)
+    if kind == "sggmc":                                               # :551-552
+      proposal.kinetic_energy_start.zero_()
+      proposal.kinetic_energy_end.zero_()
+    state.integrator_state = proposal       # data_state / key of the proposal (:547-550)
+    state.full_data_state = full_data_state
+    state.step_size = float(schedule.step_size)
+    return state, {"acceptance_ratio": state.ratio}
+
+  def get(state: MHState) -> Dict[str, Any]:
+    out = get_integrator(state.integrator_state)
+    out["acceptance_ratio"] = state.ratio
+    out["step_size"] = np.full((state.ratio.shape[0],), state.step_size, np.float32)
+    if kind == "sggmc":
+      out["kinetic_energy"] = state.kinetic
+      out["potential"] = state.potential
+    return out
+
+  return init, update, get
+
+
+def amagold(integrator_fn, full_potential_fn, full_data_map, mass_adaption=None
+            ) -> Tuple[Callable, Callable, Callable]:
+  """solver.py:301-432: reversible leapfrog proposal + amortised MH correction."""
+  return _mh_solver("amagold", integrator_fn, full_potential_fn, full_data_map,
+                    mass_adaption)
+
+
+def sggmc(integrator_fn, full_potential_fn, full_data_map, mass_adaption=None
+          ) -> Tuple[Callable, Callable, Callable]:
+  """solver.py:434-577: OBABO proposal + MH correction on the full potential."""
+  return _mh_solver("sggmc", integrator_fn, full_potential_fn, full_data_map,
+                    mass_adaption)

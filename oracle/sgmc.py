@@ -540,3 +540,157 @@ def parallel_tempering_update(state: TemperingState, grad_fn_normal,
   normal = LangevinState(*[f[0] for f in fields])
   hot = LangevinState(*[f[1] for f in fields])
   return TemperingState(normal, hot, ssq, state.F, step, key), exchange
+
+
+# ----------------------------------------------------------------------------
+# integrator.reversible_leapfrog (AMAGOLD)   (integrator.py:349-560)
+# ----------------------------------------------------------------------------
+
+def reversible_leapfrog_init(theta, keys=None, mass=None, sizes=None,
+                             layout="original"):
+  """``reversible_leapfrog.init_fn`` (integrator.py:472-512): ``key, split =
+  split(key)``; momentum = sqrt(m) * random_tree(split, sample); potential 0."""
+  theta = np.asarray(theta, F32)
+  C, P = theta.shape
+  if keys is None:
+    keys = np.tile(prng.PRNGKey(0), (C, 1))
+  sizes = [P] if sizes is None else sizes
+  sqrt_m = np.ones(P, F32) if mass is None else np.sqrt(np.asarray(mass, F32)).astype(F32)
+  ks = prng.split(np.asarray(keys, np.uint32), 2, layout)
+  key, sub = ks[..., 0, :], ks[..., 1, :]
+  p = (sqrt_m * random_tree_flat(sub, sizes, layout)).astype(F32)
+  return LeapfrogState(theta, p, key, np.zeros(C, F32))
+
+
+def reversible_leapfrog_integrate(state: LeapfrogState, grad_fns, sizes, step_size,
+                                  friction=0.25, mass=None, layout="original"):
+  """``reversible_leapfrog.integrate`` (integrator.py:514-553, body :403-466).
+
+  ``grad_fns``: one ``theta -> (U, ell, grad)`` per inner step (only the
+  gradient is used, :375).  Half position step, ``steps`` bodies (the first one
+  skips the position update, :411-418), half position step; the accumulated
+  energy starts at 0 (:531) and is returned in ``potential``.
+  """
+  P = state.theta.shape[1]
+  mass = np.ones(P, F32) if mass is None else np.asarray(mass, F32)
+  inv_m = (F32(1.0) / mass).astype(F32)
+  sqrt_m = np.sqrt(mass).astype(F32)
+  eps = F32(step_size)
+  f = F32(friction)
+  half_eps = F32(F32(0.5) * eps)
+
+  def position_update(scale, pos, mom):                      # :378-381
+    return (pos + (scale * (inv_m * mom).astype(F32)).astype(F32)).astype(F32)
+
+  theta = position_update(half_eps, state.theta, state.momentum)   # :523-524
+  p, key = state.momentum, state.key
+  energy = np.zeros(theta.shape[0], F32)                     # :531
+  noise_scale = np.sqrt(F32(F32(4.0 * friction) * eps)).astype(F32)   # :424
+  decay = F32(F32(1.0) - F32(eps * f))                       # :436
+  norm = F32(F32(1.0) / F32(F32(1.0) + F32(eps * f)))        # :446
+  neg_eps = F32(F32(-1.0) * eps)                             # :439
+  for step, g_fn in enumerate(grad_fns):
+    if step > 0:
+      theta = position_update(eps, theta, p)                 # :411-418
+    ks = prng.split(key, 2, layout)                          # :420
+    key, sub = ks[..., 0, :], ks[..., 1, :]
+    noise = (sqrt_m * random_tree_flat(sub, sizes, layout)).astype(F32)   # :383-386
+    scaled_noise = (noise_scale * noise).astype(F32)         # :423-425
+    _, _, g = g_fn(theta)                                    # :427-431
+    un = (((decay * p).astype(F32) + (neg_eps * g).astype(F32)).astype(F32)
+          + scaled_noise).astype(F32)                        # :435-444
+    pn = (norm * un).astype(F32)                             # :445-447
+    dot = _tree_dot((p + pn).astype(F32), (inv_m * g).astype(F32), sizes)   # :395-399
+    energy = ((half_eps * dot).astype(F32) + energy).astype(F32)   # :400, :455
+    p = pn
+  theta = position_update(half_eps, theta, p)                # :545-546
+  return LeapfrogState(theta, p, key, energy)
+
+
+# ----------------------------------------------------------------------------
+# solver.sggmc / solver.amagold: MH correction   (solver.py:301-577)
+# ----------------------------------------------------------------------------
+
+def mh_decision(mode, U_state, U_new, e0, e1, temperature, keys, layout="original"):
+  """Accept/reject arithmetic of solver.sggmc (:524-539) / solver.amagold
+  (:381-395).  Returns (accept[C] bool, key'[C,2], log_alpha, ratio)."""
+  if mode == "sggmc":
+    s = (((U_new - U_state).astype(F32) + e1).astype(F32) - e0).astype(F32)
+    la = (F32(F32(-1.0) / F32(temperature)) * s).astype(F32)
+    la = np.where(la <= 0, la, F32(0.0)).astype(F32)
+  else:
+    la = ((U_state - U_new).astype(F32) + e1).astype(F32)
+    la = np.where(la > 0, F32(0.0), la).astype(F32)
+  ks = prng.split(keys, 2, layout)
+  key, sub = ks[..., 0, :], ks[..., 1, :]
+  u = prng.uniform(sub, (), layout=layout)
+  accept = prng.log_libdevice(u) < la
+  return accept, key, la, np.exp(la.astype(np.float64)).astype(F32)
+
+
+class MHState(NamedTuple):
+  integrator_state: tuple   # ObaboState (sggmc) or LeapfrogState (amagold)
+  potential: np.ndarray     # f32[C] full potential of the current sample
+  key: np.ndarray           # u32[C, 2]
+  acceptance_ratio: np.ndarray
+
+
+def sggmc_init(theta, full_potential_fn, keys=None, layout="original"):
+  """solver.sggmc.init (:462-500): ``key, split = split(key)``; the integrator
+  gets ``key``, the solver keeps ``split``."""
+  theta = np.asarray(theta, F32)
+  C = theta.shape[0]
+  if keys is None:
+    keys = np.tile(prng.PRNGKey(0), (C, 1))
+  ks = prng.split(np.asarray(keys, np.uint32), 2, layout)
+  return MHState(obabo_init(theta, ks[..., 0, :]), full_potential_fn(theta),
+                 ks[..., 1, :], np.zeros(C, F32))
+
+
+def sggmc_update(state: MHState, grad_fn_pairs, full_potential_fn, sizes, step_size,
+                 temperature=1.0, friction=1.0, mass=None, layout="original"):
+  """solver.sggmc.update (:502-566)."""
+  old = state.integrator_state
+  prop = obabo_integrate(old, grad_fn_pairs, sizes, step_size, temperature, friction,
+                         mass, layout)
+  U_new = full_potential_fn(prop.theta)
+  accept, key, _, ratio = mh_decision("sggmc", state.potential, U_new,
+                                      prop.kinetic_energy_start, prop.kinetic_energy_end,
+                                      temperature, state.key, layout)
+  m = accept[:, None]
+  zeros = np.zeros_like(prop.kinetic_energy_start)
+  new_int = ObaboState(np.where(m, prop.theta, old.theta),
+                       np.where(m, prop.momentum, old.momentum), prop.key,
+                       np.where(accept, prop.potential, old.potential), zeros, zeros)
+  return MHState(new_int, np.where(accept, U_new, state.potential).astype(F32), key,
+                 ratio), accept
+
+
+def amagold_init(theta, full_potential_fn, keys=None, mass=None, sizes=None,
+                 layout="original"):
+  """solver.amagold.init (:323-362)."""
+  theta = np.asarray(theta, F32)
+  C = theta.shape[0]
+  if keys is None:
+    keys = np.tile(prng.PRNGKey(0), (C, 1))
+  ks = prng.split(np.asarray(keys, np.uint32), 2, layout)
+  return MHState(reversible_leapfrog_init(theta, ks[..., 0, :], mass, sizes, layout),
+                 full_potential_fn(theta), ks[..., 1, :], np.zeros(C, F32))
+
+
+def amagold_update(state: MHState, grad_fns, full_potential_fn, sizes, step_size,
+                   friction=0.25, mass=None, layout="original"):
+  """solver.amagold.update (:364-424): on rejection the old state is kept with
+  the momentum negated (direction = -1, :392, :399)."""
+  old = state.integrator_state
+  prop = reversible_leapfrog_integrate(old, grad_fns, sizes, step_size, friction, mass,
+                                       layout)
+  U_new = full_potential_fn(prop.theta)
+  accept, key, _, ratio = mh_decision("amagold", state.potential, U_new, None,
+                                      prop.potential, 1.0, state.key, layout)
+  m = accept[:, None]
+  new_int = LeapfrogState(np.where(m, prop.theta, old.theta),
+                          np.where(m, prop.momentum, (F32(-1.0) * old.momentum).astype(F32)),
+                          prop.key, np.where(accept, prop.potential, old.potential))
+  return MHState(new_int, np.where(accept, U_new, state.potential).astype(F32), key,
+                 ratio), accept

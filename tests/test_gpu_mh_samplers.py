@@ -1,0 +1,212 @@
+"""SGGMC / AMAGOLD: the reversible-leapfrog kernel,
+the Metropolis-Hastings decision kernel and the two solvers against the oracle's
+restatement of integrator.py:349-560 and solver.py:301-577, plus the reference's
+own statistical acceptance tests (tests/test_alias.py:165-201)."""
+import numpy as np
+import pytest
+from scipy import stats as scpstats
+
+from oracle import data as odata
+from oracle import prng
+from oracle import sgmc as osgmc
+
+pytestmark = pytest.mark.gpu
+
+
+def _keys(C, base=0):
+  return np.stack([prng.PRNGKey(base + c) for c in range(C)])
+
+
+@pytest.mark.parametrize("sizes,with_mass", [([64], False), ([1, 4, 19], True),
+                                             ([1024], False), ([7, 2, 33], False)])
+def test_revleapfrog_kernel_matches_oracle(gpu, sizes, with_mass):
+  """Three inner steps with external gradients: theta, p, keys bit-exact (every
+  op separately rounded, oracle order); accumulated energy to 1e-5 (reduction
+  order)."""
+  from jax_sgmc_b200 import ops
+  from jax_sgmc_b200.device import DeviceArray as DA
+  rng = np.random.default_rng(3)
+  C, P, steps = 5, sum(sizes), 3
+  theta = rng.standard_normal((C, P)).astype(np.float32)
+  mass = (np.abs(rng.standard_normal(P)) + 0.5).astype(np.float32) if with_mass else None
+  grads = [(rng.standard_normal((C, P)) * 2).astype(np.float32) for _ in range(steps)]
+  eps, fr = 0.013, 0.25
+  st = osgmc.reversible_leapfrog_init(theta, _keys(C, 7), mass, sizes)
+  want = osgmc.reversible_leapfrog_integrate(
+      st, [lambda th, g=g: (None, None, g) for g in grads], sizes, eps, fr, mass)
+  # device: opening half step, then the fused kernel per inner step
+  inv_m = np.ones(P, np.float32) if mass is None else (np.float32(1) / mass)
+  half = np.float32(0.5) * np.float32(eps)
+  th0 = (st.theta + (half * (inv_m * st.momentum).astype(np.float32)).astype(np.float32)
+         ).astype(np.float32)
+  d_t, d_p = DA.from_numpy(th0), DA.from_numpy(st.momentum)
+  d_e = DA.zeros((C,))
+  kk = [DA.from_numpy(st.key), DA((C, 2), np.uint32)]
+  d_m = None if mass is None else DA.from_numpy(mass)
+  for s in range(steps):
+    ops.revleapfrog_step(d_t, d_p, DA.from_numpy(grads[s]), d_e, kk[s % 2], kk[(s + 1) % 2],
+                         sizes, eps, fr, d_m, last=(s == steps - 1))
+  assert np.array_equal(kk[steps % 2].numpy(), want.key)
+  assert np.array_equal(d_p.numpy().view(np.uint32), want.momentum.view(np.uint32))
+  assert np.array_equal(d_t.numpy().view(np.uint32), want.theta.view(np.uint32))
+  np.testing.assert_allclose(d_e.numpy(), want.potential, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("mode", ["sggmc", "amagold"])
+def test_mh_decide_matches_oracle(gpu, mode):
+  from jax_sgmc_b200 import ops
+  from jax_sgmc_b200.device import DeviceArray as DA
+  rng = np.random.default_rng(1)
+  C = 1000
+  U_old = (rng.standard_normal(C) * 5 + 100).astype(np.float32)
+  U_new = (U_old + rng.standard_normal(C) * 1.5).astype(np.float32)
+  e0 = np.abs(rng.standard_normal(C)).astype(np.float32)
+  e1 = np.abs(rng.standard_normal(C)).astype(np.float32)
+  U_new[:5] = U_old[:5]                 # log_alpha == +-(e1 - e0): both signs
+  e1[:3] = e0[:3]                       # log_alpha == 0 exactly -> always accepted
+  U_new[5] = np.nan                     # see the last assertion
+  keys = _keys(C, 50)
+  T = 1.7
+  accept, key, la, ratio = osgmc.mh_decision(mode, U_old, U_new, e0, e1, T, keys)
+  d_U = DA.from_numpy(U_old)
+  rej, rat = DA((C,), np.int32), DA((C,), np.float32)
+  k1 = DA((C, 2), np.uint32)
+  ops.mh_decide(mode, d_U, DA.from_numpy(U_new), DA.from_numpy(e0), DA.from_numpy(e1), T,
+                DA.from_numpy(keys), k1, rej, rat)
+  assert np.array_equal(rej.numpy() == 0, accept)
+  assert 0.2 < accept.mean() < 0.95
+  assert np.array_equal(k1.numpy(), key)
+  got_U = d_U.numpy()
+  want_U = np.where(accept, U_new, U_old)
+  assert np.array_equal(got_U.view(np.uint32), want_U.view(np.uint32))
+  ok = ~np.isnan(ratio)
+  np.testing.assert_allclose(rat.numpy()[ok], ratio[ok], rtol=2e-6)
+  # a NaN potential: where(la <= 0, la, 0) turns it into log_alpha = 0 (accept) in
+  # sggmc (solver.py:529), where(la > 0, 0, la) keeps the NaN (reject) in amagold (:383)
+  assert accept[:3].all() and accept[5] == (mode == "sggmc")
+
+
+def _logistic_problem(C, d, N, seed=0):
+  X, y, _ = odata.logistic_dataset(N, d, seed=seed)
+  rng = np.random.default_rng(seed + 1)
+  theta = (rng.standard_normal((C, d)) * 0.1).astype(np.float32)
+  return X, y, theta
+
+
+@pytest.mark.parametrize("kind", ["sggmc", "amagold"])
+def test_mh_solver_trajectory_matches_oracle(gpu, kind):
+  """Six MH iterations of solver.sggmc / solver.amagold driven through the
+  operator API against the oracle: identical accept/reject pattern, identical
+  keys, samples within 1e-5 (fp32 SIMT gradients, different reduction order)."""
+  from jax_sgmc_b200 import data, glm, integrator, potential, scheduler, solver
+  from jax_sgmc_b200 import ops
+  ops.set_option(ops.OPT_EXACT_UPDATE_MATH, 1)
+  try:
+    C, d, N, n, steps, iters = 6, 8, 60, 12, 3, 6
+    X, y, theta = _logistic_problem(C, d, N)
+    loader = data.DeviceNumpyDataLoader(x=X, y=y)
+    prior, lik = glm.GaussianPrior(3.0), glm.LogisticRegression()
+    pot = potential.minibatch_potential(prior, lik, strategy="vmap", path="simt")
+    full = potential.full_potential(prior, lik, strategy="vmap", path="simt")
+    random_data = data.random_reference_data(loader, 1, n)
+    full_map = data.full_reference_data(loader, 16, 16)
+    eps, fr = 0.02, (1.0 if kind == "sggmc" else 0.25)
+    if kind == "sggmc":
+      integ = integrator.obabo(pot, random_data, steps, fr)
+      init, update, get = solver.sggmc(integ, full, full_map)
+    else:
+      integ = integrator.reversible_leapfrog(pot, random_data, steps, fr)
+      init, update, get = solver.amagold(integ, full, full_map)
+    keys = _keys(C, 20)
+    state = init([{"w": t} for t in theta], key=keys)
+    sched = scheduler.schedule(step_size=np.float32(eps), temperature=np.float32(1.0),
+                               burn_in=np.float32(1.0), accept=True)
+
+    # ---- oracle side: same data key stream (PRNGKey(0) shared by the chains) ----
+    o_pot = osgmc.minibatch_potential(osgmc.Logistic(d, 0), osgmc.Prior("gaussian", 0, d, 3.0))
+    o_full_fn = osgmc.full_potential(osgmc.Logistic(d, 0), osgmc.Prior("gaussian", 0, d, 3.0))
+    ids = np.arange(int(np.ceil(N / 16)) * 16).reshape(-1, 16)
+    batches = [(X[i % N], y[i % N], (i < N).astype(np.float32)) for i in ids]
+    o_full = lambda th: o_full_fn(th, batches, N)
+    dkey = prng.PRNGKey(0)
+
+    def next_grad_fn():
+      nonlocal dkey
+      dkey, idx = odata.device_draw(dkey, n, N)
+      return lambda th, idx=idx: o_pot(th, (X[idx], y[idx]), N)
+
+    if kind == "sggmc":
+      o_state = osgmc.sggmc_init(theta, o_full, keys)
+    else:
+      o_state = osgmc.amagold_init(theta, o_full, keys, sizes=[d])
+    np.testing.assert_allclose(state.potential.numpy(), o_state.potential, rtol=1e-5)
+    pattern = []
+    for it in range(iters):
+      state, stats = update(state, sched)
+      if kind == "sggmc":
+        pairs = [(next_grad_fn(), next_grad_fn()) for _ in range(steps)]
+        o_state, acc = osgmc.sggmc_update(o_state, pairs, o_full, [d], eps, 1.0, fr)
+      else:
+        fns = [next_grad_fn() for _ in range(steps)]
+        o_state, acc = osgmc.amagold_update(o_state, fns, o_full, [d], eps, fr)
+      pattern.append(acc)
+      assert np.array_equal(state.reject.numpy() == 0, acc), f"iteration {it}"
+      assert np.array_equal(state.key.current.numpy(), o_state.key)
+      got = get(state)["variables"].flat.numpy()
+      np.testing.assert_allclose(got, o_state.integrator_state.theta, rtol=1e-5, atol=1e-6)
+      np.testing.assert_allclose(state.integrator_state.momentum.flat.numpy(),
+                                 o_state.integrator_state.momentum, rtol=1e-5, atol=1e-6)
+      np.testing.assert_allclose(state.potential.numpy(), o_state.potential, rtol=1e-5)
+      np.testing.assert_allclose(stats["acceptance_ratio"].numpy(),
+                                 o_state.acceptance_ratio, rtol=1e-3, atol=1e-6)
+    pattern = np.array(pattern)
+    assert pattern.any() and not pattern.all(), "want both accepts and rejects in the test"
+  finally:
+    ops.set_option(ops.OPT_EXACT_UPDATE_MATH, 0)
+
+
+def _ks_problem():
+  """tests/test_alias.py:32-65 (see test_gpu_api._ks_problem)."""
+  from jax_sgmc_b200 import data, glm, potential
+  x = 0.5 * prng.normal(prng.PRNGKey(11), (100,))
+  loader = data.DeviceNumpyDataLoader(x=np.zeros((2, 1), np.float32),
+                                      y=np.zeros((2,), np.float32))
+  prior, lik = glm.GaussianPrior(0.5), glm.LogisticRegression()
+  pot = potential.minibatch_potential(prior, lik, strategy="vmap")
+  full = potential.full_potential(prior, lik, strategy="vmap")
+  init = {"w": np.array([x[0]], np.float32)}
+
+  def check(samples):
+    st = scpstats.kstest(np.ravel(samples), x)
+    assert st.pvalue > 0.05, f"KS p-value {st.pvalue}"
+
+  return loader, pot, full, init, check
+
+
+def test_ks_amagold_and_sggmc(gpu):
+  """tests/test_alias.py:165-201: both MH samplers reproduce N(0, 0.5^2)."""
+  from jax_sgmc_b200 import alias
+  loader, pot, full, init, check = _ks_problem()
+  for make in (alias.amagold, alias.sggmc):
+    run = make(pot, full, loader, cache_size=1, batch_size=1, first_step_size=0.5,
+               last_step_size=0.1, burn_in=100, progress_bar=False)
+    res = run(init, iterations=400)[0]
+    assert res["sample_count"] == 300
+    assert {"acceptance_ratio", "step_size"} <= set(res["samples"].keys())
+    check(res["samples"]["variables"]["w"][::3])      # thin: successive MH samples correlate
+
+
+def test_adaptive_step_size_through_sggmc(gpu):
+  """alias.sggmc(adaptive_step_size=True): the dual-averaging schedule moves the
+  step size during burn in and freezes it afterwards (scheduler.py:376-444)."""
+  from jax_sgmc_b200 import alias
+  loader, pot, full, init, check = _ks_problem()
+  run = alias.sggmc(pot, full, loader, cache_size=1, batch_size=1, first_step_size=0.05,
+                    adaptive_step_size=True, burn_in=60, target_acceptance_rate=0.6,
+                    progress_bar=False)
+  res = run(init, iterations=100)[0]
+  eps = np.ravel(res["samples"]["step_size"])
+  assert res["sample_count"] == 40
+  assert np.all(eps == eps[0]) and eps[0] != np.float32(0.05)
+  ratio = np.ravel(res["samples"]["acceptance_ratio"])
+  assert np.all((ratio >= 0) & (ratio <= 1))

@@ -114,3 +114,45 @@ def test_potential_rejects_unknown_callables_and_strategies():
     potential.full_potential(pr, lk, strategy="pmap")            # potential.py:254
   with pytest.raises(NotImplementedError):
     lk({}, {})
+
+
+def test_adaptive_step_size_follows_the_dual_averaging_formulas():
+  """scheduler.py:376-444 evaluated directly in f64 next to the package."""
+  from jax_sgmc_b200 import scheduler
+  burn_in, eps0, t0, kappa, gamma, target = 8, 0.05, 10, 0.75, 0.05, 0.25
+  sch = scheduler.adaptive_step_size(burn_in=burn_in, initial_step_size=eps0,
+                                     stabilization_constant=t0, decay_constant=kappa,
+                                     speed_constant=gamma, target_acceptance_rate=target)
+  st = sch.init(100)
+  x_bar, h_bar, mu = np.log(eps0), 0.0, np.log(10 * eps0)
+  rng = np.random.default_rng(0)
+  assert np.isclose(sch.get(st, 0), eps0, rtol=1e-6)
+  for it in range(12):
+    acc = float(rng.random())
+    st = sch.update(st, it, acceptance_ratio=np.array([acc], np.float32))
+    m = it + 1
+    h_bar = h_bar * (1 - 1 / (m + t0)) + (target - acc) / (m + t0)
+    x = mu - np.sqrt(m) / gamma * h_bar
+    lr = m ** (-kappa)
+    if it < burn_in:
+      x_bar = x_bar * (1 - lr) + lr * x
+    assert np.isclose(sch.get(st, it), np.exp(x_bar), rtol=2e-5), it
+
+
+def test_oracle_reversible_leapfrog_is_plain_leapfrog_without_friction():
+  """integrator.py:395-466 with friction 0: no noise, no decay, and the
+  accumulated energy equals KE_old - KE_new exactly as AMAGOLD's acceptance
+  (solver.py:381) needs: log_alpha = H_old - H_new."""
+  from oracle import sgmc as osgmc
+  rng = np.random.default_rng(0)
+  C, P, steps, eps = 3, 6, 5, 0.05
+  theta = rng.standard_normal((C, P)).astype(np.float32)
+  st = osgmc.reversible_leapfrog_init(theta, sizes=[P])
+  grad = lambda th: (None, None, th.astype(np.float32))        # U = |theta|^2 / 2
+  out = osgmc.reversible_leapfrog_integrate(st, [grad] * steps, [P], eps, friction=0.0)
+  ke = lambda p: 0.5 * np.sum(p.astype(np.float64) ** 2, axis=1)
+  np.testing.assert_allclose(out.potential, ke(st.momentum) - ke(out.momentum), atol=2e-5)
+  H = lambda th, p: 0.5 * np.sum(th.astype(np.float64) ** 2, axis=1) + ke(p)
+  assert np.all(np.abs(H(out.theta, out.momentum) - H(st.theta, st.momentum)) < 1e-2)
+  # the momentum of all chains started from split(PRNGKey(0))[1] noise: same rows
+  assert np.array_equal(st.momentum[0], st.momentum[1])
