@@ -166,8 +166,8 @@ __host__ __device__ constexpr uint32_t make_idesc(int ab_format, int M, int N) {
 // ---------------------------------------------------------------------------
 // Epilogues
 // ---------------------------------------------------------------------------
-// Per-row partial likelihood statistics of one CTA tile (combined by
-// k_glm_finalize_parts): {count, mean, M2, masked_sum}.
+// Per-row partial likelihood statistics of one CTA tile (combined by the
+// last-arriver block of the link epilogue): {count, mean, M2, masked_sum}.
 constexpr int kStatFields = 4;
 
 struct TcLinkEpi {      // GEMM1: z -> ell statistics, R = cot*mask*dl/dz as fp16 hi/lo
@@ -778,45 +778,6 @@ __device__ __forceinline__ float pow2_scale_for(float absmax) {
   return ldexpf(1.0f, 13 - e);
 }
 
-// One warp per chain row: row absmax -> power-of-two scale -> fp16 hi/lo split
-// (SPLIT) or plain bf16 conversion; also sum(theta^2) over the gaussian-prior
-// range of the row (for the prior value).  Theta row = theta[c*P + w_off ..+d).
-template <bool SPLIT>
-__global__ void k_theta_prepare(const float* __restrict__ theta, int64_t P, int w_off, int d,
-                                int C, int prior_lo, int prior_hi, void* __restrict__ out_hi,
-                                __half* __restrict__ out_lo, float* __restrict__ row_scale,
-                                float* __restrict__ row_sumsq) {
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (warp >= C) return;
-  const float* src = theta + (int64_t)warp * P + w_off;
-  float m = 0.f, sq = 0.f;
-  for (int j = lane; j < d; j += 32) {
-    const float x = src[j];
-    m = fmaxf(m, fabsf(x));
-    if (w_off + j >= prior_lo && w_off + j < prior_hi) sq = fmaf(x, x, sq);
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-    sq += __shfl_xor_sync(0xffffffffu, sq, o);
-  }
-  const float s = SPLIT ? pow2_scale_for(m) : 1.0f;
-  if (lane == 0) {
-    row_scale[warp] = s;
-    row_sumsq[warp] = sq;
-  }
-  for (int j = lane; j < d; j += 32) {
-    const float x = src[j] * s;
-    if (SPLIT) {
-      const __half h = __float2half_rn(x);
-      reinterpret_cast<__half*>(out_hi)[(int64_t)warp * d + j] = h;
-      out_lo[(int64_t)warp * d + j] = __float2half_rn(x - __half2float(h));
-    } else {
-      reinterpret_cast<__nv_bfloat16*>(out_hi)[(int64_t)warp * d + j] = __float2bfloat16_rn(x);
-    }
-  }
-}
-
 // |X[idx]| max over the minibatch: one warp per gathered row.
 __global__ void k_absmax_gather(const float* __restrict__ X, const int32_t* __restrict__ idx,
                                 int n, int d, uint32_t* __restrict__ out_bits) {
@@ -830,56 +791,10 @@ __global__ void k_absmax_gather(const float* __restrict__ X, const int32_t* __re
   if (lane == 0) atomicMax(out_bits, __float_as_uint(m));  // m >= 0: uint order == float order
 }
 
-// Gather minibatch rows, scale, split, and write both Xb [n][d] and its
-// transpose XbT [d][n] (32x32 tiles through shared memory).
-template <bool SPLIT>
-__global__ void k_x_prepare(const float* __restrict__ X, const int32_t* __restrict__ idx, int n,
-                            int d, const uint32_t* __restrict__ absmax_bits, float static_absmax,
-                            void* __restrict__ xb_hi, __half* __restrict__ xb_lo,
-                            void* __restrict__ xt_hi, __half* __restrict__ xt_lo,
-                            float* __restrict__ scale_out) {
-  __shared__ float tile[32][33];
-  float s = 1.0f;
-  if (SPLIT)
-    s = pow2_scale_for(static_absmax > 0.f ? static_absmax : __uint_as_float(*absmax_bits));
-  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 && threadIdx.y == 0) *scale_out = s;
-  const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
-  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
-    const int r = r0 + i, c = c0 + threadIdx.x;
-    float v = 0.f;
-    if (r < n && c < d) {
-      const int64_t row = idx ? idx[r] : r;
-      v = X[row * d + c] * s;
-      if (SPLIT) {
-        const __half h = __float2half_rn(v);
-        reinterpret_cast<__half*>(xb_hi)[(int64_t)r * d + c] = h;
-        xb_lo[(int64_t)r * d + c] = __float2half_rn(v - __half2float(h));
-      } else {
-        reinterpret_cast<__nv_bfloat16*>(xb_hi)[(int64_t)r * d + c] = __float2bfloat16_rn(v);
-      }
-    }
-    tile[i][threadIdx.x] = v;
-  }
-  __syncthreads();
-  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
-    const int c = c0 + i, r = r0 + threadIdx.x;      // transposed: row = feature c
-    if (c < d && r < n) {
-      const float v = tile[threadIdx.x][i];
-      if (SPLIT) {
-        const __half h = __float2half_rn(v);
-        reinterpret_cast<__half*>(xt_hi)[(int64_t)c * n + r] = h;
-        xt_lo[(int64_t)c * n + r] = __float2half_rn(v - __half2float(h));
-      } else {
-        reinterpret_cast<__nv_bfloat16*>(xt_hi)[(int64_t)c * n + r] = __float2bfloat16_rn(v);
-      }
-    }
-  }
-}
-
 // Both operand preparations in ONE launch (they are independent): blocks
 // [0, theta_blocks) convert Theta rows (one warp per chain row, 128-bit loads,
 // 64-bit packed stores), the remaining blocks gather / split / transpose the
-// minibatch in 32x32 tiles.  Also clears the per-row-block tile counters used by
+// minibatch in 64x64 tiles.  Also clears the per-row-block tile counters used by
 // GEMM1's last-arriver finalisation.
 struct PrepareArgs {
   const float* theta; int64_t P; int w_off, d, C, prior_lo, prior_hi;
@@ -1065,34 +980,6 @@ __global__ void __launch_bounds__(256) k_prepare_all(const PrepareArgs a) {
     if (c < d && r < n)
       store2(a.xt_hi, a.xt_lo, (int64_t)c * n + r, tile[2 * tx][cc], tile[2 * tx + 1][cc]);
   }
-}
-
-// One thread per chain: combine the per-tile likelihood statistics into
-// U = (L - prior)/T (potential.py:183-185, :210) and var(ell) (integrator.py:880).
-__global__ void k_glm_finalize_parts(const float* __restrict__ stats, int parts,
-                                     const float* __restrict__ row_sumsq, const GlmArgs a) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= a.C) return;
-  float n_t = 0.f, mean_t = 0.f, m2_t = 0.f, sm_t = 0.f;
-  for (int g = 0; g < parts; ++g) {
-    const float* st = stats + ((int64_t)c * parts + g) * kStatFields;
-    const float nb = st[0];
-    if (nb > 0.f) {
-      const float nn = n_t + nb, delta = st[1] - mean_t;
-      mean_t += delta * (nb / nn);
-      m2_t += st[2] + delta * delta * (n_t * nb / nn);
-      n_t = nn;
-    }
-    sm_t += st[3];
-  }
-  float L;
-  if (a.mask) L = (-(float)a.N / (float)a.n) * sm_t;
-  else L = -(float)a.N * mean_t;
-  float prior = 0.f;
-  if (a.spec.prior == kPriorGaussian)
-    prior = -0.5f * (1.0f / (a.spec.prior_scale * a.spec.prior_scale)) * row_sumsq[c];
-  a.potential[c] = (L - prior) / a.spec.temperature;
-  if (a.variance) a.variance[c] = m2_t / (float)a.n;
 }
 
 // ---------------------------------------------------------------------------
@@ -1284,7 +1171,7 @@ int glm_tc(cudaStream_t stream, const GlmArgs& a, int path) {
     else launch_pdl(k_prepare_all<false>, dim3(grid), dim3(256), 0, stream, pa);
     if (post_launch("k_prepare_all")) return 1;
   }
-  // The Xb scale is computed on the device (k_x_prepare) and read by the
+  // The Xb scale is computed on the device (k_prepare_all) and read by the
   // epilogues through a device scalar, so the whole op stays sync-free.
   // R scale: |R| <= |cot| for the logistic family (|dl/dz| <= 1, mask in [0,1]).
   float r_scale = 1.0f;
