@@ -29,9 +29,14 @@ DEFAULT_PATH = os.environ.get("SGMC_GLM_PATH", "auto")
 def _select_path(path: str, spec, n_chains: int, n: int) -> str:
   if path != "auto":
     return path
+  # The TMEM accumulator truncates (~0.5 ulp bias per 16-wide k-step, DESIGN.md
+  # section 4.2): the 1e-5 parity bound holds up to K ~ 2048 in GEMM1 (K = d) and
+  # ~4096 in GEMM2 (K = n); larger contractions stay on the fp32 SIMT path unless
+  # the caller asks for a tensor-core path explicitly.
   tc_ok = (spec.family == ops.FAMILY["logistic"] and spec.aux_off < 0
-           and spec.d % 8 == 0 and n % 8 == 0 and spec.d >= 64 and n >= 64
-           and n_chains >= 64 and spec.prior != ops.PRIOR["inv_sigma"])
+           and spec.d % 8 == 0 and n % 8 == 0 and 64 <= spec.d <= 2048
+           and 64 <= n <= 4096 and n_chains >= 64
+           and spec.prior != ops.PRIOR["inv_sigma"])
   return "tc_parity" if tc_ok else "simt"
 
 

@@ -166,3 +166,37 @@ def test_host_loader_gives_each_chain_its_own_stream(gpu):
     idx = odata.HostDraws(50, 5, seed=c).draw()
     wU, _, _ = opot(np.zeros((1, 8), np.float32), (X[idx], y[idx]), 50)
     np.testing.assert_allclose(U[c], wU[0], rtol=1e-5)
+
+
+@pytest.mark.parametrize("direct", [True, False])
+def test_sample_ring_equals_device_buffer(gpu, direct, monkeypatch):
+  """io.save through the host ring (kept samples stream to pinned host memory
+  on a copy stream while the chains keep stepping) returns
+  exactly what the all-in-HBM buffer returns."""
+  from jax_sgmc_b200 import adaption, data, glm, integrator, io, potential, scheduler, solver
+  from jax_sgmc_b200.tree_util import ChainTree
+  monkeypatch.setattr(io, "PINNED_RESULT_LIMIT", (24 << 30) if direct else 0)
+  X, y, _ = odata.logistic_dataset(500, 16, seed=2)
+  loader = data.DeviceNumpyDataLoader(x=X, y=y)
+  pot = potential.minibatch_potential(glm.GaussianPrior(5.0), glm.LogisticRegression(),
+                                      strategy="vmap", path="simt")
+  init = [{"w": np.full(16, 0.01 * c, np.float32)} for c in range(7)]
+
+  def run(collector):
+    integ = integrator.langevin_diffusion(pot, data.random_reference_data(loader, 1, 32),
+                                          adaption.rms_prop())
+    sched = scheduler.init_scheduler(
+        step_size=scheduler.polynomial_step_size_first_last(first=1e-2, last=1e-3),
+        burn_in=scheduler.initial_burn_in(10), progress_bar=False)
+    slv = solver.sgmc(integ)
+    mcmc = solver.mcmc(slv, sched, saving=io.save(collector))
+    return mcmc(slv[0](ChainTree.from_trees(init)), iterations=60)
+
+  a = run(io.MemoryCollector(stream_to_host=False))
+  b = run(io.MemoryCollector(stream_to_host=True))
+  assert len(a) == len(b) == 7 and a[0]["sample_count"] == b[0]["sample_count"] == 50
+  for ra, rb in zip(a, b):
+    assert np.array_equal(ra["samples"]["variables"]["w"], rb["samples"]["variables"]["w"])
+    assert np.array_equal(ra["samples"]["likelihood"], rb["samples"]["likelihood"])
+  assert not np.array_equal(a[0]["samples"]["variables"]["w"][0],
+                            a[0]["samples"]["variables"]["w"][-1])

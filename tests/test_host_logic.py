@@ -156,3 +156,20 @@ def test_oracle_reversible_leapfrog_is_plain_leapfrog_without_friction():
   assert np.all(np.abs(H(out.theta, out.momentum) - H(st.theta, st.momentum)) < 1e-2)
   # the momentum of all chains started from split(PRNGKey(0))[1] noise: same rows
   assert np.array_equal(st.momentum[0], st.momentum[1])
+
+
+def test_auto_path_selection_keeps_the_parity_bound():
+  """potential._select_path: tensor cores only for the logistic family without
+  bias, 8-aligned shapes, enough chains, and contraction lengths for which the
+  truncating TMEM accumulator stays inside the 1e-5 parity tolerance."""
+  from jax_sgmc_b200 import ops
+  from jax_sgmc_b200.potential import _select_path
+  spec = lambda d, **kw: ops.glm_spec("logistic", d, 0, prior="gaussian", prior_off=0,
+                                      prior_size=d, prior_scale=1.0, **kw)
+  assert _select_path("auto", spec(1024), 4096, 1024) == "tc_parity"
+  assert _select_path("auto", spec(4096), 4096, 1024) == "simt"       # K = d too long
+  assert _select_path("auto", spec(1024), 4096, 8192) == "simt"       # K = n too long
+  assert _select_path("auto", spec(1024), 32, 1024) == "simt"         # too few chains
+  assert _select_path("auto", spec(100), 4096, 1024) == "simt"        # d % 8
+  assert _select_path("auto", ops.glm_spec("gaussian", 64, 1, aux_off=0), 4096, 1024) == "simt"
+  assert _select_path("tc_throughput", spec(4096), 8, 8) == "tc_throughput"   # explicit wins
