@@ -87,7 +87,7 @@ PROTOTYPES = {
                                 _vp, _sz, _int],
     "sgmc_glm_sgld_step": [_vp, C.POINTER(GlmSpec), _vp, _vp, _i64, _i64, _vp, _vp, _vp,
                            _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _f32, _f32, _f32,
-                           _f32, _vp, _sz, _int, _int, _int],
+                           _f32, _vp, _sz, _int, _int, _int, _vp, _vp, C.POINTER(_i64), _int],
     "sgmc_revleapfrog_step": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, C.POINTER(_i64), _int,
                               _f32, _f32, _vp, _int, _int],
     "sgmc_mh_decide": [_vp, _int, _vp, _vp, _vp, _vp, _f32, _vp, _vp, _vp, _vp, _i64, _int],
@@ -96,6 +96,9 @@ PROTOTYPES = {
     "sgmc_swap_rows": [_vp, _vp, _vp, _vp, _i64, _i64],
     "sgmc_resgld_ladder_step": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _int,
                                 _i64, _i64, _int, _int, _vp, _vp, _int],
+    "sgmc_resgld_sharded_exchange": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp, _vp, _vp,
+                                     _vp, _vp, _vp, _vp, _vp, _int, _i64, _i64, _int, _int,
+                                     _vp, _vp, _int],
     "sgmc_nccl_unique_id": [_vp],
     "sgmc_nccl_init": [C.POINTER(_vp), _vp, _int, _int],
     "sgmc_nccl_destroy": [_vp],

@@ -297,12 +297,20 @@ int sgmc_glm_sgld_step(void* stream, const sgmc_glm_spec* spec, float* theta, fl
                        float* grad, const uint32_t* keys_in, uint32_t* keys_out,
                        float step_size, float temperature, float alpha, float lmbd,
                        void* workspace, size_t workspace_bytes, int path, int prng_layout,
-                       int write_grad) {
+                       int write_grad, const float* temp_per_chain, void* wait_event,
+                       const int64_t* leaf_sizes, int n_leaves) {
   SGMC_REQUIRE(grad && keys_in && keys_out, "null argument");
+  const int64_t whole = P;
+  if (leaf_sizes == nullptr) {       // the sample is one leaf
+    leaf_sizes = &whole;
+    n_leaves = 1;
+  }
   SGMC_REQUIRE(keys_in != keys_out, "keys_out must not alias keys_in");
   bool applied = false;
   FusedSgld fu{};
-  fu.requested = true;
+  // per-chain temperatures / an event to wait for before the update: only the
+  // plain kernel sequence supports them
+  fu.requested = temp_per_chain == nullptr && wait_event == nullptr && n_leaves == 1;
   fu.theta_rw = theta; fu.v = v; fu.keys_in = keys_in; fu.keys_out = keys_out;
   fu.step_size = step_size; fu.temperature = temperature; fu.alpha = alpha; fu.lmbd = lmbd;
   fu.layout = prng_layout; fu.applied = &applied; fu.write_grad = write_grad != 0;
@@ -311,13 +319,17 @@ int sgmc_glm_sgld_step(void* stream, const sgmc_glm_spec* spec, float* theta, fl
                            workspace_bytes, path, fu))
     return e;
   if (applied) return 0;
-  // not fusable for these shapes / options: the stand-alone fused update
-  const int64_t leaf = P;
+  if (wait_event != nullptr &&
+      check_cuda(cudaStreamWaitEvent((cudaStream_t)stream, (cudaEvent_t)wait_event, 0),
+                 "cudaStreamWaitEvent"))
+    return 1;
+  // the stand-alone fused noise + update kernel
   if (v)
-    return sgmc_sgld_rms_update(stream, theta, v, grad, keys_in, keys_out, n_chains, &leaf, 1,
-                                step_size, temperature, nullptr, alpha, lmbd, prng_layout);
-  return sgmc_sgld_update(stream, theta, grad, keys_in, keys_out, n_chains, &leaf, 1, step_size,
-                          temperature, nullptr, prng_layout);
+    return sgmc_sgld_rms_update(stream, theta, v, grad, keys_in, keys_out, n_chains, leaf_sizes,
+                                n_leaves, step_size, temperature, temp_per_chain, alpha, lmbd,
+                                prng_layout);
+  return sgmc_sgld_update(stream, theta, grad, keys_in, keys_out, n_chains, leaf_sizes, n_leaves,
+                          step_size, temperature, temp_per_chain, prng_layout);
 }
 
 }  // extern "C"

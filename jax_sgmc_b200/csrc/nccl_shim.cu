@@ -92,6 +92,49 @@ int sgmc_nccl_allgather(void* comm, void* stream, const void* send, void* recv,
                                     (cudaStream_t)stream), "ncclAllGather");
 }
 
+// One reSGLD exchange of the sharded ladder in a single call: snapshot of the
+// local (U, var) rows on the sampling stream, all-gather + decision kernels on
+// the exchange stream (or everything on the sampling stream when x_stream is
+// NULL).  comm == NULL: single rank, the gather is a device copy.
+int sgmc_resgld_sharded_exchange(void* comm, void* main_stream, void* x_stream,
+                                 void* ready_event, void* done_event, const float* uv,
+                                 float* uv_send, size_t uv_bytes, float* gathered,
+                                 int32_t* holder, float* ssq, const float* F,
+                                 const float* temps, const uint32_t* keys_in,
+                                 uint32_t* keys_out, int32_t* exchange, int n_replicas,
+                                 int64_t n_systems, int64_t step, int first_local_replica,
+                                 int n_local_replicas, float* temp_per_chain,
+                                 int32_t* temp_index, int prng_layout) {
+  cudaStream_t ms = (cudaStream_t)main_stream, xs = (cudaStream_t)x_stream;
+  const float* src = uv;
+  cudaStream_t s = ms;
+  if (xs != nullptr) {
+    SGMC_REQUIRE(ready_event && done_event && uv_send, "overlapped exchange needs events");
+    // the next potential overwrites (U, var): keep a copy for the exchange stream
+    if (check_cuda(cudaMemcpyAsync(uv_send, uv, uv_bytes, cudaMemcpyDeviceToDevice, ms),
+                   "snapshot")) return 1;
+    if (check_cuda(cudaEventRecord((cudaEvent_t)ready_event, ms), "cudaEventRecord")) return 1;
+    if (check_cuda(cudaStreamWaitEvent(xs, (cudaEvent_t)ready_event, 0), "cudaStreamWaitEvent"))
+      return 1;
+    src = uv_send;
+    s = xs;
+  }
+  if (comm != nullptr) {
+    if (int e = sgmc_nccl_allgather(comm, s, src, gathered, uv_bytes)) return e;
+  } else if (check_cuda(cudaMemcpyAsync(gathered, src, uv_bytes, cudaMemcpyDeviceToDevice, s),
+                        "gather copy")) {
+    return 1;
+  }
+  if (int e = sgmc_resgld_ladder_step(s, gathered, holder, ssq, F, temps, keys_in, keys_out,
+                                      exchange, n_replicas, n_systems, step,
+                                      first_local_replica, n_local_replicas, temp_per_chain,
+                                      temp_index, prng_layout))
+    return e;
+  if (xs != nullptr)
+    return check_cuda(cudaEventRecord((cudaEvent_t)done_event, xs), "cudaEventRecord");
+  return 0;
+}
+
 int sgmc_nccl_allreduce_sum_f32(void* comm, void* stream, const float* send,
                                 float* recv, size_t count) {
   SGMC_REQUIRE(api().ok, "libnccl.so.2 not found");

@@ -36,9 +36,9 @@ class LocalCommunicator:
   """world_size 1: the all-gather is the identity (no library involved)."""
   rank, world = 0, 1
 
-  def allgather(self, send, recv):
+  def allgather(self, send, recv, stream=None):
     if isinstance(send, DeviceArray):
-      recv.copy_from(send)
+      recv.copy_from(send, stream)
     else:
       recv[...] = np.asarray(send).reshape(recv.shape)
     return recv
@@ -58,8 +58,9 @@ class GlooCommunicator:
       dist.init_process_group("gloo")
     self.rank, self.world = dist.get_rank(), dist.get_world_size()
 
-  def allgather(self, send: np.ndarray, recv: np.ndarray) -> np.ndarray:
+  def allgather(self, send: np.ndarray, recv: np.ndarray, stream=None) -> np.ndarray:
     import torch
+    del stream
     t = torch.from_numpy(np.ascontiguousarray(send))
     outs = [torch.empty_like(t) for _ in range(self.world)]
     self._dist.all_gather(outs, t)

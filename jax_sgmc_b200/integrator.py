@@ -180,26 +180,40 @@ def langevin_diffusion(potential_fn, batch_fn, adaption=None
             "likelihood": Negated(state.potential),
             "model_state": state.model_state}
 
-  def update_fn(state: LangevinState, parameters, temp_per_chain=None) -> LangevinState:
-    """integrator.py:860-922."""
+  def update_fn(state: LangevinState, parameters, temp_per_chain=None,
+                pre_update_hook: Callable = None) -> LangevinState:
+    """integrator.py:860-922.  ``pre_update_hook`` (a callable with an ``event``
+    attribute) orders the update launch after that event -- the sharded reSGLD
+    puts its label exchange there."""
     theta = state.latent_variables
     data_state, mini_batch = batch_get(state.data_state, information=True)   # :872
     grad_buf = scratch.get(id(theta.flat))
     if grad_buf is None:
       grad_buf = scratch[id(theta.flat)] = DeviceArray(theta.flat.shape, np.float32)
-    (_, (_, new_model_state)), grad = stochastic_gradient(                 # :875-880
-        theta, mini_batch, state=state.model_state, likelihoods=True,
-        grad_out=grad_buf, U_out=state.potential, var_out=state.variance)
     v = alpha = lmbd = None
     if adaption is not None:
       v, alpha, lmbd = state.adapt_state.v.flat, state.adapt_state.alpha, \
           state.adapt_state.lmbd
-    # key, split = split(key); noise; scaled gradient / noise; adaption; theta' (:871-912)
-    ops.sgld_update(theta.flat, grad.flat, state.key.current, state.key.next,
-                    theta.sizes, float(parameters.step_size),
-                    float(parameters.temperature), temp_per_chain=temp_per_chain,
-                    v=v, alpha=alpha if alpha is not None else 0.9,
-                    lmbd=lmbd if lmbd is not None else 1e-5)
+    new_model_state = state.model_state
+    # one C call for value_and_grad + update when all chains share the minibatch
+    if not potential_fn.sgld_step(
+        theta, mini_batch, state.key.current, state.key.next,
+        float(parameters.step_size), float(parameters.temperature), v=v,
+        alpha=alpha if alpha is not None else 0.9, lmbd=lmbd if lmbd is not None else 1e-5,
+        temp_per_chain=temp_per_chain,
+        wait_event=getattr(pre_update_hook, "event", None), grad_out=grad_buf,
+        U_out=state.potential, var_out=state.variance):
+      (_, (_, new_model_state)), grad = stochastic_gradient(               # :875-880
+          theta, mini_batch, state=state.model_state, likelihoods=True,
+          grad_out=grad_buf, U_out=state.potential, var_out=state.variance)
+      if pre_update_hook is not None:
+        pre_update_hook()
+      # key, split = split(key); noise; scaled gradient / noise; adaption; theta' (:871-912)
+      ops.sgld_update(theta.flat, grad.flat, state.key.current, state.key.next,
+                      theta.sizes, float(parameters.step_size),
+                      float(parameters.temperature), temp_per_chain=temp_per_chain,
+                      v=v, alpha=alpha if alpha is not None else 0.9,
+                      lmbd=lmbd if lmbd is not None else 1e-5)
     state.key.flip()
     return LangevinState(key=state.key, latent_variables=theta,
                          adapt_state=state.adapt_state, data_state=data_state,

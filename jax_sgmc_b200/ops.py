@@ -248,7 +248,8 @@ def glm_potential_grad(spec, theta, X, y, idx, observation_count, potential,
 def glm_sgld_step(spec, theta, X, y, idx, observation_count, potential, variance,
                   grad, keys_in, keys_out, step_size, temperature=1.0, v=None,
                   alpha=0.9, lmbd=1e-5, mask=None, workspace=None, path=0,
-                  batch_size=None, layout=0, write_grad=True, stream=None):
+                  batch_size=None, layout=0, write_grad=True, temp_per_chain=None,
+                  wait_event=None, leaf_sizes=None, stream=None):
   """One langevin_diffusion step on the GLM potential: potential / variance /
   gradient at the current theta, then the SGLD (v None) or pSGLD update in
   place -- inside the gradient GEMM's epilogue when the shapes allow."""
@@ -262,7 +263,10 @@ def glm_sgld_step(spec, theta, X, y, idx, observation_count, potential, variance
             vp(potential), vp(variance), vp(grad), vp(keys_in), vp(keys_out),
             float(step_size), float(temperature), float(alpha), float(lmbd),
             vp(workspace), workspace.nbytes, PATH[path], _layout(layout),
-            1 if write_grad else 0)
+            1 if write_grad else 0, vp(temp_per_chain),
+            None if wait_event is None else wait_event.handle,
+            None if leaf_sizes is None else i64_array(leaf_sizes),
+            0 if leaf_sizes is None else len(leaf_sizes))
   return workspace
 
 
@@ -301,6 +305,20 @@ def resgld_ladder_step(gathered, holder, ssq, F, temps, keys_in, keys_out, excha
             vp(F), vp(temps), vp(keys_in), vp(keys_out), vp(exchange),
             int(n_replicas), int(n_systems), int(step), int(first_local),
             int(n_local), vp(temp_per_chain), vp(temp_index), _layout(layout))
+
+
+def resgld_sharded_exchange(comm_handle, main_stream, x_stream, ready, done, uv, uv_send,
+                            gathered, holder, ssq, F, temps, keys_in, keys_out, exchange,
+                            n_replicas, n_systems, step, first_local, n_local,
+                            temp_per_chain, temp_index, layout=0):
+  """All-gather + ladder decision in one C call; see sgmc_resgld_sharded_exchange."""
+  _lib.call("sgmc_resgld_sharded_exchange", comm_handle, main_stream.handle,
+            None if x_stream is None else x_stream.handle,
+            None if ready is None else ready.handle, None if done is None else done.handle,
+            vp(uv), vp(uv_send), uv.nbytes, vp(gathered), vp(holder), vp(ssq), vp(F),
+            vp(temps), vp(keys_in), vp(keys_out), vp(exchange), int(n_replicas),
+            int(n_systems), int(step), int(first_local), int(n_local), vp(temp_per_chain),
+            vp(temp_index), _layout(layout))
 
 
 def swap_rows(a: DeviceArray, b: DeviceArray, exchange: DeviceArray, stream=None):

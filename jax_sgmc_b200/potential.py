@@ -107,6 +107,36 @@ class _PotentialFn:
       return U, (ell, state)
     return U, state
 
+  def sgld_step(self, sample: ChainTree, reference_data, keys_in, keys_out, step_size,
+                temperature, v=None, alpha=0.9, lmbd=1e-5, temp_per_chain=None,
+                wait_event=None, grad_out=None, U_out=None, var_out=None) -> bool:
+    """The whole langevin_diffusion.update_fn body (integrator.py:860-922) --
+    value_and_grad of this potential on the minibatch, then the SGLD / pSGLD
+    update of ``sample`` in place -- as ONE C call (sgmc_glm_sgld_step).
+    Returns False (nothing done) when the chains do not share the minibatch."""
+    batch, info = reference_data
+    if batch.per_chain or batch.mask is not None:
+      return False
+    spec = glm.resolve(self.likelihood, self.prior, sample, self.temperature,
+                       batch.loader.absmax(self.likelihood.x))
+    C, P, n = sample.n_chains, sample.n_params, batch.n
+    path = _select_path(self.path, spec, C, n)
+    key = (C, P, n, path)
+    buf = self._buffers.get(key)
+    if buf is None:
+      buf = {"U": DeviceArray((C,), np.float32), "var": DeviceArray((C,), np.float32),
+             "ws": ops.glm_workspace(C, n, spec.d, path), "ell": None}
+      self._buffers[key] = buf
+    ops.glm_sgld_step(
+        spec, sample.flat, batch.loader.device_data[self.likelihood.x],
+        batch.loader.device_data[self.likelihood.y], batch.idx,
+        int(info.observation_count), U_out if U_out is not None else buf["U"],
+        var_out if var_out is not None else buf["var"], grad_out, keys_in, keys_out,
+        step_size, temperature, v=v, alpha=alpha, lmbd=lmbd, workspace=buf["ws"],
+        path=path, batch_size=n, temp_per_chain=temp_per_chain, wait_event=wait_event,
+        leaf_sizes=sample.sizes)
+    return True
+
   def value_and_grad(self, sample: ChainTree, reference_data, state: Any = None,
                      mask=None, likelihoods: bool = False,
                      grad_out: Optional[DeviceArray] = None,

@@ -10,6 +10,12 @@ Replicas exchange temperature labels, not parameters, so nothing else crosses
 NVLink; the reference exchanges whole chain states (solver.py:287-291), which
 is the same Markov chain up to relabelling.  For R = 2 the decisions, keys and
 cold-chain samples reproduce the reference (tests/test_gpu_tempering.py).
+
+``overlap_exchange=True`` moves the all-gather and the decision kernels to a
+second stream: the swap of step k only has to be known when step k+1 *updates*
+(the temperature enters the noise scale, not the potential), so it runs
+concurrently with step k+1's minibatch draw and potential / gradient kernels
+and the exchange latency disappears from the step.  Same results bit for bit.
 """
 from __future__ import annotations
 
@@ -18,17 +24,47 @@ from typing import Any, Dict, List, Sequence
 import numpy as np
 
 from . import ops
-from .device import DeviceArray
+from .device import DeviceArray, Event, Stream, current_stream
 from .dist import LocalCommunicator, shard_range
 from .integrator import KeyState, _as_chain_tree
 
 
+class _WaitFor:
+  """pre_update_hook of langevin_diffusion: order the update after ``event``."""
+
+  def __init__(self, stream, event):
+    self.stream, self.event = stream, event
+
+  def __call__(self):
+    self.stream.wait_event(self.event)
+
+
 class ShardedTemperingState:
-  def __init__(self, **kw):
+  """``exchange`` / ``temp_index`` are written by the exchange stream: reading
+  them through these properties first waits for the pending exchange."""
+
+  def __init__(self, exchange, temp_index, **kw):
     self.__dict__.update(kw)
+    self._exchange, self._temp_index = exchange, temp_index
+    self.pending: Event = None        # end of the exchange in flight (overlap mode)
+
+  def wait(self):
+    if self.pending is not None:
+      self.pending.sync()
+
+  @property
+  def exchange(self):
+    self.wait()
+    return self._exchange
+
+  @property
+  def temp_index(self):
+    self.wait()
+    return self._temp_index
 
 
-def sharded_tempering(integrator, temperatures: Sequence[float], comm=None):
+def sharded_tempering(integrator, temperatures: Sequence[float], comm=None,
+                      overlap_exchange: bool = False):
   """Returns ``(init, update, get)`` like the reference's solvers.
 
   ``init(samples, ssq_init=0.0, key=PRNGKey(0), F=1.0, **kw)``: ``samples`` is
@@ -44,6 +80,8 @@ def sharded_tempering(integrator, temperatures: Sequence[float], comm=None):
   r0, r1 = shard_range(R, comm.rank, comm.world)
   n_local = r1 - r0
   init_integrator, update_integrator, get_integrator = integrator
+  xstream = Stream.create() if overlap_exchange else None
+  ready, done = Event(), Event()       # (U, var) snapshot taken / exchange finished
 
   def init(samples, ssq_init=0.0, key=None, F=1.0, **kwargs):
     if not (isinstance(samples, (list, tuple)) and len(samples) == R
@@ -83,29 +121,53 @@ def sharded_tempering(integrator, temperatures: Sequence[float], comm=None):
         temp_per_chain=DeviceArray.from_numpy(t_local),
         temp_index=DeviceArray.from_numpy(
             np.tile(np.arange(r0, r1, dtype=np.int32)[:, None], (1, B))),
-        step=0, B=B)
+        uv_send=DeviceArray.zeros((n_local, 2, B)), step=0, B=B)
+
+  comm_handle = getattr(comm, "_comm", None)
+  native = isinstance(comm, LocalCommunicator) or comm_handle is not None
 
   def update(state: ShardedTemperingState, schedule, *unused):
     state.step += 1
     B = state.B
+    main = current_stream()
+    hook = None
+    if overlap_exchange and state.pending is not None:
+      # the previous exchange must have written the labels before this step's
+      # UPDATE kernel reads them; draw / potential / gradient do not depend on it
+      hook = _WaitFor(main, done)
     for l in range(n_local):
       t_row = state.temp_per_chain.row_slice(l, l + 1).reshape(B)
       state.replicas[l] = update_integrator(state.replicas[l], schedule,
-                                            temp_per_chain=t_row)
-    comm.allgather(state.uv, state.gathered)          # the only collective
-    ops.resgld_ladder_step(state.gathered, state.holder, state.ssq, state.F,
-                           state.temps, state.keys.current, state.keys.next,
-                           state.exchange, R, B, state.step, r0, n_local,
-                           state.temp_per_chain, state.temp_index)
+                                            temp_per_chain=t_row,
+                                            pre_update_hook=hook if l == 0 else None)
+    if native:
+      # snapshot + all-gather + decision kernels: one C call
+      ops.resgld_sharded_exchange(
+          comm_handle, main, xstream, ready if overlap_exchange else None,
+          done if overlap_exchange else None, state.uv, state.uv_send, state.gathered,
+          state.holder, state.ssq, state.F, state.temps, state.keys.current,
+          state.keys.next, state._exchange, R, B, state.step, r0, n_local,
+          state.temp_per_chain, state._temp_index)
+    else:
+      assert not overlap_exchange, "overlap needs the NCCL / local communicator"
+      comm.allgather(state.uv, state.gathered)
+      ops.resgld_ladder_step(state.gathered, state.holder, state.ssq, state.F,
+                             state.temps, state.keys.current, state.keys.next,
+                             state._exchange, R, B, state.step, r0, n_local,
+                             state.temp_per_chain, state._temp_index)
     state.keys.flip()
+    if overlap_exchange:
+      state.pending = done
     return state, None
 
   def get(state: ShardedTemperingState) -> Dict[str, Any]:
     """Local replicas' variables plus the temperature index of every system
     (index 0 marks the sample of the un-tempered chain, solver.py:296-297)."""
+    if state.pending is not None:      # order later reads on the sampling stream
+      current_stream().wait_event(state.pending)
     return {"variables": [get_integrator(s)["variables"] for s in state.replicas],
             "likelihood": [get_integrator(s)["likelihood"] for s in state.replicas],
-            "temperature_index": state.temp_index, "model_state": None}
+            "temperature_index": state._temp_index, "model_state": None}
 
   return init, update, get
 

@@ -65,12 +65,15 @@ def test_parallel_tempering_matches_oracle(gpu):
   np.testing.assert_allclose(state.ssq.numpy(), ost.ssq, rtol=1e-4)
 
 
-def test_sharded_label_swap_ladder_equals_state_swap(gpu):
+@pytest.mark.parametrize("overlap", [False, True])
+def test_sharded_label_swap_ladder_equals_state_swap(gpu, overlap):
   """R = 2 on one rank: exchanging temperature labels (what crosses NVLink in
-  the multi-GPU layout) gives the reference's cold chain."""
+  the multi-GPU layout) gives the reference's cold chain -- also with the
+  exchange running on its own stream under the next step's potential."""
   from jax_sgmc_b200 import scheduler, tempering
   X, y, integ, init_n, init_h, keys = _problem()
-  init, update, get = tempering.sharded_tempering(integ, [1.0, T_HOT])
+  init, update, get = tempering.sharded_tempering(integ, [1.0, T_HOT],
+                                                  overlap_exchange=overlap)
   state = init([[{"w": r} for r in init_n], [{"w": r} for r in init_h]], key=keys)
   cold, exch = [], []
   for _ in range(K):
@@ -83,18 +86,20 @@ def test_sharded_label_swap_ladder_equals_state_swap(gpu):
   assert err < 1e-5, err
 
 
-def test_ladder_four_replicas_keeps_a_permutation(gpu):
+@pytest.mark.parametrize("overlap", [False, True])
+def test_ladder_four_replicas_keeps_a_permutation(gpu, overlap):
   """R = 4 (extension, no reference oracle): labels stay a permutation, every
   pair gets attempted, hot replicas spread wider than cold ones."""
   from jax_sgmc_b200 import scheduler, tempering
   X, y, integ, init_n, _, keys = _problem()
   temps = [1.0, 4.0, 16.0, 64.0]
-  init, update, get = tempering.sharded_tempering(integ, temps)
+  init, update, get = tempering.sharded_tempering(integ, temps, overlap_exchange=overlap)
   state = init([{"w": r} for r in init_n], key=keys)
   seen = np.zeros((3, S), bool)
   for _ in range(200):
     state, _ = update(state, scheduler.schedule(EPS, 1.0, 1.0, True))
     seen |= state.exchange.numpy().astype(bool)
+  state.wait()
   holder = state.holder.numpy()
   assert all(sorted(holder[:, b].tolist()) == [0, 1, 2, 3] for b in range(S))
   assert seen.any(axis=1).all()

@@ -42,6 +42,8 @@ def main():
   ap.add_argument("--observations", type=int, default=100000)
   ap.add_argument("--steps", type=int, default=100)
   ap.add_argument("--path", default="auto")
+  ap.add_argument("--overlap", action="store_true",
+                  help="run the exchange on a second stream under the next step's potential")
   a = ap.parse_args()
   rank, world, local = dist.env_rank_world()
   device.set_device(local)
@@ -55,7 +57,8 @@ def main():
     a.systems, a.features, a.batch, a.observations, a.steps, a.path = 9, 16, 32, 400, 60, "simt"
   B, d = a.systems, a.features
   integ = build(d, a.batch, a.observations, a.path)
-  init, update, get = tempering.sharded_tempering(integ, temps, comm)
+  init, update, get = tempering.sharded_tempering(integ, temps, comm,
+                                                  overlap_exchange=a.overlap)
   rng = np.random.default_rng(0)
   samples = [[{"w": (rng.standard_normal(d) * 0.1).astype(np.float32)} for _ in range(B)]
              for _ in range(R)]
@@ -96,6 +99,7 @@ def main():
   e0.record(stream)
   for _ in range(a.steps):
     state, _ = update(state, sch)
+  state.wait()
   e1.record(stream)
   e1.sync()
   ms = e0.elapsed_ms(e1)
@@ -107,6 +111,7 @@ def main():
     ms = float(t[0])
   if rank == 0:
     print(json.dumps({"workload": "reSGLD ladder, one replica per GPU", "n_gpus": world,
+                      "overlap_exchange": bool(a.overlap),
                       "replicas": R, "systems": B, "features": d, "batch": a.batch,
                       "ms_per_step": ms / a.steps,
                       "replica_chain_steps_per_s": R * B * a.steps / (ms * 1e-3)}), flush=True)
