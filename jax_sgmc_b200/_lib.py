@@ -45,6 +45,7 @@ PROTOTYPES = {
     "sgmc_memcpy_d2d": [_vp, _vp, _sz, _vp],
     "sgmc_memset": [_vp, _int, _sz, _vp],
     "sgmc_stream_create": [C.POINTER(_vp)],
+    "sgmc_stream_create_high_priority": [C.POINTER(_vp)],
     "sgmc_stream_destroy": [_vp],
     "sgmc_stream_sync": [_vp],
     "sgmc_device_sync": [],

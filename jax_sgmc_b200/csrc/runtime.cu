@@ -89,6 +89,17 @@ int sgmc_stream_create(void** stream) {
   *stream = (void*)s;
   return 0;
 }
+int sgmc_stream_create_high_priority(void** stream) {
+  int lo = 0, hi = 0;
+  if (check_cuda(cudaDeviceGetStreamPriorityRange(&lo, &hi), "cudaDeviceGetStreamPriorityRange"))
+    return 1;
+  cudaStream_t s;
+  if (check_cuda(cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, hi),
+                 "cudaStreamCreateWithPriority"))
+    return 1;
+  *stream = (void*)s;
+  return 0;
+}
 int sgmc_stream_destroy(void* stream) {
   return check_cuda(cudaStreamDestroy((cudaStream_t)stream), "cudaStreamDestroy");
 }

@@ -23,9 +23,10 @@ class Stream:
     self._owned = owned
 
   @classmethod
-  def create(cls) -> "Stream":
+  def create(cls, high_priority: bool = False) -> "Stream":
     h = C.c_void_p()
-    _lib.call("sgmc_stream_create", C.byref(h))
+    _lib.call("sgmc_stream_create_high_priority" if high_priority else "sgmc_stream_create",
+              C.byref(h))
     return cls(h.value, owned=True)
 
   @classmethod

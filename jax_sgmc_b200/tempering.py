@@ -14,8 +14,10 @@ cold-chain samples reproduce the reference (tests/test_gpu_tempering.py).
 ``overlap_exchange=True`` moves the all-gather and the decision kernels to a
 second stream: the swap of step k only has to be known when step k+1 *updates*
 (the temperature enters the noise scale, not the potential), so it runs
-concurrently with step k+1's minibatch draw and potential / gradient kernels
-and the exchange latency disappears from the step.  Same results bit for bit.
+concurrently with step k+1's minibatch draw and potential / gradient kernels.
+Same results bit for bit.  Measured on 8 B200 it does not pay (the NCCL kernel
+spinning next to the GEMMs costs more than the latency it hides, DESIGN.md
+section 5), so it is off by default.
 """
 from __future__ import annotations
 
