@@ -100,6 +100,11 @@ PROTOTYPES = {
     "sgmc_resgld_sharded_exchange": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp, _vp, _vp,
                                      _vp, _vp, _vp, _vp, _vp, _int, _i64, _i64, _int, _int,
                                      _vp, _vp, _int],
+    "sgmc_p2p_export": [_vp, _vp],
+    "sgmc_p2p_open": [_vp, C.POINTER(_vp)],
+    "sgmc_p2p_close": [_vp],
+    "sgmc_p2p_allgather": [_vp, _vp, _int, _int, _vp, _sz, C.c_uint],
+    "sgmc_p2p_timeouts": [C.POINTER(C.c_uint)],
     "sgmc_nccl_unique_id": [_vp],
     "sgmc_nccl_init": [C.POINTER(_vp), _vp, _int, _int],
     "sgmc_nccl_destroy": [_vp],
@@ -114,6 +119,7 @@ SPECIAL = {
     "sgmc_launch_count": ([], C.c_ulonglong),
     "sgmc_nccl_available": ([], _int),
     "sgmc_glm_workspace_bytes": ([_i64, _i64, _i64, _int], _sz),
+    "sgmc_p2p_window_bytes": ([_int, _sz], _sz),
 }
 
 _lib = None

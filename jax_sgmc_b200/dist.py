@@ -79,6 +79,66 @@ class GlooCommunicator:
     self._dist.barrier()
 
 
+class PeerCommunicator:
+  """All-gather of a tiny payload through peer memory (NVLink / NVSwitch
+  stores + flags, ``csrc/p2p_exchange.cu``) -- the latency path of the reSGLD
+  exchange; no NCCL involved.  The windows' IPC handles travel over the gloo
+  control plane once."""
+
+  def __init__(self, ctl: GlooCommunicator, bytes_per_rank: int):
+    assert bytes_per_rank % 16 == 0, "payload per rank must be a multiple of 16 bytes"
+    self.rank, self.world, self.bytes = ctl.rank, ctl.world, int(bytes_per_rank)
+    lib = _lib.load()
+    nbytes = int(lib.sgmc_p2p_window_bytes(self.world, self.bytes))
+    self.window = DeviceArray.zeros((nbytes,), np.uint8)
+    current_stream().sync()
+    handle = (C.c_char * 64)()
+    _lib.call("sgmc_p2p_export", C.c_void_p(self.window.ptr), handle)
+    handles = np.zeros((self.world, 64), np.uint8)
+    ctl.allgather(np.frombuffer(handle.raw, np.uint8).copy(), handles)
+    self._opened, ptrs = [], []
+    for r in range(self.world):
+      if r == self.rank:
+        ptrs.append(self.window.ptr)
+        continue
+      p = C.c_void_p()
+      buf = (C.c_char * 64).from_buffer_copy(handles[r].tobytes())
+      _lib.call("sgmc_p2p_open", buf, C.byref(p))
+      self._opened.append(p)
+      ptrs.append(p.value)
+    self.peer_table = DeviceArray.from_numpy(np.array(ptrs, np.uint64))
+    self.seq = 0
+    ctl.barrier()          # every window is mapped before anyone stores into it
+    self._ctl = ctl
+
+  def allgather(self, send: DeviceArray, recv: DeviceArray = None, stream=None) -> DeviceArray:
+    """Returns a view of the gathered rows ([world] + send.shape) inside the
+    local window; ``recv`` is ignored (nothing is copied)."""
+    assert send.nbytes == self.bytes
+    self.seq += 1
+    s = (stream or current_stream()).handle
+    _lib.call("sgmc_p2p_allgather", s, C.c_void_p(self.peer_table.ptr), self.rank,
+              self.world, vp(send), self.bytes, self.seq)
+    off = (self.seq & 1) * self.world * self.bytes
+    return DeviceArray((self.world,) + tuple(send.shape), send.dtype,
+                       ptr=self.window.ptr + off, owner=self.window)
+
+  def timeouts(self) -> int:
+    n = C.c_uint()
+    _lib.call("sgmc_p2p_timeouts", C.byref(n))
+    return int(n.value)
+
+  def barrier(self):
+    self._ctl.barrier()
+
+  def __del__(self):
+    for p in getattr(self, "_opened", []):
+      try:
+        _lib.call("sgmc_p2p_close", p)
+      except Exception:
+        pass
+
+
 class NcclCommunicator:
   """Device buffers over NCCL / NVLink through the C ABI."""
 

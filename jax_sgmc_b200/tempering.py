@@ -151,9 +151,11 @@ def sharded_tempering(integrator, temperatures: Sequence[float], comm=None,
           state.keys.next, state._exchange, R, B, state.step, r0, n_local,
           state.temp_per_chain, state._temp_index)
     else:
+      # peer-memory all-gather (returns a view of the rows in its window) or a
+      # host-side communicator, then the decision kernels
       assert not overlap_exchange, "overlap needs the NCCL / local communicator"
-      comm.allgather(state.uv, state.gathered)
-      ops.resgld_ladder_step(state.gathered, state.holder, state.ssq, state.F,
+      gathered = comm.allgather(state.uv, state.gathered)
+      ops.resgld_ladder_step(gathered, state.holder, state.ssq, state.F,
                              state.temps, state.keys.current, state.keys.next,
                              state._exchange, R, B, state.step, r0, n_local,
                              state.temp_per_chain, state._temp_index)

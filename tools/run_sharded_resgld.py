@@ -42,6 +42,8 @@ def main():
   ap.add_argument("--observations", type=int, default=100000)
   ap.add_argument("--steps", type=int, default=100)
   ap.add_argument("--path", default="auto")
+  ap.add_argument("--p2p", action="store_true",
+                  help="peer-memory all-gather (NVLink stores + flags) instead of NCCL")
   ap.add_argument("--overlap", action="store_true",
                   help="run the exchange on a second stream under the next step's potential")
   a = ap.parse_args()
@@ -50,12 +52,17 @@ def main():
   stream = Stream.create()
   device.set_current_stream(stream)
   ctl = dist.GlooCommunicator() if world > 1 else None
-  comm = dist.NcclCommunicator.from_control_plane(ctl) if world > 1 else dist.LocalCommunicator()
   R = max(world, 2)
   temps = list(np.geomspace(1.0, 1000.0, R).astype(np.float32))
   if a.check:
-    a.systems, a.features, a.batch, a.observations, a.steps, a.path = 9, 16, 32, 400, 60, "simt"
+    a.systems, a.features, a.batch, a.observations, a.steps, a.path = 10, 16, 32, 400, 60, "simt"
   B, d = a.systems, a.features
+  if world == 1:
+    comm = dist.LocalCommunicator()
+  elif a.p2p:
+    comm = dist.PeerCommunicator(ctl, (R // world) * 2 * B * 4)
+  else:
+    comm = dist.NcclCommunicator.from_control_plane(ctl)
   integ = build(d, a.batch, a.observations, a.path)
   init, update, get = tempering.sharded_tempering(integ, temps, comm,
                                                   overlap_exchange=a.overlap)
@@ -87,6 +94,8 @@ def main():
     n_ex = int(sum(h[2].sum() for h in hist))
     print(f"rank {rank}: sharded == single-process: {ok}; exchanges {n_ex}", flush=True)
     assert ok and n_ex > 0
+    if a.p2p:
+      assert comm.timeouts() == 0
     ctl.barrier()
     return
 
@@ -112,6 +121,7 @@ def main():
   if rank == 0:
     print(json.dumps({"workload": "reSGLD ladder, one replica per GPU", "n_gpus": world,
                       "overlap_exchange": bool(a.overlap),
+                      "exchange": "p2p" if a.p2p else ("nccl" if world > 1 else "local"),
                       "replicas": R, "systems": B, "features": d, "batch": a.batch,
                       "ms_per_step": ms / a.steps,
                       "replica_chain_steps_per_s": R * B * a.steps / (ms * 1e-3)}), flush=True)
