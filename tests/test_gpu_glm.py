@@ -166,6 +166,52 @@ def test_sgld_logistic_trajectory_1000_steps(gpu, rms):
   assert np.array_equal(d_dk[K % 2].numpy(), dk)
 
 
+@pytest.mark.parametrize("rms", [False, True])
+def test_sgld_trajectory_1000_steps_tensor_core_path(gpu, rms):
+  """The same 1 000-step comparison with the gradient from the tcgen05 GEMMs
+  (split-fp16 "parity" path) and the whole step issued through
+  sgmc_glm_sgld_step.  Plain SGLD holds the 1e-5 trajectory bound; with RMSprop
+  the preconditioner 1/sqrt(v') amplifies the (1e-5 of the row scale) gradient
+  error on coordinates with small |g|, bound 1e-4."""
+  from jax_sgmc_b200 import ops
+  from jax_sgmc_b200.device import DeviceArray as DA
+  from oracle import scheduler as osched
+  d, C, n, N, K = 64, 128, 64, 5000, 1000
+  X, y, _ = odata.logistic_dataset(N, d, seed=0)
+  theta0 = np.zeros((C, d), np.float32)
+  keys = np.stack([prng.PRNGKey(c) for c in range(C)])
+  eps = osched.polynomial_step_size_first_last(K, 1e-3 if not rms else 2e-2,
+                                               1e-4 if not rms else 2e-3)
+  spec = ops.glm_spec("logistic", d, w_off=0, prior="gaussian", prior_off=0,
+                      prior_size=d, prior_scale=10.0)
+  pot = osgmc.minibatch_potential(osgmc.Logistic(d, 0),
+                                  osgmc.Prior("gaussian", 0, d, 10.0))
+  dX, dy = DA.from_numpy(X), DA.from_numpy(y)
+  d_theta = DA.from_numpy(theta0)
+  d_v = DA.from_numpy(np.ones_like(theta0)) if rms else None
+  d_k = [DA.from_numpy(keys), DA((C, 2), np.uint32)]
+  d_dk = [DA.from_numpy(prng.PRNGKey(0)), DA((2,), np.uint32)]
+  d_idx = DA((n,), np.int32)
+  d_U, d_var, d_g = DA((C,), np.float32), DA((C,), np.float32), DA((C, d), np.float32)
+  ws = ops.glm_workspace(C, n, d, "tc_parity")
+  for k in range(K):
+    ops.minibatch_draw(d_dk[k % 2], d_dk[(k + 1) % 2], d_idx, N)
+    ops.glm_sgld_step(spec, d_theta, dX, dy, d_idx, N, d_U, d_var, d_g, d_k[k % 2],
+                      d_k[(k + 1) % 2], eps[k], 1.0, v=d_v, workspace=ws, path="tc_parity")
+  st = osgmc.langevin_init(theta0, keys, rms=rms)
+  dk = prng.PRNGKey(0)
+  for k in range(K):
+    dk, idx = odata.device_draw(dk, n, N)
+    Xb, yb = X[idx], y[idx]
+    st = osgmc.langevin_update(st, lambda th: pot(th, (Xb, yb), N), [d], eps[k], 1.0)
+  got = d_theta.numpy()
+  err = np.abs(got - st.theta).max() / np.abs(st.theta).max()
+  assert err < (1e-4 if rms else 1e-5), err
+  np.testing.assert_allclose(d_U.numpy(), st.potential, rtol=1e-4 if rms else 1e-5)
+  assert np.array_equal(d_k[K % 2].numpy(), st.key)      # noise stream: bit-exact
+  assert np.array_equal(d_dk[K % 2].numpy(), dk)         # minibatch stream: bit-exact
+
+
 # ---- tensor-core (tcgen05) paths ------------------------------------------------
 
 def _tc_case(C, n, d, seed=0):
