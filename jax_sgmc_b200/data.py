@@ -44,9 +44,18 @@ class BatchRef:
   """
 
   def __init__(self, loader: "DataLoader", idx: Optional[DeviceArray], n: int,
-               mask: Optional[DeviceArray] = None, host_idx=None):
+               mask: Optional[DeviceArray] = None, host_idx=None,
+               rows: Optional[Dict[str, DeviceArray]] = None):
     self.loader, self.idx, self.n, self.mask = loader, idx, int(n), mask
     self.host_idx = host_idx
+    # streaming loader: the minibatch rows themselves ({leaf: f32[n, ...]} on
+    # the device, already gathered on the host), idx is None
+    self.rows = rows
+
+  def leaf(self, name: str) -> DeviceArray:
+    """The array the potential kernels read ``name`` from: the gathered rows of
+    a streamed batch, else the HBM-resident data set (indexed by ``idx``)."""
+    return self.rows[name] if self.rows is not None else self.loader.device_data[name]
 
   @property
   def per_chain(self) -> bool:
@@ -54,6 +63,8 @@ class BatchRef:
 
   def materialize(self) -> Dict[str, np.ndarray]:
     """Gathered rows on the host (debugging / tests): {name: array[n, ...]}."""
+    if self.rows is not None:
+      return {k: v.numpy() for k, v in self.rows.items()}
     idx = self.idx.numpy() if self.idx is not None else np.arange(self.n)
     return {k: v.numpy()[idx] for k, v in self.loader.device_data.items()}
 
@@ -209,6 +220,60 @@ class NumpyDataLoader(DataLoader):
     return sel, mask
 
 
+class StreamingNumpyDataLoader(NumpyDataLoader):
+  """A host-resident data set that does NOT fit (or should not live) in HBM:
+  the reference's ``NumpyDataLoader`` cache refills (data/core.py:664-791,
+  numpy_loader.py:342-389) with the ``io_callback`` replaced by pinned-memory
+  double buffering -- while the chains consume the cached block, the next block
+  of ``cache_size`` minibatches is gathered on the host into page-locked memory
+  and copied to the device on a second stream.
+
+  Index streams are ``NumpyDataLoader``'s (same PCG64 draws).  All chains of a
+  solver call share ONE stream of minibatches (``shared`` = the first chain's
+  pipeline): shipping a separate batch per chain would multiply the host link
+  traffic by the number of chains."""
+
+  def __init__(self, copy=True, **reference_data):
+    del copy
+    assert len(reference_data) > 0, "Observations are required."
+    counts = {int(np.shape(v)[0]) for v in reference_data.values()}
+    assert len(counts) == 1, "All arrays must have the same leading dimension."
+    self._observation_count = counts.pop()
+    self.host_data = {k: np.ascontiguousarray(v, dtype=np.float32)
+                      for k, v in reference_data.items()}
+    self.host_shapes = {k: v.shape for k, v in self.host_data.items()}
+    self.device_data = {}            # nothing is resident
+    self._chains: List[dict] = []
+
+  def absmax(self, name: str) -> float:
+    cache = self.__dict__.setdefault("_absmax", {})
+    if name not in cache:
+      cache[name] = float(np.abs(self.host_data[name]).max())
+    return cache[name]
+
+  @property
+  def _format(self):
+    return {k: ((), v.shape[1:]) for k, v in self.host_data.items()}
+
+
+class _StreamSlot:
+  """One cached block: pinned staging + device copy of ``cache`` minibatches."""
+
+  def __init__(self, loader: StreamingNumpyDataLoader, cache: int, n: int):
+    from .device import Event
+    from .io import _pinned_array
+    self.host, self.dev, self.addr = {}, {}, {}
+    for k, v in loader.host_data.items():
+      row = int(np.prod(v.shape[1:], dtype=np.int64))
+      arr, addr = _pinned_array(cache * n * row)
+      self.host[k] = arr.reshape((cache * n,) + v.shape[1:])
+      self.addr[k] = addr
+      self.dev[k] = DeviceArray((cache, n) + v.shape[1:], np.float32)
+    self.copied = Event()
+    self.consumed = Event()
+    self.host_idx = None
+
+
 class CacheState:
   """State of the random-batch functional (data/core.py:240-263).
 
@@ -255,6 +320,60 @@ def random_reference_data(data_loader: DataLoader, cached_batches_count: int,
 
     return init_fn, get_fn, lambda: None
 
+  if isinstance(data_loader, StreamingNumpyDataLoader):
+    import ctypes as C
+    from . import _lib
+    from .device import Stream, current_stream
+
+    def init_fn(**kwargs) -> CacheState:
+      chain_id = data_loader.register_random_pipeline(
+          cached_batches_count, mb_size, **kwargs)
+      return CacheState("stream", chain_ids=[chain_id], line=cached_batches_count,
+                        cache_size=cached_batches_count, slots=None, cur=1,
+                        copy_stream=None, staged=False)
+
+    def _stage(state: CacheState, slot: "_StreamSlot"):
+      """Draw the next block of indices, gather its rows into the slot's pinned
+      memory and enqueue the H2D copy on the copy stream."""
+      idx, _ = data_loader.get_indices(state.chain_ids[0])        # [cache, n]
+      slot.host_idx = idx
+      flat = idx.reshape(-1)
+      # host: the previous copy OUT of this pinned buffer has finished (the host
+      # runs ahead of the device); device: the chains are done with the slot
+      slot.copied.sync()
+      state.copy_stream.wait_event(slot.consumed)
+      for k, v in data_loader.host_data.items():
+        np.take(v, flat, axis=0, out=slot.host[k])
+        _lib.call("sgmc_memcpy_h2d", C.c_void_p(slot.dev[k].ptr), C.c_void_p(slot.addr[k]),
+                  slot.dev[k].nbytes, state.copy_stream.handle)
+      slot.copied.record(state.copy_stream)
+
+    def get_fn(state: CacheState, information: bool = False):
+      main = current_stream()
+      if state.slots is None:
+        state.copy_stream = Stream.create()
+        state.slots = [_StreamSlot(data_loader, cached_batches_count, mb_size)
+                       for _ in range(2)]
+        for sl in state.slots:
+          sl.consumed.record(main)
+        _stage(state, state.slots[0])
+      if state.line == state.cache_size:               # block exhausted: switch slots
+        old = state.slots[state.cur]
+        old.consumed.record(main)
+        state.cur = 1 - state.cur
+        main.wait_event(state.slots[state.cur].copied)
+        state.line = 0
+        _stage(state, old)                             # prefetch the block after this one
+      slot = state.slots[state.cur]
+      rows = {k: v.row_slice(state.line, state.line + 1).reshape((mb_size,) + v.shape[2:])
+              for k, v in slot.dev.items()}
+      batch = BatchRef(data_loader, None, mb_size, rows=rows,
+                       host_idx=slot.host_idx[state.line][None])
+      state.line += 1
+      return (state, (batch, info)) if information else (state, batch)
+
+    return init_fn, get_fn, lambda: None
+
   if isinstance(data_loader, NumpyDataLoader):
     def init_fn(**kwargs) -> CacheState:
       chain_id = data_loader.register_random_pipeline(
@@ -293,6 +412,8 @@ def merge_cache_states(states: List[CacheState]) -> CacheState:
   starts from PRNGKey(0), numpy_loader.py:124) so that one minibatch is shared.
   """
   first = states[0]
+  if first.mode == "stream":      # one shared stream of minibatches for all chains
+    return first
   if first.mode == "device":
     for s in states[1:]:
       if not np.array_equal(s.host_key, first.host_key):
@@ -316,6 +437,9 @@ def full_reference_data(data_loader: DataLoader, cached_batches_count: int = 100
   ``cached_batches_count`` as the batch size (core.py:552-553).
   """
   N = data_loader.static_information["observation_count"]
+  if isinstance(data_loader, StreamingNumpyDataLoader):
+    raise NotImplementedError("full-data passes over a streamed (host-resident) data set "
+                              "are not implemented; use NumpyDataLoader (HBM-resident)")
   if isinstance(data_loader, DeviceNumpyDataLoader):
     mb_size = cached_batches_count
   if mb_size is None or mb_size <= 0:

@@ -60,8 +60,8 @@ class _PotentialFn:
                        batch.loader.absmax(self.likelihood.x))
     C, P, n = sample.n_chains, sample.n_params, batch.n
     N = int(info.observation_count)
-    X = batch.loader.device_data[self.likelihood.x]
-    y = batch.loader.device_data[self.likelihood.y]
+    X = batch.leaf(self.likelihood.x)
+    y = batch.leaf(self.likelihood.y)
     if mask is None:
       mask = batch.mask
     path = _select_path(self.path, spec, C, n)
@@ -128,8 +128,8 @@ class _PotentialFn:
              "ws": ops.glm_workspace(C, n, spec.d, path), "ell": None}
       self._buffers[key] = buf
     ops.glm_sgld_step(
-        spec, sample.flat, batch.loader.device_data[self.likelihood.x],
-        batch.loader.device_data[self.likelihood.y], batch.idx,
+        spec, sample.flat, batch.leaf(self.likelihood.x),
+        batch.leaf(self.likelihood.y), batch.idx,
         int(info.observation_count), U_out if U_out is not None else buf["U"],
         var_out if var_out is not None else buf["var"], grad_out, keys_in, keys_out,
         step_size, temperature, v=v, alpha=alpha, lmbd=lmbd, workspace=buf["ws"],

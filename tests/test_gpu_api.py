@@ -200,3 +200,34 @@ def test_sample_ring_equals_device_buffer(gpu, direct, monkeypatch):
     assert np.array_equal(ra["samples"]["likelihood"], rb["samples"]["likelihood"])
   assert not np.array_equal(a[0]["samples"]["variables"]["w"][0],
                             a[0]["samples"]["variables"]["w"][-1])
+
+
+def test_streaming_loader_equals_resident_loader(gpu):
+  """StreamingNumpyDataLoader (rows gathered on the host into pinned memory,
+  double-buffered H2D of cache_size minibatches on a copy stream; SURVEY.md
+  8f-2) feeds the chains the same minibatches as the HBM-resident
+  NumpyDataLoader: identical samples, several cache refills deep."""
+  from jax_sgmc_b200 import alias, data, glm, potential
+  X, y, _ = odata.logistic_dataset(700, 16, seed=4)
+  pot = potential.minibatch_potential(glm.GaussianPrior(5.0), glm.LogisticRegression(),
+                                      strategy="vmap", path="simt")
+  init = {"w": np.zeros(16, np.float32)}
+  out = []
+  for cls in (data.NumpyDataLoader, data.StreamingNumpyDataLoader):
+    loader = cls(x=X, y=y)
+    run = alias.sgld(pot, loader, cache_size=7, batch_size=24, first_step_size=1e-2,
+                     last_step_size=1e-3, burn_in=5, accepted_samples=40, rms_prop=True,
+                     progress_bar=False)
+    out.append(run(init, iterations=60)[0])
+  a, b = out
+  assert a["sample_count"] == b["sample_count"] == 40
+  assert np.array_equal(a["samples"]["variables"]["w"], b["samples"]["variables"]["w"])
+  assert np.array_equal(a["samples"]["likelihood"], b["samples"]["likelihood"])
+  # many chains share the one stream of minibatches
+  loader = data.StreamingNumpyDataLoader(x=X, y=y)
+  run = alias.sgld(pot, loader, cache_size=4, batch_size=24, first_step_size=1e-2,
+                   last_step_size=1e-3, accepted_samples=10, progress_bar=False)
+  res = run(init, init, init, iterations=20, keys=np.stack([prng.PRNGKey(i) for i in range(3)]))
+  assert len(res) == 3 and res[2]["samples"]["variables"]["w"].shape == (10, 16)
+  assert not np.array_equal(res[0]["samples"]["variables"]["w"],
+                            res[1]["samples"]["variables"]["w"])
