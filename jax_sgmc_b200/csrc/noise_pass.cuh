@@ -52,6 +52,7 @@ int build_leaf_table(LeafTable* t, const int64_t* leaf_sizes, int n_leaves,
 
 struct NoiseLaunch {
   int grid;
+  int threads;              // CTA size: a multiple of 32 in [kNoiseThreads / 2, kNoiseThreads]
   size_t smem;
   int64_t tiles_total;
   int max_chains_per_cta;
@@ -130,7 +131,8 @@ k_noise_pass(const __grid_constant__ LeafTable tab,
   const int n_ch = (int)(c_hi - c_lo + 1);
 
   // ---- prologue: per-(chain, leaf) noise keys --------------------------
-  for (int idx = threadIdx.x; idx < n_ch * L; idx += kNoiseThreads) {
+  const int n_threads = blockDim.x, n_warps = n_threads >> 5;
+  for (int idx = threadIdx.x; idx < n_ch * L; idx += n_threads) {
     const int ci = idx / L, l = idx - ci * L;
     const int64_t c = c_lo + ci;
     Key k;
@@ -160,12 +162,12 @@ k_noise_pass(const __grid_constant__ LeafTable tab,
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // rotate the first warp per CTA so the odd tiles of the CTAs spread evenly
   // over the four SM sub-partitions (warp w runs on sub-partition w % 4)
-  const int wrot = (warp + blockIdx.x) & (kNoiseWarps - 1);
+  const int wrot = (warp + blockIdx.x) % n_warps;
   // (chain, tile-in-chain) advance incrementally: no division in the loop
   const uint32_t tpc = tab.tiles_per_chain;
   int64_t c = (t0 + wrot) / tpc;
   uint32_t lt = (uint32_t)((t0 + wrot) - c * tpc);
-  for (int64_t tile = t0 + wrot; tile < t1; tile += kNoiseWarps, lt += kNoiseWarps) {
+  for (int64_t tile = t0 + wrot; tile < t1; tile += n_warps, lt += n_warps) {
     while (lt >= tpc) { lt -= tpc; ++c; }
     const uint32_t g = lt * 32u + lane;
     float partial = 0.0f;
@@ -216,10 +218,10 @@ int launch_noise_pass(cudaStream_t stream, const LeafTable& tab,
   if (plan_noise_launch(tab, n_chains, fn, &nl)) return 1;
   if (nl.tiles_total == 0) return 0;
   if (layout == 0)
-    launch_pdl(k_noise_pass<0, Op>, dim3(nl.grid), dim3(kNoiseThreads), nl.smem, stream, tab,
+    launch_pdl(k_noise_pass<0, Op>, dim3(nl.grid), dim3(nl.threads), nl.smem, stream, tab,
                keys_in, keys_out, n_chains, nl.tiles_total, key_mode, op);
   else
-    launch_pdl(k_noise_pass<1, Op>, dim3(nl.grid), dim3(kNoiseThreads), nl.smem, stream, tab,
+    launch_pdl(k_noise_pass<1, Op>, dim3(nl.grid), dim3(nl.threads), nl.smem, stream, tab,
                keys_in, keys_out, n_chains, nl.tiles_total, key_mode, op);
   return post_launch(name);
 }

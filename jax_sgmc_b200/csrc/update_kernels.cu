@@ -83,6 +83,22 @@ int plan_noise_launch(const LeafTable& t, int64_t n_chains, const void* kernel,
     grid = grid * 2 > out->tiles_total ? out->tiles_total : grid * 2;
   }
   out->grid = (int)grid;
+  // Warps per CTA: a warp walks whole tiles, so with only a few tiles per warp the
+  // slowest warp sets the pace (C2: 55.4 tiles per CTA over 16 warps = 3.46 -> 4
+  // rounds, 86 % busy; over 14 warps = 3.95 -> 4 rounds, 99 % busy).  Pick the
+  // block size that wastes the fewest tile slots (ties: more warps).
+  const int64_t tiles_per_cta = (out->tiles_total + grid - 1) / grid;
+  int best_w = kNoiseWarps;
+  double best_eff = -1.0;
+  for (int w = kNoiseWarps; w >= kNoiseWarps / 2; --w) {
+    const int64_t rounds = (tiles_per_cta + w - 1) / w;
+    const double eff = (double)tiles_per_cta / (double)(rounds * w);
+    if (eff > best_eff + 1e-9) {
+      best_eff = eff;
+      best_w = w;
+    }
+  }
+  out->threads = best_w * 32;
   return 0;
 }
 
