@@ -173,3 +173,29 @@ def test_auto_path_selection_keeps_the_parity_bound():
   assert _select_path("auto", spec(100), 4096, 1024) == "simt"        # d % 8
   assert _select_path("auto", ops.glm_spec("gaussian", 64, 1, aux_off=0), 4096, 1024) == "simt"
   assert _select_path("tc_throughput", spec(4096), 8, 8) == "tc_throughput"   # explicit wins
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+  """bench.py --impl reference (CPU only): one JSON line with the keys the driver
+  reads, the b200 arm's metric / unit / workload, a cpu_baseline describing the run."""
+  import json
+  import os
+  import subprocess
+  import sys
+  root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+  out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference",
+                        "--steps", "3", "--warmup", "1"], capture_output=True, text=True,
+                       timeout=600, cwd=root)
+  assert out.returncode == 0, out.stderr[-2000:]
+  lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+  assert len(lines) == 1
+  line = json.loads(lines[0])
+  for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step",
+              "higher_is_better", "scaling", "vs_baseline", "dtype", "data", "config",
+              "cpu_baseline", "e2e"):
+    assert key in line, key
+  assert line["impl"] == "reference" and line["steps"] == 3
+  assert line["unit"] == "chain-steps/s" and line["value"] > 0
+  assert line["config"]["workload"].startswith("C2")
+  assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+  assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"]
