@@ -26,7 +26,8 @@ struct GlmArgs {
   int64_t C, P;
   const float* X;         // f32[N_total][d]
   const float* y;         // f32[N_total]
-  const int32_t* idx;     // int32[n] or null (rows 0..n-1)
+  const int32_t* idx;     // int32[n] or null (rows 0..n-1); int32[C][n] when idx_stride = n
+  int64_t idx_stride;     // 0: one minibatch shared by all chains; n: one per chain
   const float* mask;      // f32[n] or null
   int64_t n, N;
   float cot;              // (-N/n)/T

@@ -22,9 +22,13 @@ template <bool NT, class Epi>
 __global__ void __launch_bounds__(256)
 k_sgemm(const float* __restrict__ A, int64_t lda, const float* __restrict__ B,
         int64_t ldb, const int32_t* __restrict__ bidx, int M, int N, int K,
-        const Epi epi) {
+        const Epi epi, int64_t a_zstride, int64_t bidx_zstride) {
   __shared__ float As[TK][TM + 4];
   __shared__ float Bs[TK][TN + 4];
+  // blockIdx.z = chain when every chain has its own minibatch (M = 1 per slice)
+  const int z = blockIdx.z;
+  A += (int64_t)z * a_zstride;
+  if (bidx) bidx += (int64_t)z * bidx_zstride;
   const int tid = threadIdx.x;
   const int m0 = blockIdx.y * TM, n0 = blockIdx.x * TN;
   const int tx = tid & 15, ty = tid >> 4;
@@ -82,7 +86,7 @@ k_sgemm(const float* __restrict__ A, int64_t lda, const float* __restrict__ B,
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int nn = n0 + tx * 4 + j;
-      if (nn < N) epi(m, nn, acc[i][j]);
+      if (nn < N) epi(m + z, nn, acc[i][j]);
     }
   }
 }
@@ -95,7 +99,7 @@ struct LinkEpi {
     GaussConst gc{1.f, 0.f};
     if (a.spec.family == kFamilyGaussian) gc = gauss_const(th[a.spec.aux_off]);
     else if (a.spec.aux_off >= 0) z += th[a.spec.aux_off];
-    const float y = a.y[a.idx ? a.idx[i] : i];
+    const float y = a.y[a.idx ? a.idx[(int64_t)c * a.idx_stride + i] : i];
     float ell, dz;
     glm_link(a.spec.family, z, y, gc, ell, dz);
     float cot = a.cot;
@@ -204,17 +208,23 @@ int glm_finalize(cudaStream_t stream, const GlmArgs& a) {
 
 int glm_simt(cudaStream_t stream, const GlmArgs& a) {
   const int C = (int)a.C, n = (int)a.n, d = a.spec.d;
+  // one minibatch per chain: a [1 x n] / [1 x d] slice per chain along grid.z
+  const bool per_chain = a.idx_stride != 0;
+  const int M = per_chain ? 1 : C;
+  const unsigned gz = per_chain ? (unsigned)C : 1u;
+  SGMC_REQUIRE(gz <= 65535u, "per-chain minibatches: at most 65535 chains per call");
   {
-    dim3 grid((n + TN - 1) / TN, (C + TM - 1) / TM);
+    dim3 grid((n + TN - 1) / TN, (M + TM - 1) / TM, gz);
     k_sgemm<true, LinkEpi><<<grid, 256, 0, stream>>>(
-        a.theta + a.spec.w_off, a.P, a.X, d, a.idx, C, n, d, LinkEpi{a});
+        a.theta + a.spec.w_off, a.P, a.X, d, a.idx, M, n, d, LinkEpi{a},
+        per_chain ? a.P : 0, a.idx_stride);
     if (post_launch("k_sgemm<link>")) return 1;
   }
   if (glm_finalize(stream, a)) return 1;
   if (a.grad) {
-    dim3 grid((d + TN - 1) / TN, (C + TM - 1) / TM);
+    dim3 grid((d + TN - 1) / TN, (M + TM - 1) / TM, gz);
     k_sgemm<false, GradEpi><<<grid, 256, 0, stream>>>(
-        a.R, a.n, a.X, d, a.idx, C, d, n, GradEpi{a});
+        a.R, a.n, a.X, d, a.idx, M, d, n, GradEpi{a}, per_chain ? a.n : 0, a.idx_stride);
     if (post_launch("k_sgemm<grad>")) return 1;
   }
   return 0;
@@ -242,7 +252,7 @@ static int glm_dispatch(void* stream, const sgmc_glm_spec* spec, const float* th
                         const int32_t* idx, const float* mask, int64_t batch_size,
                         int64_t observation_count, float* potential, float* variance,
                         float* grad, float* ell, void* workspace, size_t workspace_bytes,
-                        int path, const FusedSgld& fused) {
+                        int path, const FusedSgld& fused, int64_t idx_stride = 0) {
   SGMC_REQUIRE(spec && theta && X && y && potential, "null argument");
   SGMC_REQUIRE(spec->family == kFamilyGaussian || spec->family == kFamilyLogistic,
                "unknown GLM family %d", spec->family);
@@ -262,6 +272,7 @@ static int glm_dispatch(void* stream, const sgmc_glm_spec* spec, const float* th
   a.spec = *spec;
   a.theta = theta; a.C = n_chains; a.P = P;
   a.X = X; a.y = y; a.idx = idx; a.mask = mask;
+  a.idx_stride = idx_stride;
   a.n = batch_size; a.N = observation_count;
   a.potential = potential; a.variance = variance; a.grad = grad;
   float* ws = reinterpret_cast<float*>(
@@ -288,6 +299,20 @@ int sgmc_glm_potential_grad(void* stream, const sgmc_glm_spec* spec,
   return glm_dispatch(stream, spec, theta, n_chains, P, X, y, idx, mask, batch_size,
                       observation_count, potential, variance, grad, ell, workspace,
                       workspace_bytes, path, none);
+}
+
+int sgmc_glm_potential_grad_per_chain(void* stream, const sgmc_glm_spec* spec,
+                                      const float* theta, int64_t n_chains, int64_t P,
+                                      const float* X, const float* y, const int32_t* idx,
+                                      const float* mask, int64_t batch_size,
+                                      int64_t observation_count, float* potential,
+                                      float* variance, float* grad, float* ell,
+                                      void* workspace, size_t workspace_bytes) {
+  SGMC_REQUIRE(idx != nullptr, "per-chain minibatches need idx int32[C][n]");
+  FusedSgld none{};
+  return glm_dispatch(stream, spec, theta, n_chains, P, X, y, idx, mask, batch_size,
+                      observation_count, potential, variance, grad, ell, workspace,
+                      workspace_bytes, 0, none, batch_size);
 }
 
 int sgmc_glm_sgld_step(void* stream, const sgmc_glm_spec* spec, float* theta, float* v,

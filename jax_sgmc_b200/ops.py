@@ -245,6 +245,20 @@ def glm_potential_grad(spec, theta, X, y, idx, observation_count, potential,
   return workspace
 
 
+def glm_potential_grad_per_chain(spec, theta, X, y, idx, observation_count, potential,
+                                 variance=None, grad=None, ell=None, mask=None,
+                                 workspace=None, stream=None):
+  """One minibatch per chain: idx int32[C, n]; fp32 SIMT kernels, one launch set."""
+  C_, P = theta.shape
+  n = int(idx.shape[1])
+  if workspace is None:
+    workspace = glm_workspace(C_, n, spec.d, "simt")
+  _lib.call("sgmc_glm_potential_grad_per_chain", _s(stream), C.byref(spec), vp(theta), C_,
+            P, vp(X), vp(y), vp(idx), vp(mask), n, int(observation_count), vp(potential),
+            vp(variance), vp(grad), vp(ell), vp(workspace), workspace.nbytes)
+  return workspace
+
+
 def glm_sgld_step(spec, theta, X, y, idx, observation_count, potential, variance,
                   grad, keys_in, keys_out, step_size, temperature=1.0, v=None,
                   alpha=0.9, lmbd=1e-5, mask=None, workspace=None, path=0,

@@ -69,7 +69,7 @@ class _PotentialFn:
     buf = self._buffers.get(key)
     if buf is None:
       buf = {"U": DeviceArray((C,), np.float32), "var": DeviceArray((C,), np.float32),
-             "ws": ops.glm_workspace(C if not batch.per_chain else 1, n, spec.d, path),
+             "ws": ops.glm_workspace(C, n, spec.d, "simt" if batch.per_chain else path),
              "ell": None}
       self._buffers[key] = buf
     grad = None
@@ -87,16 +87,11 @@ class _PotentialFn:
                              var_buf, grad, ell, mask=mask, workspace=buf["ws"],
                              path=path, batch_size=n)
     else:
-      # one minibatch per chain (host loader with per-chain seeds): no sharing,
-      # evaluate chain by chain
-      for c in range(C):
-        ops.glm_potential_grad(
-            spec, sample.flat.row_slice(c, c + 1), X, y,
-            batch.idx.row_slice(c, c + 1).reshape(n), N,
-            U_buf.row_slice(c, c + 1), var_buf.row_slice(c, c + 1),
-            None if grad is None else grad.row_slice(c, c + 1),
-            None if ell is None else ell.row_slice(c, c + 1), mask=mask,
-            workspace=buf["ws"], path="simt", batch_size=n)
+      # one minibatch per chain (host loader with per-chain seeds): no operand
+      # sharing between chains -> fp32 SIMT kernels, all chains in one launch set
+      ops.glm_potential_grad_per_chain(spec, sample.flat, X, y, batch.idx, N, U_buf,
+                                       var_buf, grad, ell, mask=mask,
+                                       workspace=buf["ws"])
     return U_buf, var_buf, grad, ell
 
   # -- public protocol --------------------------------------------------------------

@@ -275,3 +275,46 @@ def test_tc_path_rejects_unsupported(gpu):
   spec = ops.glm_spec("logistic", 12, w_off=0)
   with pytest.raises(_lib.SgmcError):
     _run(ops, DA, spec, theta, X, y, idx, 3000, path="tc_parity")
+
+
+@pytest.mark.parametrize("family", ["logistic", "gaussian"])
+def test_per_chain_minibatches_one_launch_set(gpu, family):
+  """sgmc_glm_potential_grad_per_chain (every chain its own index vector, the
+  reference's host-loader default) equals C single-chain calls bit for bit and
+  the oracle within the fp32 tolerance."""
+  from jax_sgmc_b200 import ops
+  from jax_sgmc_b200.device import DeviceArray as DA
+  rng = np.random.default_rng(12)
+  C, n, d, N = 9, 37, 11, 300
+  X = rng.standard_normal((N, d)).astype(np.float32)
+  if family == "logistic":
+    y = (rng.random(N) < 0.5).astype(np.float32)
+    theta = (rng.standard_normal((C, d)) * 0.4).astype(np.float32)
+    spec = ops.glm_spec("logistic", d, 0, prior="gaussian", prior_off=0, prior_size=d,
+                        prior_scale=2.0)
+    model, prior = osgmc.Logistic(d, 0), osgmc.Prior("gaussian", 0, d, 2.0)
+  else:
+    y = (X @ rng.standard_normal(d) + 0.3 * rng.standard_normal(N)).astype(np.float32)
+    theta = np.concatenate([rng.standard_normal((C, 1)) * 0.2 + 0.3,
+                            rng.standard_normal((C, d)) * 0.4], axis=1).astype(np.float32)
+    spec = ops.glm_spec("gaussian", d, w_off=1, aux_off=0, prior="inv_sigma", prior_off=0)
+    model, prior = osgmc.GaussianLinear(d, 1, 0), osgmc.Prior("inv_sigma", 0)
+  P = theta.shape[1]
+  idx = rng.integers(0, N, (C, n)).astype(np.int32)
+  dX, dy, dth = DA.from_numpy(X), DA.from_numpy(y), DA.from_numpy(theta)
+  U, var, g, ell = (DA((C,), np.float32), DA((C,), np.float32), DA((C, P), np.float32),
+                    DA((C, n), np.float32))
+  ops.glm_potential_grad_per_chain(spec, dth, dX, dy, DA.from_numpy(idx), N, U, var, g, ell)
+  pot = osgmc.minibatch_potential(model, prior)
+  for c in range(C):
+    U1, v1, g1, e1 = (DA((1,), np.float32), DA((1,), np.float32), DA((1, P), np.float32),
+                      DA((1, n), np.float32))
+    ops.glm_potential_grad(spec, DA.from_numpy(theta[c:c + 1]), dX, dy,
+                           DA.from_numpy(idx[c]), N, U1, v1, g1, e1, path="simt")
+    assert np.array_equal(U.numpy()[c:c + 1].view(np.uint32), U1.numpy().view(np.uint32))
+    assert np.array_equal(g.numpy()[c].view(np.uint32), g1.numpy()[0].view(np.uint32))
+    assert np.array_equal(ell.numpy()[c].view(np.uint32), e1.numpy()[0].view(np.uint32))
+    assert np.array_equal(var.numpy()[c:c + 1].view(np.uint32), v1.numpy().view(np.uint32))
+    wU, well, wg = pot(theta[c:c + 1], (X[idx[c]], y[idx[c]]), N)
+    np.testing.assert_allclose(U.numpy()[c], wU[0], rtol=1e-5)
+    _grad_close(g.numpy()[c:c + 1], wg)
