@@ -201,6 +201,31 @@ __global__ void __launch_bounds__(256) k_glm_finalize(const GlmArgs a) {
   }
 }
 
+// full-potential helpers: wrapped index / mask vector of the last batch
+// (data/core.py:571-572) and the running sum over batches
+__global__ void k_wrap_batch(int32_t* __restrict__ idx, float* __restrict__ mask, int64_t first,
+                             int64_t n, int64_t N) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int64_t id = first + i;
+  idx[i] = (int32_t)(id % N);
+  mask[i] = id < N ? 1.0f : 0.0f;
+}
+__global__ void k_fill(float* __restrict__ x, float v, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) x[i] = v;
+}
+__global__ void k_axpy_acc(float* __restrict__ total, float a, const float* __restrict__ u,
+                           int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) total[i] = __fadd_rn(__fmul_rn(1.0f, total[i]), __fmul_rn(a, u[i]));
+}
+__global__ void k_full_finish(float* __restrict__ out, const float* __restrict__ total,
+                              const float* __restrict__ neg_prior, float inv_T, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = __fadd_rn(__fmul_rn(inv_T, total[i]), __fmul_rn(inv_T, neg_prior[i]));
+}
+
 int glm_finalize(cudaStream_t stream, const GlmArgs& a) {
   k_glm_finalize<<<(unsigned)a.C, 256, 0, stream>>>(a);
   return post_launch("k_glm_finalize");
@@ -313,6 +338,61 @@ int sgmc_glm_potential_grad_per_chain(void* stream, const sgmc_glm_spec* spec,
   return glm_dispatch(stream, spec, theta, n_chains, P, X, y, idx, mask, batch_size,
                       observation_count, potential, variance, grad, ell, workspace,
                       workspace_bytes, 0, none, batch_size);
+}
+
+int sgmc_glm_full_potential(void* stream, const sgmc_glm_spec* spec, const float* theta,
+                            int64_t n_chains, int64_t P, const float* X, const float* y,
+                            int64_t observation_count, int64_t batch_size, float* potential,
+                            float* scratch, int32_t* wrap_idx, float* wrap_mask,
+                            void* workspace, size_t workspace_bytes, int path) {
+  SGMC_REQUIRE(spec && potential && scratch && wrap_idx && wrap_mask, "null argument");
+  SGMC_REQUIRE(batch_size > 0 && observation_count > 0, "bad sizes");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int64_t C = n_chains, n = batch_size, N = observation_count;
+  const int d = spec->d;
+  float* total = scratch;            // f32[C]
+  float* U_b = scratch + C;          // f32[C]
+  const unsigned gc = (unsigned)((C + 255) / 256);
+  FusedSgld none{};
+  // inner potential: zero prior, T = 1 (potential.py:258-262)
+  sgmc_glm_spec inner = *spec;
+  inner.prior = kPriorFlat;
+  inner.temperature = 1.0f;
+  k_fill<<<gc, 256, 0, s>>>(total, 0.0f, C);
+  if (post_launch("k_fill")) return 1;
+  // the reference maps with masking=True: every batch goes through the masked
+  // form -N/n * dot(ell, mask) (potential.py:185), whole batches with mask = 1
+  float* ones = wrap_mask;           // f32[n]
+  float* last_mask = wrap_mask + n;  // f32[n]
+  k_fill<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(ones, 1.0f, n);
+  if (post_launch("k_fill")) return 1;
+  const float unscale = (float)((double)n / (double)N);   // undo N/n (potential.py:264-271)
+  const int64_t n_batches = (N + n - 1) / n;
+  for (int64_t b = 0; b < n_batches; ++b) {
+    const bool whole = (b + 1) * n <= N;
+    if (!whole) {                     // last batch: wrap modulo N, mask the overhang
+      k_wrap_batch<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(wrap_idx, last_mask, b * n, n, N);
+      if (post_launch("k_wrap_batch")) return 1;
+    }
+    if (int e = glm_dispatch(stream, &inner, theta, C, P, whole ? X + b * n * d : X,
+                             whole ? y + b * n : y, whole ? nullptr : wrap_idx,
+                             whole ? ones : last_mask, n, N, U_b, nullptr, nullptr, nullptr,
+                             workspace, workspace_bytes, path, none))
+      return e;
+    k_axpy_acc<<<gc, 256, 0, s>>>(total, unscale, U_b, C);
+    if (post_launch("k_axpy_acc")) return 1;
+  }
+  // prior: the potential of an all-masked batch is -prior (T = 1)
+  sgmc_glm_spec pr = *spec;
+  pr.temperature = 1.0f;
+  k_fill<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(last_mask, 0.0f, n);
+  if (post_launch("k_fill")) return 1;
+  if (int e = glm_dispatch(stream, &pr, theta, C, P, X, y, nullptr, last_mask, n, N, U_b, nullptr,
+                           nullptr, nullptr, workspace, workspace_bytes, path, none))
+    return e;
+  k_full_finish<<<gc, 256, 0, s>>>(potential, total, U_b,
+                                   (float)(1.0 / (double)spec->temperature), C);
+  return post_launch("k_full_finish");
 }
 
 int sgmc_glm_sgld_step(void* stream, const sgmc_glm_spec* spec, float* theta, float* v,

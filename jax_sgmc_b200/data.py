@@ -469,4 +469,6 @@ def full_reference_data(data_loader: DataLoader, cached_batches_count: int = 100
       results.append(res)
     return data_state, (results, carry)
 
+  # lets potential.full_potential run all batches inside one C call
+  map_fn.loader, map_fn.mb_size = data_loader, mb_size
   return init_fn, map_fn, lambda: None

@@ -259,6 +259,15 @@ def glm_potential_grad_per_chain(spec, theta, X, y, idx, observation_count, pote
   return workspace
 
 
+def glm_full_potential(spec, theta, X, y, observation_count, batch_size, potential,
+                       scratch, wrap_idx, wrap_mask, workspace, path=0, stream=None):
+  """potential.full_potential over the HBM-resident data set in one C call."""
+  C_, P = theta.shape
+  _lib.call("sgmc_glm_full_potential", _s(stream), C.byref(spec), vp(theta), C_, P, vp(X),
+            vp(y), int(observation_count), int(batch_size), vp(potential), vp(scratch),
+            vp(wrap_idx), vp(wrap_mask), vp(workspace), workspace.nbytes, PATH[path])
+
+
 def glm_sgld_step(spec, theta, X, y, idx, observation_count, potential, variance,
                   grad, keys_in, keys_out, step_size, temperature=1.0, v=None,
                   alpha=0.9, lmbd=1e-5, mask=None, workspace=None, path=0,

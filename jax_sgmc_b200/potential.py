@@ -190,10 +190,34 @@ def full_potential(prior, likelihood, strategy: str = "map", has_state: bool = F
   prior_only = minibatch_potential(prior, likelihood, strategy, has_state,
                                    is_batched, 1.0, path)
 
+  scratch = {}
+
+  def _full_in_one_call(sample: ChainTree, loader, mb_size: int) -> DeviceArray:
+    spec = glm.resolve(likelihood, prior, sample, temperature, loader.absmax(likelihood.x))
+    C, n = sample.n_chains, int(mb_size)
+    run_path = _select_path(path or DEFAULT_PATH, spec, C, n)
+    key = (C, n, run_path)
+    if key not in scratch:
+      scratch[key] = {"s": DeviceArray((2 * C,), np.float32), "idx": DeviceArray((n,), np.int32),
+                      "mask": DeviceArray((2 * n,), np.float32),
+                      "ws": ops.glm_workspace(C, n, spec.d, run_path)}
+    b = scratch[key]
+    out = DeviceArray((C,), np.float32)
+    ops.glm_full_potential(spec, sample.flat, loader.device_data[likelihood.x],
+                           loader.device_data[likelihood.y],
+                           loader.static_information["observation_count"], n, out, b["s"],
+                           b["idx"], b["mask"], b["ws"], path=run_path)
+    return out
+
   def sum_batched_evaluations(sample: ChainTree, data_state, full_data_map_fn,
                               state: Any = None):
     """Returns ``(U f32[C] on the device, (data_state, state))``; everything is
     enqueued, nothing synchronises (the MH solvers consume U on the device)."""
+    loader = getattr(full_data_map_fn, "loader", None)
+    if loader is not None and state is None and not has_state:
+      # the standard full_reference_data pass over an HBM-resident data set: all
+      # batches inside one C call (same arithmetic as the loop below)
+      return _full_in_one_call(sample, loader, full_data_map_fn.mb_size), (data_state, state)
     first = []
     total = DeviceArray.zeros((sample.n_chains,))
 

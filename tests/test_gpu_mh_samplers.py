@@ -210,3 +210,26 @@ def test_adaptive_step_size_through_sggmc(gpu):
   assert np.all(eps == eps[0]) and eps[0] != np.float32(0.05)
   ratio = np.ravel(res["samples"]["acceptance_ratio"])
   assert np.all((ratio >= 0) & (ratio <= 1))
+
+
+@pytest.mark.parametrize("C,d,N,mb,path", [(5, 8, 60, 16, "simt"), (64, 64, 1000, 128, "tc_parity"),
+                                           (3, 8, 64, 16, "simt")])
+def test_full_potential_one_call_equals_the_batch_loop(gpu, C, d, N, mb, path):
+  """sgmc_glm_full_potential (all batches inside one C call) against the generic
+  full_data_map loop of potential.full_potential: same bits; and the oracle."""
+  from jax_sgmc_b200 import data, glm, potential
+  from jax_sgmc_b200.tree_util import ChainTree
+  X, y, theta = _logistic_problem(C, d, N, seed=3)
+  loader = data.NumpyDataLoader(x=X, y=y)
+  prior, lik = glm.GaussianPrior(3.0), glm.LogisticRegression()
+  full = potential.full_potential(prior, lik, strategy="vmap", path=path, temperature=1.5)
+  init, map_fn, _ = data.full_reference_data(loader, 4, mb)
+  sample = ChainTree.from_trees([{"w": t} for t in theta])
+  fast, _ = full(sample, init(), map_fn)
+  loop_map = lambda *a, **k: map_fn(*a, **k)          # no .loader attribute: generic loop
+  slow, _ = full(sample, init(), loop_map)
+  assert np.array_equal(fast.numpy().view(np.uint32), slow.numpy().view(np.uint32))
+  o_full = osgmc.full_potential(osgmc.Logistic(d, 0), osgmc.Prior("gaussian", 0, d, 3.0), 1.5)
+  ids = np.arange(int(np.ceil(N / mb)) * mb).reshape(-1, mb)
+  batches = [(X[i % N], y[i % N], (i < N).astype(np.float32)) for i in ids]
+  np.testing.assert_allclose(fast.numpy(), o_full(theta, batches, N), rtol=2e-5)
