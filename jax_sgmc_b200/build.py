@@ -24,7 +24,8 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3",
     "-std=c++17", "-Xcompiler", "-fPIC",
     "--expt-relaxed-constexpr",
-] + ([f"-DSGMC_TC_BK={os.environ['SGMC_TC_BK']}"] if os.environ.get("SGMC_TC_BK") else [])
+] + ([f"-DSGMC_TC_BK={os.environ['SGMC_TC_BK']}"] if os.environ.get("SGMC_TC_BK") else []) \
+  + (["-DSGMC_TC_DEBUG"] if os.environ.get("SGMC_TC_DEBUG") else [])
 
 
 def _nvcc() -> str:

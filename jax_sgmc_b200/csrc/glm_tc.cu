@@ -49,13 +49,20 @@ constexpr int kTcWarps = kTcThreads / 32;
 constexpr int kTcFusedThreads = kTcThreads + 32;
 constexpr uint32_t kTmemCols = 256;
 
-// debug timers (globaltimer ns) of CTA 0: [start, setup done, mainloop done, end]
+// Phase timers (globaltimer ns) of CTA (0,0), thread 64 -- compiled in only with
+// -DSGMC_TC_DEBUG (SGMC_TC_DEBUG=1 python -m jax_sgmc_b200.build), read back with
+// sgmc_debug_tc_timers (tools/dbg_tc_timers.py, tools/dbg_fused_timers.py).
 __device__ unsigned long long g_tc_dbg[10];
+#ifdef SGMC_TC_DEBUG
 __device__ __forceinline__ unsigned long long gtime() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
   return t;
 }
+#define TC_DBG(cond, i) do { if (cond) g_tc_dbg[i] = gtime(); } while (0)
+#else
+#define TC_DBG(cond, i) do { } while (0)
+#endif
 
 // ---------------------------------------------------------------------------
 // PTX wrappers
@@ -278,7 +285,7 @@ k_glm_tc_gemm(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
   // block): accumulator columns [0,128) = features n0a.., [128,256) = n0b..
   const int n0a = blockIdx.x * (BN / 2), n0b = (int)gradp.half + n0a;
   Key* s_lk = reinterpret_cast<Key*>(s_y);         // EPI 2: per-row noise keys
-  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 64) g_tc_dbg[0] = gtime();
+  TC_DBG(blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 64, 0);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA0);
@@ -353,7 +360,7 @@ k_glm_tc_gemm(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
   const bool dbg = blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 64;
-  if (dbg) g_tc_dbg[1] = gtime();
+  TC_DBG(dbg, 1);
 
   float nzA[32], nzB[32];   // EPI 2: noise of (row q*32+r, feature n0a/n0b + cg*32 + lane)
   if (EPI == 2) {
@@ -425,7 +432,7 @@ k_glm_tc_gemm(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
           if (normal_is_tail(pb)) nzB[r] = normal_tail(pb);
         }
       }
-      if (dbg) g_tc_dbg[8] = gtime();
+      TC_DBG(dbg, 8);
     }
   } else if (warp == 0 && lane == 0) {
     // ===== TMA producer =====
@@ -508,7 +515,7 @@ k_glm_tc_gemm(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
   }
   mbar_wait(tmem_full_bar, 0);
   tc_fence_after();
-  if (dbg) g_tc_dbg[2] = gtime();
+  TC_DBG(dbg, 2);
   // All TMA writes have landed and all MMAs have read them: the pipeline smem
   // is free and becomes 16 private 32x33 f32 transpose buffers.
   float* stage = reinterpret_cast<float*>(tiles) + warp * (32 * 33);
@@ -526,7 +533,7 @@ k_glm_tc_gemm(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
       const int col0 = n0 + ct;
       uint32_t acc[32];
       tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)ct, acc);
-      if (dbg && c == 0) g_tc_dbg[4] = gtime();
+      TC_DBG(dbg && c == 0, 4);
       if (col0 >= link.n) continue;                      // warp-uniform
       float ellv[32];
       const bool full_cols = col0 + 32 <= link.n;        // warp-uniform
@@ -567,7 +574,7 @@ k_glm_tc_gemm(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
         }
       }
       __syncwarp();
-      if (dbg && c == 0) g_tc_dbg[5] = gtime();
+      TC_DBG(dbg && c == 0, 5);
       // coalesced R stores: two rows per instruction, two columns per lane
       const int64_t ro0 = (int64_t)(m0 + q * 32 + rsub) * link.n + col0 + csub;
       const bool full_tile = (m0 + q * 32 + 32 <= link.C) && (col0 + 32 <= link.n);
@@ -587,7 +594,7 @@ k_glm_tc_gemm(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
           }
         }
       }
-      if (dbg && c == 0) g_tc_dbg[6] = gtime();
+      TC_DBG(dbg && c == 0, 6);
       if (link.ell) {                                    // optional per-observation output
         __syncwarp();
 #pragma unroll
@@ -602,7 +609,7 @@ k_glm_tc_gemm(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
       }
       __syncwarp();
     }
-    if (dbg) g_tc_dbg[7] = gtime();
+    TC_DBG(dbg, 7);
     // per-row statistics of this warp's 64 columns -> smem -> combine 4 groups
     {
       float mean = 0.f, m2 = 0.f;
@@ -672,11 +679,11 @@ k_glm_tc_gemm(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
       const int p = (h ? n0b : n0a) + cg * 32 + lane;        // flat parameter index (w_off = 0)
       uint32_t acc[32];
       tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)ct, acc);
-      if (dbg && h == 0) g_tc_dbg[4] = gtime();
+      TC_DBG(dbg && h == 0, 4);
 #pragma unroll
       for (int j = 0; j < 32; ++j) stage[lane * 33 + j] = __uint_as_float(acc[j]) * inv_scale;
       __syncwarp();
-      if (dbg && h == 0) g_tc_dbg[5] = gtime();
+      TC_DBG(dbg && h == 0, 5);
       const float coef = (p >= gradp.prior_lo && p < gradp.prior_hi) ? gradp.prior_coef : 0.f;
       const int64_t o0 = (int64_t)row0 * gradp.P + p;
       float* tp = gradp.theta_rw + o0;
@@ -709,7 +716,7 @@ k_glm_tc_gemm(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
         }
       }
       __syncwarp();
-      if (dbg && h == 0) g_tc_dbg[6] = gtime();
+      TC_DBG(dbg && h == 0, 6);
     }
   } else {
     const float inv_scale = 1.0f / (gradp.r_scale * __ldg(gradp.xt_scale));
@@ -719,12 +726,12 @@ k_glm_tc_gemm(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
       const int col0 = n0 + ct;
       uint32_t acc[32];
       tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)ct, acc);
-      if (dbg && c == 0) g_tc_dbg[4] = gtime();
+      TC_DBG(dbg && c == 0, 4);
       if (col0 >= gradp.d) continue;
 #pragma unroll
       for (int j = 0; j < 32; ++j) stage[lane * 33 + j] = __uint_as_float(acc[j]) * inv_scale;
       __syncwarp();
-      if (dbg && c == 0) g_tc_dbg[5] = gtime();
+      TC_DBG(dbg && c == 0, 5);
       const int gcol = col0 + lane;
       const int p = gradp.w_off + gcol;
       const bool in_prior = p >= gradp.prior_lo && p < gradp.prior_hi;
@@ -756,15 +763,15 @@ k_glm_tc_gemm(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
         }
       }
       __syncwarp();
-      if (dbg && c == 0) g_tc_dbg[6] = gtime();
+      TC_DBG(dbg && c == 0, 6);
     }
   }
-  if (dbg) g_tc_dbg[7] = gtime();
+  TC_DBG(dbg, 7);
   }  // epilogue warps
   tc_fence_before();
   __syncthreads();
   if (warp == 2) tmem_dealloc(tmem_base, kTmemCols);
-  if (dbg) g_tc_dbg[3] = gtime();
+  TC_DBG(dbg, 3);
 }
 
 // ---------------------------------------------------------------------------

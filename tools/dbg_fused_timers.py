@@ -1,4 +1,5 @@
-"""Phase timers (globaltimer, CTA (0,0), thread 64) of the fused GEMM2 + update kernel."""
+"""(needs the debug build: SGMC_TC_DEBUG=1 python -c "import __graft_entry__ as g; g.build()")
+Phase timers (globaltimer, CTA (0,0), thread 64) of the fused GEMM2 + update kernel."""
 import ctypes as C
 import os
 import sys

@@ -1,3 +1,4 @@
+# needs the debug build: SGMC_TC_DEBUG=1 python -c "import __graft_entry__ as g; g.build()"
 import sys, ctypes as C, numpy as np
 sys.path.insert(0,'/root/repo')
 from jax_sgmc_b200 import device, ops, _lib
