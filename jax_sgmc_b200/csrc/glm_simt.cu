@@ -437,4 +437,80 @@ int sgmc_glm_sgld_step(void* stream, const sgmc_glm_spec* spec, float* theta, fl
                           step_size, temperature, temp_per_chain, prng_layout);
 }
 
+// K Langevin steps over minibatches that live in (pinned) HOST memory: the inner
+// loop of solver.mcmc (solver.py:152-160) with the reference's host data cache
+// (data/core.py:664-791) in native code.  Step k reads host batch k mod
+// host_batch_count = host_batches + that * stride floats, laid out [n][d] rows
+// followed by [n] labels.  A ring of n_slots device
+// buffers is filled by the copy stream n_slots - 1 batches ahead of the sampling
+// stream (events order reuse); every step's (U, var) rows are read back to
+// host_results[k] on the copy stream.  Nothing synchronises: the caller waits on
+// the two streams when it needs the results.
+int sgmc_glm_sgld_scan_host(void* stream, void* copy_stream, const sgmc_glm_spec* spec,
+                            float* theta, float* v, int64_t n_chains, int64_t P,
+                            const float* host_batches, int64_t host_batch_count,
+                            int64_t n_steps, int64_t batch_size,
+                            int64_t observation_count, float* device_slots, int n_slots,
+                            float* potential_variance, float* host_results, float* grad,
+                            uint32_t* keys_a, uint32_t* keys_b, const float* step_sizes,
+                            float temperature, float alpha, float lmbd, void* workspace,
+                            size_t workspace_bytes, int path, int prng_layout) {
+  SGMC_REQUIRE(spec && theta && host_batches && device_slots && potential_variance && grad &&
+               keys_a && keys_b && step_sizes, "null argument");
+  SGMC_REQUIRE(n_slots >= 2 && n_slots <= 8 && n_steps >= 0 && host_batch_count >= 1,
+               "2..8 slots, at least one host batch");
+  cudaStream_t ms = (cudaStream_t)stream, cs = (cudaStream_t)copy_stream;
+  const int64_t n = batch_size, d = spec->d, C = n_chains;
+  const size_t stride = (size_t)n * d + n;                 // floats per batch
+  cudaEvent_t copied[8], consumed[8], computed[2], read_back[2];
+  for (int i = 0; i < n_slots; ++i) {
+    if (check_cuda(cudaEventCreateWithFlags(&copied[i], cudaEventDisableTiming), "event") ||
+        check_cuda(cudaEventCreateWithFlags(&consumed[i], cudaEventDisableTiming), "event"))
+      return 1;
+    cudaEventRecord(consumed[i], ms);                      // all slots start free
+  }
+  for (int i = 0; i < 2; ++i) {
+    if (check_cuda(cudaEventCreateWithFlags(&computed[i], cudaEventDisableTiming), "event") ||
+        check_cuda(cudaEventCreateWithFlags(&read_back[i], cudaEventDisableTiming), "event"))
+      return 1;
+    cudaEventRecord(read_back[i], cs);
+  }
+  auto prefetch = [&](int64_t k) {
+    const int sl = (int)(k % n_slots);
+    cudaStreamWaitEvent(cs, consumed[sl], 0);
+    cudaMemcpyAsync(device_slots + sl * stride,
+                    host_batches + (k % host_batch_count) * stride, stride * 4,
+                    cudaMemcpyHostToDevice, cs);
+    cudaEventRecord(copied[sl], cs);
+  };
+  for (int64_t k = 0; k < n_steps && k < n_slots - 1; ++k) prefetch(k);
+  int rc = 0;
+  for (int64_t k = 0; k < n_steps && rc == 0; ++k) {
+    if (k + n_slots - 1 < n_steps) prefetch(k + n_slots - 1);
+    const int sl = (int)(k % n_slots);
+    float* Xb = device_slots + sl * stride;
+    float* uv = potential_variance + (k & 1) * 2 * C;      // (U, var) double-buffered
+    cudaStreamWaitEvent(ms, copied[sl], 0);
+    cudaStreamWaitEvent(ms, read_back[k & 1], 0);          // its previous contents are on the host
+    rc = sgmc_glm_sgld_step(ms, spec, theta, v, C, P, Xb, Xb + n * d, nullptr, nullptr, n,
+                            observation_count, uv, uv + C, grad, (k & 1) ? keys_b : keys_a,
+                            (k & 1) ? keys_a : keys_b, step_sizes[k], temperature, alpha, lmbd,
+                            workspace, workspace_bytes, path, prng_layout, 0, nullptr, nullptr,
+                            nullptr, 0);
+    cudaEventRecord(consumed[sl], ms);
+    if (host_results != nullptr) {
+      cudaEventRecord(computed[k & 1], ms);
+      cudaStreamWaitEvent(cs, computed[k & 1], 0);
+      cudaMemcpyAsync(host_results + k * 2 * C, uv, (size_t)2 * C * 4, cudaMemcpyDeviceToHost, cs);
+      cudaEventRecord(read_back[k & 1], cs);
+    }
+  }
+  // the sampling stream finishes after the last read-back was issued; events can go
+  // (destruction is deferred by the runtime until they have completed)
+  for (int i = 0; i < n_slots; ++i) { cudaEventDestroy(copied[i]); cudaEventDestroy(consumed[i]); }
+  for (int i = 0; i < 2; ++i) { cudaEventDestroy(computed[i]); cudaEventDestroy(read_back[i]); }
+  if (rc) return rc;
+  return check_cuda(cudaGetLastError(), "sgmc_glm_sgld_scan_host");
+}
+
 }  // extern "C"

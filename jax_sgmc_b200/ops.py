@@ -259,6 +259,25 @@ def glm_potential_grad_per_chain(spec, theta, X, y, idx, observation_count, pote
   return workspace
 
 
+def glm_sgld_scan_host(spec, theta, host_batches_ptr, host_batch_count, n_steps, batch_size,
+                       observation_count,
+                       device_slots, n_slots, potential_variance, host_results_ptr, grad,
+                       keys_a, keys_b, step_sizes, copy_stream, temperature=1.0, v=None,
+                       alpha=0.9, lmbd=1e-5, workspace=None, path=0, layout=0, stream=None):
+  """n_steps pSGLD / SGLD steps over minibatches in pinned host memory, one C call
+  (see sgmc_glm_sgld_scan_host).  ``host_batches_ptr`` / ``host_results_ptr`` are
+  addresses of page-locked buffers; ``step_sizes`` a float32 NumPy array."""
+  C_, P = theta.shape
+  ss = np.ascontiguousarray(step_sizes, np.float32)
+  assert ss.size >= n_steps
+  _lib.call("sgmc_glm_sgld_scan_host", _s(stream), copy_stream.handle, C.byref(spec),
+            vp(theta), vp(v), C_, P, C.c_void_p(host_batches_ptr), int(host_batch_count),
+            int(n_steps), int(batch_size), int(observation_count), vp(device_slots), int(n_slots),
+            vp(potential_variance), C.c_void_p(host_results_ptr), vp(grad), vp(keys_a),
+            vp(keys_b), ss.ctypes.data_as(C.c_void_p), float(temperature), float(alpha),
+            float(lmbd), vp(workspace), workspace.nbytes, PATH[path], _layout(layout))
+
+
 def glm_full_potential(spec, theta, X, y, observation_count, batch_size, potential,
                        scratch, wrap_idx, wrap_mask, workspace, path=0, stream=None):
   """potential.full_potential over the HBM-resident data set in one C call."""
