@@ -8,6 +8,7 @@ there is no CPU fallback for any of it.
 from __future__ import annotations
 
 import ctypes as C
+import math
 from typing import Optional, Sequence
 
 import numpy as np
@@ -107,7 +108,7 @@ class DeviceArray:
                owner=None):
     self.shape = tuple(int(s) for s in shape)
     self.dtype = np.dtype(dtype)
-    self.nbytes = int(np.prod(self.shape, dtype=np.int64)) * self.dtype.itemsize
+    self.nbytes = math.prod(self.shape) * self.dtype.itemsize
     if ptr is None:
       p = C.c_void_p()
       _lib.call("sgmc_malloc", C.byref(p), self.nbytes)
@@ -176,24 +177,24 @@ class DeviceArray:
   def reshape(self, *shape) -> "DeviceArray":
     if len(shape) == 1 and isinstance(shape[0], (tuple, list)):
       shape = tuple(shape[0])
-    n = int(np.prod(self.shape, dtype=np.int64))
+    n = math.prod(self.shape)
     shape = list(shape)
     if -1 in shape:
       k = shape.index(-1)
-      rest = int(np.prod([s for s in shape if s != -1], dtype=np.int64))
+      rest = math.prod(s for s in shape if s != -1)
       shape[k] = n // max(rest, 1)
-    assert int(np.prod(shape, dtype=np.int64)) == n, (shape, self.shape)
+    assert math.prod(shape) == n, (shape, self.shape)
     return DeviceArray(shape, self.dtype, ptr=self.ptr, owner=self)
 
   def row_slice(self, start: int, stop: int) -> "DeviceArray":
     """View of rows [start, stop) along the leading axis."""
-    row = int(np.prod(self.shape[1:], dtype=np.int64)) * self.dtype.itemsize
+    row = math.prod(self.shape[1:]) * self.dtype.itemsize
     return DeviceArray((stop - start,) + self.shape[1:], self.dtype,
                        ptr=self.ptr + start * row, owner=self)
 
   @property
   def size(self) -> int:
-    return int(np.prod(self.shape, dtype=np.int64))
+    return math.prod(self.shape)
 
   @property
   def ndim(self) -> int:

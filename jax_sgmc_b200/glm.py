@@ -63,8 +63,25 @@ class InvSigmaPrior(_Spec):
     self.leaf = log_sigma
 
 
+_SPEC_CACHE = {}
+
+
 def resolve(likelihood, prior, sample, temperature: float, x_absmax: float = 0.0):
-  """Build the C-ABI ``sgmc_glm_spec`` for a ChainTree layout."""
+  """Build the C-ABI ``sgmc_glm_spec`` for a ChainTree layout (cached per layout:
+  this runs once per sampling step)."""
+  key = (id(likelihood), id(prior), id(sample.treedef), tuple(sample.sizes),
+         float(temperature), float(x_absmax))
+  hit = _SPEC_CACHE.get(key)
+  if hit is not None and hit[0] is likelihood and hit[1] is prior and hit[3] is sample.treedef:
+    return hit[2]
+  spec = _resolve(likelihood, prior, sample, temperature, x_absmax)
+  if len(_SPEC_CACHE) > 256:
+    _SPEC_CACHE.clear()
+  _SPEC_CACHE[key] = (likelihood, prior, spec, sample.treedef)
+  return spec
+
+
+def _resolve(likelihood, prior, sample, temperature: float, x_absmax: float = 0.0):
   offs, sizes = sample.offsets(), sample.sizes
   wl = sample.leaf_index(likelihood.weights)
   d, w_off = sizes[wl], offs[wl]
