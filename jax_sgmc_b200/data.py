@@ -179,8 +179,9 @@ class NumpyDataLoader(DataLoader):
     return np.mod(idcs, N), mask
 
   def _draw_indices(self, chain):
-    sel = chain["rng"].choice(np.arange(0, self._observation_count),
-                              size=chain["mb_size"], replace=True)
+    # == rng.choice(np.arange(0, N), size=mb, replace=True) of numpy_loader.py:382-389,
+    # which draws exactly these integers (tests/test_host_logic.py pins the equality)
+    sel = chain["rng"].integers(0, self._observation_count, size=chain["mb_size"])
     return sel, np.ones(chain["mb_size"], dtype=np.bool_)
 
   def _shuffle_indices(self, chain):

@@ -199,3 +199,17 @@ def test_bench_reference_arm_prints_the_contract_line():
   assert line["config"]["workload"].startswith("C2")
   assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
   assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"]
+
+
+def test_host_index_draws_equal_the_reference_choice_call():
+  """NumpyDataLoader._draw_indices uses rng.integers; the reference calls
+  rng.choice(np.arange(0, N), size=mb, replace=True) (numpy_loader.py:382-389).
+  Same PCG64 stream, same integers."""
+  for seed in range(6):
+    for N in (2, 10, 1000, 54321):
+      for mb in (1, 10, 64):
+        a = np.random.default_rng(np.random.SeedSequence(seed).spawn(1)[0])
+        b = np.random.default_rng(np.random.SeedSequence(seed).spawn(1)[0])
+        for _ in range(4):
+          assert np.array_equal(a.choice(np.arange(0, N), size=mb, replace=True),
+                                b.integers(0, N, size=mb))
