@@ -44,3 +44,19 @@ def test_errors_are_reported_not_swallowed():
                             None, 0)
   assert rc != 0
   assert b"alias" in lib.sgmc_last_error() or b"n_leaves" in lib.sgmc_last_error()
+
+
+def test_binding_argument_counts_match_the_header():
+  """Every ctypes prototype has as many arguments as the declaration in
+  include/sgmc_b200.h (the binding is written by hand: guard against drift)."""
+  text = open(os.path.join(ROOT, "include", "sgmc_b200.h")).read()
+  text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+  decls = dict()
+  for name, args in re.findall(r"\b(sgmc_[a-z0-9_]+)\s*\(([^;{}]*?)\)\s*;", text, flags=re.S):
+    args = " ".join(args.split())
+    decls[name] = 0 if args in ("", "void") else args.count(",") + 1
+  protos = {**{k: v for k, v in _lib.PROTOTYPES.items()},
+            **{k: v[0] for k, v in _lib.SPECIAL.items()}}
+  assert set(protos) <= set(decls)
+  for name, argtypes in protos.items():
+    assert len(argtypes) == decls[name], (name, len(argtypes), decls[name])
