@@ -92,6 +92,10 @@ PROTOTYPES = {
     "sgmc_glm_sgld_scan_host": [_vp, _vp, C.POINTER(GlmSpec), _vp, _vp, _i64, _i64, _vp, _i64,
                                 _i64, _i64, _i64, _vp, _int, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _f32,
                                 _f32, _vp, _sz, _int, _int],
+    "sgmc_glm_sgld_scan_device": [_vp, C.POINTER(GlmSpec), _vp, _vp, _i64, _i64, _vp, _vp, _i64,
+                                  _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                  C.POINTER(_i64), _int, _vp, _vp, _vp, _i64, _vp, _vp, _i64,
+                                  C.POINTER(_i64), _f32, _f32, _vp, _sz, _int, _int],
     "sgmc_glm_full_potential": [_vp, C.POINTER(GlmSpec), _vp, _i64, _i64, _vp, _vp, _i64, _i64,
                                 _vp, _vp, _vp, _vp, _vp, _sz, _int],
     "sgmc_glm_sgld_step": [_vp, C.POINTER(GlmSpec), _vp, _vp, _i64, _i64, _vp, _vp, _vp,

@@ -513,4 +513,55 @@ int sgmc_glm_sgld_scan_host(void* stream, void* copy_stream, const sgmc_glm_spec
   return check_cuda(cudaGetLastError(), "sgmc_glm_sgld_scan_host");
 }
 
+// K Langevin steps over a data set resident in HBM, one C call: the lax.scan of
+// solver.mcmc (solver.py:152-160) with the draw of data/numpy_loader.py:128-141
+// (idx_all == NULL) or pre-drawn index rows (idx_all = device int32[K][n], the
+// host loader's cached index blocks), the step of integrator.py:860-922 and the
+// collection of io.py:696-713: after step k with keep[k] != 0 the sample and its
+// potential are copied to slot *kept of samples_out / scalars_out.
+int sgmc_glm_sgld_scan_device(void* stream, const sgmc_glm_spec* spec, float* theta, float* v,
+                              int64_t n_chains, int64_t P, const float* X, const float* y,
+                              int64_t observation_count, int64_t batch_size,
+                              uint32_t* data_key_a, uint32_t* data_key_b, int32_t* idx_buf,
+                              const int32_t* idx_all, float* potential, float* variance,
+                              float* grad, uint32_t* keys_a, uint32_t* keys_b,
+                              const int64_t* leaf_sizes, int n_leaves,
+                              const float* step_sizes, const float* temperatures,
+                              const uint8_t* keep, int64_t n_steps, float* samples_out,
+                              float* scalars_out, int64_t capacity, int64_t* kept,
+                              float alpha, float lmbd, void* workspace,
+                              size_t workspace_bytes, int path, int prng_layout) {
+  SGMC_REQUIRE(spec && theta && X && y && potential && grad && keys_a && keys_b && step_sizes &&
+               temperatures && kept, "null argument");
+  SGMC_REQUIRE(idx_all != nullptr || (data_key_a && data_key_b && idx_buf),
+               "device draws need the data keys and an index buffer");
+  cudaStream_t ms = (cudaStream_t)stream;
+  const int64_t C = n_chains, n = batch_size;
+  for (int64_t k = 0; k < n_steps; ++k) {
+    const int32_t* idx = idx_all ? idx_all + k * n : idx_buf;
+    if (!idx_all) {
+      if (int e = sgmc_minibatch_draw(stream, (k & 1) ? data_key_b : data_key_a,
+                                      (k & 1) ? data_key_a : data_key_b, idx_buf, n,
+                                      observation_count, prng_layout))
+        return e;
+    }
+    if (int e = sgmc_glm_sgld_step(stream, spec, theta, v, C, P, X, y, idx, nullptr, n,
+                                   observation_count, potential, variance, grad,
+                                   (k & 1) ? keys_b : keys_a, (k & 1) ? keys_a : keys_b,
+                                   step_sizes[k], temperatures[k], alpha, lmbd, workspace,
+                                   workspace_bytes, path, prng_layout, 0, nullptr, nullptr,
+                                   leaf_sizes, n_leaves))
+      return e;
+    if (keep && keep[k] && samples_out && *kept < capacity) {
+      if (check_cuda(cudaMemcpyAsync(samples_out + *kept * C * P, theta, (size_t)C * P * 4,
+                                     cudaMemcpyDeviceToDevice, ms), "collect") ||
+          check_cuda(cudaMemcpyAsync(scalars_out + *kept * C, potential, (size_t)C * 4,
+                                     cudaMemcpyDeviceToDevice, ms), "collect"))
+        return 1;
+      ++*kept;
+    }
+  }
+  return 0;
+}
+
 }  // extern "C"

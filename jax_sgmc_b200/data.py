@@ -319,6 +319,15 @@ def random_reference_data(data_loader: DataLoader, cached_batches_count: int,
       batch = BatchRef(data_loader, state.idx, mb_size)
       return (state, (batch, info)) if information else (state, batch)
 
+    def scan_source(state: CacheState, steps: int):
+      """What a native scan needs to draw the next ``steps`` minibatches itself."""
+      src = {"loader": data_loader, "n": mb_size, "N": N, "idx_all": None,
+             "key_a": state.keys[state.flip], "key_b": state.keys[1 - state.flip],
+             "idx_buf": state.idx}
+      state.flip = (state.flip + steps) % 2          # the keys ping-pong once per draw
+      return src
+
+    get_fn.scan_source = scan_source
     return init_fn, get_fn, lambda: None
 
   if isinstance(data_loader, StreamingNumpyDataLoader):
@@ -400,6 +409,24 @@ def random_reference_data(data_loader: DataLoader, cached_batches_count: int,
       state.line += 1
       return (state, (batch, info)) if information else (state, batch)
 
+    def scan_source(state: CacheState, steps: int):
+      """The index rows of the next ``steps`` minibatches (one chain): the rest of
+      the current cache block, then freshly drawn blocks -- the sequence get_fn
+      would hand out -- as one device array int32[steps][n]."""
+      if len(state.chain_ids) != 1:
+        return None                        # one index stream per chain: step loop
+      rows, need = [], steps
+      while need > 0:
+        if state.cache is None or state.line == state.cache_size:
+          _refill(state)
+        take = min(need, state.cache_size - state.line)
+        rows.append(state.host_cache[0, state.line:state.line + take])
+        state.line += take
+        need -= take
+      idx_all = DeviceArray.from_numpy(np.concatenate(rows).astype(np.int32))
+      return {"loader": data_loader, "n": mb_size, "N": N, "idx_all": idx_all}
+
+    get_fn.scan_source = scan_source
     return init_fn, get_fn, lambda: None
 
   raise TypeError("The DataLoader must inherit from HostDataLoader or "

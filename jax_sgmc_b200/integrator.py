@@ -220,6 +220,35 @@ def langevin_diffusion(potential_fn, batch_fn, adaption=None
                          model_state=new_model_state, potential=state.potential,
                          variance=state.variance)
 
+  def scan_fn(state: LangevinState, step_sizes, temperatures, keep, samples_out,
+              scalars_out, kept: int):
+    """len(step_sizes) update_fn steps + sample collection in one C call.
+    Returns ``(state, kept)`` or None when this configuration needs the step
+    loop (per-chain minibatches, streamed data, stateful models)."""
+    source_fn = getattr(batch_get, "scan_source", None)
+    if source_fn is None or state.model_state is not None:
+      return None
+    theta = state.latent_variables
+    steps = len(step_sizes)
+    source = source_fn(state.data_state, steps)
+    if source is None:
+      return None
+    grad_buf = scratch.get(id(theta.flat))
+    if grad_buf is None:
+      grad_buf = scratch[id(theta.flat)] = DeviceArray(theta.flat.shape, np.float32)
+    v, alpha, lmbd = None, 0.9, 1e-5
+    if adaption is not None:
+      v, alpha, lmbd = state.adapt_state.v.flat, state.adapt_state.alpha, \
+          state.adapt_state.lmbd
+    kept = potential_fn.sgld_scan(
+        theta, source, state.key.current, state.key.next, step_sizes, temperatures, keep,
+        samples_out, scalars_out, kept, v=v, alpha=alpha, lmbd=lmbd, grad_out=grad_buf,
+        U_out=state.potential, var_out=state.variance)
+    if steps % 2:
+      state.key.flip()
+    return state, kept
+
+  update_fn.scan = scan_fn
   return init_fn, update_fn, get_fn
 
 

@@ -278,6 +278,32 @@ def glm_sgld_scan_host(spec, theta, host_batches_ptr, host_batch_count, n_steps,
             float(lmbd), vp(workspace), workspace.nbytes, PATH[path], _layout(layout))
 
 
+def glm_sgld_scan_device(spec, theta, X, y, observation_count, batch_size, potential,
+                         variance, grad, keys_a, keys_b, leaf_sizes, step_sizes,
+                         temperatures, keep, samples_out, scalars_out, kept: int,
+                         data_key_a=None, data_key_b=None, idx_buf=None, idx_all=None, v=None,
+                         alpha=0.9, lmbd=1e-5, workspace=None, path=0, layout=0,
+                         stream=None) -> int:
+  """len(step_sizes) Langevin steps in one C call (see sgmc_glm_sgld_scan_device);
+  returns the new number of collected samples."""
+  C_, P = theta.shape
+  ss = np.ascontiguousarray(step_sizes, np.float32)
+  tt = np.ascontiguousarray(temperatures, np.float32)
+  kp = np.ascontiguousarray(keep, np.uint8)
+  assert ss.size == tt.size == kp.size
+  cnt = C.c_int64(int(kept))
+  cap = 0 if samples_out is None else samples_out.shape[0]
+  _lib.call("sgmc_glm_sgld_scan_device", _s(stream), C.byref(spec), vp(theta), vp(v), C_, P,
+            vp(X), vp(y), int(observation_count), int(batch_size), vp(data_key_a),
+            vp(data_key_b), vp(idx_buf), vp(idx_all), vp(potential), vp(variance), vp(grad),
+            vp(keys_a), vp(keys_b), i64_array(leaf_sizes), len(leaf_sizes),
+            ss.ctypes.data_as(C.c_void_p), tt.ctypes.data_as(C.c_void_p),
+            kp.ctypes.data_as(C.c_void_p), int(ss.size), vp(samples_out), vp(scalars_out),
+            int(cap), C.byref(cnt), float(alpha), float(lmbd), vp(workspace),
+            workspace.nbytes, PATH[path], _layout(layout))
+  return int(cnt.value)
+
+
 def glm_full_potential(spec, theta, X, y, observation_count, batch_size, potential,
                        scratch, wrap_idx, wrap_mask, workspace, path=0, stream=None):
   """potential.full_potential over the HBM-resident data set in one C call."""

@@ -132,6 +132,33 @@ class _PotentialFn:
         leaf_sizes=sample.sizes)
     return True
 
+  def sgld_scan(self, sample: ChainTree, source, keys_a, keys_b, step_sizes, temperatures,
+                keep, samples_out, scalars_out, kept: int, v=None, alpha=0.9, lmbd=1e-5,
+                grad_out=None, U_out=None, var_out=None) -> int:
+    """len(step_sizes) whole Langevin steps (draw, value_and_grad, update,
+    collection) in ONE C call (sgmc_glm_sgld_scan_device); ``source`` comes from
+    the data functional's ``scan_source``.  Returns the new sample count."""
+    loader, n, N = source["loader"], source["n"], source["N"]
+    spec = glm.resolve(self.likelihood, self.prior, sample, self.temperature,
+                       loader.absmax(self.likelihood.x))
+    C = sample.n_chains
+    path = _select_path(self.path, spec, C, n)
+    key = (C, sample.n_params, n, path)
+    buf = self._buffers.get(key)
+    if buf is None:
+      buf = {"U": DeviceArray((C,), np.float32), "var": DeviceArray((C,), np.float32),
+             "ws": ops.glm_workspace(C, n, spec.d, path), "ell": None}
+      self._buffers[key] = buf
+    return ops.glm_sgld_scan_device(
+        spec, sample.flat, loader.device_data[self.likelihood.x],
+        loader.device_data[self.likelihood.y], N, n,
+        U_out if U_out is not None else buf["U"],
+        var_out if var_out is not None else buf["var"], grad_out, keys_a, keys_b,
+        sample.sizes, step_sizes, temperatures, keep, samples_out, scalars_out, kept,
+        data_key_a=source.get("key_a"), data_key_b=source.get("key_b"),
+        idx_buf=source.get("idx_buf"), idx_all=source.get("idx_all"), v=v, alpha=alpha,
+        lmbd=lmbd, workspace=buf["ws"], path=path)
+
   def value_and_grad(self, sample: ChainTree, reference_data, state: Any = None,
                      mask=None, likelihoods: bool = False,
                      grad_out: Optional[DeviceArray] = None,

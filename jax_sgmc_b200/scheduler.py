@@ -23,6 +23,10 @@ scheduler_state = namedtuple("scheduler_state",
 static_information = namedtuple("static_information", ["samples_collected"])
 
 
+# specific schedulers whose state depends on solver statistics (no precomputation)
+_DYNAMIC = []
+
+
 def init_scheduler(step_size: specific_scheduler = None,
                    temperature: specific_scheduler = None,
                    burn_in: specific_scheduler = None,
@@ -79,6 +83,22 @@ def init_scheduler(step_size: specific_scheduler = None,
         burn_in=F32(burn_in.get(state.burn_in_state, it, **kw)),
         accept=bool(thinning.get(state.thinning_state, it, **kw)))
 
+  def precompute(state: scheduler_state, iterations: int):
+    """(step sizes f32[K], temperatures f32[K], keep bool[K]) of the next K
+    iterations when every specific scheduler is static -- what lets solver.mcmc
+    hand the whole scan to native code -- else None."""
+    parts = (step_size, temperature, burn_in, thinning)
+    if any(p is dyn for p in parts for dyn in _DYNAMIC):
+      return None
+    it0 = state.state[0]
+    its = range(it0, it0 + iterations)
+    eps = np.array([step_size.get(state.step_size_state, i) for i in its], F32)
+    tau = np.array([temperature.get(state.temperature_state, i) for i in its], F32)
+    keep = np.array([bool(burn_in.get(state.burn_in_state, i))
+                     and bool(thinning.get(state.thinning_state, i)) for i in its])
+    return eps, tau, keep
+
+  get_fn.precompute = precompute
   return init_fn, update_fn, get_fn
 
 
@@ -166,7 +186,9 @@ def adaptive_step_size(burn_in=0, initial_step_size=0.05, stabilization_constant
     del iteration, kw
     return F32(np.exp(state[1]))
 
-  return specific_scheduler(init_fn, update_fn, get_fn)
+  sched = specific_scheduler(init_fn, update_fn, get_fn)
+  _DYNAMIC.append(sched)
+  return sched
 
 
 def initial_burn_in(n: int = 0) -> specific_scheduler:

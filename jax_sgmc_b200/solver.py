@@ -44,6 +44,10 @@ def mcmc(solver, scheduler, strategy="map", saving=None, loading=None):
       saving_state = init_saving(solver_get(init_state),
                                  (init_state, scheduler_states), static_information)
       state = init_state
+      if schedulers is None and _native_scan(solver_update, scheduler_get, main_scheduler,
+                                            iterations, state, saving_state):
+        results.extend(postprocess_saving(saving_state, None))
+        continue
       for _ in range(iterations):                                   # solver.py:152-160
         schedules = [scheduler_get(s) for s in scheduler_states]    # :97-101
         state, stats = solver_update(state, *schedules)             # :102
@@ -56,6 +60,33 @@ def mcmc(solver, scheduler, strategy="map", saving=None, loading=None):
     return results
 
   return run
+
+
+def _native_scan(solver_update, scheduler_get, scheduler_state, iterations, state,
+                 saving_state) -> bool:
+  """Run the whole scan of solver.py:152-160 in native code when the solver has a
+  scan (sgmc over langevin_diffusion on a GLM potential), the schedules are
+  static and the samples go to the in-HBM buffer.  SGMC_NATIVE_SCAN=0 disables."""
+  import os
+  scan = getattr(solver_update, "scan", None)
+  precompute = getattr(scheduler_get, "precompute", None)
+  if scan is None or precompute is None or os.environ.get("SGMC_NATIVE_SCAN", "1") == "0":
+    return False
+  if not isinstance(saving_state, io._SavingState) or saving_state.ring is not None \
+      or saving_state.extra or saving_state.scalar_key != "likelihood":
+    return False
+  arrays = precompute(scheduler_state, iterations)
+  if arrays is None:
+    return False
+  eps, tau, keep = arrays
+  collect = saving_state.capacity > 0
+  out = scan(state, eps, tau, keep, saving_state.variables if collect else None,
+             saving_state.scalars if collect else None, saving_state.count)
+  if out is None:
+    return False
+  _, saving_state.count = out
+  saving_state.negate = True          # langevin.get_fn reports likelihood = -potential
+  return True
 
 
 def sgmc(integrator) -> Tuple[Callable, Callable, Callable]:
@@ -71,6 +102,7 @@ def sgmc(integrator) -> Tuple[Callable, Callable, Callable]:
   def get(state) -> Dict[str, Any]:
     return get_integrator(state)
 
+  update.scan = getattr(update_integrator, "scan", None)    # native scan, if any
   return init, update, get
 
 

@@ -231,3 +231,31 @@ def test_streaming_loader_equals_resident_loader(gpu):
   assert len(res) == 3 and res[2]["samples"]["variables"]["w"].shape == (10, 16)
   assert not np.array_equal(res[0]["samples"]["variables"]["w"],
                             res[1]["samples"]["variables"]["w"])
+
+
+@pytest.mark.parametrize("loader_kind,chains", [("device", 3), ("host", 1)])
+@pytest.mark.parametrize("rms", [True, False])
+def test_native_scan_equals_the_python_step_loop(gpu, monkeypatch, loader_kind, chains, rms):
+  """solver.mcmc hands the whole scan to sgmc_glm_sgld_scan_device when it can
+  (static schedules, langevin on a GLM potential, shared minibatches); the
+  samples must be those of the step-by-step loop, bit for bit -- burn in,
+  thinning, odd iteration counts, cache refills of the host loader included."""
+  from jax_sgmc_b200 import alias, data, glm, potential
+  X, y, _ = odata.logistic_dataset(300, 8, seed=7)
+  pot = potential.minibatch_potential(glm.GaussianPrior(4.0), glm.LogisticRegression(),
+                                      strategy="vmap")
+  init = [{"w": np.full(8, 0.05 * c, np.float32)} for c in range(chains)]
+  keys = np.stack([prng.PRNGKey(40 + c) for c in range(chains)])
+  out = []
+  for native in ("1", "0"):
+    monkeypatch.setenv("SGMC_NATIVE_SCAN", native)
+    cls = data.DeviceNumpyDataLoader if loader_kind == "device" else data.NumpyDataLoader
+    loader = cls(x=X, y=y)
+    run = alias.sgld(pot, loader, cache_size=1 if loader_kind == "device" else 7,
+                     batch_size=16, first_step_size=2e-2, last_step_size=2e-3, burn_in=11,
+                     accepted_samples=23, rms_prop=rms, progress_bar=False)
+    out.append(run(*init, iterations=77, keys=keys))
+  for a, b in zip(*out):
+    assert a["sample_count"] == b["sample_count"] == 23
+    assert np.array_equal(a["samples"]["variables"]["w"], b["samples"]["variables"]["w"])
+    assert np.array_equal(a["samples"]["likelihood"], b["samples"]["likelihood"])
