@@ -213,3 +213,62 @@ def test_host_index_draws_equal_the_reference_choice_call():
         for _ in range(4):
           assert np.array_equal(a.choice(np.arange(0, N), size=mb, replace=True),
                                 b.integers(0, N, size=mb))
+
+
+def _host_loader(n, d=2):
+  from jax_sgmc_b200 import data
+  x = np.arange(n * d, dtype=np.float32).reshape(n, d)
+  return data.StreamingNumpyDataLoader(x=x, y=np.arange(n, dtype=np.float32)), x
+
+
+def test_ordered_pipeline_walks_the_data_set_and_masks_the_overhang():
+  """tests/test_data.py:103-116, :229-253 (ordered batches): consecutive rows, the
+  last batch wraps modulo N with the overhang masked, then starts over."""
+  dl, _ = _host_loader(7)
+  c = dl.register_ordered_pipeline(cache_size=2, mb_size=3)
+  idx, mask = dl.get_indices(c)
+  assert idx.tolist() == [[0, 1, 2], [3, 4, 5]] and mask.all()
+  idx, mask = dl.get_indices(c)
+  assert idx.tolist() == [[6, 0, 1], [0, 1, 2]]
+  assert mask.tolist() == [[True, False, False], [True, True, True]]
+  assert dl.initializer_batch(3)["x"].shape == (3, 2) and dl.initializer_batch()["y"].shape == ()
+
+
+@pytest.mark.parametrize("shuffle,in_epochs", [(False, False), (True, False), (True, True)])
+def test_seeding_and_cache_size_independence(shuffle, in_epochs):
+  """tests/test_data.py:255-300: the same seed gives the same batches, chains get
+  different streams by default (seed = chain id), and the sequence of batches
+  does not depend on how many are cached per refill."""
+  def draws(cache, n_batches, **kw):
+    dl, _ = _host_loader(11)
+    c = dl.register_random_pipeline(cache_size=cache, mb_size=3, shuffle=shuffle,
+                                    in_epochs=in_epochs, **kw)
+    out = []
+    while len(out) < n_batches:
+      out.extend(dl.get_indices(c)[0].tolist())
+    return out[:n_batches]
+
+  assert draws(1, 12, seed=5) == draws(4, 12, seed=5) == draws(12, 12, seed=5)
+  assert draws(3, 6, seed=1) != draws(3, 6, seed=2)
+  dl, _ = _host_loader(11)
+  c0 = dl.register_random_pipeline(cache_size=2, mb_size=3, shuffle=shuffle, in_epochs=in_epochs)
+  c1 = dl.register_random_pipeline(cache_size=2, mb_size=3, shuffle=shuffle, in_epochs=in_epochs)
+  assert (c0, c1) == (0, 1)
+  assert dl.get_indices(c0)[0].tolist() != dl.get_indices(c1)[0].tolist()
+
+
+def test_loader_argument_validation():
+  """tests/test_data.py:399-423, :617-643."""
+  from jax_sgmc_b200 import data
+  with pytest.raises(AssertionError):
+    data.StreamingNumpyDataLoader()
+  with pytest.raises(AssertionError):
+    data.StreamingNumpyDataLoader(x=np.zeros((4, 2)), y=np.zeros(5))
+  dl, _ = _host_loader(6)
+  with pytest.raises(ValueError):
+    data.random_reference_data(dl, 0, 2)
+  with pytest.raises(ValueError):
+    data.random_reference_data(dl, 2, 0)
+  with pytest.raises(ValueError):
+    data.random_reference_data(dl, 1, 7)
+  assert dl.static_information == {"observation_count": 6}
