@@ -259,3 +259,29 @@ def test_native_scan_equals_the_python_step_loop(gpu, monkeypatch, loader_kind, 
     assert a["sample_count"] == b["sample_count"] == 23
     assert np.array_equal(a["samples"]["variables"]["w"], b["samples"]["variables"]["w"])
     assert np.array_equal(a["samples"]["likelihood"], b["samples"]["likelihood"])
+
+
+@pytest.mark.parametrize("iterations", [100, 1000])
+def test_random_thinning_respects_burn_in(gpu, iterations):
+  """tests/test_scheduler.py:125-160: with an arbitrary burn-in mask, exactly
+  `selections` iterations are accepted and none of them is subject to burn in;
+  iterations with larger step sizes are preferred (probability ~ step size)."""
+  from jax_sgmc_b200 import scheduler
+  accepted = (prng.uniform(prng.PRNGKey(0), (iterations,)) < 0.3)
+  nonzero = np.nonzero(accepted)[0]
+  burn_in = scheduler.specific_scheduler(lambda *a: (None, int(accepted.sum())),
+                                         lambda *a, **k: None,
+                                         lambda _, it, **k: bool(accepted[it]))
+  step_size = scheduler.polynomial_step_size(a=1.0, b=1.0, gamma=1.0)
+  selections = int(0.5 * nonzero.size)
+  thinning = scheduler.random_thinning(step_size_schedule=step_size, burn_in_schedule=burn_in,
+                                       selections=selections)
+  state, total = thinning.init(iterations)
+  chosen = [i for i in range(iterations) if thinning.get(state, i)]
+  assert total == selections and len(chosen) == selections
+  assert set(chosen) <= set(nonzero.tolist())
+  # step size ~ 1/(1+i): early eligible iterations are (much) more likely to be kept
+  assert np.mean(chosen) < np.mean(nonzero)
+  # deterministic (default key PRNGKey(0))
+  state2, _ = thinning.init(iterations)
+  assert [i for i in range(iterations) if thinning.get(state2, i)] == chosen
