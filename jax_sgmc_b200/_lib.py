@@ -156,6 +156,12 @@ def load() -> C.CDLL:
     fn.argtypes = argtypes
     fn.restype = restype
   _lib = lib
+  # SGMC_OPTIONS="4=1,5=256": process-wide sgmc_set_option calls for A/B runs of
+  # the tools and the benchmark (option numbers: include/sgmc_b200.h)
+  for item in filter(None, os.environ.get("SGMC_OPTIONS", "").split(",")):
+    k, v = item.split("=")
+    if lib.sgmc_set_option(int(k), int(v)) != 0:
+      raise SgmcError(f"SGMC_OPTIONS: bad option {item!r}")
   return lib
 
 

@@ -26,6 +26,7 @@
 #include "glm.cuh"
 #include "noise_pass.cuh"
 #include "sgld_math.cuh"
+#include "tc_ptx.cuh"
 
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -64,110 +65,8 @@ __device__ __forceinline__ unsigned long long gtime() {
 #define TC_DBG(cond, i) do { } while (0)
 #endif
 
-// ---------------------------------------------------------------------------
-// PTX wrappers
-// ---------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-  return (uint32_t)__cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
-               "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred P1;\n"
-      "WAIT_LOOP:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-      "@P1 bra WAIT_DONE;\n"
-      "bra WAIT_LOOP;\n"
-      "WAIT_DONE:\n"
-      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void fence_barrier_init() {
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() {
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-}
-__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map,
-                                            uint64_t* bar, int c_inner, int c_outer) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes "
-      "[%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(smem_dst)),
-      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c_inner), "r"(c_outer)
-      : "memory");
-}
-__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
-  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
-}
-__device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t cols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
-                   smem_u32(smem_dst)), "r"(cols) : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols)
-               : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() {
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-}
-__device__ __forceinline__ void tc_fence_after() {
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-}
-// D[tmem] (+)= A[smem] . B[smem]^T, kind::f16 (fp16 / bf16 operands, fp32 acc)
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
-                                         uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
-      "}\n" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// arrive on an mbarrier when all previously issued MMAs have completed
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::
-                   "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
-        "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
-        "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]),
-        "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]),
-        "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-      : "r"(taddr) : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-// K-major, 128B-swizzled operand tile (rows x 64 two-byte elements = rows x 128 B):
-// canonical layout Swizzle<3,4,3> o ((8,m),(8,2)):((8,SBO),(1,1)) in 16 B units,
-// SBO = 1024 B between 8-row groups, LBO = 1 (ignored), version 1 (sm_100),
-// layout type 2 (SWIZZLE_128B).  cute/arch/mma_sm100_desc.hpp SmemDescriptor.
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
-  d |= (uint64_t)1 << 16;
-  d |= (uint64_t)((8 * BK * 2) >> 4) << 32;            // SBO: 8 rows of BK*2 bytes
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)(BK == 64 ? 2 : 4) << 61;             // SWIZZLE_128B / SWIZZLE_64B
-  return d;
-}
-// kind::f16 instruction descriptor: fp32 accumulate, A/B format (0 fp16, 1 bf16),
-// both K-major, N>>3 at [17,23), M>>4 at [24,29).
-__host__ __device__ constexpr uint32_t make_idesc(int ab_format, int M, int N) {
-  return (1u << 4) | ((uint32_t)ab_format << 7) | ((uint32_t)ab_format << 10) |
-         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+  return make_smem_desc_k<BK>(smem_addr);
 }
 
 // ---------------------------------------------------------------------------
@@ -775,6 +674,433 @@ k_glm_tc_gemm(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
 }
 
 // ---------------------------------------------------------------------------
+// The fused, persistent potential kernel (the default tensor-core path).
+//
+// ONE launch evaluates both contractions of the stochastic potential:
+//   tiles [0, T1)        GEMM1  Z = Theta . Xb^T  -> link epilogue (ell stats, R)
+//   tiles [T1, T1 + T2)  GEMM2  G = R . Xb        -> gradient epilogue
+// One CTA per SM walks the tile list with stride gridDim.x (row-block-major, so
+// a GEMM2 tile only ever waits for GEMM1 tiles EARLIER in the list: a per-row-
+// block arrival counter, release / acquire + proxy fences, hands R from the
+// epilogue's st.global to the TMA loads of the consumer CTA).  Warp roles:
+//   warps 0..15   epilogue: tcgen05.ld one 32x32 sub-block -> link / gradient
+//                 math in registers -> 16-byte stores straight from registers
+//                 (a thread owns 32 consecutive columns of one row = whole
+//                 32-byte sectors, so no shared-memory transpose is needed)
+//   warp 16       TMA producer (one thread), 3-stage ring of 64-wide k-blocks
+//   warp 17       tcgen05.mma issuer (one thread) + TMEM allocator
+// The accumulator is double-buffered in TMEM (2 x BNF columns): the MMA warp
+// starts tile i+1 as soon as its operands land while the epilogue warps are
+// still busy with tile i, so the SFU-heavy link epilogue and the gradient
+// stores disappear behind the next mainloop; only the last tile's epilogue of
+// each CTA is exposed.
+// ---------------------------------------------------------------------------
+constexpr int kFuEpiWarps = 16;
+constexpr int kFuEpiThreads = kFuEpiWarps * 32;
+constexpr int kFuThreads = kFuEpiThreads + 64;
+constexpr int kFuPipeBytes = 196608;           // 192 KB of operand stages
+
+struct FusedMaps {
+  CUtensorMap a[2][2];    // [gemm][hi / lo]: Theta (GEMM1), R (GEMM2)
+  CUtensorMap b[2][2];    // [gemm][hi / lo]: Xb (GEMM1), XbT (GEMM2)
+};
+
+struct FusedSched {
+  int mt;                 // 128-row blocks
+  int nt1, nt2;           // column tiles of GEMM1 (over n) / GEMM2 (over d)
+  int kb1, kb2;           // 64-wide k-blocks of GEMM1 (over d) / GEMM2 (over n)
+  int tiles1, tiles_total;
+};
+
+template <int TERMS, int BNF>
+struct FuSmem {
+  static constexpr int kNA = TERMS == 3 ? 2 : 1;
+  static constexpr int kStageBytes = kNA * (BM * BK * 2) + kNA * (BNF * BK * 2);
+  static constexpr int kStages = kFuPipeBytes / kStageBytes;
+  static constexpr int kAuxBytes = 256 /*barriers, tmem ptr, flags*/ + 2 * 3 * BNF * 4;
+  static constexpr int kBytes = kFuPipeBytes + kAuxBytes + 1024 /*alignment slack*/;
+  static_assert(kStages >= 2 && 2 * kStages + 4 <= 24, "barrier block is 256 bytes");
+};
+
+__device__ __forceinline__ uint32_t pack_half2(float a, float b) {
+  const __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+template <int TERMS, int ABFMT, int BNF>
+__global__ void __launch_bounds__(kFuThreads, 1)
+k_glm_tc_fused(const __grid_constant__ FusedMaps maps, const FusedSched sch,
+               const TcLinkEpi link, const TcGradEpi gradp) {
+  using S = FuSmem<TERMS, BNF>;
+  static_assert(BNF == 128 || BNF == 256, "tile width");
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(
+      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* tiles = smem;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kFuPipeBytes);
+  uint64_t* empty_bar = full_bar + S::kStages;
+  uint64_t* acc_full = empty_bar + S::kStages;      // [2]
+  uint64_t* acc_empty = acc_full + 2;               // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + kFuPipeBytes + 224);
+  int* s_last = reinterpret_cast<int*>(tmem_ptr + 1);   // [2]
+  float* s_col = reinterpret_cast<float*>(smem + kFuPipeBytes + 256);   // [2][3][BNF]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool have2 = sch.tiles_total > sch.tiles1;
+  if (warp == kFuEpiWarps && lane == 0) {
+    tma_prefetch_desc(&maps.a[0][0]);
+    tma_prefetch_desc(&maps.b[0][0]);
+    if (TERMS == 3) {
+      tma_prefetch_desc(&maps.a[0][1]);
+      tma_prefetch_desc(&maps.b[0][1]);
+    }
+    if (have2) {
+      tma_prefetch_desc(&maps.a[1][0]);
+      tma_prefetch_desc(&maps.b[1][0]);
+      if (TERMS == 3) {
+        tma_prefetch_desc(&maps.a[1][1]);
+        tma_prefetch_desc(&maps.b[1][1]);
+      }
+    }
+  }
+  if (warp == kFuEpiWarps + 1) {
+    if (lane == 0) {
+      for (int s = 0; s < S::kStages; ++s) {
+        mbar_init(&full_bar[s], 1);
+        mbar_init(&empty_bar[s], 1);
+      }
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&acc_full[i], 1);
+        mbar_init(&acc_empty[i], kFuEpiWarps);
+      }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_ptr, 2 * BNF);
+  }
+  // Everything above overlaps the previous kernel's tail (programmatic dependent launch).
+  pdl_launch_dependents();
+  pdl_wait();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == kFuEpiWarps) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      uint32_t kbg = 0;
+      for (int t = blockIdx.x; t < sch.tiles_total; t += gridDim.x) {
+        const int g2 = t >= sch.tiles1 ? 1 : 0;
+        const int tt = g2 ? t - sch.tiles1 : t;
+        const int ntl = g2 ? sch.nt2 : sch.nt1;
+        const int rb = tt / ntl, tn = tt - rb * ntl;
+        const int m0 = rb * BM, n0 = tn * BNF;
+        const int kbs = g2 ? sch.kb2 : sch.kb1;
+        if (g2) {
+          // every R tile of this row block has been stored (GEMM1 epilogues of
+          // tiles earlier in the list, possibly on other SMs)
+          while (ld_acquire_gpu(&link.counters[rb]) < (uint32_t)sch.nt1) __nanosleep(40);
+          fence_proxy_async_global();
+        }
+        for (int kb = 0; kb < kbs; ++kb, ++kbg) {
+          const int s = kbg % S::kStages;
+          const uint32_t ph = (kbg / S::kStages) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          uint8_t* st = tiles + s * S::kStageBytes;
+          mbar_expect_tx(&full_bar[s], S::kStageBytes);
+          tma_load_2d(st, &maps.a[g2][0], &full_bar[s], kb * BK, m0);
+          if (TERMS == 3) tma_load_2d(st + BM * BK * 2, &maps.a[g2][1], &full_bar[s], kb * BK, m0);
+          uint8_t* sb = st + S::kNA * BM * BK * 2;
+          tma_load_2d(sb, &maps.b[g2][0], &full_bar[s], kb * BK, n0);
+          if (TERMS == 3) tma_load_2d(sb + BNF * BK * 2, &maps.b[g2][1], &full_bar[s], kb * BK, n0);
+        }
+      }
+    }
+  } else if (warp == kFuEpiWarps + 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(ABFMT, BM, BNF);
+      uint32_t kbg = 0, it = 0;
+      for (int t = blockIdx.x; t < sch.tiles_total; t += gridDim.x, ++it) {
+        const int kbs = t >= sch.tiles1 ? sch.kb2 : sch.kb1;
+        const uint32_t par = it & 1, aph = (it >> 1) & 1;
+        mbar_wait(&acc_empty[par], aph ^ 1);        // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + par * BNF;
+        for (int kb = 0; kb < kbs; ++kb, ++kbg) {
+          const int s = kbg % S::kStages;
+          const uint32_t ph = (kbg / S::kStages) & 1;
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t a0 = smem_u32(tiles + s * S::kStageBytes);
+          const uint32_t a1 = a0 + BM * BK * 2;
+          const uint32_t b0 = a0 + S::kNA * BM * BK * 2;
+          const uint32_t b1 = b0 + BNF * BK * 2;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t da0 = make_smem_desc(a0 + k * 32), db0 = make_smem_desc(b0 + k * 32);
+            if (TERMS == 3) {
+              const uint64_t da1 = make_smem_desc(a1 + k * 32), db1 = make_smem_desc(b1 + k * 32);
+              umma_f16(d_tmem, da1, db0, idesc, (kb | k) != 0);   // lo*hi
+              umma_f16(d_tmem, da0, db1, idesc, 1);               // hi*lo
+              umma_f16(d_tmem, da0, db0, idesc, 1);               // hi*hi
+            } else {
+              umma_f16(d_tmem, da0, db0, idesc, (kb | k) != 0);
+            }
+          }
+          umma_commit(&empty_bar[s]);       // frees the smem stage when the MMAs retire
+        }
+        umma_commit(&acc_full[par]);        // accumulator complete
+      }
+    }
+  } else {
+    // ===== epilogue warps =====
+    const int q = warp & 3;                          // TMEM lane quarter
+    const int cg = warp >> 2;                        // column group: BNF / 4 columns
+    constexpr int kChunks = BNF / 128;               // 32-column chunks per warp and tile
+    const int parts = sch.nt1 * (BNF / 32);
+    uint32_t it = 0;
+    for (int t = blockIdx.x; t < sch.tiles_total; t += gridDim.x, ++it) {
+      const int g2 = t >= sch.tiles1 ? 1 : 0;
+      const int tt = g2 ? t - sch.tiles1 : t;
+      const int ntl = g2 ? sch.nt2 : sch.nt1;
+      const int rb = tt / ntl, tn = tt - rb * ntl;
+      const int m0 = rb * BM, n0 = tn * BNF;
+      const uint32_t par = it & 1, aph = (it >> 1) & 1;
+      const int row = m0 + q * 32 + lane;            // this thread's accumulator row
+      const uint32_t tmem_row = tmem_base + par * BNF + ((uint32_t)(q * 32) << 16);
+
+      if (!g2) {
+        // ---- link epilogue: z -> ell statistics, R = cot * mask * dl/dz (fp16 hi/lo) ----
+        float* cy = s_col + par * 3 * BNF;
+        float* cm = cy + BNF;
+        float* crm = cm + BNF;
+        if ((int)threadIdx.x < BNF) {                // per-column observation data of this tile
+          const int col = n0 + threadIdx.x;
+          float yv = 0.f, mv = 0.f;
+          if (col < link.n) {
+            yv = link.y[link.idx ? link.idx[col] : col];
+            mv = link.mask ? link.mask[col] : 1.0f;
+          }
+          cy[threadIdx.x] = yv;
+          cm[threadIdx.x] = mv;
+          crm[threadIdx.x] = link.cot * mv * link.r_scale;
+        }
+        const bool row_ok = row < link.C;
+        const float inv = row_ok ? 1.0f / (link.row_scale[row] * __ldg(link.b_scale)) : 0.f;
+        named_bar_sync(1, kFuEpiThreads);
+        mbar_wait(&acc_full[par], aph);
+        tc_fence_after();
+#pragma unroll 1
+        for (int ch = 0; ch < kChunks; ++ch) {
+          const int ct = cg * (BNF / 4) + ch * 32;   // column inside the tile
+          const int col0 = n0 + ct;
+          uint32_t acc[32];
+          tmem_ld32(tmem_row + (uint32_t)ct, acc);
+          if (ch == kChunks - 1) {                   // accumulator drained: hand it back
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[par]);
+          }
+          float cnt = 0.f, shift = 0.f, s1 = 0.f, s2 = 0.f, sm = 0.f;
+          if (col0 < link.n) {                       // warp-uniform
+            const bool full_cols = col0 + 32 <= link.n;
+            float ellv[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float z = __uint_as_float(acc[j]) * inv;
+              float l, dz;
+              logistic_link_fast(z, cy[ct + j], l, dz);
+              ellv[j] = l;
+              acc[j] = __float_as_uint(dz * crm[ct + j]);
+            }
+            if (full_cols) {
+              shift = ellv[0];
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const float dl = ellv[j] - shift;
+                s1 += dl;
+                s2 = fmaf(dl, dl, s2);
+                sm = fmaf(ellv[j], cm[ct + j], sm);
+              }
+              cnt = 32.f;
+            } else {
+              shift = ellv[0];
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                if (col0 + j < link.n) {
+                  const float dl = ellv[j] - shift;
+                  cnt += 1.f; s1 += dl; s2 = fmaf(dl, dl, s2); sm = fmaf(ellv[j], cm[ct + j], sm);
+                }
+              }
+            }
+            if (row_ok) {
+              // R stores straight from registers: 8 columns = 16 bytes per store,
+              // a thread covers whole 32-byte sectors of its row
+              const int64_t ro = (int64_t)row * link.n + col0;
+#pragma unroll
+              for (int k8 = 0; k8 < 4; ++k8) {
+                if (full_cols || col0 + k8 * 8 + 8 <= link.n) {   // n % 8 == 0: groups never straddle
+                  const float* v = reinterpret_cast<const float*>(acc) + k8 * 8;
+                  if (TERMS == 3) {
+                    uint4 hi, lo;
+                    uint32_t* hp = reinterpret_cast<uint32_t*>(&hi);
+                    uint32_t* lp = reinterpret_cast<uint32_t*>(&lo);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                      const __half2 h = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
+                      const float2 hf = __half22float2(h);
+                      hp[e] = *reinterpret_cast<const uint32_t*>(&h);
+                      lp[e] = pack_half2(v[2 * e] - hf.x, v[2 * e + 1] - hf.y);
+                    }
+                    *reinterpret_cast<uint4*>(link.r_hi + ro + k8 * 8) = hi;
+                    *reinterpret_cast<uint4*>(link.r_lo + ro + k8 * 8) = lo;
+                  } else {
+                    uint4 b;
+                    uint32_t* bp = reinterpret_cast<uint32_t*>(&b);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                      const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
+                      bp[e] = *reinterpret_cast<const uint32_t*>(&h);
+                    }
+                    *reinterpret_cast<uint4*>(link.r_bf + ro + k8 * 8) = b;
+                  }
+                }
+              }
+              if (link.ell) {                        // optional per-observation output
+                float* ep = link.ell + (int64_t)row * link.n + col0;
+#pragma unroll
+                for (int k4 = 0; k4 < 8; ++k4)
+                  if (full_cols || col0 + k4 * 4 + 4 <= link.n)
+                    *reinterpret_cast<float4*>(ep + k4 * 4) =
+                        make_float4(ellv[4 * k4], ellv[4 * k4 + 1], ellv[4 * k4 + 2], ellv[4 * k4 + 3]);
+              }
+            }
+          }
+          if (row_ok) {
+            // partial statistics of this (row, 32-column chunk), combined in fixed
+            // order by the CTA that completes the row block last
+            float mean = 0.f, m2 = 0.f;
+            if (cnt > 0.f) {
+              mean = shift + s1 / cnt;
+              m2 = fmaxf(s2 - s1 * s1 / cnt, 0.f);
+            }
+            const int part = tn * (BNF / 32) + cg * kChunks + ch;
+            *reinterpret_cast<float4*>(link.stats + ((int64_t)row * parts + part) * kStatFields) =
+                make_float4(cnt, mean, m2, sm);
+          }
+        }
+        // publish: R + stats of this tile are visible (also to TMA) before the counter moves
+        __threadfence();
+        fence_proxy_async_global();
+        if (warp < 4) {
+          named_bar_sync(2, kFuEpiThreads);
+          if (threadIdx.x == 0) {
+            const uint32_t prev = atom_add_release_gpu(&link.counters[rb], 1u);
+            s_last[par] = prev == (uint32_t)sch.nt1 - 1u;
+          }
+          named_bar_sync(3, 128);
+          if (s_last[par]) {
+            // last tile of the row block: U = (L - prior)/T (potential.py:183-185, :210)
+            // and var(ell) (integrator.py:880) from the partials, Chan et al. in fixed order
+            __threadfence();
+            const int c = m0 + threadIdx.x;
+            if (c < link.C) {
+              float n_t = 0.f, mean_t = 0.f, m2_t = 0.f, sm_t = 0.f;
+              const float4* sp = reinterpret_cast<const float4*>(
+                  link.stats + (int64_t)c * parts * kStatFields);
+              for (int g0 = 0; g0 < parts; g0 += 8) {
+                float4 stv[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u)
+                  stv[u] = g0 + u < parts ? __ldcg(sp + g0 + u) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                  const float4 st = stv[u];
+                  if (st.x > 0.f) {
+                    const float nn = n_t + st.x, delta = st.y - mean_t;
+                    mean_t += delta * (st.x / nn);
+                    m2_t += st.z + delta * delta * (n_t * st.x / nn);
+                    n_t = nn;
+                  }
+                  sm_t += st.w;
+                }
+              }
+              const float L = link.mask ? (-link.n_obs / (float)link.n) * sm_t : -link.n_obs * mean_t;
+              const float prior = -link.prior_half_inv * link.row_sumsq[c];
+              link.potential[c] = (L - prior) * link.inv_temperature;
+              if (link.variance) link.variance[c] = m2_t / (float)link.n;
+            }
+          }
+        } else {
+          named_bar_arrive(2, kFuEpiThreads);
+        }
+      } else {
+        // ---- gradient epilogue: G * 1/scale + theta * prior_coef -> grad ----
+        const float inv_scale = 1.0f / (gradp.r_scale * __ldg(gradp.xt_scale));
+        const bool row_ok = row < gradp.C;
+#pragma unroll 1
+        for (int ch = 0; ch < kChunks; ++ch) {
+          const int ct = cg * (BNF / 4) + ch * 32;
+          const int col0 = n0 + ct;
+          const int p0 = gradp.w_off + col0;
+          const bool cols_any = col0 < gradp.d;
+          const bool has_prior = cols_any && p0 < gradp.prior_hi && p0 + 32 > gradp.prior_lo;
+          // the prior-gradient operand does not depend on the accumulator: fetch the
+          // thread's 128-byte line of theta while the tensor pipe is still busy
+          float4 th[8];
+          if (has_prior && row_ok) {
+            const float* tp = gradp.theta + (int64_t)row * gradp.P + p0;
+#pragma unroll
+            for (int k4 = 0; k4 < 8; ++k4)
+              th[k4] = col0 + k4 * 4 + 4 <= gradp.d ? __ldg(reinterpret_cast<const float4*>(tp) + k4)
+                                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+          } else {
+#pragma unroll
+            for (int k4 = 0; k4 < 8; ++k4) th[k4] = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+          if (ch == 0) {
+            mbar_wait(&acc_full[par], aph);
+            tc_fence_after();
+          }
+          uint32_t acc[32];
+          tmem_ld32(tmem_row + (uint32_t)ct, acc);
+          if (ch == kChunks - 1) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[par]);
+          }
+          if (cols_any && row_ok) {
+            float* gp = gradp.grad + (int64_t)row * gradp.P + p0;
+            const bool all_prior = p0 >= gradp.prior_lo && p0 + 32 <= gradp.prior_hi;
+#pragma unroll
+            for (int k4 = 0; k4 < 8; ++k4) {
+              if (col0 + k4 * 4 + 4 <= gradp.d) {       // d % 8 == 0: groups never straddle
+                const float tv[4] = {th[k4].x, th[k4].y, th[k4].z, th[k4].w};
+                float o[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const int p = p0 + k4 * 4 + e;
+                  const float coef = (all_prior || (p >= gradp.prior_lo && p < gradp.prior_hi))
+                                         ? gradp.prior_coef : 0.f;
+                  o[e] = fmaf(tv[e], coef, __uint_as_float(acc[k4 * 4 + e]) * inv_scale);
+                }
+                *reinterpret_cast<float4*>(gp + k4 * 4) = make_float4(o[0], o[1], o[2], o[3]);
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kFuEpiWarps + 1) tmem_dealloc(tmem_base, 2 * BNF);
+}
+
+// ---------------------------------------------------------------------------
 // Operand preparation / finalisation kernels
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ float pow2_scale_for(float absmax) {
@@ -1047,7 +1373,9 @@ static size_t carve(TcWorkspace* w, uint8_t* base, int64_t C, int64_t n, int64_t
     off += align256(bytes);
     return p;
   };
-  const int64_t parts = (n + BN - 1) / BN;
+  // per-(row, 32-column chunk) likelihood partials of the fused kernel (tiles of up to
+  // 256 columns, so n is padded to the next multiple of 256)
+  const int64_t parts = ((n + 255) / 256) * 8;
   void* th_hi = take((size_t)C * d * 2);
   void* th_lo = take((size_t)C * d * 2);
   void* rs = take((size_t)C * 4);
@@ -1132,6 +1460,25 @@ static int launch_gemm(cudaStream_t stream, const CUtensorMap& a0, const CUtenso
   }
   launch_pdl(kfn, grid, dim3(EPI == 2 ? kTcFusedThreads : kTcThreads), S::kBytes, stream, a0, a1, b0, b1,
              (int)((K + BK - 1) / BK), link, gradp, job);
+  return post_launch(name);
+}
+
+template <int TERMS, int ABFMT, int BNF>
+static int launch_fused(cudaStream_t stream, const FusedMaps& maps, const FusedSched& sch,
+                        const TcLinkEpi& link, const TcGradEpi& gradp, const char* name) {
+  using S = FuSmem<TERMS, BNF>;
+  auto kfn = k_glm_tc_fused<TERMS, ABFMT, BNF>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (check_cuda(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        S::kBytes), "cudaFuncSetAttribute"))
+      return 1;
+    attr_set = true;
+  }
+  // one CTA per SM (192 KB of stages): every CTA of the grid is resident, which the
+  // row-block hand-over between GEMM1 and GEMM2 tiles relies on
+  const int grid = std::min(sm_count(), sch.tiles_total);
+  launch_pdl(kfn, dim3(grid), dim3(kFuThreads), S::kBytes, stream, maps, sch, link, gradp);
   return post_launch(name);
 }
 
@@ -1231,7 +1578,46 @@ int glm_tc(cudaStream_t stream, const GlmArgs& a, int path) {
     job2.tile0 = tiles / 2; job2.tile_end = tiles;
   }
 
+  // ---- default: both contractions in one persistent launch -----------------------
+  const bool legacy = option(SGMC_OPT_TC_LEGACY) || epilogue_update || noise_job ||
+                      ((reinterpret_cast<uintptr_t>(a.theta) | reinterpret_cast<uintptr_t>(a.grad) |
+                        reinterpret_cast<uintptr_t>(link.ell)) & 15u) != 0;
+  if (!legacy) {
+    const int bnf = option(SGMC_OPT_TC_TILE_N) == 256 ? 256 : 128;
+    FusedMaps maps;
+    FusedSched sch;
+    sch.mt = (int)((C + BM - 1) / BM);
+    sch.nt1 = (int)((n + bnf - 1) / bnf);
+    sch.nt2 = a.grad ? (d + bnf - 1) / bnf : 0;
+    sch.kb1 = (d + BK - 1) / BK;
+    sch.kb2 = (int)((n + BK - 1) / BK);
+    sch.tiles1 = sch.mt * sch.nt1;
+    sch.tiles_total = sch.tiles1 + sch.mt * sch.nt2;
+    if (make_map(&maps.a[0][0], w.th_hi, !split, C, d, BM)) return 2;
+    if (make_map(&maps.b[0][0], w.xb_hi, !split, n, d, bnf)) return 2;
+    if (make_map(&maps.a[1][0], w.r_hi, !split, C, n, BM)) return 2;
+    if (make_map(&maps.b[1][0], w.xt_hi, !split, d, n, bnf)) return 2;
+    if (split) {
+      if (make_map(&maps.a[0][1], w.th_lo, 0, C, d, BM)) return 2;
+      if (make_map(&maps.b[0][1], w.xb_lo, 0, n, d, bnf)) return 2;
+      if (make_map(&maps.a[1][1], w.r_lo, 0, C, n, BM)) return 2;
+      if (make_map(&maps.b[1][1], w.xt_lo, 0, d, n, bnf)) return 2;
+    } else {
+      maps.a[0][1] = maps.a[0][0]; maps.b[0][1] = maps.b[0][0];
+      maps.a[1][1] = maps.a[1][0]; maps.b[1][1] = maps.b[1][0];
+    }
+    if (split) {
+      if (bnf == 256) return launch_fused<3, 0, 256>(stream, maps, sch, link, gradp,
+                                                     "k_glm_tc_fused<split,256>");
+      return launch_fused<3, 0, 128>(stream, maps, sch, link, gradp, "k_glm_tc_fused<split,128>");
+    }
+    if (bnf == 256) return launch_fused<1, 1, 256>(stream, maps, sch, link, gradp,
+                                                   "k_glm_tc_fused<bf16,256>");
+    return launch_fused<1, 1, 128>(stream, maps, sch, link, gradp, "k_glm_tc_fused<bf16,128>");
+  }
+
   CUtensorMap mA0, mA1, mB0, mB1;
+  // ---- legacy two-kernel sequence (SGMC_OPT_TC_LEGACY, the opt-in fused-update modes) ----
   // ---- GEMM1: Z[C,n] = Theta[C,d] . Xb[n,d]^T ------------------------------
   if (make_map(&mA0, w.th_hi, !split, C, d, BM)) return 2;
   if (make_map(&mB0, w.xb_hi, !split, n, d, BN)) return 2;

@@ -400,6 +400,8 @@ OPT_EXACT_UPDATE_MATH = 0
 OPT_SERIAL_LAUNCH = 1      # 1: disable programmatic dependent launch
 OPT_FUSED_STEP_EPILOGUE = 2  # 1: glm_sgld_step updates inside the gradient GEMM's epilogue
 OPT_STEP_NOISE_IN_GEMM = 3   # 1: glm_sgld_step generates the noise in the GEMMs' idle warps
+OPT_TC_LEGACY = 4            # 1: round-1 kernel sequence instead of the persistent fused potential kernel
+OPT_TC_TILE_N = 5            # tile width of the persistent kernel: 128 (default) or 256
 
 
 def set_option(option: int, value: int):
