@@ -2,6 +2,7 @@
 #pragma once
 #include "common.cuh"
 #include "glm_math.cuh"
+#include "sgld_split.cuh"
 
 namespace sgmc {
 
@@ -18,6 +19,17 @@ struct FusedSgld {
   int layout;
   bool write_grad;
   bool* applied;
+};
+
+// sgmc_glm_sgld_step with SGMC_STEP_CARRY*: Theta's tensor-core operand form travels
+// from one step's update to the next step's potential inside the workspace.
+struct CarryCtx {
+  int mode;                 // 1: first step of a carried sequence, 2: carried
+  const uint32_t* keys_in;  // chain keys of this step (noise-key cache)
+  uint32_t* keys_out;
+  int prng_layout;
+  bool active;              // set by glm_tc when the carried path was taken
+  SgldSplitOut out;         // filled by glm_tc: what this step's update must write
 };
 
 struct GlmArgs {
@@ -39,6 +51,7 @@ struct GlmArgs {
   bool ell_requested;     // the caller passed an ell output buffer
   float* tc_ws;           // extra scratch of the tensor-core path
   FusedSgld fused;
+  CarryCtx* carry;        // null: stateless operand preparation
 };
 
 // -(d prior / d theta_p) / T for flat parameter index p of chain c.

@@ -277,7 +277,8 @@ static int glm_dispatch(void* stream, const sgmc_glm_spec* spec, const float* th
                         const int32_t* idx, const float* mask, int64_t batch_size,
                         int64_t observation_count, float* potential, float* variance,
                         float* grad, float* ell, void* workspace, size_t workspace_bytes,
-                        int path, const FusedSgld& fused, int64_t idx_stride = 0) {
+                        int path, const FusedSgld& fused, int64_t idx_stride = 0,
+                        CarryCtx* carry = nullptr) {
   SGMC_REQUIRE(spec && theta && X && y && potential, "null argument");
   SGMC_REQUIRE(spec->family == kFamilyGaussian || spec->family == kFamilyLogistic,
                "unknown GLM family %d", spec->family);
@@ -307,6 +308,7 @@ static int glm_dispatch(void* stream, const sgmc_glm_spec* spec, const float* th
   a.ell_requested = ell != nullptr;
   a.tc_ws = ws + 2 * (size_t)n_chains * batch_size;
   a.fused = fused;
+  a.carry = carry;
   // cotangent of every ell_i: (1/T) * (-N) / n    (potential.py:183,210)
   a.cot = (-(float)observation_count / (float)batch_size) / spec->temperature;
   if (path == 0) return glm_simt((cudaStream_t)stream, a);
@@ -403,7 +405,7 @@ int sgmc_glm_sgld_step(void* stream, const sgmc_glm_spec* spec, float* theta, fl
                        float step_size, float temperature, float alpha, float lmbd,
                        void* workspace, size_t workspace_bytes, int path, int prng_layout,
                        int write_grad, const float* temp_per_chain, void* wait_event,
-                       const int64_t* leaf_sizes, int n_leaves) {
+                       const int64_t* leaf_sizes, int n_leaves, int flags) {
   SGMC_REQUIRE(grad && keys_in && keys_out, "null argument");
   const int64_t whole = P;
   if (leaf_sizes == nullptr) {       // the sample is one leaf
@@ -419,15 +421,25 @@ int sgmc_glm_sgld_step(void* stream, const sgmc_glm_spec* spec, float* theta, fl
   fu.theta_rw = theta; fu.v = v; fu.keys_in = keys_in; fu.keys_out = keys_out;
   fu.step_size = step_size; fu.temperature = temperature; fu.alpha = alpha; fu.lmbd = lmbd;
   fu.layout = prng_layout; fu.applied = &applied; fu.write_grad = write_grad != 0;
+  CarryCtx cc{};
+  if ((flags & (SGMC_STEP_CARRY_INIT | SGMC_STEP_CARRY)) && path != 0 && n_leaves == 1) {
+    cc.mode = (flags & SGMC_STEP_CARRY_INIT) ? 1 : 2;
+    cc.keys_in = keys_in; cc.keys_out = keys_out; cc.prng_layout = prng_layout;
+  }
   if (int e = glm_dispatch(stream, spec, theta, n_chains, P, X, y, idx, mask, batch_size,
                            observation_count, potential, variance, grad, nullptr, workspace,
-                           workspace_bytes, path, fu))
+                           workspace_bytes, path, fu, 0, cc.mode ? &cc : nullptr))
     return e;
   if (applied) return 0;
   if (wait_event != nullptr &&
       check_cuda(cudaStreamWaitEvent((cudaStream_t)stream, (cudaEvent_t)wait_event, 0),
                  "cudaStreamWaitEvent"))
     return 1;
+  if (cc.active && write_grad) cc.out.grad_rw = grad;   // hand the completed gradient out
+  if (cc.active)   // the update also writes Theta's operand form for the next step
+    return sgld_update_split((cudaStream_t)stream, theta, v, grad, keys_in, keys_out, n_chains, P,
+                             step_size, temperature, temp_per_chain, alpha, lmbd, prng_layout,
+                             cc.out);
   // the stand-alone fused noise + update kernel
   if (v)
     return sgmc_sgld_rms_update(stream, theta, v, grad, keys_in, keys_out, n_chains, leaf_sizes,
@@ -496,7 +508,7 @@ int sgmc_glm_sgld_scan_host(void* stream, void* copy_stream, const sgmc_glm_spec
                             observation_count, uv, uv + C, grad, (k & 1) ? keys_b : keys_a,
                             (k & 1) ? keys_a : keys_b, step_sizes[k], temperature, alpha, lmbd,
                             workspace, workspace_bytes, path, prng_layout, 0, nullptr, nullptr,
-                            nullptr, 0);
+                            nullptr, 0, k == 0 ? SGMC_STEP_CARRY_INIT : SGMC_STEP_CARRY);
     cudaEventRecord(consumed[sl], ms);
     if (host_results != nullptr) {
       cudaEventRecord(computed[k & 1], ms);
@@ -550,7 +562,8 @@ int sgmc_glm_sgld_scan_device(void* stream, const sgmc_glm_spec* spec, float* th
                                    (k & 1) ? keys_b : keys_a, (k & 1) ? keys_a : keys_b,
                                    step_sizes[k], temperatures[k], alpha, lmbd, workspace,
                                    workspace_bytes, path, prng_layout, 0, nullptr, nullptr,
-                                   leaf_sizes, n_leaves))
+                                   leaf_sizes, n_leaves,
+                                   k == 0 ? SGMC_STEP_CARRY_INIT : SGMC_STEP_CARRY))
       return e;
     if (keep && keep[k] && samples_out && *kept < capacity) {
       if (check_cuda(cudaMemcpyAsync(samples_out + *kept * C * P, theta, (size_t)C * P * 4,

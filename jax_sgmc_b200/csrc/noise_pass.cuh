@@ -22,6 +22,8 @@
 #include "common.cuh"
 #include "rng.cuh"
 
+#include <type_traits>
+
 namespace sgmc {
 
 constexpr int kNoiseThreads = 512;
@@ -45,6 +47,8 @@ enum KeyMode : int {
   kKeySplit2 = 1,   // key', sub = split(key); noise = sub; keys_out = key'
   kKeySplit3A = 2,  // key', s1, s2 = split(key,3); noise = s1; keys_out = key'
   kKeySplit3B = 3,  // noise = s2; nothing written
+  kKeyCached = 4,   // keys_in = u32[C][L][2] per-(chain, leaf) NOISE keys derived by an
+                    // earlier kernel of the step (k_prepare_all); nothing written
 };
 
 int build_leaf_table(LeafTable* t, const int64_t* leaf_sizes, int n_leaves,
@@ -110,9 +114,16 @@ __device__ __forceinline__ void group_noise(Key lk, uint32_t j0, uint32_t half,
 //     float apply_one(int64_t i, float noise, int64_t chain, uint32_t e) const;
 //     void reduce(int64_t chain, float warp_sum) const;         // lane 0 only
 //     static constexpr bool kReduce;
+//     static constexpr bool kSplit;   // optional: apply_vec also returns |max| and
+//                                     // reduce2(chain, tile_in_chain, sum, max) is called
 //   };
 // eA/eB/e are element offsets inside the chain (for per-parameter vectors such
 // as mass or friction).
+template <class Op, class = void>
+struct OpSplits { static constexpr bool value = false; };
+template <class Op>
+struct OpSplits<Op, std::enable_if_t<Op::kSplit>> { static constexpr bool value = true; };
+
 template <int LAYOUT, class Op>
 __global__ void __launch_bounds__(kNoiseThreads, 2)
 k_noise_pass(const __grid_constant__ LeafTable tab,
@@ -132,6 +143,14 @@ k_noise_pass(const __grid_constant__ LeafTable tab,
 
   // ---- prologue: per-(chain, leaf) noise keys --------------------------
   const int n_threads = blockDim.x, n_warps = n_threads >> 5;
+  if (key_mode == kKeyCached) {
+    // the noise keys were derived by an earlier kernel of the step: one coalesced load
+    const uint2* ck = reinterpret_cast<const uint2*>(keys_in) + c_lo * L;
+    for (int idx = threadIdx.x; idx < n_ch * L; idx += n_threads) {
+      const uint2 k = ck[idx];
+      s_keys[idx] = Key{k.x, k.y};
+    }
+  } else
   for (int idx = threadIdx.x; idx < n_ch * L; idx += n_threads) {
     const int ci = idx / L, l = idx - ci * L;
     const int64_t c = c_lo + ci;
@@ -171,6 +190,7 @@ k_noise_pass(const __grid_constant__ LeafTable tab,
     while (lt >= tpc) { lt -= tpc; ++c; }
     const uint32_t g = lt * 32u + lane;
     float partial = 0.0f;
+    float amax = 0.0f;
     if (g < tab.groups) {
       int l = 0;
       while (l + 1 < L && g >= tab.gstart[l + 1]) ++l;
@@ -185,7 +205,10 @@ k_noise_pass(const __grid_constant__ LeafTable tab,
         typename Op::Regs r;
         op.load_vec(r, base + j0, base + half + j0);   // loads first ...
         group_noise<LAYOUT, true>(lk, j0, half, size, nA, nB);  // ... then ALU work
-        partial = op.apply_vec(r, nA, nB, base + j0, base + half + j0, c, eA, eB);
+        if constexpr (OpSplits<Op>::value)
+          partial = op.apply_vec2(r, nA, nB, base + j0, base + half + j0, c, eA, eB, amax);
+        else
+          partial = op.apply_vec(r, nA, nB, base + j0, base + half + j0, c, eA, eB);
       } else {
         group_noise<LAYOUT>(lk, j0, half, size, nA, nB);
 #pragma unroll
@@ -198,7 +221,14 @@ k_noise_pass(const __grid_constant__ LeafTable tab,
         }
       }
     }
-    if (Op::kReduce) {
+    if constexpr (OpSplits<Op>::value) {
+#pragma unroll
+      for (int s = 16; s > 0; s >>= 1) {
+        partial += __shfl_xor_sync(0xffffffffu, partial, s);
+        amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, s));
+      }
+      if (lane == 0) op.reduce2(c, lt, partial, amax);
+    } else if (Op::kReduce) {
 #pragma unroll
       for (int s = 16; s > 0; s >>= 1)
         partial += __shfl_xor_sync(0xffffffffu, partial, s);

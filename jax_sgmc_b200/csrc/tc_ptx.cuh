@@ -138,6 +138,116 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   tmem_ld_wait();
 }
 
+// ---- CTA pairs (cta_group::2): two SMs of one TPC run one MMA of M = 256 --------------
+// In the shared::cluster window the peer CTA's copy of a shared-memory object
+// differs from the local address in bit 24 only; clearing it addresses the
+// even (leader) CTA of the pair.
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+template <int CG>
+__device__ __forceinline__ void tmem_alloc_cg(uint32_t* smem_dst, uint32_t cols) {
+  if (CG == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(smem_dst)), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  } else {
+    tmem_alloc(smem_dst, cols);
+  }
+}
+template <int CG>
+__device__ __forceinline__ void tmem_dealloc_cg(uint32_t taddr, uint32_t cols) {
+  if (CG == 2)
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols)
+                 : "memory");
+  else
+    tmem_dealloc(taddr, cols);
+}
+// TMA load issued by either CTA of a pair: the bytes land in the issuing CTA's
+// shared memory, the transaction count is credited to the LEADER's mbarrier.
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* map,
+                                                 uint64_t* bar, int c_inner, int c_outer) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c_inner),
+      "r"(c_outer)
+      : "memory");
+}
+template <int CG>
+__device__ __forceinline__ void umma_f16_cg(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
+                                            uint32_t idesc, uint32_t accumulate) {
+  if (CG == 2) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    umma_f16(tmem_d, desc_a, desc_b, idesc, accumulate);
+  }
+}
+// Arrive on the mbarrier at this shared-memory offset in BOTH CTAs of the pair once
+// all previously issued MMAs have completed.
+template <int CG>
+__device__ __forceinline__ void umma_commit_cg(uint64_t* bar) {
+  if (CG == 2) {
+    const uint16_t mask = 3;
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 "
+        "[%0], %1;" ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+  } else {
+    umma_commit(bar);
+  }
+}
+// arrive (release at cluster scope) on the LEADER CTA's copy of `bar`
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(
+                   smem_u32(bar) & kPeerBitMask) : "memory");
+}
+// wait with acquire at cluster scope (the arrivals may come from the peer CTA)
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+// ---- TMA stores (shared -> global), bulk async-groups ----------------------------
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* smem_src,
+                                             int c_inner, int c_outer) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+          reinterpret_cast<uint64_t>(map)), "r"(smem_u32(smem_src)), "r"(c_inner), "r"(c_outer)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() {
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+// the shared-memory sources of all committed bulk groups have been read
+__device__ __forceinline__ void bulk_wait_read_all() {
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+// all committed bulk groups have completed (their global writes are performed)
+__device__ __forceinline__ void bulk_wait_all() {
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
 // K-major, swizzled operand tile (rows x BKE two-byte elements): canonical
 // layout Swizzle<3,4,3> o ((8,m),(8,2)):((8,SBO),(1,1)) in 16 B units for
 // BKE = 64 (128-byte swizzle span), the 64-byte variant for BKE = 32;

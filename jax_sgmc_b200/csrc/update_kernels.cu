@@ -14,6 +14,10 @@
 // SGHMC step 20, OBABO pass A 20 + pass B 12.
 #include "noise_pass.cuh"
 #include "sgld_math.cuh"
+#include "sgld_split.cuh"
+
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include <cmath>
 
@@ -202,6 +206,111 @@ struct SgldOp {
     return 0.f;
   }
   __device__ void reduce(int64_t, float) const {}
+};
+
+// ---- SGLD / pSGLD that also emits the tensor-core operand of the NEXT potential ----
+// sgmc_glm_sgld_step in carried mode: the GLM potential's GEMM1 consumes Theta as
+// fp16 hi/lo (or bf16) K-major rows.  The update has theta' in registers, so it
+// writes that split itself (scale[c] = a power of two chosen from the row's
+// previous |max|; k_prepare_all validates it against the new |max| and only
+// re-splits rows that left the safe window) together with the row statistics the
+// potential needs: |max| (atomicMax on the bit pattern) and the per-warp-tile
+// sum of squares over the gaussian-prior range (combined in fixed order by
+// k_prepare_all, so the potential stays run-to-run deterministic).  This removes
+// the Theta pass of k_prepare_all (16.8 MB read + 16.8 MB written at C2) from
+// every step.
+template <bool RMS, bool FAST, int FMT>
+struct SgldSplitOp : SgldOp<RMS, FAST> {
+  using Base = SgldOp<RMS, FAST>;
+  using Regs = typename Base::Regs;
+  static constexpr bool kSplit = true;
+  void* th_hi;                 // fp16 (FMT 1) or bf16 (FMT 2) [C][P]
+  __half* th_lo;               // fp16 [C][P] (FMT 1)
+  const float* scale;          // f32[C]
+  uint32_t* amax_bits;         // u32[C]
+  float* sumsq_part;           // f32[C][tiles_per_chain]
+  uint32_t tiles_per_chain;
+  uint32_t prior_lo, prior_hi; // element range of the gaussian prior (empty: lo == hi)
+  float prior_coef;            // != 0: `grad` lacks the prior term theta * coef (added here)
+  float* grad_rw;              // completed gradient written back (or null)
+
+  // g + theta * coef on the prior range: the same fmaf the gradient epilogue of the
+  // potential kernel applies when it adds the prior itself
+  __device__ __forceinline__ float4 with_prior(const float4& g, const float4& t, uint32_t e) const {
+    float4 o = g;
+    if (e >= prior_lo && e + 4u <= prior_hi) {
+      o.x = fmaf(t.x, prior_coef, g.x); o.y = fmaf(t.y, prior_coef, g.y);
+      o.z = fmaf(t.z, prior_coef, g.z); o.w = fmaf(t.w, prior_coef, g.w);
+    } else {
+      if (e >= prior_lo && e < prior_hi) o.x = fmaf(t.x, prior_coef, g.x);
+      if (e + 1u >= prior_lo && e + 1u < prior_hi) o.y = fmaf(t.y, prior_coef, g.y);
+      if (e + 2u >= prior_lo && e + 2u < prior_hi) o.z = fmaf(t.z, prior_coef, g.z);
+      if (e + 3u >= prior_lo && e + 3u < prior_hi) o.w = fmaf(t.w, prior_coef, g.w);
+    }
+    return o;
+  }
+  __device__ __forceinline__ void emit4(int64_t i, const float4& t, float s) const {
+    const float v0 = t.x * s, v1 = t.y * s, v2 = t.z * s, v3 = t.w * s;
+    if (FMT == 1) {
+      const __half2 h01 = __floats2half2_rn(v0, v1), h23 = __floats2half2_rn(v2, v3);
+      const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+      const __half2 l01 = __floats2half2_rn(v0 - f01.x, v1 - f01.y);
+      const __half2 l23 = __floats2half2_rn(v2 - f23.x, v3 - f23.y);
+      uint2 ph, pl;
+      ph.x = *reinterpret_cast<const uint32_t*>(&h01); ph.y = *reinterpret_cast<const uint32_t*>(&h23);
+      pl.x = *reinterpret_cast<const uint32_t*>(&l01); pl.y = *reinterpret_cast<const uint32_t*>(&l23);
+      *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(th_hi) + i) = ph;
+      *reinterpret_cast<uint2*>(th_lo + i) = pl;
+    } else {
+      const __nv_bfloat162 b01 = __floats2bfloat162_rn(v0, v1), b23 = __floats2bfloat162_rn(v2, v3);
+      uint2 pb;
+      pb.x = *reinterpret_cast<const uint32_t*>(&b01); pb.y = *reinterpret_cast<const uint32_t*>(&b23);
+      *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(th_hi) + i) = pb;
+    }
+  }
+  __device__ __forceinline__ float sq4(const float4& t, uint32_t e, float& amax) const {
+    amax = fmaxf(fmaxf(amax, fmaxf(fabsf(t.x), fabsf(t.y))), fmaxf(fabsf(t.z), fabsf(t.w)));
+    if (e >= prior_lo && e + 4u <= prior_hi)
+      return (t.x * t.x + t.y * t.y) + (t.z * t.z + t.w * t.w);
+    float q = 0.f;
+    if (e >= prior_lo && e < prior_hi) q = fmaf(t.x, t.x, q);
+    if (e + 1u >= prior_lo && e + 1u < prior_hi) q = fmaf(t.y, t.y, q);
+    if (e + 2u >= prior_lo && e + 2u < prior_hi) q = fmaf(t.z, t.z, q);
+    if (e + 3u >= prior_lo && e + 3u < prior_hi) q = fmaf(t.w, t.w, q);
+    return q;
+  }
+  __device__ float apply_vec2(Regs& r, const float nA[4], const float nB[4], int64_t iA,
+                              int64_t iB, int64_t c, uint32_t eA, uint32_t eB,
+                              float& amax) const {
+    const float ns = Base::scale_for(c);
+    float va[4] = {r.vA.x, r.vA.y, r.vA.z, r.vA.w};
+    float vb[4] = {r.vB.x, r.vB.y, r.vB.z, r.vB.w};
+    if (prior_coef != 0.f) {
+      r.gA = with_prior(r.gA, r.tA, eA);
+      r.gB = with_prior(r.gB, r.tB, eB);
+      if (grad_rw) {
+        st4(grad_rw, iA, r.gA);
+        st4(grad_rw, iB, r.gB);
+      }
+    }
+    float4 oA, oB;
+    SGMC_F4_MAP(oA, Base::one(f4get(r.tA, k), f4get(r.gA, k), va[k], nA[k], ns));
+    SGMC_F4_MAP(oB, Base::one(f4get(r.tB, k), f4get(r.gB, k), vb[k], nB[k], ns));
+    st4(Base::theta, iA, oA);
+    st4(Base::theta, iB, oB);
+    if (RMS) {
+      st4(Base::v, iA, make_float4(va[0], va[1], va[2], va[3]));
+      st4(Base::v, iB, make_float4(vb[0], vb[1], vb[2], vb[3]));
+    }
+    const float s = FMT == 1 ? __ldg(scale + c) : 1.0f;
+    emit4(iA, oA, s);
+    emit4(iB, oB, s);
+    return sq4(oA, eA, amax) + sq4(oB, eB, amax);
+  }
+  __device__ void reduce2(int64_t c, uint32_t tile_in_chain, float sum, float amax) const {
+    sumsq_part[c * tiles_per_chain + tile_in_chain] = sum;
+    atomicMax(amax_bits + c, __float_as_uint(amax));   // amax >= 0: uint order == float order
+  }
 };
 
 // ---- SGHMC ------------------------------------------------------------------
@@ -557,6 +666,64 @@ static int sgld_common(void* stream, float* theta, float* v, const float* grad,
                            n_chains, kKeySplit2, prng_layout, op,
                            "sgmc_sgld_update");
 }
+
+}  // extern "C"
+
+namespace sgmc {
+
+template <bool RMS, bool FAST, int FMT>
+static int launch_split(cudaStream_t stream, const LeafTable& tab, const uint32_t* keys_in,
+                        uint32_t* keys_out, int64_t C, int key_mode, int layout,
+                        const SgldOp<RMS, FAST>& base, const SgldSplitOut& so) {
+  SgldSplitOp<RMS, FAST, FMT> op;
+  static_cast<SgldOp<RMS, FAST>&>(op) = base;
+  op.th_hi = so.th_hi; op.th_lo = reinterpret_cast<__half*>(so.th_lo);
+  op.scale = so.scale; op.amax_bits = so.amax_bits; op.sumsq_part = so.sumsq_part;
+  op.tiles_per_chain = tab.tiles_per_chain;
+  op.prior_lo = (uint32_t)so.prior_lo; op.prior_hi = (uint32_t)so.prior_hi;
+  op.prior_coef = so.prior_coef; op.grad_rw = so.grad_rw;
+  return launch_noise_pass(stream, tab, keys_in, keys_out, C, key_mode, layout, op,
+                           "sgmc_sgld_update<split>");
+}
+
+int sgld_split_tiles_per_chain(int64_t P) { return (int)(((P / 2 + 3) / 4 + 31) / 32); }
+
+int sgld_update_split(cudaStream_t stream, float* theta, float* v, const float* grad,
+                      const uint32_t* keys_in, uint32_t* keys_out, int64_t n_chains, int64_t P,
+                      float step_size, float temperature, const float* temp_per_chain,
+                      float alpha, float lmbd, int prng_layout, const SgldSplitOut& so) {
+  SGMC_REQUIRE(so.fmt == 1 || so.fmt == 2, "unknown split format");
+  SGMC_REQUIRE(P % 8 == 0, "split update needs P %% 8 == 0");
+  LeafTable tab;
+  const int64_t sizes[1] = {P};
+  if (int e = build_leaf_table(&tab, sizes, 1, n_chains,
+                               aligned16({theta, v, grad, so.th_hi, so.th_lo}))) return e;
+  SGMC_REQUIRE(tab.vec_ok[0], "split update needs 16-byte aligned buffers");
+  const float eps = step_size;
+  const float ns = sqrtf((2.0f * temperature) * eps);
+  const bool rms = v != nullptr;
+  const int key_mode = so.noise_keys ? kKeyCached : kKeySplit2;
+  const uint32_t* kin = so.noise_keys ? so.noise_keys : keys_in;
+  uint32_t* kout = so.noise_keys ? nullptr : keys_out;
+#define SGMC_SPLIT_CASE(R, F)                                                              \
+  {                                                                                        \
+    SgldOp<R, F> base{theta, v, grad, temp_per_chain, eps, -eps, ns, alpha, 1.0f - alpha,   \
+                      lmbd};                                                               \
+    if (so.fmt == 1)                                                                       \
+      return launch_split<R, F, 1>(stream, tab, kin, kout, n_chains, key_mode, prng_layout, \
+                                   base, so);                                              \
+    return launch_split<R, F, 2>(stream, tab, kin, kout, n_chains, key_mode, prng_layout,   \
+                                 base, so);                                                \
+  }
+  if (rms && option(SGMC_OPT_EXACT_UPDATE_MATH)) SGMC_SPLIT_CASE(true, false)
+  if (rms) SGMC_SPLIT_CASE(true, true)
+  SGMC_SPLIT_CASE(false, false)
+#undef SGMC_SPLIT_CASE
+}
+
+}  // namespace sgmc
+
+extern "C" {
 
 int sgmc_sgld_update(void* stream, float* theta, const float* grad,
                      const uint32_t* keys_in, uint32_t* keys_out,

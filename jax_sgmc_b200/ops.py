@@ -317,7 +317,7 @@ def glm_sgld_step(spec, theta, X, y, idx, observation_count, potential, variance
                   grad, keys_in, keys_out, step_size, temperature=1.0, v=None,
                   alpha=0.9, lmbd=1e-5, mask=None, workspace=None, path=0,
                   batch_size=None, layout=0, write_grad=True, temp_per_chain=None,
-                  wait_event=None, leaf_sizes=None, stream=None):
+                  wait_event=None, leaf_sizes=None, stream=None, carry=0):
   """One langevin_diffusion step on the GLM potential: potential / variance /
   gradient at the current theta, then the SGLD (v None) or pSGLD update in
   place -- inside the gradient GEMM's epilogue when the shapes allow."""
@@ -334,7 +334,7 @@ def glm_sgld_step(spec, theta, X, y, idx, observation_count, potential, variance
             1 if write_grad else 0, vp(temp_per_chain),
             None if wait_event is None else wait_event.handle,
             None if leaf_sizes is None else i64_array(leaf_sizes),
-            0 if leaf_sizes is None else len(leaf_sizes))
+            0 if leaf_sizes is None else len(leaf_sizes), int(carry))
   return workspace
 
 
@@ -400,8 +400,9 @@ OPT_EXACT_UPDATE_MATH = 0
 OPT_SERIAL_LAUNCH = 1      # 1: disable programmatic dependent launch
 OPT_FUSED_STEP_EPILOGUE = 2  # 1: glm_sgld_step updates inside the gradient GEMM's epilogue
 OPT_STEP_NOISE_IN_GEMM = 3   # 1: glm_sgld_step generates the noise in the GEMMs' idle warps
+STEP_CARRY_INIT, STEP_CARRY = 1, 2   # glm_sgld_step(carry=...): see sgmc_glm_sgld_step
 OPT_TC_LEGACY = 4            # 1: round-1 kernel sequence instead of the persistent fused potential kernel
-OPT_TC_TILE_N = 5            # tile width of the persistent kernel: 128 (default) or 256
+OPT_TC_CTA_GROUP = 5         # 2 (default): tcgen05 cta_group::2 on CTA pairs; 1: single CTAs
 
 
 def set_option(option: int, value: int):

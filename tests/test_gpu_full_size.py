@@ -132,11 +132,9 @@ def test_c2_full_step_keys_rows_determinism(c2):
                            np.zeros(len(rows), np.float32), np.ones(len(rows), np.float32))
   want = osgmc.langevin_update(st, lambda th: pot(th, (c2["Xb"], c2["yb"]), N), [d], 1e-3, 1.0)
   scale = np.abs(want.theta).max(axis=1, keepdims=True)
-  # RMSprop divides by sqrt(v') ~ |g|: where |g| is small the 1e-5-of-row-scale
-  # gradient error of the tensor-core GEMM is amplified, hence 1e-4 here ...
-  assert (np.abs(t1[rows] - want.theta) / scale).max() < 1e-4
+  assert (np.abs(t1[rows] - want.theta) / scale).max() < 1e-5
   np.testing.assert_allclose(U1[rows], want.potential, rtol=1e-5)
-  # ... while noise + update on the device's own gradient agree to the last bits
+  # noise + update on the device's own gradient agree to the last bits
   # (default mode: SFU sqrt / rcp, <= 2 ulp)
   same = osgmc.langevin_update(st, lambda th: (want.potential, np.zeros((len(rows), 2), np.float32),
                                                g1[rows]), [d], 1e-3, 1.0)

@@ -170,9 +170,9 @@ def test_sgld_logistic_trajectory_1000_steps(gpu, rms):
 def test_sgld_trajectory_1000_steps_tensor_core_path(gpu, rms):
   """The same 1 000-step comparison with the gradient from the tcgen05 GEMMs
   (split-fp16 "parity" path) and the whole step issued through
-  sgmc_glm_sgld_step.  Plain SGLD holds the 1e-5 trajectory bound; with RMSprop
-  the preconditioner 1/sqrt(v') amplifies the (1e-5 of the row scale) gradient
-  error on coordinates with small |g|, bound 1e-4."""
+  sgmc_glm_sgld_step.  Both plain SGLD and pSGLD (RMSprop) hold the north
+  star's 1e-5 trajectory bound (measured on B200: 3e-7 .. 8e-7, next to 2e-7 ..
+  4e-7 for the fp32 SIMT path; tools/r2_traj_err.py)."""
   from jax_sgmc_b200 import ops
   from jax_sgmc_b200.device import DeviceArray as DA
   from oracle import scheduler as osched
@@ -206,8 +206,8 @@ def test_sgld_trajectory_1000_steps_tensor_core_path(gpu, rms):
     st = osgmc.langevin_update(st, lambda th: pot(th, (Xb, yb), N), [d], eps[k], 1.0)
   got = d_theta.numpy()
   err = np.abs(got - st.theta).max() / np.abs(st.theta).max()
-  assert err < (1e-4 if rms else 1e-5), err
-  np.testing.assert_allclose(d_U.numpy(), st.potential, rtol=1e-4 if rms else 1e-5)
+  assert err < 1e-5, err
+  np.testing.assert_allclose(d_U.numpy(), st.potential, rtol=1e-5)
   assert np.array_equal(d_k[K % 2].numpy(), st.key)      # noise stream: bit-exact
   assert np.array_equal(d_dk[K % 2].numpy(), dk)         # minibatch stream: bit-exact
 
