@@ -259,11 +259,17 @@ int glm_simt(cudaStream_t stream, const GlmArgs& a) {
 
 using namespace sgmc;
 
-namespace sgmc { int glm_tc_debug_read(unsigned long long* out); }
+namespace sgmc {
+int glm_tc_debug_read(unsigned long long* out);
+int glm_pair_timeline_read(unsigned long long* out, int n);
+}
 
 extern "C" {
 
 int sgmc_debug_tc_timers(unsigned long long* out8) { return sgmc::glm_tc_debug_read(out8); }
+int sgmc_debug_pair_timeline(unsigned long long* out, int n) {
+  return sgmc::glm_pair_timeline_read(out, n);
+}
 
 size_t sgmc_glm_workspace_bytes(int64_t n_chains, int64_t batch_size, int64_t d,
                                 int path) {

@@ -132,12 +132,15 @@ constexpr int kNoiseJobMaxChains = 128;
 // logistic link with SFU-based exp / log / reciprocal (abs. error ~1e-7):
 //   ell = y z - softplus(z),  dz = y - sigmoid(z)
 __device__ __forceinline__ void logistic_link_fast(float z, float y, float& ell, float& dz) {
-  const float e = __expf(-fabsf(z));
+  // e = exp(-|z|) in (0, 1], den = 1 + e in (1, 2]: the flush-to-zero SFU forms need
+  // no sub-normal fix-up code around them
+  float e, lg, rden;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fabsf(z) * -1.4426950408889634f));
   const float den = 1.0f + e;
-  // log1p(e): log(1+e) loses e below 2^-24; the series e - e^2/2 covers small e
-  const float lp = __logf(den);     // abs. error <= 1 ulp(1) = 6e-8 (|ell| >= 7 when e < 1e-3)
-  ell = y * z - (fmaxf(z, 0.0f) + lp);
-  const float rden = __fdividef(1.0f, den);
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(den));
+  // log(1+e) = lg2(den) * ln 2: abs. error <= 1 ulp(1) = 6e-8 (|ell| >= 7 when e < 1e-3)
+  ell = y * z - fmaf(lg, 0.6931471805599453f, fmaxf(z, 0.0f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rden) : "f"(den));
   dz = y - (z >= 0.0f ? rden : 1.0f - rden);
 }
 
@@ -706,6 +709,19 @@ __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
   return *reinterpret_cast<const uint32_t*>(&h);
 }
 
+// Timeline of k_glm_tc_pair (globaltimer ns), one row of 16 stamps per pair; written only
+// when PairSched::dbg != 0 (sgmc_set_option(SGMC_OPT_TC_TIMELINE, 1)), read back with
+// sgmc_debug_pair_timeline (tools/r2_timeline.py).
+constexpr int kDbgPairs = 80, kDbgSlots = 16;
+__device__ unsigned long long g_pair_dbg[kDbgPairs * kDbgSlots];
+__device__ __forceinline__ void pair_stamp(int enabled, int pair, int slot) {
+  if (enabled && pair < kDbgPairs && slot < kDbgSlots) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    g_pair_dbg[pair * kDbgSlots + slot] = t;
+  }
+}
+
 constexpr int kPrEpiWarps = 16;
 constexpr int kPrEpiThreads = kPrEpiWarps * 32;
 constexpr int kPrThreads = kPrEpiThreads + 64;
@@ -725,6 +741,7 @@ struct PairSched {
   int nt1, nt2;           // 256-column tiles of GEMM1 (over n) / GEMM2 (over d)
   int kb1, kb2;           // 32-wide k-blocks of GEMM1 (over d) / GEMM2 (over n)
   int tiles1, tiles_total;
+  int dbg;                // record the timeline (g_pair_dbg)
 };
 
 template <int TERMS, int CG>
@@ -809,6 +826,8 @@ k_glm_tc_pair(const __grid_constant__ PairMaps maps, const PairSched sch,
   if (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  const int dbg = sch.dbg && leader;
+  if (threadIdx.x == 0) pair_stamp(dbg, pair, 0);
 
   if (warp == kPrEpiWarps) {
     // ===== TMA producer (both CTAs of the pair; bytes are credited to the leader's barrier) =====
@@ -825,8 +844,10 @@ k_glm_tc_pair(const __grid_constant__ PairMaps maps, const PairSched sch,
         if (g2) {
           // every R tile of this row block has been stored (GEMM1 epilogues of tiles
           // earlier in the list, on this pair or another one)
+          pair_stamp(dbg, pair, 12);
           while (ld_acquire_gpu(&link.counters[rb]) < (uint32_t)(CG * sch.nt1)) __nanosleep(40);
           fence_proxy_async_global();
+          pair_stamp(dbg, pair, 13);
         }
         for (int kb = 0; kb < kbs; ++kb, ++kbg) {
           const int s = kbg % S::kStages;
@@ -888,10 +909,14 @@ k_glm_tc_pair(const __grid_constant__ PairMaps maps, const PairSched sch,
           umma_commit_cg<CG>(&empty_bar[s]);   // frees the stage in both CTAs when the MMAs retire
         }
         umma_commit_cg<CG>(&acc_full[par]);    // accumulator complete (both CTAs)
+        pair_stamp(dbg, pair, 14 + (it > 0 ? 1 : 0));   // last MMA of the tile ISSUED
       }
     }
   } else {
     // ===== epilogue warps =====
+    // 18 warps leave 96 registers per thread at launch; the four epilogue warpgroups
+    // take the unused part of the register file (16 x 32 x 16 = 8192 of 10240 free)
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 112;" ::: "memory");
     const int q = warp & 3;                          // TMEM lane quarter
     const int cg = warp >> 2;                        // column group: 64 columns
     uint8_t* sbuf = out_stage + warp * kPrStageOut;  // private staging buffer
@@ -928,8 +953,10 @@ k_glm_tc_pair(const __grid_constant__ PairMaps maps, const PairSched sch,
         const bool row_ok = row < link.C;
         const float inv = row_ok ? 1.0f / (link.row_scale[row] * __ldg(link.b_scale)) : 0.f;
         named_bar_sync(1, kPrEpiThreads);
+        if (threadIdx.x == 0) pair_stamp(dbg, pair, 1 + 5 * (int)it);
         mbar_wait(&acc_full[par], aph);
         tc_fence_after();
+        if (threadIdx.x == 0) pair_stamp(dbg, pair, 2 + 5 * (int)it);
 #pragma unroll 1
         for (int ch = 0; ch < 2; ++ch) {
           const int ct = cg * 64 + ch * 32;          // column inside the tile
@@ -944,32 +971,38 @@ k_glm_tc_pair(const __grid_constant__ PairMaps maps, const PairSched sch,
           float cnt = 0.f, shift = 0.f, s1 = 0.f, s2 = 0.f, sm = 0.f;
           if (col0 < link.n) {                       // warp-uniform
             const bool full_cols = col0 + 32 <= link.n;
-            float ellv[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const float z = __uint_as_float(acc[j]) * inv;
-              float l, dz;
-              logistic_link_fast(z, cy[ct + j], l, dz);
-              ellv[j] = l;
-              acc[j] = __float_as_uint(dz * crm[ct + j]);
-            }
-            shift = ellv[0];
-            if (full_cols) {
+            float* ep = (link.ell && row_ok) ? link.ell + (int64_t)row * link.n + col0 : nullptr;
+            // the statistics run on the fly (shifted by the first likelihood of the
+            // chunk) so no per-element state beyond R stays live: more chains of
+            // exp / log / rcp in flight per thread
+            if (full_cols && link.mask == nullptr && link.ell == nullptr) {
+              const float rmc = link.cot * link.r_scale;       // mask == 1 everywhere
 #pragma unroll
               for (int j = 0; j < 32; ++j) {
-                const float dl = ellv[j] - shift;
+                const float z = __uint_as_float(acc[j]) * inv;
+                float l, dz;
+                logistic_link_fast(z, cy[ct + j], l, dz);
+                if (j == 0) shift = l;
+                const float dl = l - shift;
                 s1 += dl;
                 s2 = fmaf(dl, dl, s2);
-                sm = fmaf(ellv[j], cm[ct + j], sm);
+                acc[j] = __float_as_uint(dz * rmc);
               }
               cnt = 32.f;
+              sm = fmaf(32.f, shift, s1);                       // sum(ell * 1)
             } else {
 #pragma unroll
               for (int j = 0; j < 32; ++j) {
+                const float z = __uint_as_float(acc[j]) * inv;
+                float l, dz;
+                logistic_link_fast(z, cy[ct + j], l, dz);
+                if (j == 0) shift = l;
                 if (col0 + j < link.n) {
-                  const float dl = ellv[j] - shift;
-                  cnt += 1.f; s1 += dl; s2 = fmaf(dl, dl, s2); sm = fmaf(ellv[j], cm[ct + j], sm);
+                  const float dl = l - shift;
+                  cnt += 1.f; s1 += dl; s2 = fmaf(dl, dl, s2); sm = fmaf(l, cm[ct + j], sm);
+                  if (ep) ep[j] = l;                           // optional per-observation output
                 }
+                acc[j] = __float_as_uint(dz * crm[ct + j]);
               }
             }
             // R tile -> swizzled staging (row = lane, 64 bytes per row: hi at +0, lo at
@@ -1006,14 +1039,6 @@ k_glm_tc_pair(const __grid_constant__ PairMaps maps, const PairSched sch,
               if (TERMS == 3) tma_store_2d(&maps.r[1], sbuf + 2048, col0, row0);
               bulk_commit_group();
             }
-            if (link.ell && row_ok) {                // optional per-observation output
-              float* ep = link.ell + (int64_t)row * link.n + col0;
-#pragma unroll
-              for (int k4 = 0; k4 < 8; ++k4)
-                if (full_cols || col0 + k4 * 4 + 4 <= link.n)
-                  *reinterpret_cast<float4*>(ep + k4 * 4) =
-                      make_float4(ellv[4 * k4], ellv[4 * k4 + 1], ellv[4 * k4 + 2], ellv[4 * k4 + 3]);
-            }
           }
           if (row_ok) {
             // partial statistics of this (row, 32-column chunk), combined in fixed
@@ -1030,9 +1055,11 @@ k_glm_tc_pair(const __grid_constant__ PairMaps maps, const PairSched sch,
         }
         // publish: R (TMA stores complete) + stats of this tile are visible -- also to the
         // TMA loads of other SMs -- before the row-block counter moves
+        if (threadIdx.x == 0) pair_stamp(dbg, pair, 3 + 5 * (int)it);
         if (lane == 0) bulk_wait_all();
         __threadfence();
         fence_proxy_async_global();
+        if (threadIdx.x == 0) pair_stamp(dbg, pair, 4 + 5 * (int)it);
         if (warp < 4) {
           named_bar_sync(2, kPrEpiThreads);
           if (threadIdx.x == 0) {
@@ -1073,6 +1100,7 @@ k_glm_tc_pair(const __grid_constant__ PairMaps maps, const PairSched sch,
               if (link.variance) link.variance[c] = m2_t / (float)link.n;
             }
           }
+          if (threadIdx.x == 0) pair_stamp(dbg, pair, 5 + 5 * (int)it);
         } else {
           named_bar_arrive(2, kPrEpiThreads);
         }
@@ -1080,8 +1108,10 @@ k_glm_tc_pair(const __grid_constant__ PairMaps maps, const PairSched sch,
         // ---- gradient epilogue: G * 1/scale (+ theta * prior_coef) -> grad ----
         const float inv_scale = 1.0f / (gradp.r_scale * __ldg(gradp.xt_scale));
         const bool row_ok = row < gradp.C;
+        if (threadIdx.x == 0) pair_stamp(dbg, pair, 1 + 5 * (int)it);
         mbar_wait(&acc_full[par], aph);
         tc_fence_after();
+        if (threadIdx.x == 0) pair_stamp(dbg, pair, 2 + 5 * (int)it);
 #pragma unroll 1
         for (int ch = 0; ch < 2; ++ch) {
           const int ct = cg * 64 + ch * 32;
@@ -1124,9 +1154,11 @@ k_glm_tc_pair(const __grid_constant__ PairMaps maps, const PairSched sch,
             bulk_commit_group();
           }
         }
+        if (threadIdx.x == 0) pair_stamp(dbg, pair, 3 + 5 * (int)it);
       }
     }
     if (lane == 0) bulk_wait_all();                  // staging buffers are read, stores performed
+    if (threadIdx.x == 0) pair_stamp(dbg, pair, 11);
   }
   __syncwarp();
   tc_fence_before();
@@ -1542,6 +1574,11 @@ __global__ void __launch_bounds__(256) k_sgld_apply(float* __restrict__ theta, f
   }
 }
 
+int glm_pair_timeline_read(unsigned long long* out, int n) {
+  const size_t cnt = (size_t)std::min(n, kDbgPairs * kDbgSlots);
+  return check_cuda(cudaMemcpyFromSymbol(out, g_pair_dbg, sizeof(unsigned long long) * cnt), "dbg");
+}
+
 int glm_tc_debug_read(unsigned long long* out) {
   return check_cuda(cudaMemcpyFromSymbol(out, g_tc_dbg, sizeof(unsigned long long) * 10), "dbg");
 }
@@ -1770,6 +1807,7 @@ int glm_tc(cudaStream_t stream, const GlmArgs& a, int path) {
     sch.kb2 = (int)((n + kPrBK - 1) / kPrBK);
     sch.tiles1 = sch.mt * sch.nt1;
     sch.tiles_total = sch.tiles1 + sch.mt * sch.nt2;
+    sch.dbg = option(SGMC_OPT_TC_TIMELINE);
     // The maps only depend on the workspace / gradient addresses and the shapes:
     // encode them once per (workspace, shape) instead of once per step.
     const MapKey mkey{base, a.grad, C, n, a.P, d, cgn, split ? 1 : 0};

@@ -102,7 +102,7 @@ def synchronize():
 class DeviceArray:
   """An n-d array in device memory (row-major, contiguous)."""
 
-  __slots__ = ("ptr", "shape", "dtype", "_owner", "nbytes")
+  __slots__ = ("ptr", "shape", "dtype", "_owner", "nbytes", "__weakref__")
 
   def __init__(self, shape: Sequence[int], dtype, ptr: Optional[int] = None,
                owner=None):

@@ -14,6 +14,7 @@ reproducing ``jax.random`` bit for bit).
 """
 from __future__ import annotations
 
+import weakref
 from typing import Any, Callable, Dict, NamedTuple, Tuple
 
 import numpy as np
@@ -147,6 +148,34 @@ def random_tree(key, a: ChainTree) -> ChainTree:
 
 
 # -----------------------------------------------------------------------------
+
+class _Scratch:
+  """Scratch buffers (gradient, mass / friction vectors) of one integrator,
+  looked up by the state's flat sample array.
+
+  An entry is only valid for the very array object it was built for (a weak
+  reference is kept and compared -- ``id()`` alone can be reused by a later
+  array of a different shape) and for the same ``token`` objects (e.g. the
+  ``mass`` argument of ``integrate``); entries of dead arrays are dropped.
+  """
+
+  def __init__(self):
+    self._entries: Dict[int, Any] = {}
+
+  def get(self, owner: DeviceArray, build: Callable[[], Any], *token):
+    ent = self._entries.get(id(owner))
+    if ent is not None:
+      ref, tok, val = ent
+      if ref() is owner and len(tok) == len(token) and all(
+          a is b for a, b in zip(tok, token)):
+        return val
+    for k in [k for k, (r, _, _) in self._entries.items() if r() is None]:
+      del self._entries[k]
+    val = build()
+    self._entries[id(owner)] = (weakref.ref(owner), token, val)
+    return val
+
+
 def langevin_diffusion(potential_fn, batch_fn, adaption=None
                        ) -> Tuple[Callable, Callable, Callable]:
   """integrator.py:767-924."""
@@ -157,7 +186,7 @@ def langevin_diffusion(potential_fn, batch_fn, adaption=None
     adapt_init, _, _ = adaption
   batch_init, batch_get, _ = batch_fn
   stochastic_gradient = _potential.value_and_grad(potential_fn)
-  scratch: Dict[int, DeviceArray] = {}
+  scratch = _Scratch()
 
   def init_fn(init_sample, key=None, adaption_kwargs: Dict = None,
               batch_kwargs: Dict = None, init_model_state: PyTree = None
@@ -187,9 +216,8 @@ def langevin_diffusion(potential_fn, batch_fn, adaption=None
     puts its label exchange there."""
     theta = state.latent_variables
     data_state, mini_batch = batch_get(state.data_state, information=True)   # :872
-    grad_buf = scratch.get(id(theta.flat))
-    if grad_buf is None:
-      grad_buf = scratch[id(theta.flat)] = DeviceArray(theta.flat.shape, np.float32)
+    grad_buf = scratch.get(theta.flat, lambda: DeviceArray(theta.flat.shape, np.float32))
+    assert grad_buf.shape == theta.flat.shape
     v = alpha = lmbd = None
     if adaption is not None:
       v, alpha, lmbd = state.adapt_state.v.flat, state.adapt_state.alpha, \
@@ -233,9 +261,8 @@ def langevin_diffusion(potential_fn, batch_fn, adaption=None
     source = source_fn(state.data_state, steps)
     if source is None:
       return None
-    grad_buf = scratch.get(id(theta.flat))
-    if grad_buf is None:
-      grad_buf = scratch[id(theta.flat)] = DeviceArray(theta.flat.shape, np.float32)
+    grad_buf = scratch.get(theta.flat, lambda: DeviceArray(theta.flat.shape, np.float32))
+    assert grad_buf.shape == theta.flat.shape
     v, alpha, lmbd = None, 0.9, 1e-5
     if adaption is not None:
       v, alpha, lmbd = state.adapt_state.v.flat, state.adapt_state.alpha, \
@@ -261,7 +288,7 @@ def friction_leapfrog(potential_fn, batch_fn, steps: int = 10, friction=0.25,
     raise NotImplementedError("the Fisher noise model is outside this path")
   init_data, get_data, _ = batch_fn
   stochastic_gradient = _potential.value_and_grad(potential_fn)
-  scratch: Dict[int, Any] = {}
+  scratch = _Scratch()
 
   def init_fn(init_sample, key=None, batch_kwargs: Dict = None,
               init_model_state: PyTree = None) -> LeapfrogState:
@@ -278,16 +305,17 @@ def friction_leapfrog(potential_fn, batch_fn, steps: int = 10, friction=0.25,
   def integrate(state: LeapfrogState, parameters, mass: PyTree = None) -> LeapfrogState:
     theta, p = state.positions, state.momentum
     eps = float(parameters.step_size)
-    sc = scratch.get(id(theta.flat))
-    if sc is None:
+    def build():
       m = mass if mass is not None else const_mass
       fr_leaves = tree_flatten(friction)[0]
       scalar_fr = len(fr_leaves) == 1 and np.ndim(fr_leaves[0]) == 0
-      sc = scratch[id(theta.flat)] = {
+      return {
           "grad": DeviceArray(theta.flat.shape, np.float32),
           "mass": None if m is None else _flat_vector(m, theta),
           "friction": None if scalar_fr else _flat_vector(friction, theta),
           "friction_scalar": float(fr_leaves[0]) if scalar_fr else 0.0}
+    sc = scratch.get(theta.flat, build, mass)      # rebuilt when `mass` changes
+    assert sc["grad"].shape == theta.flat.shape
     # resample momentum (:736-738) fused with the first position update (:610-612)
     ops.sghmc_begin(theta.flat, p.flat, state.key.current, state.key.next,
                     theta.sizes, eps, sc["mass"])
@@ -319,7 +347,7 @@ def obabo(potential_fn, batch_fn, steps: int = 10, friction: float = 1.0,
   """integrator.py:138-346."""
   init_data, get_data, _ = batch_fn
   stochastic_gradient = _potential.value_and_grad(potential_fn)
-  scratch: Dict[int, Any] = {}
+  scratch = _Scratch()
 
   def init_fn(init_sample, key=None, batch_kwargs: Dict = None,
               init_model_state: PyTree = None) -> ObaboState:
@@ -338,13 +366,14 @@ def obabo(potential_fn, batch_fn, steps: int = 10, friction: float = 1.0,
     theta, p = state.positions, state.momentum
     eps, T = float(parameters.step_size), float(parameters.temperature)
     C = theta.n_chains
-    sc = scratch.get(id(theta.flat))
-    if sc is None:
+    def build():
       m = mass if mass is not None else const_mass
-      sc = scratch[id(theta.flat)] = {
+      return {
           "grad": DeviceArray(theta.flat.shape, np.float32),
           "U1": DeviceArray((C,), np.float32), "U2": DeviceArray((C,), np.float32),
           "mass": None if m is None else _flat_vector(m, theta)}
+    sc = scratch.get(theta.flat, build, mass)      # rebuilt when `mass` changes
+    assert sc["grad"].shape == theta.flat.shape
     data_state, model_state = state.data_state, state.model_state
     for _ in range(steps):                                               # :333-336
       data_state, mb = get_data(data_state, information=True)            # :225
@@ -381,7 +410,7 @@ def reversible_leapfrog(potential_fn, batch_fn, steps: int = 10, friction=0.25,
   half position step."""
   init_data, get_data, _ = batch_fn
   stochastic_gradient = _potential.value_and_grad(potential_fn)
-  scratch: Dict[int, Any] = {}
+  scratch = _Scratch()
 
   def _mass_vector(mass, theta):
     m = mass if mass is not None else const_mass
@@ -405,18 +434,19 @@ def reversible_leapfrog(potential_fn, batch_fn, steps: int = 10, friction=0.25,
   def integrate(state: LeapfrogState, parameters, mass: PyTree = None) -> LeapfrogState:
     theta, p = state.positions, state.momentum
     eps = np.float32(parameters.step_size)
-    sc = scratch.get(id(theta.flat))
-    if sc is None:
+    def build():
       m = _mass_vector(mass, theta)
       inv_full = None
       if m is not None:      # inv_m broadcast over the chains for the opening half step
         inv_full = DeviceArray.from_numpy(
             np.tile((np.float32(1.0) / m.numpy())[None, :], (theta.n_chains, 1)))
-      sc = scratch[id(theta.flat)] = {
+      return {
           "grad": DeviceArray(theta.flat.shape, np.float32), "mass": m,
           "inv_full": inv_full, "tmp": None if m is None else DeviceArray(theta.flat.shape,
                                                                          np.float32),
           "U": DeviceArray((theta.n_chains,), np.float32)}
+    sc = scratch.get(theta.flat, build, mass)      # rebuilt when `mass` changes
+    assert sc["grad"].shape == theta.flat.shape
     half = float(np.float32(0.5) * eps)
     if sc["mass"] is None:                                           # :523-524
       ops.axpby(theta.flat, 1.0, theta.flat, half, p.flat)
