@@ -712,7 +712,7 @@ __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
 // Timeline of k_glm_tc_pair (globaltimer ns), one row of 16 stamps per pair; written only
 // when PairSched::dbg != 0 (sgmc_set_option(SGMC_OPT_TC_TIMELINE, 1)), read back with
 // sgmc_debug_pair_timeline (tools/r2_timeline.py).
-constexpr int kDbgPairs = 80, kDbgSlots = 16;
+constexpr int kDbgPairs = 80, kDbgSlots = 32;
 __device__ unsigned long long g_pair_dbg[kDbgPairs * kDbgSlots];
 __device__ __forceinline__ void pair_stamp(int enabled, int pair, int slot) {
   if (enabled && pair < kDbgPairs && slot < kDbgSlots) {
@@ -725,59 +725,120 @@ __device__ __forceinline__ void pair_stamp(int enabled, int pair, int slot) {
 constexpr int kPrEpiWarps = 16;
 constexpr int kPrEpiThreads = kPrEpiWarps * 32;
 constexpr int kPrThreads = kPrEpiThreads + 64;
-constexpr int kPrBK = 32;                       // k-block: 32 elements = 64-byte swizzle span
-constexpr int kPrBN = 256;                      // accumulator columns per CTA and tile
+constexpr int kPrBK = 64;                       // k-block: 64 elements = 128-byte swizzle span
+constexpr int kPrSwz = 128;                     // (TMA delivers a fixed number of box ROWS per
+                                                // cycle: 128-byte rows halve the row count)
 constexpr int kPrStageOut = 4096;               // epilogue staging bytes per warp
 
 struct PairMaps {
   CUtensorMap a[2][2];    // loads, [gemm][hi / lo]: Theta (GEMM1), R (GEMM2); box 128 x 32
-  CUtensorMap b[2][2];    // loads, [gemm][hi / lo]: Xb (GEMM1), XbT (GEMM2); box (256/CG) x 32
+  CUtensorMap b[2][2];    // loads, [gemm][hi / lo]: Xb (GEMM1), XbT (GEMM2); box (BN/CG) x 32
   CUtensorMap r[2];       // stores: R hi / lo, box 32 x 32 halves (64-byte swizzle)
   CUtensorMap g;          // store: grad, box 32 x 32 floats (128-byte swizzle)
 };
 
 struct PairSched {
   int mt;                 // row blocks of 128 * CG rows
-  int nt1, nt2;           // 256-column tiles of GEMM1 (over n) / GEMM2 (over d)
+  int nt1, nt2;           // BN-column tiles of GEMM1 (over n) / GEMM2 (over d)
   int kb1, kb2;           // 32-wide k-blocks of GEMM1 (over d) / GEMM2 (over n)
   int tiles1, tiles_total;
   int dbg;                // record the timeline (g_pair_dbg)
 };
 
-template <int TERMS, int CG>
+// BN = accumulator columns per CTA and tile: 256 (one tile per pair and GEMM at C2: the
+// least L2 traffic, but the epilogues are exposed) or 128 (two to four tiles per pair: every
+// epilogue but the last runs under the next tile's mainloop).
+template <int TERMS, int CG, int BN>
 struct PrSmem {
+  static_assert(BN == 128 || BN == 256, "tile width");
   static constexpr int kNA = TERMS == 3 ? 2 : 1;
-  static constexpr int kBRows = kPrBN / CG;
+  static constexpr int kBRows = BN / CG;
   static constexpr int kABytes = BM * kPrBK * 2;
   static constexpr int kBBytes = kBRows * kPrBK * 2;
   static constexpr int kStageBytes = kNA * (kABytes + kBBytes);
-  static constexpr int kStages = (CG == 2 ? 4 : 3) * (TERMS == 3 ? 1 : 2);
+  // 192 KB of operand stages.  The epilogue's 64 KB of staging buffers ALIAS the last
+  // kStgStages stages: the producer hands them over per tile (epi_done barrier), which
+  // costs nothing when a pair runs one tile per GEMM (the epilogue and the next
+  // mainloop cannot overlap there anyway: GEMM2 waits for R).
+  static constexpr int kStages = 196608 / kStageBytes > 8 ? 8 : 196608 / kStageBytes;
   static constexpr int kPipeBytes = kStages * kStageBytes;
   static constexpr int kOutBytes = kPrEpiWarps * kPrStageOut;
-  static constexpr int kAuxBytes = 256 /*barriers, tmem ptr, flags*/ + 2 * 3 * kPrBN * 4;
-  static constexpr int kBytes = kPipeBytes + kOutBytes + kAuxBytes + 1024 /*alignment slack*/;
-  static_assert(2 * kStages + 4 <= 24, "barrier block is 256 bytes");
+  static constexpr int kStgStages = (kOutBytes + kStageBytes - 1) / kStageBytes;
+  static constexpr int kAuxBytes = 256 /*barriers, tmem ptr, flags*/ + 2 * 3 * BN * 4;
+  static constexpr int kBytes = kPipeBytes + kAuxBytes + 1024 /*alignment slack*/;
+  static_assert(kStages > kStgStages, "need at least one stage that is never handed over");
+  static_assert(2 * kStages + 5 <= 24, "barrier block is 256 bytes");
   static_assert(kBytes <= 232448, "exceeds the 227 KB of shared memory per CTA");
 };
 
-template <int TERMS, int ABFMT, int CG>
+// Side job of the epilogue warps while the tensor pipe works (sgmc_glm_sgld_step in
+// carried mode): the step's Gaussian noise (integrator.random_tree, one leaf of d
+// elements per chain, original threefry layout) is generated into xi[C][d] from the
+// per-chain noise keys k_prepare_all derived; k_sgld_apply_split consumes it.  The
+// threefry + erf_inv arithmetic is issue-bound (about 120 instructions per normal)
+// and would otherwise be the bulk of the update kernel; here it runs in issue slots
+// the GEMM mainloops leave idle.  Unit of work: 32 consecutive elements j of a chain's
+// first half and their block partners j + d/2 (64 normals, two coalesced 128-byte
+// stores per warp).
+struct PairNoise {
+  float* xi;                 // f32[C][d] or null (no job)
+  const uint32_t* noise_keys;
+  int d;
+  int units_per_chain;       // d / 64
+  int units_total;           // C * units_per_chain
+};
+
+__device__ __forceinline__ void pair_noise_unit(const PairNoise& nz, int u, int lane) {
+  const int c = u / nz.units_per_chain;
+  const uint32_t half = (uint32_t)nz.d >> 1;
+  const uint32_t j = (uint32_t)(u - c * nz.units_per_chain) * 32u + (uint32_t)lane;
+  const Key lk{__ldg(nz.noise_keys + 2 * c), __ldg(nz.noise_keys + 2 * c + 1)};
+  uint32_t wa = j, wb = j + half;
+  threefry2x32(lk, wa, wb);
+  NormalPartial pa, pb;
+  float na = normal_main(wa, pa), nb = normal_main(wb, pb);
+  if (normal_is_tail(pa) | normal_is_tail(pb)) {
+    if (normal_is_tail(pa)) na = normal_tail(pa);
+    if (normal_is_tail(pb)) nb = normal_tail(pb);
+  }
+  float* row = nz.xi + (int64_t)c * nz.d;
+  row[j] = na;
+  row[half + j] = nb;
+}
+
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "mbarrier.test_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, P1;\n"
+      "}\n" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+
+template <int TERMS, int ABFMT, int CG, int BN>
 __global__ void __launch_bounds__(kPrThreads, 1)
 k_glm_tc_pair(const __grid_constant__ PairMaps maps, const PairSched sch,
-              const TcLinkEpi link, const TcGradEpi gradp) {
-  using S = PrSmem<TERMS, CG>;
+              const TcLinkEpi link, const TcGradEpi gradp, const PairNoise nz) {
+  using S = PrSmem<TERMS, CG, BN>;
+  constexpr int kChunks = BN / 128;                // 32-column chunks per epilogue warp and tile
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* tiles = smem;
-  uint8_t* out_stage = smem + S::kPipeBytes;                       // 16 x 4 KB, 4 KB aligned
-  uint8_t* aux = out_stage + S::kOutBytes;
+  // epilogue staging (16 x 4 KB) aliases the last stage(s) of the operand ring
+  uint8_t* out_stage = smem + S::kPipeBytes - S::kOutBytes;
+  uint8_t* aux = smem + S::kPipeBytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(aux);
   uint64_t* empty_bar = full_bar + S::kStages;
   uint64_t* acc_full = empty_bar + S::kStages;      // [2]
   uint64_t* acc_empty = acc_full + 2;               // [2]
+  uint64_t* epi_done = acc_empty + 2;               // staging buffers free again (per tile)
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(aux + 224);
   int* s_last = reinterpret_cast<int*>(tmem_ptr + 1);   // [2]
-  float* s_col = reinterpret_cast<float*>(aux + 256);   // [2][3][256]
+  int* s_noise_next = s_last + 2;                       // next noise unit of this CTA
+  float* s_col = reinterpret_cast<float*>(aux + 256);   // [2][3][BN]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;
@@ -804,6 +865,10 @@ k_glm_tc_pair(const __grid_constant__ PairMaps maps, const PairSched sch,
       }
     }
   }
+  // this CTA's share of the noise job
+  const int nu0 = nz.xi ? (int)((int64_t)nz.units_total * blockIdx.x / gridDim.x) : 0;
+  const int nu1 = nz.xi ? (int)((int64_t)nz.units_total * (blockIdx.x + 1) / gridDim.x) : 0;
+  if (threadIdx.x == 0) *s_noise_next = nu0;
   if (warp == kPrEpiWarps + 1) {
     if (lane == 0) {
       for (int s = 0; s < S::kStages; ++s) {
@@ -814,10 +879,11 @@ k_glm_tc_pair(const __grid_constant__ PairMaps maps, const PairSched sch,
         mbar_init(&acc_full[i], 1);
         mbar_init(&acc_empty[i], CG * kPrEpiWarps);
       }
+      mbar_init(epi_done, kPrEpiWarps);
       fence_barrier_init();
     }
     __syncwarp();
-    tmem_alloc_cg<CG>(tmem_ptr, 2 * kPrBN);
+    tmem_alloc_cg<CG>(tmem_ptr, 2 * BN);
   }
   // Everything above overlaps the previous kernel's tail (programmatic dependent launch).
   pdl_launch_dependents();
@@ -832,27 +898,36 @@ k_glm_tc_pair(const __grid_constant__ PairMaps maps, const PairSched sch,
   if (warp == kPrEpiWarps) {
     // ===== TMA producer (both CTAs of the pair; bytes are credited to the leader's barrier) =====
     if (lane == 0) {
-      uint32_t kbg = 0;
-      for (int t = pair; t < sch.tiles_total; t += n_pairs) {
+      uint32_t uses[S::kStages];                     // fills of each stage so far (phase = use & 1)
+#pragma unroll
+      for (int s = 0; s < S::kStages; ++s) uses[s] = 0;
+      uint32_t it = 0;
+      for (int t = pair; t < sch.tiles_total; t += n_pairs, ++it) {
         const int g2 = t >= sch.tiles1 ? 1 : 0;
         const int tt = g2 ? t - sch.tiles1 : t;
         const int ntl = g2 ? sch.nt2 : sch.nt1;
         const int rb = tt / ntl, tn = tt - rb * ntl;
         const int m0 = rb * (BM * CG) + (int)rank * BM;
-        const int n0 = tn * kPrBN + (int)rank * S::kBRows;
+        const int n0 = tn * BN + (int)rank * S::kBRows;
         const int kbs = g2 ? sch.kb2 : sch.kb1;
         if (g2) {
           // every R tile of this row block has been stored (GEMM1 epilogues of tiles
           // earlier in the list, on this pair or another one)
-          pair_stamp(dbg, pair, 12);
+          pair_stamp(dbg, pair, 2);
           while (ld_acquire_gpu(&link.counters[rb]) < (uint32_t)(CG * sch.nt1)) __nanosleep(40);
           fence_proxy_async_global();
-          pair_stamp(dbg, pair, 13);
+          pair_stamp(dbg, pair, 3);
         }
-        for (int kb = 0; kb < kbs; ++kb, ++kbg) {
-          const int s = kbg % S::kStages;
-          const uint32_t ph = (kbg / S::kStages) & 1;
-          mbar_wait(&empty_bar[s], ph ^ 1);
+#pragma unroll 1
+        for (int kb = 0; kb < kbs; ++kb) {
+          const int s = kb % S::kStages;               // the ring restarts with every tile
+          if (it > 0 && kb == s && s >= S::kStages - S::kStgStages)
+            mbar_wait(epi_done, (it - 1) & 1);         // previous tile's epilogue left the staging
+          uint32_t use = 0;
+#pragma unroll
+          for (int q = 0; q < S::kStages; ++q)
+            if (q == s) { use = uses[q]; uses[q] = use + 1; }
+          mbar_wait(&empty_bar[s], (use & 1) ^ 1);
           uint8_t* st = tiles + s * S::kStageBytes;
           uint8_t* sb = st + S::kNA * S::kABytes;
           if (CG == 2) {
@@ -874,18 +949,25 @@ k_glm_tc_pair(const __grid_constant__ PairMaps maps, const PairSched sch,
   } else if (warp == kPrEpiWarps + 1) {
     // ===== MMA issuer: one thread of the leader CTA drives both SMs' tensor cores =====
     if (lane == 0 && leader) {
-      constexpr uint32_t idesc = make_idesc(ABFMT, BM * CG, kPrBN);
-      uint32_t kbg = 0, it = 0;
+      constexpr uint32_t idesc = make_idesc(ABFMT, BM * CG, BN);
+      uint32_t uses[S::kStages];
+#pragma unroll
+      for (int s = 0; s < S::kStages; ++s) uses[s] = 0;
+      uint32_t it = 0;
       for (int t = pair; t < sch.tiles_total; t += n_pairs, ++it) {
         const int kbs = t >= sch.tiles1 ? sch.kb2 : sch.kb1;
         const uint32_t par = it & 1, aph = (it >> 1) & 1;
         mbar_wait_cluster(&acc_empty[par], aph ^ 1);   // both CTAs' epilogues drained this accumulator
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + par * kPrBN;
-        for (int kb = 0; kb < kbs; ++kb, ++kbg) {
-          const int s = kbg % S::kStages;
-          const uint32_t ph = (kbg / S::kStages) & 1;
-          mbar_wait_cluster(&full_bar[s], ph);
+        const uint32_t d_tmem = tmem_base + par * BN;
+#pragma unroll 1
+        for (int kb = 0; kb < kbs; ++kb) {
+          const int s = kb % S::kStages;
+          uint32_t use = 0;
+#pragma unroll
+          for (int q = 0; q < S::kStages; ++q)
+            if (q == s) { use = uses[q]; uses[q] = use + 1; }
+          mbar_wait_cluster(&full_bar[s], use & 1);
           tc_fence_after();
           const uint32_t a0 = smem_u32(tiles + s * S::kStageBytes);
           const uint32_t a1 = a0 + S::kABytes;
@@ -893,7 +975,7 @@ k_glm_tc_pair(const __grid_constant__ PairMaps maps, const PairSched sch,
           const uint32_t b1 = b0 + S::kBBytes;
 #pragma unroll
           for (int k = 0; k < kPrBK / 16; ++k) {
-            // advancing K by 16 elements (32 B) inside the 64 B swizzle atom
+            // advancing K by 16 elements (32 B) inside the 128 B swizzle atom
             const uint64_t da0 = make_smem_desc_k<kPrBK>(a0 + k * 32);
             const uint64_t db0 = make_smem_desc_k<kPrBK>(b0 + k * 32);
             if (TERMS == 3) {
@@ -909,18 +991,33 @@ k_glm_tc_pair(const __grid_constant__ PairMaps maps, const PairSched sch,
           umma_commit_cg<CG>(&empty_bar[s]);   // frees the stage in both CTAs when the MMAs retire
         }
         umma_commit_cg<CG>(&acc_full[par]);    // accumulator complete (both CTAs)
-        pair_stamp(dbg, pair, 14 + (it > 0 ? 1 : 0));   // last MMA of the tile ISSUED
+        pair_stamp(dbg, pair, 4 + (it > 0 ? 1 : 0));   // last MMA of the tile ISSUED
       }
     }
   } else {
     // ===== epilogue warps =====
-    // 18 warps leave 96 registers per thread at launch; the four epilogue warpgroups
-    // take the unused part of the register file (16 x 32 x 16 = 8192 of 10240 free)
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 112;" ::: "memory");
     const int q = warp & 3;                          // TMEM lane quarter
-    const int cg = warp >> 2;                        // column group: 64 columns
+    const int cg = warp >> 2;                        // column group: BN / 4 columns
     uint8_t* sbuf = out_stage + warp * kPrStageOut;  // private staging buffer
-    const int parts = sch.nt1 * (kPrBN / 32);
+    // wait for an accumulator; meanwhile generate noise units (64 normals each)
+    auto wait_acc = [&](uint64_t* bar, uint32_t parity) {
+      if (nz.xi != nullptr) {
+        for (;;) {
+          int done = 0, u = 0;
+          if (lane == 0) {
+            done = mbar_test(bar, parity) ? 1 : 0;
+            if (!done) u = atomicAdd(s_noise_next, 1);
+          }
+          done = __shfl_sync(0xffffffffu, done, 0);
+          if (done) break;
+          u = __shfl_sync(0xffffffffu, u, 0);
+          if (u >= nu1) break;
+          pair_noise_unit(nz, u, lane);
+        }
+      }
+      mbar_wait(bar, parity);
+    };
+    const int parts = sch.nt1 * (BN / 32);
     uint32_t it = 0;
     for (int t = pair; t < sch.tiles_total; t += n_pairs, ++it) {
       const int g2 = t >= sch.tiles1 ? 1 : 0;
@@ -928,18 +1025,18 @@ k_glm_tc_pair(const __grid_constant__ PairMaps maps, const PairSched sch,
       const int ntl = g2 ? sch.nt2 : sch.nt1;
       const int rb = tt / ntl, tn = tt - rb * ntl;
       const int m0 = rb * (BM * CG) + (int)rank * BM;
-      const int n0 = tn * kPrBN;                     // accumulator column 0 of this tile
+      const int n0 = tn * BN;                        // accumulator column 0 of this tile
       const uint32_t par = it & 1, aph = (it >> 1) & 1;
       const int row0 = m0 + q * 32;
       const int row = row0 + lane;                   // this thread's accumulator row
-      const uint32_t tmem_row = tmem_base + par * kPrBN + ((uint32_t)(q * 32) << 16);
+      const uint32_t tmem_row = tmem_base + par * BN + ((uint32_t)(q * 32) << 16);
 
       if (!g2) {
         // ---- link epilogue: z -> ell statistics, R = cot * mask * dl/dz (fp16 hi/lo) ----
-        float* cy = s_col + par * 3 * kPrBN;
-        float* cm = cy + kPrBN;
-        float* crm = cm + kPrBN;
-        if ((int)threadIdx.x < kPrBN) {              // per-column observation data of this tile
+        float* cy = s_col + par * 3 * BN;
+        float* cm = cy + BN;
+        float* crm = cm + BN;
+        if ((int)threadIdx.x < BN) {              // per-column observation data of this tile
           const int col = n0 + threadIdx.x;
           float yv = 0.f, mv = 0.f;
           if (col < link.n) {
@@ -953,17 +1050,17 @@ k_glm_tc_pair(const __grid_constant__ PairMaps maps, const PairSched sch,
         const bool row_ok = row < link.C;
         const float inv = row_ok ? 1.0f / (link.row_scale[row] * __ldg(link.b_scale)) : 0.f;
         named_bar_sync(1, kPrEpiThreads);
-        if (threadIdx.x == 0) pair_stamp(dbg, pair, 1 + 5 * (int)it);
-        mbar_wait(&acc_full[par], aph);
+        if (threadIdx.x == 0) pair_stamp(dbg, pair, 8 + 5 * (int)it);
+        wait_acc(&acc_full[par], aph);
         tc_fence_after();
-        if (threadIdx.x == 0) pair_stamp(dbg, pair, 2 + 5 * (int)it);
+        if (threadIdx.x == 0) pair_stamp(dbg, pair, 9 + 5 * (int)it);
 #pragma unroll 1
-        for (int ch = 0; ch < 2; ++ch) {
-          const int ct = cg * 64 + ch * 32;          // column inside the tile
+        for (int ch = 0; ch < kChunks; ++ch) {
+          const int ct = cg * (BN / 4) + ch * 32;          // column inside the tile
           const int col0 = n0 + ct;
           uint32_t acc[32];
           tmem_ld32(tmem_row + (uint32_t)ct, acc);
-          if (ch == 1) {                             // accumulator drained: hand it back
+          if (ch == kChunks - 1) {                             // accumulator drained: hand it back
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_leader(&acc_empty[par]);
@@ -1048,18 +1145,21 @@ k_glm_tc_pair(const __grid_constant__ PairMaps maps, const PairSched sch,
               mean = shift + s1 / cnt;
               m2 = fmaxf(s2 - s1 * s1 / cnt, 0.f);
             }
-            const int part = tn * (kPrBN / 32) + cg * 2 + ch;
+            const int part = tn * (BN / 32) + cg * kChunks + ch;
             *reinterpret_cast<float4*>(link.stats + ((int64_t)row * parts + part) * kStatFields) =
                 make_float4(cnt, mean, m2, sm);
           }
         }
         // publish: R (TMA stores complete) + stats of this tile are visible -- also to the
         // TMA loads of other SMs -- before the row-block counter moves
-        if (threadIdx.x == 0) pair_stamp(dbg, pair, 3 + 5 * (int)it);
-        if (lane == 0) bulk_wait_all();
+        if (threadIdx.x == 0) pair_stamp(dbg, pair, 10 + 5 * (int)it);
+        if (lane == 0) {
+          bulk_wait_all();
+          mbar_arrive(epi_done);                     // this warp's staging buffer is free again
+        }
         __threadfence();
         fence_proxy_async_global();
-        if (threadIdx.x == 0) pair_stamp(dbg, pair, 4 + 5 * (int)it);
+        if (threadIdx.x == 0) pair_stamp(dbg, pair, 11 + 5 * (int)it);
         if (warp < 4) {
           named_bar_sync(2, kPrEpiThreads);
           if (threadIdx.x == 0) {
@@ -1100,7 +1200,7 @@ k_glm_tc_pair(const __grid_constant__ PairMaps maps, const PairSched sch,
               if (link.variance) link.variance[c] = m2_t / (float)link.n;
             }
           }
-          if (threadIdx.x == 0) pair_stamp(dbg, pair, 5 + 5 * (int)it);
+          if (threadIdx.x == 0) pair_stamp(dbg, pair, 12 + 5 * (int)it);
         } else {
           named_bar_arrive(2, kPrEpiThreads);
         }
@@ -1108,18 +1208,18 @@ k_glm_tc_pair(const __grid_constant__ PairMaps maps, const PairSched sch,
         // ---- gradient epilogue: G * 1/scale (+ theta * prior_coef) -> grad ----
         const float inv_scale = 1.0f / (gradp.r_scale * __ldg(gradp.xt_scale));
         const bool row_ok = row < gradp.C;
-        if (threadIdx.x == 0) pair_stamp(dbg, pair, 1 + 5 * (int)it);
-        mbar_wait(&acc_full[par], aph);
+        if (threadIdx.x == 0) pair_stamp(dbg, pair, 8 + 5 * (int)it);
+        wait_acc(&acc_full[par], aph);
         tc_fence_after();
-        if (threadIdx.x == 0) pair_stamp(dbg, pair, 2 + 5 * (int)it);
+        if (threadIdx.x == 0) pair_stamp(dbg, pair, 9 + 5 * (int)it);
 #pragma unroll 1
-        for (int ch = 0; ch < 2; ++ch) {
-          const int ct = cg * 64 + ch * 32;
+        for (int ch = 0; ch < kChunks; ++ch) {
+          const int ct = cg * (BN / 4) + ch * 32;
           const int col0 = n0 + ct;
           const int p0 = gradp.w_off + col0;
           uint32_t acc[32];
           tmem_ld32(tmem_row + (uint32_t)ct, acc);
-          if (ch == 1) {
+          if (ch == kChunks - 1) {
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_leader(&acc_empty[par]);
@@ -1154,16 +1254,30 @@ k_glm_tc_pair(const __grid_constant__ PairMaps maps, const PairSched sch,
             bulk_commit_group();
           }
         }
-        if (threadIdx.x == 0) pair_stamp(dbg, pair, 3 + 5 * (int)it);
+        if (lane == 0) {
+          bulk_wait_read_all();
+          mbar_arrive(epi_done);
+        }
+        if (threadIdx.x == 0) pair_stamp(dbg, pair, 10 + 5 * (int)it);
       }
     }
     if (lane == 0) bulk_wait_all();                  // staging buffers are read, stores performed
-    if (threadIdx.x == 0) pair_stamp(dbg, pair, 11);
+    if (threadIdx.x == 0) pair_stamp(dbg, pair, 6);
+    if (nz.xi != nullptr) {                          // whatever is left of the noise job
+      for (;;) {
+        int u = 0;
+        if (lane == 0) u = atomicAdd(s_noise_next, 1);
+        u = __shfl_sync(0xffffffffu, u, 0);
+        if (u >= nu1) break;
+        pair_noise_unit(nz, u, lane);
+      }
+    }
+    if (threadIdx.x == 0) pair_stamp(dbg, pair, 1);
   }
   __syncwarp();
   tc_fence_before();
   if (CG == 2) cluster_sync_all(); else __syncthreads();
-  if (warp == kPrEpiWarps + 1) tmem_dealloc_cg<CG>(tmem_base, 2 * kPrBN);
+  if (warp == kPrEpiWarps + 1) tmem_dealloc_cg<CG>(tmem_base, 2 * BN);
 }
 
 // ---------------------------------------------------------------------------
@@ -1210,6 +1324,7 @@ struct PrepareArgs {
   float* next_scale; uint32_t* amax_bits; const float* sumsq_part; int tiles_per_chain;
   // noise-key cache of the step's update: chain keys in, key' out, noise key out
   const uint32_t* keys_in; uint32_t* keys_out; uint32_t* noise_keys; int prng_layout;
+  int key_blocks;           // leading blocks that derive the noise keys (one thread per chain)
 };
 
 constexpr int kPrepTile = 64;   // minibatch tile: 64 observations x 64 features
@@ -1220,23 +1335,28 @@ __global__ void __launch_bounds__(256) k_prepare_all(const PrepareArgs a) {
   const int lane = threadIdx.x & 31;
   pdl_launch_dependents();
   pdl_wait();
-  if ((int)blockIdx.x < a.theta_blocks) {
-    if (blockIdx.x == 0)
-      for (int i = threadIdx.x; i < a.n_counters; i += 256) a.tile_counters[i] = 0u;
-    const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (row >= a.C) return;
-    if (a.keys_in != nullptr && lane == 31) {
-      // key', sub = split(key) (integrator.py:871); the single leaf's noise key is
-      // split(sub, 1)[0] (integrator.py:131-133): derived here, one lane per chain, so
-      // the update kernel starts without its serial key prologue
-      const Key k{a.keys_in[2 * row], a.keys_in[2 * row + 1]};
+  if ((int)blockIdx.x < a.key_blocks) {
+    // key', sub = split(key) (integrator.py:871); the single leaf's noise key is
+    // split(sub, 1)[0] (integrator.py:131-133): derived here, one THREAD per chain (four
+    // dependent threefry evaluations), so the update kernel starts without its serial
+    // key prologue
+    const int c = (int)blockIdx.x * 256 + (int)threadIdx.x;
+    if (c < a.C) {
+      const Key k{a.keys_in[2 * c], a.keys_in[2 * c + 1]};
       Key newk, sub;
       split2(k, a.prng_layout, newk, sub);
       const Key nk = split_key(sub, 0u, 1u, a.prng_layout);
-      a.noise_keys[2 * row] = nk.k0; a.noise_keys[2 * row + 1] = nk.k1;
-      a.keys_out[2 * row] = newk.k0; a.keys_out[2 * row + 1] = newk.k1;
+      a.noise_keys[2 * c] = nk.k0; a.noise_keys[2 * c + 1] = nk.k1;
+      a.keys_out[2 * c] = newk.k0; a.keys_out[2 * c + 1] = newk.k1;
     }
-    __syncwarp();
+    return;
+  }
+  const int bid = (int)blockIdx.x - a.key_blocks;
+  if (bid < a.theta_blocks) {
+    if (bid == 0)
+      for (int i = threadIdx.x; i < a.n_counters; i += 256) a.tile_counters[i] = 0u;
+    const int row = bid * 8 + (threadIdx.x >> 5);
+    if (row >= a.C) return;
     if (a.theta_mode == 2) {
       const float s_used = a.next_scale[row];
       const float amax = __uint_as_float(a.amax_bits[row]);
@@ -1376,7 +1496,7 @@ __global__ void __launch_bounds__(256) k_prepare_all(const PrepareArgs a) {
   }
   // ---- minibatch tile: gather, scale, split; row-major and transposed copies --------
   // (n and d are multiples of 8 on this path: element pairs never straddle an edge)
-  const int t = blockIdx.x - a.theta_blocks;
+  const int t = bid - a.theta_blocks;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;           // 32 x 8
   const int n = a.n, d = a.d;
   float s = 1.0f;
@@ -1612,10 +1732,10 @@ static int launch_gemm(cudaStream_t stream, const CUtensorMap& a0, const CUtenso
 }
 
 struct MapKey {
-  const void* base; const void* grad; int64_t C, n, P; int d, cg, split;
+  const void* base; const void* grad; int64_t C, n, P; int d, cg, bn, split;
   bool operator==(const MapKey& o) const {
     return base == o.base && grad == o.grad && C == o.C && n == o.n && P == o.P && d == o.d &&
-           cg == o.cg && split == o.split;
+           cg == o.cg && bn == o.bn && split == o.split;
   }
 };
 struct MapCacheEntry { MapKey key; PairMaps maps; };
@@ -1633,11 +1753,12 @@ static void map_cache_put(const MapKey& k, const PairMaps& m) {
   g_map_cache.push_back(MapCacheEntry{k, m});
 }
 
-template <int TERMS, int ABFMT, int CG>
+template <int TERMS, int ABFMT, int CG, int BN>
 static int launch_pair(cudaStream_t stream, const PairMaps& maps, const PairSched& sch,
-                       const TcLinkEpi& link, const TcGradEpi& gradp, const char* name) {
-  using S = PrSmem<TERMS, CG>;
-  auto kfn = k_glm_tc_pair<TERMS, ABFMT, CG>;
+                       const TcLinkEpi& link, const TcGradEpi& gradp, const PairNoise& nz,
+                       const char* name) {
+  using S = PrSmem<TERMS, CG, BN>;
+  auto kfn = k_glm_tc_pair<TERMS, ABFMT, CG, BN>;
   static bool attr_set = false;
   static int max_pairs = 0;
   cudaLaunchConfig_t cfg = {};
@@ -1670,9 +1791,10 @@ static int launch_pair(cudaStream_t stream, const PairMaps& maps, const PairSche
     }
     attr_set = true;
   }
-  const int pairs = std::min(max_pairs, sch.tiles_total);
+  // with a noise job every SM takes part, also pairs without a tile
+  const int pairs = nz.xi ? max_pairs : std::min(max_pairs, sch.tiles_total);
   cfg.gridDim = dim3(CG * pairs);
-  if (check_cuda(cudaLaunchKernelEx(&cfg, kfn, maps, sch, link, gradp), name)) return 1;
+  if (check_cuda(cudaLaunchKernelEx(&cfg, kfn, maps, sch, link, gradp, nz), name)) return 1;
   return post_launch(name);
 }
 
@@ -1757,8 +1879,9 @@ int glm_tc(cudaStream_t stream, const GlmArgs& a, int path) {
       cc->out.prior_lo = prior_lo; cc->out.prior_hi = prior_hi;
       cc->out.noise_keys = w.noise_keys;
     }
-    const unsigned grid =
-        (unsigned)(pa.theta_blocks + pa.x_tiles_x * ((n + kPrepTile - 1) / kPrepTile));
+    pa.key_blocks = pa.keys_in ? (int)((C + 255) / 256) : 0;
+    const unsigned grid = (unsigned)(pa.key_blocks + pa.theta_blocks +
+                                     pa.x_tiles_x * ((n + kPrepTile - 1) / kPrepTile));
     if (split) launch_pdl(k_prepare_all<true>, dim3(grid), dim3(256), 0, stream, pa);
     else launch_pdl(k_prepare_all<false>, dim3(grid), dim3(256), 0, stream, pa);
     if (post_launch("k_prepare_all")) return 1;
@@ -1798,11 +1921,12 @@ int glm_tc(cudaStream_t stream, const GlmArgs& a, int path) {
   // ---- default: both contractions in one persistent launch -----------------------
   if (!legacy) {
     const int cgn = option(SGMC_OPT_TC_CTA_GROUP) == 1 ? 1 : 2;
+    const int bn = option(SGMC_OPT_TC_TILE_N) == 128 ? 128 : 256;
     PairMaps maps;
     PairSched sch;
     sch.mt = (int)((C + BM * cgn - 1) / (BM * cgn));
-    sch.nt1 = (int)((n + kPrBN - 1) / kPrBN);
-    sch.nt2 = a.grad ? (d + kPrBN - 1) / kPrBN : 0;
+    sch.nt1 = (int)((n + bn - 1) / bn);
+    sch.nt2 = a.grad ? (d + bn - 1) / bn : 0;
     sch.kb1 = (d + kPrBK - 1) / kPrBK;
     sch.kb2 = (int)((n + kPrBK - 1) / kPrBK);
     sch.tiles1 = sch.mt * sch.nt1;
@@ -1810,19 +1934,19 @@ int glm_tc(cudaStream_t stream, const GlmArgs& a, int path) {
     sch.dbg = option(SGMC_OPT_TC_TIMELINE);
     // The maps only depend on the workspace / gradient addresses and the shapes:
     // encode them once per (workspace, shape) instead of once per step.
-    const MapKey mkey{base, a.grad, C, n, a.P, d, cgn, split ? 1 : 0};
+    const MapKey mkey{base, a.grad, C, n, a.P, d, cgn, bn, split ? 1 : 0};
     if (!map_cache_get(mkey, &maps)) {
-      const int dt = split ? 0 : 1, brows = kPrBN / cgn;
-      if (make_map_ex(&maps.a[0][0], w.th_hi, dt, C, d, BM, kPrBK, 64)) return 2;
-      if (make_map_ex(&maps.b[0][0], w.xb_hi, dt, n, d, brows, kPrBK, 64)) return 2;
-      if (make_map_ex(&maps.a[1][0], w.r_hi, dt, C, n, BM, kPrBK, 64)) return 2;
-      if (make_map_ex(&maps.b[1][0], w.xt_hi, dt, d, n, brows, kPrBK, 64)) return 2;
+      const int dt = split ? 0 : 1, brows = bn / cgn;
+      if (make_map_ex(&maps.a[0][0], w.th_hi, dt, C, d, BM, kPrBK, kPrSwz)) return 2;
+      if (make_map_ex(&maps.b[0][0], w.xb_hi, dt, n, d, brows, kPrBK, kPrSwz)) return 2;
+      if (make_map_ex(&maps.a[1][0], w.r_hi, dt, C, n, BM, kPrBK, kPrSwz)) return 2;
+      if (make_map_ex(&maps.b[1][0], w.xt_hi, dt, d, n, brows, kPrBK, kPrSwz)) return 2;
       if (make_map_ex(&maps.r[0], w.r_hi, dt, C, n, 32, 32, 64)) return 2;
       if (split) {
-        if (make_map_ex(&maps.a[0][1], w.th_lo, 0, C, d, BM, kPrBK, 64)) return 2;
-        if (make_map_ex(&maps.b[0][1], w.xb_lo, 0, n, d, brows, kPrBK, 64)) return 2;
-        if (make_map_ex(&maps.a[1][1], w.r_lo, 0, C, n, BM, kPrBK, 64)) return 2;
-        if (make_map_ex(&maps.b[1][1], w.xt_lo, 0, d, n, brows, kPrBK, 64)) return 2;
+        if (make_map_ex(&maps.a[0][1], w.th_lo, 0, C, d, BM, kPrBK, kPrSwz)) return 2;
+        if (make_map_ex(&maps.b[0][1], w.xb_lo, 0, n, d, brows, kPrBK, kPrSwz)) return 2;
+        if (make_map_ex(&maps.a[1][1], w.r_lo, 0, C, n, BM, kPrBK, kPrSwz)) return 2;
+        if (make_map_ex(&maps.b[1][1], w.xt_lo, 0, d, n, brows, kPrBK, kPrSwz)) return 2;
         if (make_map_ex(&maps.r[1], w.r_lo, 0, C, n, 32, 32, 64)) return 2;
       } else {
         maps.a[0][1] = maps.a[0][0]; maps.b[0][1] = maps.b[0][0];
@@ -1836,16 +1960,33 @@ int glm_tc(cudaStream_t stream, const GlmArgs& a, int path) {
       }
       map_cache_put(mkey, maps);
     }
+    PairNoise nz{};
     if (carry) {   // the update kernel adds the prior gradient (it reads theta anyway)
       cc->out.prior_coef = gradp.prior_coef;
       gradp.prior_lo = gradp.prior_hi = 0;
+      // the step's noise is generated under the mainloops when the layout allows
+      if (cc->prng_layout == 0 && d % 64 == 0 && !option(SGMC_OPT_NO_SHADOW_NOISE)) {
+        nz.xi = w.xi; nz.noise_keys = w.noise_keys; nz.d = d;
+        nz.units_per_chain = d / 64;
+        nz.units_total = (int)(C * (d / 64));
+        cc->out.xi = w.xi;
+      }
     }
+#define SGMC_PAIR_CASE(T, F, G, B, NAME) \
+    if (cgn == G && bn == B) return launch_pair<T, F, G, B>(stream, maps, sch, link, gradp, nz, NAME)
     if (split) {
-      if (cgn == 2) return launch_pair<3, 0, 2>(stream, maps, sch, link, gradp, "k_glm_tc_pair<split,2>");
-      return launch_pair<3, 0, 1>(stream, maps, sch, link, gradp, "k_glm_tc_pair<split,1>");
+      SGMC_PAIR_CASE(3, 0, 2, 128, "k_glm_tc_pair<split,2,128>");
+      SGMC_PAIR_CASE(3, 0, 2, 256, "k_glm_tc_pair<split,2,256>");
+      SGMC_PAIR_CASE(3, 0, 1, 128, "k_glm_tc_pair<split,1,128>");
+      SGMC_PAIR_CASE(3, 0, 1, 256, "k_glm_tc_pair<split,1,256>");
+    } else {
+      SGMC_PAIR_CASE(1, 1, 2, 128, "k_glm_tc_pair<bf16,2,128>");
+      SGMC_PAIR_CASE(1, 1, 2, 256, "k_glm_tc_pair<bf16,2,256>");
+      SGMC_PAIR_CASE(1, 1, 1, 128, "k_glm_tc_pair<bf16,1,128>");
+      SGMC_PAIR_CASE(1, 1, 1, 256, "k_glm_tc_pair<bf16,1,256>");
     }
-    if (cgn == 2) return launch_pair<1, 1, 2>(stream, maps, sch, link, gradp, "k_glm_tc_pair<bf16,2>");
-    return launch_pair<1, 1, 1>(stream, maps, sch, link, gradp, "k_glm_tc_pair<bf16,1>");
+#undef SGMC_PAIR_CASE
+    SGMC_REQUIRE(false, "no kernel for cta_group %d, tile %d", cgn, bn);
   }
 
   CUtensorMap mA0, mA1, mB0, mB1;

@@ -17,6 +17,8 @@ struct SgldSplitOut {
   float prior_coef;            // != 0: grad lacks the prior term; the update adds theta * coef
   float* grad_rw;              // the completed gradient is written back here (or null)
   const uint32_t* noise_keys;  // u32[C][2] noise keys derived earlier in the step, or null
+  const float* xi;             // f32[C][P]: the step's noise, generated earlier in the step
+                               // (k_glm_tc_pair's shadow job), or null: generate it here
 };
 
 // warp-tiles per chain of the update kernel for a one-leaf sample of P elements

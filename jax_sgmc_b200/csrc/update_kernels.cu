@@ -671,6 +671,58 @@ static int sgld_common(void* stream, float* theta, float* v, const float* grad,
 
 namespace sgmc {
 
+// The carried step's update when its noise was already generated (xi, by the potential
+// kernel's shadow job): one elementwise pass, one warp per 256 consecutive elements of a
+// chain (two float4 per lane), same arithmetic and outputs as SgldSplitOp::apply_vec2.
+// HBM-bound: reads theta, grad, v, xi (grad and xi were just written: L2 hits), writes
+// theta, v and the fp16 hi/lo (or bf16) operand form.
+template <bool RMS, bool FAST, int FMT>
+__global__ void __launch_bounds__(256)
+k_sgld_apply_split(const SgldSplitOp<RMS, FAST, FMT> op, const float* __restrict__ xi, int64_t P,
+                   int64_t n_tiles) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int lane = threadIdx.x & 31;
+  const int64_t tile = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (tile >= n_tiles) return;
+  const uint32_t tpc = op.tiles_per_chain;
+  const int64_t c = tile / tpc;
+  const uint32_t t = (uint32_t)(tile - c * tpc);
+  const float ns = op.scale_for(c);
+  const float s = FMT == 1 ? __ldg(op.scale + c) : 1.0f;
+  float sum = 0.f, amax = 0.f;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const uint32_t e = t * 256u + (uint32_t)h * 128u + (uint32_t)lane * 4u;
+    if (e < (uint32_t)P) {                       // P % 8 == 0: whole float4 or nothing
+      const int64_t i = c * P + e;
+      const float4 th = ld4(op.theta, i);
+      float4 g = ld4(op.grad, i);
+      const float4 x = ld4(xi, i);
+      float4 vv = RMS ? ld4(op.v, i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      if (op.prior_coef != 0.f) {
+        g = op.with_prior(g, th, e);
+        if (op.grad_rw) st4(op.grad_rw, i, g);
+      }
+      float4 o;
+      o.x = op.one(th.x, g.x, vv.x, x.x, ns);
+      o.y = op.one(th.y, g.y, vv.y, x.y, ns);
+      o.z = op.one(th.z, g.z, vv.z, x.z, ns);
+      o.w = op.one(th.w, g.w, vv.w, x.w, ns);
+      st4(op.theta, i, o);
+      if (RMS) st4(op.v, i, vv);
+      op.emit4(i, o, s);
+      sum += op.sq4(o, e, amax);
+    }
+  }
+#pragma unroll
+  for (int k = 16; k > 0; k >>= 1) {
+    sum += __shfl_xor_sync(0xffffffffu, sum, k);
+    amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, k));
+  }
+  if (lane == 0) op.reduce2(c, t, sum, amax);
+}
+
 template <bool RMS, bool FAST, int FMT>
 static int launch_split(cudaStream_t stream, const LeafTable& tab, const uint32_t* keys_in,
                         uint32_t* keys_out, int64_t C, int key_mode, int layout,
@@ -682,6 +734,12 @@ static int launch_split(cudaStream_t stream, const LeafTable& tab, const uint32_
   op.tiles_per_chain = tab.tiles_per_chain;
   op.prior_lo = (uint32_t)so.prior_lo; op.prior_hi = (uint32_t)so.prior_hi;
   op.prior_coef = so.prior_coef; op.grad_rw = so.grad_rw;
+  if (so.xi != nullptr) {
+    const int64_t n_tiles = C * (int64_t)tab.tiles_per_chain;
+    launch_pdl(k_sgld_apply_split<RMS, FAST, FMT>, dim3((unsigned)((n_tiles + 7) / 8)), dim3(256),
+               0, stream, op, so.xi, (int64_t)tab.P, n_tiles);
+    return post_launch("k_sgld_apply_split");
+  }
   return launch_noise_pass(stream, tab, keys_in, keys_out, C, key_mode, layout, op,
                            "sgmc_sgld_update<split>");
 }

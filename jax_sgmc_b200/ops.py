@@ -402,6 +402,9 @@ OPT_FUSED_STEP_EPILOGUE = 2  # 1: glm_sgld_step updates inside the gradient GEMM
 OPT_STEP_NOISE_IN_GEMM = 3   # 1: glm_sgld_step generates the noise in the GEMMs' idle warps
 STEP_CARRY_INIT, STEP_CARRY = 1, 2   # glm_sgld_step(carry=...): see sgmc_glm_sgld_step
 OPT_TC_LEGACY = 4            # 1: round-1 kernel sequence instead of the persistent fused potential kernel
+OPT_TC_TIMELINE = 6          # 1: k_glm_tc_pair records its phase timeline
+OPT_TC_TILE_N = 7            # accumulator columns per CTA and tile: 256 (default) or 128
+OPT_NO_SHADOW_NOISE = 8      # 1: noise in the update kernel instead of under the GEMM mainloops
 OPT_TC_CTA_GROUP = 5         # 2 (default): tcgen05 cta_group::2 on CTA pairs; 1: single CTAs
 
 

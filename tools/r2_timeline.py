@@ -1,10 +1,10 @@
 #!/usr/bin/env python
 """Phase timeline of k_glm_tc_pair at the C2 shape (SGMC_OPT_TC_TIMELINE):
 per CTA pair, ns since the earliest kernel start of
-  [0] start  per tile i (slots 1+5i..5+5i): epilogue ready / accumulator full /
-  chunks done / stores complete / published+finalised;  [11] epilogue warps done
-  [12,13] GEMM2 producer: begins to wait for R / R available
-  [14,15] MMA issue of tile 0 / last tile finished (issue, not completion)."""
+  [0] start  [1] epilogue warps done  [2,3] GEMM2 producer: begins to wait for R /
+  R available (last GEMM2 tile)  [4,5] MMA issue of tile 0 / last tile finished
+  per tile i < 4 (slots 8+5i..12+5i): epilogue ready / accumulator full / chunks
+  done / stores complete / published+finalised."""
 import ctypes as C
 import os
 import sys
@@ -31,20 +31,30 @@ lib.sgmc_debug_pair_timeline.argtypes = [C.c_void_p, C.c_int]
 ops.set_option(6, 1)
 for path in os.environ.get("PATHS", "tc_parity,tc_throughput").split(","):
   ws = ops.glm_workspace(Cc, n, d, path)
-  for rep in range(3):
-    ops.glm_potential_grad(spec, theta, X, y, idx, N, U, var, g, workspace=ws, path=path)
-    device.synchronize()
-  buf = (C.c_ulonglong * (80 * 16))()
-  lib.sgmc_debug_pair_timeline(buf, 80 * 16)
-  t = np.array(buf[:], dtype=np.int64).reshape(80, 16)
+  if os.environ.get("MODE", "potential") == "step":
+    # the carried Langevin step (the benchmark's hot path): prior gradient in the update
+    v = DA.full((Cc, d), 1.0)
+    kk = [ops.prng_keys(range(Cc)), DA((Cc, 2), np.uint32)]
+    for k in range(6):
+      ops.glm_sgld_step(spec, theta, X, y, idx, N, U, var, g, kk[k % 2], kk[(k + 1) % 2], 1e-3,
+                        1.0, v=v, workspace=ws, path=path, write_grad=False,
+                        carry=ops.STEP_CARRY_INIT if k == 0 else ops.STEP_CARRY)
+      device.synchronize()
+  else:
+    for rep in range(3):
+      ops.glm_potential_grad(spec, theta, X, y, idx, N, U, var, g, workspace=ws, path=path)
+      device.synchronize()
+  buf = (C.c_ulonglong * (80 * 32))()
+  lib.sgmc_debug_pair_timeline(buf, 80 * 32)
+  t = np.array(buf[:], dtype=np.int64).reshape(80, 32)
   used = t[:, 0] > 0
   t0 = t[used, 0].min()
   rel = np.where(t > 0, t - t0, -1)
-  print(f"== {path}: {used.sum()} pairs; columns = slots 0..15 (ns since first start, -1 unused)")
-  for p in (0, 1, 31, 32, 63):
+  print(f"== {path}: {used.sum()} pairs; columns = slots 0..31 (ns since first start, -1 unused)")
+  for p in (0, 33, 34, 54, 73):
     if p < 80 and used[p]:
       print(f"pair {p:2d}:", " ".join(f"{v:6d}" for v in rel[p]))
-  for sl in range(16):
+  for sl in range(32):
     col = rel[used, sl]
     col = col[col >= 0]
     if col.size:
