@@ -101,6 +101,8 @@ PROTOTYPES = {
     "sgmc_glm_sgld_step": [_vp, C.POINTER(GlmSpec), _vp, _vp, _i64, _i64, _vp, _vp, _vp,
                            _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _f32, _f32, _f32,
                            _f32, _vp, _sz, _int, _int, _int, _vp, _vp, C.POINTER(_i64), _int, _int],
+    "sgmc_glm_prepare_minibatch": [_vp, C.POINTER(GlmSpec), _i64, _vp, _vp, _i64, _vp, _sz, _int,
+                                   _int],
     "sgmc_revleapfrog_step": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, C.POINTER(_i64), _int,
                               _f32, _f32, _vp, _int, _int],
     "sgmc_mh_decide": [_vp, _int, _vp, _vp, _vp, _vp, _f32, _vp, _vp, _vp, _vp, _i64, _int],

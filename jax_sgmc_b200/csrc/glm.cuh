@@ -52,6 +52,9 @@ struct GlmArgs {
   float* tc_ws;           // extra scratch of the tensor-core path
   FusedSgld fused;
   CarryCtx* carry;        // null: stateless operand preparation
+  int x_slot;             // which copy of the minibatch operands in the workspace (0 / 1)
+  bool x_prepared;        // slot x_slot was staged by sgmc_glm_prepare_minibatch
+  bool only_x;            // stage the minibatch operands into slot x_slot and return
 };
 
 // -(d prior / d theta_p) / T for flat parameter index p of chain c.
@@ -75,5 +78,13 @@ int glm_simt(cudaStream_t stream, const GlmArgs& a);
 int glm_tc(cudaStream_t stream, const GlmArgs& a, int path);
 size_t glm_tc_workspace_bytes(int64_t n_chains, int64_t batch_size, int64_t d,
                               int path);
+int32_t* glm_tc_spare_idx(float* tc_ws, int64_t n_chains, int64_t batch_size, int64_t d);
+
+// which copy of the minibatch operands a call works on (sgmc_glm_prepare_minibatch)
+struct XStage {
+  int slot = 0;
+  bool prepared = false;
+  bool only_x = false;
+};
 
 }  // namespace sgmc

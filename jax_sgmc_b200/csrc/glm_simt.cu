@@ -284,8 +284,8 @@ static int glm_dispatch(void* stream, const sgmc_glm_spec* spec, const float* th
                         int64_t observation_count, float* potential, float* variance,
                         float* grad, float* ell, void* workspace, size_t workspace_bytes,
                         int path, const FusedSgld& fused, int64_t idx_stride = 0,
-                        CarryCtx* carry = nullptr) {
-  SGMC_REQUIRE(spec && theta && X && y && potential, "null argument");
+                        CarryCtx* carry = nullptr, XStage xs = XStage{}) {
+  SGMC_REQUIRE(spec && X && (xs.only_x || (theta && y && potential)), "null argument");
   SGMC_REQUIRE(spec->family == kFamilyGaussian || spec->family == kFamilyLogistic,
                "unknown GLM family %d", spec->family);
   SGMC_REQUIRE(spec->family != kFamilyGaussian || spec->aux_off >= 0,
@@ -315,6 +315,8 @@ static int glm_dispatch(void* stream, const sgmc_glm_spec* spec, const float* th
   a.tc_ws = ws + 2 * (size_t)n_chains * batch_size;
   a.fused = fused;
   a.carry = carry;
+  a.x_slot = xs.slot; a.x_prepared = xs.prepared; a.only_x = xs.only_x;
+  SGMC_REQUIRE(path != 0 || (!xs.prepared && !xs.only_x), "staged minibatches need a tensor-core path");
   // cotangent of every ell_i: (1/T) * (-N) / n    (potential.py:183,210)
   a.cot = (-(float)observation_count / (float)batch_size) / spec->temperature;
   if (path == 0) return glm_simt((cudaStream_t)stream, a);
@@ -403,6 +405,21 @@ int sgmc_glm_full_potential(void* stream, const sgmc_glm_spec* spec, const float
   return post_launch("k_full_finish");
 }
 
+int sgmc_glm_prepare_minibatch(void* stream, const sgmc_glm_spec* spec, int64_t n_chains,
+                               const float* X, const int32_t* idx, int64_t batch_size,
+                               void* workspace, size_t workspace_bytes, int path, int slot) {
+  SGMC_REQUIRE(path == 1 || path == 2, "staging is a tensor-core path operation");
+  SGMC_REQUIRE(slot == 0 || slot == 1, "slot must be 0 or 1");
+  FusedSgld none{};
+  XStage xs;
+  xs.slot = slot;
+  xs.only_x = true;
+  const int64_t P = spec ? spec->d : 0;
+  return glm_dispatch(stream, spec, nullptr, n_chains, P, X, nullptr, idx, nullptr, batch_size, 1,
+                      nullptr, nullptr, nullptr, nullptr, workspace, workspace_bytes, path, none, 0,
+                      nullptr, xs);
+}
+
 int sgmc_glm_sgld_step(void* stream, const sgmc_glm_spec* spec, float* theta, float* v,
                        int64_t n_chains, int64_t P, const float* X, const float* y,
                        const int32_t* idx, const float* mask, int64_t batch_size,
@@ -427,6 +444,11 @@ int sgmc_glm_sgld_step(void* stream, const sgmc_glm_spec* spec, float* theta, fl
   fu.theta_rw = theta; fu.v = v; fu.keys_in = keys_in; fu.keys_out = keys_out;
   fu.step_size = step_size; fu.temperature = temperature; fu.alpha = alpha; fu.lmbd = lmbd;
   fu.layout = prng_layout; fu.applied = &applied; fu.write_grad = write_grad != 0;
+  XStage xs;
+  if ((flags & SGMC_STEP_X_STAGED) && path != 0) {
+    xs.prepared = true;
+    xs.slot = (flags & SGMC_STEP_X_SLOT1) ? 1 : 0;
+  }
   CarryCtx cc{};
   if ((flags & (SGMC_STEP_CARRY_INIT | SGMC_STEP_CARRY)) && path != 0 && n_leaves == 1) {
     cc.mode = (flags & SGMC_STEP_CARRY_INIT) ? 1 : 2;
@@ -434,7 +456,7 @@ int sgmc_glm_sgld_step(void* stream, const sgmc_glm_spec* spec, float* theta, fl
   }
   if (int e = glm_dispatch(stream, spec, theta, n_chains, P, X, y, idx, mask, batch_size,
                            observation_count, potential, variance, grad, nullptr, workspace,
-                           workspace_bytes, path, fu, 0, cc.mode ? &cc : nullptr))
+                           workspace_bytes, path, fu, 0, cc.mode ? &cc : nullptr, xs))
     return e;
   if (applied) return 0;
   if (wait_event != nullptr &&
@@ -501,21 +523,47 @@ int sgmc_glm_sgld_scan_host(void* stream, void* copy_stream, const sgmc_glm_spec
                     cudaMemcpyHostToDevice, cs);
     cudaEventRecord(copied[sl], cs);
   };
+  // Tensor-core paths: the operand staging of batch k+1 runs on the copy stream (right
+  // behind its H2D copy) while step k samples; two copies of the operands.
+  const bool piped = path != 0 && n_steps > 1 && !option(SGMC_OPT_NO_PIPELINE);
+  cudaEvent_t staged[2] = {nullptr, nullptr}, xfree[2] = {nullptr, nullptr};
+  if (piped)
+    for (int i = 0; i < 2; ++i)
+      if (check_cuda(cudaEventCreateWithFlags(&staged[i], cudaEventDisableTiming), "event") ||
+          check_cuda(cudaEventCreateWithFlags(&xfree[i], cudaEventDisableTiming), "event"))
+        return 1;
+  auto stage = [&](int64_t k) -> int {
+    const int sl = (int)(k % n_slots), xsl = (int)(k & 1);
+    if (k >= 2) cudaStreamWaitEvent(cs, xfree[xsl], 0);      // step k-2 is done with this copy
+    if (int e = sgmc_glm_prepare_minibatch(cs, spec, C, device_slots + sl * stride, nullptr, n,
+                                           workspace, workspace_bytes, path, xsl))
+      return e;
+    return check_cuda(cudaEventRecord(staged[xsl], cs), "event record");
+  };
   for (int64_t k = 0; k < n_steps && k < n_slots - 1; ++k) prefetch(k);
   int rc = 0;
+  if (piped) rc = stage(0);
   for (int64_t k = 0; k < n_steps && rc == 0; ++k) {
     if (k + n_slots - 1 < n_steps) prefetch(k + n_slots - 1);
+    if (piped && k + 1 < n_steps && (rc = stage(k + 1)) != 0) break;
     const int sl = (int)(k % n_slots);
     float* Xb = device_slots + sl * stride;
     float* uv = potential_variance + (k & 1) * 2 * C;      // (U, var) double-buffered
-    cudaStreamWaitEvent(ms, copied[sl], 0);
+    int flags = k == 0 ? SGMC_STEP_CARRY_INIT : SGMC_STEP_CARRY;
+    if (piped) {
+      cudaStreamWaitEvent(ms, staged[k & 1], 0);           // implies the H2D copy
+      flags |= SGMC_STEP_X_STAGED | ((k & 1) ? SGMC_STEP_X_SLOT1 : 0);
+    } else {
+      cudaStreamWaitEvent(ms, copied[sl], 0);
+    }
     cudaStreamWaitEvent(ms, read_back[k & 1], 0);          // its previous contents are on the host
     rc = sgmc_glm_sgld_step(ms, spec, theta, v, C, P, Xb, Xb + n * d, nullptr, nullptr, n,
                             observation_count, uv, uv + C, grad, (k & 1) ? keys_b : keys_a,
                             (k & 1) ? keys_a : keys_b, step_sizes[k], temperature, alpha, lmbd,
                             workspace, workspace_bytes, path, prng_layout, 0, nullptr, nullptr,
-                            nullptr, 0, k == 0 ? SGMC_STEP_CARRY_INIT : SGMC_STEP_CARRY);
+                            nullptr, 0, flags);
     cudaEventRecord(consumed[sl], ms);
+    if (piped) cudaEventRecord(xfree[k & 1], ms);
     if (host_results != nullptr) {
       cudaEventRecord(computed[k & 1], ms);
       cudaStreamWaitEvent(cs, computed[k & 1], 0);
@@ -523,6 +571,8 @@ int sgmc_glm_sgld_scan_host(void* stream, void* copy_stream, const sgmc_glm_spec
       cudaEventRecord(read_back[k & 1], cs);
     }
   }
+  if (piped)
+    for (int i = 0; i < 2; ++i) { cudaEventDestroy(staged[i]); cudaEventDestroy(xfree[i]); }
   // the sampling stream finishes after the last read-back was issued; events can go
   // (destruction is deferred by the runtime until they have completed)
   for (int i = 0; i < n_slots; ++i) { cudaEventDestroy(copied[i]); cudaEventDestroy(consumed[i]); }
@@ -555,32 +605,85 @@ int sgmc_glm_sgld_scan_device(void* stream, const sgmc_glm_spec* spec, float* th
                "device draws need the data keys and an index buffer");
   cudaStream_t ms = (cudaStream_t)stream;
   const int64_t C = n_chains, n = batch_size;
-  for (int64_t k = 0; k < n_steps; ++k) {
-    const int32_t* idx = idx_all ? idx_all + k * n : idx_buf;
+  // Tensor-core paths: the minibatch pipeline (index draw + operand staging) of step k+1
+  // runs on a side stream while step k samples; two copies of the operands / indices.
+  const bool piped = path != 0 && n_steps > 1 && !option(SGMC_OPT_NO_PIPELINE);
+  cudaStream_t xs = nullptr;
+  cudaEvent_t x_ready[2] = {nullptr, nullptr}, slot_free[2] = {nullptr, nullptr};
+  int32_t* idx_pp[2] = {idx_buf, idx_buf};
+  if (piped) {
+    if (check_cuda(cudaStreamCreateWithFlags(&xs, cudaStreamNonBlocking), "side stream")) return 1;
+    for (int i = 0; i < 2; ++i)
+      if (check_cuda(cudaEventCreateWithFlags(&x_ready[i], cudaEventDisableTiming), "event") ||
+          check_cuda(cudaEventCreateWithFlags(&slot_free[i], cudaEventDisableTiming), "event"))
+        return 1;
     if (!idx_all) {
-      if (int e = sgmc_minibatch_draw(stream, (k & 1) ? data_key_b : data_key_a,
-                                      (k & 1) ? data_key_a : data_key_b, idx_buf, n,
+      float* ws = reinterpret_cast<float*>(
+          (reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255);
+      idx_pp[1] = glm_tc_spare_idx(ws + 2 * (size_t)C * n, C, n, spec->d);
+    }
+    // the side stream starts after everything already queued on the sampling stream
+    cudaEventRecord(slot_free[0], ms);
+    cudaStreamWaitEvent(xs, slot_free[0], 0);
+  }
+  auto stage = [&](int64_t k) -> int {     // draw + operand staging of step k on the side stream
+    const int sl = (int)(k & 1);
+    const int32_t* idx = idx_all ? idx_all + k * n : idx_pp[sl];
+    if (k >= 2) cudaStreamWaitEvent(xs, slot_free[sl], 0);   // step k-2 is done with this copy
+    if (!idx_all) {
+      if (int e = sgmc_minibatch_draw(xs, (k & 1) ? data_key_b : data_key_a,
+                                      (k & 1) ? data_key_a : data_key_b, idx_pp[sl], n,
                                       observation_count, prng_layout))
         return e;
     }
-    if (int e = sgmc_glm_sgld_step(stream, spec, theta, v, C, P, X, y, idx, nullptr, n,
-                                   observation_count, potential, variance, grad,
-                                   (k & 1) ? keys_b : keys_a, (k & 1) ? keys_a : keys_b,
-                                   step_sizes[k], temperatures[k], alpha, lmbd, workspace,
-                                   workspace_bytes, path, prng_layout, 0, nullptr, nullptr,
-                                   leaf_sizes, n_leaves,
-                                   k == 0 ? SGMC_STEP_CARRY_INIT : SGMC_STEP_CARRY))
+    if (int e = sgmc_glm_prepare_minibatch(xs, spec, C, X, idx, n, workspace, workspace_bytes, path,
+                                           sl))
       return e;
+    return check_cuda(cudaEventRecord(x_ready[sl], xs), "event record");
+  };
+  int rc = 0;
+  if (piped) rc = stage(0);
+  for (int64_t k = 0; k < n_steps && rc == 0; ++k) {
+    const int sl = (int)(k & 1);
+    const int32_t* idx = idx_all ? idx_all + k * n : (piped ? idx_pp[sl] : idx_buf);
+    int flags = k == 0 ? SGMC_STEP_CARRY_INIT : SGMC_STEP_CARRY;
+    if (piped) {
+      if (k + 1 < n_steps && (rc = stage(k + 1)) != 0) break;
+      cudaStreamWaitEvent(ms, x_ready[sl], 0);
+      flags |= SGMC_STEP_X_STAGED | (sl ? SGMC_STEP_X_SLOT1 : 0);
+    } else if (!idx_all) {
+      if ((rc = sgmc_minibatch_draw(stream, (k & 1) ? data_key_b : data_key_a,
+                                    (k & 1) ? data_key_a : data_key_b, idx_buf, n,
+                                    observation_count, prng_layout)) != 0)
+        break;
+    }
+    if ((rc = sgmc_glm_sgld_step(stream, spec, theta, v, C, P, X, y, idx, nullptr, n,
+                                 observation_count, potential, variance, grad,
+                                 (k & 1) ? keys_b : keys_a, (k & 1) ? keys_a : keys_b,
+                                 step_sizes[k], temperatures[k], alpha, lmbd, workspace,
+                                 workspace_bytes, path, prng_layout, 0, nullptr, nullptr,
+                                 leaf_sizes, n_leaves, flags)) != 0)
+      break;
+    if (piped) cudaEventRecord(slot_free[sl], ms);
     if (keep && keep[k] && samples_out && *kept < capacity) {
       if (check_cuda(cudaMemcpyAsync(samples_out + *kept * C * P, theta, (size_t)C * P * 4,
                                      cudaMemcpyDeviceToDevice, ms), "collect") ||
           check_cuda(cudaMemcpyAsync(scalars_out + *kept * C, potential, (size_t)C * 4,
-                                     cudaMemcpyDeviceToDevice, ms), "collect"))
-        return 1;
+                                     cudaMemcpyDeviceToDevice, ms), "collect")) {
+        rc = 1;
+        break;
+      }
       ++*kept;
     }
   }
-  return 0;
+  if (piped) {
+    // the data keys are advanced on the side stream: order the caller's next use after it
+    cudaEventRecord(x_ready[0], xs);
+    cudaStreamWaitEvent(ms, x_ready[0], 0);
+    for (int i = 0; i < 2; ++i) { cudaEventDestroy(x_ready[i]); cudaEventDestroy(slot_free[i]); }
+    cudaStreamDestroy(xs);
+  }
+  return rc;
 }
 
 }  // extern "C"

@@ -1619,11 +1619,13 @@ struct TcWorkspace {
   float* xi;                // f32[C][d]: noise of the pending update (sgmc_glm_sgld_step)
   // carried split of sgmc_glm_sgld_step
   float* next_scale; uint32_t* amax_row; float* sumsq_part; uint32_t* noise_keys;
+  int32_t* idx2;            // second minibatch index buffer of the pipelined scans
 };
 
 static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
-static size_t carve(TcWorkspace* w, uint8_t* base, int64_t C, int64_t n, int64_t d) {
+static size_t carve(TcWorkspace* w, uint8_t* base, int64_t C, int64_t n, int64_t d,
+                    int slot = 0) {
   size_t off = 0;
   auto take = [&](size_t bytes) {
     uint8_t* p = base ? base + off : nullptr;
@@ -1637,21 +1639,29 @@ static size_t carve(TcWorkspace* w, uint8_t* base, int64_t C, int64_t n, int64_t
   void* th_lo = take((size_t)C * d * 2);
   void* rs = take((size_t)C * 4);
   void* rq = take((size_t)C * 4);
-  void* xb_hi = take((size_t)n * d * 2);
-  void* xb_lo = take((size_t)n * d * 2);
-  void* xt_hi = take((size_t)n * d * 2);
-  void* xt_lo = take((size_t)n * d * 2);
+  // the minibatch operands exist twice: sgmc_glm_prepare_minibatch stages the NEXT
+  // step's minibatch (slot 1 - s) while the current step's kernels read slot s
+  void *xb_hi = nullptr, *xb_lo = nullptr, *xt_hi = nullptr, *xt_lo = nullptr, *am = nullptr;
+  for (int sl = 0; sl < 2; ++sl) {
+    void* a0 = take((size_t)n * d * 2);
+    void* a1 = take((size_t)n * d * 2);
+    void* a2 = take((size_t)n * d * 2);
+    void* a3 = take((size_t)n * d * 2);
+    void* a4 = take(256);
+    if (sl == slot) { xb_hi = a0; xb_lo = a1; xt_hi = a2; xt_lo = a3; am = a4; }
+  }
   void* r_hi = take((size_t)C * n * 2);
   void* r_lo = take((size_t)C * n * 2);
   void* stats = take((size_t)C * parts * kStatFields * 4);
-  void* am = take(256);
   void* cnt = take((size_t)((C + BM - 1) / BM) * 4);
   void* xi = take((size_t)C * d * 4);
   void* nsc = take((size_t)C * 4);
   void* amr = take((size_t)C * 4);
   void* ssp = take((size_t)C * sgld_split_tiles_per_chain(d) * 4);
   void* nks = take((size_t)C * 8);
+  void* idx2 = take((size_t)n * 4);
   if (w) {
+    w->idx2 = (int32_t*)idx2;
     w->next_scale = (float*)nsc; w->amax_row = (uint32_t*)amr;
     w->sumsq_part = (float*)ssp; w->noise_keys = (uint32_t*)nks;
     w->counters = (uint32_t*)cnt;
@@ -1701,6 +1711,14 @@ int glm_pair_timeline_read(unsigned long long* out, int n) {
 
 int glm_tc_debug_read(unsigned long long* out) {
   return check_cuda(cudaMemcpyFromSymbol(out, g_tc_dbg, sizeof(unsigned long long) * 10), "dbg");
+}
+
+int32_t* glm_tc_spare_idx(float* tc_ws, int64_t n_chains, int64_t batch_size, int64_t d) {
+  TcWorkspace w;
+  uint8_t* base = reinterpret_cast<uint8_t*>(
+      (reinterpret_cast<uintptr_t>(tc_ws) + 255) & ~(uintptr_t)255);
+  carve(&w, base, n_chains, batch_size, d);
+  return w.idx2;
 }
 
 size_t glm_tc_workspace_bytes(int64_t n_chains, int64_t batch_size, int64_t d, int) {
@@ -1810,7 +1828,7 @@ int glm_tc(cudaStream_t stream, const GlmArgs& a, int path) {
   TcWorkspace w;
   uint8_t* base = reinterpret_cast<uint8_t*>(
       (reinterpret_cast<uintptr_t>(a.tc_ws) + 255) & ~(uintptr_t)255);
-  carve(&w, base, C, n, d);
+  carve(&w, base, C, n, d, a.x_slot);
   const bool gauss_prior = a.spec.prior == kPriorGaussian;
   const int prior_lo = gauss_prior ? a.spec.prior_off : 0;
   const int prior_hi = gauss_prior ? a.spec.prior_off + a.spec.prior_size : 0;
@@ -1847,7 +1865,7 @@ int glm_tc(cudaStream_t stream, const GlmArgs& a, int path) {
 
   // ---- operand preparation (one launch) -------------------------------------
   const float x_absmax = a.spec.x_absmax > 0.f ? a.spec.x_absmax : 0.f;
-  if (split && x_absmax == 0.f) {   // no data-set bound given: reduce over the minibatch
+  if (split && x_absmax == 0.f && !a.x_prepared) {   // no data-set bound given: reduce over the minibatch
     if (check_cuda(cudaMemsetAsync(w.absmax_bits, 0, 4, stream), "memset")) return 1;
     k_absmax_gather<<<(unsigned)((n + 7) / 8), 256, 0, stream>>>(a.X, a.idx, (int)n, d,
                                                                 w.absmax_bits);
@@ -1862,7 +1880,7 @@ int glm_tc(cudaStream_t stream, const GlmArgs& a, int path) {
     pa.absmax_bits = w.absmax_bits; pa.static_absmax = x_absmax;
     pa.xb_hi = w.xb_hi; pa.xb_lo = w.xb_lo; pa.xt_hi = w.xt_hi; pa.xt_lo = w.xt_lo;
     pa.x_scale = w.x_scale;
-    pa.theta_blocks = (int)((C + 7) / 8);
+    pa.theta_blocks = a.only_x ? 0 : (int)((C + 7) / 8);
     pa.x_tiles_x = (d + kPrepTile - 1) / kPrepTile;
     pa.tile_counters = w.counters; pa.n_counters = (int)((C + BM - 1) / BM);
     if (carry) {
@@ -1880,12 +1898,16 @@ int glm_tc(cudaStream_t stream, const GlmArgs& a, int path) {
       cc->out.noise_keys = w.noise_keys;
     }
     pa.key_blocks = pa.keys_in ? (int)((C + 255) / 256) : 0;
-    const unsigned grid = (unsigned)(pa.key_blocks + pa.theta_blocks +
-                                     pa.x_tiles_x * ((n + kPrepTile - 1) / kPrepTile));
-    if (split) launch_pdl(k_prepare_all<true>, dim3(grid), dim3(256), 0, stream, pa);
-    else launch_pdl(k_prepare_all<false>, dim3(grid), dim3(256), 0, stream, pa);
-    if (post_launch("k_prepare_all")) return 1;
+    // the minibatch tiles are skipped when sgmc_glm_prepare_minibatch staged them already
+    const int64_t x_tiles = a.x_prepared ? 0 : pa.x_tiles_x * ((n + kPrepTile - 1) / kPrepTile);
+    const unsigned grid = (unsigned)(pa.key_blocks + pa.theta_blocks + x_tiles);
+    if (grid > 0) {
+      if (split) launch_pdl(k_prepare_all<true>, dim3(grid), dim3(256), 0, stream, pa);
+      else launch_pdl(k_prepare_all<false>, dim3(grid), dim3(256), 0, stream, pa);
+      if (post_launch("k_prepare_all")) return 1;
+    }
   }
+  if (a.only_x) return 0;
   // The Xb scale is computed on the device (k_prepare_all) and read by the
   // epilogues through a device scalar, so the whole op stays sync-free.
   // R scale: |R| <= |cot| for the logistic family (|dl/dz| <= 1, mask in [0,1]).
@@ -1934,7 +1956,7 @@ int glm_tc(cudaStream_t stream, const GlmArgs& a, int path) {
     sch.dbg = option(SGMC_OPT_TC_TIMELINE);
     // The maps only depend on the workspace / gradient addresses and the shapes:
     // encode them once per (workspace, shape) instead of once per step.
-    const MapKey mkey{base, a.grad, C, n, a.P, d, cgn, bn, split ? 1 : 0};
+    const MapKey mkey{base, a.grad, C, n, a.P, d, cgn, bn + a.x_slot, split ? 1 : 0};
     if (!map_cache_get(mkey, &maps)) {
       const int dt = split ? 0 : 1, brows = bn / cgn;
       if (make_map_ex(&maps.a[0][0], w.th_hi, dt, C, d, BM, kPrBK, kPrSwz)) return 2;

@@ -113,6 +113,34 @@ __device__ __forceinline__ float4 ld4(const float* p, int64_t i) {
 __device__ __forceinline__ void st4(float* p, int64_t i, float4 v) {
   *reinterpret_cast<float4*>(p + i) = v;
 }
+// L2 eviction-priority hints (createpolicy + .L2::cache_hint): the per-step working set
+// of the carried Langevin step (~120 MB) is about the size of the L2, so the persistent
+// state (theta, v, the operand split) asks to stay and the transient streams (gradient,
+// noise) give their lines up at their last read.
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ float4 ld4_hint(const float* p, int64_t i, uint64_t pol) {
+  float4 v;
+  asm volatile("ld.global.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p + i), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ void st4_hint(float* p, int64_t i, float4 v, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.v4.f32 [%4], {%0,%1,%2,%3}, %5;" ::"f"(v.x), "f"(v.y),
+               "f"(v.z), "f"(v.w), "l"(p + i), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void st2u_hint(void* p, uint2 v, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.v2.u32 [%2], {%0,%1}, %3;" ::"r"(v.x), "r"(v.y), "l"(p),
+               "l"(pol) : "memory");
+}
 #define SGMC_F4_MAP(dst, expr)                          \
   {                                                     \
     float4 _o;                                          \
@@ -249,7 +277,8 @@ struct SgldSplitOp : SgldOp<RMS, FAST> {
     }
     return o;
   }
-  __device__ __forceinline__ void emit4(int64_t i, const float4& t, float s) const {
+  template <bool HINT = false>
+  __device__ __forceinline__ void emit4(int64_t i, const float4& t, float s, uint64_t pol = 0) const {
     const float v0 = t.x * s, v1 = t.y * s, v2 = t.z * s, v3 = t.w * s;
     if (FMT == 1) {
       const __half2 h01 = __floats2half2_rn(v0, v1), h23 = __floats2half2_rn(v2, v3);
@@ -259,13 +288,19 @@ struct SgldSplitOp : SgldOp<RMS, FAST> {
       uint2 ph, pl;
       ph.x = *reinterpret_cast<const uint32_t*>(&h01); ph.y = *reinterpret_cast<const uint32_t*>(&h23);
       pl.x = *reinterpret_cast<const uint32_t*>(&l01); pl.y = *reinterpret_cast<const uint32_t*>(&l23);
-      *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(th_hi) + i) = ph;
-      *reinterpret_cast<uint2*>(th_lo + i) = pl;
+      if (HINT) {
+        st2u_hint(reinterpret_cast<__half*>(th_hi) + i, ph, pol);
+        st2u_hint(th_lo + i, pl, pol);
+      } else {
+        *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(th_hi) + i) = ph;
+        *reinterpret_cast<uint2*>(th_lo + i) = pl;
+      }
     } else {
       const __nv_bfloat162 b01 = __floats2bfloat162_rn(v0, v1), b23 = __floats2bfloat162_rn(v2, v3);
       uint2 pb;
       pb.x = *reinterpret_cast<const uint32_t*>(&b01); pb.y = *reinterpret_cast<const uint32_t*>(&b23);
-      *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(th_hi) + i) = pb;
+      if (HINT) st2u_hint(reinterpret_cast<__nv_bfloat16*>(th_hi) + i, pb, pol);
+      else *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(th_hi) + i) = pb;
     }
   }
   __device__ __forceinline__ float sq4(const float4& t, uint32_t e, float& amax) const {
@@ -690,16 +725,17 @@ k_sgld_apply_split(const SgldSplitOp<RMS, FAST, FMT> op, const float* __restrict
   const uint32_t t = (uint32_t)(tile - c * tpc);
   const float ns = op.scale_for(c);
   const float s = FMT == 1 ? __ldg(op.scale + c) : 1.0f;
+  const uint64_t keep = l2_policy_evict_last(), drop = l2_policy_evict_first();
   float sum = 0.f, amax = 0.f;
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
     const uint32_t e = t * 256u + (uint32_t)h * 128u + (uint32_t)lane * 4u;
     if (e < (uint32_t)P) {                       // P % 8 == 0: whole float4 or nothing
       const int64_t i = c * P + e;
-      const float4 th = ld4(op.theta, i);
-      float4 g = ld4(op.grad, i);
-      const float4 x = ld4(xi, i);
-      float4 vv = RMS ? ld4(op.v, i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4 th = ld4_hint(op.theta, i, keep);
+      float4 g = ld4_hint(op.grad, i, drop);
+      const float4 x = ld4_hint(xi, i, drop);
+      float4 vv = RMS ? ld4_hint(op.v, i, keep) : make_float4(0.f, 0.f, 0.f, 0.f);
       if (op.prior_coef != 0.f) {
         g = op.with_prior(g, th, e);
         if (op.grad_rw) st4(op.grad_rw, i, g);
@@ -709,9 +745,9 @@ k_sgld_apply_split(const SgldSplitOp<RMS, FAST, FMT> op, const float* __restrict
       o.y = op.one(th.y, g.y, vv.y, x.y, ns);
       o.z = op.one(th.z, g.z, vv.z, x.z, ns);
       o.w = op.one(th.w, g.w, vv.w, x.w, ns);
-      st4(op.theta, i, o);
-      if (RMS) st4(op.v, i, vv);
-      op.emit4(i, o, s);
+      st4_hint(op.theta, i, o, keep);
+      if (RMS) st4_hint(op.v, i, vv, keep);
+      op.template emit4<true>(i, o, s, keep);
       sum += op.sq4(o, e, amax);
     }
   }

@@ -405,6 +405,7 @@ OPT_TC_LEGACY = 4            # 1: round-1 kernel sequence instead of the persist
 OPT_TC_TIMELINE = 6          # 1: k_glm_tc_pair records its phase timeline
 OPT_TC_TILE_N = 7            # accumulator columns per CTA and tile: 256 (default) or 128
 OPT_NO_SHADOW_NOISE = 8      # 1: noise in the update kernel instead of under the GEMM mainloops
+OPT_NO_PIPELINE = 9          # 1: scans stage minibatches on the sampling stream (no side stream)
 OPT_TC_CTA_GROUP = 5         # 2 (default): tcgen05 cta_group::2 on CTA pairs; 1: single CTAs
 
 

@@ -132,7 +132,14 @@ def test_c2_full_step_keys_rows_determinism(c2):
                            np.zeros(len(rows), np.float32), np.ones(len(rows), np.float32))
   want = osgmc.langevin_update(st, lambda th: pot(th, (c2["Xb"], c2["yb"]), N), [d], 1e-3, 1.0)
   scale = np.abs(want.theta).max(axis=1, keepdims=True)
-  assert (np.abs(t1[rows] - want.theta) / scale).max() < 1e-5
+  # Cold start of RMSprop (v = 1 while g^2 ~ 1e5): coordinates with |g| of order one sit
+  # on the steep part of g / sqrt(0.9 + 0.1 g^2), so an ABSOLUTE gradient error of 1e-5
+  # of the row's max |g| (tensor-core accumulation, asserted above) moves theta' by
+  # eps * 1e-5 * max|g| ~ 1e-5 -- 5e-5 of this test's small |theta| ~ 0.15.  Any fp32
+  # gradient shows the same amplification against an fp64 one
+  # (tools/r2_cold_start_amplification.py); it disappears once v has adapted, which is
+  # what the 1 000-step trajectory test below bounds by 1e-5.
+  assert (np.abs(t1[rows] - want.theta) / scale).max() < 1e-4
   np.testing.assert_allclose(U1[rows], want.potential, rtol=1e-5)
   # noise + update on the device's own gradient agree to the last bits
   # (default mode: SFU sqrt / rcp, <= 2 ulp)
@@ -189,3 +196,52 @@ def test_c3_sghmc_step_full_size(gpu):
   assert np.array_equal(got_p[rows].view(np.uint32), want.momentum.view(np.uint32))
   # every other chain moved too (zero gradient: pure noise + friction)
   assert np.all(np.abs(got_p).max(axis=1) > 0)
+
+
+@pytest.mark.parametrize("carried", [True, False])
+def test_c2_trajectory_1000_steps_sampled_chains(gpu, carried):
+  """north star: "parameter trajectories ... within rtol 1e-5 (fp32) after 1,000
+  steps".  All 4096 chains x 1024 features (batch 1024) run 1 000 pSGLD steps on
+  the benchmarked path (tensor-core parity potential, RMSprop, carried operand
+  split + shadow noise when `carried`); eight sampled chains are compared with
+  the oracle run on those chains alone (chains are independent), same keys, same
+  minibatch stream.  N = 65 536 observations so the host copy the oracle gathers
+  from stays small; C, d, n are the C2 sizes."""
+  from jax_sgmc_b200 import ops
+  from jax_sgmc_b200.device import DeviceArray as DA
+  from oracle import data as odata
+  from oracle import scheduler as osched
+  C, d, n, N, K = 4096, 1024, 1024, 65536, 1000
+  X, y, _ = ops.synth_logistic_data(0, N, d)
+  hX, hy = X.numpy(), y.numpy()
+  rows = np.array([0, 1, 777, 2047, 2048, 3000, 4094, 4095])
+  keys = np.stack([prng.PRNGKey(c) for c in range(C)])
+  eps = osched.polynomial_step_size_first_last(K, 1e-2, 1e-3)
+  spec = ops.glm_spec("logistic", d, 0, prior="gaussian", prior_off=0, prior_size=d,
+                      prior_scale=10.0, x_absmax=ops.absmax(X))
+  theta, v = DA.zeros((C, d)), DA.full((C, d), 1.0)
+  U, var, g = DA((C,), np.float32), DA((C,), np.float32), DA((C, d), np.float32)
+  kk = [DA.from_numpy(keys), DA((C, 2), np.uint32)]
+  dk = [DA.from_numpy(prng.PRNGKey(0)), DA((2,), np.uint32)]
+  idx = DA((n,), np.int32)
+  ws = ops.glm_workspace(C, n, d, "tc_parity")
+  for k in range(K):
+    ops.minibatch_draw(dk[k % 2], dk[(k + 1) % 2], idx, N)
+    carry = 0 if not carried else (ops.STEP_CARRY_INIT if k == 0 else ops.STEP_CARRY)
+    ops.glm_sgld_step(spec, theta, X, y, idx, N, U, var, g, kk[k % 2], kk[(k + 1) % 2],
+                      float(eps[k]), 1.0, v=v, workspace=ws, path="tc_parity",
+                      write_grad=False, carry=carry)
+  got, gotU = theta.numpy()[rows], U.numpy()[rows]
+  pot = osgmc.minibatch_potential(osgmc.Logistic(d, 0), osgmc.Prior("gaussian", 0, d, 10.0))
+  st = osgmc.langevin_init(np.zeros((len(rows), d), np.float32), keys[rows], rms=True)
+  dkey = prng.PRNGKey(0)
+  for k in range(K):
+    dkey, ix = odata.device_draw(dkey, n, N)
+    Xb, yb = hX[ix], hy[ix]
+    st = osgmc.langevin_update(st, lambda th: pot(th, (Xb, yb), N), [d], eps[k], 1.0)
+  scale = np.abs(st.theta).max(axis=1, keepdims=True)
+  err = (np.abs(got - st.theta) / scale).max()
+  assert err < 1e-5, err
+  np.testing.assert_allclose(gotU, st.potential, rtol=1e-5)
+  assert np.array_equal(kk[K % 2].numpy()[rows], st.key)        # noise stream: bit-exact
+  assert np.array_equal(dk[K % 2].numpy(), dkey)                # minibatch stream: bit-exact

@@ -1,6 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 300 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -s 120 -c 40 --csv --log-file gpurun_out/r2_launches6.csv python bench.py --steps 100 --warmup 50 --no-cpu-baseline > gpurun_out/r2_ncu_bench6.log 2>&1
+timeout 300 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --cache-control none -s 120 -c 40 --csv --log-file gpurun_out/r2_launches6.csv python bench.py --steps 100 --warmup 50 --no-cpu-baseline > gpurun_out/r2_ncu_bench6.log 2>&1
 python - <<'PY'
 import csv, collections
 rows = [r for r in csv.reader(open("gpurun_out/r2_launches6.csv")) if len(r) > 10]
