@@ -494,14 +494,27 @@ int sgmc_glm_sgld_scan_host(void* stream, void* copy_stream, const sgmc_glm_spec
                             float* potential_variance, float* host_results, float* grad,
                             uint32_t* keys_a, uint32_t* keys_b, const float* step_sizes,
                             float temperature, float alpha, float lmbd, void* workspace,
-                            size_t workspace_bytes, int path, int prng_layout) {
+                            size_t workspace_bytes, int path, int prng_layout,
+                            void* nccl_comm, int rank, int n_ranks) {
   SGMC_REQUIRE(spec && theta && host_batches && device_slots && potential_variance && grad &&
                keys_a && keys_b && step_sizes, "null argument");
   SGMC_REQUIRE(n_slots >= 2 && n_slots <= 8 && n_steps >= 0 && host_batch_count >= 1,
                "2..8 slots, at least one host batch");
+  const bool sharded = nccl_comm != nullptr && n_ranks > 1;
+  SGMC_REQUIRE(!sharded || (batch_size % n_ranks == 0 && rank >= 0 && rank < n_ranks),
+               "sharded upload: batch_size must be a multiple of the rank count");
   cudaStream_t ms = (cudaStream_t)stream, cs = (cudaStream_t)copy_stream;
   const int64_t n = batch_size, d = spec->d, C = n_chains;
-  const size_t stride = (size_t)n * d + n;                 // floats per batch
+  const size_t stride = (size_t)n * d + n;                 // floats per device batch
+  // Every rank of a chain-sharded job consumes the SAME minibatch.  Sharded upload: a
+  // rank's host batches hold only its n / R rows (then all n labels); the rows are
+  // all-gathered over NVLink into the device slot, so the host link carries 1 / R of
+  // the batch per rank instead of R identical copies.
+  const int64_t rows_local = sharded ? n / n_ranks : n;
+  const size_t host_stride = (size_t)rows_local * d + n;
+  cudaStream_t rs = nullptr;                               // read-back stream (D2H runs
+  if (check_cuda(cudaStreamCreateWithFlags(&rs, cudaStreamNonBlocking), "stream"))   // beside H2D)
+    return 1;
   cudaEvent_t copied[8], consumed[8], computed[2], read_back[2];
   for (int i = 0; i < n_slots; ++i) {
     if (check_cuda(cudaEventCreateWithFlags(&copied[i], cudaEventDisableTiming), "event") ||
@@ -513,14 +526,21 @@ int sgmc_glm_sgld_scan_host(void* stream, void* copy_stream, const sgmc_glm_spec
     if (check_cuda(cudaEventCreateWithFlags(&computed[i], cudaEventDisableTiming), "event") ||
         check_cuda(cudaEventCreateWithFlags(&read_back[i], cudaEventDisableTiming), "event"))
       return 1;
-    cudaEventRecord(read_back[i], cs);
+    cudaEventRecord(read_back[i], rs);
   }
+  int rc = 0;
   auto prefetch = [&](int64_t k) {
     const int sl = (int)(k % n_slots);
+    float* dst = device_slots + sl * stride;
+    const float* src = host_batches + (k % host_batch_count) * host_stride;
     cudaStreamWaitEvent(cs, consumed[sl], 0);
-    cudaMemcpyAsync(device_slots + sl * stride,
-                    host_batches + (k % host_batch_count) * stride, stride * 4,
+    cudaMemcpyAsync(dst + (size_t)rank * (sharded ? rows_local : 0) * d, src,
+                    (size_t)rows_local * d * 4, cudaMemcpyHostToDevice, cs);
+    cudaMemcpyAsync(dst + (size_t)n * d, src + (size_t)rows_local * d, (size_t)n * 4,
                     cudaMemcpyHostToDevice, cs);
+    if (sharded && rc == 0)
+      rc = sgmc_nccl_allgather(nccl_comm, cs, dst + (size_t)rank * rows_local * d, dst,
+                               (size_t)rows_local * d * 4);
     cudaEventRecord(copied[sl], cs);
   };
   // Tensor-core paths: the operand staging of batch k+1 runs on the copy stream (right
@@ -541,11 +561,13 @@ int sgmc_glm_sgld_scan_host(void* stream, void* copy_stream, const sgmc_glm_spec
     return check_cuda(cudaEventRecord(staged[xsl], cs), "event record");
   };
   for (int64_t k = 0; k < n_steps && k < n_slots - 1; ++k) prefetch(k);
-  int rc = 0;
-  if (piped) rc = stage(0);
+  if (piped && rc == 0) rc = stage(0);
   for (int64_t k = 0; k < n_steps && rc == 0; ++k) {
-    if (k + n_slots - 1 < n_steps) prefetch(k + n_slots - 1);
+    // copy-stream order per iteration: stage(k+1) (its rows arrived one iteration ago),
+    // then the copy of batch k + n_slots - 1
     if (piped && k + 1 < n_steps && (rc = stage(k + 1)) != 0) break;
+    if (k + n_slots - 1 < n_steps) prefetch(k + n_slots - 1);
+    if (rc) break;
     const int sl = (int)(k % n_slots);
     float* Xb = device_slots + sl * stride;
     float* uv = potential_variance + (k & 1) * 2 * C;      // (U, var) double-buffered
@@ -566,17 +588,21 @@ int sgmc_glm_sgld_scan_host(void* stream, void* copy_stream, const sgmc_glm_spec
     if (piped) cudaEventRecord(xfree[k & 1], ms);
     if (host_results != nullptr) {
       cudaEventRecord(computed[k & 1], ms);
-      cudaStreamWaitEvent(cs, computed[k & 1], 0);
-      cudaMemcpyAsync(host_results + k * 2 * C, uv, (size_t)2 * C * 4, cudaMemcpyDeviceToHost, cs);
-      cudaEventRecord(read_back[k & 1], cs);
+      cudaStreamWaitEvent(rs, computed[k & 1], 0);
+      cudaMemcpyAsync(host_results + k * 2 * C, uv, (size_t)2 * C * 4, cudaMemcpyDeviceToHost, rs);
+      cudaEventRecord(read_back[k & 1], rs);
     }
   }
+  // the caller waits on `stream` and `copy_stream`: order the read-back stream before
+  // the end of the copy stream
+  cudaEventRecord(computed[0], rs);
+  cudaStreamWaitEvent(cs, computed[0], 0);
   if (piped)
     for (int i = 0; i < 2; ++i) { cudaEventDestroy(staged[i]); cudaEventDestroy(xfree[i]); }
-  // the sampling stream finishes after the last read-back was issued; events can go
-  // (destruction is deferred by the runtime until they have completed)
+  // events can go (destruction is deferred by the runtime until they have completed)
   for (int i = 0; i < n_slots; ++i) { cudaEventDestroy(copied[i]); cudaEventDestroy(consumed[i]); }
   for (int i = 0; i < 2; ++i) { cudaEventDestroy(computed[i]); cudaEventDestroy(read_back[i]); }
+  cudaStreamDestroy(rs);
   if (rc) return rc;
   return check_cuda(cudaGetLastError(), "sgmc_glm_sgld_scan_host");
 }

@@ -3,10 +3,12 @@
 The data path needs exactly one collective -- the all-gather of per-replica
 ``(U, var)`` scalars in sharded reSGLD -- issued through NCCL by the C ABI
 (``sgmc_nccl_allgather``) on the compute stream.  Everything else (chains
-sharded over ranks) is communication free.  ``GlooCommunicator`` offers the
-same interface on host arrays through ``torch.distributed`` (gloo) so the
-host-side logic is testable on CPU boxes with world_size 2; the unique id of
-the NCCL communicator is distributed over the same control plane.
+sharded over ranks) is communication free.  ``SocketCommunicator`` is the
+host-side control plane (plain TCP, no framework: the package imports neither
+torch nor jax): it distributes the NCCL unique id and the peer-memory IPC
+handles and offers the same ``allgather`` interface on host arrays, so the
+host-side logic is testable on CPU boxes with world_size 2 (the tests also run
+it over ``torch.distributed`` gloo through ``tests/_gloo_comm.py``).
 """
 from __future__ import annotations
 
@@ -47,36 +49,124 @@ class LocalCommunicator:
     pass
 
 
-class GlooCommunicator:
-  """Host arrays over torch.distributed (gloo): CPU tests / control plane."""
+class SocketCommunicator:
+  """Host-side control plane without any framework: a star of TCP connections
+  (rank 0 listens on ``MASTER_ADDR``:``SGMC_CONTROL_PORT``, default
+  ``MASTER_PORT`` + 29; every other rank connects once).  Small host payloads
+  only -- the NCCL unique id, peer-memory IPC handles, barriers, max-over-ranks
+  of a timing -- never the data path.  Same interface as the communicators
+  below (``allgather`` on NumPy arrays, ``broadcast_bytes``, ``barrier``)."""
 
-  def __init__(self, init: bool = True):
-    import torch.distributed as dist
-    self._dist = dist
-    if init and not dist.is_initialized():
-      os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-      dist.init_process_group("gloo")
-    self.rank, self.world = dist.get_rank(), dist.get_world_size()
+  def __init__(self, rank: Optional[int] = None, world: Optional[int] = None,
+               addr: Optional[str] = None, port: Optional[int] = None, timeout: float = 120.0):
+    import socket
+    import time
+    er, ew, _ = env_rank_world()
+    self.rank = er if rank is None else int(rank)
+    self.world = ew if world is None else int(world)
+    addr = addr or os.environ.get("MASTER_ADDR", "127.0.0.1")
+    if port is None:
+      port = int(os.environ.get("SGMC_CONTROL_PORT",
+                                int(os.environ.get("MASTER_PORT", "29500")) + 29))
+    self._peers = {}
+    if self.world == 1:
+      return
+    if self.rank == 0:
+      srv = socket.socket(socket.AF_INET, socket.SOCK_STREAM)
+      srv.setsockopt(socket.SOL_SOCKET, socket.SO_REUSEADDR, 1)
+      srv.bind((addr, port))
+      srv.listen(self.world)
+      srv.settimeout(timeout)
+      for _ in range(self.world - 1):
+        conn, _ = srv.accept()
+        conn.setsockopt(socket.IPPROTO_TCP, socket.TCP_NODELAY, 1)
+        r = int.from_bytes(self._recv_exact(conn, 4), "little")
+        self._peers[r] = conn
+      srv.close()
+    else:
+      deadline = time.time() + timeout
+      while True:
+        try:
+          conn = socket.create_connection((addr, port), timeout=timeout)
+          break
+        except OSError:
+          if time.time() > deadline:
+            raise
+          time.sleep(0.05)
+      conn.setsockopt(socket.IPPROTO_TCP, socket.TCP_NODELAY, 1)
+      conn.sendall(self.rank.to_bytes(4, "little"))
+      self._peers[0] = conn
+
+  @staticmethod
+  def _recv_exact(conn, n: int) -> bytes:
+    chunks, got = [], 0
+    while got < n:
+      c = conn.recv(n - got)
+      if not c:
+        raise ConnectionError("control plane peer closed the connection")
+      chunks.append(c)
+      got += len(c)
+    return b"".join(chunks)
+
+  def _send_msg(self, conn, payload: bytes):
+    conn.sendall(len(payload).to_bytes(8, "little") + payload)
+
+  def _recv_msg(self, conn) -> bytes:
+    n = int.from_bytes(self._recv_exact(conn, 8), "little")
+    return self._recv_exact(conn, n)
+
+  def allgather_bytes(self, payload: bytes):
+    """Every rank contributes ``payload``; returns the list ordered by rank."""
+    if self.world == 1:
+      return [payload]
+    if self.rank == 0:
+      parts = [payload] + [None] * (self.world - 1)
+      for r, conn in self._peers.items():
+        parts[r] = self._recv_msg(conn)
+      blob = b"".join(len(p).to_bytes(8, "little") + p for p in parts)
+      for conn in self._peers.values():
+        self._send_msg(conn, blob)
+      return parts
+    conn = self._peers[0]
+    self._send_msg(conn, payload)
+    blob, parts, off = self._recv_msg(conn), [], 0
+    for _ in range(self.world):
+      n = int.from_bytes(blob[off:off + 8], "little")
+      parts.append(blob[off + 8:off + 8 + n])
+      off += 8 + n
+    return parts
 
   def allgather(self, send: np.ndarray, recv: np.ndarray, stream=None) -> np.ndarray:
-    import torch
     del stream
-    t = torch.from_numpy(np.ascontiguousarray(send))
-    outs = [torch.empty_like(t) for _ in range(self.world)]
-    self._dist.all_gather(outs, t)
-    recv[...] = np.stack([o.numpy() for o in outs]).reshape(recv.shape)
+    send = np.ascontiguousarray(send)
+    parts = self.allgather_bytes(send.tobytes())
+    recv[...] = np.stack([np.frombuffer(p, send.dtype).reshape(send.shape)
+                          for p in parts]).reshape(recv.shape)
     return recv
 
   def broadcast_bytes(self, payload: Optional[bytes], nbytes: int, src: int = 0) -> bytes:
-    import torch
-    t = torch.zeros(nbytes, dtype=torch.uint8)
-    if self.rank == src:
-      t = torch.frombuffer(bytearray(payload), dtype=torch.uint8).clone()
-    self._dist.broadcast(t, src)
-    return bytes(t.numpy().tobytes())
+    parts = self.allgather_bytes(payload if self.rank == src else b"")
+    assert len(parts[src]) == nbytes
+    return parts[src]
 
   def barrier(self):
-    self._dist.barrier()
+    self.allgather_bytes(b"")
+
+  def max(self, x: float) -> float:
+    parts = self.allgather_bytes(np.float64(x).tobytes())
+    return float(max(np.frombuffer(p, np.float64)[0] for p in parts))
+
+  def sum(self, x: float) -> float:
+    parts = self.allgather_bytes(np.float64(x).tobytes())
+    return float(sum(np.frombuffer(p, np.float64)[0] for p in parts))
+
+  def close(self):
+    for conn in self._peers.values():
+      try:
+        conn.close()
+      except OSError:
+        pass
+    self._peers = {}
 
 
 class PeerCommunicator:
@@ -85,7 +175,7 @@ class PeerCommunicator:
   exchange; no NCCL involved.  The windows' IPC handles travel over the gloo
   control plane once."""
 
-  def __init__(self, ctl: GlooCommunicator, bytes_per_rank: int):
+  def __init__(self, ctl, bytes_per_rank: int):
     assert bytes_per_rank % 16 == 0, "payload per rank must be a multiple of 16 bytes"
     self.rank, self.world, self.bytes = ctl.rank, ctl.world, int(bytes_per_rank)
     lib = _lib.load()
@@ -156,7 +246,7 @@ class NcclCommunicator:
     return bytes(buf.raw)
 
   @classmethod
-  def from_control_plane(cls, ctl: GlooCommunicator) -> "NcclCommunicator":
+  def from_control_plane(cls, ctl) -> "NcclCommunicator":
     uid = cls.create_unique_id() if ctl.rank == 0 else None
     uid = ctl.broadcast_bytes(uid, 128, 0)
     return cls(ctl.rank, ctl.world, uid)

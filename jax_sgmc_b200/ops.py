@@ -263,10 +263,13 @@ def glm_sgld_scan_host(spec, theta, host_batches_ptr, host_batch_count, n_steps,
                        observation_count,
                        device_slots, n_slots, potential_variance, host_results_ptr, grad,
                        keys_a, keys_b, step_sizes, copy_stream, temperature=1.0, v=None,
-                       alpha=0.9, lmbd=1e-5, workspace=None, path=0, layout=0, stream=None):
+                       alpha=0.9, lmbd=1e-5, workspace=None, path=0, layout=0, stream=None,
+                       nccl_comm=None, rank=0, n_ranks=1):
   """n_steps pSGLD / SGLD steps over minibatches in pinned host memory, one C call
   (see sgmc_glm_sgld_scan_host).  ``host_batches_ptr`` / ``host_results_ptr`` are
-  addresses of page-locked buffers; ``step_sizes`` a float32 NumPy array."""
+  addresses of page-locked buffers; ``step_sizes`` a float32 NumPy array.
+  ``nccl_comm`` (the handle of sgmc_nccl_init) switches to the sharded upload: the
+  host batches then hold this rank's n / n_ranks rows + all labels."""
   C_, P = theta.shape
   ss = np.ascontiguousarray(step_sizes, np.float32)
   assert ss.size >= n_steps
@@ -275,7 +278,8 @@ def glm_sgld_scan_host(spec, theta, host_batches_ptr, host_batch_count, n_steps,
             int(n_steps), int(batch_size), int(observation_count), vp(device_slots), int(n_slots),
             vp(potential_variance), C.c_void_p(host_results_ptr), vp(grad), vp(keys_a),
             vp(keys_b), ss.ctypes.data_as(C.c_void_p), float(temperature), float(alpha),
-            float(lmbd), vp(workspace), workspace.nbytes, PATH[path], _layout(layout))
+            float(lmbd), vp(workspace), workspace.nbytes, PATH[path], _layout(layout),
+            None if nccl_comm is None else C.c_void_p(nccl_comm), int(rank), int(n_ranks))
 
 
 def glm_sgld_scan_device(spec, theta, X, y, observation_count, batch_size, potential,

@@ -9,7 +9,7 @@ independent, so both strategy names are accepted and run batched.
 
 Multi-GPU: ``ShardedTempering`` shards reSGLD replicas over ranks and
 exchanges the per-replica energies with an all-gather (NCCL on the device,
-``torch.distributed`` gloo in the CPU tests).
+host arrays over the socket control plane / gloo in the CPU tests).
 """
 from __future__ import annotations
 

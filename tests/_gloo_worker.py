@@ -18,6 +18,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 from jax_sgmc_b200 import dist  # noqa: E402
 from oracle import prng  # noqa: E402
@@ -25,7 +26,14 @@ from oracle import sgmc as osgmc  # noqa: E402
 
 
 def main():
-  comm = dist.GlooCommunicator()
+  # SGMC_TEST_COMM=socket: the package's own framework-free control plane;
+  # otherwise torch.distributed (gloo) through the test-side shim
+  use_socket = os.environ.get("SGMC_TEST_COMM") == "socket"
+  if use_socket:
+    comm = dist.SocketCommunicator()
+  else:
+    from _gloo_comm import GlooCommunicator
+    comm = GlooCommunicator()
   rank, world = comm.rank, comm.world
   assert world == 2
 
@@ -78,13 +86,18 @@ def main():
   assert got == bytes(range(128))
 
   # max over ranks as bench.py does it
-  import torch
-  import torch.distributed as td
-  t = torch.tensor([float(rank + 1)], dtype=torch.float64)
-  td.all_reduce(t, op=td.ReduceOp.MAX)
-  assert float(t[0]) == 2.0
-  comm.barrier()
-  td.destroy_process_group()
+  if use_socket:
+    assert comm.max(float(rank + 1)) == 2.0 and comm.sum(float(rank + 1)) == 3.0
+    comm.barrier()
+    comm.close()
+  else:
+    import torch
+    import torch.distributed as td
+    t = torch.tensor([float(rank + 1)], dtype=torch.float64)
+    td.all_reduce(t, op=td.ReduceOp.MAX)
+    assert float(t[0]) == 2.0
+    comm.barrier()
+    td.destroy_process_group()
   print(f"rank {rank} ok")
 
 
