@@ -91,7 +91,9 @@ PROTOTYPES = {
                                           _vp, _sz],
     "sgmc_glm_sgld_scan_host": [_vp, _vp, C.POINTER(GlmSpec), _vp, _vp, _i64, _i64, _vp, _i64,
                                 _i64, _i64, _i64, _vp, _int, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _f32,
-                                _f32, _vp, _sz, _int, _int, _vp, _int, _int],
+                                _f32, _vp, _sz, _int, _int, _vp, _int, _int, _vp, _vp, _vp, _i64,
+                                C.POINTER(_i64)],
+    "sgmc_host_gather_batches": [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _int],
     "sgmc_glm_sgld_scan_device": [_vp, C.POINTER(GlmSpec), _vp, _vp, _i64, _i64, _vp, _vp, _i64,
                                   _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                   C.POINTER(_i64), _int, _vp, _vp, _vp, _i64, _vp, _vp, _i64,

@@ -13,6 +13,7 @@ namespace sgmc {
 void set_error(const char* fmt, ...);
 extern std::atomic<unsigned long long> g_launches;
 int option(int which);
+void prof_mark(cudaStream_t stream, int slot);   // SGMC_OPT_STEP_PROFILE, runtime.cu
 
 inline int check_cuda(cudaError_t e, const char* what) {
   if (e != cudaSuccess) {

@@ -444,6 +444,7 @@ int sgmc_glm_sgld_step(void* stream, const sgmc_glm_spec* spec, float* theta, fl
   fu.theta_rw = theta; fu.v = v; fu.keys_in = keys_in; fu.keys_out = keys_out;
   fu.step_size = step_size; fu.temperature = temperature; fu.alpha = alpha; fu.lmbd = lmbd;
   fu.layout = prng_layout; fu.applied = &applied; fu.write_grad = write_grad != 0;
+  prof_mark((cudaStream_t)stream, 0);
   XStage xs;
   if ((flags & SGMC_STEP_X_STAGED) && path != 0) {
     xs.prepared = true;
@@ -463,11 +464,15 @@ int sgmc_glm_sgld_step(void* stream, const sgmc_glm_spec* spec, float* theta, fl
       check_cuda(cudaStreamWaitEvent((cudaStream_t)stream, (cudaEvent_t)wait_event, 0),
                  "cudaStreamWaitEvent"))
     return 1;
+  prof_mark((cudaStream_t)stream, 2);
   if (cc.active && write_grad) cc.out.grad_rw = grad;   // hand the completed gradient out
-  if (cc.active)   // the update also writes Theta's operand form for the next step
-    return sgld_update_split((cudaStream_t)stream, theta, v, grad, keys_in, keys_out, n_chains, P,
-                             step_size, temperature, temp_per_chain, alpha, lmbd, prng_layout,
-                             cc.out);
+  if (cc.active) {  // the update also writes Theta's operand form for the next step
+    const int e = sgld_update_split((cudaStream_t)stream, theta, v, grad, keys_in, keys_out,
+                                    n_chains, P, step_size, temperature, temp_per_chain, alpha,
+                                    lmbd, prng_layout, cc.out);
+    prof_mark((cudaStream_t)stream, 3);
+    return e;
+  }
   // the stand-alone fused noise + update kernel
   if (v)
     return sgmc_sgld_rms_update(stream, theta, v, grad, keys_in, keys_out, n_chains, leaf_sizes,
@@ -495,9 +500,13 @@ int sgmc_glm_sgld_scan_host(void* stream, void* copy_stream, const sgmc_glm_spec
                             uint32_t* keys_a, uint32_t* keys_b, const float* step_sizes,
                             float temperature, float alpha, float lmbd, void* workspace,
                             size_t workspace_bytes, int path, int prng_layout,
-                            void* nccl_comm, int rank, int n_ranks) {
+                            void* nccl_comm, int rank, int n_ranks, const uint8_t* keep,
+                            float* samples_out, float* scalars_out, int64_t capacity,
+                            int64_t* kept) {
   SGMC_REQUIRE(spec && theta && host_batches && device_slots && potential_variance && grad &&
                keys_a && keys_b && step_sizes, "null argument");
+  SGMC_REQUIRE(keep == nullptr || samples_out == nullptr || (scalars_out && kept),
+               "sample collection needs scalars_out and kept");
   SGMC_REQUIRE(n_slots >= 2 && n_slots <= 8 && n_steps >= 0 && host_batch_count >= 1,
                "2..8 slots, at least one host batch");
   const bool sharded = nccl_comm != nullptr && n_ranks > 1;
@@ -586,6 +595,15 @@ int sgmc_glm_sgld_scan_host(void* stream, void* copy_stream, const sgmc_glm_spec
                             nullptr, 0, flags);
     cudaEventRecord(consumed[sl], ms);
     if (piped) cudaEventRecord(xfree[k & 1], ms);
+    if (rc == 0 && keep && keep[k] && samples_out && *kept < capacity) {   // io.py:696-713
+      if (check_cuda(cudaMemcpyAsync(samples_out + *kept * C * P, theta, (size_t)C * P * 4,
+                                     cudaMemcpyDeviceToDevice, ms), "collect") ||
+          check_cuda(cudaMemcpyAsync(scalars_out + *kept * C, uv, (size_t)C * 4,
+                                     cudaMemcpyDeviceToDevice, ms), "collect"))
+        rc = 1;
+      else
+        ++*kept;
+    }
     if (host_results != nullptr) {
       cudaEventRecord(computed[k & 1], ms);
       cudaStreamWaitEvent(rs, computed[k & 1], 0);

@@ -1908,6 +1908,7 @@ int glm_tc(cudaStream_t stream, const GlmArgs& a, int path) {
     }
   }
   if (a.only_x) return 0;
+  prof_mark(stream, 1);
   // The Xb scale is computed on the device (k_prepare_all) and read by the
   // epilogues through a device scalar, so the whole op stays sync-free.
   // R scale: |R| <= |cot| for the logistic family (|dl/dz| <= 1, mask in [0,1]).

@@ -3,7 +3,10 @@
 // Python (ctypes) or C needs no other CUDA binding.  Not on the hot path.
 #include "common.cuh"
 
+#include <algorithm>
 #include <cstring>
+#include <thread>
+#include <vector>
 
 namespace sgmc {
 
@@ -24,9 +27,60 @@ void set_error(const char* fmt, ...) {
 
 }  // namespace sgmc
 
+namespace sgmc {
+
+// Per-kernel timing of sgmc_glm_sgld_step (SGMC_OPT_STEP_PROFILE): CUDA events on the
+// launching stream after each of the step's launches; the intervals are accumulated
+// when the next step begins (which synchronises on the previous step -- profile mode
+// only).  Marks: 0 step entry, 1 after the operand preparation, 2 after the potential
+// kernel, 3 after the update.
+static cudaEvent_t g_prof_ev[4];
+static bool g_prof_init = false, g_prof_pending = false;
+static double g_prof_acc[3] = {0, 0, 0};
+static long long g_prof_steps = 0;
+
+static void prof_fold() {
+  if (!g_prof_pending) return;
+  if (cudaEventSynchronize(g_prof_ev[3]) == cudaSuccess) {
+    for (int i = 0; i < 3; ++i) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, g_prof_ev[i], g_prof_ev[i + 1]) == cudaSuccess)
+        g_prof_acc[i] += (double)ms * 1e3;
+    }
+    ++g_prof_steps;
+  }
+  g_prof_pending = false;
+}
+
+void prof_mark(cudaStream_t stream, int slot) {
+  if (!option(SGMC_OPT_STEP_PROFILE)) return;
+  if (!g_prof_init) {
+    for (int i = 0; i < 4; ++i) cudaEventCreate(&g_prof_ev[i]);
+    g_prof_init = true;
+  }
+  if (slot == 0) prof_fold();
+  cudaEventRecord(g_prof_ev[slot], stream);
+  if (slot == 3) g_prof_pending = true;
+}
+
+}  // namespace sgmc
+
 using namespace sgmc;
 
 extern "C" {
+
+// us per step spent in {operand preparation, potential kernel, update} since the last
+// reset, and the number of steps folded; reset != 0 clears the accumulators.
+int sgmc_debug_step_profile(double* us3, long long* steps, int reset) {
+  prof_fold();
+  for (int i = 0; i < 3; ++i) us3[i] = g_prof_steps ? g_prof_acc[i] / (double)g_prof_steps : 0.0;
+  if (steps) *steps = g_prof_steps;
+  if (reset) {
+    for (int i = 0; i < 3; ++i) g_prof_acc[i] = 0;
+    g_prof_steps = 0;
+  }
+  return 0;
+}
 
 const char* sgmc_last_error(void) { return g_err; }
 int sgmc_version(void) { return 100; }
@@ -131,6 +185,44 @@ int sgmc_stream_wait_event(void* stream, void* event) {
   return check_cuda(cudaStreamWaitEvent((cudaStream_t)stream, (cudaEvent_t)event, 0),
                     "cudaStreamWaitEvent");
 }
+// Host side of the streaming data loader (data/core.py:664-791: the reference refills
+// its cache with NumPy fancy indexing inside an io_callback): gather `n_batches`
+// minibatches of rows [row0, row0 + rows) of each index row into the staging layout
+// sgmc_glm_sgld_scan_host consumes -- per batch `rows` feature rows of d floats, then
+// all n labels -- with `n_threads` host threads (memcpy of whole rows; the staging
+// buffer is page-locked memory the H2D copies read directly).
+int sgmc_host_gather_batches(float* dst, const float* X, const float* y, const int32_t* idx,
+                             int64_t n_batches, int64_t n, int64_t d, int64_t row0,
+                             int64_t rows, int n_threads) {
+  SGMC_REQUIRE(dst && X && y && idx && n_batches >= 0 && n > 0 && d > 0 && row0 >= 0 &&
+               rows >= 0 && row0 + rows <= n, "bad gather arguments");
+  const int64_t stride = rows * d + n;
+  const int64_t items = n_batches * rows;              // one item = one feature row
+  const int T = (int)std::max<int64_t>(1, std::min<int64_t>(n_threads, items / 64 + 1));
+  auto work = [&](int t) {
+    const int64_t lo = items * t / T, hi = items * (t + 1) / T;
+    for (int64_t it = lo; it < hi; ++it) {
+      const int64_t b = it / rows, r = it - b * rows;
+      const int64_t src = (int64_t)idx[b * n + row0 + r];
+      std::memcpy(dst + b * stride + r * d, X + src * d, (size_t)d * sizeof(float));
+    }
+    for (int64_t b = n_batches * t / T; b < n_batches * (t + 1) / T; ++b) {
+      float* lab = dst + b * stride + rows * d;
+      for (int64_t i = 0; i < n; ++i) lab[i] = y[idx[b * n + i]];
+    }
+  };
+  if (T == 1) {
+    work(0);
+    return 0;
+  }
+  std::vector<std::thread> pool;
+  pool.reserve(T - 1);
+  for (int t = 1; t < T; ++t) pool.emplace_back(work, t);
+  work(0);
+  for (auto& th : pool) th.join();
+  return 0;
+}
+
 int sgmc_event_elapsed_ms(void* start, void* stop, float* ms) {
   return check_cuda(
       cudaEventElapsedTime(ms, (cudaEvent_t)start, (cudaEvent_t)stop),

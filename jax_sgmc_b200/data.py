@@ -245,6 +245,15 @@ class StreamingNumpyDataLoader(NumpyDataLoader):
     self.host_shapes = {k: v.shape for k, v in self.host_data.items()}
     self.device_data = {}            # nothing is resident
     self._chains: List[dict] = []
+    self.upload_comm = None          # see shard_upload
+
+  def shard_upload(self, comm):
+    """Chain-sharded multi-GPU runs: every rank consumes the same minibatches, so
+    each rank gathers / uploads only rows [rank n / R, (rank + 1) n / R) of a batch
+    and the rows are all-gathered over NVLink on the device (``comm``: a
+    ``dist.NcclCommunicator``).  The host link then carries 1 / R of the batch per
+    rank instead of R identical copies through one host."""
+    self.upload_comm = comm
 
   def absmax(self, name: str) -> float:
     cache = self.__dict__.setdefault("_absmax", {})
@@ -382,6 +391,31 @@ def random_reference_data(data_loader: DataLoader, cached_batches_count: int,
       state.line += 1
       return (state, (batch, info)) if information else (state, batch)
 
+    def scan_source(state: CacheState, steps: int):
+      """What the native host scan needs: the loader, and a function handing out
+      the index rows of the next k minibatches (the chain's PCG64 pipeline, block by
+      block as get_fn would draw them).  Only before get_fn started streaming."""
+      del steps
+      if state.slots is not None or len(state.chain_ids) != 1:
+        return None
+      left = []
+
+      def draw(k: int) -> np.ndarray:
+        rows, need = [], k
+        while need > 0:
+          if not left:
+            blk, _ = data_loader.get_indices(state.chain_ids[0])     # [cache, n]
+            left.extend(np.asarray(blk, np.int32))
+          take = min(need, len(left))
+          rows.extend(left[:take])
+          del left[:take]
+          need -= take
+        return np.stack(rows)
+
+      return {"loader": data_loader, "n": mb_size, "N": N, "host_stream": True,
+              "draw": draw, "chunk": cached_batches_count}
+
+    get_fn.scan_source = scan_source
     return init_fn, get_fn, lambda: None
 
   if isinstance(data_loader, NumpyDataLoader):

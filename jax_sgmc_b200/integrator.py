@@ -210,10 +210,11 @@ def langevin_diffusion(potential_fn, batch_fn, adaption=None
             "model_state": state.model_state}
 
   def update_fn(state: LangevinState, parameters, temp_per_chain=None,
-                pre_update_hook: Callable = None) -> LangevinState:
+                pre_update_hook: Callable = None, carry_ok: bool = False) -> LangevinState:
     """integrator.py:860-922.  ``pre_update_hook`` (a callable with an ``event``
     attribute) orders the update launch after that event -- the sharded reSGLD
-    puts its label exchange there."""
+    puts its label exchange there.  ``carry_ok``: the caller never writes the
+    sample between updates (see ``_PotentialFn.sgld_step``)."""
     theta = state.latent_variables
     data_state, mini_batch = batch_get(state.data_state, information=True)   # :872
     grad_buf = scratch.get(theta.flat, lambda: DeviceArray(theta.flat.shape, np.float32))
@@ -230,7 +231,7 @@ def langevin_diffusion(potential_fn, batch_fn, adaption=None
         alpha=alpha if alpha is not None else 0.9, lmbd=lmbd if lmbd is not None else 1e-5,
         temp_per_chain=temp_per_chain,
         wait_event=getattr(pre_update_hook, "event", None), grad_out=grad_buf,
-        U_out=state.potential, var_out=state.variance):
+        U_out=state.potential, var_out=state.variance, carry_ok=carry_ok):
       (_, (_, new_model_state)), grad = stochastic_gradient(               # :875-880
           theta, mini_batch, state=state.model_state, likelihoods=True,
           grad_out=grad_buf, U_out=state.potential, var_out=state.variance)
@@ -271,6 +272,8 @@ def langevin_diffusion(potential_fn, batch_fn, adaption=None
         theta, source, state.key.current, state.key.next, step_sizes, temperatures, keep,
         samples_out, scalars_out, kept, v=v, alpha=alpha, lmbd=lmbd, grad_out=grad_buf,
         U_out=state.potential, var_out=state.variance)
+    if kept is None:          # the native scan declined (after consuming nothing)
+      return None
     if steps % 2:
       state.key.flip()
     return state, kept

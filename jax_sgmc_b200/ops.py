@@ -264,7 +264,8 @@ def glm_sgld_scan_host(spec, theta, host_batches_ptr, host_batch_count, n_steps,
                        device_slots, n_slots, potential_variance, host_results_ptr, grad,
                        keys_a, keys_b, step_sizes, copy_stream, temperature=1.0, v=None,
                        alpha=0.9, lmbd=1e-5, workspace=None, path=0, layout=0, stream=None,
-                       nccl_comm=None, rank=0, n_ranks=1):
+                       nccl_comm=None, rank=0, n_ranks=1, keep=None, samples_out=None,
+                       scalars_out=None, kept: int = 0) -> int:
   """n_steps pSGLD / SGLD steps over minibatches in pinned host memory, one C call
   (see sgmc_glm_sgld_scan_host).  ``host_batches_ptr`` / ``host_results_ptr`` are
   addresses of page-locked buffers; ``step_sizes`` a float32 NumPy array.
@@ -273,13 +274,30 @@ def glm_sgld_scan_host(spec, theta, host_batches_ptr, host_batch_count, n_steps,
   C_, P = theta.shape
   ss = np.ascontiguousarray(step_sizes, np.float32)
   assert ss.size >= n_steps
+  kp = None if keep is None else np.ascontiguousarray(keep, np.uint8)
+  cnt = C.c_int64(int(kept))
+  cap = 0 if samples_out is None else samples_out.shape[0]
   _lib.call("sgmc_glm_sgld_scan_host", _s(stream), copy_stream.handle, C.byref(spec),
             vp(theta), vp(v), C_, P, C.c_void_p(host_batches_ptr), int(host_batch_count),
             int(n_steps), int(batch_size), int(observation_count), vp(device_slots), int(n_slots),
             vp(potential_variance), C.c_void_p(host_results_ptr), vp(grad), vp(keys_a),
             vp(keys_b), ss.ctypes.data_as(C.c_void_p), float(temperature), float(alpha),
             float(lmbd), vp(workspace), workspace.nbytes, PATH[path], _layout(layout),
-            None if nccl_comm is None else C.c_void_p(nccl_comm), int(rank), int(n_ranks))
+            None if nccl_comm is None else C.c_void_p(nccl_comm), int(rank), int(n_ranks),
+            None if kp is None else kp.ctypes.data_as(C.c_void_p), vp(samples_out),
+            vp(scalars_out), int(cap), C.byref(cnt))
+  return int(cnt.value)
+
+
+def host_gather_batches(dst_ptr: int, X: np.ndarray, y: np.ndarray, idx: np.ndarray, row0: int,
+                        rows: int, n_threads: int):
+  """Threaded host gather into a page-locked staging buffer (see
+  sgmc_host_gather_batches); releases the GIL while it runs."""
+  idx = np.ascontiguousarray(idx, np.int32)
+  nb, n = idx.shape
+  _lib.call("sgmc_host_gather_batches", C.c_void_p(dst_ptr), X.ctypes.data_as(C.c_void_p),
+            y.ctypes.data_as(C.c_void_p), idx.ctypes.data_as(C.c_void_p), int(nb), int(n),
+            int(X.shape[1]), int(row0), int(rows), int(n_threads))
 
 
 def glm_sgld_scan_device(spec, theta, X, y, observation_count, batch_size, potential,
@@ -410,6 +428,7 @@ OPT_TC_TIMELINE = 6          # 1: k_glm_tc_pair records its phase timeline
 OPT_TC_TILE_N = 7            # accumulator columns per CTA and tile: 256 (default) or 128
 OPT_NO_SHADOW_NOISE = 8      # 1: noise in the update kernel instead of under the GEMM mainloops
 OPT_NO_PIPELINE = 9          # 1: scans stage minibatches on the sampling stream (no side stream)
+OPT_STEP_PROFILE = 10        # 1: per-kernel CUDA-event timing of the carried step
 OPT_TC_CTA_GROUP = 5         # 2 (default): tcgen05 cta_group::2 on CTA pairs; 1: single CTAs
 
 
@@ -419,3 +438,14 @@ def set_option(option: int, value: int):
 
 def launch_count() -> int:
   return int(_lib.load().sgmc_launch_count())
+
+
+def step_profile(reset: bool = True):
+  """(us_prepare, us_potential, us_update, steps) averaged since the last reset
+  (needs set_option(OPT_STEP_PROFILE, 1) while stepping)."""
+  lib = _lib.load()
+  us = (C.c_double * 3)()
+  n = C.c_longlong()
+  lib.sgmc_debug_step_profile.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+  lib.sgmc_debug_step_profile(us, C.byref(n), 1 if reset else 0)
+  return float(us[0]), float(us[1]), float(us[2]), int(n.value)

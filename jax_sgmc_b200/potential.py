@@ -48,6 +48,7 @@ class _PotentialFn:
     self.prior, self.likelihood = prior, likelihood
     self.temperature, self.path = float(temperature), path
     self._buffers = {}
+    self._carried = None      # (buffer key, sample pointer) of a running carried step sequence
 
   # -- internal ------------------------------------------------------------------
   def _run(self, sample: ChainTree, reference_data, mask, want_grad, want_ell,
@@ -66,6 +67,7 @@ class _PotentialFn:
       mask = batch.mask
     path = _select_path(self.path, spec, C, n)
     key = (C, P, n, path)
+    self._carried = None          # this call reuses the workspace: a carried split ends here
     buf = self._buffers.get(key)
     if buf is None:
       buf = {"U": DeviceArray((C,), np.float32), "var": DeviceArray((C,), np.float32),
@@ -104,11 +106,18 @@ class _PotentialFn:
 
   def sgld_step(self, sample: ChainTree, reference_data, keys_in, keys_out, step_size,
                 temperature, v=None, alpha=0.9, lmbd=1e-5, temp_per_chain=None,
-                wait_event=None, grad_out=None, U_out=None, var_out=None) -> bool:
+                wait_event=None, grad_out=None, U_out=None, var_out=None,
+                carry_ok: bool = False) -> bool:
     """The whole langevin_diffusion.update_fn body (integrator.py:860-922) --
     value_and_grad of this potential on the minibatch, then the SGLD / pSGLD
     update of ``sample`` in place -- as ONE C call (sgmc_glm_sgld_step).
-    Returns False (nothing done) when the chains do not share the minibatch."""
+    Returns False (nothing done) when the chains do not share the minibatch.
+
+    ``carry_ok``: the caller guarantees that nothing but these calls writes
+    ``sample`` between steps (solver.sgmc, the sharded tempering).  The operand form
+    of the sample then travels from one step's update to the next potential inside
+    the workspace (SGMC_STEP_CARRY); any other use of the workspace (a
+    ``value_and_grad`` call) or a different sample array ends the sequence."""
     batch, info = reference_data
     if batch.per_chain or batch.mask is not None:
       return False
@@ -122,6 +131,13 @@ class _PotentialFn:
       buf = {"U": DeviceArray((C,), np.float32), "var": DeviceArray((C,), np.float32),
              "ws": ops.glm_workspace(C, n, spec.d, path), "ell": None}
       self._buffers[key] = buf
+    carry = 0
+    if carry_ok and path != "simt":
+      token = (key, sample.flat.ptr)
+      carry = ops.STEP_CARRY if self._carried == token else ops.STEP_CARRY_INIT
+      self._carried = token
+    else:
+      self._carried = None
     ops.glm_sgld_step(
         spec, sample.flat, batch.leaf(self.likelihood.x),
         batch.leaf(self.likelihood.y), batch.idx,
@@ -129,7 +145,7 @@ class _PotentialFn:
         var_out if var_out is not None else buf["var"], grad_out, keys_in, keys_out,
         step_size, temperature, v=v, alpha=alpha, lmbd=lmbd, workspace=buf["ws"],
         path=path, batch_size=n, temp_per_chain=temp_per_chain, wait_event=wait_event,
-        leaf_sizes=sample.sizes)
+        leaf_sizes=sample.sizes, carry=carry)
     return True
 
   def sgld_scan(self, sample: ChainTree, source, keys_a, keys_b, step_sizes, temperatures,
@@ -139,11 +155,16 @@ class _PotentialFn:
     collection) in ONE C call (sgmc_glm_sgld_scan_device); ``source`` comes from
     the data functional's ``scan_source``.  Returns the new sample count."""
     loader, n, N = source["loader"], source["n"], source["N"]
+    if source.get("host_stream"):
+      return self._sgld_scan_host_stream(sample, source, keys_a, keys_b, step_sizes,
+                                         temperatures, keep, samples_out, scalars_out, kept,
+                                         v, alpha, lmbd, grad_out, U_out, var_out)
     spec = glm.resolve(self.likelihood, self.prior, sample, self.temperature,
                        loader.absmax(self.likelihood.x))
     C = sample.n_chains
     path = _select_path(self.path, spec, C, n)
     key = (C, sample.n_params, n, path)
+    self._carried = None          # the scan starts its own carried sequence
     buf = self._buffers.get(key)
     if buf is None:
       buf = {"U": DeviceArray((C,), np.float32), "var": DeviceArray((C,), np.float32),
@@ -158,6 +179,96 @@ class _PotentialFn:
         data_key_a=source.get("key_a"), data_key_b=source.get("key_b"),
         idx_buf=source.get("idx_buf"), idx_all=source.get("idx_all"), v=v, alpha=alpha,
         lmbd=lmbd, workspace=buf["ws"], path=path)
+
+  def _sgld_scan_host_stream(self, sample, source, keys_a, keys_b, step_sizes, temperatures,
+                             keep, samples_out, scalars_out, kept, v, alpha, lmbd, grad_out,
+                             U_out, var_out):
+    """The scan over a HOST-resident data set (StreamingNumpyDataLoader): chunks of
+    minibatches are gathered by host threads into page-locked memory
+    (sgmc_host_gather_batches) while the device works through the previous chunk
+    (sgmc_glm_sgld_scan_host: H2D copies two batches ahead, operand staging one step
+    ahead, (U, var) of every step read back).  Returns None when the configuration
+    needs the step loop."""
+    import os
+    import threading
+    from .device import Stream, current_stream
+    from .io import _pinned_array
+    loader, n, N = source["loader"], source["n"], source["N"]
+    temps = np.asarray(temperatures, np.float32)
+    if temps.size and not np.all(temps == temps[0]):
+      return None
+    X = loader.host_data[self.likelihood.x]
+    y = loader.host_data[self.likelihood.y].reshape(-1)
+    if X.ndim != 2:
+      return None
+    spec = glm.resolve(self.likelihood, self.prior, sample, self.temperature,
+                       loader.absmax(self.likelihood.x))
+    C, d = sample.n_chains, int(X.shape[1])
+    path = _select_path(self.path, spec, C, n)
+    comm = loader.upload_comm
+    world = comm.world if comm is not None else 1
+    rank = comm.rank if comm is not None else 0
+    if n % world:
+      return None
+    rows = n // world
+    host_stride, dev_stride = rows * d + n, n * d + n
+    K = len(step_sizes)
+    CH = max(2, min(int(source["chunk"]), 64, K))
+    CH -= CH % 2                       # the chain keys ping-pong once per step
+    key = ("host_stream", C, sample.n_params, n, path, CH, world)
+    buf = self._buffers.get(key)
+    if buf is None:
+      ring, ring_addr = _pinned_array(2 * CH * host_stride)
+      res, res_addr = _pinned_array(CH * 2 * C)
+      buf = {"ring": ring, "ring_addr": ring_addr, "res": res, "res_addr": res_addr,
+             "slots": DeviceArray((3 * dev_stride,), np.float32),
+             "uv": DeviceArray((2, 2, C), np.float32), "copy": Stream.create(),
+             "ws": ops.glm_workspace(C, n, spec.d, path)}
+      self._buffers[key] = buf
+    self._carried = None
+    threads = max(1, (os.cpu_count() or 1) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1"))))
+    main = current_stream()
+
+    def gather(idx_rows, half):
+      ops.host_gather_batches(buf["ring_addr"] + half * CH * host_stride * 4, X, y, idx_rows,
+                              rank * rows, rows, threads)
+
+    ss = np.ascontiguousarray(step_sizes, np.float32)
+    kp = None if keep is None else np.ascontiguousarray(keep, np.uint8)
+    done, half, last_k = 0, 0, 0
+    gather(source["draw"](min(CH, K)), 0)
+    trace = []
+    while done < K:
+      k = min(CH, K - done)
+      worker = None
+      if done + k < K:
+        nxt = source["draw"](min(CH, K - done - k))
+        worker = threading.Thread(target=gather, args=(nxt, 1 - half))
+        worker.start()
+      kept = ops.glm_sgld_scan_host(
+          spec, sample.flat, buf["ring_addr"] + half * CH * host_stride * 4, k, k, n, N,
+          buf["slots"], 3, buf["uv"], buf["res_addr"], grad_out, keys_a, keys_b, ss[done:done + k],
+          buf["copy"], temperature=float(temps[0]) if temps.size else 1.0, v=v, alpha=alpha,
+          lmbd=lmbd, workspace=buf["ws"], path=path,
+          nccl_comm=getattr(comm, "_comm", None) and comm._comm.value, rank=rank, n_ranks=world,
+          keep=None if kp is None else kp[done:done + k], samples_out=samples_out,
+          scalars_out=scalars_out, kept=kept)
+      main.sync()
+      buf["copy"].sync()
+      trace.append(buf["res"][:k * 2 * C].reshape(k, 2, C)[:, 0].mean(axis=1))   # host reads U
+      if worker is not None:
+        worker.join()
+      done, half, last_k = done + k, 1 - half, k
+    self.last_potential_trace = np.concatenate(trace) if trace else np.zeros(0, np.float32)
+    if last_k:                          # LangevinState.potential / .variance of the last step
+      last = buf["uv"].row_slice((last_k - 1) & 1, ((last_k - 1) & 1) + 1).reshape(2, C)
+      if U_out is not None:
+        U_out.copy_from(last.row_slice(0, 1).reshape(C))
+      if var_out is not None:
+        var_out.copy_from(last.row_slice(1, 2).reshape(C))
+    self.h2d_bytes_per_step = (rows * d + n) * 4
+    self.d2h_bytes_per_step = 2 * C * 4
+    return kept
 
   def value_and_grad(self, sample: ChainTree, reference_data, state: Any = None,
                      mask=None, likelihoods: bool = False,

@@ -96,7 +96,13 @@ def sgmc(integrator) -> Tuple[Callable, Callable, Callable]:
   def init(*args, **kwargs):
     return init_integrator(*args, **kwargs)
 
+  takes_carry = "carry_ok" in getattr(update_integrator, "__code__", update).co_varnames
+
   def update(state, schedule):
+    # sgmc never touches the sample between updates: the Langevin integrator may
+    # carry its operand form from step to step
+    if takes_carry:
+      return update_integrator(state, schedule, carry_ok=True), None
     return update_integrator(state, schedule), None
 
   def get(state) -> Dict[str, Any]:

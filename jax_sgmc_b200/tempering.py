@@ -139,9 +139,12 @@ def sharded_tempering(integrator, temperatures: Sequence[float], comm=None,
       hook = _WaitFor(main, done)
     for l in range(n_local):
       t_row = state.temp_per_chain.row_slice(l, l + 1).reshape(B)
+      # labels are exchanged, never parameters: the replica's sample is only written by
+      # its own updates (with one replica per rank the operand form is carried)
       state.replicas[l] = update_integrator(state.replicas[l], schedule,
                                             temp_per_chain=t_row,
-                                            pre_update_hook=hook if l == 0 else None)
+                                            pre_update_hook=hook if l == 0 else None,
+                                            carry_ok=n_local == 1)
     if native:
       # snapshot + all-gather + decision kernels: one C call
       ops.resgld_sharded_exchange(
