@@ -49,12 +49,9 @@ def parse():
   p.add_argument("--no-cpu-baseline", action="store_true")
   p.add_argument("--serial-launch", action="store_true",
                  help="disable programmatic dependent launch (A/B of the launch overlap)")
-  p.add_argument("--noise-in-gemm", action="store_true",
-                 help="experimental: the update's noise generated by the GEMMs' idle warps "
-                      "(SGMC_OPT_STEP_NOISE_IN_GEMM)")
-  p.add_argument("--fused-epilogue", action="store_true",
-                 help="experimental: pSGLD update inside the gradient GEMM's epilogue "
-                      "(SGMC_OPT_FUSED_STEP_EPILOGUE)")
+  p.add_argument("--no-resgld", action="store_true")
+  p.add_argument("--resgld-systems", type=int, default=4096)
+  p.add_argument("--resgld-steps", type=int, default=200)
   p.add_argument("--cpu-seconds", type=float, default=15.0)
   return p.parse_args()
 
@@ -113,43 +110,6 @@ def dist_env():
   world = int(os.environ.get("WORLD_SIZE", "1"))
   local = int(os.environ.get("LOCAL_RANK", "0"))
   return rank, world, local
-
-
-class Control:
-  """Barrier + max-over-ranks on the host control plane (torch.distributed,
-  gloo).  Plumbing only: no data-path collective exists for sharded chains."""
-
-  def __init__(self, world):
-    self.world = world
-    if world > 1:
-      import torch.distributed as dist
-      os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-      dist.init_process_group("gloo")
-      self.dist = dist
-
-  def barrier(self):
-    if self.world > 1:
-      self.dist.barrier()
-
-  def max(self, x: float) -> float:
-    if self.world == 1:
-      return x
-    import torch
-    t = torch.tensor([x], dtype=torch.float64)
-    self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
-    return float(t[0])
-
-  def sum(self, x: float) -> float:
-    if self.world == 1:
-      return x
-    import torch
-    t = torch.tensor([x], dtype=torch.float64)
-    self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
-    return float(t[0])
-
-  def close(self):
-    if self.world > 1:
-      self.dist.destroy_process_group()
 
 
 # ---------------------------------------------------------------------------
@@ -240,21 +200,122 @@ def run_reference(args):
 
 
 # ---------------------------------------------------------------------------
+class Control:
+  """Barrier + max-over-ranks on the host control plane (torch.distributed, gloo), and
+  the carrier of the NCCL unique id.  Plumbing only."""
+
+  def __init__(self, rank, world):
+    self.rank, self.world = rank, world
+    if world > 1:
+      import torch.distributed as dist
+      os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+      dist.init_process_group("gloo")
+      self.dist = dist
+
+  def barrier(self):
+    if self.world > 1:
+      self.dist.barrier()
+
+  def _reduce(self, x: float, op) -> float:
+    if self.world == 1:
+      return x
+    import torch
+    t = torch.tensor([x], dtype=torch.float64)
+    self.dist.all_reduce(t, op=op)
+    return float(t[0])
+
+  def max(self, x: float) -> float:
+    return self._reduce(x, self.dist.ReduceOp.MAX) if self.world > 1 else x
+
+  def sum(self, x: float) -> float:
+    return self._reduce(x, self.dist.ReduceOp.SUM) if self.world > 1 else x
+
+  def broadcast_bytes(self, payload, nbytes: int, src: int = 0) -> bytes:
+    if self.world == 1:
+      return payload
+    box = [payload if self.rank == src else None]
+    self.dist.broadcast_object_list(box, src=src)
+    assert len(box[0]) == nbytes
+    return box[0]
+
+  def close(self):
+    if self.world > 1:
+      self.dist.destroy_process_group()
+
+
+def bench_resgld(args, ctl, nccl, stream, path):
+  """C4: a reSGLD ladder of 8 replicas (geometric temperatures 1 ... 1000, every replica
+  `--resgld-systems` independent systems of the C2 model) sharded over the ranks: per step
+  every rank advances its replicas, ONE NCCL all-gather shares the (U, var) rows, every
+  rank takes the identical swap decisions.  Strong scaling: the ladder is the same at
+  every N."""
+  from jax_sgmc_b200 import data, dist, glm, integrator, ops, potential, scheduler, tempering
+  from jax_sgmc_b200.device import Event
+  world, rank = ctl.world, ctl.rank
+  R, B, d, n = 8, args.resgld_systems, args.features, args.batch
+  if R % world:
+    return None
+  Nr = 100_000
+  X, y, _ = ops.synth_logistic_data(0, Nr, d)
+  loader = data.DeviceNumpyDataLoader(x=X, y=y)
+  pot = potential.minibatch_potential(glm.GaussianPrior(10.0), glm.LogisticRegression(), path=path)
+  integ = integrator.langevin_diffusion(pot, data.random_reference_data(loader, 1, n))
+  comm = nccl if world > 1 else dist.LocalCommunicator()
+  temps = list(np.geomspace(1.0, 1000.0, R).astype(np.float32))
+  init, update, _ = tempering.sharded_tempering(integ, temps, comm)
+  from jax_sgmc_b200.tree_util import ChainTree
+  from jax_sgmc_b200.device import DeviceArray as DA
+  template = ChainTree.from_trees([{"w": np.zeros(d, np.float32)}])
+  samples = [ChainTree.like(template, DA.zeros((B, d))) for _ in range(R)]
+  keys = np.stack([ops.prng_key(100 + b) for b in range(B)])
+  state = init(samples, key=keys)
+  sch = scheduler.schedule(np.float32(1e-3), np.float32(1.0), 1.0, True)
+  for _ in range(10):
+    state, _ = update(state, sch)
+  stream.sync()
+  ctl.barrier()
+  K = args.resgld_steps
+  e0, e1 = Event(), Event()
+  e0.record(stream)
+  for _ in range(K):
+    state, _ = update(state, sch)
+  state.wait()
+  e1.record(stream)
+  e1.sync()
+  ms = ctl.max(e0.elapsed_ms(e1))
+  swaps = int(state.exchange.numpy().sum())
+  return {"workload": "C4: reSGLD ladder, 8 replicas sharded over the ranks "
+                      "(temperature labels exchanged, one all-gather of (U, var) per step)",
+          "replicas": R, "systems_per_replica": B, "features": d, "batch": n, "n_gpus": world,
+          "replicas_per_gpu": R // world, "exchange": "nccl_allgather" if world > 1 else "local",
+          "steps": K, "us_per_step": ms * 1e3 / K,
+          "replica_chain_steps_per_s": R * B * K / (ms * 1e-3), "scaling": "strong",
+          "swaps_in_last_step": swaps}
+
+
+def bench_row_sharded(args, ctl, nccl, stream):
+  """C5 collective: the minibatch ROWS of the GLM potential sharded over the ranks --
+  every rank evaluates its n / R rows for all chains, then one all-reduce of
+  [grad | sum ell | sum ell^2] (sgmc_glm_potential_grad_row_sharded).  Reports the
+  all-reduce's bus bandwidth."""
+  from jax_sgmc_b200 import ops
+  if not hasattr(ops, "glm_potential_grad_row_sharded") or ctl.world < 2:
+    return None
+  return ops.bench_row_sharded(args, ctl, nccl, stream)
+
+
 def run_b200(args):
-  from jax_sgmc_b200 import _lib, device, ops
+  from jax_sgmc_b200 import _lib, alias, data, device, dist, glm, ops, potential
   from jax_sgmc_b200.device import DeviceArray as DA, Event, Stream
   rank, world, local = dist_env()
-  ctl = Control(world)
+  ctl = Control(rank, world)
   _lib.load()
   device.set_device(local)
   stream = Stream.create()
   device.set_current_stream(stream)
   if args.serial_launch:
     ops.set_option(ops.OPT_SERIAL_LAUNCH, 1)
-  if args.fused_epilogue:
-    ops.set_option(ops.OPT_FUSED_STEP_EPILOGUE, 1)
-  if args.noise_in_gemm:
-    ops.set_option(ops.OPT_STEP_NOISE_IN_GEMM, 1)
+  nccl = dist.NcclCommunicator.from_control_plane(ctl) if world > 1 else None
 
   C, d, n, N = args.chains, args.features, args.batch, args.observations
   path = args.path
@@ -278,33 +339,32 @@ def run_b200(args):
                       x_absmax=ops.absmax(X))   # data-set statistic, computed once
   ws = ops.glm_workspace(C, n, d, path)
   eps = 1e-3
-  state = {"k": 0, "carried": False}   # carried: theta's operand split lives in `ws`
 
-  def step():
-    k = state["k"]
-    ops.minibatch_draw(dkey[k % 2], dkey[(k + 1) % 2], idx, N)
-    # the whole langevin_diffusion step in one C call (operand prepare, two
-    # tcgen05 GEMMs, fused noise + pSGLD update)
-    ops.glm_sgld_step(spec, theta, X, y, idx, N, U, var, grad, keys[k % 2],
-                      keys[(k + 1) % 2], eps, 1.0, v=v, alpha=0.9, lmbd=1e-5,
-                      workspace=ws, path=path, write_grad=False,
-                      carry=ops.STEP_CARRY if state["carried"] else ops.STEP_CARRY_INIT)
-    state["carried"] = True
-    state["k"] = k + 1
+  def scan(k):
+    # k steps of solver.mcmc's scan in ONE C call (what alias.sgld runs for a data set
+    # resident in HBM): per step minibatch draw (threefry randint) + operand staging one
+    # step ahead on a side stream, the tcgen05 potential kernel, the fused pSGLD update
+    ops.glm_sgld_scan_device(spec, theta, X, y, N, n, U, var, grad, keys[0], keys[1], [d],
+                             np.full(k, eps, np.float32), np.ones(k, np.float32),
+                             np.zeros(k, np.uint8), None, None, 0, data_key_a=dkey[0],
+                             data_key_b=dkey[1], idx_buf=idx, idx_all=None, v=v, alpha=0.9,
+                             lmbd=1e-5, workspace=ws, path=path)
+    if k % 2:                                  # the chain / data keys ping-pong once per step
+      keys.reverse()
+      dkey.reverse()
 
   # Clock sampler runs from the warm-up on, so that every nvidia-smi sample is
   # taken under the same load as the timed region that follows immediately; the
   # warm-up is W steps, extended to ~0.4 s so the sampler is up before timing.
   sampler = ClockSampler(local)
   sampler.start()
-  t_w = time.perf_counter()
-  n_w = 0
-  while n_w < max(3, args.warmup) or time.perf_counter() - t_w < 0.4:
-    step()
-    n_w += 1
-    if n_w % 50 == 0:
-      stream.sync()
+  W = max(3, args.warmup)
+  scan(W)
   stream.sync()
+  t_w = time.perf_counter()
+  while time.perf_counter() - t_w < 0.4:
+    scan(200)
+    stream.sync()
 
   # ---- timed region: exactly K steps ----------------------------------------
   ctl.barrier()
@@ -312,8 +372,7 @@ def run_b200(args):
   e0, e1 = Event(), Event()
   l0 = ops.launch_count()
   e0.record(stream)
-  for _ in range(args.steps):
-    step()
+  scan(args.steps)
   e1.record(stream)
   e1.sync()
   device.synchronize()
@@ -323,6 +382,29 @@ def run_b200(args):
   clocks = sampler.stop()
   ms = ctl.max(ms)
   value = world * C * args.steps / (ms * 1e-3)
+
+  # ---- where the step's time goes: CUDA events between the launches of the carried
+  # step (synchronises every step -- measurement only, not the number above) -----------
+  step_profile = None
+  if path != "simt":
+    st = {"k": 0}
+    ops.set_option(ops.OPT_STEP_PROFILE, 1)
+    for i in range(120):
+      k = st["k"]
+      ops.minibatch_draw(dkey[k % 2], dkey[(k + 1) % 2], idx, N)
+      ops.glm_sgld_step(spec, theta, X, y, idx, N, U, var, grad, keys[k % 2],
+                        keys[(k + 1) % 2], eps, 1.0, v=v, alpha=0.9, lmbd=1e-5,
+                        workspace=ws, path=path, write_grad=False,
+                        carry=ops.STEP_CARRY if k else ops.STEP_CARRY_INIT)
+      st["k"] = k + 1
+      if i == 19:
+        ops.step_profile(reset=True)
+    pr = ops.step_profile()
+    ops.set_option(ops.OPT_STEP_PROFILE, 0)
+    stream.sync()
+    step_profile = {"us_prepare": pr[0], "us_potential": pr[1], "us_update": pr[2],
+                    "steps": pr[3], "note": "every step synchronised; prepare = minibatch "
+                    "operand staging (off the critical path in the scan)"}
 
   # ---- roofline of the dominant HBM kernel (fused pSGLD update) --------------
   # rotating state sets so the working set (R x 67 MB) exceeds the 126 MB L2
@@ -341,111 +423,95 @@ def run_b200(args):
   e1.record(stream)
   e1.sync()
   upd_ms = e0.elapsed_ms(e1) / (reps * R)
+  del sets
   alg_bytes = C * d * BYTES_PER_PARAM["sgld_rms"]
   achieved = alg_bytes / (upd_ms * 1e-3) / 1e9
   peak = peaks.get("hbm_gbs", 6650.0)
+  traffic = None
+  tp = os.path.join(ROOT, "profiles", "r02_update_traffic.json")
+  if os.path.exists(tp) and (C, d) == (4096, 1024):
+    # dram__bytes_read.sum + dram__bytes_write.sum per launch, parsed from the committed
+    # ncu capture (tools/summarize_ncu.py writes this file)
+    traffic = json.load(open(tp)).get("k_noise_pass_rms_bytes_per_launch")
   roofline = {"bound": "hbm", "kernel": "k_noise_pass<SgldOp<rms>>",
               "achieved": achieved, "peak": peak, "unit": "GB/s",
-              "frac": achieved / peak,
-              # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set
-              # full capture profiles/r01_step_kernels_ncu.md (C2 shape): reads are the
-              # algorithmic 50.3 MB; the 33.6 MB of stores were still in the write-back
-              # L2 when the capture ended
-              "traffic": 50.58e6 if (C, d) == (4096, 1024) else None,
+              "frac": achieved / peak, "traffic": traffic,
               "us_per_launch": upd_ms * 1e3,
               "peak_source": "measured" if "hbm_gbs" in peaks else "fallback",
               "algorithmic_bytes_per_launch": alg_bytes}
+  if step_profile is not None:
+    # the update of the carried step (k_sgld_apply_split: noise pre-generated under the
+    # GEMM mainloops, also emits theta's fp16 operand form): same algorithmic bytes
+    roofline["in_step_update"] = {
+        "kernel": "k_sgld_apply_split", "us_per_launch": step_profile["us_update"],
+        "achieved": alg_bytes / (step_profile["us_update"] * 1e-6) / 1e9,
+        "frac": alg_bytes / (step_profile["us_update"] * 1e-6) / 1e9 / peak}
 
-  # ---- tensor-pipe roofline of the GLM potential op (prepare + 2 tcgen05 GEMMs) -
+  # ---- tensor-pipe roofline of the GLM potential kernel --------------------------
   roofline_tensor = None
-  if path != "simt":
-    ws2 = ops.glm_workspace(C, n, d, path)
-    for _ in range(3):
-      ops.glm_potential_grad(spec, theta, X, y, idx, N, U, var, grad, workspace=ws2,
-                             path=path)
-    e0.record(stream)
-    for _ in range(reps):
-      ops.glm_potential_grad(spec, theta, X, y, idx, N, U, var, grad, workspace=ws2,
-                             path=path)
-    e1.record(stream)
-    e1.sync()
-    pot_ms = e0.elapsed_ms(e1) / reps
+  if step_profile is not None:
     flops = 4.0 * n * d * C                      # algorithmic: 2ndC forward + 2ndC backward
-    tf = flops / (pot_ms * 1e-3) / 1e12
-    tpeak = peaks.get("bf16_tflops_sustained", 1400.0)
+    passes = 3 if path == "tc_parity" else 1
+    pot_us = step_profile["us_potential"]
+    tf = flops / (pot_us * 1e-6) / 1e12
+    tpeak = peaks.get("bf16_tflops", 1650.0)
     roofline_tensor = {
-        "bound": "tensor", "kernel": "k_glm_tc_gemm (x2) + k_prepare_all",
+        "bound": "tensor", "kernel": "k_glm_tc_pair (both contractions, one launch)",
         "achieved": tf, "peak": tpeak, "unit": "TFLOP/s", "frac": tf / tpeak,
-        "us_per_call": pot_ms * 1e3, "algorithmic_flops_per_call": flops,
-        "tensor_passes": 3 if path == "tc_parity" else 1,
-        "note": "peak = measured sustained bf16 GEMM; the parity path spends 3 "
-                "fp16 MMA passes per algorithmic FLOP (fp32-level accuracy)"}
+        "us_per_call": pot_us, "algorithmic_flops_per_call": flops,
+        "tensor_passes": passes, "hardware_frac": passes * tf / tpeak,
+        "note": "peak = measured burst bf16 GEMM; CUDA events around the kernel inside the "
+                "step; the parity path spends 3 fp16 MMA passes per algorithmic FLOP "
+                "(fp32-level accuracy), hardware_frac counts them"}
 
-  # ---- e2e: host data loader path ---------------------------------------------
-  # Every step's minibatch rows travel host -> device from pinned memory and the
-  # step's result (U, var per chain) travels device -> host, all inside the timed
-  # region, through the library's native scan (sgmc_glm_sgld_scan_host): the inner
-  # loop of solver.mcmc over host-resident batches in one C call per 100 steps --
-  # a copy stream keeps two batches ahead of the sampling stream through a ring of
-  # three device slots, results are read back every step, and the host consumes
-  # them chunk by chunk (the natural pipelining of the reference's host cache,
-  # data/core.py:664-791; the minibatch sequence does not depend on the chains).
-  import ctypes as Ct
-  from jax_sgmc_b200.io import _pinned_array
-  copy_stream = Stream.create()
-  stride = n * d + n
-  HB, SLOTS, CHUNK = 4, 3, 100
-  hb, hb_addr = _pinned_array(HB * stride)
-  Xg = ops.gather_rows(X, idx).numpy().ravel()
-  yg = ops.gather_rows(y.reshape(N, 1), idx).numpy().ravel()
-  for b in range(HB):
-    hb[b * stride:b * stride + n * d] = Xg
-    hb[b * stride + n * d:(b + 1) * stride] = yg
-  res, res_addr = _pinned_array(CHUNK * 2 * C)
-  slots, uv = DA((SLOTS * stride,), np.float32), DA((2, 2, C), np.float32)
-  eps_arr = np.full(CHUNK, eps, np.float32)
-
-  def run_e2e(steps):
-    done, checksum = 0, 0.0
-    while done < steps:
-      k = min(CHUNK, steps - done)
-      ka, kb = keys[state["k"] % 2], keys[(state["k"] + 1) % 2]
-      ops.glm_sgld_scan_host(spec, theta, hb_addr, HB, k, n, N, slots, SLOTS, uv, res_addr,
-                             grad, ka, kb, eps_arr, copy_stream, temperature=1.0, v=v,
-                             alpha=0.9, lmbd=1e-5, workspace=ws, path=path)
-      state["k"] += k
-      stream.sync()
-      copy_stream.sync()
-      checksum += float(res[:k * 2 * C].reshape(k, 2, C)[:, 0, 0].sum())   # host reads results
-      done += k
-    return checksum
-
-  # the host->device link on its own (pinned 4 MB copies back to back): the e2e
-  # number is bounded by bytes_per_step / this bandwidth
-  l0e, l1e = Event(), Event()
-  l0e.record(copy_stream)
-  for _ in range(20):
-    _lib.call("sgmc_memcpy_h2d", Ct.c_void_p(slots.ptr), Ct.c_void_p(hb_addr), n * d * 4,
-              copy_stream.handle)
-  l1e.record(copy_stream)
-  l1e.sync()
-  h2d_gbs = 20 * n * d * 4 / (l0e.elapsed_ms(l1e) * 1e-3) / 1e9
-
-  run_e2e(8)
+  # ---- e2e: the operator API over a HOST-resident data set -------------------------
+  # alias.sgld(potential, StreamingNumpyDataLoader(...)) -> solver.mcmc -> native host
+  # scan.  Inside the timed region, every step: the host gathers the minibatch's rows
+  # from the 4.1 GB array (threads, into page-locked memory), the rows travel H2D on a
+  # copy stream (with N ranks each rank uploads 1/N of the rows and NCCL all-gathers them
+  # over NVLink), the step runs, (U, var) of every chain travel D2H; the kept sample is
+  # downloaded at the end.
+  hX, hy = X.numpy(), y.numpy()
+  del X, y
+  loader = data.StreamingNumpyDataLoader(x=hX, y=hy)
+  if nccl is not None:
+    loader.shard_upload(nccl)
+  pot = potential.minibatch_potential(glm.GaussianPrior(10.0), glm.LogisticRegression(),
+                                      path=path)
+  e2e_steps = max(args.steps, 4000)
+  sampler_fn = alias.sgld(pot, loader, cache_size=64, batch_size=n, first_step_size=eps,
+                          last_step_size=eps / 10, burn_in=0, accepted_samples=1,
+                          rms_prop=True, progress_bar=False)
+  from jax_sgmc_b200.tree_util import ChainTree
+  init = ChainTree.like(ChainTree.from_trees([{"w": np.zeros(d, np.float32)}]), DA.zeros((C, d)))
+  chain_keys = np.stack([ops.prng_key(rank * C + c) for c in range(C)])
+  sampler_fn(init, iterations=128, keys=chain_keys)           # warm-up (buffers, maps)
+  init = ChainTree.like(init, DA.zeros((C, d)))
   ctl.barrier()
-  e2e_steps = max(10, args.steps // 2)
   t0 = time.perf_counter()
-  e2e_checksum = run_e2e(e2e_steps)
+  res = sampler_fn(init, iterations=e2e_steps, keys=chain_keys)
+  device.synchronize()
   e2e_s = ctl.max(time.perf_counter() - t0)
-  assert np.isfinite(e2e_checksum)
+  kept = np.asarray(res[0]["samples"]["variables"]["w"])
+  assert np.all(np.isfinite(kept))
+  h2d = int(getattr(pot, "h2d_bytes_per_step", 0))
+  d2h = int(getattr(pot, "d2h_bytes_per_step", 0))
+  assert h2d > 0 and d2h > 0, "the e2e run did not take the host-stream scan"
   e2e = {"value": world * C * e2e_steps / e2e_s, "unit": UNIT,
-         "h2d_bytes_per_step": n * d * 4 + n * 4, "d2h_bytes_per_step": C * 8,
-         "steps": e2e_steps, "h2d_link_gbs_measured": h2d_gbs,
-         "link_bound_us_per_step": (n * d * 4 + n * 4) / (h2d_gbs * 1e9) * 1e6,
-         "what": "host data loader through sgmc_glm_sgld_scan_host: every step's minibatch "
-                 "rows H2D from pinned host memory (copy stream two batches ahead, three "
-                 "device slots), potential + variance of every chain D2H every step, read "
-                 "by the host per 100-step call"}
+         "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+         "seconds": e2e_s,
+         "what": "through alias.sgld(minibatch_potential, StreamingNumpyDataLoader): host "
+                 "gather of every minibatch from the host-resident data set, H2D of the rows "
+                 "from pinned memory" + (f" (1/{world} per rank + NCCL all-gather)" if world > 1
+                                         else "") +
+                 ", (U, var) of every chain D2H every step, kept sample downloaded; wall "
+                 "clock around the whole run_fn call"}
+  del loader, hX, hy
+
+  resgld = None
+  if not args.no_resgld:
+    resgld = bench_resgld(args, ctl, nccl, stream, path)
+  row_sharded = bench_row_sharded(args, ctl, nccl, stream)
 
   cpu_base = None
   if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -454,7 +520,7 @@ def run_b200(args):
   if rank == 0:
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
-        "steps": args.steps, "warmup": max(3, args.warmup),
+        "steps": args.steps, "warmup": W,
         "ms_per_step": ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
@@ -468,8 +534,9 @@ def run_b200(args):
                          f"{R} rotating state sets ({R * 3 * C * d * 4 / 1e6:.0f} MB)",
                    "parallelism": f"chains x{world}"},
         "clocks": clocks, "gpu_launches": int(launches),
-        "roofline": roofline, "roofline_tensor": roofline_tensor, "e2e": e2e,
-        "cpu_baseline": cpu_base,
+        "roofline": roofline, "roofline_tensor": roofline_tensor,
+        "step_profile": step_profile, "e2e": e2e,
+        "cpu_baseline": cpu_base, "resgld": resgld, "row_sharded_gradient": row_sharded,
     }
     print(json.dumps(line), flush=True)
   ctl.close()

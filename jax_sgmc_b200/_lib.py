@@ -26,6 +26,18 @@ class GlmSpec(C.Structure):
               ("x_absmax", C.c_float)]
 
 
+MLP_MAX_LAYERS = 8
+
+
+class MlpSpec(C.Structure):
+  """``sgmc_mlp_spec`` (include/sgmc_b200.h)."""
+  _fields_ = [("n_layers", C.c_int32), ("sizes", C.c_int32 * (MLP_MAX_LAYERS + 1)),
+              ("w_off", C.c_int64 * MLP_MAX_LAYERS), ("b_off", C.c_int64 * MLP_MAX_LAYERS),
+              ("activation", C.c_int32), ("prior", C.c_int32), ("prior_off", C.c_int64),
+              ("prior_size", C.c_int64), ("prior_scale", C.c_float),
+              ("temperature", C.c_float)]
+
+
 _vp, _i64, _i32, _f32, _sz = C.c_void_p, C.c_int64, C.c_int32, C.c_float, C.c_size_t
 _int = C.c_int
 
@@ -93,6 +105,8 @@ PROTOTYPES = {
                                 _i64, _i64, _i64, _vp, _int, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _f32,
                                 _f32, _vp, _sz, _int, _int, _vp, _int, _int, _vp, _vp, _vp, _i64,
                                 C.POINTER(_i64)],
+    "sgmc_mlp_potential_grad": [_vp, C.POINTER(MlpSpec), _vp, _i64, _i64, _vp, _vp, _vp, _vp,
+                                _i64, _i64, _vp, _vp, _vp, _vp, _vp, _sz],
     "sgmc_host_gather_batches": [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _int],
     "sgmc_glm_sgld_scan_device": [_vp, C.POINTER(GlmSpec), _vp, _vp, _i64, _i64, _vp, _vp, _i64,
                                   _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
@@ -136,6 +150,7 @@ SPECIAL = {
     "sgmc_nccl_available": ([], _int),
     "sgmc_glm_workspace_bytes": ([_i64, _i64, _i64, _int], _sz),
     "sgmc_p2p_window_bytes": ([_int, _sz], _sz),
+    "sgmc_mlp_workspace_bytes": ([C.POINTER(MlpSpec), _i64, _i64], _sz),
 }
 
 _lib = None

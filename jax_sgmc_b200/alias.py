@@ -22,6 +22,15 @@ from .tree_util import ChainTree
 Pytree = Any
 
 
+def _chains(init_samples) -> ChainTree:
+  """One host pytree per chain (the reference's ``*init_samples``), or a single
+  ChainTree that already holds every chain on the device."""
+  init_samples = list(init_samples)
+  if len(init_samples) == 1 and isinstance(init_samples[0], ChainTree):
+    return init_samples[0]
+  return ChainTree.from_trees(init_samples)
+
+
 def _schedule(first_step_size, last_step_size, burn_in, accepted_samples,
               progress_bar, temperature=None):
   step_size_schedule = scheduler.polynomial_step_size_first_last(
@@ -57,7 +66,7 @@ def sgld(potential_fn, data_loader, cache_size: int = 512, batch_size: int = 32,
 
   def run_fn(*init_samples, init_model_state: Pytree = None, iterations=1000,
              keys=None):
-    state = sgld_solver[0](ChainTree.from_trees(list(init_samples)), key=keys,
+    state = sgld_solver[0](_chains(init_samples), key=keys,
                            adaption_kwargs={"alpha": alpha, "lmbd": lmbd},
                            init_model_state=init_model_state)
     return mcmc(state, iterations=iterations)
@@ -84,8 +93,8 @@ def re_sgld(potential_fn, data_loader, cache_size: int = 512, batch_size: int = 
   def run_fn(*init_samples, init_model_state: Pytree = None, iterations=1000,
              keys=None):
     normal, tempered = zip(*init_samples)
-    state = resgld_solver[0](ChainTree.from_trees(list(normal)),
-                             ChainTree.from_trees(list(tempered)), key=keys,
+    state = resgld_solver[0](_chains(normal),
+                             _chains(tempered), key=keys,
                              init_model_state=init_model_state)
     return mcmc(state, iterations=iterations,
                 schedulers=[{"temperature": {"tau": temperature}}])   # :205-207
@@ -116,7 +125,7 @@ def sghmc(potential_fn, data_loader, cache_size: int = 512, batch_size: int = 32
 
   def run_fn(*init_samples, init_model_state: Pytree = None, iterations=1000,
              keys=None):
-    state = sghmc_solver[0](ChainTree.from_trees(list(init_samples)), key=keys,
+    state = sghmc_solver[0](_chains(init_samples), key=keys,
                             init_model_state=init_model_state)
     return mcmc(state, iterations=iterations)
 
@@ -142,7 +151,7 @@ def obabo(potential_fn, data_loader, cache_size: int = 512, batch_size: int = 32
 
   def run_fn(*init_samples, init_model_state: Pytree = None, iterations=1000,
              keys=None):
-    state = obabo_solver[0](ChainTree.from_trees(list(init_samples)), key=keys,
+    state = obabo_solver[0](_chains(init_samples), key=keys,
                             init_model_state=init_model_state)
     return mcmc(state, iterations=iterations)
 
@@ -192,7 +201,7 @@ def amagold(stochastic_potential_fn, full_potential_fn, data_loader,
                      saving=_saving(save_to_numpy))
 
   def run_fn(*init_samples, init_model_state: Pytree = None, iterations=1000, keys=None):
-    state = amagold_solver[0](ChainTree.from_trees(list(init_samples)), key=keys,
+    state = amagold_solver[0](_chains(init_samples), key=keys,
                               init_model_state=init_model_state)
     return mcmc(state, iterations=iterations)
 
@@ -220,7 +229,7 @@ def sggmc(stochastic_potential_fn, full_potential_fn, data_loader,
                      saving=_saving(save_to_numpy))
 
   def run_fn(*init_samples, init_model_state: Pytree = None, iterations=1000, keys=None):
-    state = sggmc_solver[0](ChainTree.from_trees(list(init_samples)), key=keys,
+    state = sggmc_solver[0](_chains(init_samples), key=keys,
                             init_model_state=init_model_state)
     return mcmc(state, iterations=iterations)
 

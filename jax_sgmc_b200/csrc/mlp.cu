@@ -1,0 +1,428 @@
+// Bayesian MLP classifier potential + gradient, batched over chains (BASELINE.json
+// configs[2]: 784-512-512-10, tanh, 256 chains).
+//
+// Replaces, for the dense-network likelihood, what the reference obtains from
+// jax.value_and_grad(potential_fn) (jax_sgmc/integrator.py:593, :166, :792) over
+// potential.minibatch_potential (jax_sgmc/potential.py:159-214) with the per-observation
+// likelihood of examples/cifar.md:196-204 evaluated under vmap (potential.py:141-156):
+// the forward pass, the softmax cross entropy, and the hand-derived reverse pass.
+// Every chain has its own weights, so each layer is a chain-batched GEMM (blockIdx.z =
+// chain); the minibatch is shared by all chains (gathered through `idx` inside the
+// operand loads).  Launches per evaluation for L layers: 1 (prior) + L (forward) + 1
+// (head) + per layer 2..3 (bias gradient, weight gradient, input gradient).
+//
+// This file is the fp32 path: 128 x 128 x 16 shared-memory tiles, 8 x 8 register
+// micro-tiles, FFMA; operand loads are scalar and bounds-checked so any offset /
+// alignment of the layers inside the raveled sample works (the reference's pytrees put
+// biases of 10 floats between the weight matrices).
+#include "common.cuh"
+#include "glm_math.cuh"
+
+namespace sgmc {
+
+constexpr int kBM = 128, kBN = 128, kBK = 16, kBThreads = 256, kBPad = 4;
+constexpr int kSumsqParts = 32;
+
+enum : int { kEpiStore = 0, kEpiBiasTanh = 1, kEpiBias = 2, kEpiDtanh = 3, kEpiPrior = 4 };
+
+struct BgemmArgs {
+  // C[b] (M x N) = opA(A[b]) (M x K) . opB(B[b]) (K x N)
+  const float* A; int64_t a_batch, lda; const int32_t* a_idx;   // a_idx: gather on A's strided dim
+  const float* B; int64_t b_batch, ldb;
+  float* C; int64_t c_batch, ldc;
+  int M, N, K;
+  const float* bias; int64_t bias_batch;                        // kEpiBias*: + bias[n]
+  const float* aux; int64_t aux_batch, ldaux;                   // kEpiDtanh: * (1 - aux^2); kEpiPrior: + coef * aux
+  float coef;
+  int64_t p0, prior_lo, prior_hi;                               // kEpiPrior: flat index of C(0,0), prior range
+};
+
+// One operand tile -> registers.  MN_CONTIG: element (k, mn) at base + row(k) * ld + mn
+// (the tile's M / N index is contiguous in memory); otherwise element (mn, k) at
+// base + row(mn) * ld + k (K contiguous).  `row` applies the optional gather.
+template <bool MN_CONTIG>
+__device__ __forceinline__ void load_tile(float (&r)[8], const float* __restrict__ base, int64_t ld,
+                                          const int32_t* __restrict__ idx, int mn0, int k0, int MN,
+                                          int K, int t) {
+  if (MN_CONTIG) {
+    const int mn = mn0 + (t & 127);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int k = k0 + (t >> 7) + 2 * i;
+      float v = 0.f;
+      if (mn < MN && k < K) v = __ldg(base + (int64_t)(idx ? idx[k] : k) * ld + mn);
+      r[i] = v;
+    }
+  } else {
+    const int k = k0 + (t & 15);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int mn = mn0 + (t >> 4) + 16 * i;
+      float v = 0.f;
+      if (mn < MN && k < K) v = __ldg(base + (int64_t)(idx ? idx[mn] : mn) * ld + k);
+      r[i] = v;
+    }
+  }
+}
+
+template <bool MN_CONTIG>
+__device__ __forceinline__ void store_tile(float (*s)[kBM + kBPad], const float (&r)[8], int t) {
+  if (MN_CONTIG) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s[(t >> 7) + 2 * i][t & 127] = r[i];
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s[t & 15][(t >> 4) + 16 * i] = r[i];
+  }
+}
+
+// A_T: A is stored K x M (M contiguous), else M x K (K contiguous).
+// B_T: B is stored N x K (K contiguous), else K x N (N contiguous).
+template <bool A_T, bool B_T, int EPI>
+__global__ void __launch_bounds__(kBThreads, 2) k_bgemm(const BgemmArgs a) {
+  __shared__ __align__(16) float As[2][kBK][kBM + kBPad];
+  __shared__ __align__(16) float Bs[2][kBK][kBN + kBPad];
+  const int t = threadIdx.x, tx = t & 15, ty = t >> 4;
+  const int m0 = blockIdx.y * kBM, n0 = blockIdx.x * kBN;
+  const int64_t b = blockIdx.z;
+  const float* A = a.A + b * a.a_batch;
+  const float* B = a.B + b * a.b_batch;
+  pdl_launch_dependents();
+  pdl_wait();
+
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+  float ra[8], rb[8];
+  const int kt = (a.K + kBK - 1) / kBK;
+  load_tile<A_T>(ra, A, a.lda, a.a_idx, m0, 0, a.M, a.K, t);
+  load_tile<!B_T>(rb, B, a.ldb, nullptr, n0, 0, a.N, a.K, t);
+  store_tile<A_T>(As[0], ra, t);
+  store_tile<!B_T>(Bs[0], rb, t);
+  __syncthreads();
+  for (int it = 0; it < kt; ++it) {
+    const int cur = it & 1;
+    if (it + 1 < kt) {
+      load_tile<A_T>(ra, A, a.lda, a.a_idx, m0, (it + 1) * kBK, a.M, a.K, t);
+      load_tile<!B_T>(rb, B, a.ldb, nullptr, n0, (it + 1) * kBK, a.N, a.K, t);
+    }
+#pragma unroll
+    for (int kk = 0; kk < kBK; ++kk) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[cur][kk][ty * 4]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[cur][kk][64 + ty * 4]);
+      const float4 b0 = *reinterpret_cast<const float4*>(&Bs[cur][kk][tx * 4]);
+      const float4 b1 = *reinterpret_cast<const float4*>(&Bs[cur][kk][64 + tx * 4]);
+      const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    if (it + 1 < kt) {
+      store_tile<A_T>(As[cur ^ 1], ra, t);
+      store_tile<!B_T>(Bs[cur ^ 1], rb, t);
+    }
+    __syncthreads();
+  }
+
+  float* Cb = a.C + b * a.c_batch;
+  const float* bias = (EPI == kEpiBiasTanh || EPI == kEpiBias) ? a.bias + b * a.bias_batch : nullptr;
+  const float* aux = (EPI == kEpiDtanh || EPI == kEpiPrior) ? a.aux + b * a.aux_batch : nullptr;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int m = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + i - 4);
+    if (m >= a.M) continue;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int n = n0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + j - 4);
+      if (n >= a.N) continue;
+      float v = acc[i][j];
+      if (EPI == kEpiBiasTanh) v = tanhf(v + __ldg(bias + n));
+      if (EPI == kEpiBias) v = v + __ldg(bias + n);
+      if (EPI == kEpiDtanh) {
+        const float h = __ldg(aux + (int64_t)m * a.ldaux + n);
+        v = v * (1.0f - h * h);
+      }
+      if (EPI == kEpiPrior) {
+        const int64_t p = a.p0 + (int64_t)m * a.ldc + n;
+        if (p >= a.prior_lo && p < a.prior_hi)
+          v = fmaf(a.coef, __ldg(aux + (int64_t)m * a.ldaux + n), v);
+      }
+      Cb[(int64_t)m * a.ldc + n] = v;
+    }
+  }
+}
+
+template <bool A_T, bool B_T, int EPI>
+static int launch_bgemm(cudaStream_t s, const BgemmArgs& a, int64_t batch, const char* name) {
+  SGMC_REQUIRE(batch <= 65535, "%s: more than 65535 chains per call", name);
+  dim3 grid((unsigned)((a.N + kBN - 1) / kBN), (unsigned)((a.M + kBM - 1) / kBM), (unsigned)batch);
+  launch_pdl(k_bgemm<A_T, B_T, EPI>, grid, dim3(kBThreads), 0, s, a);
+  return post_launch(name);
+}
+
+// ---- prior: per-chain partial sums of theta^2 over [lo, hi) ------------------------
+__global__ void __launch_bounds__(256) k_mlp_sumsq(const float* __restrict__ theta, int64_t P,
+                                                   int64_t lo, int64_t hi,
+                                                   float* __restrict__ parts) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int64_t c = blockIdx.y;
+  const int64_t span = hi - lo, per = (span + kSumsqParts - 1) / kSumsqParts;
+  const int64_t b0 = lo + blockIdx.x * per, b1 = min(hi, b0 + per);
+  const float* row = theta + c * P;
+  float s = 0.f;
+  for (int64_t p = b0 + threadIdx.x; p < b1; p += 256) {
+    const float v = row[p];
+    s = fmaf(v, v, s);
+  }
+  __shared__ float red[256];
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int w = 128; w > 0; w >>= 1) {
+    if ((int)threadIdx.x < w) red[threadIdx.x] += red[threadIdx.x + w];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) parts[c * kSumsqParts + blockIdx.x] = red[0];
+}
+
+// ---- head: softmax cross entropy, statistics, d logits ------------------------------
+// One CTA per chain.  ell_i = logits[label_i] - logsumexp(logits_i) (the max-shifted form
+// of jax.nn.log_softmax); U = (-N mean(ell) - prior) / T or the masked form
+// (potential.py:183-185, :210); var(ell) (integrator.py:880);
+// dlogits_i = cot_i (onehot - softmax), cot_i = (-N / n) / T (* mask_i).
+struct HeadArgs {
+  const float* logits;      // [C][n][K]
+  float* dlogits;           // [C][n][K] or null
+  float* ell_ws;            // [C][n]
+  float* ell_out;           // [C][n] or null
+  const float* y; const int32_t* idx; const float* mask;
+  int n, K;
+  float n_obs, inv_temperature, prior_half_inv;
+  const float* sumsq_parts; // [C][kSumsqParts] or null (flat prior)
+  float* potential; float* variance;
+};
+
+__device__ __forceinline__ float block_sum_256(float v, float* red) {
+  __syncthreads();
+  red[threadIdx.x] = v;
+  __syncthreads();
+  for (int w = 128; w > 0; w >>= 1) {
+    if ((int)threadIdx.x < w) red[threadIdx.x] += red[threadIdx.x + w];
+    __syncthreads();
+  }
+  return red[0];
+}
+
+__global__ void __launch_bounds__(256) k_mlp_head(const HeadArgs a) {
+  pdl_launch_dependents();
+  pdl_wait();
+  __shared__ float red[256];
+  const int64_t c = blockIdx.x;
+  const float cot = (-a.n_obs / (float)a.n) * a.inv_temperature;
+  float s_ell = 0.f, s_mask = 0.f;
+  for (int i = threadIdx.x; i < a.n; i += 256) {
+    const float* lg = a.logits + (c * a.n + i) * a.K;
+    const int label = (int)a.y[a.idx ? a.idx[i] : i];
+    float m = -INFINITY;
+    for (int k = 0; k < a.K; ++k) m = fmaxf(m, lg[k]);
+    float se = 0.f;
+    for (int k = 0; k < a.K; ++k) se += expf(lg[k] - m);
+    const float lse = logf(se);
+    const float mk = a.mask ? a.mask[i] : 1.0f;
+    const float l = (lg[label] - m) - lse;
+    a.ell_ws[c * a.n + i] = l;
+    if (a.ell_out) a.ell_out[c * a.n + i] = l;
+    s_ell += l;
+    s_mask = fmaf(l, mk, s_mask);
+    if (a.dlogits) {
+      float* dl = a.dlogits + (c * a.n + i) * a.K;
+      const float ci = cot * mk;
+      for (int k = 0; k < a.K; ++k) {
+        const float soft = expf(lg[k] - m) / se;
+        dl[k] = ci * ((k == label ? 1.0f : 0.0f) - soft);
+      }
+    }
+  }
+  const float sum = block_sum_256(s_ell, red);
+  const float msum = block_sum_256(s_mask, red);
+  const float mean = sum / (float)a.n;
+  float dev = 0.f;
+  for (int i = threadIdx.x; i < a.n; i += 256) {
+    const float dlt = a.ell_ws[c * a.n + i] - mean;
+    dev = fmaf(dlt, dlt, dev);
+  }
+  const float m2 = block_sum_256(dev, red);
+  if (threadIdx.x == 0) {
+    float prior = 0.f;
+    if (a.sumsq_parts) {
+      float ss = 0.f;
+      for (int q = 0; q < kSumsqParts; ++q) ss += a.sumsq_parts[c * kSumsqParts + q];
+      prior = -a.prior_half_inv * ss;
+    }
+    const float L = a.mask ? (-a.n_obs / (float)a.n) * msum : -a.n_obs * mean;
+    a.potential[c] = (L - prior) * a.inv_temperature;
+    if (a.variance) a.variance[c] = m2 / (float)a.n;
+  }
+}
+
+// ---- bias gradient: db[c][o] = sum_i dA[c][i][o] (+ prior term) -----------------------
+__global__ void __launch_bounds__(256) k_mlp_bias_grad(const float* __restrict__ dA, int n, int out,
+                                                       const float* __restrict__ theta,
+                                                       float* __restrict__ grad, int64_t P,
+                                                       int64_t b_off, float coef, int64_t prior_lo,
+                                                       int64_t prior_hi) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int o = blockIdx.x * 256 + threadIdx.x;
+  const int64_t c = blockIdx.y;
+  if (o >= out) return;
+  const float* src = dA + c * (int64_t)n * out + o;
+  float s = 0.f;
+  for (int i = 0; i < n; ++i) s += src[(int64_t)i * out];
+  const int64_t p = b_off + o;
+  if (p >= prior_lo && p < prior_hi) s = fmaf(coef, theta[c * P + p], s);
+  grad[c * P + p] = s;
+}
+
+struct MlpWs {
+  float* H[SGMC_MLP_MAX_LAYERS + 1];   // activations h_1 .. h_{L-1}, logits = H[L]
+  float* dA[SGMC_MLP_MAX_LAYERS + 1];  // dA_1 .. dA_L
+  float* ell; float* sumsq;
+};
+
+static size_t mlp_carve(MlpWs* w, uint8_t* base, const sgmc_mlp_spec& s, int64_t C, int64_t n) {
+  size_t off = 0;
+  auto take = [&](size_t floats) {
+    float* p = base ? reinterpret_cast<float*>(base + off) : nullptr;
+    off += (floats * 4 + 255) & ~(size_t)255;
+    return p;
+  };
+  for (int l = 1; l <= s.n_layers; ++l) {
+    float* h = take((size_t)C * n * s.sizes[l]);
+    float* d = take((size_t)C * n * s.sizes[l]);
+    if (w) { w->H[l] = h; w->dA[l] = d; }
+  }
+  float* ell = take((size_t)C * n);
+  float* sq = take((size_t)C * kSumsqParts);
+  if (w) { w->ell = ell; w->sumsq = sq; }
+  return off;
+}
+
+static int mlp_check(const sgmc_mlp_spec* s, int64_t P) {
+  SGMC_REQUIRE(s != nullptr, "null spec");
+  SGMC_REQUIRE(s->n_layers >= 1 && s->n_layers <= SGMC_MLP_MAX_LAYERS, "1..%d layers",
+               SGMC_MLP_MAX_LAYERS);
+  SGMC_REQUIRE(s->activation == 0, "activation: 0 (tanh)");
+  SGMC_REQUIRE(s->prior == kPriorFlat || s->prior == kPriorGaussian, "prior: flat or gaussian");
+  for (int l = 0; l < s->n_layers; ++l) {
+    SGMC_REQUIRE(s->sizes[l] > 0 && s->sizes[l + 1] > 0, "layer widths must be positive");
+    SGMC_REQUIRE(s->w_off[l] >= 0 && s->w_off[l] + (int64_t)s->sizes[l] * s->sizes[l + 1] <= P &&
+                 s->b_off[l] >= 0 && s->b_off[l] + s->sizes[l + 1] <= P,
+                 "layer %d lies outside the sample", l);
+  }
+  return 0;
+}
+
+}  // namespace sgmc
+
+using namespace sgmc;
+
+extern "C" {
+
+size_t sgmc_mlp_workspace_bytes(const sgmc_mlp_spec* spec, int64_t n_chains, int64_t batch_size) {
+  if (!spec || spec->n_layers < 1 || spec->n_layers > SGMC_MLP_MAX_LAYERS) return 0;
+  return mlp_carve(nullptr, nullptr, *spec, n_chains, batch_size) + 256;
+}
+
+int sgmc_mlp_potential_grad(void* stream, const sgmc_mlp_spec* spec, const float* theta,
+                            int64_t n_chains, int64_t P, const float* X, const float* y,
+                            const int32_t* idx, const float* mask, int64_t batch_size,
+                            int64_t observation_count, float* potential, float* variance,
+                            float* grad, float* ell, void* workspace, size_t workspace_bytes) {
+  if (int e = mlp_check(spec, P)) return e;
+  SGMC_REQUIRE(theta && X && y && potential && workspace, "null argument");
+  const int64_t C = n_chains, n = batch_size;
+  SGMC_REQUIRE(C > 0 && n > 0 && n <= (1 << 24), "bad sizes");
+  SGMC_REQUIRE(workspace_bytes >= sgmc_mlp_workspace_bytes(spec, C, n), "workspace too small");
+  const sgmc_mlp_spec& sp = *spec;
+  const int L = sp.n_layers;
+  cudaStream_t s = (cudaStream_t)stream;
+  MlpWs w;
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(workspace) + 255) &
+                                             ~(uintptr_t)255);
+  mlp_carve(&w, base, sp, C, n);
+  const bool gauss = sp.prior == kPriorGaussian;
+  const int64_t prior_lo = gauss ? sp.prior_off : 0, prior_hi = gauss ? sp.prior_off + sp.prior_size : 0;
+  const float inv_T = 1.0f / sp.temperature;
+  // -(d prior / d theta) / T = theta / scale^2 / T
+  const float coef = gauss ? (1.0f / (sp.prior_scale * sp.prior_scale)) / sp.temperature : 0.f;
+
+  if (gauss && prior_hi > prior_lo) {
+    launch_pdl(k_mlp_sumsq, dim3(kSumsqParts, (unsigned)C), dim3(256), 0, s, theta, P, prior_lo,
+               prior_hi, w.sumsq);
+    if (post_launch("k_mlp_sumsq")) return 1;
+  }
+  // ---- forward: h_l = tanh(h_{l-1} W_l + b_l), logits = h_{L-1} W_L + b_L -------------
+  for (int l = 0; l < L; ++l) {
+    BgemmArgs g{};
+    const int in = sp.sizes[l], out = sp.sizes[l + 1];
+    if (l == 0) { g.A = X; g.a_batch = 0; g.lda = in; g.a_idx = idx; }
+    else { g.A = w.H[l]; g.a_batch = n * (int64_t)in; g.lda = in; }
+    g.B = theta + sp.w_off[l]; g.b_batch = P; g.ldb = out;
+    g.C = w.H[l + 1]; g.c_batch = n * (int64_t)out; g.ldc = out;
+    g.M = (int)n; g.N = out; g.K = in;
+    g.bias = theta + sp.b_off[l]; g.bias_batch = P;
+    if (l < L - 1) {
+      if (launch_bgemm<false, false, kEpiBiasTanh>(s, g, C, "k_bgemm<fwd,tanh>")) return 1;
+    } else {
+      if (launch_bgemm<false, false, kEpiBias>(s, g, C, "k_bgemm<fwd,logits>")) return 1;
+    }
+  }
+  // ---- head ------------------------------------------------------------------------------
+  HeadArgs h{};
+  h.logits = w.H[L]; h.dlogits = grad ? w.dA[L] : nullptr; h.ell_ws = w.ell; h.ell_out = ell;
+  h.y = y; h.idx = idx; h.mask = mask; h.n = (int)n; h.K = sp.sizes[L];
+  h.n_obs = (float)observation_count; h.inv_temperature = inv_T;
+  h.prior_half_inv = gauss ? 0.5f / (sp.prior_scale * sp.prior_scale) : 0.f;
+  h.sumsq_parts = gauss && prior_hi > prior_lo ? w.sumsq : nullptr;
+  h.potential = potential; h.variance = variance;
+  launch_pdl(k_mlp_head, dim3((unsigned)C), dim3(256), 0, s, h);
+  if (post_launch("k_mlp_head")) return 1;
+  if (!grad) return 0;
+  // ---- reverse pass ------------------------------------------------------------------------
+  for (int l = L - 1; l >= 0; --l) {
+    const int in = sp.sizes[l], out = sp.sizes[l + 1];
+    launch_pdl(k_mlp_bias_grad, dim3((unsigned)((out + 255) / 256), (unsigned)C), dim3(256), 0, s,
+               (const float*)w.dA[l + 1], (int)n, out, theta, grad, P, (int64_t)sp.b_off[l], coef,
+               prior_lo, prior_hi);
+    if (post_launch("k_mlp_bias_grad")) return 1;
+    {   // dW_l [in, out] = h_{l-1}^T [in, n] . dA_l [n, out]  (+ prior term) -> grad
+      BgemmArgs g{};
+      if (l == 0) { g.A = X; g.a_batch = 0; g.lda = in; g.a_idx = idx; }
+      else { g.A = w.H[l]; g.a_batch = n * (int64_t)in; g.lda = in; }
+      g.B = w.dA[l + 1]; g.b_batch = n * (int64_t)out; g.ldb = out;
+      g.C = grad + sp.w_off[l]; g.c_batch = P; g.ldc = out;
+      g.M = in; g.N = out; g.K = (int)n;
+      g.aux = theta + sp.w_off[l]; g.aux_batch = P; g.ldaux = out;
+      g.coef = coef; g.p0 = sp.w_off[l]; g.prior_lo = prior_lo; g.prior_hi = prior_hi;
+      if (launch_bgemm<true, false, kEpiPrior>(s, g, C, "k_bgemm<dW>")) return 1;
+    }
+    if (l > 0) {   // dA_{l-1} [n, in] = (dA_l [n, out] . W_l^T [out, in]) * (1 - h_{l-1}^2)
+      BgemmArgs g{};
+      g.A = w.dA[l + 1]; g.a_batch = n * (int64_t)out; g.lda = out;
+      g.B = theta + sp.w_off[l]; g.b_batch = P; g.ldb = out;      // stored [in][out] = N x K
+      g.C = w.dA[l]; g.c_batch = n * (int64_t)in; g.ldc = in;
+      g.M = (int)n; g.N = in; g.K = out;
+      g.aux = w.H[l]; g.aux_batch = n * (int64_t)in; g.ldaux = in;
+      if (launch_bgemm<false, true, kEpiDtanh>(s, g, C, "k_bgemm<dH>")) return 1;
+    }
+  }
+  return 0;
+}
+
+}  // extern "C"

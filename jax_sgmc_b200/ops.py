@@ -259,6 +259,44 @@ def glm_potential_grad_per_chain(spec, theta, X, y, idx, observation_count, pote
   return workspace
 
 
+def mlp_spec(sizes, w_off, b_off, prior="flat", prior_off=0, prior_size=0, prior_scale=1.0,
+             temperature=1.0) -> _lib.MlpSpec:
+  """``sgmc_mlp_spec``: dense layers sizes[l] -> sizes[l+1], tanh between them."""
+  L = len(sizes) - 1
+  assert 1 <= L <= _lib.MLP_MAX_LAYERS and len(w_off) == L and len(b_off) == L
+  spec = _lib.MlpSpec()
+  spec.n_layers = L
+  for i, v in enumerate(sizes):
+    spec.sizes[i] = int(v)
+  for l in range(L):
+    spec.w_off[l], spec.b_off[l] = int(w_off[l]), int(b_off[l])
+  spec.activation = 0
+  spec.prior, spec.prior_off, spec.prior_size = PRIOR[prior], int(prior_off), int(prior_size)
+  spec.prior_scale, spec.temperature = float(prior_scale), float(temperature)
+  return spec
+
+
+def mlp_workspace(spec, n_chains: int, batch_size: int) -> DeviceArray:
+  nbytes = _lib.load().sgmc_mlp_workspace_bytes(C.byref(spec), n_chains, batch_size)
+  return DeviceArray((int(nbytes),), np.uint8)
+
+
+def mlp_potential_grad(spec, theta, X, y, idx, observation_count, potential, variance=None,
+                       grad=None, ell=None, mask=None, workspace=None, batch_size=None,
+                       stream=None):
+  """U, var(ell), dU/dtheta of the MLP classifier for all chains on one shared minibatch
+  (see sgmc_mlp_potential_grad)."""
+  C_, P = theta.shape
+  n = int(batch_size if batch_size is not None
+          else (idx.size if idx is not None else X.shape[0]))
+  if workspace is None:
+    workspace = mlp_workspace(spec, C_, n)
+  _lib.call("sgmc_mlp_potential_grad", _s(stream), C.byref(spec), vp(theta), C_, P, vp(X),
+            vp(y), vp(idx), vp(mask), n, int(observation_count), vp(potential), vp(variance),
+            vp(grad), vp(ell), vp(workspace), workspace.nbytes)
+  return workspace
+
+
 def glm_sgld_scan_host(spec, theta, host_batches_ptr, host_batch_count, n_steps, batch_size,
                        observation_count,
                        device_slots, n_slots, potential_variance, host_results_ptr, grad,

@@ -16,7 +16,7 @@ from typing import Any, Callable, Optional
 
 import numpy as np
 
-from . import glm, ops
+from . import glm, nn, ops
 from .data import BatchRef, MiniBatchInformation
 from .device import DeviceArray
 from .tree_util import ChainTree
@@ -286,6 +286,70 @@ class _PotentialFn:
     return (U, state), g
 
 
+class _MlpPotentialFn:
+  """StochasticPotential protocol (potential.py:42-66) for the recognised dense-network
+  likelihood (``nn.MLPClassifier``): chain-batched forward + hand-derived reverse pass
+  (csrc/mlp.cu).  All chains share the minibatch."""
+
+  def __init__(self, prior, likelihood, temperature):
+    self.prior, self.likelihood, self.temperature = prior, likelihood, float(temperature)
+    self._buffers = {}
+
+  def sgld_step(self, *args, **kwargs) -> bool:
+    return False          # no fused whole-step call: the integrator runs potential, then update
+
+  def _run(self, sample: ChainTree, reference_data, mask, want_grad, want_ell,
+           grad_out=None, U_out=None, var_out=None):
+    batch, info = reference_data
+    assert isinstance(batch, BatchRef), "reference_data must come from jax_sgmc_b200.data"
+    if batch.per_chain:
+      raise NotImplementedError(
+          "the MLP potential evaluates one minibatch shared by all chains (device loader, "
+          "or a host loader with shared streams)")
+    spec = nn.resolve(self.likelihood, self.prior, sample, self.temperature)
+    C, P, n = sample.n_chains, sample.n_params, batch.n
+    N = int(info.observation_count)
+    X, y = batch.leaf(self.likelihood.x), batch.leaf(self.likelihood.y)
+    if mask is None:
+      mask = batch.mask
+    key = (C, P, n)
+    buf = self._buffers.get(key)
+    if buf is None:
+      buf = {"U": DeviceArray((C,), np.float32), "var": DeviceArray((C,), np.float32),
+             "ws": ops.mlp_workspace(spec, C, n), "ell": None}
+      self._buffers[key] = buf
+    grad = None
+    if want_grad:
+      grad = grad_out if grad_out is not None else DeviceArray((C, P), np.float32)
+    ell = None
+    if want_ell:
+      if buf["ell"] is None:
+        buf["ell"] = DeviceArray((C, n), np.float32)
+      ell = buf["ell"]
+    U_buf = U_out if U_out is not None else buf["U"]
+    var_buf = var_out if var_out is not None else buf["var"]
+    ops.mlp_potential_grad(spec, sample.flat, X, y, batch.idx, N, U_buf, var_buf, grad, ell,
+                           mask=mask, workspace=buf["ws"], batch_size=n)
+    return U_buf, var_buf, grad, ell
+
+  def __call__(self, sample: ChainTree, reference_data, state: Any = None, mask=None,
+               likelihoods: bool = False):
+    U, _, _, ell = self._run(sample, reference_data, mask, False, likelihoods)
+    if likelihoods:
+      return U, (ell, state)
+    return U, state
+
+  def value_and_grad(self, sample: ChainTree, reference_data, state: Any = None, mask=None,
+                     likelihoods: bool = False, grad_out=None, U_out=None, var_out=None):
+    U, var, grad, _ = self._run(sample, reference_data, mask, True, False, grad_out, U_out,
+                                var_out)
+    self.last_variance = var
+    g = ChainTree.like(sample, grad)
+    if likelihoods:
+      return (U, (var, state)), g
+    return (U, state), g
+
+
 def value_and_grad(potential_fn: _PotentialFn) -> Callable:
   """Stand-in for ``jax.value_and_grad(potential_fn, argnums=0, has_aux=True)``.
 
@@ -308,11 +372,15 @@ def minibatch_potential(prior, likelihood, strategy: str = "map",
   if has_state:
     raise NotImplementedError(
         "stateful likelihoods are outside the fused GLM path")
+  if isinstance(likelihood, nn.MLPClassifier):
+    if not isinstance(prior, (glm.FlatPrior, glm.GaussianPrior)):
+      raise TypeError("the MLP potential takes a FlatPrior or a GaussianPrior")
+    return _MlpPotentialFn(prior, likelihood, temperature)
   if not isinstance(likelihood, (glm.GaussianRegression, glm.LogisticRegression)):
     raise TypeError(
-        "likelihood must be a jax_sgmc_b200.glm specification (GaussianRegression, "
-        "LogisticRegression); arbitrary callables need the JAX route, see "
-        "INTEGRATION.md")
+        "likelihood must be a jax_sgmc_b200.glm / jax_sgmc_b200.nn specification "
+        "(GaussianRegression, LogisticRegression, MLPClassifier); arbitrary callables "
+        "need the JAX route, see INTEGRATION.md")
   if not isinstance(prior, (glm.FlatPrior, glm.GaussianPrior, glm.InvSigmaPrior)):
     raise TypeError("prior must be a jax_sgmc_b200.glm prior specification")
   return _PotentialFn(prior, likelihood, temperature, path or DEFAULT_PATH)
@@ -352,7 +420,8 @@ def full_potential(prior, likelihood, strategy: str = "map", has_state: bool = F
     """Returns ``(U f32[C] on the device, (data_state, state))``; everything is
     enqueued, nothing synchronises (the MH solvers consume U on the device)."""
     loader = getattr(full_data_map_fn, "loader", None)
-    if loader is not None and state is None and not has_state:
+    if loader is not None and state is None and not has_state and \
+        not isinstance(likelihood, nn.MLPClassifier):
       # the standard full_reference_data pass over an HBM-resident data set: all
       # batches inside one C call (same arithmetic as the loop below)
       return _full_in_one_call(sample, loader, full_data_map_fn.mb_size), (data_state, state)

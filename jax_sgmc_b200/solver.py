@@ -96,7 +96,8 @@ def sgmc(integrator) -> Tuple[Callable, Callable, Callable]:
   def init(*args, **kwargs):
     return init_integrator(*args, **kwargs)
 
-  takes_carry = "carry_ok" in getattr(update_integrator, "__code__", update).co_varnames
+  code = getattr(update_integrator, "__code__", None)
+  takes_carry = code is not None and "carry_ok" in code.co_varnames[:code.co_argcount]
 
   def update(state, schedule):
     # sgmc never touches the sample between updates: the Langevin integrator may

@@ -117,6 +117,91 @@ class Logistic:
 
 
 @dataclass
+class MLPClassifier:
+  """Bayesian MLP classifier (BASELINE.json configs[2]: 784-512-512-10, tanh).
+
+  The likelihood a jax-sgmc user writes for it (examples/cifar.md:196-204 with a
+  dense network instead of MobileNet): ``logits = apply(sample, x)``,
+  ``ell = -softmax_cross_entropy_with_integer_labels(logits, label)``; the
+  reference evaluates it per observation under ``vmap`` (potential.py:141-156)
+  and differentiates it with ``jax.value_and_grad`` (integrator.py:593, :166).
+  Restated: ``h_0 = x``, ``a_l = h_{l-1} W_l + b_l``, ``h_l = tanh(a_l)`` for all
+  but the last layer, ``logits = a_L``;
+  ``ell = logits[label] - logsumexp(logits)`` with the max-shifted logsumexp of
+  ``jax.nn.log_softmax``.  The gradient is the hand-derived reverse pass (what
+  reverse-mode AD emits): ``d logits = cot * (onehot - softmax)``,
+  ``dW_l = h_{l-1}^T dA_l``, ``db_l = sum_i dA_l``, ``dH_{l-1} = dA_l W_l^T``,
+  ``dA_{l-1} = dH_{l-1} * (1 - h_{l-1}^2)``.
+
+  ``sizes``: layer widths (input, hidden..., classes); ``w_off`` / ``b_off``:
+  offsets of ``W_l`` (row-major ``[in, out]``) and ``b_l`` in the raveled sample.
+  Labels are stored as f32 class indices (the data loaders hold f32 arrays).
+  """
+  sizes: Sequence[int]
+  w_off: Sequence[int]
+  b_off: Sequence[int]
+
+  def _params(self, theta, l):
+    i, o = self.sizes[l], self.sizes[l + 1]
+    W = theta[:, self.w_off[l]:self.w_off[l] + i * o].reshape(-1, i, o)
+    b = theta[:, self.b_off[l]:self.b_off[l] + o]
+    return W, b
+
+  def loglik(self, theta, X, y):
+    C, L = theta.shape[0], len(self.sizes) - 1
+    h = np.broadcast_to(np.asarray(X, F32)[None], (C,) + X.shape)
+    hs = [h]
+    for l in range(L):
+      W, b = self._params(theta, l)
+      a = (np.matmul(h, W).astype(F32) + b[:, None, :]).astype(F32)
+      h = np.tanh(a).astype(F32) if l < L - 1 else a
+      hs.append(h)
+    logits = hs[-1]
+    m = logits.max(axis=2, keepdims=True)
+    sh = (logits - m).astype(F32)
+    ex = np.exp(sh).astype(F32)
+    se = np.sum(ex, axis=2, keepdims=True, dtype=F32)
+    lsm = (sh - np.log(se).astype(F32)).astype(F32)            # log_softmax
+    lab = np.asarray(y).astype(np.int64)
+    ell = np.take_along_axis(lsm, np.broadcast_to(lab[None, :, None], (C, len(lab), 1)),
+                             axis=2)[..., 0].astype(F32)
+    soft = (ex / se).astype(F32)
+    return ell, (hs, soft, lab)
+
+  def vjp(self, theta, X, y, aux, cot):
+    hs, soft, lab = aux
+    C, L = theta.shape[0], len(self.sizes) - 1
+    g = np.zeros_like(theta)
+    onehot = np.zeros(soft.shape[1:], F32)
+    onehot[np.arange(len(lab)), lab] = 1
+    dA = ((onehot[None] - soft).astype(F32) * cot[..., None]).astype(F32)
+    for l in range(L - 1, -1, -1):
+      i, o = self.sizes[l], self.sizes[l + 1]
+      W, _ = self._params(theta, l)
+      dW = np.matmul(np.swapaxes(hs[l], 1, 2), dA).astype(F32)          # [C, in, out]
+      g[:, self.w_off[l]:self.w_off[l] + i * o] = dW.reshape(C, -1)
+      g[:, self.b_off[l]:self.b_off[l] + o] = np.sum(dA, axis=1, dtype=F32)
+      if l > 0:
+        dH = np.matmul(dA, np.swapaxes(W, 1, 2)).astype(F32)
+        dA = (dH * (F32(1.0) - (hs[l] * hs[l]).astype(F32)).astype(F32)).astype(F32)
+    return g
+
+
+def mlp_layout(sizes, order="haiku"):
+  """Offsets of (W_l, b_l) in the raveled sample for the pytree
+  ``{"layer_0": {"b": [out], "w": [in, out]}, ...}`` (tree_flatten visits dict keys
+  sorted: b before w inside a layer; layers by name)."""
+  w_off, b_off, off = [], [], 0
+  for l in range(len(sizes) - 1):
+    i, o = sizes[l], sizes[l + 1]
+    b_off.append(off)
+    off += o
+    w_off.append(off)
+    off += i * o
+  return w_off, b_off, off
+
+
+@dataclass
 class Prior:
   """Log-priors used by the reference examples.
 
