@@ -293,15 +293,53 @@ def bench_resgld(args, ctl, nccl, stream, path):
           "swaps_in_last_step": swaps}
 
 
-def bench_row_sharded(args, ctl, nccl, stream):
-  """C5 collective: the minibatch ROWS of the GLM potential sharded over the ranks --
-  every rank evaluates its n / R rows for all chains, then one all-reduce of
-  [grad | sum ell | sum ell^2] (sgmc_glm_potential_grad_row_sharded).  Reports the
-  all-reduce's bus bandwidth."""
+def bench_row_sharded(args, ctl, nccl, stream, path):
+  """C5's collective on the C2 model: the minibatch ROWS of the GLM potential sharded over
+  the ranks -- every rank evaluates n / R rows for all chains, then ncclAllReduce of the
+  gradient (16.8 MB) and three scalars per chain (sgmc_glm_potential_grad_row_sharded).
+  Reports the time of the sharded evaluation and the all-reduce's bus bandwidth
+  (2 (R-1) / R x bytes / time, the nccl-tests convention)."""
   from jax_sgmc_b200 import ops
-  if not hasattr(ops, "glm_potential_grad_row_sharded") or ctl.world < 2:
+  from jax_sgmc_b200.device import DeviceArray as DA, Event
+  world, rank = ctl.world, ctl.rank
+  C, d, n, N = args.chains, args.features, args.batch, 100_000
+  if world < 2 or n % world or N % world or (n // world) % 8:
     return None
-  return ops.bench_row_sharded(args, ctl, nccl, stream)
+  X, y, _ = ops.synth_logistic_data(0, N, d)
+  spec = ops.glm_spec("logistic", d, 0, prior="gaussian", prior_off=0, prior_size=d,
+                      prior_scale=10.0, x_absmax=ops.absmax(X))
+  theta = DA.from_numpy((np.random.default_rng(0).standard_normal((C, d)) * 0.1).astype(np.float32))
+  idx = DA.from_numpy(np.random.default_rng(1).integers(0, N, n).astype(np.int32))
+  U, var, g = DA((C,), np.float32), DA((C,), np.float32), DA((C, d), np.float32)
+  comm = nccl._comm.value
+  ws, scratch = ops.glm_potential_grad_row_sharded(spec, theta, X, y, idx, N, U, var, g, n, rank,
+                                                   world, comm, path=path)
+  e0, e1 = Event(), Event()
+  K = 50
+
+  def timed(fn):
+    for _ in range(3):
+      fn()
+    stream.sync()
+    ctl.barrier()
+    e0.record(stream)
+    for _ in range(K):
+      fn()
+    e1.record(stream)
+    e1.sync()
+    return ctl.max(e0.elapsed_ms(e1)) / K
+
+  ms_all = timed(lambda: ops.glm_potential_grad_row_sharded(
+      spec, theta, X, y, idx, N, U, var, g, n, rank, world, comm, workspace=ws, scratch=scratch,
+      path=path))
+  ms_ar = timed(lambda: nccl.allreduce_sum(g, g))
+  nbytes = C * d * 4
+  return {"workload": "C2 model, minibatch rows sharded over the ranks, gradient all-reduce "
+                      "(the collective of configs[4])", "n_gpus": world, "rows_per_rank": n // world,
+          "us_per_evaluation": ms_all * 1e3, "allreduce_bytes": nbytes,
+          "allreduce_us": ms_ar * 1e3,
+          "allreduce_busbw_gbs": 2 * (world - 1) / world * nbytes / (ms_ar * 1e-3) / 1e9,
+          "potential_path": path}
 
 
 def run_b200(args):
@@ -511,7 +549,7 @@ def run_b200(args):
   resgld = None
   if not args.no_resgld:
     resgld = bench_resgld(args, ctl, nccl, stream, path)
-  row_sharded = bench_row_sharded(args, ctl, nccl, stream)
+  row_sharded = bench_row_sharded(args, ctl, nccl, stream, path)
 
   cpu_base = None
   if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -105,6 +105,10 @@ PROTOTYPES = {
                                 _i64, _i64, _i64, _vp, _int, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _f32,
                                 _f32, _vp, _sz, _int, _int, _vp, _int, _int, _vp, _vp, _vp, _i64,
                                 C.POINTER(_i64)],
+    "sgmc_glm_potential_grad_row_sharded": [_vp, C.POINTER(GlmSpec), _vp, _i64, _i64, _vp, _vp,
+                                            _vp, _i64, _i64, _vp, _vp, _vp, _vp, _sz, _int, _vp,
+                                            _int, _int, _vp],
+    "sgmc_glm_row_shard_finalize": [_vp, _vp, _i64, _vp, _vp, _i64],
     "sgmc_mlp_potential_grad": [_vp, C.POINTER(MlpSpec), _vp, _i64, _i64, _vp, _vp, _vp, _vp,
                                 _i64, _i64, _vp, _vp, _vp, _vp, _vp, _sz],
     "sgmc_host_gather_batches": [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _int],

@@ -405,6 +405,103 @@ int sgmc_glm_full_potential(void* stream, const sgmc_glm_spec* spec, const float
   return post_launch("k_full_finish");
 }
 
+// ---- minibatch rows sharded over ranks (BASELINE.json configs[4], north star (3)) -------
+// Rank r evaluates rows [r n/R, (r+1) n/R) of the shared minibatch for ALL chains; the
+// partial gradients and likelihood sums are all-reduced over NVLink.  The split is exact:
+// with N_r = N / R the local cotangent (-N_r / n_r) / T equals the global one, rank 0
+// carries the prior and the other ranks a flat one, so sum_r U_r = U and sum_r g_r = g.
+// var(ell) is rebuilt from e1 = sum ell and e2 = sum ell^2 (accumulated around the local
+// mean): var = (E2 - E1^2 / n) / n.
+__global__ void __launch_bounds__(256) k_row_shard_stats(const float* __restrict__ ell, int n_r,
+                                                         const float* __restrict__ U_r,
+                                                         float* __restrict__ extras) {
+  pdl_launch_dependents();
+  pdl_wait();
+  __shared__ float red[256];
+  const int64_t c = blockIdx.x;
+  const float* row = ell + c * n_r;
+  float s = 0.f;
+  for (int i = threadIdx.x; i < n_r; i += 256) s += row[i];
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int w = 128; w > 0; w >>= 1) {
+    if ((int)threadIdx.x < w) red[threadIdx.x] += red[threadIdx.x + w];
+    __syncthreads();
+  }
+  const float e1 = red[0];
+  const float mean = e1 / (float)n_r;
+  __syncthreads();
+  float q = 0.f;
+  for (int i = threadIdx.x; i < n_r; i += 256) {
+    const float dlt = row[i] - mean;
+    q = fmaf(dlt, dlt, q);
+  }
+  red[threadIdx.x] = q;
+  __syncthreads();
+  for (int w = 128; w > 0; w >>= 1) {
+    if ((int)threadIdx.x < w) red[threadIdx.x] += red[threadIdx.x + w];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    extras[c * 3 + 0] = U_r[c];
+    extras[c * 3 + 1] = e1;
+    extras[c * 3 + 2] = fmaf((float)n_r * mean, mean, red[0]);
+  }
+}
+
+__global__ void k_row_shard_finalize(const float* __restrict__ extras, float n,
+                                     float* __restrict__ potential, float* __restrict__ variance,
+                                     int64_t C) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float U = extras[c * 3], e1 = extras[c * 3 + 1], e2 = extras[c * 3 + 2];
+  potential[c] = U;
+  if (variance) variance[c] = fmaxf(e2 - e1 * e1 / n, 0.f) / n;
+}
+
+int sgmc_glm_row_shard_finalize(void* stream, const float* extras, int64_t batch_size,
+                                float* potential, float* variance, int64_t n_chains) {
+  SGMC_REQUIRE(extras && potential && n_chains > 0 && batch_size > 0, "bad arguments");
+  launch_pdl(k_row_shard_finalize, dim3((unsigned)((n_chains + 255) / 256)), dim3(256), 0,
+             (cudaStream_t)stream, extras, (float)batch_size, potential, variance, n_chains);
+  return post_launch("k_row_shard_finalize");
+}
+
+int sgmc_glm_potential_grad_row_sharded(void* stream, const sgmc_glm_spec* spec,
+                                        const float* theta, int64_t n_chains, int64_t P,
+                                        const float* X, const float* y, const int32_t* idx,
+                                        int64_t batch_size, int64_t observation_count,
+                                        float* potential, float* variance, float* grad,
+                                        void* workspace, size_t workspace_bytes, int path,
+                                        void* nccl_comm, int rank, int n_ranks, float* scratch) {
+  SGMC_REQUIRE(spec && theta && X && y && potential && grad && scratch, "null argument");
+  SGMC_REQUIRE(n_ranks >= 1 && rank >= 0 && rank < n_ranks, "bad rank");
+  SGMC_REQUIRE(batch_size % n_ranks == 0 && observation_count % n_ranks == 0,
+               "batch size and observation count must be multiples of the rank count");
+  const int64_t C = n_chains, n_r = batch_size / n_ranks, row0 = (int64_t)rank * n_r;
+  float* ell = scratch;                       // f32[C][n_r]
+  float* extras = scratch + (size_t)C * n_r;  // f32[C][3]: U_r, sum ell, sum ell^2
+  sgmc_glm_spec local = *spec;
+  if (rank != 0) { local.prior = kPriorFlat; local.prior_size = 0; }
+  FusedSgld none{};
+  if (int e = glm_dispatch(stream, &local, theta, C, P, idx ? X : X + row0 * spec->d,
+                           idx ? y : y + row0, idx ? idx + row0 : nullptr, nullptr, n_r,
+                           observation_count / n_ranks, extras + (size_t)3 * C, nullptr, grad, ell,
+                           workspace, workspace_bytes, path, none))
+    return e;
+  // (extras + 3C is a C-float slot behind the table: the local potential lands there first)
+  launch_pdl(k_row_shard_stats, dim3((unsigned)C), dim3(256), 0, (cudaStream_t)stream,
+             (const float*)ell, (int)n_r, (const float*)(extras + (size_t)3 * C), extras);
+  if (post_launch("k_row_shard_stats")) return 1;
+  if (nccl_comm == nullptr) return 0;         // partials only (single-process emulation)
+  if (int e = sgmc_nccl_allreduce_sum_f32(nccl_comm, stream, grad, grad, (size_t)C * P)) return e;
+  if (int e = sgmc_nccl_allreduce_sum_f32(nccl_comm, stream, extras, extras, (size_t)3 * C))
+    return e;
+  return sgmc_glm_row_shard_finalize(stream, extras, batch_size, potential, variance, C);
+}
+
 int sgmc_glm_prepare_minibatch(void* stream, const sgmc_glm_spec* spec, int64_t n_chains,
                                const float* X, const int32_t* idx, int64_t batch_size,
                                void* workspace, size_t workspace_bytes, int path, int slot) {

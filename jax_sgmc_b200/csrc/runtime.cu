@@ -4,6 +4,9 @@
 #include "common.cuh"
 
 #include <algorithm>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 #include <cstring>
 #include <thread>
 #include <vector>
@@ -191,6 +194,37 @@ int sgmc_stream_wait_event(void* stream, void* event) {
 // sgmc_glm_sgld_scan_host consumes -- per batch `rows` feature rows of d floats, then
 // all n labels -- with `n_threads` host threads (memcpy of whole rows; the staging
 // buffer is page-locked memory the H2D copies read directly).
+// One feature row -> staging.  The destination is page-locked memory only the DMA engine
+// reads, so it is written with non-temporal stores (no read-for-ownership of the
+// destination lines); the NEXT row of the gather is prefetched while this one streams
+// (rows are scattered over a multi-GB array: every row starts with a TLB + DRAM miss).
+static inline void copy_row_nt(float* dst, const float* src, const float* next, int64_t d) {
+#if defined(__SSE2__)
+  if (((reinterpret_cast<uintptr_t>(dst) | (uintptr_t)(d * 4)) & 15u) == 0) {
+    const int64_t bytes = d * 4;
+    if (next != nullptr)
+      for (int64_t o = 0; o < bytes; o += 64)
+        __builtin_prefetch(reinterpret_cast<const char*>(next) + o, 0, 0);
+    const __m128i* s = reinterpret_cast<const __m128i*>(src);
+    __m128i* t = reinterpret_cast<__m128i*>(dst);
+    const int64_t q = bytes / 16;
+    int64_t i = 0;
+    for (; i + 4 <= q; i += 4) {
+      const __m128i a = _mm_loadu_si128(s + i), b = _mm_loadu_si128(s + i + 1);
+      const __m128i c = _mm_loadu_si128(s + i + 2), e = _mm_loadu_si128(s + i + 3);
+      _mm_stream_si128(t + i, a);
+      _mm_stream_si128(t + i + 1, b);
+      _mm_stream_si128(t + i + 2, c);
+      _mm_stream_si128(t + i + 3, e);
+    }
+    for (; i < q; ++i) _mm_stream_si128(t + i, _mm_loadu_si128(s + i));
+    return;
+  }
+#endif
+  (void)next;
+  std::memcpy(dst, src, (size_t)d * sizeof(float));
+}
+
 int sgmc_host_gather_batches(float* dst, const float* X, const float* y, const int32_t* idx,
                              int64_t n_batches, int64_t n, int64_t d, int64_t row0,
                              int64_t rows, int n_threads) {
@@ -204,8 +238,16 @@ int sgmc_host_gather_batches(float* dst, const float* X, const float* y, const i
     for (int64_t it = lo; it < hi; ++it) {
       const int64_t b = it / rows, r = it - b * rows;
       const int64_t src = (int64_t)idx[b * n + row0 + r];
-      std::memcpy(dst + b * stride + r * d, X + src * d, (size_t)d * sizeof(float));
+      const float* next = nullptr;
+      if (it + 1 < hi) {
+        const int64_t b1 = (it + 1) / rows, r1 = it + 1 - b1 * rows;
+        next = X + (int64_t)idx[b1 * n + row0 + r1] * d;
+      }
+      copy_row_nt(dst + b * stride + r * d, X + src * d, next, d);
     }
+#if defined(__SSE2__)
+    _mm_sfence();
+#endif
     for (int64_t b = n_batches * t / T; b < n_batches * (t + 1) / T; ++b) {
       float* lab = dst + b * stride + rows * d;
       for (int64_t i = 0; i < n; ++i) lab[i] = y[idx[b * n + i]];

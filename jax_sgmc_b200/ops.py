@@ -259,6 +259,32 @@ def glm_potential_grad_per_chain(spec, theta, X, y, idx, observation_count, pote
   return workspace
 
 
+def glm_potential_grad_row_sharded(spec, theta, X, y, idx, observation_count, potential,
+                                   variance, grad, batch_size, rank, n_ranks, nccl_comm=None,
+                                   workspace=None, scratch=None, path=0, stream=None):
+  """The minibatch's rows sharded over ``n_ranks`` ranks + all-reduce of the gradient
+  (see sgmc_glm_potential_grad_row_sharded).  ``nccl_comm``: the raw handle of
+  ``dist.NcclCommunicator`` (None: partials only).  Returns ``(workspace, scratch)``."""
+  C_, P = theta.shape
+  n = int(batch_size)
+  n_r = n // n_ranks
+  if workspace is None:
+    workspace = glm_workspace(C_, n_r, spec.d, path)
+  if scratch is None:
+    scratch = DeviceArray((C_ * (n_r + 4),), np.float32)
+  _lib.call("sgmc_glm_potential_grad_row_sharded", _s(stream), C.byref(spec), vp(theta), C_, P,
+            vp(X), vp(y), vp(idx), n, int(observation_count), vp(potential), vp(variance),
+            vp(grad), vp(workspace), workspace.nbytes, PATH[path],
+            None if nccl_comm is None else C.c_void_p(nccl_comm), int(rank), int(n_ranks),
+            vp(scratch))
+  return workspace, scratch
+
+
+def glm_row_shard_finalize(extras, batch_size, potential, variance, stream=None):
+  _lib.call("sgmc_glm_row_shard_finalize", _s(stream), vp(extras), int(batch_size),
+            vp(potential), vp(variance), potential.size)
+
+
 def mlp_spec(sizes, w_off, b_off, prior="flat", prior_off=0, prior_size=0, prior_scale=1.0,
              temperature=1.0) -> _lib.MlpSpec:
   """``sgmc_mlp_spec``: dense layers sizes[l] -> sizes[l+1], tanh between them."""

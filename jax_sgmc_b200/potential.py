@@ -233,17 +233,21 @@ class _PotentialFn:
       ops.host_gather_batches(buf["ring_addr"] + half * CH * host_stride * 4, X, y, idx_rows,
                               rank * rows, rows, threads)
 
+    def produce(count, half):
+      # index draw (the chain's NumPy PCG64 pipeline) + row gather of one chunk; runs in a
+      # worker thread beside the device's work on the previous chunk
+      gather(source["draw"](count), half)
+
     ss = np.ascontiguousarray(step_sizes, np.float32)
     kp = None if keep is None else np.ascontiguousarray(keep, np.uint8)
     done, half, last_k = 0, 0, 0
-    gather(source["draw"](min(CH, K)), 0)
+    produce(min(CH, K), 0)
     trace = []
     while done < K:
       k = min(CH, K - done)
       worker = None
       if done + k < K:
-        nxt = source["draw"](min(CH, K - done - k))
-        worker = threading.Thread(target=gather, args=(nxt, 1 - half))
+        worker = threading.Thread(target=produce, args=(min(CH, K - done - k), 1 - half))
         worker.start()
       kept = ops.glm_sgld_scan_host(
           spec, sample.flat, buf["ring_addr"] + half * CH * host_stride * 4, k, k, n, N,
