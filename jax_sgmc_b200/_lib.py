@@ -128,6 +128,8 @@ PROTOTYPES = {
     "sgmc_mh_decide": [_vp, _int, _vp, _vp, _vp, _vp, _f32, _vp, _vp, _vp, _vp, _i64, _int],
     "sgmc_resgld_decide": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _f32, _f32, _vp,
                            _vp, _vp, _i64, _int],
+    "sgmc_resgld_decide_eta": [_vp, _vp, _vp, _vp, _vp, _vp, _f32, _f32, _f32, _vp,
+                               _vp, _vp, _i64, _int],
     "sgmc_swap_rows": [_vp, _vp, _vp, _vp, _i64, _i64],
     "sgmc_resgld_ladder_step": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _int,
                                 _i64, _i64, _int, _int, _vp, _vp, _int],

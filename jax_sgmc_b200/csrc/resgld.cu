@@ -89,21 +89,31 @@ using namespace sgmc;
 
 extern "C" {
 
-int sgmc_resgld_decide(void* stream, const float* U_normal, const float* U_hot,
-                       const float* var_normal, float* ssq, const float* F,
-                       int64_t step, float T_normal, float T_hot,
-                       const uint32_t* keys_in, uint32_t* keys_out,
-                       int32_t* exchange, int64_t n_systems, int prng_layout) {
+int sgmc_resgld_decide_eta(void* stream, const float* U_normal, const float* U_hot,
+                           const float* var_normal, float* ssq, const float* F,
+                           float eta, float T_normal, float T_hot,
+                           const uint32_t* keys_in, uint32_t* keys_out,
+                           int32_t* exchange, int64_t n_systems, int prng_layout) {
   SGMC_REQUIRE(keys_in != keys_out, "keys_out must not alias keys_in");
-  SGMC_REQUIRE(step >= 1, "step must be >= 1 (already incremented)");
   if (n_systems == 0) return 0;
-  const float eta = 1.0f / (float)step;                     // sa_schedule, :221
   const float temps = 1.0f / T_normal - 1.0f / T_hot;       // :279
   k_resgld_decide<<<(unsigned)((n_systems + 127) / 128), 128, 0,
                     (cudaStream_t)stream>>>(
       U_normal, U_hot, var_normal, ssq, F, eta, temps, keys_in, keys_out,
       exchange, n_systems, prng_layout);
   return post_launch("sgmc_resgld_decide");
+}
+
+int sgmc_resgld_decide(void* stream, const float* U_normal, const float* U_hot,
+                       const float* var_normal, float* ssq, const float* F,
+                       int64_t step, float T_normal, float T_hot,
+                       const uint32_t* keys_in, uint32_t* keys_out,
+                       int32_t* exchange, int64_t n_systems, int prng_layout) {
+  SGMC_REQUIRE(step >= 1, "step must be >= 1 (already incremented)");
+  // the reference's default sa_schedule, 1 / n (solver.py:221)
+  return sgmc_resgld_decide_eta(stream, U_normal, U_hot, var_normal, ssq, F,
+                                1.0f / (float)step, T_normal, T_hot, keys_in, keys_out,
+                                exchange, n_systems, prng_layout);
 }
 
 int sgmc_mh_decide(void* stream, int mode, float* U_state, const float* U_new,
@@ -124,12 +134,15 @@ int sgmc_swap_rows(void* stream, void* a, void* b, const int32_t* exchange,
                    int64_t n_rows, int64_t row_bytes) {
   SGMC_REQUIRE(row_bytes % 4 == 0, "row_bytes must be a multiple of 4");
   if (n_rows == 0 || row_bytes == 0) return 0;
-  SGMC_REQUIRE(n_rows <= 65535, "too many rows for one launch");
   const int64_t words = row_bytes / 4;
   unsigned gx = (unsigned)((words + 255) / 256);
   if (gx > 64) gx = 64;
-  k_swap_rows<<<dim3(gx, (unsigned)n_rows), 256, 0, (cudaStream_t)stream>>>(
-      (uint32_t*)a, (uint32_t*)b, exchange, n_rows, words);
+  // gridDim.y holds at most 65535 rows: larger row counts go in slices
+  for (int64_t r0 = 0; r0 < n_rows; r0 += 65535) {
+    const int64_t nr = n_rows - r0 < 65535 ? n_rows - r0 : 65535;
+    k_swap_rows<<<dim3(gx, (unsigned)nr), 256, 0, (cudaStream_t)stream>>>(
+        (uint32_t*)a + r0 * words, (uint32_t*)b + r0 * words, exchange + r0, nr, words);
+  }
   return post_launch("sgmc_swap_rows");
 }
 

@@ -445,11 +445,19 @@ def mh_decide(mode, U_state, U_new, e0, e1, temperature, keys_in, keys_out, reje
 # ---- reSGLD ------------------------------------------------------------------------
 
 def resgld_decide(U_n, U_h, var_n, ssq, F, step, T_normal, T_hot, keys_in,
-                  keys_out, exchange, layout=0, stream=None):
-  _lib.call("sgmc_resgld_decide", _s(stream), vp(U_n), vp(U_h), vp(var_n),
-            vp(ssq), vp(F), int(step), float(T_normal), float(T_hot),
-            vp(keys_in), vp(keys_out), vp(exchange), exchange.size,
-            _layout(layout))
+                  keys_out, exchange, layout=0, stream=None, eta=None):
+  """``eta`` = sa_schedule(step) when the caller supplies its own schedule
+  (solver.py:274-276); None = the reference default 1 / step."""
+  if eta is None:
+    _lib.call("sgmc_resgld_decide", _s(stream), vp(U_n), vp(U_h), vp(var_n),
+              vp(ssq), vp(F), int(step), float(T_normal), float(T_hot),
+              vp(keys_in), vp(keys_out), vp(exchange), exchange.size,
+              _layout(layout))
+  else:
+    _lib.call("sgmc_resgld_decide_eta", _s(stream), vp(U_n), vp(U_h), vp(var_n),
+              vp(ssq), vp(F), float(eta), float(T_normal), float(T_hot),
+              vp(keys_in), vp(keys_out), vp(exchange), exchange.size,
+              _layout(layout))
 
 
 def resgld_ladder_step(gathered, holder, ssq, F, temps, keys_in, keys_out, exchange,

@@ -23,8 +23,17 @@ scheduler_state = namedtuple("scheduler_state",
 static_information = namedtuple("static_information", ["samples_collected"])
 
 
-# specific schedulers whose state depends on solver statistics (no precomputation)
-_DYNAMIC = []
+def _keep_state(state, iteration, **kw):
+  """update() of the schedulers whose state never changes.  Carrying THIS function is the
+  opt-in tag that lets ``precompute`` evaluate a scheduler ahead of the run; a scheduler
+  with any other ``update`` (user-defined, ``adaptive_step_size``) is driven step by
+  step, as in the reference."""
+  del iteration, kw
+  return state
+
+
+def is_static(sched: specific_scheduler) -> bool:
+  return sched.update is _keep_state
 
 
 def init_scheduler(step_size: specific_scheduler = None,
@@ -43,7 +52,7 @@ def init_scheduler(step_size: specific_scheduler = None,
     burn_in = initial_burn_in(n=0)
   if thinning is None:
     thinning = specific_scheduler(lambda iterations: (None, iterations),
-                                  lambda *a, **k: None, lambda *a, **k: True)
+                                  _keep_state, lambda *a, **k: True)
 
   def init_fn(iterations: int, **kw):
     thinning_state, total = thinning.init(iterations, **kw.get("thinning", {}))
@@ -85,10 +94,12 @@ def init_scheduler(step_size: specific_scheduler = None,
 
   def precompute(state: scheduler_state, iterations: int):
     """(step sizes f32[K], temperatures f32[K], keep bool[K]) of the next K
-    iterations when every specific scheduler is static -- what lets solver.mcmc
-    hand the whole scan to native code -- else None."""
+    iterations when every specific scheduler is tagged static (the built-in polynomial /
+    constant / burn-in / thinning schedules) -- what lets solver.mcmc hand the whole
+    scan to native code -- else None: the step loop then calls update() / get() per
+    iteration."""
     parts = (step_size, temperature, burn_in, thinning)
-    if any(p is dyn for p in parts for dyn in _DYNAMIC):
+    if not all(is_static(p) for p in parts):
       return None
     it0 = state.state[0]
     its = range(it0, it0 + iterations)
@@ -105,7 +116,7 @@ def init_scheduler(step_size: specific_scheduler = None,
 def constant_temperature(tau: float = 1.0) -> specific_scheduler:
   """scheduler.py:245-276."""
   return specific_scheduler(lambda iterations, tau=tau: tau,
-                            lambda state, iteration, **kw: state,
+                            _keep_state,
                             lambda state, iteration, **kw: state)
 
 
@@ -121,7 +132,7 @@ def polynomial_step_size(a: float = 1.0, b: float = 1.0, gamma: float = 0.33
     unscaled = np.power((F32(b) + n).astype(F32), F32(-gamma)).astype(F32)
     return (F32(a) * unscaled).astype(F32)
 
-  return specific_scheduler(init_fn, lambda state, iteration, **kw: state,
+  return specific_scheduler(init_fn, _keep_state,
                             lambda state, iteration, **kw: state[iteration])
 
 
@@ -146,7 +157,7 @@ def polynomial_step_size_first_last(first: float = 1.0, last: float = 1.0,
     a, b = find_ab(iterations, gamma, first, last)
     return polynomial_step_size(a=a, b=b, gamma=gamma).init(iterations)
 
-  return specific_scheduler(init_fn, lambda state, iteration, **kw: state,
+  return specific_scheduler(init_fn, _keep_state,
                             lambda state, iteration, **kw: state[iteration])
 
 
@@ -186,16 +197,14 @@ def adaptive_step_size(burn_in=0, initial_step_size=0.05, stabilization_constant
     del iteration, kw
     return F32(np.exp(state[1]))
 
-  sched = specific_scheduler(init_fn, update_fn, get_fn)
-  _DYNAMIC.append(sched)
-  return sched
+  return specific_scheduler(init_fn, update_fn, get_fn)
 
 
 def initial_burn_in(n: int = 0) -> specific_scheduler:
   """scheduler.py:567-596: discard the first n steps (returns 0.0 / 1.0)."""
   return specific_scheduler(
       lambda iterations, n=n: (n, iterations - n),
-      lambda state, iteration, **kw: state,
+      _keep_state,
       lambda state, iteration, **kw: F32(1.0) if state <= iteration else F32(0.0))
 
 
@@ -233,5 +242,5 @@ def random_thinning(step_size_schedule: specific_scheduler,
     lookup[accepted] = True
     return lookup, selections
 
-  return specific_scheduler(init_fn, lambda state, iteration, **kw: state,
+  return specific_scheduler(init_fn, _keep_state,
                             lambda state, iteration, **kw: bool(state[iteration]))

@@ -80,11 +80,25 @@ def _native_scan(solver_update, scheduler_get, scheduler_state, iterations, stat
     return False
   eps, tau, keep = arrays
   collect = saving_state.capacity > 0
-  out = scan(state, eps, tau, keep, saving_state.variables if collect else None,
-             saving_state.scalars if collect else None, saving_state.count)
-  if out is None:
-    return False
-  _, saving_state.count = out
+  # the progress bar of scheduler.update_fn (one line every `every` iterations): the scan
+  # is cut at those iterations, otherwise it is one native call
+  pb = scheduler_state.progress_bar_state
+  every = pb["every"] if pb is not None and pb["enabled"] else iterations
+  it0 = scheduler_state.state[0]
+  done = 0
+  while done < iterations:
+    k = min(iterations - done, every - (it0 + done) % every)
+    if pb is not None and pb["enabled"] and (it0 + done) % every == 0:
+      print(f"[Step {it0 + done}/{pb['iterations']}]"
+            f"({100 * (it0 + done) // pb['iterations']:.0f}%)", flush=True)
+    out = scan(state, eps[done:done + k], tau[done:done + k], keep[done:done + k],
+               saving_state.variables if collect else None,
+               saving_state.scalars if collect else None, saving_state.count)
+    if out is None:
+      assert done == 0, "the native scan refused a later chunk of a run it had accepted"
+      return False
+    _, saving_state.count = out
+    done += k
   saving_state.negate = True          # langevin.get_fn reports likelihood = -potential
   return True
 
@@ -142,10 +156,16 @@ def _swap_langevin(a: LangevinState, b: LangevinState, exchange: DeviceArray):
     ops.swap_rows(a.adapt_state.v.flat, b.adapt_state.v.flat, exchange)
 
 
-def parallel_tempering(integrator, sa_schedule: Callable = lambda n: 1 / n
+def _default_sa_schedule(n):
+  return 1 / n
+
+
+def parallel_tempering(integrator, sa_schedule: Callable = _default_sa_schedule
                        ) -> Tuple[Callable, Callable, Callable]:
-  """solver.py:220-299 (reSGLD, two temperatures per system)."""
-  del sa_schedule          # 1/n is fused in the decision kernel (solver.py:221)
+  """solver.py:220-299 (reSGLD, two temperatures per system).  The default
+  ``sa_schedule`` (1 / n, solver.py:221) is evaluated inside the decision kernel; any
+  other schedule is evaluated on the host per step (solver.py:274-276) and handed to
+  the kernel as ``eta``."""
   init_integrator, update_integrator, get_integrator = integrator
 
   def init(normal_sample, tempered_sample, ssq_init=0.0, key=None, F=1.0, **kwargs):
@@ -171,7 +191,9 @@ def parallel_tempering(integrator, sa_schedule: Callable = lambda n: 1 / n
                       state.normal.variance, state.ssq, state.F, state.step,
                       float(normal_schedule.temperature),
                       float(hot_schedule.temperature), state.key.current,
-                      state.key.next, state.exchange)
+                      state.key.next, state.exchange,
+                      eta=None if sa_schedule is _default_sa_schedule
+                      else float(np.float32(sa_schedule(state.step))))
     state.key.flip()
     _swap_langevin(state.normal, state.hot, state.exchange)          # :287-291
     return state, None

@@ -580,14 +580,15 @@ def parallel_tempering_init(normal_theta, hot_theta, ssq_init=0.0, keys=None,
 
 
 def resgld_swap_decision(U_n, U_h, var_n, ssq, F, step, T_n, T_h, keys,
-                         layout="original"):
+                         layout="original", sa_schedule=None):
   """Swap arithmetic of solver.py:273-291.
 
   Returns (exchange[S] bool, ssq'[S], key'[S,2], log_s, log_u).  The reference
   exchanges the chains iff ``not (log_u < log_s)`` (:287-291) -- inverted
   with respect to the paper; reproduced as is.
   """
-  eta = F32(1.0) / F32(step)                                 # sa_schedule :221
+  # sa_schedule(step) (:274), default 1 / n (:221)
+  eta = F32(1.0) / F32(step) if sa_schedule is None else F32(sa_schedule(step))
   ssq = (((F32(1.0) - eta).astype(F32) * ssq).astype(F32)
          + (eta * var_n).astype(F32)).astype(F32)            # :275-276
   temps = (F32(1.0) / F32(T_n) - F32(1.0) / F32(T_h)).astype(F32)   # :279
@@ -603,7 +604,7 @@ def resgld_swap_decision(U_n, U_h, var_n, ssq, F, step, T_n, T_h, keys,
 
 def parallel_tempering_update(state: TemperingState, grad_fn_normal,
                               grad_fn_hot, sizes, step_size, T_normal, T_hot,
-                              step_size_hot=None, layout="original"):
+                              step_size_hot=None, layout="original", sa_schedule=None):
   """solver.py:264-293: update both chains, then maybe exchange whole states."""
   step = state.step + 1                                      # :267
   eps_h = step_size if step_size_hot is None else step_size_hot
@@ -613,7 +614,7 @@ def parallel_tempering_update(state: TemperingState, grad_fn_normal,
                         layout=layout)                       # :271
   exchange, ssq, key, _, _ = resgld_swap_decision(
       normal.potential, hot.potential, normal.variance, state.ssq, state.F,
-      step, T_normal, T_hot, state.key, layout)
+      step, T_normal, T_hot, state.key, layout, sa_schedule)
 
   def pick(a, b):
     if a is None:

@@ -30,7 +30,7 @@ def _problem():
   return X, y, integ, init_n, init_h, keys
 
 
-def _oracle_run(X, y, init_n, init_h, keys):
+def _oracle_run(X, y, init_n, init_h, keys, sa_schedule=None):
   opot = osgmc.minibatch_potential(osgmc.Logistic(D, 0), osgmc.Prior("gaussian", 0, D, 3.0))
   st = osgmc.parallel_tempering_init(init_n, init_h, keys=keys)
   dk = prng.PRNGKey(0)
@@ -39,7 +39,8 @@ def _oracle_run(X, y, init_n, init_h, keys):
     dk, idx = odata.device_draw(dk, NB, N)
     Xb, yb = X[idx], y[idx]
     fn = lambda th: opot(th, (Xb, yb), N)
-    st, ex = osgmc.parallel_tempering_update(st, fn, fn, [D], EPS, 1.0, T_HOT)
+    st, ex = osgmc.parallel_tempering_update(st, fn, fn, [D], EPS, 1.0, T_HOT,
+                                             sa_schedule=sa_schedule)
     cold.append(st.normal.theta.copy())
     exch.append(ex.copy())
   return np.stack(cold), np.stack(exch), st
@@ -63,6 +64,42 @@ def test_parallel_tempering_matches_oracle(gpu):
   assert err < 1e-5, err
   assert np.array_equal(state.key.numpy(), ost.key)
   np.testing.assert_allclose(state.ssq.numpy(), ost.ssq, rtol=1e-4)
+
+
+def test_parallel_tempering_custom_sa_schedule(gpu):
+  """A user-supplied stochastic-approximation schedule (solver.py:221, :274-276) is
+  applied, not replaced by 1 / n: decisions and ssq follow the oracle run with it."""
+  from jax_sgmc_b200 import scheduler, solver
+  X, y, integ, init_n, init_h, keys = _problem()
+  sa = lambda n: 1.0 / (n + 10.0) ** 0.6
+  init, update, _ = solver.parallel_tempering(integ, sa_schedule=sa)
+  state = init([{"w": r} for r in init_n], [{"w": r} for r in init_h], key=keys)
+  exch = []
+  for _ in range(K):
+    state, _ = update(state, scheduler.schedule(EPS, 1.0, 1.0, True),
+                      scheduler.schedule(EPS, T_HOT, 1.0, True))
+    exch.append(state.exchange.numpy().astype(bool))
+  _, w_exch, ost = _oracle_run(X, y, init_n, init_h, keys, sa_schedule=sa)
+  _, d_exch, dst = _oracle_run(X, y, init_n, init_h, keys)
+  assert np.array_equal(np.stack(exch), w_exch)
+  np.testing.assert_allclose(state.ssq.numpy(), ost.ssq, rtol=1e-4)
+  assert not np.allclose(ost.ssq, dst.ssq, rtol=1e-3)       # the schedule matters
+
+
+def test_swap_rows_beyond_one_grid_dimension(gpu):
+  """More rows than gridDim.y holds (65 535): rows are exchanged in slices."""
+  from jax_sgmc_b200 import ops
+  from jax_sgmc_b200.device import DeviceArray as DA
+  rows, w = 70_001, 3
+  rng = np.random.default_rng(2)
+  a = rng.standard_normal((rows, w)).astype(np.float32)
+  b = rng.standard_normal((rows, w)).astype(np.float32)
+  ex = (rng.random(rows) < 0.5).astype(np.int32)
+  da, db = DA.from_numpy(a), DA.from_numpy(b)
+  ops.swap_rows(da, db, DA.from_numpy(ex))
+  m = ex.astype(bool)[:, None]
+  assert np.array_equal(da.numpy(), np.where(m, b, a))
+  assert np.array_equal(db.numpy(), np.where(m, a, b))
 
 
 @pytest.mark.parametrize("overlap", [False, True])

@@ -272,3 +272,32 @@ def test_loader_argument_validation():
   with pytest.raises(ValueError):
     data.random_reference_data(dl, 1, 7)
   assert dl.static_information == {"observation_count": 6}
+
+
+def test_only_tagged_static_schedulers_are_precomputed():
+  """The native scan may evaluate the schedules ahead of the run only when every specific
+  scheduler is one of the built-in static ones; a user-defined scheduler whose update()
+  evolves its state (or adaptive_step_size) must be driven step by step, as in the
+  reference (scheduler.py:214-235)."""
+  from jax_sgmc_b200 import scheduler
+  init, _, get = scheduler.init_scheduler(
+      step_size=scheduler.polynomial_step_size_first_last(first=0.05, last=0.001),
+      burn_in=scheduler.initial_burn_in(3), progress_bar=False)
+  st, _ = init(10)
+  eps, tau, keep = get.precompute(st, 10)
+  assert eps.shape == (10,) and tau.dtype == np.float32 and keep.sum() == 7
+  # a stateful user scheduler: halves the step size after every iteration
+  user = scheduler.specific_scheduler(lambda iterations: 1.0,
+                                      lambda state, iteration, **kw: state * 0.5,
+                                      lambda state, iteration, **kw: state)
+  init, nxt, get = scheduler.init_scheduler(step_size=user, progress_bar=False)
+  st, _ = init(4)
+  assert get.precompute(st, 4) is None
+  seen = []
+  for _ in range(3):
+    seen.append(float(get(st).step_size))
+    st = nxt(st)
+  assert seen == [1.0, 0.5, 0.25]
+  init, _, get = scheduler.init_scheduler(step_size=scheduler.adaptive_step_size(),
+                                          progress_bar=False)
+  assert get.precompute(init(4)[0], 4) is None
