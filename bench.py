@@ -517,13 +517,13 @@ def run_b200(args):
   pot = potential.minibatch_potential(glm.GaussianPrior(10.0), glm.LogisticRegression(),
                                       path=path)
   e2e_steps = max(args.steps, 4000)
-  sampler_fn = alias.sgld(pot, loader, cache_size=64, batch_size=n, first_step_size=eps,
+  sampler_fn = alias.sgld(pot, loader, cache_size=512, batch_size=n, first_step_size=eps,
                           last_step_size=eps / 10, burn_in=0, accepted_samples=1,
                           rms_prop=True, progress_bar=False)
   from jax_sgmc_b200.tree_util import ChainTree
   init = ChainTree.like(ChainTree.from_trees([{"w": np.zeros(d, np.float32)}]), DA.zeros((C, d)))
   chain_keys = np.stack([ops.prng_key(rank * C + c) for c in range(C)])
-  sampler_fn(init, iterations=128, keys=chain_keys)           # warm-up (buffers, maps)
+  sampler_fn(init, iterations=1024, keys=chain_keys)          # warm-up (buffers, page locking)
   init = ChainTree.like(init, DA.zeros((C, d)))
   ctl.barrier()
   t0 = time.perf_counter()
@@ -535,13 +535,16 @@ def run_b200(args):
   h2d = int(getattr(pot, "h2d_bytes_per_step", 0))
   d2h = int(getattr(pot, "d2h_bytes_per_step", 0))
   assert h2d > 0 and d2h > 0, "the e2e run did not take the host-stream scan"
+  link = getattr(pot, "host_link_mode", "staged")
+  how = ("the GPU pulls every minibatch's rows over the host link out of the page-locked, "
+         "mapped host data set by index (index rows H2D per chunk)" if link == "pull" else
+         "host gather of every minibatch from the host-resident data set, H2D of the rows "
+         "from pinned memory")
   e2e = {"value": world * C * e2e_steps / e2e_s, "unit": UNIT,
          "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
-         "seconds": e2e_s,
-         "what": "through alias.sgld(minibatch_potential, StreamingNumpyDataLoader): host "
-                 "gather of every minibatch from the host-resident data set, H2D of the rows "
-                 "from pinned memory" + (f" (1/{world} per rank + NCCL all-gather)" if world > 1
-                                         else "") +
+         "seconds": e2e_s, "host_link": link,
+         "what": "through alias.sgld(minibatch_potential, StreamingNumpyDataLoader): " + how +
+                 (f" (1/{world} per rank + NCCL all-gather)" if world > 1 else "") +
                  ", (U, var) of every chain D2H every step, kept sample downloaded; wall "
                  "clock around the whole run_fn call"}
   del loader, hX, hy

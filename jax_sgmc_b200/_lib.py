@@ -105,12 +105,19 @@ PROTOTYPES = {
                                 _i64, _i64, _i64, _vp, _int, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _f32,
                                 _f32, _vp, _sz, _int, _int, _vp, _int, _int, _vp, _vp, _vp, _i64,
                                 C.POINTER(_i64)],
+    "sgmc_glm_sgld_scan_pull": [_vp, _vp, C.POINTER(GlmSpec), _vp, _vp, _i64, _i64, _vp, _vp,
+                                _vp, _int, _i64, _i64, _i64, _vp, _int, _vp, _vp, _vp, _vp, _vp,
+                                _vp, _f32, _f32, _f32, _vp, _sz, _int, _int, _vp, _int, _int,
+                                _vp, _vp, _vp, _i64, C.POINTER(_i64)],
     "sgmc_glm_potential_grad_row_sharded": [_vp, C.POINTER(GlmSpec), _vp, _i64, _i64, _vp, _vp,
                                             _vp, _i64, _i64, _vp, _vp, _vp, _vp, _sz, _int, _vp,
                                             _int, _int, _vp],
     "sgmc_glm_row_shard_finalize": [_vp, _vp, _i64, _vp, _vp, _i64],
     "sgmc_mlp_potential_grad": [_vp, C.POINTER(MlpSpec), _vp, _i64, _i64, _vp, _vp, _vp, _vp,
                                 _i64, _i64, _vp, _vp, _vp, _vp, _vp, _sz],
+    "sgmc_host_register": [_vp, _sz, C.POINTER(_vp)],
+    "sgmc_host_unregister": [_vp],
+    "sgmc_pull_rows": [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _vp, _vp, _int],
     "sgmc_host_gather_batches": [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _int],
     "sgmc_glm_sgld_scan_device": [_vp, C.POINTER(GlmSpec), _vp, _vp, _i64, _i64, _vp, _vp, _i64,
                                   _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,

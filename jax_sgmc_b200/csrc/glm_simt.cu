@@ -579,33 +579,50 @@ int sgmc_glm_sgld_step(void* stream, const sgmc_glm_spec* spec, float* theta, fl
                           step_size, temperature, temp_per_chain, prng_layout);
 }
 
-// K Langevin steps over minibatches that live in (pinned) HOST memory: the inner
-// loop of solver.mcmc (solver.py:152-160) with the reference's host data cache
-// (data/core.py:664-791) in native code.  Step k reads host batch k mod
-// host_batch_count = host_batches + that * stride floats, laid out [n][d] rows
-// followed by [n] labels.  A ring of n_slots device
-// buffers is filled by the copy stream n_slots - 1 batches ahead of the sampling
-// stream (events order reuse); every step's (U, var) rows are read back to
-// host_results[k] on the copy stream.  Nothing synchronises: the caller waits on
-// the two streams when it needs the results.
-int sgmc_glm_sgld_scan_host(void* stream, void* copy_stream, const sgmc_glm_spec* spec,
-                            float* theta, float* v, int64_t n_chains, int64_t P,
-                            const float* host_batches, int64_t host_batch_count,
-                            int64_t n_steps, int64_t batch_size,
-                            int64_t observation_count, float* device_slots, int n_slots,
-                            float* potential_variance, float* host_results, float* grad,
-                            uint32_t* keys_a, uint32_t* keys_b, const float* step_sizes,
-                            float temperature, float alpha, float lmbd, void* workspace,
-                            size_t workspace_bytes, int path, int prng_layout,
-                            void* nccl_comm, int rank, int n_ranks, const uint8_t* keep,
-                            float* samples_out, float* scalars_out, int64_t capacity,
-                            int64_t* kept) {
-  SGMC_REQUIRE(spec && theta && host_batches && device_slots && potential_variance && grad &&
+// K Langevin steps over minibatches that live in HOST memory: the inner loop of
+// solver.mcmc (solver.py:152-160) with the reference's host data cache
+// (data/core.py:664-791) in native code.  Two sources:
+//   staged  (sgmc_glm_sgld_scan_host): step k reads host batch k mod host_batch_count =
+//           host_batches + that * stride floats of page-locked memory, laid out [n][d]
+//           rows followed by [n] labels (gathered by sgmc_host_gather_batches), copied by
+//           the DMA engine;
+//   pulled  (sgmc_glm_sgld_scan_pull): the data set itself is mapped (sgmc_host_register)
+//           and a kernel reads the rows idx_all[k][:] of step k over the host link
+//           (sgmc_pull_rows) -- no host gather, no staging.
+// A ring of n_slots device buffers is filled on a transfer stream n_slots - 1 batches
+// ahead of the sampling stream, the operand staging of batch k + 1 runs on the copy
+// stream while step k samples (events order reuse); every step's (U, var) rows are read
+// back to host_results[k] on a third stream.  Nothing synchronises: the caller waits on
+// the two streams it passed when it needs the results.
+namespace {
+struct HostSource {
+  const float* host_batches = nullptr;   // staged
+  int64_t host_batch_count = 0;
+  const float* X_mapped = nullptr;       // pulled
+  const float* y_mapped = nullptr;
+  const int32_t* idx_all = nullptr;      // device int32[n_steps][n]
+  int pull_ctas = 0;
+};
+
+int scan_host_impl(void* stream, void* copy_stream, const sgmc_glm_spec* spec,
+                   float* theta, float* v, int64_t n_chains, int64_t P, const HostSource& src,
+                   int64_t n_steps, int64_t batch_size,
+                   int64_t observation_count, float* device_slots, int n_slots,
+                   float* potential_variance, float* host_results, float* grad,
+                   uint32_t* keys_a, uint32_t* keys_b, const float* step_sizes,
+                   float temperature, float alpha, float lmbd, void* workspace,
+                   size_t workspace_bytes, int path, int prng_layout,
+                   void* nccl_comm, int rank, int n_ranks, const uint8_t* keep,
+                   float* samples_out, float* scalars_out, int64_t capacity,
+                   int64_t* kept) {
+  const bool pull = src.X_mapped != nullptr;
+  SGMC_REQUIRE(spec && theta && device_slots && potential_variance && grad &&
                keys_a && keys_b && step_sizes, "null argument");
+  SGMC_REQUIRE(pull ? (src.y_mapped && src.idx_all) : (src.host_batches && src.host_batch_count >= 1),
+               "no minibatch source");
   SGMC_REQUIRE(keep == nullptr || samples_out == nullptr || (scalars_out && kept),
                "sample collection needs scalars_out and kept");
-  SGMC_REQUIRE(n_slots >= 2 && n_slots <= 8 && n_steps >= 0 && host_batch_count >= 1,
-               "2..8 slots, at least one host batch");
+  SGMC_REQUIRE(n_slots >= 2 && n_slots <= 8 && n_steps >= 0, "2..8 slots");
   const bool sharded = nccl_comm != nullptr && n_ranks > 1;
   SGMC_REQUIRE(!sharded || (batch_size % n_ranks == 0 && rank >= 0 && rank < n_ranks),
                "sharded upload: batch_size must be a multiple of the rank count");
@@ -613,15 +630,20 @@ int sgmc_glm_sgld_scan_host(void* stream, void* copy_stream, const sgmc_glm_spec
   const int64_t n = batch_size, d = spec->d, C = n_chains;
   const size_t stride = (size_t)n * d + n;                 // floats per device batch
   // Every rank of a chain-sharded job consumes the SAME minibatch.  Sharded upload: a
-  // rank's host batches hold only its n / R rows (then all n labels); the rows are
+  // rank moves only its n / R rows (then all n labels) over its host link; the rows are
   // all-gathered over NVLink into the device slot, so the host link carries 1 / R of
   // the batch per rank instead of R identical copies.
   const int64_t rows_local = sharded ? n / n_ranks : n;
   const size_t host_stride = (size_t)rows_local * d + n;
   cudaStream_t rs = nullptr;                               // read-back stream (D2H runs
-  if (check_cuda(cudaStreamCreateWithFlags(&rs, cudaStreamNonBlocking), "stream"))   // beside H2D)
+  cudaStream_t hs = nullptr;                               // beside H2D); transfer stream
+  if (check_cuda(cudaStreamCreateWithFlags(&rs, cudaStreamNonBlocking), "stream") ||
+      check_cuda(cudaStreamCreateWithFlags(&hs, cudaStreamNonBlocking), "stream"))
     return 1;
-  cudaEvent_t copied[8], consumed[8], computed[2], read_back[2];
+  cudaEvent_t copied[8], consumed[8], computed[2], read_back[2], begin;
+  if (check_cuda(cudaEventCreateWithFlags(&begin, cudaEventDisableTiming), "event")) return 1;
+  cudaEventRecord(begin, cs);                              // what the caller queued on the copy
+  cudaStreamWaitEvent(hs, begin, 0);                       // stream (index upload) comes first
   for (int i = 0; i < n_slots; ++i) {
     if (check_cuda(cudaEventCreateWithFlags(&copied[i], cudaEventDisableTiming), "event") ||
         check_cuda(cudaEventCreateWithFlags(&consumed[i], cudaEventDisableTiming), "event"))
@@ -638,19 +660,26 @@ int sgmc_glm_sgld_scan_host(void* stream, void* copy_stream, const sgmc_glm_spec
   auto prefetch = [&](int64_t k) {
     const int sl = (int)(k % n_slots);
     float* dst = device_slots + sl * stride;
-    const float* src = host_batches + (k % host_batch_count) * host_stride;
-    cudaStreamWaitEvent(cs, consumed[sl], 0);
-    cudaMemcpyAsync(dst + (size_t)rank * (sharded ? rows_local : 0) * d, src,
-                    (size_t)rows_local * d * 4, cudaMemcpyHostToDevice, cs);
-    cudaMemcpyAsync(dst + (size_t)n * d, src + (size_t)rows_local * d, (size_t)n * 4,
-                    cudaMemcpyHostToDevice, cs);
+    cudaStreamWaitEvent(hs, consumed[sl], 0);
+    if (pull) {
+      if (rc == 0)
+        rc = sgmc_pull_rows(hs, src.X_mapped, src.y_mapped, src.idx_all + k * n, n,
+                            (int64_t)rank * (sharded ? rows_local : 0), rows_local, d, dst,
+                            dst + (size_t)n * d, src.pull_ctas);
+    } else {
+      const float* hb = src.host_batches + (k % src.host_batch_count) * host_stride;
+      cudaMemcpyAsync(dst + (size_t)rank * (sharded ? rows_local : 0) * d, hb,
+                      (size_t)rows_local * d * 4, cudaMemcpyHostToDevice, hs);
+      cudaMemcpyAsync(dst + (size_t)n * d, hb + (size_t)rows_local * d, (size_t)n * 4,
+                      cudaMemcpyHostToDevice, hs);
+    }
     if (sharded && rc == 0)
-      rc = sgmc_nccl_allgather(nccl_comm, cs, dst + (size_t)rank * rows_local * d, dst,
+      rc = sgmc_nccl_allgather(nccl_comm, hs, dst + (size_t)rank * rows_local * d, dst,
                                (size_t)rows_local * d * 4);
-    cudaEventRecord(copied[sl], cs);
+    cudaEventRecord(copied[sl], hs);
   };
-  // Tensor-core paths: the operand staging of batch k+1 runs on the copy stream (right
-  // behind its H2D copy) while step k samples; two copies of the operands.
+  // Tensor-core paths: the operand staging of batch k+1 runs on the copy stream (as soon
+  // as its rows have arrived) while step k samples; two copies of the operands.
   const bool piped = path != 0 && n_steps > 1 && !option(SGMC_OPT_NO_PIPELINE);
   cudaEvent_t staged[2] = {nullptr, nullptr}, xfree[2] = {nullptr, nullptr};
   if (piped)
@@ -660,6 +689,7 @@ int sgmc_glm_sgld_scan_host(void* stream, void* copy_stream, const sgmc_glm_spec
         return 1;
   auto stage = [&](int64_t k) -> int {
     const int sl = (int)(k % n_slots), xsl = (int)(k & 1);
+    cudaStreamWaitEvent(cs, copied[sl], 0);                  // the rows of batch k are there
     if (k >= 2) cudaStreamWaitEvent(cs, xfree[xsl], 0);      // step k-2 is done with this copy
     if (int e = sgmc_glm_prepare_minibatch(cs, spec, C, device_slots + sl * stride, nullptr, n,
                                            workspace, workspace_bytes, path, xsl))
@@ -667,19 +697,17 @@ int sgmc_glm_sgld_scan_host(void* stream, void* copy_stream, const sgmc_glm_spec
     return check_cuda(cudaEventRecord(staged[xsl], cs), "event record");
   };
   for (int64_t k = 0; k < n_steps && k < n_slots - 1; ++k) prefetch(k);
-  if (piped && rc == 0) rc = stage(0);
+  if (piped && rc == 0 && n_steps > 0) rc = stage(0);
   for (int64_t k = 0; k < n_steps && rc == 0; ++k) {
-    // copy-stream order per iteration: stage(k+1) (its rows arrived one iteration ago),
-    // then the copy of batch k + n_slots - 1
-    if (piped && k + 1 < n_steps && (rc = stage(k + 1)) != 0) break;
     if (k + n_slots - 1 < n_steps) prefetch(k + n_slots - 1);
+    if (piped && k + 1 < n_steps && rc == 0 && (rc = stage(k + 1)) != 0) break;
     if (rc) break;
     const int sl = (int)(k % n_slots);
     float* Xb = device_slots + sl * stride;
     float* uv = potential_variance + (k & 1) * 2 * C;      // (U, var) double-buffered
     int flags = k == 0 ? SGMC_STEP_CARRY_INIT : SGMC_STEP_CARRY;
     if (piped) {
-      cudaStreamWaitEvent(ms, staged[k & 1], 0);           // implies the H2D copy
+      cudaStreamWaitEvent(ms, staged[k & 1], 0);           // implies the transfer
       flags |= SGMC_STEP_X_STAGED | ((k & 1) ? SGMC_STEP_X_SLOT1 : 0);
     } else {
       cudaStreamWaitEvent(ms, copied[sl], 0);
@@ -708,18 +736,70 @@ int sgmc_glm_sgld_scan_host(void* stream, void* copy_stream, const sgmc_glm_spec
       cudaEventRecord(read_back[k & 1], rs);
     }
   }
-  // the caller waits on `stream` and `copy_stream`: order the read-back stream before
-  // the end of the copy stream
+  // the caller waits on `stream` and `copy_stream`: order the read-back and transfer
+  // streams before the end of the copy stream
   cudaEventRecord(computed[0], rs);
   cudaStreamWaitEvent(cs, computed[0], 0);
+  cudaEventRecord(begin, hs);
+  cudaStreamWaitEvent(cs, begin, 0);
   if (piped)
     for (int i = 0; i < 2; ++i) { cudaEventDestroy(staged[i]); cudaEventDestroy(xfree[i]); }
   // events can go (destruction is deferred by the runtime until they have completed)
   for (int i = 0; i < n_slots; ++i) { cudaEventDestroy(copied[i]); cudaEventDestroy(consumed[i]); }
   for (int i = 0; i < 2; ++i) { cudaEventDestroy(computed[i]); cudaEventDestroy(read_back[i]); }
+  cudaEventDestroy(begin);
   cudaStreamDestroy(rs);
+  cudaStreamDestroy(hs);
   if (rc) return rc;
   return check_cuda(cudaGetLastError(), "sgmc_glm_sgld_scan_host");
+}
+}  // namespace
+
+int sgmc_glm_sgld_scan_host(void* stream, void* copy_stream, const sgmc_glm_spec* spec,
+                            float* theta, float* v, int64_t n_chains, int64_t P,
+                            const float* host_batches, int64_t host_batch_count,
+                            int64_t n_steps, int64_t batch_size,
+                            int64_t observation_count, float* device_slots, int n_slots,
+                            float* potential_variance, float* host_results, float* grad,
+                            uint32_t* keys_a, uint32_t* keys_b, const float* step_sizes,
+                            float temperature, float alpha, float lmbd, void* workspace,
+                            size_t workspace_bytes, int path, int prng_layout,
+                            void* nccl_comm, int rank, int n_ranks, const uint8_t* keep,
+                            float* samples_out, float* scalars_out, int64_t capacity,
+                            int64_t* kept) {
+  HostSource src;
+  src.host_batches = host_batches;
+  src.host_batch_count = host_batch_count;
+  return scan_host_impl(stream, copy_stream, spec, theta, v, n_chains, P, src, n_steps,
+                        batch_size, observation_count, device_slots, n_slots,
+                        potential_variance, host_results, grad, keys_a, keys_b, step_sizes,
+                        temperature, alpha, lmbd, workspace, workspace_bytes, path, prng_layout,
+                        nccl_comm, rank, n_ranks, keep, samples_out, scalars_out, capacity, kept);
+}
+
+int sgmc_glm_sgld_scan_pull(void* stream, void* copy_stream, const sgmc_glm_spec* spec,
+                            float* theta, float* v, int64_t n_chains, int64_t P,
+                            const float* X_mapped, const float* y_mapped,
+                            const int32_t* idx_all, int pull_ctas,
+                            int64_t n_steps, int64_t batch_size,
+                            int64_t observation_count, float* device_slots, int n_slots,
+                            float* potential_variance, float* host_results, float* grad,
+                            uint32_t* keys_a, uint32_t* keys_b, const float* step_sizes,
+                            float temperature, float alpha, float lmbd, void* workspace,
+                            size_t workspace_bytes, int path, int prng_layout,
+                            void* nccl_comm, int rank, int n_ranks, const uint8_t* keep,
+                            float* samples_out, float* scalars_out, int64_t capacity,
+                            int64_t* kept) {
+  HostSource src;
+  src.X_mapped = X_mapped;
+  src.y_mapped = y_mapped;
+  src.idx_all = idx_all;
+  src.pull_ctas = pull_ctas;
+  return scan_host_impl(stream, copy_stream, spec, theta, v, n_chains, P, src, n_steps,
+                        batch_size, observation_count, device_slots, n_slots,
+                        potential_variance, host_results, grad, keys_a, keys_b, step_sizes,
+                        temperature, alpha, lmbd, workspace, workspace_bytes, path, prng_layout,
+                        nccl_comm, rank, n_ranks, keep, samples_out, scalars_out, capacity, kept);
 }
 
 // K Langevin steps over a data set resident in HBM, one C call: the lax.scan of

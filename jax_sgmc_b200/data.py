@@ -246,6 +246,24 @@ class StreamingNumpyDataLoader(NumpyDataLoader):
     self.device_data = {}            # nothing is resident
     self._chains: List[dict] = []
     self.upload_comm = None          # see shard_upload
+    self.pull = False                # True: the GPU reads the rows over the host link itself
+    self._mapped = {}
+
+  def mapped(self, name: str) -> int:
+    """Device-visible address of ``host_data[name]``: the array's pages are locked and
+    mapped in place on first use (cudaHostRegister, no copy), so kernels can read
+    minibatch rows straight out of host memory (sgmc_pull_rows)."""
+    if name not in self._mapped:
+      self._mapped[name] = ops.host_register(self.host_data[name])
+    return self._mapped[name]
+
+  def __del__(self):
+    for name in list(getattr(self, "_mapped", {})):
+      try:
+        ops.host_unregister(self.host_data[name])
+      except Exception:       # interpreter shutdown / context already gone
+        pass
+      self._mapped.pop(name, None)
 
   def shard_upload(self, comm):
     """Chain-sharded multi-GPU runs: every rank consumes the same minibatches, so

@@ -146,6 +146,14 @@ class DeviceArray:
               arr.ctypes.data_as(C.c_void_p), self.nbytes, s.handle)
     s.sync()   # pageable source: do not let the caller free it early
 
+  def copy_from_pinned(self, host_addr: int, nbytes: int, stream: Optional[Stream] = None):
+    """Asynchronous H2D copy of ``nbytes`` from page-locked host memory at ``host_addr``
+    (the caller keeps the source alive and untouched until the stream has passed)."""
+    assert 0 <= nbytes <= self.nbytes
+    s = stream or current_stream()
+    _lib.call("sgmc_memcpy_h2d", C.c_void_p(self.ptr), C.c_void_p(host_addr), int(nbytes),
+              s.handle)
+
   def numpy(self, stream: Optional[Stream] = None) -> np.ndarray:
     out = np.empty(self.shape, dtype=self.dtype)
     s = stream or current_stream()

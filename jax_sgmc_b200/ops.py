@@ -353,6 +353,34 @@ def glm_sgld_scan_host(spec, theta, host_batches_ptr, host_batch_count, n_steps,
   return int(cnt.value)
 
 
+def glm_sgld_scan_pull(spec, theta, X_mapped: int, y_mapped: int, idx_all, n_steps, batch_size,
+                       observation_count, device_slots, n_slots, potential_variance,
+                       host_results_ptr, grad, keys_a, keys_b, step_sizes, copy_stream,
+                       temperature=1.0, v=None, alpha=0.9, lmbd=1e-5, workspace=None, path=0,
+                       layout=0, stream=None, nccl_comm=None, rank=0, n_ranks=1, keep=None,
+                       samples_out=None, scalars_out=None, kept: int = 0, pull_ctas=0) -> int:
+  """n_steps pSGLD / SGLD steps over a registered HOST data set whose minibatch rows the
+  GPU pulls over the host link by index (see sgmc_glm_sgld_scan_pull).  ``X_mapped`` /
+  ``y_mapped`` come from ``host_register``; ``idx_all`` is a device int32[n_steps, n]."""
+  C_, P = theta.shape
+  ss = np.ascontiguousarray(step_sizes, np.float32)
+  assert ss.size >= n_steps
+  kp = None if keep is None else np.ascontiguousarray(keep, np.uint8)
+  cnt = C.c_int64(int(kept))
+  cap = 0 if samples_out is None else samples_out.shape[0]
+  _lib.call("sgmc_glm_sgld_scan_pull", _s(stream), copy_stream.handle, C.byref(spec),
+            vp(theta), vp(v), C_, P, C.c_void_p(X_mapped), C.c_void_p(y_mapped), vp(idx_all),
+            int(pull_ctas), int(n_steps), int(batch_size), int(observation_count),
+            vp(device_slots), int(n_slots), vp(potential_variance),
+            C.c_void_p(host_results_ptr), vp(grad), vp(keys_a), vp(keys_b),
+            ss.ctypes.data_as(C.c_void_p), float(temperature), float(alpha), float(lmbd),
+            vp(workspace), workspace.nbytes, PATH[path], _layout(layout),
+            None if nccl_comm is None else C.c_void_p(nccl_comm), int(rank), int(n_ranks),
+            None if kp is None else kp.ctypes.data_as(C.c_void_p), vp(samples_out),
+            vp(scalars_out), int(cap), C.byref(cnt))
+  return int(cnt.value)
+
+
 def host_gather_batches(dst_ptr: int, X: np.ndarray, y: np.ndarray, idx: np.ndarray, row0: int,
                         rows: int, n_threads: int):
   """Threaded host gather into a page-locked staging buffer (see
@@ -362,6 +390,30 @@ def host_gather_batches(dst_ptr: int, X: np.ndarray, y: np.ndarray, idx: np.ndar
   _lib.call("sgmc_host_gather_batches", C.c_void_p(dst_ptr), X.ctypes.data_as(C.c_void_p),
             y.ctypes.data_as(C.c_void_p), idx.ctypes.data_as(C.c_void_p), int(nb), int(n),
             int(X.shape[1]), int(row0), int(rows), int(n_threads))
+
+
+def host_register(arr: np.ndarray) -> int:
+  """Lock the pages of a host array in place and map them for the device (see
+  sgmc_host_register); returns the address kernels read it at."""
+  assert arr.flags["C_CONTIGUOUS"]
+  out = C.c_void_p()
+  _lib.call("sgmc_host_register", C.c_void_p(arr.ctypes.data), int(arr.nbytes), C.byref(out))
+  return int(out.value)
+
+
+def host_unregister(arr: np.ndarray):
+  _lib.call("sgmc_host_unregister", C.c_void_p(arr.ctypes.data))
+
+
+def pull_rows(X_mapped: int, y_mapped, idx, batch_size, row0, rows, d, dst_rows, dst_labels=None,
+              n_ctas=0, stream=None):
+  """Rows idx[row0 : row0 + rows] of a registered host data set -> device (see
+  sgmc_pull_rows).  ``dst_rows`` / ``dst_labels`` are DeviceArrays or raw addresses."""
+  as_ptr = lambda a: C.c_void_p(a) if isinstance(a, int) else vp(a)
+  _lib.call("sgmc_pull_rows", _s(stream), C.c_void_p(X_mapped),
+            None if y_mapped is None else C.c_void_p(y_mapped), as_ptr(idx), int(batch_size),
+            int(row0), int(rows), int(d), as_ptr(dst_rows),
+            None if dst_labels is None else as_ptr(dst_labels), int(n_ctas))
 
 
 def glm_sgld_scan_device(spec, theta, X, y, observation_count, batch_size, potential,

@@ -183,12 +183,20 @@ class _PotentialFn:
   def _sgld_scan_host_stream(self, sample, source, keys_a, keys_b, step_sizes, temperatures,
                              keep, samples_out, scalars_out, kept, v, alpha, lmbd, grad_out,
                              U_out, var_out):
-    """The scan over a HOST-resident data set (StreamingNumpyDataLoader): chunks of
-    minibatches are gathered by host threads into page-locked memory
-    (sgmc_host_gather_batches) while the device works through the previous chunk
-    (sgmc_glm_sgld_scan_host: H2D copies two batches ahead, operand staging one step
-    ahead, (U, var) of every step read back).  Returns None when the configuration
-    needs the step loop."""
+    """The scan over a HOST-resident data set (StreamingNumpyDataLoader).
+
+    staged (default): chunks of minibatches are gathered by host threads into page-locked
+    memory (sgmc_host_gather_batches) and copied by the DMA engine
+    (sgmc_glm_sgld_scan_host) while the device works through the previous chunk.
+    pull (``SGMC_HOST_PULL=1`` or ``loader.pull = True``; no host thread touches the data,
+    but SM-issued host reads and the HBM-bound kernels slow each other down, see
+    csrc/host_pull.cu): the data set is page-locked and mapped in place once
+    (``loader.mapped``); per chunk only the index rows of the chain's NumPy PCG64 pipeline
+    go to the device, and the GPU reads every minibatch's rows over the host link itself
+    (sgmc_glm_sgld_scan_pull: rows two batches ahead, operand staging one step ahead,
+    (U, var) of every step read back).
+    Both give identical samples.  Returns None when the configuration needs the step
+    loop."""
     import os
     import threading
     from .device import Stream, current_stream
@@ -211,35 +219,49 @@ class _PotentialFn:
     if n % world:
       return None
     rows = n // world
+    pull = bool(getattr(loader, "pull", False)) or os.environ.get("SGMC_HOST_PULL", "0") == "1"
     host_stride, dev_stride = rows * d + n, n * d + n
     K = len(step_sizes)
-    CH = max(2, min(int(source["chunk"]), 64, K))
+    CH = max(2, min(int(source["chunk"]), 512 if pull else 64, K))
     CH -= CH % 2                       # the chain keys ping-pong once per step
-    key = ("host_stream", C, sample.n_params, n, path, CH, world)
+    key = ("host_stream", C, sample.n_params, n, path, CH, world, pull)
     buf = self._buffers.get(key)
     if buf is None:
-      ring, ring_addr = _pinned_array(2 * CH * host_stride)
       res, res_addr = _pinned_array(CH * 2 * C)
-      buf = {"ring": ring, "ring_addr": ring_addr, "res": res, "res_addr": res_addr,
+      buf = {"res": res, "res_addr": res_addr,
              "slots": DeviceArray((3 * dev_stride,), np.float32),
              "uv": DeviceArray((2, 2, C), np.float32), "copy": Stream.create(),
              "ws": ops.glm_workspace(C, n, spec.d, path)}
+      if pull:
+        hidx, hidx_addr = _pinned_array(2 * CH * n)
+        buf.update(hidx=hidx.view(np.int32).reshape(2, CH, n), hidx_addr=hidx_addr,
+                   didx=DeviceArray((2, CH, n), np.int32))
+      else:
+        ring, ring_addr = _pinned_array(2 * CH * host_stride)
+        buf.update(ring=ring, ring_addr=ring_addr)
       self._buffers[key] = buf
     self._carried = None
-    threads = max(1, (os.cpu_count() or 1) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1"))))
+    # gather threads: the physical cores (the gather is DRAM-bound: 8 threads move as
+    # much as 16 on a 16-vCPU host), shared between the ranks of a node
+    threads = max(1, int(os.environ.get("SGMC_GATHER_THREADS", (os.cpu_count() or 2) // 2)) //
+                  max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1"))))
     main = current_stream()
-
-    def gather(idx_rows, half):
-      ops.host_gather_batches(buf["ring_addr"] + half * CH * host_stride * 4, X, y, idx_rows,
-                              rank * rows, rows, threads)
+    Xm = loader.mapped(self.likelihood.x) if pull else 0
+    ym = loader.mapped(self.likelihood.y) if pull else 0
 
     def produce(count, half):
-      # index draw (the chain's NumPy PCG64 pipeline) + row gather of one chunk; runs in a
-      # worker thread beside the device's work on the previous chunk
-      gather(source["draw"](count), half)
+      # index draw (the chain's NumPy PCG64 pipeline) of one chunk, then (staged mode) the
+      # row gather; runs in a worker thread beside the device's work on the previous chunk
+      idx_rows = source["draw"](count)
+      if pull:
+        buf["hidx"][half, :count] = idx_rows
+      else:
+        ops.host_gather_batches(buf["ring_addr"] + half * CH * host_stride * 4, X, y, idx_rows,
+                                rank * rows, rows, threads)
 
     ss = np.ascontiguousarray(step_sizes, np.float32)
     kp = None if keep is None else np.ascontiguousarray(keep, np.uint8)
+    nccl = getattr(comm, "_comm", None) and comm._comm.value
     done, half, last_k = 0, 0, 0
     produce(min(CH, K), 0)
     trace = []
@@ -249,14 +271,22 @@ class _PotentialFn:
       if done + k < K:
         worker = threading.Thread(target=produce, args=(min(CH, K - done - k), 1 - half))
         worker.start()
-      kept = ops.glm_sgld_scan_host(
-          spec, sample.flat, buf["ring_addr"] + half * CH * host_stride * 4, k, k, n, N,
-          buf["slots"], 3, buf["uv"], buf["res_addr"], grad_out, keys_a, keys_b, ss[done:done + k],
-          buf["copy"], temperature=float(temps[0]) if temps.size else 1.0, v=v, alpha=alpha,
-          lmbd=lmbd, workspace=buf["ws"], path=path,
-          nccl_comm=getattr(comm, "_comm", None) and comm._comm.value, rank=rank, n_ranks=world,
-          keep=None if kp is None else kp[done:done + k], samples_out=samples_out,
-          scalars_out=scalars_out, kept=kept)
+      common = dict(temperature=float(temps[0]) if temps.size else 1.0, v=v, alpha=alpha,
+                    lmbd=lmbd, workspace=buf["ws"], path=path, nccl_comm=nccl, rank=rank,
+                    n_ranks=world, keep=None if kp is None else kp[done:done + k],
+                    samples_out=samples_out, scalars_out=scalars_out, kept=kept)
+      if pull:
+        didx = buf["didx"].row_slice(half, half + 1)
+        didx.copy_from_pinned(buf["hidx_addr"] + half * CH * n * 4, k * n * 4, buf["copy"])
+        kept = ops.glm_sgld_scan_pull(
+            spec, sample.flat, Xm, ym, didx, k, n, N, buf["slots"], 3, buf["uv"],
+            buf["res_addr"], grad_out, keys_a, keys_b, ss[done:done + k], buf["copy"],
+            pull_ctas=int(os.environ.get("SGMC_PULL_CTAS", "0")), **common)
+      else:
+        kept = ops.glm_sgld_scan_host(
+            spec, sample.flat, buf["ring_addr"] + half * CH * host_stride * 4, k, k, n, N,
+            buf["slots"], 3, buf["uv"], buf["res_addr"], grad_out, keys_a, keys_b,
+            ss[done:done + k], buf["copy"], **common)
       main.sync()
       buf["copy"].sync()
       trace.append(buf["res"][:k * 2 * C].reshape(k, 2, C)[:, 0].mean(axis=1))   # host reads U
@@ -270,7 +300,8 @@ class _PotentialFn:
         U_out.copy_from(last.row_slice(0, 1).reshape(C))
       if var_out is not None:
         var_out.copy_from(last.row_slice(1, 2).reshape(C))
-    self.h2d_bytes_per_step = (rows * d + n) * 4
+    self.host_link_mode = "pull" if pull else "staged"
+    self.h2d_bytes_per_step = (rows * d + n) * 4 + (n * 4 if pull else 0)   # + the index row
     self.d2h_bytes_per_step = 2 * C * 4
     return kept
 

@@ -202,12 +202,14 @@ def test_sample_ring_equals_device_buffer(gpu, direct, monkeypatch):
                             a[0]["samples"]["variables"]["w"][-1])
 
 
-def test_streaming_loader_equals_resident_loader(gpu):
-  """StreamingNumpyDataLoader (rows gathered on the host into pinned memory,
-  double-buffered H2D of cache_size minibatches on a copy stream; SURVEY.md
-  8f-2) feeds the chains the same minibatches as the HBM-resident
-  NumpyDataLoader: identical samples, several cache refills deep."""
+@pytest.mark.parametrize("link", ["pull", "staged"])
+def test_streaming_loader_equals_resident_loader(gpu, monkeypatch, link):
+  """StreamingNumpyDataLoader feeds the chains the same minibatches as
+  the HBM-resident NumpyDataLoader: identical samples, several cache refills deep --
+  with the rows gathered on the host into pinned memory and copied by the DMA engine
+  (default) and with the rows pulled by the GPU out of the mapped host arrays."""
   from jax_sgmc_b200 import alias, data, glm, potential
+  monkeypatch.setenv("SGMC_HOST_PULL", "1" if link == "pull" else "0")
   X, y, _ = odata.logistic_dataset(700, 16, seed=4)
   pot = potential.minibatch_potential(glm.GaussianPrior(5.0), glm.LogisticRegression(),
                                       strategy="vmap", path="simt")
@@ -223,6 +225,7 @@ def test_streaming_loader_equals_resident_loader(gpu):
   assert a["sample_count"] == b["sample_count"] == 40
   assert np.array_equal(a["samples"]["variables"]["w"], b["samples"]["variables"]["w"])
   assert np.array_equal(a["samples"]["likelihood"], b["samples"]["likelihood"])
+  assert pot.host_link_mode == link
   # many chains share the one stream of minibatches
   loader = data.StreamingNumpyDataLoader(x=X, y=y)
   run = alias.sgld(pot, loader, cache_size=4, batch_size=24, first_step_size=1e-2,
@@ -285,3 +288,31 @@ def test_random_thinning_respects_burn_in(gpu, iterations):
   # deterministic (default key PRNGKey(0))
   state2, _ = thinning.init(iterations)
   assert [i for i in range(iterations) if thinning.get(state2, i)] == chosen
+
+
+def test_pull_rows_reads_the_mapped_host_array(gpu):
+  """sgmc_host_register + sgmc_pull_rows: rows (and labels) of a host array the GPU
+  reads over the host link by index -- whole batches, a rank's row slice, row lengths
+  that are not a multiple of 4 floats."""
+  from jax_sgmc_b200 import ops
+  from jax_sgmc_b200.device import DeviceArray as DA
+  rng = np.random.default_rng(5)
+  for N, d, n in ((5000, 256, 64), (777, 10, 33)):
+    X = rng.standard_normal((N, d)).astype(np.float32)
+    y = rng.standard_normal(N).astype(np.float32)
+    Xm, ym = ops.host_register(X), ops.host_register(y)
+    assert ops.host_register(X) == Xm                      # idempotent
+    idx = rng.integers(0, N, n).astype(np.int32)
+    d_idx = DA.from_numpy(idx)
+    dst, lab = DA.zeros((n, d)), DA.zeros((n,))
+    ops.pull_rows(Xm, ym, d_idx, n, 0, n, d, dst, lab)
+    assert np.array_equal(dst.numpy(), X[idx])
+    assert np.array_equal(lab.numpy(), y[idx])
+    dst2 = DA.zeros((n, d))
+    r0, rows = n // 3, n // 2
+    ops.pull_rows(Xm, None, d_idx, n, r0, rows, d, dst2, n_ctas=3)
+    want = np.zeros((n, d), np.float32)
+    want[r0:r0 + rows] = X[idx[r0:r0 + rows]]
+    assert np.array_equal(dst2.numpy(), want)
+    ops.host_unregister(X)
+    ops.host_unregister(y)
