@@ -51,6 +51,7 @@ PROTOTYPES = {
     "sgmc_malloc": [C.POINTER(_vp), _sz],
     "sgmc_free": [_vp],
     "sgmc_host_alloc": [C.POINTER(_vp), _sz],
+    "sgmc_host_alloc_wc": [C.POINTER(_vp), _sz],
     "sgmc_host_free": [_vp],
     "sgmc_memcpy_h2d": [_vp, _vp, _sz, _vp],
     "sgmc_memcpy_d2h": [_vp, _vp, _sz, _vp],

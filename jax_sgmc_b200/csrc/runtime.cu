@@ -119,6 +119,10 @@ int sgmc_free(void* dptr) { return check_cuda(cudaFree(dptr), "cudaFree"); }
 int sgmc_host_alloc(void** hptr, size_t bytes) {
   return check_cuda(cudaMallocHost(hptr, bytes ? bytes : 1), "cudaMallocHost");
 }
+int sgmc_host_alloc_wc(void** hptr, size_t bytes) {
+  return check_cuda(cudaHostAlloc(hptr, bytes ? bytes : 1, cudaHostAllocWriteCombined),
+                    "cudaHostAlloc");
+}
 int sgmc_host_free(void* hptr) {
   return check_cuda(cudaFreeHost(hptr), "cudaFreeHost");
 }

@@ -63,11 +63,13 @@ class _PinnedOwner:
       pass
 
 
-def _pinned_array(n_floats: int):
+def _pinned_array(n_floats: int, write_combined: bool = False):
   """float32[n] backed by page-locked host memory; freed when the last numpy
-  view of it dies.  Returns (array, address)."""
+  view of it dies.  Returns (array, address).  ``write_combined``: for staging the host
+  only ever writes (reading it back from the CPU is very slow)."""
   h = C.c_void_p()
-  _lib.call("sgmc_host_alloc", C.byref(h), max(n_floats, 1) * 4)
+  _lib.call("sgmc_host_alloc_wc" if write_combined else "sgmc_host_alloc", C.byref(h),
+            max(n_floats, 1) * 4)
   raw = (C.c_float * max(n_floats, 1)).from_address(h.value)
   raw._owner = _PinnedOwner(h)
   return np.ctypeslib.as_array(raw), h.value

@@ -237,13 +237,14 @@ class _PotentialFn:
         buf.update(hidx=hidx.view(np.int32).reshape(2, CH, n), hidx_addr=hidx_addr,
                    didx=DeviceArray((2, CH, n), np.int32))
       else:
-        ring, ring_addr = _pinned_array(2 * CH * host_stride)
+        ring, ring_addr = _pinned_array(2 * CH * host_stride,
+                                        write_combined=os.environ.get("SGMC_RING_WC", "0") == "1")
         buf.update(ring=ring, ring_addr=ring_addr)
       self._buffers[key] = buf
     self._carried = None
-    # gather threads: the physical cores (the gather is DRAM-bound: 8 threads move as
-    # much as 16 on a 16-vCPU host), shared between the ranks of a node
-    threads = max(1, int(os.environ.get("SGMC_GATHER_THREADS", (os.cpu_count() or 2) // 2)) //
+    # gather threads (the gather is DRAM-bound: 8 threads move as much as 16 on a 16-vCPU
+    # host), shared between the ranks of a node
+    threads = max(1, int(os.environ.get("SGMC_GATHER_THREADS", os.cpu_count() or 1)) //
                   max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1"))))
     main = current_stream()
     Xm = loader.mapped(self.likelihood.x) if pull else 0
