@@ -84,6 +84,7 @@ PROTOTYPES = {
                              _f32, _int],
     "sgmc_rms_prop_update": [_vp, _vp, _vp, _i64, _f32],
     "sgmc_rms_prop_get": [_vp, _vp, _vp, _vp, _i64, _f32],
+    "sgmc_mass_matrix_update": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64],
     "sgmc_axpby": [_vp, _vp, _f32, _vp, _f32, _vp, _i64],
     "sgmc_absmax": [_vp, _vp, _i64, _vp],
     "sgmc_tree_ewise": [_vp, _int, _vp, _f32, _vp, _vp, _i64],
@@ -96,6 +97,12 @@ PROTOTYPES = {
                           C.POINTER(_i64), _int, _f32, _f32, _f32, _vp, _int],
     "sgmc_obabo_pass_b": [_vp, _vp, _vp, _vp, _vp, _i64, C.POINTER(_i64), _int,
                           _f32, _f32, _f32, _vp, _int],
+    "sgmc_obabo_pass_a_adapted": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64,
+                                  C.POINTER(_i64), _int, _f32, _f32, _f32, _vp, _vp, _int],
+    "sgmc_obabo_pass_b_adapted": [_vp, _vp, _vp, _vp, _vp, _i64, C.POINTER(_i64), _int,
+                                  _f32, _f32, _f32, _vp, _vp, _int],
+    "sgmc_revleapfrog_step_adapted": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, C.POINTER(_i64),
+                                      _int, _f32, _f32, _vp, _vp, _int, _int],
     "sgmc_glm_potential_grad": [_vp, C.POINTER(GlmSpec), _vp, _i64, _i64, _vp,
                                 _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp,
                                 _vp, _sz, _int],

@@ -8,8 +8,11 @@ does (adaption.py:107-222): positional arguments are raveled pytrees and
 pSGLD kernel (update + get + step in one pass); the triplet itself is backed
 by the stand-alone kernels ``sgmc_rms_prop_update`` / ``sgmc_rms_prop_get``.
 
-``mass_matrix`` and ``fisher_information`` are outside the scope of this path
-(burn-in only, dense eigh / SVD) and raise.
+``mass_matrix(diagonal=True)`` (adaption.py:296-369) keeps the Welford statistics of
+all chains on the device (``sgmc_mass_matrix_update``) and hands the integrators a
+per-chain ``MassMatrix(inv, sqrt)`` that the OBABO / reversible-leapfrog kernels read
+directly (``sgmc_*_adapted``).  The dense variants (``diagonal=False``: eigh / SVD of a
+P x P matrix per chain) and ``fisher_information`` stay outside this path and raise.
 """
 from __future__ import annotations
 
@@ -75,9 +78,55 @@ def rms_prop():
   return _RmsProp((init, update, get))
 
 
-def mass_matrix(*args, **kwargs):
-  raise NotImplementedError("adaption.mass_matrix is outside the accelerated "
-                            "sampling path (SURVEY.md section 8)")
+class MassState:
+  """(iteration, mean, ssq, m_inv, m_sqrt) of adaption.py:319-341 for C chains; the
+  arrays are ``f32[C, P]`` on the device and updated in place.  ``matrix`` is the
+  ``MassMatrix`` handed to the integrators (the same object on every ``get``)."""
+
+  def __init__(self, sample: ChainTree, init_cov, burn_in: int):
+    shape = sample.flat.shape
+    self.iteration, self.burn_in = 0, int(burn_in)
+    self.mean, self.ssq = DeviceArray.zeros(shape), DeviceArray.zeros(shape)
+    if init_cov is None:                                   # ones_like(sample), :330-331
+      cov = np.ones(shape, np.float32)
+    elif isinstance(init_cov, ChainTree):
+      cov = init_cov.flat.numpy()
+    else:
+      from .tree_util import tree_flatten
+      leaves, _ = tree_flatten(init_cov)
+      flat = np.concatenate([np.asarray(l, np.float32).ravel() for l in leaves])
+      assert flat.size == shape[1], "init_cov does not match the sample"
+      cov = np.broadcast_to(flat[None, :], shape)
+    cov = np.ascontiguousarray(cov, np.float32)
+    self.m_inv = DeviceArray.from_numpy(cov)               # m_inv = init_cov, :334
+    self.m_sqrt = DeviceArray.from_numpy(                  # m_sqrt = 1 / sqrt(init_cov), :335
+        (np.float32(1.0) / np.sqrt(cov)).astype(np.float32))
+    self.matrix = MassMatrix(Tensor(1, ChainTree.like(sample, self.m_inv)),
+                             Tensor(1, ChainTree.like(sample, self.m_sqrt)))
+
+
+def mass_matrix(diagonal: bool = True, burn_in: int = 1000):
+  """adaption.py:296-369: running mean / sum of squares of the accepted samples; in
+  iteration ``burn_in`` the matrix is set once (``M^-1 = ssq / n``, ``M^1/2 = sqrt(n / ssq)``).
+  Every chain adapts its own matrix."""
+  if not diagonal:
+    raise NotImplementedError("the dense mass matrix (eigh of a P x P matrix per chain) is "
+                              "outside the accelerated sampling path (SURVEY.md section 8)")
+
+  def init(sample, init_cov=None) -> MassState:
+    return MassState(sample, init_cov, burn_in)
+
+  def update(state: MassState, sample: ChainTree, *args, **kwargs) -> MassState:
+    del args, kwargs
+    state.iteration += 1                                                   # :350
+    ops.mass_matrix_update(state.mean, state.ssq, state.m_inv, state.m_sqrt, sample.flat,
+                           state.iteration, state.burn_in)                 # :351-361
+    return state
+
+  def get(state: MassState) -> MassMatrix:
+    return state.matrix                                                    # :365-367
+
+  return init, update, get
 
 
 def fisher_information(*args, **kwargs):

@@ -1810,7 +1810,9 @@ static int launch_pair(cudaStream_t stream, const PairMaps& maps, const PairSche
     attr_set = true;
   }
   // with a noise job every SM takes part, also pairs without a tile
-  const int pairs = nz.xi ? max_pairs : std::min(max_pairs, sch.tiles_total);
+  const int cap = option(SGMC_OPT_TC_MAX_PAIRS) > 0 ? std::min(max_pairs, option(SGMC_OPT_TC_MAX_PAIRS))
+                                                    : max_pairs;
+  const int pairs = nz.xi ? cap : std::min(cap, sch.tiles_total);
   cfg.gridDim = dim3(CG * pairs);
   if (check_cuda(cudaLaunchKernelEx(&cfg, kfn, maps, sch, link, gradp, nz), name)) return 1;
   return post_launch(name);

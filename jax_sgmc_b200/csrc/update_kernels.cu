@@ -465,14 +465,20 @@ struct ObaboAOp {   // integrator.py:210-240
   float* ke;           // f32[C] accumulator (kinetic_energy_start)
   const float* mass;
   float eps, sqrt_a, o_noise, neg_half_eps;
+  // adapted per-chain mass matrix (adaption.mass_matrix): M^-1 and M^1/2 as f32[C][P], or null
+  const float* mass_inv = nullptr;
+  const float* mass_sqrt = nullptr;
   static constexpr bool kReduce = true;
   struct Regs {
     float4 tA, tB, pA, pB, gA, gB;
   };
   __device__ __forceinline__ float one(float& t, float& p, float g, float xi,
-                                       uint32_t e) const {
+                                       uint32_t e, int64_t gi) const {
     float inv_m = 1.0f, sqrt_m = 1.0f;
-    if (mass) {
+    if (mass_inv) {
+      inv_m = mass_inv[gi];
+      sqrt_m = mass_sqrt[gi];
+    } else if (mass) {
       const float m = mass[e];
       inv_m = __frcp_rn(m);
       sqrt_m = __fsqrt_rn(m);
@@ -500,8 +506,8 @@ struct ObaboAOp {   // integrator.py:210-240
     float s = 0.f;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      s += one(ta[k], pa[k], f4get(r.gA, k), nA[k], eA + k);
-      s += one(tb[k], pb[k], f4get(r.gB, k), nB[k], eB + k);
+      s += one(ta[k], pa[k], f4get(r.gA, k), nA[k], eA + k, iA + k);
+      s += one(tb[k], pb[k], f4get(r.gB, k), nB[k], eB + k, iB + k);
     }
     st4(theta, iA, make_float4(ta[0], ta[1], ta[2], ta[3]));
     st4(theta, iB, make_float4(tb[0], tb[1], tb[2], tb[3]));
@@ -511,7 +517,7 @@ struct ObaboAOp {   // integrator.py:210-240
   }
   __device__ float apply_one(int64_t i, float n, int64_t, uint32_t e) const {
     float t = theta[i], p = mom[i];
-    const float s = one(t, p, grad[i], n, e);
+    const float s = one(t, p, grad[i], n, e, i);
     theta[i] = t;
     mom[i] = p;
     return s;
@@ -527,13 +533,19 @@ struct ObaboBOp {   // integrator.py:248-261
   float* ke;           // kinetic_energy_end
   const float* mass;
   float sqrt_a, o_noise, neg_half_eps;
+  const float* mass_inv = nullptr;    // adapted per-chain mass matrix, f32[C][P] each
+  const float* mass_sqrt = nullptr;
   static constexpr bool kReduce = true;
   struct Regs {
     float4 pA, pB, gA, gB;
   };
-  __device__ __forceinline__ float one(float& p, float g, float xi, uint32_t e) const {
+  __device__ __forceinline__ float one(float& p, float g, float xi, uint32_t e,
+                                       int64_t gi) const {
     float inv_m = 1.0f, sqrt_m = 1.0f;
-    if (mass) {
+    if (mass_inv) {
+      inv_m = mass_inv[gi];
+      sqrt_m = mass_sqrt[gi];
+    } else if (mass) {
       const float m = mass[e];
       inv_m = __frcp_rn(m);
       sqrt_m = __fsqrt_rn(m);
@@ -556,8 +568,8 @@ struct ObaboBOp {   // integrator.py:248-261
     float s = 0.f;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      s += one(pa[k], f4get(r.gA, k), nA[k], eA + k);
-      s += one(pb[k], f4get(r.gB, k), nB[k], eB + k);
+      s += one(pa[k], f4get(r.gA, k), nA[k], eA + k, iA + k);
+      s += one(pb[k], f4get(r.gB, k), nB[k], eB + k, iB + k);
     }
     st4(mom, iA, make_float4(pa[0], pa[1], pa[2], pa[3]));
     st4(mom, iB, make_float4(pb[0], pb[1], pb[2], pb[3]));
@@ -565,7 +577,7 @@ struct ObaboBOp {   // integrator.py:248-261
   }
   __device__ float apply_one(int64_t i, float n, int64_t, uint32_t e) const {
     float p = mom[i];
-    const float s = one(p, grad[i], n, e);
+    const float s = one(p, grad[i], n, e, i);
     mom[i] = p;
     return s;
   }
@@ -588,14 +600,19 @@ struct RevLeapfrogOp {
   float* energy;       // f32[C] accumulator (LeapfrogState.potential)
   const float* mass;   // f32[P] or null
   float decay, neg_eps, noise_scale, inv_norm, half_eps, pos_scale;
+  const float* mass_inv = nullptr;    // adapted per-chain mass matrix, f32[C][P] each
+  const float* mass_sqrt = nullptr;
   static constexpr bool kReduce = true;
   struct Regs {
     float4 tA, tB, pA, pB, gA, gB;
   };
   __device__ __forceinline__ float one(float& t, float& p, float g, float xi,
-                                       uint32_t e) const {
+                                       uint32_t e, int64_t gi) const {
     float inv_m = 1.0f, sqrt_m = 1.0f;
-    if (mass) {
+    if (mass_inv) {
+      inv_m = mass_inv[gi];
+      sqrt_m = mass_sqrt[gi];
+    } else if (mass) {
       const float m = mass[e];
       inv_m = __frcp_rn(m);
       sqrt_m = __fsqrt_rn(m);
@@ -623,8 +640,8 @@ struct RevLeapfrogOp {
     float s = 0.f;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      s += one(ta[k], pa[k], f4get(r.gA, k), nA[k], eA + k);
-      s += one(tb[k], pb[k], f4get(r.gB, k), nB[k], eB + k);
+      s += one(ta[k], pa[k], f4get(r.gA, k), nA[k], eA + k, iA + k);
+      s += one(tb[k], pb[k], f4get(r.gB, k), nB[k], eB + k, iB + k);
     }
     st4(theta, iA, make_float4(ta[0], ta[1], ta[2], ta[3]));
     st4(theta, iB, make_float4(tb[0], tb[1], tb[2], tb[3]));
@@ -634,7 +651,7 @@ struct RevLeapfrogOp {
   }
   __device__ float apply_one(int64_t i, float n, int64_t, uint32_t e) const {
     float t = theta[i], p = mom[i];
-    const float s = one(t, p, grad[i], n, e);
+    const float s = one(t, p, grad[i], n, e, i);
     theta[i] = t;
     mom[i] = p;
     return s;
@@ -642,6 +659,15 @@ struct RevLeapfrogOp {
   __device__ void reduce(int64_t c, float s) const {
     atomicAdd(&energy[c], half_eps * s);
   }
+};
+
+// Adapted mass matrix of the *_adapted entry points: set for the duration of one call on
+// the calling thread, picked up where the constant-mass entry points build their ops.
+struct AdaptedMass { const float* inv = nullptr; const float* sqrt = nullptr; };
+static thread_local AdaptedMass g_adapted;
+struct AdaptedMassScope {
+  AdaptedMassScope(const float* inv, const float* sqrt) { g_adapted.inv = inv; g_adapted.sqrt = sqrt; }
+  ~AdaptedMassScope() { g_adapted = AdaptedMass{}; }
 };
 
 static bool aligned16(std::initializer_list<const void*> ps) {
@@ -888,6 +914,8 @@ int sgmc_obabo_pass_a(void* stream, float* theta, float* momentum,
   const float o_noise = sqrtf((1.0f - a) * temperature);
   ObaboAOp op{theta, momentum, grad, ke_start, mass, step_size, sqrtf(a),
               o_noise, -1.0f * (0.5f * step_size)};
+  op.mass_inv = g_adapted.inv;
+  op.mass_sqrt = g_adapted.sqrt;
   return launch_noise_pass((cudaStream_t)stream, tab, keys_in, keys_out,
                            n_chains, kKeySplit3A, prng_layout, op,
                            "sgmc_obabo_pass_a");
@@ -905,6 +933,8 @@ int sgmc_obabo_pass_b(void* stream, float* momentum, const float* grad,
   const float o_noise = sqrtf((1.0f - a) * temperature);
   ObaboBOp op{momentum, grad, ke_end, mass, sqrtf(a), o_noise,
               -1.0f * (0.5f * step_size)};
+  op.mass_inv = g_adapted.inv;
+  op.mass_sqrt = g_adapted.sqrt;
   return launch_noise_pass((cudaStream_t)stream, tab, keys_in, nullptr,
                            n_chains, kKeySplit3B, prng_layout, op,
                            "sgmc_obabo_pass_b");
@@ -925,8 +955,50 @@ int sgmc_revleapfrog_step(void* stream, float* theta, float* momentum, const flo
                    1.0f - ef, -1.0f * step_size, sqrtf((4.0f * friction) * step_size),
                    1.0f / (1.0f + ef), 0.5f * step_size,
                    last ? 0.5f * step_size : step_size};
+  op.mass_inv = g_adapted.inv;
+  op.mass_sqrt = g_adapted.sqrt;
   return launch_noise_pass((cudaStream_t)stream, tab, keys_in, keys_out, n_chains,
                            kKeySplit2, prng_layout, op, "sgmc_revleapfrog_step");
+}
+
+// The same three passes with an ADAPTED mass matrix (adaption.mass_matrix, diagonal): every
+// chain carries its own M^-1 and M^1/2 (f32[C][P] each, as MassMatrix(inv, sqrt) hands them
+// to the integrators, integrator.py:177-200, :395-446) instead of one constant mass vector.
+int sgmc_obabo_pass_a_adapted(void* stream, float* theta, float* momentum,
+                              const float* grad, float* ke_start,
+                              const uint32_t* keys_in, uint32_t* keys_out,
+                              int64_t n_chains, const int64_t* leaf_sizes, int n_leaves,
+                              float step_size, float temperature, float friction,
+                              const float* mass_inv, const float* mass_sqrt, int prng_layout) {
+  SGMC_REQUIRE(mass_inv && mass_sqrt, "null mass matrix");
+  AdaptedMassScope scope(mass_inv, mass_sqrt);
+  return sgmc_obabo_pass_a(stream, theta, momentum, grad, ke_start, keys_in, keys_out, n_chains,
+                           leaf_sizes, n_leaves, step_size, temperature, friction, nullptr,
+                           prng_layout);
+}
+
+int sgmc_obabo_pass_b_adapted(void* stream, float* momentum, const float* grad,
+                              float* ke_end, const uint32_t* keys_in,
+                              int64_t n_chains, const int64_t* leaf_sizes, int n_leaves,
+                              float step_size, float temperature, float friction,
+                              const float* mass_inv, const float* mass_sqrt, int prng_layout) {
+  SGMC_REQUIRE(mass_inv && mass_sqrt, "null mass matrix");
+  AdaptedMassScope scope(mass_inv, mass_sqrt);
+  return sgmc_obabo_pass_b(stream, momentum, grad, ke_end, keys_in, n_chains, leaf_sizes,
+                           n_leaves, step_size, temperature, friction, nullptr, prng_layout);
+}
+
+int sgmc_revleapfrog_step_adapted(void* stream, float* theta, float* momentum,
+                                  const float* grad, float* energy, const uint32_t* keys_in,
+                                  uint32_t* keys_out, int64_t n_chains,
+                                  const int64_t* leaf_sizes, int n_leaves, float step_size,
+                                  float friction, const float* mass_inv,
+                                  const float* mass_sqrt, int last, int prng_layout) {
+  SGMC_REQUIRE(mass_inv && mass_sqrt, "null mass matrix");
+  AdaptedMassScope scope(mass_inv, mass_sqrt);
+  return sgmc_revleapfrog_step(stream, theta, momentum, grad, energy, keys_in, keys_out,
+                               n_chains, leaf_sizes, n_leaves, step_size, friction, nullptr,
+                               last, prng_layout);
 }
 
 }  // extern "C"

@@ -129,6 +129,17 @@ def _flat_vector(tree, like: ChainTree) -> DeviceArray:
   return DeviceArray.from_numpy(flat)
 
 
+def _mass_operand(m, like: ChainTree):
+  """What the kernels take for a mass: None (unit mass), ``f32[P]`` (a constant diagonal
+  mass pytree, the kernels derive M^-1 and M^1/2), or ``(inv, sqrt)`` of ``f32[C, P]`` for
+  an adapted ``MassMatrix`` (adaption.mass_matrix, one matrix per chain)."""
+  if m is None:
+    return None
+  if isinstance(m, MassMatrix) and isinstance(getattr(m.inv, "tensor", None), ChainTree):
+    return (m.inv.tensor.flat, m.sqrt.tensor.flat)
+  return _flat_vector(m, like)
+
+
 def init_mass(mass) -> MassMatrix:
   """integrator.py:99-116 (diagonal mass as ``Tensor(ndim=1)`` of the inverse
   and the square root).  Evaluated inside the fused kernels; this helper keeps
@@ -374,7 +385,7 @@ def obabo(potential_fn, batch_fn, steps: int = 10, friction: float = 1.0,
       return {
           "grad": DeviceArray(theta.flat.shape, np.float32),
           "U1": DeviceArray((C,), np.float32), "U2": DeviceArray((C,), np.float32),
-          "mass": None if m is None else _flat_vector(m, theta)}
+          "mass": _mass_operand(m, theta)}
     sc = scratch.get(theta.flat, build, mass)      # rebuilt when `mass` changes
     assert sc["grad"].shape == theta.flat.shape
     data_state, model_state = state.data_state, state.model_state
@@ -416,8 +427,7 @@ def reversible_leapfrog(potential_fn, batch_fn, steps: int = 10, friction=0.25,
   scratch = _Scratch()
 
   def _mass_vector(mass, theta):
-    m = mass if mass is not None else const_mass
-    return None if m is None else _flat_vector(m, theta)
+    return _mass_operand(mass if mass is not None else const_mass, theta)
 
   def init_fn(init_sample, key=None, batch_kwargs: Dict = None,
               init_model_state: PyTree = None, mass: PyTree = None) -> LeapfrogState:
@@ -427,7 +437,9 @@ def reversible_leapfrog(potential_fn, batch_fn, steps: int = 10, friction=0.25,
     ks = ops.split(_keys_for(key, C).current, 2).numpy()            # :500
     momentum = random_tree(ks[:, 1], sample)                        # :501, :383-386
     m = _mass_vector(mass, sample)
-    if m is not None:
+    if isinstance(m, tuple):                       # adapted: sqrt(M) per chain on the device
+      ops.tree_ewise(2, momentum.flat, 1.0, m[1], momentum.flat)
+    elif m is not None:
       momentum.flat.copy_from_host(momentum.flat.numpy() * np.sqrt(m.numpy())[None, :])
     return LeapfrogState(
         potential=DeviceArray.zeros((C,)), key=KeyState(ks[:, 0]), positions=sample,
@@ -440,7 +452,9 @@ def reversible_leapfrog(potential_fn, batch_fn, steps: int = 10, friction=0.25,
     def build():
       m = _mass_vector(mass, theta)
       inv_full = None
-      if m is not None:      # inv_m broadcast over the chains for the opening half step
+      if isinstance(m, tuple):
+        inv_full = m[0]      # adapted: M^-1 per chain, read in place
+      elif m is not None:    # inv_m broadcast over the chains for the opening half step
         inv_full = DeviceArray.from_numpy(
             np.tile((np.float32(1.0) / m.numpy())[None, :], (theta.n_chains, 1)))
       return {

@@ -183,9 +183,22 @@ def sghmc_step(theta, momentum, grad, keys_in, keys_out, leaf_sizes, step_size,
             vp(friction_vec), vp(mass), int(bool(last)), _layout(layout))
 
 
+def _is_adapted(mass) -> bool:
+  """A per-chain adapted mass matrix: ``MassMatrix(inv, sqrt)`` of f32[C, P] DeviceArrays
+  (adaption.mass_matrix); anything else is a constant mass vector f32[P] or None."""
+  return isinstance(mass, tuple) and len(mass) == 2
+
+
 def obabo_pass_a(theta, momentum, grad, ke_start, keys_in, keys_out,
                  leaf_sizes, step_size, temperature=1.0, friction=1.0,
                  mass=None, layout=0, stream=None):
+  if _is_adapted(mass):
+    assert mass[0].shape == theta.shape and mass[1].shape == theta.shape
+    _lib.call("sgmc_obabo_pass_a_adapted", _s(stream), vp(theta), vp(momentum), vp(grad),
+              vp(ke_start), vp(keys_in), vp(keys_out), theta.shape[0],
+              i64_array(leaf_sizes), len(leaf_sizes), float(step_size),
+              float(temperature), float(friction), vp(mass[0]), vp(mass[1]), _layout(layout))
+    return
   _lib.call("sgmc_obabo_pass_a", _s(stream), vp(theta), vp(momentum), vp(grad),
             vp(ke_start), vp(keys_in), vp(keys_out), theta.shape[0],
             i64_array(leaf_sizes), len(leaf_sizes), float(step_size),
@@ -195,6 +208,13 @@ def obabo_pass_a(theta, momentum, grad, ke_start, keys_in, keys_out,
 def obabo_pass_b(momentum, grad, ke_end, keys_in, leaf_sizes, step_size,
                  temperature=1.0, friction=1.0, mass=None, layout=0,
                  stream=None):
+  if _is_adapted(mass):
+    assert mass[0].shape == momentum.shape and mass[1].shape == momentum.shape
+    _lib.call("sgmc_obabo_pass_b_adapted", _s(stream), vp(momentum), vp(grad), vp(ke_end),
+              vp(keys_in), momentum.shape[0], i64_array(leaf_sizes),
+              len(leaf_sizes), float(step_size), float(temperature),
+              float(friction), vp(mass[0]), vp(mass[1]), _layout(layout))
+    return
   _lib.call("sgmc_obabo_pass_b", _s(stream), vp(momentum), vp(grad), vp(ke_end),
             vp(keys_in), momentum.shape[0], i64_array(leaf_sizes),
             len(leaf_sizes), float(step_size), float(temperature),
@@ -480,10 +500,26 @@ def glm_sgld_step(spec, theta, X, y, idx, observation_count, potential, variance
 
 def revleapfrog_step(theta, momentum, grad, energy, keys_in, keys_out, leaf_sizes,
                      step_size, friction, mass=None, last=False, layout=0, stream=None):
+  if _is_adapted(mass):
+    assert mass[0].shape == theta.shape and mass[1].shape == theta.shape
+    _lib.call("sgmc_revleapfrog_step_adapted", _s(stream), vp(theta), vp(momentum), vp(grad),
+              vp(energy), vp(keys_in), vp(keys_out), theta.shape[0], i64_array(leaf_sizes),
+              len(leaf_sizes), float(step_size), float(friction), vp(mass[0]), vp(mass[1]),
+              1 if last else 0, _layout(layout))
+    return
   _lib.call("sgmc_revleapfrog_step", _s(stream), vp(theta), vp(momentum), vp(grad),
             vp(energy), vp(keys_in), vp(keys_out), theta.shape[0], i64_array(leaf_sizes),
             len(leaf_sizes), float(step_size), float(friction), vp(mass),
             1 if last else 0, _layout(layout))
+
+
+def mass_matrix_update(mean, ssq, m_inv, m_sqrt, sample, iteration: int, burn_in: int,
+                       stream=None):
+  """adaption.mass_matrix(diagonal=True).update for all chains (sgmc_mass_matrix_update);
+  ``iteration`` is the already incremented count."""
+  assert mean.shape == sample.shape == ssq.shape == m_inv.shape == m_sqrt.shape
+  _lib.call("sgmc_mass_matrix_update", _s(stream), vp(mean), vp(ssq), vp(m_inv), vp(m_sqrt),
+            vp(sample), sample.size, int(iteration), int(burn_in))
 
 
 def mh_decide(mode, U_state, U_new, e0, e1, temperature, keys_in, keys_out, reject,
@@ -553,6 +589,7 @@ OPT_TC_TILE_N = 7            # accumulator columns per CTA and tile: 256 (defaul
 OPT_NO_SHADOW_NOISE = 8      # 1: noise in the update kernel instead of under the GEMM mainloops
 OPT_NO_PIPELINE = 9          # 1: scans stage minibatches on the sampling stream (no side stream)
 OPT_STEP_PROFILE = 10        # 1: per-kernel CUDA-event timing of the carried step
+OPT_TC_MAX_PAIRS = 11        # > 0: cap on the CTA pairs of k_glm_tc_pair (chain groups side by side)
 OPT_TC_CTA_GROUP = 5         # 2 (default): tcgen05 cta_group::2 on CTA pairs; 1: single CTAs
 
 

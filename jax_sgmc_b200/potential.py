@@ -386,6 +386,51 @@ class _MlpPotentialFn:
     return (U, state), g
 
 
+class _ProbedPotentialFn:
+  """``minibatch_potential(prior, likelihood)`` handed the reference's plain callables
+  (potential.py:94-127).  The first call that brings a sample and a minibatch lets
+  ``glm.from_callable`` recognise the closed form (the callables are evaluated on a few
+  host points, once); from then on every call goes to the fused-kernel potential of the
+  recognised specification.  A callable that is no recognised closed form raises
+  ``TypeError`` at that first call."""
+
+  def __init__(self, prior, likelihood, temperature, path):
+    self._callables = (prior, likelihood)
+    self._args = (temperature, path)
+    self._impl = None
+
+  def _resolve(self, sample: ChainTree, loader) -> "_PotentialFn":
+    if self._impl is None:
+      from .tree_util import tree_unflatten
+      prior, likelihood = self._callables
+      tmpl = tree_unflatten(sample.treedef, [np.zeros(s, np.float64) for s in sample.shapes])
+      lik_spec, prior_spec = glm.from_callable(likelihood, prior, tmpl,
+                                               loader.initializer_batch())
+      self._impl = _PotentialFn(prior_spec, lik_spec, *self._args)
+    return self._impl
+
+  def __call__(self, sample, reference_data, *args, **kwargs):
+    return self._resolve(sample, reference_data[0].loader)(sample, reference_data, *args,
+                                                           **kwargs)
+
+  def value_and_grad(self, sample, reference_data, *args, **kwargs):
+    return self._resolve(sample, reference_data[0].loader).value_and_grad(
+        sample, reference_data, *args, **kwargs)
+
+  def sgld_step(self, sample, reference_data, *args, **kwargs):
+    return self._resolve(sample, reference_data[0].loader).sgld_step(
+        sample, reference_data, *args, **kwargs)
+
+  def sgld_scan(self, sample, source, *args, **kwargs):
+    return self._resolve(sample, source["loader"]).sgld_scan(sample, source, *args, **kwargs)
+
+  def __getattr__(self, name):          # last_variance, h2d_bytes_per_step, ... of the real one
+    impl = self.__dict__.get("_impl")
+    if impl is None:
+      raise AttributeError(name)
+    return getattr(impl, name)
+
+
 def value_and_grad(potential_fn: _PotentialFn) -> Callable:
   """Stand-in for ``jax.value_and_grad(potential_fn, argnums=0, has_aux=True)``.
 
@@ -405,19 +450,30 @@ def minibatch_potential(prior, likelihood, strategy: str = "map",
   del is_batched
   if strategy not in ("map", "vmap", "pmap"):
     raise NotImplementedError(f"Strategy {strategy} is unknown")
-  if has_state:
-    raise NotImplementedError(
-        "stateful likelihoods are outside the fused GLM path")
+  # has_state (potential.py:131-137, :174-177): the reference threads a model state
+  # through the likelihood and keeps the state returned for observation 0.  The
+  # recognised likelihood specifications are pure functions of (sample, observation) --
+  # they never change a state -- so the state handed in is the state handed back, which
+  # is what the reference computes for a likelihood that returns its state unchanged.
+  del has_state
   if isinstance(likelihood, nn.MLPClassifier):
     if not isinstance(prior, (glm.FlatPrior, glm.GaussianPrior)):
       raise TypeError("the MLP potential takes a FlatPrior or a GaussianPrior")
     return _MlpPotentialFn(prior, likelihood, temperature)
-  if not isinstance(likelihood, (glm.GaussianRegression, glm.LogisticRegression)):
+  lik_is_spec = isinstance(likelihood, (glm.GaussianRegression, glm.LogisticRegression))
+  prior_is_spec = isinstance(prior, (glm.FlatPrior, glm.GaussianPrior, glm.InvSigmaPrior))
+  if not lik_is_spec and not prior_is_spec and callable(likelihood) and callable(prior) \
+      and not isinstance(likelihood, glm._Spec) and not isinstance(prior, glm._Spec):
+    # the reference's own calling convention: plain Python callables, recognised as one
+    # of the closed forms on first use (glm.from_callable) or rejected there
+    return _ProbedPotentialFn(prior, likelihood, temperature, path or DEFAULT_PATH)
+  if not lik_is_spec:
     raise TypeError(
         "likelihood must be a jax_sgmc_b200.glm / jax_sgmc_b200.nn specification "
-        "(GaussianRegression, LogisticRegression, MLPClassifier); arbitrary callables "
-        "need the JAX route, see INTEGRATION.md")
-  if not isinstance(prior, (glm.FlatPrior, glm.GaussianPrior, glm.InvSigmaPrior)):
+        "(GaussianRegression, LogisticRegression, MLPClassifier) or, together with the "
+        "prior, a reference-style callable of a recognised closed form; arbitrary "
+        "callables need the JAX route, see INTEGRATION.md")
+  if not prior_is_spec:
     raise TypeError("prior must be a jax_sgmc_b200.glm prior specification")
   return _PotentialFn(prior, likelihood, temperature, path or DEFAULT_PATH)
 

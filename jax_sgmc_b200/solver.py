@@ -230,16 +230,19 @@ class MHState:
 
 
 def _mh_solver(kind, integrator_fn, full_potential_fn, full_data_map, mass_adaption):
-  if mass_adaption is not None:
-    raise NotImplementedError("adaption.mass_matrix is outside this path")
+  init_mass = update_mass = get_mass = None
+  if mass_adaption is not None:                                       # :322-323 / :459-460
+    init_mass, update_mass, get_mass = mass_adaption
   init_integrator, update_integrator, get_integrator = integrator_fn
   init_full_data, full_data_map_fn, _ = full_data_map
 
   def init(init_sample, key=None, initial_mass=None, full_data_kwargs: dict = None,
            **kwargs) -> MHState:
-    del initial_mass
     sample = _as_chain_tree(init_sample)
     C = sample.n_chains
+    mass_state = init_mass(sample, initial_mass) if init_mass else None   # :330-335 / :486-489
+    if mass_state is not None and kind == "amagold":
+      kwargs["mass"] = get_mass(mass_state)        # the initial momentum draw uses it (:353)
     full_data_state = init_full_data(**(full_data_kwargs or {}))
     potential, (full_data_state, model_state) = full_potential_fn(    # :474-478 / :341-345
         sample, full_data_state, full_data_map_fn, state=kwargs.get("init_model_state"))
@@ -249,8 +252,10 @@ def _mh_solver(kind, integrator_fn, full_potential_fn, full_data_map, mass_adapt
       key = np.tile(key, (C, 1))
     ks = ops.split(DeviceArray.from_numpy(key), 2).numpy()            # :483 / :349
     integrator_state = init_integrator(sample, key=ks[:, 0], **kwargs)
-    return MHState(integrator_state, potential, full_data_state, KeyState(ks[:, 1]),
-                   C, sample.n_params)
+    state = MHState(integrator_state, potential, full_data_state, KeyState(ks[:, 1]),
+                    C, sample.n_params)
+    state.mass_state = mass_state
+    return state
 
   def update(state: MHState, schedule):
     old = state.integrator_state
@@ -258,7 +263,8 @@ def _mh_solver(kind, integrator_fn, full_potential_fn, full_data_map, mass_adapt
     state.saved["theta"].copy_from(old.positions.flat)
     state.saved["momentum"].copy_from(old.momentum.flat)
     state.saved["potential"].copy_from(old.potential)
-    proposal = update_integrator(old, schedule, mass=None)            # :512-515 / :372-375
+    mass = get_mass(state.mass_state) if get_mass else None           # :503-506 / :366-369
+    proposal = update_integrator(old, schedule, mass=mass)            # :512-515 / :372-375
     new_potential, (full_data_state, _) = full_potential_fn(          # :518-522 / :378-382
         proposal.positions, state.full_data_state, full_data_map_fn,
         state=proposal.model_state)
@@ -282,6 +288,8 @@ def _mh_solver(kind, integrator_fn, full_potential_fn, full_data_map, mass_adapt
     if kind == "sggmc":                                               # :551-552
       proposal.kinetic_energy_start.zero_()
       proposal.kinetic_energy_end.zero_()
+    if update_mass:          # adapt the mass on the accepted sample (:552-553 / :409-410)
+      state.mass_state = update_mass(state.mass_state, proposal.positions)
     state.integrator_state = proposal       # data_state / key of the proposal (:547-550)
     state.full_data_state = full_data_state
     state.step_size = float(schedule.step_size)

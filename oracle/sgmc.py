@@ -515,16 +515,20 @@ def obabo_o_step(p, xi, step_size, temperature, friction, sqrt_m):
 
 def obabo_integrate(state: ObaboState, grad_fn_pairs, sizes, step_size,
                     temperature=1.0, friction=1.0, mass=None,
-                    layout="original"):
+                    layout="original", mass_matrix=None):
   """``obabo.integrate`` (integrator.py:318-338; step :203-273).
 
   ``grad_fn_pairs``: one ``(grad_fn_1, grad_fn_2)`` per step -- two minibatch
-  draws and two gradient evaluations per step (:225, :243).
+  draws and two gradient evaluations per step (:225, :243).  ``mass_matrix``: an
+  adapted ``MassMatrix(inv, sqrt)`` (adaption.py:296-369; arrays broadcastable to the
+  positions) used as handed over instead of ``init_mass(mass)`` (:320-321).
   """
   P = state.theta.shape[1]
   mass = np.ones(P, F32) if mass is None else np.asarray(mass, F32)
   inv_m = (F32(1.0) / mass).astype(F32)
   sqrt_m = np.sqrt(mass).astype(F32)
+  if mass_matrix is not None:
+    inv_m, sqrt_m = (np.asarray(a, F32) for a in mass_matrix)
   eps = F32(step_size)
   theta, p, key = state.theta, state.momentum, state.key
   ke_s, ke_e = state.kinetic_energy_start, state.kinetic_energy_end
@@ -633,7 +637,7 @@ def parallel_tempering_update(state: TemperingState, grad_fn_normal,
 # ----------------------------------------------------------------------------
 
 def reversible_leapfrog_init(theta, keys=None, mass=None, sizes=None,
-                             layout="original"):
+                             layout="original", mass_matrix=None):
   """``reversible_leapfrog.init_fn`` (integrator.py:472-512): ``key, split =
   split(key)``; momentum = sqrt(m) * random_tree(split, sample); potential 0."""
   theta = np.asarray(theta, F32)
@@ -642,6 +646,8 @@ def reversible_leapfrog_init(theta, keys=None, mass=None, sizes=None,
     keys = np.tile(prng.PRNGKey(0), (C, 1))
   sizes = [P] if sizes is None else sizes
   sqrt_m = np.ones(P, F32) if mass is None else np.sqrt(np.asarray(mass, F32)).astype(F32)
+  if mass_matrix is not None:
+    sqrt_m = np.asarray(mass_matrix[1], F32)
   ks = prng.split(np.asarray(keys, np.uint32), 2, layout)
   key, sub = ks[..., 0, :], ks[..., 1, :]
   p = (sqrt_m * random_tree_flat(sub, sizes, layout)).astype(F32)
@@ -649,7 +655,8 @@ def reversible_leapfrog_init(theta, keys=None, mass=None, sizes=None,
 
 
 def reversible_leapfrog_integrate(state: LeapfrogState, grad_fns, sizes, step_size,
-                                  friction=0.25, mass=None, layout="original"):
+                                  friction=0.25, mass=None, layout="original",
+                                  mass_matrix=None):
   """``reversible_leapfrog.integrate`` (integrator.py:514-553, body :403-466).
 
   ``grad_fns``: one ``theta -> (U, ell, grad)`` per inner step (only the
@@ -661,6 +668,8 @@ def reversible_leapfrog_integrate(state: LeapfrogState, grad_fns, sizes, step_si
   mass = np.ones(P, F32) if mass is None else np.asarray(mass, F32)
   inv_m = (F32(1.0) / mass).astype(F32)
   sqrt_m = np.sqrt(mass).astype(F32)
+  if mass_matrix is not None:                                # adapted MassMatrix(inv, sqrt)
+    inv_m, sqrt_m = (np.asarray(a, F32) for a in mass_matrix)
   eps = F32(step_size)
   f = F32(friction)
   half_eps = F32(F32(0.5) * eps)
@@ -691,6 +700,47 @@ def reversible_leapfrog_integrate(state: LeapfrogState, grad_fns, sizes, step_si
     p = pn
   theta = position_update(half_eps, theta, p)                # :545-546
   return LeapfrogState(theta, p, key, energy)
+
+
+# ----------------------------------------------------------------------------
+# adaption.mass_matrix, diagonal   (adaption.py:296-369)
+# ----------------------------------------------------------------------------
+
+class MassState(NamedTuple):
+  iteration: int
+  mean: np.ndarray     # f32[C, P]
+  ssq: np.ndarray      # f32[C, P]
+  m_inv: np.ndarray    # f32[C, P]
+  m_sqrt: np.ndarray   # f32[C, P]
+
+
+def mass_matrix_init(theta, init_cov=None) -> MassState:
+  """adaption.py:319-341: zero statistics; ``m_inv = init_cov`` (ones by default),
+  ``m_sqrt = 1 / sqrt(init_cov)``."""
+  theta = np.asarray(theta, F32)
+  cov = np.ones_like(theta) if init_cov is None else \
+      np.broadcast_to(np.asarray(init_cov, F32), theta.shape).astype(F32)
+  return MassState(0, np.zeros_like(theta), np.zeros_like(theta), cov,
+                   (F32(1.0) / np.sqrt(cov)).astype(F32))
+
+
+def mass_matrix_update(state: MassState, sample, burn_in: int) -> MassState:
+  """adaption.py:343-363 (Welford); the matrix is replaced once, in iteration
+  ``burn_in`` (:310-313: ``inv = ssq / n``, ``sqrt = sqrt(n / ssq)``).  The iteration
+  counter is an int32: ``(n - 1) / n`` and ``1 / n`` are f32 true divisions."""
+  x = np.asarray(sample, F32)
+  it = state.iteration + 1
+  fi = F32(it)
+  w_old, w_new = F32(F32(it - 1) / fi), F32(F32(1.0) / fi)
+  new_mean = ((w_old * state.mean).astype(F32) + (w_new * x).astype(F32)).astype(F32)
+  ssq = (state.ssq + ((x - state.mean).astype(F32) * (x - new_mean).astype(F32)).astype(F32)
+         ).astype(F32)
+  m_inv, m_sqrt = state.m_inv, state.m_sqrt
+  if it == burn_in:
+    with np.errstate(divide="ignore", invalid="ignore"):
+      m_inv = (ssq / fi).astype(F32)
+      m_sqrt = np.sqrt((fi / ssq).astype(F32)).astype(F32)
+  return MassState(it, new_mean, ssq, m_inv, m_sqrt)
 
 
 # ----------------------------------------------------------------------------
@@ -734,11 +784,12 @@ def sggmc_init(theta, full_potential_fn, keys=None, layout="original"):
 
 
 def sggmc_update(state: MHState, grad_fn_pairs, full_potential_fn, sizes, step_size,
-                 temperature=1.0, friction=1.0, mass=None, layout="original"):
+                 temperature=1.0, friction=1.0, mass=None, layout="original",
+                 mass_matrix=None):
   """solver.sggmc.update (:502-566)."""
   old = state.integrator_state
   prop = obabo_integrate(old, grad_fn_pairs, sizes, step_size, temperature, friction,
-                         mass, layout)
+                         mass, layout, mass_matrix)
   U_new = full_potential_fn(prop.theta)
   accept, key, _, ratio = mh_decision("sggmc", state.potential, U_new,
                                       prop.kinetic_energy_start, prop.kinetic_energy_end,
@@ -753,24 +804,25 @@ def sggmc_update(state: MHState, grad_fn_pairs, full_potential_fn, sizes, step_s
 
 
 def amagold_init(theta, full_potential_fn, keys=None, mass=None, sizes=None,
-                 layout="original"):
+                 layout="original", mass_matrix=None):
   """solver.amagold.init (:323-362)."""
   theta = np.asarray(theta, F32)
   C = theta.shape[0]
   if keys is None:
     keys = np.tile(prng.PRNGKey(0), (C, 1))
   ks = prng.split(np.asarray(keys, np.uint32), 2, layout)
-  return MHState(reversible_leapfrog_init(theta, ks[..., 0, :], mass, sizes, layout),
+  return MHState(reversible_leapfrog_init(theta, ks[..., 0, :], mass, sizes, layout,
+                                          mass_matrix),
                  full_potential_fn(theta), ks[..., 1, :], np.zeros(C, F32))
 
 
 def amagold_update(state: MHState, grad_fns, full_potential_fn, sizes, step_size,
-                   friction=0.25, mass=None, layout="original"):
+                   friction=0.25, mass=None, layout="original", mass_matrix=None):
   """solver.amagold.update (:364-424): on rejection the old state is kept with
   the momentum negated (direction = -1, :392, :399)."""
   old = state.integrator_state
   prop = reversible_leapfrog_integrate(old, grad_fns, sizes, step_size, friction, mass,
-                                       layout)
+                                       layout, mass_matrix)
   U_new = full_potential_fn(prop.theta)
   accept, key, _, ratio = mh_decision("amagold", state.potential, U_new, None,
                                       prop.potential, 1.0, state.key, layout)

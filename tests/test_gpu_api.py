@@ -94,6 +94,59 @@ def test_quickstart_sgld_posterior(gpu):
   assert abs(sigma - 0.5) < 0.1, sigma
 
 
+def test_reference_callables_run_the_quickstart_unmodified(gpu):
+  """The quickstart's own model code (examples/quickstart.md:158-173: plain likelihood /
+  prior callables written against jax.numpy and jax.scipy.stats) handed to
+  minibatch_potential as the reference does: recognised on first use as the gaussian
+  regression + 1/sigma prior, then the very same samples as the specification objects --
+  also with has_state=True (potential.py:131-137) for a likelihood that keeps its state."""
+  import sys
+  from jax_sgmc_b200 import alias, compat, data, glm, potential
+  shimmed = compat.install_jax_shim()
+  import jax.numpy as jnp
+  from jax.scipy.stats import norm
+
+  def model(sample, observations):
+    weights = sample["w"]
+    predictors = observations["x"]
+    return jnp.dot(predictors, weights)
+
+  def likelihood(sample, observations):
+    sigma = jnp.exp(sample["log_sigma"])
+    y = observations["y"]
+    y_pred = model(sample, observations)
+    return norm.logpdf(y - y_pred, scale=sigma)
+
+  def prior(sample):
+    return 1 / jnp.exp(sample["log_sigma"])
+
+  x, y, _ = odata.quickstart_dataset()
+  init = {"w": np.zeros((4, 1), np.float32), "log_sigma": np.array(2.5, np.float32)}
+  out = []
+  for pot in (potential.minibatch_potential(prior=prior, likelihood=likelihood, strategy="vmap"),
+              potential.minibatch_potential(prior=glm.InvSigmaPrior("log_sigma"),
+                                            likelihood=glm.GaussianRegression(
+                                                weights="w", log_sigma="log_sigma"),
+                                            strategy="vmap", has_state=True)):
+    loader = data.NumpyDataLoader(x=x, y=y)
+    run = alias.sgld(pot, loader, cache_size=64, batch_size=10, first_step_size=0.05,
+                     last_step_size=0.001, burn_in=100, accepted_samples=50,
+                     rms_prop=True, progress_bar=False)
+    out.append(run(init, iterations=300)[0]["samples"])
+  assert np.array_equal(out[0]["variables"]["w"], out[1]["variables"]["w"])
+  assert np.array_equal(out[0]["variables"]["log_sigma"], out[1]["variables"]["log_sigma"])
+  assert np.array_equal(out[0]["likelihood"], out[1]["likelihood"])
+  bad = potential.minibatch_potential(prior=prior, likelihood=lambda s, o: jnp.sum(o["x"]) * 0.0,
+                                      strategy="vmap")
+  run = alias.sgld(bad, data.NumpyDataLoader(x=x, y=y), cache_size=8, batch_size=10,
+                   accepted_samples=5, progress_bar=False)
+  with pytest.raises(TypeError):
+    run(init, iterations=10)
+  if shimmed:
+    for name in [m for m in sys.modules if m == "jax" or m.startswith("jax.")]:
+      del sys.modules[name]
+
+
 def test_langevin_api_matches_oracle_trajectory(gpu):
   """integrator.langevin_diffusion + adaption.rms_prop + solver.sgmc driven
   through the API for 300 steps == the oracle, same keys, same minibatches."""

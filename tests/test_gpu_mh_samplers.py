@@ -93,16 +93,105 @@ def _logistic_problem(C, d, N, seed=0):
   return X, y, theta
 
 
+def test_mass_matrix_update_matches_oracle(gpu):
+  """adaption.mass_matrix(diagonal=True) (adaption.py:296-369): Welford statistics of
+  every chain and the one-off matrix update in iteration burn_in, bit for bit against
+  the oracle; get() hands out the same MassMatrix object every time."""
+  from jax_sgmc_b200 import adaption
+  from jax_sgmc_b200.tree_util import ChainTree
+  rng = np.random.default_rng(11)
+  C, burn_in = 5, 7
+  tmpl = {"b": np.zeros((), np.float32), "w": np.zeros((3, 4), np.float32)}
+  init, update, get = adaption.mass_matrix(burn_in=burn_in)
+  first = rng.standard_normal((C, 13)).astype(np.float32)
+  tree = ChainTree.from_trees([tmpl] * C)
+  tree.flat.copy_from_host(first)
+  cov = (np.abs(rng.standard_normal(13)) + 0.5).astype(np.float32)
+  state = init(tree, {"b": cov[:1].reshape(()), "w": cov[1:].reshape(3, 4)})
+  want = osgmc.mass_matrix_init(first, cov)
+  m0 = get(state)
+  assert np.array_equal(m0.inv.tensor.flat.numpy(), want.m_inv)
+  assert np.array_equal(m0.sqrt.tensor.flat.numpy().view(np.uint32), want.m_sqrt.view(np.uint32))
+  for it in range(1, 11):
+    x = (rng.standard_normal((C, 13)) * (1 + it)).astype(np.float32)
+    tree.flat.copy_from_host(x)
+    state = update(state, tree)
+    want = osgmc.mass_matrix_update(want, x, burn_in)
+    assert get(state) is m0
+    for got, ref in ((state.mean, want.mean), (state.ssq, want.ssq), (state.m_inv, want.m_inv),
+                     (state.m_sqrt, want.m_sqrt)):
+      assert np.array_equal(got.numpy().view(np.uint32), ref.view(np.uint32)), it
+    assert (it < burn_in) == np.array_equal(want.m_inv, np.broadcast_to(cov, (C, 13)))
+  with pytest.raises(NotImplementedError):
+    adaption.mass_matrix(diagonal=False)
+
+
+def test_adapted_mass_kernels_match_oracle(gpu):
+  """The OBABO passes and the reversible-leapfrog step with a per-chain MassMatrix(inv,
+  sqrt): theta, p, keys bit-exact against the oracle run with the same matrices."""
+  from jax_sgmc_b200 import ops
+  from jax_sgmc_b200.device import DeviceArray as DA
+  rng = np.random.default_rng(5)
+  sizes = [3, 20, 41]
+  C, P, steps = 4, sum(sizes), 2
+  theta = rng.standard_normal((C, P)).astype(np.float32)
+  inv = (np.abs(rng.standard_normal((C, P))) + 0.3).astype(np.float32)
+  sqrt = (np.abs(rng.standard_normal((C, P))) + 0.3).astype(np.float32)   # independent arrays
+  g = [(rng.standard_normal((C, P)) * 2).astype(np.float32) for _ in range(2 * steps)]
+  eps, T, fr = 0.011, 1.3, 0.7
+  d_inv, d_sqrt = DA.from_numpy(inv), DA.from_numpy(sqrt)
+  # ---- OBABO
+  st = osgmc.obabo_init(theta, _keys(C, 3))
+  st = st._replace(momentum=rng.standard_normal((C, P)).astype(np.float32))
+  pairs = [(lambda th, a=g[2 * s]: (np.zeros(C, np.float32), None, a),
+            lambda th, b=g[2 * s + 1]: (np.zeros(C, np.float32), None, b)) for s in range(steps)]
+  want = osgmc.obabo_integrate(st, pairs, sizes, eps, T, fr, mass_matrix=(inv, sqrt))
+  d_t, d_p = DA.from_numpy(theta), DA.from_numpy(st.momentum)
+  ke0, ke1 = DA.zeros((C,)), DA.zeros((C,))
+  kk = [DA.from_numpy(st.key), DA((C, 2), np.uint32)]
+  for s in range(steps):
+    ops.obabo_pass_a(d_t, d_p, DA.from_numpy(g[2 * s]), ke0, kk[s % 2], kk[(s + 1) % 2], sizes,
+                     eps, T, fr, (d_inv, d_sqrt))
+    ops.obabo_pass_b(d_p, DA.from_numpy(g[2 * s + 1]), ke1, kk[s % 2], sizes, eps, T, fr,
+                     (d_inv, d_sqrt))
+  assert np.array_equal(kk[steps % 2].numpy(), want.key)
+  assert np.array_equal(d_t.numpy().view(np.uint32), want.theta.view(np.uint32))
+  assert np.array_equal(d_p.numpy().view(np.uint32), want.momentum.view(np.uint32))
+  np.testing.assert_allclose(ke0.numpy(), want.kinetic_energy_start, rtol=1e-5)
+  np.testing.assert_allclose(ke1.numpy(), want.kinetic_energy_end, rtol=1e-5)
+  # ---- reversible leapfrog
+  ls = osgmc.reversible_leapfrog_init(theta, _keys(C, 9), None, sizes, mass_matrix=(inv, sqrt))
+  want = osgmc.reversible_leapfrog_integrate(
+      ls, [lambda th, a=a: (None, None, a) for a in g[:steps]], sizes, eps, 0.25,
+      mass_matrix=(inv, sqrt))
+  half = np.float32(0.5) * np.float32(eps)
+  th0 = (ls.theta + (half * (inv * ls.momentum).astype(np.float32)).astype(np.float32)
+         ).astype(np.float32)
+  d_t, d_p, d_e = DA.from_numpy(th0), DA.from_numpy(ls.momentum), DA.zeros((C,))
+  kk = [DA.from_numpy(ls.key), DA((C, 2), np.uint32)]
+  for s in range(steps):
+    ops.revleapfrog_step(d_t, d_p, DA.from_numpy(g[s]), d_e, kk[s % 2], kk[(s + 1) % 2], sizes,
+                         eps, 0.25, (d_inv, d_sqrt), last=(s == steps - 1))
+  assert np.array_equal(kk[steps % 2].numpy(), want.key)
+  assert np.array_equal(d_p.numpy().view(np.uint32), want.momentum.view(np.uint32))
+  assert np.array_equal(d_t.numpy().view(np.uint32), want.theta.view(np.uint32))
+  np.testing.assert_allclose(d_e.numpy(), want.potential, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("adapt_mass", [False, True])
 @pytest.mark.parametrize("kind", ["sggmc", "amagold"])
-def test_mh_solver_trajectory_matches_oracle(gpu, kind):
+def test_mh_solver_trajectory_matches_oracle(gpu, kind, adapt_mass):
   """Six MH iterations of solver.sggmc / solver.amagold driven through the
   operator API against the oracle: identical accept/reject pattern, identical
-  keys, samples within 1e-5 (fp32 SIMT gradients, different reduction order)."""
-  from jax_sgmc_b200 import data, glm, integrator, potential, scheduler, solver
+  keys, samples within 1e-5 (fp32 SIMT gradients, different reduction order).
+  ``adapt_mass``: with ``mass_adaption=adaption.mass_matrix(burn_in=3)`` -- the matrix
+  changes after the third iteration (solver.py:503-506, :552-553 / :366-369, :409-410)."""
+  from jax_sgmc_b200 import adaption, data, glm, integrator, potential, scheduler, solver
   from jax_sgmc_b200 import ops
   ops.set_option(ops.OPT_EXACT_UPDATE_MATH, 1)
   try:
     C, d, N, n, steps, iters = 6, 8, 60, 12, 3, 6
+    adapt = adaption.mass_matrix(burn_in=3) if adapt_mass else None
     X, y, theta = _logistic_problem(C, d, N)
     loader = data.DeviceNumpyDataLoader(x=X, y=y)
     prior, lik = glm.GaussianPrior(3.0), glm.LogisticRegression()
@@ -113,10 +202,10 @@ def test_mh_solver_trajectory_matches_oracle(gpu, kind):
     eps, fr = 0.02, (1.0 if kind == "sggmc" else 0.25)
     if kind == "sggmc":
       integ = integrator.obabo(pot, random_data, steps, fr)
-      init, update, get = solver.sggmc(integ, full, full_map)
+      init, update, get = solver.sggmc(integ, full, full_map, mass_adaption=adapt)
     else:
       integ = integrator.reversible_leapfrog(pot, random_data, steps, fr)
-      init, update, get = solver.amagold(integ, full, full_map)
+      init, update, get = solver.amagold(integ, full, full_map, mass_adaption=adapt)
     keys = _keys(C, 20)
     state = init([{"w": t} for t in theta], key=keys)
     sched = scheduler.schedule(step_size=np.float32(eps), temperature=np.float32(1.0),
@@ -135,20 +224,26 @@ def test_mh_solver_trajectory_matches_oracle(gpu, kind):
       dkey, idx = odata.device_draw(dkey, n, N)
       return lambda th, idx=idx: o_pot(th, (X[idx], y[idx]), N)
 
+    o_mass = osgmc.mass_matrix_init(theta) if adapt_mass else None
+    mm = lambda: (o_mass.m_inv, o_mass.m_sqrt) if adapt_mass else None
     if kind == "sggmc":
       o_state = osgmc.sggmc_init(theta, o_full, keys)
     else:
-      o_state = osgmc.amagold_init(theta, o_full, keys, sizes=[d])
+      o_state = osgmc.amagold_init(theta, o_full, keys, sizes=[d], mass_matrix=mm())
     np.testing.assert_allclose(state.potential.numpy(), o_state.potential, rtol=1e-5)
     pattern = []
     for it in range(iters):
       state, stats = update(state, sched)
       if kind == "sggmc":
         pairs = [(next_grad_fn(), next_grad_fn()) for _ in range(steps)]
-        o_state, acc = osgmc.sggmc_update(o_state, pairs, o_full, [d], eps, 1.0, fr)
+        o_state, acc = osgmc.sggmc_update(o_state, pairs, o_full, [d], eps, 1.0, fr,
+                                          mass_matrix=mm())
       else:
         fns = [next_grad_fn() for _ in range(steps)]
-        o_state, acc = osgmc.amagold_update(o_state, fns, o_full, [d], eps, fr)
+        o_state, acc = osgmc.amagold_update(o_state, fns, o_full, [d], eps, fr,
+                                            mass_matrix=mm())
+      if adapt_mass:
+        o_mass = osgmc.mass_matrix_update(o_mass, o_state.integrator_state.theta, 3)
       pattern.append(acc)
       assert np.array_equal(state.reject.numpy() == 0, acc), f"iteration {it}"
       assert np.array_equal(state.key.current.numpy(), o_state.key)
@@ -160,7 +255,14 @@ def test_mh_solver_trajectory_matches_oracle(gpu, kind):
       np.testing.assert_allclose(stats["acceptance_ratio"].numpy(),
                                  o_state.acceptance_ratio, rtol=1e-3, atol=1e-6)
     pattern = np.array(pattern)
-    assert pattern.any() and not pattern.all(), "want both accepts and rejects in the test"
+    assert pattern.any()
+    if not adapt_mass:
+      assert not pattern.all(), "want both accepts and rejects in the test"
+    if adapt_mass:
+      assert state.mass_state.iteration == iters
+      assert not np.allclose(state.mass_state.m_inv.numpy(), 1.0)
+      np.testing.assert_allclose(state.mass_state.m_inv.numpy(), o_mass.m_inv, rtol=2e-4,
+                                 atol=1e-9)
   finally:
     ops.set_option(ops.OPT_EXACT_UPDATE_MATH, 0)
 

@@ -109,7 +109,7 @@ def test_potential_rejects_unknown_callables_and_strategies():
   with pytest.raises(NotImplementedError):
     potential.minibatch_potential(pr, lk, strategy="bogus")      # potential.py:156
   with pytest.raises(TypeError):
-    potential.minibatch_potential(pr, lambda s, o: 0.0)
+    potential.minibatch_potential(pr, lambda s, o: 0.0)      # a spec mixed with a callable
   with pytest.raises(AssertionError):
     potential.full_potential(pr, lk, strategy="pmap")            # potential.py:254
   with pytest.raises(NotImplementedError):
@@ -301,3 +301,63 @@ def test_only_tagged_static_schedulers_are_precomputed():
   init, _, get = scheduler.init_scheduler(step_size=scheduler.adaptive_step_size(),
                                           progress_bar=False)
   assert get.precompute(init(4)[0], 4) is None
+
+
+def test_reference_style_callables_are_recognised_as_closed_forms():
+  """potential.py:94-127 takes likelihood(sample, observation) / prior(sample) callables.
+  glm.from_callable evaluates them on a few host points and names the closed form the
+  fused kernels run: the quickstart model verbatim (examples/quickstart.md:158-173, with
+  the NumPy-backed jax shim), a logistic regression with bias and a gaussian prior on the
+  weights only; anything else is rejected."""
+  from jax_sgmc_b200 import compat, glm
+  shimmed = compat.install_jax_shim()
+  import jax.numpy as jnp
+  from jax.scipy.stats import norm
+
+  def model(sample, observations):
+    weights = sample["w"]
+    predictors = observations["x"]
+    return jnp.dot(predictors, weights)
+
+  def likelihood(sample, observations):
+    sigma = jnp.exp(sample["log_sigma"])
+    y = observations["y"]
+    y_pred = model(sample, observations)
+    return norm.logpdf(y - y_pred, scale=sigma)
+
+  def prior(sample):
+    return 1 / jnp.exp(sample["log_sigma"])
+
+  lik, pr = glm.from_callable(likelihood, prior,
+                              {"log_sigma": np.zeros(()), "w": np.zeros((4, 1))},
+                              {"x": np.zeros(4), "y": np.zeros(1)})
+  assert isinstance(lik, glm.GaussianRegression)
+  assert (lik.x, lik.y, lik.weights, lik.aux) == ("x", "y", "w", "log_sigma")
+  assert isinstance(pr, glm.InvSigmaPrior) and pr.leaf == "log_sigma"
+
+  def logistic(s, o):
+    z = jnp.dot(o["feat"], s["beta"]) + s["b0"]
+    p = 1 / (1 + jnp.exp(-z))
+    return o["lab"] * jnp.log(p) + (1 - o["lab"]) * jnp.log(1 - p)
+
+  lik, pr = glm.from_callable(logistic, lambda s: -0.5 * jnp.sum(s["beta"] ** 2) / 9.0,
+                              {"b0": np.zeros(()), "beta": np.zeros(7)},
+                              {"feat": np.zeros(7), "lab": np.zeros(())})
+  assert isinstance(lik, glm.LogisticRegression)
+  assert (lik.x, lik.y, lik.weights, lik.aux) == ("feat", "lab", "beta", "b0")
+  assert isinstance(pr, glm.GaussianPrior) and abs(pr.scale - 3.0) < 1e-9
+  assert pr.leaves == ["beta"]
+  lik, pr = glm.from_callable(lambda s, o: logistic({**s, "b0": 0.0}, o), lambda s: 0.0,
+                              {"beta": np.zeros(7)}, {"feat": np.zeros(7), "lab": np.zeros(())})
+  assert lik.aux is None and isinstance(pr, glm.FlatPrior)
+  with pytest.raises(TypeError):
+    glm.from_callable(lambda s, o: jnp.sum(jnp.tanh(o["feat"] * s["beta"])), lambda s: 0.0,
+                      {"beta": np.zeros(7)}, {"feat": np.zeros(7), "lab": np.zeros(())})
+  with pytest.raises(TypeError):
+    glm.from_callable(logistic, lambda s: -jnp.sum(jnp.abs(s["beta"])),
+                      {"b0": np.zeros(()), "beta": np.zeros(7)},
+                      {"feat": np.zeros(7), "lab": np.zeros(())})
+  if shimmed:
+    import sys
+    for name in [m for m in sys.modules if m == "jax" or m.startswith("jax.")]:
+      del sys.modules[name]
