@@ -8,7 +8,8 @@
 namespace sgmc {
 
 // theta' from (theta, g, v, xi).  RMS: v is updated in place.  FAST: the
-// preconditioner uses the SFU approximations + FMA contraction (<= 2 ulp);
+// preconditioner uses the SFU approximations (flush-to-zero forms: one MUFU each, no
+// denormal fix-up code; v >= 0 and lmbd + sqrt(v) >= lmbd > 0) + FMA contraction (<= 2 ulp);
 // otherwise every operation is a separately rounded IEEE op (oracle order).
 template <bool RMS, bool FAST>
 __device__ __forceinline__ float sgld_one(float t, float g, float& vv, float xi, float ns,
@@ -20,10 +21,10 @@ __device__ __forceinline__ float sgld_one(float t, float g, float& vv, float xi,
   if (RMS && FAST) {
     vv = fmaf(alpha, vv, one_m_alpha * (g * g));
     float s, G, S;
-    asm("sqrt.approx.f32 %0, %1;" : "=f"(s) : "f"(vv));
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(s) : "f"(vv));
     const float den = lmbd + s;
-    asm("rcp.approx.f32 %0, %1;" : "=f"(G) : "f"(den));
-    asm("rsqrt.approx.f32 %0, %1;" : "=f"(S) : "f"(den));   // sqrt(1/den)
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(G) : "f"(den));
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(S) : "f"(den));   // sqrt(1/den)
     delta = fmaf(S, sn, G * sg);
   } else if (RMS) {
     vv = __fadd_rn(__fmul_rn(alpha, vv), __fmul_rn(one_m_alpha, __fmul_rn(g, g)));

@@ -15,6 +15,7 @@
 #include "noise_pass.cuh"
 #include "sgld_math.cuh"
 #include "sgld_split.cuh"
+#include "tc_ptx.cuh"
 
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
@@ -753,28 +754,64 @@ k_sgld_apply_split(const SgldSplitOp<RMS, FAST, FMT> op, const float* __restrict
   const float s = FMT == 1 ? __ldg(op.scale + c) : 1.0f;
   const uint64_t keep = l2_policy_evict_last(), drop = l2_policy_evict_first();
   float sum = 0.f, amax = 0.f;
+  const uint32_t e0 = t * 256u;
+  if (e0 + 256u <= (uint32_t)P && e0 >= op.prior_lo && e0 + 256u <= op.prior_hi &&
+      op.prior_coef != 0.f && op.grad_rw == nullptr) {
+    // the common tile: whole, inside the prior range -- all eight loads first, no
+    // per-element range tests
+    const int64_t i0 = c * P + e0 + (uint32_t)lane * 4u, i1 = i0 + 128;
+    const float4 th0 = ld4_hint(op.theta, i0, keep), th1 = ld4_hint(op.theta, i1, keep);
+    float4 g0 = ld4_hint(op.grad, i0, drop), g1 = ld4_hint(op.grad, i1, drop);
+    const float4 x0 = ld4_hint(xi, i0, drop), x1 = ld4_hint(xi, i1, drop);
+    float4 v0 = RMS ? ld4_hint(op.v, i0, keep) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 v1 = RMS ? ld4_hint(op.v, i1, keep) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float pc = op.prior_coef;
+    g0.x = fmaf(th0.x, pc, g0.x); g0.y = fmaf(th0.y, pc, g0.y);
+    g0.z = fmaf(th0.z, pc, g0.z); g0.w = fmaf(th0.w, pc, g0.w);
+    g1.x = fmaf(th1.x, pc, g1.x); g1.y = fmaf(th1.y, pc, g1.y);
+    g1.z = fmaf(th1.z, pc, g1.z); g1.w = fmaf(th1.w, pc, g1.w);
+    float4 o0, o1;
+    o0.x = op.one(th0.x, g0.x, v0.x, x0.x, ns); o0.y = op.one(th0.y, g0.y, v0.y, x0.y, ns);
+    o0.z = op.one(th0.z, g0.z, v0.z, x0.z, ns); o0.w = op.one(th0.w, g0.w, v0.w, x0.w, ns);
+    o1.x = op.one(th1.x, g1.x, v1.x, x1.x, ns); o1.y = op.one(th1.y, g1.y, v1.y, x1.y, ns);
+    o1.z = op.one(th1.z, g1.z, v1.z, x1.z, ns); o1.w = op.one(th1.w, g1.w, v1.w, x1.w, ns);
+    st4_hint(op.theta, i0, o0, keep);
+    st4_hint(op.theta, i1, o1, keep);
+    if (RMS) {
+      st4_hint(op.v, i0, v0, keep);
+      st4_hint(op.v, i1, v1, keep);
+    }
+    op.template emit4<true>(i0, o0, s, keep);
+    op.template emit4<true>(i1, o1, s, keep);
+    amax = fmaxf(fmaxf(fmaxf(fabsf(o0.x), fabsf(o0.y)), fmaxf(fabsf(o0.z), fabsf(o0.w))),
+                 fmaxf(fmaxf(fabsf(o1.x), fabsf(o1.y)), fmaxf(fabsf(o1.z), fabsf(o1.w))));
+    // same association as sq4 on both halves (the sums feed the prior value bit for bit)
+    sum = ((o0.x * o0.x + o0.y * o0.y) + (o0.z * o0.z + o0.w * o0.w)) +
+          ((o1.x * o1.x + o1.y * o1.y) + (o1.z * o1.z + o1.w * o1.w));
+  } else {
 #pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    const uint32_t e = t * 256u + (uint32_t)h * 128u + (uint32_t)lane * 4u;
-    if (e < (uint32_t)P) {                       // P % 8 == 0: whole float4 or nothing
-      const int64_t i = c * P + e;
-      const float4 th = ld4_hint(op.theta, i, keep);
-      float4 g = ld4_hint(op.grad, i, drop);
-      const float4 x = ld4_hint(xi, i, drop);
-      float4 vv = RMS ? ld4_hint(op.v, i, keep) : make_float4(0.f, 0.f, 0.f, 0.f);
-      if (op.prior_coef != 0.f) {
-        g = op.with_prior(g, th, e);
-        if (op.grad_rw) st4(op.grad_rw, i, g);
+    for (int h = 0; h < 2; ++h) {
+      const uint32_t e = t * 256u + (uint32_t)h * 128u + (uint32_t)lane * 4u;
+      if (e < (uint32_t)P) {                       // P % 8 == 0: whole float4 or nothing
+        const int64_t i = c * P + e;
+        const float4 th = ld4_hint(op.theta, i, keep);
+        float4 g = ld4_hint(op.grad, i, drop);
+        const float4 x = ld4_hint(xi, i, drop);
+        float4 vv = RMS ? ld4_hint(op.v, i, keep) : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (op.prior_coef != 0.f) {
+          g = op.with_prior(g, th, e);
+          if (op.grad_rw) st4(op.grad_rw, i, g);
+        }
+        float4 o;
+        o.x = op.one(th.x, g.x, vv.x, x.x, ns);
+        o.y = op.one(th.y, g.y, vv.y, x.y, ns);
+        o.z = op.one(th.z, g.z, vv.z, x.z, ns);
+        o.w = op.one(th.w, g.w, vv.w, x.w, ns);
+        st4_hint(op.theta, i, o, keep);
+        if (RMS) st4_hint(op.v, i, vv, keep);
+        op.template emit4<true>(i, o, s, keep);
+        sum += op.sq4(o, e, amax);
       }
-      float4 o;
-      o.x = op.one(th.x, g.x, vv.x, x.x, ns);
-      o.y = op.one(th.y, g.y, vv.y, x.y, ns);
-      o.z = op.one(th.z, g.z, vv.z, x.z, ns);
-      o.w = op.one(th.w, g.w, vv.w, x.w, ns);
-      st4_hint(op.theta, i, o, keep);
-      if (RMS) st4_hint(op.v, i, vv, keep);
-      op.template emit4<true>(i, o, s, keep);
-      sum += op.sq4(o, e, amax);
     }
   }
 #pragma unroll
@@ -783,6 +820,197 @@ k_sgld_apply_split(const SgldSplitOp<RMS, FAST, FMT> op, const float* __restrict
     amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, k));
   }
   if (lane == 0) op.reduce2(c, t, sum, amax);
+}
+
+// The same update as a STREAMING kernel: two persistent CTAs per SM, a producer thread keeps
+// kStreamStages units (2048 consecutive parameters: theta, grad, xi, v = 32 KB) in flight as
+// bulk async copies into shared memory, eight compute warps work through the units (a warp
+// owns the same 256 elements, in the same order, as in k_sgld_apply_split: identical bits),
+// and the four outputs leave through double-buffered shared memory as bulk stores.  The bytes
+// in flight per SM (128 KB) no longer depend on registers or occupancy.  MEASURED (C2 step,
+// B200): 21.4 us against 20.5 us of the one-shot kernel above (one CTA per SM with three
+// stages: 26.7 us -- eight compute warps cannot hide their own instruction latencies), i.e.
+// no gain: in steady state the update moves 117 MB (theta, grad, xi, v in; theta, v and the
+// fp16 hi / lo operand form out), 75 MB of them through DRAM (grad and xi hit the L2), at
+// 5.7 TB/s = 0.87 of the measured copy bandwidth -- the kernel is at the roof of the bytes it
+// moves, not of the 83.9 MB the algorithm needs.  Kept as an opt-in A/B
+// (SGMC_OPT_STREAM_UPDATE); needs P % 256 == 0, the prior on the whole sample (or none) and
+// no gradient write-back.
+constexpr int kStreamUnit = 2048;                  // parameters per unit: 8 warps x 256
+constexpr int kStreamStages = 2;                  // per CTA; two CTAs share an SM
+constexpr int kStreamInBytes = 4 * kStreamUnit * 4;            // theta, grad, xi, v
+constexpr int kStreamOutBytes = 2 * kStreamUnit * 4 + 2 * kStreamUnit * 2;   // theta, v, hi, lo
+constexpr int kStreamSmem = kStreamStages * kStreamInBytes + 2 * kStreamOutBytes + 128;
+constexpr int kStreamThreads = 256 + 32;
+
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes,
+                                          uint64_t* bar, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint "
+      "[%0], [%1], %2, [%3], %4;"
+      :: "r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_store(void* gdst, const void* smem_src, uint32_t bytes,
+                                           uint64_t policy) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;"
+               :: "l"(gdst), "r"(smem_u32(smem_src)), "r"(bytes), "l"(policy) : "memory");
+}
+__device__ __forceinline__ void bulk_wait_read_1() {
+  asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+}
+
+template <bool RMS, bool FAST, int FMT>
+__global__ void __launch_bounds__(kStreamThreads, 2)
+k_sgld_apply_stream(const SgldSplitOp<RMS, FAST, FMT> op, const float* __restrict__ xi, int64_t P,
+                    int64_t n_units, int64_t n_params) {
+  extern __shared__ uint8_t stream_smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(
+      (reinterpret_cast<uintptr_t>(stream_smem_raw) + 127) & ~(uintptr_t)127);
+  uint8_t* in_buf = smem;
+  uint8_t* out_buf = smem + kStreamStages * kStreamInBytes;
+  __shared__ uint64_t full_bar[kStreamStages], empty_bar[kStreamStages];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int st = 0; st < kStreamStages; ++st) {
+      mbar_init(&full_bar[st], 1);
+      mbar_init(&empty_bar[st], 8);
+    }
+    fence_barrier_init();
+  }
+  pdl_launch_dependents();
+  pdl_wait();
+  __syncthreads();
+  const uint64_t keep = l2_policy_evict_last(), drop = l2_policy_evict_first();
+  const int64_t first = blockIdx.x, stride = gridDim.x;
+  if (warp == 8) {
+    // ===== producer: bulk loads of the next units =====
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int64_t u = first; u < n_units; u += stride, ++it) {
+        const int st = it % kStreamStages;
+        if (it >= (uint32_t)kStreamStages) mbar_wait(&empty_bar[st], ((it / kStreamStages) - 1) & 1);
+        const int64_t e = u * kStreamUnit;
+        const int64_t left = n_params - e;
+        const uint32_t bytes = (uint32_t)((left < kStreamUnit ? left : kStreamUnit) * 4);
+        uint8_t* dst = in_buf + st * kStreamInBytes;
+        mbar_expect_tx(&full_bar[st], (RMS ? 4u : 3u) * bytes);
+        bulk_load(dst, op.theta + e, bytes, &full_bar[st], keep);
+        bulk_load(dst + kStreamUnit * 4, op.grad + e, bytes, &full_bar[st], drop);
+        bulk_load(dst + 2 * kStreamUnit * 4, xi + e, bytes, &full_bar[st], drop);
+        if (RMS) bulk_load(dst + 3 * kStreamUnit * 4, op.v + e, bytes, &full_bar[st], keep);
+      }
+    }
+    return;
+  }
+  // ===== compute warps =====
+  const float pc = op.prior_coef;
+  uint32_t it = 0;
+  for (int64_t u = first; u < n_units; u += stride, ++it) {
+    const int st = it % kStreamStages, ob = it & 1;
+    const int64_t wt = u * 8 + warp;                     // this warp's 256-element tile
+    const int64_t e_warp = wt * 256;
+    const bool active = e_warp < n_params;               // (the last unit may be short)
+    const uint32_t tpc = op.tiles_per_chain;
+    const int64_t c = active ? wt / tpc : 0;
+    const uint32_t t = (uint32_t)(wt - c * tpc);
+    const float ns = op.scale_for(c);
+    const float s = FMT == 1 ? __ldg(op.scale + c) : 1.0f;
+    mbar_wait(&full_bar[st], (it / kStreamStages) & 1);
+    const uint8_t* src = in_buf + st * kStreamInBytes;
+    const int l0 = warp * 256 + lane * 4, l1 = l0 + 128;            // element inside the unit
+    const float4 th0 = *reinterpret_cast<const float4*>(src + l0 * 4);
+    const float4 th1 = *reinterpret_cast<const float4*>(src + l1 * 4);
+    float4 g0 = *reinterpret_cast<const float4*>(src + kStreamUnit * 4 + l0 * 4);
+    float4 g1 = *reinterpret_cast<const float4*>(src + kStreamUnit * 4 + l1 * 4);
+    const float4 x0 = *reinterpret_cast<const float4*>(src + 2 * kStreamUnit * 4 + l0 * 4);
+    const float4 x1 = *reinterpret_cast<const float4*>(src + 2 * kStreamUnit * 4 + l1 * 4);
+    float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
+    if (RMS) {
+      v0 = *reinterpret_cast<const float4*>(src + 3 * kStreamUnit * 4 + l0 * 4);
+      v1 = *reinterpret_cast<const float4*>(src + 3 * kStreamUnit * 4 + l1 * 4);
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty_bar[st]);          // the stage can be refilled
+    if (pc != 0.f) {
+      g0.x = fmaf(th0.x, pc, g0.x); g0.y = fmaf(th0.y, pc, g0.y);
+      g0.z = fmaf(th0.z, pc, g0.z); g0.w = fmaf(th0.w, pc, g0.w);
+      g1.x = fmaf(th1.x, pc, g1.x); g1.y = fmaf(th1.y, pc, g1.y);
+      g1.z = fmaf(th1.z, pc, g1.z); g1.w = fmaf(th1.w, pc, g1.w);
+    }
+    float4 o0, o1;
+    o0.x = op.one(th0.x, g0.x, v0.x, x0.x, ns); o0.y = op.one(th0.y, g0.y, v0.y, x0.y, ns);
+    o0.z = op.one(th0.z, g0.z, v0.z, x0.z, ns); o0.w = op.one(th0.w, g0.w, v0.w, x0.w, ns);
+    o1.x = op.one(th1.x, g1.x, v1.x, x1.x, ns); o1.y = op.one(th1.y, g1.y, v1.y, x1.y, ns);
+    o1.z = op.one(th1.z, g1.z, v1.z, x1.z, ns); o1.w = op.one(th1.w, g1.w, v1.w, x1.w, ns);
+    // the output buffer of two units ago has been read by its bulk stores
+    if (threadIdx.x == 0) bulk_wait_read_1();
+    named_bar_sync(1, 256);
+    uint8_t* dst = out_buf + ob * kStreamOutBytes;
+    *reinterpret_cast<float4*>(dst + l0 * 4) = o0;
+    *reinterpret_cast<float4*>(dst + l1 * 4) = o1;
+    if (RMS) {
+      *reinterpret_cast<float4*>(dst + kStreamUnit * 4 + l0 * 4) = v0;
+      *reinterpret_cast<float4*>(dst + kStreamUnit * 4 + l1 * 4) = v1;
+    }
+    uint8_t* hi = dst + 2 * kStreamUnit * 4;
+    uint8_t* lo = hi + kStreamUnit * 2;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const float4 o = h ? o1 : o0;
+      const int l = h ? l1 : l0;
+      const float w0 = o.x * s, w1 = o.y * s, w2 = o.z * s, w3 = o.w * s;
+      if (FMT == 1) {
+        const __half2 h01 = __floats2half2_rn(w0, w1), h23 = __floats2half2_rn(w2, w3);
+        const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+        const __half2 l01 = __floats2half2_rn(w0 - f01.x, w1 - f01.y);
+        const __half2 l23 = __floats2half2_rn(w2 - f23.x, w3 - f23.y);
+        uint2 ph, pl;
+        ph.x = *reinterpret_cast<const uint32_t*>(&h01); ph.y = *reinterpret_cast<const uint32_t*>(&h23);
+        pl.x = *reinterpret_cast<const uint32_t*>(&l01); pl.y = *reinterpret_cast<const uint32_t*>(&l23);
+        *reinterpret_cast<uint2*>(hi + l * 2) = ph;
+        *reinterpret_cast<uint2*>(lo + l * 2) = pl;
+      } else {
+        const __nv_bfloat162 b01 = __floats2bfloat162_rn(w0, w1), b23 = __floats2bfloat162_rn(w2, w3);
+        uint2 pb;
+        pb.x = *reinterpret_cast<const uint32_t*>(&b01); pb.y = *reinterpret_cast<const uint32_t*>(&b23);
+        *reinterpret_cast<uint2*>(hi + l * 2) = pb;
+      }
+    }
+    fence_proxy_async();
+    named_bar_sync(2, 256);
+    if (threadIdx.x == 0) {
+      const int64_t e = u * kStreamUnit;
+      const int64_t left = n_params - e;
+      const uint32_t cnt = (uint32_t)(left < kStreamUnit ? left : kStreamUnit);
+      bulk_store(op.theta + e, dst, cnt * 4, keep);
+      if (RMS) bulk_store(op.v + e, dst + kStreamUnit * 4, cnt * 4, keep);
+      if (FMT == 1) {
+        bulk_store(reinterpret_cast<__half*>(op.th_hi) + e, hi, cnt * 2, keep);
+        bulk_store(op.th_lo + e, lo, cnt * 2, keep);
+      } else {
+        bulk_store(reinterpret_cast<__nv_bfloat16*>(op.th_hi) + e, hi, cnt * 2, keep);
+      }
+      bulk_commit_group();
+    }
+    if (active) {
+      // partial statistics of the warp's 256 elements: the association of sq4 / the
+      // one-shot kernel, so the prior value comes out bit-identical
+      float amax = fmaxf(fmaxf(fmaxf(fabsf(o0.x), fabsf(o0.y)), fmaxf(fabsf(o0.z), fabsf(o0.w))),
+                         fmaxf(fmaxf(fabsf(o1.x), fabsf(o1.y)), fmaxf(fabsf(o1.z), fabsf(o1.w))));
+      float sum = 0.f;
+      if (op.prior_hi > op.prior_lo)
+        sum = ((o0.x * o0.x + o0.y * o0.y) + (o0.z * o0.z + o0.w * o0.w)) +
+              ((o1.x * o1.x + o1.y * o1.y) + (o1.z * o1.z + o1.w * o1.w));
+#pragma unroll
+      for (int k = 16; k > 0; k >>= 1) {
+        sum += __shfl_xor_sync(0xffffffffu, sum, k);
+        amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, k));
+      }
+      if (lane == 0) op.reduce2(c, t, sum, amax);
+    }
+  }
+  if (threadIdx.x == 0) bulk_wait_all();                 // the stores have been performed
 }
 
 template <bool RMS, bool FAST, int FMT>
@@ -796,6 +1024,24 @@ static int launch_split(cudaStream_t stream, const LeafTable& tab, const uint32_
   op.tiles_per_chain = tab.tiles_per_chain;
   op.prior_lo = (uint32_t)so.prior_lo; op.prior_hi = (uint32_t)so.prior_hi;
   op.prior_coef = so.prior_coef; op.grad_rw = so.grad_rw;
+  if (so.xi != nullptr && tab.P % 256 == 0 && so.grad_rw == nullptr &&
+      (so.prior_hi == so.prior_lo || (so.prior_lo == 0 && so.prior_hi == (int)tab.P)) &&
+      (so.prior_coef != 0.f) == (so.prior_hi > so.prior_lo) && option(SGMC_OPT_STREAM_UPDATE)) {
+    auto kfn = k_sgld_apply_stream<RMS, FAST, FMT>;
+    static bool attr_set = false;
+    if (!attr_set) {
+      if (check_cuda(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          kStreamSmem), "cudaFuncSetAttribute"))
+        return 1;
+      attr_set = true;
+    }
+    const int64_t n_params = C * (int64_t)tab.P;
+    const int64_t n_units = (n_params + kStreamUnit - 1) / kStreamUnit;
+    const unsigned grid = (unsigned)std::min<int64_t>(n_units, 2 * sm_count());
+    launch_pdl(kfn, dim3(grid), dim3(kStreamThreads), (size_t)kStreamSmem, stream, op, so.xi,
+               (int64_t)tab.P, n_units, n_params);
+    return post_launch("k_sgld_apply_stream");
+  }
   if (so.xi != nullptr) {
     const int64_t n_tiles = C * (int64_t)tab.tiles_per_chain;
     launch_pdl(k_sgld_apply_split<RMS, FAST, FMT>, dim3((unsigned)((n_tiles + 7) / 8)), dim3(256),

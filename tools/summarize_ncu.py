@@ -3,6 +3,8 @@
 
   summarize_ncu.py launches <launches.csv> <out.csv>      per-kernel totals / shares
   summarize_ncu.py report <file.ncu-rep> <out.md>         key metrics per captured launch
+  summarize_ncu.py traffic <file.ncu-rep> <out.json>      dram bytes per launch of the fused
+                                                          update (bench.py's roofline.traffic)
 """
 import csv
 import subprocess
@@ -70,5 +72,29 @@ def report(src, dst):
   print(open(dst).read()[:3000])
 
 
+def traffic(src, dst):
+  import json
+  raw = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"],
+                       capture_output=True, text=True).stdout
+  rows = list(csv.reader(raw.splitlines()))
+  hdr, units, data = rows[0], rows[1], rows[2:]
+  mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+  ir, iw = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+  it = hdr.index("gpu__time_duration.sum")
+  rd = [float(r[ir].replace(",", "")) * mult[units[ir]] for r in data]
+  wr = [float(r[iw].replace(",", "")) * mult[units[iw]] for r in data]
+  out = {"source": src, "kernel": data[0][hdr.index("Kernel Name")][:80], "launches": len(data),
+         "dram_read_bytes_per_launch": sum(rd) / len(rd),
+         "dram_write_bytes_per_launch": sum(wr) / len(wr),
+         "k_noise_pass_rms_bytes_per_launch": (sum(rd) + sum(wr)) / len(rd),
+         "us_per_launch_under_ncu": sum(float(r[it].replace(",", "")) for r in data) / len(data),
+         "note": "ncu --set full --clock-control none: the caches are flushed before every "
+                 "replay pass, so all loads come from DRAM, and the launch's own stores are "
+                 "still in the write-back L2 when the measurement ends (they show up as DRAM "
+                 "writes of LATER kernels: see r02_warm_traffic_raw.csv for a warm run)"}
+  json.dump(out, open(dst, "w"), indent=1)
+  print(json.dumps(out, indent=1))
+
+
 if __name__ == "__main__":
-  {"launches": launches, "report": report}[sys.argv[1]](sys.argv[2], sys.argv[3])
+  {"launches": launches, "report": report, "traffic": traffic}[sys.argv[1]](sys.argv[2], sys.argv[3])
