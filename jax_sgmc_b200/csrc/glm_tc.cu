@@ -844,6 +844,7 @@ k_glm_tc_pair(const __grid_constant__ PairMaps maps, const PairSched sch,
   const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;
   const bool leader = rank == 0;
   const int pair = CG == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  if (threadIdx.x == 0) pair_stamp(sch.dbg && leader, pair, 7);      // kernel entry
   const int n_pairs = CG == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   const bool have2 = sch.tiles_total > sch.tiles1;
   if (warp == kPrEpiWarps && lane == 0) {
@@ -1228,16 +1229,19 @@ k_glm_tc_pair(const __grid_constant__ PairMaps maps, const PairSched sch,
           float* o = reinterpret_cast<float*>(acc);
 #pragma unroll
           for (int j = 0; j < 32; ++j) o[j] = __uint_as_float(acc[j]) * inv_scale;
-          if (p0 < gradp.prior_hi && p0 + 32 > gradp.prior_lo && row_ok) {
-            // prior gradient in the epilogue (stand-alone potential calls; the carried
-            // step folds it into the update kernel instead, see SgldSplitOp)
-            const float* tp = gradp.theta + (int64_t)row * gradp.P + p0;
+          // prior gradient in the epilogue (stand-alone potential calls; the carried step
+          // folds it into the update kernel instead, see SgldSplitOp): theta is read
+          // COALESCED, one 128-byte row segment per load (lane = column), issued before
+          // the staging buffer is written, and added to the staged tile afterwards
+          const bool with_prior = p0 < gradp.prior_hi && p0 + 32 > gradp.prior_lo;
+          float tv[32];
+          if (with_prior) {
+            const int p = p0 + lane;
+            const bool col_ok = col0 + lane < gradp.d && p >= gradp.prior_lo && p < gradp.prior_hi;
+            const float* tp = gradp.theta + (int64_t)row0 * gradp.P + p;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const int p = p0 + j;
-              if (col0 + j < gradp.d && p >= gradp.prior_lo && p < gradp.prior_hi)
-                o[j] = fmaf(__ldg(tp + j), gradp.prior_coef, o[j]);
-            }
+            for (int r = 0; r < 32; ++r)
+              tv[r] = (col_ok && row0 + r < gradp.C) ? __ldg(tp + (int64_t)r * gradp.P) : 0.f;
           }
           if (lane == 0) bulk_wait_read_all();
           __syncwarp();
@@ -1246,6 +1250,17 @@ k_glm_tc_pair(const __grid_constant__ PairMaps maps, const PairSched sch,
             const uint32_t pos = (uint32_t)lane * 128u + (uint32_t)((c16 ^ (lane & 7)) * 16);
             *reinterpret_cast<float4*>(sbuf + pos) =
                 make_float4(o[4 * c16], o[4 * c16 + 1], o[4 * c16 + 2], o[4 * c16 + 3]);
+          }
+          if (with_prior) {
+            __syncwarp();
+            // element (r, lane) of the tile lives in 16-byte chunk (lane >> 2) ^ (r & 7) of
+            // staging row r: 32 distinct words per row, no bank conflicts
+#pragma unroll
+            for (int r = 0; r < 32; ++r) {
+              float* q = reinterpret_cast<float*>(
+                  sbuf + (uint32_t)r * 128u + (uint32_t)((((lane >> 2) ^ (r & 7)) * 16) + (lane & 3) * 4));
+              *q = fmaf(tv[r], gradp.prior_coef, *q);
+            }
           }
           fence_proxy_async();
           __syncwarp();
@@ -1278,6 +1293,7 @@ k_glm_tc_pair(const __grid_constant__ PairMaps maps, const PairSched sch,
   tc_fence_before();
   if (CG == 2) cluster_sync_all(); else __syncthreads();
   if (warp == kPrEpiWarps + 1) tmem_dealloc_cg<CG>(tmem_base, 2 * BN);
+  if (threadIdx.x == 0) pair_stamp(dbg, pair, 31);                   // kernel exit
 }
 
 // ---------------------------------------------------------------------------

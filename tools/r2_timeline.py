@@ -2,7 +2,7 @@
 """Phase timeline of k_glm_tc_pair at the C2 shape (SGMC_OPT_TC_TIMELINE):
 per CTA pair, ns since the earliest kernel start of
   [0] start  [1] epilogue warps done  [2,3] GEMM2 producer: begins to wait for R /
-  R available (last GEMM2 tile)  [4,5] MMA issue of tile 0 / last tile finished
+  R available (last GEMM2 tile)  [4,5] MMA issue of tile 0 / last tile finished  [7] kernel entry  [31] kernel exit
   per tile i < 4 (slots 8+5i..12+5i): epilogue ready / accumulator full / chunks
   done / stores complete / published+finalised."""
 import ctypes as C
@@ -41,9 +41,14 @@ for path in os.environ.get("PATHS", "tc_parity,tc_throughput").split(","):
                         carry=ops.STEP_CARRY_INIT if k == 0 else ops.STEP_CARRY)
       device.synchronize()
   else:
+    from jax_sgmc_b200.device import Event, current_stream
+    e0, e1, e2 = Event(), Event(), Event()
     for rep in range(3):
+      e0.record(current_stream())
       ops.glm_potential_grad(spec, theta, X, y, idx, N, U, var, g, workspace=ws, path=path)
+      e1.record(current_stream())
       device.synchronize()
+    print(f"CUDA events around the whole op (prepare + pair kernel): {e0.elapsed_ms(e1) * 1e3:.1f} us")
   buf = (C.c_ulonglong * (80 * 32))()
   lib.sgmc_debug_pair_timeline(buf, 80 * 32)
   t = np.array(buf[:], dtype=np.int64).reshape(80, 32)
