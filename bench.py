@@ -53,6 +53,11 @@ def parse():
   p.add_argument("--resgld-systems", type=int, default=4096)
   p.add_argument("--resgld-steps", type=int, default=200)
   p.add_argument("--cpu-seconds", type=float, default=15.0)
+  p.add_argument("--resgld-overlap", type=int, default=int(os.environ.get("SGMC_RESGLD_OVERLAP", "-1")),
+                 help="1: run the ladder's exchange on a second stream under the next step's "
+                      "potential (default: on for N > 1)")
+  p.add_argument("--only-resgld", action="store_true",
+                 help="tool mode: print only the reSGLD record (not the contract line)")
   return p.parse_args()
 
 
@@ -262,7 +267,8 @@ def bench_resgld(args, ctl, nccl, stream, path):
   integ = integrator.langevin_diffusion(pot, data.random_reference_data(loader, 1, n))
   comm = nccl if world > 1 else dist.LocalCommunicator()
   temps = list(np.geomspace(1.0, 1000.0, R).astype(np.float32))
-  init, update, _ = tempering.sharded_tempering(integ, temps, comm)
+  overlap = world > 1 if args.resgld_overlap < 0 else bool(args.resgld_overlap)
+  init, update, _ = tempering.sharded_tempering(integ, temps, comm, overlap_exchange=overlap)
   from jax_sgmc_b200.tree_util import ChainTree
   from jax_sgmc_b200.device import DeviceArray as DA
   template = ChainTree.from_trees([{"w": np.zeros(d, np.float32)}])
@@ -288,6 +294,7 @@ def bench_resgld(args, ctl, nccl, stream, path):
                       "(temperature labels exchanged, one all-gather of (U, var) per step)",
           "replicas": R, "systems_per_replica": B, "features": d, "batch": n, "n_gpus": world,
           "replicas_per_gpu": R // world, "exchange": "nccl_allgather" if world > 1 else "local",
+          "overlap_exchange": overlap,
           "steps": K, "us_per_step": ms * 1e3 / K,
           "replica_chain_steps_per_s": R * B * K / (ms * 1e-3), "scaling": "strong",
           "swaps_in_last_step": swaps}
@@ -360,6 +367,12 @@ def run_b200(args):
   if path == "auto":
     # tensor-core path at fp32-level parity (fp16 hi/lo split operands)
     path = os.environ.get("SGMC_BENCH_PATH", "tc_parity")
+  if args.only_resgld:
+    rec = bench_resgld(args, ctl, nccl, stream, path)
+    if rank == 0:
+      print(json.dumps(rec), flush=True)
+    ctl.close()
+    return
   pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
   peaks = json.load(open(pk)) if os.path.exists(pk) else {}
 

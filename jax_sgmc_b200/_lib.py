@@ -93,6 +93,10 @@ PROTOTYPES = {
                          _f32, _vp, _int],
     "sgmc_sghmc_step": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, C.POINTER(_i64),
                         _int, _f32, _f32, _vp, _vp, _int, _int],
+    "sgmc_sghmc_step_noise_model": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, C.POINTER(_i64),
+                                    _int, _f32, _f32, _vp, _vp, _vp, _int, _int],
+    "sgmc_glm_fisher_diag": [_vp, C.POINTER(GlmSpec), _vp, _i64, _i64, _vp, _vp, _vp, _i64, _i64,
+                             _vp, _vp, _f32, _f32, _vp, _vp, _vp],
     "sgmc_obabo_pass_a": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64,
                           C.POINTER(_i64), _int, _f32, _f32, _f32, _vp, _int],
     "sgmc_obabo_pass_b": [_vp, _vp, _vp, _vp, _vp, _i64, C.POINTER(_i64), _int,
@@ -172,6 +176,7 @@ SPECIAL = {
     "sgmc_glm_workspace_bytes": ([_i64, _i64, _i64, _int], _sz),
     "sgmc_p2p_window_bytes": ([_int, _sz], _sz),
     "sgmc_mlp_workspace_bytes": ([C.POINTER(MlpSpec), _i64, _i64], _sz),
+    "sgmc_glm_fisher_scratch_floats": ([_i64, _i64, _i64], _sz),
 }
 
 _lib = None

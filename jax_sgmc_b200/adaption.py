@@ -12,7 +12,12 @@ by the stand-alone kernels ``sgmc_rms_prop_update`` / ``sgmc_rms_prop_get``.
 all chains on the device (``sgmc_mass_matrix_update``) and hands the integrators a
 per-chain ``MassMatrix(inv, sqrt)`` that the OBABO / reversible-leapfrog kernels read
 directly (``sgmc_*_adapted``).  The dense variants (``diagonal=False``: eigh / SVD of a
-P x P matrix per chain) and ``fisher_information`` stay outside this path and raise.
+P x P matrix per chain) stay outside this path and raise.
+
+``fisher_information(minibatch_potential, diagonal=True)`` (adaption.py:372-457): the
+empirical Fisher noise model of SGHMC for a recognised GLM potential, evaluated by
+``sgmc_glm_fisher_diag`` on the minibatch of the leapfrog step; ``get`` returns
+``NoiseModel(cb_diff_sqrt, b_sqrt)`` of per-chain ``Tensor(ndim=1)``.
 """
 from __future__ import annotations
 
@@ -129,6 +134,59 @@ def mass_matrix(diagonal: bool = True, burn_in: int = 1000):
   return init, update, get
 
 
-def fisher_information(*args, **kwargs):
-  raise NotImplementedError("adaption.fisher_information is outside the "
-                            "accelerated sampling path (SURVEY.md section 8)")
+class NoiseModel(NamedTuple):
+  """adaption.py:78-88."""
+  cb_diff_sqrt: Any
+  b_sqrt: Any
+
+
+def fisher_information(minibatch_potential=None, diagonal: bool = True):
+  """adaption.py:372-457: ``init`` / ``update`` do nothing; ``get(state, sample,
+  sample_grad, friction, mini_batch=..., step_size=..., model_state=...)`` estimates the
+  gradient noise from the per-observation likelihood gradients of the minibatch and returns
+  the corrected noise scales.  ``friction``: a scalar or a per-parameter ``f32[P]`` device
+  vector (what ``friction_leapfrog`` holds)."""
+  assert minibatch_potential, "Fisher information requires potential function."
+  if not diagonal:
+    raise NotImplementedError("the dense Fisher noise model (an SVD of a P x P matrix per "
+                              "chain) is outside the accelerated sampling path")
+  from . import glm
+  buffers = {}
+
+  def init(*args):
+    del args
+
+  def update(*args, **kwargs):
+    del args, kwargs
+
+  def get(state, sample: ChainTree, sample_grad: ChainTree, friction, *args, mini_batch,
+          flat_potential=None, step_size=1.0, model_state=None, **kwargs) -> NoiseModel:
+    del state, args, flat_potential, model_state, kwargs
+    pot = minibatch_potential
+    if hasattr(pot, "_resolve"):                      # reference-style callables, probed lazily
+      pot = pot._resolve(sample, mini_batch[0].loader)
+    if not hasattr(pot, "likelihood") or not isinstance(
+        pot.likelihood, (glm.LogisticRegression, glm.GaussianRegression)):
+      raise NotImplementedError("the Fisher noise model needs a GLM potential")
+    batch, info = mini_batch
+    if batch.per_chain or batch.mask is not None:
+      raise NotImplementedError("the Fisher noise model needs one unmasked minibatch shared "
+                                "by the chains")
+    spec = glm.resolve(pot.likelihood, pot.prior, sample, pot.temperature,
+                       batch.loader.absmax(pot.likelihood.x))
+    key = sample.flat.shape
+    buf = buffers.get(key)
+    if buf is None:
+      buf = {"ns": DeviceArray(key, np.float32), "sc": DeviceArray(key, np.float32),
+             "scratch": None}
+      buffers[key] = buf
+    vec = friction if isinstance(friction, DeviceArray) else None
+    buf["scratch"] = ops.glm_fisher_diag(
+        spec, sample.flat, batch.leaf(pot.likelihood.x), batch.leaf(pot.likelihood.y),
+        batch.idx, batch.n, int(info.observation_count), sample_grad.flat, vec,
+        0.0 if vec is not None else float(friction), float(step_size), buf["ns"], buf["sc"],
+        buf["scratch"])
+    return NoiseModel(Tensor(1, ChainTree.like(sample, buf["ns"])),
+                      Tensor(1, ChainTree.like(sample, buf["sc"])))
+
+  return init, update, get

@@ -110,13 +110,14 @@ def sghmc(potential_fn, data_loader, cache_size: int = 512, batch_size: int = 32
           diagonal_noise: bool = True, save_to_numpy: bool = True,
           progress_bar: bool = True):
   """alias.py:451-540."""
-  del diagonal_noise
-  if adapt_noise_model:
-    raise NotImplementedError("adaption.fisher_information is outside this path")
   random_data = data.random_reference_data(data_loader, cache_size, batch_size)
+  noise_model = None
+  if adapt_noise_model:                                                # alias.py:506-510
+    noise_model = adaption.fisher_information(minibatch_potential=potential_fn,
+                                              diagonal=diagonal_noise)
   leapfrog = integrator.friction_leapfrog(potential_fn, random_data,
                                           friction=friction, const_mass=mass,
-                                          steps=integration_steps)
+                                          steps=integration_steps, noise_model=noise_model)
   schedule = _schedule(first_step_size, last_step_size, burn_in, accepted_samples,
                        progress_bar)
   sghmc_solver = solver.sgmc(leapfrog)

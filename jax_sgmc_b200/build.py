@@ -18,7 +18,7 @@ LIB = os.path.join(OUT_DIR, "libsgmc_b200.so")
 
 SOURCES = ["runtime.cu", "prng_kernels.cu", "update_kernels.cu", "glm_simt.cu",
            "glm_tc.cu", "resgld.cu", "nccl_shim.cu", "adaption_kernels.cu",
-           "resgld_ladder.cu", "misc_kernels.cu", "tree_kernels.cu", "p2p_exchange.cu", "mlp.cu", "host_pull.cu"]
+           "resgld_ladder.cu", "misc_kernels.cu", "tree_kernels.cu", "p2p_exchange.cu", "mlp.cu", "host_pull.cu", "fisher.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3",

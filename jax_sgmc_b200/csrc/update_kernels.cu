@@ -405,18 +405,24 @@ struct SghmcStepOp {
   const float* mass;      // f32[P] or null
   float eps, neg_eps, noise_scale, friction_scalar;
   int last;
+  // Fisher noise model (adaption.fisher_information): cb_diff_sqrt as f32[C][P], or null.
+  // The noise becomes sqrt(2 eps) * (cb_diff_sqrt o xi) and is NOT multiplied by the
+  // friction (integrator.py:632-650).
+  const float* noise_mul = nullptr;
   static constexpr bool kReduce = false;
   struct Regs {
     float4 tA, tB, pA, pB, gA, gB;
   };
   __device__ __forceinline__ float one(float t, float& p, float g, float xi,
-                                       uint32_t e) const {
+                                       uint32_t e, int64_t gi) const {
     const float C = friction ? friction[e] : friction_scalar;
     const float inv_m = mass ? __frcp_rn(mass[e]) : 1.0f;
     const float m = __fmul_rn(inv_m, p);
     const float p1 = __fadd_rn(p, __fmul_rn(__fmul_rn(neg_eps, C), m));
     const float p2 = __fadd_rn(p1, __fmul_rn(neg_eps, g));
-    const float p3 = __fadd_rn(p2, __fmul_rn(C, __fmul_rn(noise_scale, xi)));
+    const float p3 = noise_mul
+        ? __fadd_rn(p2, __fmul_rn(noise_scale, __fmul_rn(noise_mul[gi], xi)))
+        : __fadd_rn(p2, __fmul_rn(C, __fmul_rn(noise_scale, xi)));
     p = p3;
     if (last) return t;
     return __fadd_rn(t, __fmul_rn(eps, __fmul_rn(inv_m, p3)));
@@ -437,8 +443,8 @@ struct SghmcStepOp {
     float pa[4] = {r.pA.x, r.pA.y, r.pA.z, r.pA.w};
     float pb[4] = {r.pB.x, r.pB.y, r.pB.z, r.pB.w};
     float4 oA, oB;
-    SGMC_F4_MAP(oA, one(f4get(r.tA, k), pa[k], f4get(r.gA, k), nA[k], eA + k));
-    SGMC_F4_MAP(oB, one(f4get(r.tB, k), pb[k], f4get(r.gB, k), nB[k], eB + k));
+    SGMC_F4_MAP(oA, one(f4get(r.tA, k), pa[k], f4get(r.gA, k), nA[k], eA + k, iA + k));
+    SGMC_F4_MAP(oB, one(f4get(r.tB, k), pb[k], f4get(r.gB, k), nB[k], eB + k, iB + k));
     if (!last) {
       st4(theta, iA, oA);
       st4(theta, iB, oB);
@@ -449,7 +455,7 @@ struct SghmcStepOp {
   }
   __device__ float apply_one(int64_t i, float n, int64_t, uint32_t e) const {
     float p = mom[i];
-    const float t = one(last ? 0.f : theta[i], p, grad[i], n, e);
+    const float t = one(last ? 0.f : theta[i], p, grad[i], n, e, i);
     if (!last) theta[i] = t;
     mom[i] = p;
     return 0.f;
@@ -666,6 +672,7 @@ struct RevLeapfrogOp {
 // the calling thread, picked up where the constant-mass entry points build their ops.
 struct AdaptedMass { const float* inv = nullptr; const float* sqrt = nullptr; };
 static thread_local AdaptedMass g_adapted;
+static thread_local const float* g_noise_mul = nullptr;   // sgmc_sghmc_step_noise_model
 struct AdaptedMassScope {
   AdaptedMassScope(const float* inv, const float* sqrt) { g_adapted.inv = inv; g_adapted.sqrt = sqrt; }
   ~AdaptedMassScope() { g_adapted = AdaptedMass{}; }
@@ -1140,9 +1147,29 @@ int sgmc_sghmc_step(void* stream, float* theta, float* momentum,
   const float eps = step_size;
   SghmcStepOp op{theta, momentum, grad, friction, mass, eps, -eps,
                  sqrtf(2.0f * eps), friction_scalar, last};
+  op.noise_mul = g_noise_mul;
   return launch_noise_pass((cudaStream_t)stream, tab, keys_in, keys_out,
                            n_chains, kKeySplit2, prng_layout, op,
                            "sgmc_sghmc_step");
+}
+
+// The SGHMC step with a Fisher noise model (friction_leapfrog(noise_model=...),
+// integrator.py:632-650): the injected noise is sqrt(2 eps) * (cb_diff_sqrt o xi) with
+// cb_diff_sqrt f32[n_chains][P] from sgmc_glm_fisher_diag, instead of friction * sqrt(2 eps) xi.
+int sgmc_sghmc_step_noise_model(void* stream, float* theta, float* momentum,
+                                const float* grad, const uint32_t* keys_in,
+                                uint32_t* keys_out, int64_t n_chains,
+                                const int64_t* leaf_sizes, int n_leaves, float step_size,
+                                float friction_scalar, const float* friction,
+                                const float* mass, const float* cb_diff_sqrt, int last,
+                                int prng_layout) {
+  SGMC_REQUIRE(cb_diff_sqrt != nullptr, "null noise model");
+  g_noise_mul = cb_diff_sqrt;
+  const int rc = sgmc_sghmc_step(stream, theta, momentum, grad, keys_in, keys_out, n_chains,
+                                 leaf_sizes, n_leaves, step_size, friction_scalar, friction,
+                                 mass, last, prng_layout);
+  g_noise_mul = nullptr;
+  return rc;
 }
 
 int sgmc_obabo_pass_a(void* stream, float* theta, float* momentum,

@@ -297,9 +297,10 @@ def langevin_diffusion(potential_fn, batch_fn, adaption=None
 def friction_leapfrog(potential_fn, batch_fn, steps: int = 10, friction=0.25,
                       const_mass: PyTree = None, noise_model=None
                       ) -> Tuple[Callable, Callable, Callable]:
-  """integrator.py:563-765 (SGHMC)."""
-  if noise_model:
-    raise NotImplementedError("the Fisher noise model is outside this path")
+  """integrator.py:563-765 (SGHMC).  ``noise_model``: an ``adaption.fisher_information``
+  triplet; its ``get`` is evaluated at the new positions on the step's minibatch and the
+  corrected scale multiplies the injected noise (:632-650)."""
+  get_noise_model = noise_model[2] if noise_model else None
   init_data, get_data, _ = batch_fn
   stochastic_gradient = _potential.value_and_grad(potential_fn)
   scratch = _Scratch()
@@ -340,9 +341,15 @@ def friction_leapfrog(potential_fn, batch_fn, steps: int = 10, friction=0.25,
       (_, model_state), grad = stochastic_gradient(                      # :622-625
           theta, mini_batch, state=model_state, grad_out=sc["grad"],
           U_out=state.potential)
+      noise_mul = None
+      if get_noise_model is not None:                                    # :632-650
+        fr = sc["friction"] if sc["friction"] is not None else sc["friction_scalar"]
+        noise_mul = get_noise_model(None, theta, grad, fr, mini_batch=mini_batch,
+                                    step_size=eps, model_state=model_state
+                                    ).cb_diff_sqrt.tensor.flat
       ops.sghmc_step(theta.flat, p.flat, grad.flat, state.key.current,
                      state.key.next, theta.sizes, eps, sc["friction_scalar"],
-                     sc["friction"], sc["mass"], last=(s == steps - 1))
+                     sc["friction"], sc["mass"], last=(s == steps - 1), noise_mul=noise_mul)
       state.key.flip()
     return LeapfrogState(positions=theta, momentum=p, key=state.key,
                          potential=state.potential, model_state=model_state,

@@ -176,7 +176,15 @@ def sghmc_begin(theta, momentum, keys_in, keys_out, leaf_sizes, step_size,
 
 def sghmc_step(theta, momentum, grad, keys_in, keys_out, leaf_sizes, step_size,
                friction=0.25, friction_vec=None, mass=None, last=False,
-               layout=0, stream=None):
+               layout=0, stream=None, noise_mul=None):
+  """``noise_mul``: cb_diff_sqrt f32[C, P] of a Fisher noise model (glm_fisher_diag)."""
+  if noise_mul is not None:
+    assert noise_mul.shape == theta.shape
+    _lib.call("sgmc_sghmc_step_noise_model", _s(stream), vp(theta), vp(momentum), vp(grad),
+              vp(keys_in), vp(keys_out), theta.shape[0], i64_array(leaf_sizes),
+              len(leaf_sizes), float(step_size), float(friction),
+              vp(friction_vec), vp(mass), vp(noise_mul), int(bool(last)), _layout(layout))
+    return
   _lib.call("sgmc_sghmc_step", _s(stream), vp(theta), vp(momentum), vp(grad),
             vp(keys_in), vp(keys_out), theta.shape[0], i64_array(leaf_sizes),
             len(leaf_sizes), float(step_size), float(friction),
@@ -511,6 +519,20 @@ def revleapfrog_step(theta, momentum, grad, energy, keys_in, keys_out, leaf_size
             vp(energy), vp(keys_in), vp(keys_out), theta.shape[0], i64_array(leaf_sizes),
             len(leaf_sizes), float(step_size), float(friction), vp(mass),
             1 if last else 0, _layout(layout))
+
+
+def glm_fisher_diag(spec, theta, X, y, idx, batch_size, observation_count, grad, friction_vec,
+                    friction_scalar, step_size, noise_scale, scale, scratch=None, stream=None):
+  """adaption.fisher_information(diagonal=True).get for a GLM potential (see
+  sgmc_glm_fisher_diag); returns the scratch buffer for reuse."""
+  C_, P = theta.shape
+  need = int(_lib.load().sgmc_glm_fisher_scratch_floats(C_, P, int(batch_size)))
+  if scratch is None or scratch.size < need:
+    scratch = DeviceArray((need,), np.float32)
+  _lib.call("sgmc_glm_fisher_diag", _s(stream), C.byref(spec), vp(theta), C_, P, vp(X), vp(y),
+            vp(idx), int(batch_size), int(observation_count), vp(grad), vp(friction_vec),
+            float(friction_scalar), float(step_size), vp(noise_scale), vp(scale), vp(scratch))
+  return scratch
 
 
 def mass_matrix_update(mean, ssq, m_inv, m_sqrt, sample, iteration: int, burn_in: int,

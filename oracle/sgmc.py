@@ -420,25 +420,31 @@ def leapfrog_init(theta, keys=None):
                        np.zeros(C, F32))
 
 
-def sghmc_inner_apply(theta_new, p, m, grad, xi, step_size, friction):
+def sghmc_inner_apply(theta_new, p, m, grad, xi, step_size, friction, cb_diff_sqrt=None):
   """Momentum part of ``_body_fun`` after the gradient (integrator.py:616-655).
 
   m = M^-1 p (computed by the caller from the *old* momentum, :610).
-  p1 = p + ((-eps*C) * m); p2 = p1 + ((-eps)*g); p3 = p2 + (C*(sqrt(2 eps)*xi)).
+  p1 = p + ((-eps*C) * m); p2 = p1 + ((-eps)*g); p3 = p2 + (C*(sqrt(2 eps)*xi)), or with a
+  noise model (:632-650) p3 = p2 + sqrt(2 eps)*(cb_diff_sqrt*xi).
   """
   eps = F32(step_size)
   C = np.asarray(friction, F32)
   p1 = (p + ((F32(-eps) * C).astype(F32) * m).astype(F32)).astype(F32)
   p2 = (p1 + (F32(-eps) * grad).astype(F32)).astype(F32)
   ns = np.sqrt(F32(F32(2.0) * eps)).astype(F32)
+  if cb_diff_sqrt is not None:
+    return (p2 + (ns * (np.asarray(cb_diff_sqrt, F32) * xi).astype(F32)).astype(F32)).astype(F32)
   p3 = (p2 + (C * (ns * xi).astype(F32)).astype(F32)).astype(F32)
   return p3
 
 
 def friction_leapfrog_integrate(state: LeapfrogState, grad_fns, sizes,
                                 step_size, friction=0.25, mass=None,
-                                layout="original"):
+                                layout="original", noise_model_fn=None):
   """``friction_leapfrog.integrate`` (integrator.py:716-757).
+
+  ``noise_model_fn(theta_new, grad, step_index) -> cb_diff_sqrt`` stands for
+  ``get_noise_model`` evaluated on the step's minibatch (:632-647).
 
   ``grad_fns`` is a sequence of ``steps`` callables, one per inner step (each
   inner step draws a fresh minibatch, :621).  ``mass`` is the flat diagonal
@@ -456,6 +462,7 @@ def friction_leapfrog_integrate(state: LeapfrogState, grad_fns, sizes,
   theta = state.theta
   U = np.zeros(theta.shape[0], F32)
   eps = F32(step_size)
+  step_i = 0
   for grad_fn in grad_fns:                                   # :749-755
     m = (inv_m * p).astype(F32)                              # :610
     theta = (theta + (eps * m).astype(F32)).astype(F32)      # :611-612
@@ -463,7 +470,9 @@ def friction_leapfrog_integrate(state: LeapfrogState, grad_fns, sizes,
     ks = prng.split(key, 2, layout)                          # :630
     key, sub = ks[..., 0, :], ks[..., 1, :]
     xi = random_tree_flat(sub, sizes, layout)                # :631
-    p = sghmc_inner_apply(theta, p, m, g, xi, eps, fr)
+    cb = None if noise_model_fn is None else noise_model_fn(theta, g, step_i)
+    p = sghmc_inner_apply(theta, p, m, g, xi, eps, fr, cb)
+    step_i += 1
   return LeapfrogState(theta, p, key, U.astype(F32))
 
 
@@ -741,6 +750,42 @@ def mass_matrix_update(state: MassState, sample, burn_in: int) -> MassState:
       m_inv = (ssq / fi).astype(F32)
       m_sqrt = np.sqrt((fi / ssq).astype(F32)).astype(F32)
   return MassState(it, new_mean, ssq, m_inv, m_sqrt)
+
+
+# ----------------------------------------------------------------------------
+# adaption.fisher_information, diagonal   (adaption.py:372-457)
+# ----------------------------------------------------------------------------
+
+def fisher_information_get(model, theta, batch, N, sample_grad, friction, step_size):
+  """``fisher_information(diagonal=True).get`` (adaption.py:391-438) for C chains.
+
+  ``sample_grad``: gradient of the stochastic potential at ``theta`` on ``batch``;
+  ``friction``: scalar or f32[P].  Per-observation gradients ``grad(likelihoods[i])`` come
+  from the model's vjp with a one-hot cotangent.  Returns ``(noise_scale, scale)`` =
+  ``(cb_diff_sqrt, b_sqrt)``, f32[C, P] each.  The reference subtracts the un-scaled
+  POTENTIAL gradient from the per-observation LIKELIHOOD gradient (:404, :416); kept."""
+  X, y = batch
+  n = X.shape[0]
+  theta = np.asarray(theta, F32)
+  C, P = theta.shape
+  m = (np.asarray(sample_grad, F32) / F32(N)).astype(F32)                     # :404
+  ell, aux = model.loglik(theta, X, y)
+  ssq = np.zeros((C, P), F32)
+  for i in range(n):
+    cot = np.zeros_like(ell)
+    cot[:, i] = F32(1.0)
+    gi = model.vjp(theta, X, y, aux, cot)                                     # :406-412
+    d = (gi - m).astype(F32)
+    ssq = (ssq + (d * d).astype(F32)).astype(F32)                             # :414-420
+  v = (F32(1.0 / (n - 1)) * ssq).astype(F32)                                  # :423
+  b = (F32(F32(0.5) * F32(step_size)) * v).astype(F32)                        # :424
+  fr = np.broadcast_to(np.asarray(friction, F32), (C, P))
+  corr = (fr - b).astype(F32)                                                 # :427
+  smallest = np.min(np.where(corr <= 0, np.inf, corr), axis=1, keepdims=True)  # :428
+  pos = np.where(corr <= 0, smallest, corr).astype(F32)                       # :429
+  b_corr = (fr - pos).astype(F32)                                             # :432
+  with np.errstate(invalid="ignore"):
+    return np.sqrt(pos).astype(F32), np.sqrt(b_corr).astype(F32)              # :434-435
 
 
 # ----------------------------------------------------------------------------

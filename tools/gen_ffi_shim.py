@@ -81,6 +81,11 @@ HANDLERS = [
                     "out:U32:keys_out", "x:theta.dimensions()[0]", "span:leaf_sizes",
                     "a:float:step_size", "a:float:friction_scalar", "opt:F32:friction",
                     "opt:F32:mass", "a:int32:last", "a:int32:prng_layout"]),
+    ("sghmc_step_noise_model", ["S", "io:F32:theta", "io:F32:momentum", "in:F32:grad",
+                                "in:U32:keys", "out:U32:keys_out", "x:theta.dimensions()[0]",
+                                "span:leaf_sizes", "a:float:step_size", "a:float:friction_scalar",
+                                "opt:F32:friction", "opt:F32:mass", "in:F32:cb_diff_sqrt",
+                                "a:int32:last", "a:int32:prng_layout"]),
     ("obabo_pass_a", ["S", "io:F32:theta", "io:F32:momentum", "in:F32:grad", "io:F32:ke_start",
                       "in:U32:keys", "out:U32:keys_out", "x:theta.dimensions()[0]",
                       "span:leaf_sizes", "a:float:step_size", "a:float:temperature",
@@ -129,6 +134,11 @@ HANDLERS = [
                             "a:int64:observation_count", "a:int64:batch_size", "out:F32:potential",
                             "out:F32:scratch", "out:S32:wrap_idx", "out:F32:wrap_mask",
                             "ws:workspace", "a:int32:path"]),
+    ("glm_fisher_diag", ["S", "glm", "in:F32:theta", "x:theta.dimensions()[0]",
+                         "x:theta.dimensions()[1]", "in:F32:X", "in:F32:y", "opt:S32:idx",
+                         "a:int64:batch_size", "a:int64:observation_count", "in:F32:grad",
+                         "opt:F32:friction", "a:float:friction_scalar", "a:float:step_size",
+                         "out:F32:noise_scale", "out:F32:scale", "out:F32:scratch"]),
     ("glm_sgld_step", ["S", "glm", "io:F32:theta", "ioopt:F32:v", "x:theta.dimensions()[0]",
                        "x:theta.dimensions()[1]", "in:F32:X", "in:F32:y", "opt:S32:idx",
                        "opt:F32:mask", "a:int64:batch_size", "a:int64:observation_count",
