@@ -89,7 +89,7 @@ struct TcLinkEpi {      // GEMM1: z -> ell statistics, R = cot*mask*dl/dz as fp1
   float* stats;             // f32[C][parts][4]
   int parts;
   // last-arriver finalisation (U, var) per 128-row block
-  uint32_t* counters;       // u32[ceil(C/128)], zeroed by k_prepare_all
+  uint32_t* counters;       // u32[2 ceil(C/128)], zeroed by k_prepare_all
   const float* row_sumsq;   // f32[C]: sum theta^2 over the gaussian-prior range
   float* potential; float* variance;
   float n_obs, inv_temperature, prior_half_inv;   // N, 1/T, 0.5/scale^2 (0: no gaussian prior)
@@ -764,7 +764,8 @@ struct PrSmem {
   static constexpr int kPipeBytes = kStages * kStageBytes;
   static constexpr int kOutBytes = kPrEpiWarps * kPrStageOut;
   static constexpr int kStgStages = (kOutBytes + kStageBytes - 1) / kStageBytes;
-  static constexpr int kAuxBytes = 256 /*barriers, tmem ptr, flags*/ + 2 * 3 * BN * 4;
+  static constexpr int kAuxBytes = 256 /*barriers, tmem ptr, flags*/ + 2 * 3 * BN * 4 +
+                                   2 * BM * 4 * 16 /*likelihood partials per (row, column group)*/;
   static constexpr int kBytes = kPipeBytes + kAuxBytes + 1024 /*alignment slack*/;
   static_assert(kStages > kStgStages, "need at least one stage that is never handed over");
   static_assert(2 * kStages + 5 <= 24, "barrier block is 256 bytes");
@@ -823,6 +824,9 @@ k_glm_tc_pair(const __grid_constant__ PairMaps maps, const PairSched sch,
               const TcLinkEpi link, const TcGradEpi gradp, const PairNoise nz) {
   using S = PrSmem<TERMS, CG, BN>;
   constexpr int kChunks = BN / 128;                // 32-column chunks per epilogue warp and tile
+  // R is handed to GEMM2 per column HALF of a tile (256-wide tiles): the epilogue warps
+  // work through columns [0, 128) first and publish them while they compute [128, 256)
+  constexpr int kHalves = kChunks;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -839,6 +843,7 @@ k_glm_tc_pair(const __grid_constant__ PairMaps maps, const PairSched sch,
   int* s_last = reinterpret_cast<int*>(tmem_ptr + 1);   // [2]
   int* s_noise_next = s_last + 2;                       // next noise unit of this CTA
   float* s_col = reinterpret_cast<float*>(aux + 256);   // [2][3][BN]
+  float4* s_part_all = reinterpret_cast<float4*>(aux + 256 + 2 * 3 * BN * 4);   // [2][BM][4]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;
@@ -911,18 +916,36 @@ k_glm_tc_pair(const __grid_constant__ PairMaps maps, const PairSched sch,
         const int m0 = rb * (BM * CG) + (int)rank * BM;
         const int n0 = tn * BN + (int)rank * S::kBRows;
         const int kbs = g2 ? sch.kb2 : sch.kb1;
-        if (g2) {
-          // every R tile of this row block has been stored (GEMM1 epilogues of tiles
-          // earlier in the list, on this pair or another one)
-          pair_stamp(dbg, pair, 2);
-          while (ld_acquire_gpu(&link.counters[rb]) < (uint32_t)(CG * sch.nt1)) __nanosleep(40);
-          fence_proxy_async_global();
-          pair_stamp(dbg, pair, 3);
+        // GEMM2 consumes R in the order the GEMM1 epilogues publish it: first the k-blocks
+        // of the FIRST column half of every R tile, then those of the second halves
+        // (kHalves = 2; with 128-wide tiles a tile is one half and the order is the natural one)
+        constexpr int kKbTile = BN / kPrBK;            // k-blocks of GEMM2 per R tile
+        constexpr int kKbHalf = kKbTile / kHalves;
+        int count0 = kbs;
+        if (g2 && kHalves == 2) {
+          const int full = kbs / kKbTile, rem = kbs - full * kKbTile;
+          count0 = full * kKbHalf + (rem < kKbHalf ? rem : kKbHalf);
         }
+        if (g2) pair_stamp(dbg, pair, 2);
 #pragma unroll 1
-        for (int kb = 0; kb < kbs; ++kb) {
-          const int s = kb % S::kStages;               // the ring restarts with every tile
-          if (it > 0 && kb == s && s >= S::kStages - S::kStgStages)
+        for (int i = 0; i < kbs; ++i) {
+          int kb = i;
+          if (g2) {
+            if (kHalves == 2) {
+              const int h = i >= count0 ? 1 : 0, ii = i - h * count0;
+              kb = (ii / kKbHalf) * kKbTile + h * kKbHalf + ii % kKbHalf;
+            }
+            if (i == 0 || (kHalves == 2 && i == count0)) {
+              // every R tile of this row block has stored this column half (GEMM1
+              // epilogues of tiles earlier in the list, on this pair or another one)
+              const uint32_t* cnt = &link.counters[rb * kHalves + (i == 0 ? 0 : 1)];
+              while (ld_acquire_gpu(cnt) < (uint32_t)(CG * sch.nt1)) __nanosleep(40);
+              fence_proxy_async_global();
+              if (i == 0) pair_stamp(dbg, pair, 3);
+            }
+          }
+          const int s = i % S::kStages;                // the ring restarts with every tile
+          if (it > 0 && i == s && s >= S::kStages - S::kStgStages)
             mbar_wait(epi_done, (it - 1) & 1);         // previous tile's epilogue left the staging
           uint32_t use = 0;
 #pragma unroll
@@ -1018,7 +1041,7 @@ k_glm_tc_pair(const __grid_constant__ PairMaps maps, const PairSched sch,
       }
       mbar_wait(bar, parity);
     };
-    const int parts = sch.nt1 * (BN / 32);
+    const int parts = sch.nt1;                       // one likelihood partial per (row, R tile)
     uint32_t it = 0;
     for (int t = pair; t < sch.tiles_total; t += n_pairs, ++it) {
       const int g2 = t >= sch.tiles1 ? 1 : 0;
@@ -1055,9 +1078,10 @@ k_glm_tc_pair(const __grid_constant__ PairMaps maps, const PairSched sch,
         wait_acc(&acc_full[par], aph);
         tc_fence_after();
         if (threadIdx.x == 0) pair_stamp(dbg, pair, 9 + 5 * (int)it);
+        float n_w = 0.f, mean_w = 0.f, m2_w = 0.f, sm_w = 0.f;   // this row over the warp's chunks
 #pragma unroll 1
         for (int ch = 0; ch < kChunks; ++ch) {
-          const int ct = cg * (BN / 4) + ch * 32;          // column inside the tile
+          const int ct = (ch * 4 + cg) * 32;               // column inside the tile (half ch)
           const int col0 = n0 + ct;
           uint32_t acc[32];
           tmem_ld32(tmem_row + (uint32_t)ct, acc);
@@ -1138,17 +1162,31 @@ k_glm_tc_pair(const __grid_constant__ PairMaps maps, const PairSched sch,
               bulk_commit_group();
             }
           }
-          if (row_ok) {
-            // partial statistics of this (row, 32-column chunk), combined in fixed
-            // order by the CTA that completes the row block last
-            float mean = 0.f, m2 = 0.f;
-            if (cnt > 0.f) {
-              mean = shift + s1 / cnt;
-              m2 = fmaxf(s2 - s1 * s1 / cnt, 0.f);
+          if (cnt > 0.f) {
+            // statistics of this (row, 32-column chunk) folded into the warp's running
+            // ones (Chan et al., chunk order)
+            const float mean = shift + s1 / cnt;
+            const float m2 = fmaxf(s2 - s1 * s1 / cnt, 0.f);
+            const float nn = n_w + cnt, delta = mean - mean_w;
+            mean_w += delta * (cnt / nn);
+            m2_w += m2 + delta * delta * (n_w * cnt / nn);
+            n_w = nn;
+          }
+          sm_w += sm;
+          if (ch < kChunks - 1) {
+            // publish this column half of R: the TMA stores of all sixteen warps are
+            // performed and visible to the TMA loads of other SMs before the half's
+            // counter of the row block moves (GEMM2 of this row block may start on it)
+            if (lane == 0) bulk_wait_all();
+            __syncwarp();
+            __threadfence();
+            fence_proxy_async_global();
+            if (warp == 0) {
+              named_bar_sync(4, kPrEpiThreads);
+              if (lane == 0) atom_add_release_gpu(&link.counters[rb * kHalves + ch], 1u);
+            } else {
+              named_bar_arrive(4, kPrEpiThreads);
             }
-            const int part = tn * (BN / 32) + cg * kChunks + ch;
-            *reinterpret_cast<float4*>(link.stats + ((int64_t)row * parts + part) * kStatFields) =
-                make_float4(cnt, mean, m2, sm);
           }
         }
         // publish: R (TMA stores complete) + stats of this tile are visible -- also to the
@@ -1158,16 +1196,40 @@ k_glm_tc_pair(const __grid_constant__ PairMaps maps, const PairSched sch,
           bulk_wait_all();
           mbar_arrive(epi_done);                     // this warp's staging buffer is free again
         }
+        // the four column groups of a row meet in shared memory: one partial per (row, tile)
+        // goes to global memory, so the CTA that finishes a row block folds nt1 partials per
+        // chain, not 8 nt1 (that serial fold used to hold its gradient epilogue back by 20 us)
+        float4* s_part = s_part_all + par * (BM * 4);
+        s_part[(q * 32 + lane) * 4 + cg] = make_float4(n_w, mean_w, m2_w, sm_w);
         __threadfence();
         fence_proxy_async_global();
         if (threadIdx.x == 0) pair_stamp(dbg, pair, 11 + 5 * (int)it);
         if (warp < 4) {
           named_bar_sync(2, kPrEpiThreads);
+          if (row0 - q * 32 + (int)threadIdx.x < link.C) {
+            float n_t = 0.f, mean_t = 0.f, m2_t = 0.f, sm_t = 0.f;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const float4 st = s_part[threadIdx.x * 4 + g];
+              if (st.x > 0.f) {
+                const float nn = n_t + st.x, delta = st.y - mean_t;
+                mean_t += delta * (st.x / nn);
+                m2_t += st.z + delta * delta * (n_t * st.x / nn);
+                n_t = nn;
+              }
+              sm_t += st.w;
+            }
+            *reinterpret_cast<float4*>(
+                link.stats + ((int64_t)(m0 + (int)threadIdx.x) * parts + tn) * kStatFields) =
+                make_float4(n_t, mean_t, m2_t, sm_t);
+          }
+          __threadfence();
+          named_bar_sync(3, 128);
           if (threadIdx.x == 0) {
-            const uint32_t prev = atom_add_release_gpu(&link.counters[rb], 1u);
+            const uint32_t prev = atom_add_release_gpu(&link.counters[rb * kHalves + kHalves - 1], 1u);
             s_last[par] = prev == (uint32_t)(CG * sch.nt1) - 1u;
           }
-          named_bar_sync(3, 128);
+          named_bar_sync(5, 128);
           if (s_last[par]) {
             // last tile of the row block: U = (L - prior)/T (potential.py:183-185, :210)
             // and var(ell) (integrator.py:880) from the partials, Chan et al. in fixed order
@@ -1669,7 +1731,7 @@ static size_t carve(TcWorkspace* w, uint8_t* base, int64_t C, int64_t n, int64_t
   void* r_hi = take((size_t)C * n * 2);
   void* r_lo = take((size_t)C * n * 2);
   void* stats = take((size_t)C * parts * kStatFields * 4);
-  void* cnt = take((size_t)((C + BM - 1) / BM) * 4);
+  void* cnt = take((size_t)(2 * ((C + BM - 1) / BM)) * 4);   // two hand-over counters per row block
   void* xi = take((size_t)C * d * 4);
   void* nsc = take((size_t)C * 4);
   void* amr = take((size_t)C * 4);
@@ -1900,7 +1962,7 @@ int glm_tc(cudaStream_t stream, const GlmArgs& a, int path) {
     pa.x_scale = w.x_scale;
     pa.theta_blocks = a.only_x ? 0 : (int)((C + 7) / 8);
     pa.x_tiles_x = (d + kPrepTile - 1) / kPrepTile;
-    pa.tile_counters = w.counters; pa.n_counters = (int)((C + BM - 1) / BM);
+    pa.tile_counters = w.counters; pa.n_counters = (int)(2 * ((C + BM - 1) / BM));
     if (carry) {
       pa.theta_mode = cc->mode == 2 ? 2 : 0;
       pa.next_scale = w.next_scale; pa.amax_bits = w.amax_row; pa.sumsq_part = w.sumsq_part;

@@ -59,6 +59,13 @@ for path in os.environ.get("PATHS", "tc_parity,tc_throughput").split(","):
   for p in (0, 33, 34, 54, 73):
     if p < 80 and used[p]:
       print(f"pair {p:2d}:", " ".join(f"{v:6d}" for v in rel[p]))
+  if os.environ.get("ALL_PAIRS"):
+    order = np.argsort(rel[:, 31])
+    print("pairs by exit time: pair exit | R-wait-begin R-ready | t1: ready accfull chunksdone | noise-done")
+    for p in order:
+      if used[p]:
+        print(f"  pair {p:2d} exit {rel[p, 31]:6d} | {rel[p, 2]:6d} {rel[p, 3]:6d} | "
+              f"{rel[p, 13]:6d} {rel[p, 14]:6d} {rel[p, 15]:6d} | t0: {rel[p, 9]:6d} {rel[p, 10]:6d} | {rel[p, 1]:6d}")
   for sl in range(32):
     col = rel[used, sl]
     col = col[col >= 0]
