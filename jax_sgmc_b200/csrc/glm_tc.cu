@@ -26,9 +26,11 @@
 #include "glm.cuh"
 #include "noise_pass.cuh"
 #include "sgld_math.cuh"
+#include "sgld_apply_tile.cuh"
 #include "sgld_split.cuh"
 #include "tc_ptx.cuh"
 
+#include <cstdlib>
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
@@ -789,6 +791,18 @@ struct PairNoise {
   int units_total;           // C * units_per_chain
 };
 
+// Update phase at the tail of the launch (sgmc_glm_sgld_step in carried mode, opt-in
+// SGMC_OPT_FUSED_PAIR_UPDATE): once EVERY CTA has stored its gradient tiles and its share of
+// the noise (one grid-wide arrival counter; all CTAs are resident), the sixteen epilogue
+// warps of every CTA run the pSGLD update of k_sgld_apply_split over warp-tiles dealt round
+// robin -- same tile body (sgld_apply_tile.cuh), same bits, no second launch.
+struct PairUpdate {
+  ApplyTileArgs t;
+  uint32_t* grid_counter;     // zeroed by k_prepare_all
+  int64_t n_tiles;            // C * tiles_per_chain warp-tiles of 256 parameters
+  int enabled, rms;
+};
+
 __device__ __forceinline__ void pair_noise_unit(const PairNoise& nz, int u, int lane) {
   const int c = u / nz.units_per_chain;
   const uint32_t half = (uint32_t)nz.d >> 1;
@@ -821,7 +835,8 @@ __device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
 template <int TERMS, int ABFMT, int CG, int BN>
 __global__ void __launch_bounds__(kPrThreads, 1)
 k_glm_tc_pair(const __grid_constant__ PairMaps maps, const PairSched sch,
-              const TcLinkEpi link, const TcGradEpi gradp, const PairNoise nz) {
+              const TcLinkEpi link, const TcGradEpi gradp, const PairNoise nz,
+              const PairUpdate upd) {
   using S = PrSmem<TERMS, CG, BN>;
   constexpr int kChunks = BN / 128;                // 32-column chunks per epilogue warp and tile
   // R is handed to GEMM2 per column HALF of a tile (256-wide tiles): the epilogue warps
@@ -1350,6 +1365,29 @@ k_glm_tc_pair(const __grid_constant__ PairMaps maps, const PairSched sch,
       }
     }
     if (threadIdx.x == 0) pair_stamp(dbg, pair, 1);
+    if (upd.enabled) {
+      // ---- update phase: G and xi of every CTA are complete and visible first ----
+      __threadfence();
+      fence_proxy_async_global();
+      named_bar_sync(6, kPrEpiThreads);
+      if (threadIdx.x == 0) {
+        atom_add_release_gpu(upd.grid_counter, 1u);
+        while (ld_acquire_gpu(upd.grid_counter) < gridDim.x) __nanosleep(64);
+        pair_stamp(dbg, pair, 28);
+      }
+      named_bar_sync(7, kPrEpiThreads);
+      constexpr int kFmt = TERMS == 3 ? 1 : 2;
+      const uint64_t keep = l2_policy_evict_last(), drop = l2_policy_evict_first();
+      const uint32_t tpc = upd.t.tiles_per_chain;
+      for (int64_t tile = (int64_t)blockIdx.x * kPrEpiWarps + warp; tile < upd.n_tiles;
+           tile += (int64_t)gridDim.x * kPrEpiWarps) {
+        const int64_t c = tile / tpc;
+        const uint32_t t = (uint32_t)(tile - c * tpc);
+        if (upd.rms) apply_tile_fast<true, true, kFmt>(upd.t, c, t, lane, keep, drop);
+        else apply_tile_fast<false, true, kFmt>(upd.t, c, t, lane, keep, drop);
+      }
+      if (threadIdx.x == 0) pair_stamp(dbg, pair, 29);
+    }
   }
   __syncwarp();
   tc_fence_before();
@@ -1731,7 +1769,8 @@ static size_t carve(TcWorkspace* w, uint8_t* base, int64_t C, int64_t n, int64_t
   void* r_hi = take((size_t)C * n * 2);
   void* r_lo = take((size_t)C * n * 2);
   void* stats = take((size_t)C * parts * kStatFields * 4);
-  void* cnt = take((size_t)(2 * ((C + BM - 1) / BM)) * 4);   // two hand-over counters per row block
+  // two hand-over counters per row block + the grid-wide arrival counter of the update phase
+  void* cnt = take((size_t)(2 * ((C + BM - 1) / BM) + 8) * 4);
   void* xi = take((size_t)C * d * 4);
   void* nsc = take((size_t)C * 4);
   void* amr = take((size_t)C * 4);
@@ -1852,7 +1891,7 @@ static void map_cache_put(const MapKey& k, const PairMaps& m) {
 template <int TERMS, int ABFMT, int CG, int BN>
 static int launch_pair(cudaStream_t stream, const PairMaps& maps, const PairSched& sch,
                        const TcLinkEpi& link, const TcGradEpi& gradp, const PairNoise& nz,
-                       const char* name) {
+                       const PairUpdate& upd, const char* name) {
   using S = PrSmem<TERMS, CG, BN>;
   auto kfn = k_glm_tc_pair<TERMS, ABFMT, CG, BN>;
   static bool attr_set = false;
@@ -1892,7 +1931,7 @@ static int launch_pair(cudaStream_t stream, const PairMaps& maps, const PairSche
                                                     : max_pairs;
   const int pairs = nz.xi ? cap : std::min(cap, sch.tiles_total);
   cfg.gridDim = dim3(CG * pairs);
-  if (check_cuda(cudaLaunchKernelEx(&cfg, kfn, maps, sch, link, gradp, nz), name)) return 1;
+  if (check_cuda(cudaLaunchKernelEx(&cfg, kfn, maps, sch, link, gradp, nz, upd), name)) return 1;
   return post_launch(name);
 }
 
@@ -1962,7 +2001,7 @@ int glm_tc(cudaStream_t stream, const GlmArgs& a, int path) {
     pa.x_scale = w.x_scale;
     pa.theta_blocks = a.only_x ? 0 : (int)((C + 7) / 8);
     pa.x_tiles_x = (d + kPrepTile - 1) / kPrepTile;
-    pa.tile_counters = w.counters; pa.n_counters = (int)(2 * ((C + BM - 1) / BM));
+    pa.tile_counters = w.counters; pa.n_counters = (int)(2 * ((C + BM - 1) / BM) + 8);
     if (carry) {
       pa.theta_mode = cc->mode == 2 ? 2 : 0;
       pa.next_scale = w.next_scale; pa.amax_bits = w.amax_row; pa.sumsq_part = w.sumsq_part;
@@ -2075,8 +2114,30 @@ int glm_tc(cudaStream_t stream, const GlmArgs& a, int path) {
         cc->out.xi = w.xi;
       }
     }
+    // the update of sgmc_glm_sgld_step at the tail of the same launch
+    PairUpdate upd{};
+    if (carry && nz.xi != nullptr && fu.requested && !fu.write_grad && fu.layout == 0 &&
+        option(SGMC_OPT_FUSED_PAIR_UPDATE) && !option(SGMC_OPT_EXACT_UPDATE_MATH) && d % 256 == 0 &&
+        (prior_hi == prior_lo || (prior_lo == 0 && prior_hi == d)) &&
+        (cc->out.prior_coef != 0.f) == (prior_hi > prior_lo) && aligned) {
+      upd.enabled = 1;
+      upd.rms = fu.v != nullptr;
+      upd.grid_counter = w.counters + 2 * ((C + BM - 1) / BM);
+      upd.n_tiles = C * (int64_t)sgld_split_tiles_per_chain(d);
+      ApplyTileArgs& t = upd.t;
+      t.theta = fu.theta_rw; t.v = fu.v; t.grad = a.grad; t.xi = w.xi;
+      t.th_hi = w.th_hi; t.th_lo = w.th_lo; t.scale = w.next_scale;
+      t.amax_bits = w.amax_row; t.sumsq_part = w.sumsq_part; t.P = a.P;
+      t.tiles_per_chain = (uint32_t)sgld_split_tiles_per_chain(d);
+      t.prior_on = prior_hi > prior_lo ? 1 : 0;
+      t.prior_coef = cc->out.prior_coef;
+      t.noise_scale = sqrtf((2.0f * fu.temperature) * fu.step_size);   // integrator.py:882-884
+      t.neg_eps = -fu.step_size; t.alpha = fu.alpha; t.one_m_alpha = 1.0f - fu.alpha;
+      t.lmbd = fu.lmbd;
+      *fu.applied = true;
+    }
 #define SGMC_PAIR_CASE(T, F, G, B, NAME) \
-    if (cgn == G && bn == B) return launch_pair<T, F, G, B>(stream, maps, sch, link, gradp, nz, NAME)
+    if (cgn == G && bn == B) return launch_pair<T, F, G, B>(stream, maps, sch, link, gradp, nz, upd, NAME)
     if (split) {
       SGMC_PAIR_CASE(3, 0, 2, 128, "k_glm_tc_pair<split,2,128>");
       SGMC_PAIR_CASE(3, 0, 2, 256, "k_glm_tc_pair<split,2,256>");

@@ -14,6 +14,7 @@
 // SGHMC step 20, OBABO pass A 20 + pass B 12.
 #include "noise_pass.cuh"
 #include "sgld_math.cuh"
+#include "sgld_apply_tile.cuh"
 #include "sgld_split.cuh"
 #include "tc_ptx.cuh"
 
@@ -108,40 +109,6 @@ int plan_noise_launch(const LeafTable& t, int64_t n_chains, const void* kernel,
 }
 
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ float4 ld4(const float* p, int64_t i) {
-  return *reinterpret_cast<const float4*>(p + i);
-}
-__device__ __forceinline__ void st4(float* p, int64_t i, float4 v) {
-  *reinterpret_cast<float4*>(p + i) = v;
-}
-// L2 eviction-priority hints (createpolicy + .L2::cache_hint): the per-step working set
-// of the carried Langevin step (~120 MB) is about the size of the L2, so the persistent
-// state (theta, v, the operand split) asks to stay and the transient streams (gradient,
-// noise) give their lines up at their last read.
-__device__ __forceinline__ uint64_t l2_policy_evict_last() {
-  uint64_t p;
-  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
-  return p;
-}
-__device__ __forceinline__ uint64_t l2_policy_evict_first() {
-  uint64_t p;
-  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
-  return p;
-}
-__device__ __forceinline__ float4 ld4_hint(const float* p, int64_t i, uint64_t pol) {
-  float4 v;
-  asm volatile("ld.global.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
-               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p + i), "l"(pol));
-  return v;
-}
-__device__ __forceinline__ void st4_hint(float* p, int64_t i, float4 v, uint64_t pol) {
-  asm volatile("st.global.L2::cache_hint.v4.f32 [%4], {%0,%1,%2,%3}, %5;" ::"f"(v.x), "f"(v.y),
-               "f"(v.z), "f"(v.w), "l"(p + i), "l"(pol) : "memory");
-}
-__device__ __forceinline__ void st2u_hint(void* p, uint2 v, uint64_t pol) {
-  asm volatile("st.global.L2::cache_hint.v2.u32 [%2], {%0,%1}, %3;" ::"r"(v.x), "r"(v.y), "l"(p),
-               "l"(pol) : "memory");
-}
 #define SGMC_F4_MAP(dst, expr)                          \
   {                                                     \
     float4 _o;                                          \
@@ -764,37 +731,16 @@ k_sgld_apply_split(const SgldSplitOp<RMS, FAST, FMT> op, const float* __restrict
   const uint32_t e0 = t * 256u;
   if (e0 + 256u <= (uint32_t)P && e0 >= op.prior_lo && e0 + 256u <= op.prior_hi &&
       op.prior_coef != 0.f && op.grad_rw == nullptr) {
-    // the common tile: whole, inside the prior range -- all eight loads first, no
-    // per-element range tests
-    const int64_t i0 = c * P + e0 + (uint32_t)lane * 4u, i1 = i0 + 128;
-    const float4 th0 = ld4_hint(op.theta, i0, keep), th1 = ld4_hint(op.theta, i1, keep);
-    float4 g0 = ld4_hint(op.grad, i0, drop), g1 = ld4_hint(op.grad, i1, drop);
-    const float4 x0 = ld4_hint(xi, i0, drop), x1 = ld4_hint(xi, i1, drop);
-    float4 v0 = RMS ? ld4_hint(op.v, i0, keep) : make_float4(0.f, 0.f, 0.f, 0.f);
-    float4 v1 = RMS ? ld4_hint(op.v, i1, keep) : make_float4(0.f, 0.f, 0.f, 0.f);
-    const float pc = op.prior_coef;
-    g0.x = fmaf(th0.x, pc, g0.x); g0.y = fmaf(th0.y, pc, g0.y);
-    g0.z = fmaf(th0.z, pc, g0.z); g0.w = fmaf(th0.w, pc, g0.w);
-    g1.x = fmaf(th1.x, pc, g1.x); g1.y = fmaf(th1.y, pc, g1.y);
-    g1.z = fmaf(th1.z, pc, g1.z); g1.w = fmaf(th1.w, pc, g1.w);
-    float4 o0, o1;
-    o0.x = op.one(th0.x, g0.x, v0.x, x0.x, ns); o0.y = op.one(th0.y, g0.y, v0.y, x0.y, ns);
-    o0.z = op.one(th0.z, g0.z, v0.z, x0.z, ns); o0.w = op.one(th0.w, g0.w, v0.w, x0.w, ns);
-    o1.x = op.one(th1.x, g1.x, v1.x, x1.x, ns); o1.y = op.one(th1.y, g1.y, v1.y, x1.y, ns);
-    o1.z = op.one(th1.z, g1.z, v1.z, x1.z, ns); o1.w = op.one(th1.w, g1.w, v1.w, x1.w, ns);
-    st4_hint(op.theta, i0, o0, keep);
-    st4_hint(op.theta, i1, o1, keep);
-    if (RMS) {
-      st4_hint(op.v, i0, v0, keep);
-      st4_hint(op.v, i1, v1, keep);
-    }
-    op.template emit4<true>(i0, o0, s, keep);
-    op.template emit4<true>(i1, o1, s, keep);
-    amax = fmaxf(fmaxf(fmaxf(fabsf(o0.x), fabsf(o0.y)), fmaxf(fabsf(o0.z), fabsf(o0.w))),
-                 fmaxf(fmaxf(fabsf(o1.x), fabsf(o1.y)), fmaxf(fabsf(o1.z), fabsf(o1.w))));
-    // same association as sq4 on both halves (the sums feed the prior value bit for bit)
-    sum = ((o0.x * o0.x + o0.y * o0.y) + (o0.z * o0.z + o0.w * o0.w)) +
-          ((o1.x * o1.x + o1.y * o1.y) + (o1.z * o1.z + o1.w * o1.w));
+    // the common tile: whole, inside the prior range (sgld_apply_tile.cuh)
+    ApplyTileArgs ta;
+    ta.theta = op.theta; ta.v = op.v; ta.grad = op.grad; ta.xi = xi;
+    ta.th_hi = op.th_hi; ta.th_lo = op.th_lo; ta.scale = op.scale;
+    ta.amax_bits = op.amax_bits; ta.sumsq_part = op.sumsq_part; ta.P = P;
+    ta.tiles_per_chain = tpc; ta.prior_on = 1; ta.prior_coef = op.prior_coef;
+    ta.noise_scale = ns; ta.neg_eps = op.neg_eps; ta.alpha = op.alpha;
+    ta.one_m_alpha = op.one_m_alpha; ta.lmbd = op.lmbd;
+    apply_tile_fast<RMS, FAST, FMT>(ta, c, t, lane, keep, drop);
+    return;
   } else {
 #pragma unroll
     for (int h = 0; h < 2; ++h) {

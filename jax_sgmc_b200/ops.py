@@ -612,6 +612,7 @@ OPT_NO_SHADOW_NOISE = 8      # 1: noise in the update kernel instead of under th
 OPT_NO_PIPELINE = 9          # 1: scans stage minibatches on the sampling stream (no side stream)
 OPT_STEP_PROFILE = 10        # 1: per-kernel CUDA-event timing of the carried step
 OPT_TC_MAX_PAIRS = 11        # > 0: cap on the CTA pairs of k_glm_tc_pair (chain groups side by side)
+OPT_FUSED_PAIR_UPDATE = 13   # 1: the carried step's update as the tail phase of the potential kernel
 OPT_STREAM_UPDATE = 12       # 1: streaming (bulk-copy) update kernel of the carried step (A/B)
 OPT_TC_CTA_GROUP = 5         # 2 (default): tcgen05 cta_group::2 on CTA pairs; 1: single CTAs
 
