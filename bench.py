@@ -538,11 +538,18 @@ def run_b200(args):
   chain_keys = np.stack([ops.prng_key(rank * C + c) for c in range(C)])
   sampler_fn(init, iterations=1024, keys=chain_keys)          # warm-up (buffers, page locking)
   init = ChainTree.like(init, DA.zeros((C, d)))
-  ctl.barrier()
-  t0 = time.perf_counter()
-  res = sampler_fn(init, iterations=e2e_steps, keys=chain_keys)
-  device.synchronize()
-  e2e_s = ctl.max(time.perf_counter() - t0)
+  # three runs of e2e_steps iterations each; the MEDIAN is reported (the host side of this
+  # leg shares its cores and memory bandwidth with other tenants of the box), all three are
+  # listed in e2e.runs
+  e2e_runs = []
+  for _ in range(3):
+    init = ChainTree.like(init, DA.zeros((C, d)))
+    ctl.barrier()
+    t0 = time.perf_counter()
+    res = sampler_fn(init, iterations=e2e_steps, keys=chain_keys)
+    device.synchronize()
+    e2e_runs.append(ctl.max(time.perf_counter() - t0))
+  e2e_s = sorted(e2e_runs)[1]
   kept = np.asarray(res[0]["samples"]["variables"]["w"])
   assert np.all(np.isfinite(kept))
   h2d = int(getattr(pot, "h2d_bytes_per_step", 0))
@@ -556,10 +563,11 @@ def run_b200(args):
   e2e = {"value": world * C * e2e_steps / e2e_s, "unit": UNIT,
          "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
          "seconds": e2e_s, "host_link": link,
+         "runs": [world * C * e2e_steps / t for t in e2e_runs],
          "what": "through alias.sgld(minibatch_potential, StreamingNumpyDataLoader): " + how +
                  (f" (1/{world} per rank + NCCL all-gather)" if world > 1 else "") +
                  ", (U, var) of every chain D2H every step, kept sample downloaded; wall "
-                 "clock around the whole run_fn call"}
+                 "clock around the whole run_fn call, median of three calls"}
   del loader, hX, hy
 
   resgld = None
