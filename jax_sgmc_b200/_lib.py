@@ -117,6 +117,10 @@ PROTOTYPES = {
                                 _i64, _i64, _i64, _vp, _int, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _f32,
                                 _f32, _vp, _sz, _int, _int, _vp, _int, _int, _vp, _vp, _vp, _i64,
                                 C.POINTER(_i64)],
+    "sgmc_glm_sgld_scan_hybrid": [_vp, _vp, C.POINTER(GlmSpec), _vp, _vp, _i64, _i64, _vp, _i64,
+                                  _i64, _vp, _vp, _int, _i64, _i64, _i64, _vp, _int, _vp, _vp, _vp,
+                                  _vp, _vp, _vp, _f32, _f32, _f32, _vp, _sz, _int, _int, _vp, _int,
+                                  _int, _vp, _vp, _vp, _i64, C.POINTER(_i64)],
     "sgmc_glm_sgld_scan_pull": [_vp, _vp, C.POINTER(GlmSpec), _vp, _vp, _i64, _i64, _vp, _vp,
                                 _vp, _int, _i64, _i64, _i64, _vp, _int, _vp, _vp, _vp, _vp, _vp,
                                 _vp, _f32, _f32, _f32, _vp, _sz, _int, _int, _vp, _int, _int,

@@ -602,6 +602,9 @@ struct HostSource {
   const float* y_mapped = nullptr;
   const int32_t* idx_all = nullptr;      // device int32[n_steps][n]
   int pull_ctas = 0;
+  // hybrid: the first rows_dma rows of a rank's slice come from host_batches (DMA engine),
+  // the rest is pulled (both sources set); -1 = all rows from the one source that is set
+  int64_t rows_dma = -1;
 };
 
 int scan_host_impl(void* stream, void* copy_stream, const sgmc_glm_spec* spec,
@@ -615,11 +618,13 @@ int scan_host_impl(void* stream, void* copy_stream, const sgmc_glm_spec* spec,
                    void* nccl_comm, int rank, int n_ranks, const uint8_t* keep,
                    float* samples_out, float* scalars_out, int64_t capacity,
                    int64_t* kept) {
-  const bool pull = src.X_mapped != nullptr;
+  const bool hybrid = src.X_mapped != nullptr && src.host_batches != nullptr;
+  const bool pull = src.X_mapped != nullptr && !hybrid;
   SGMC_REQUIRE(spec && theta && device_slots && potential_variance && grad &&
                keys_a && keys_b && step_sizes, "null argument");
-  SGMC_REQUIRE(pull ? (src.y_mapped && src.idx_all) : (src.host_batches && src.host_batch_count >= 1),
+  SGMC_REQUIRE(src.X_mapped ? (src.idx_all && (hybrid || src.y_mapped)) : src.host_batches != nullptr,
                "no minibatch source");
+  SGMC_REQUIRE(src.host_batches == nullptr || src.host_batch_count >= 1, "no host batches");
   SGMC_REQUIRE(keep == nullptr || samples_out == nullptr || (scalars_out && kept),
                "sample collection needs scalars_out and kept");
   SGMC_REQUIRE(n_slots >= 2 && n_slots <= 8 && n_steps >= 0, "2..8 slots");
@@ -634,16 +639,24 @@ int scan_host_impl(void* stream, void* copy_stream, const sgmc_glm_spec* spec,
   // all-gathered over NVLink into the device slot, so the host link carries 1 / R of
   // the batch per rank instead of R identical copies.
   const int64_t rows_local = sharded ? n / n_ranks : n;
-  const size_t host_stride = (size_t)rows_local * d + n;
+  const int64_t rows_dma = hybrid ? src.rows_dma : rows_local;      // rows of the slice staged on the host
+  SGMC_REQUIRE(rows_dma >= 0 && rows_dma <= rows_local, "bad DMA / pull split");
+  const size_t host_stride = (size_t)rows_dma * d + n;
   cudaStream_t rs = nullptr;                               // read-back stream (D2H runs
   cudaStream_t hs = nullptr;                               // beside H2D); transfer stream
+  cudaStream_t ps = nullptr;                               // hybrid: the pull beside the DMA
   if (check_cuda(cudaStreamCreateWithFlags(&rs, cudaStreamNonBlocking), "stream") ||
-      check_cuda(cudaStreamCreateWithFlags(&hs, cudaStreamNonBlocking), "stream"))
+      check_cuda(cudaStreamCreateWithFlags(&hs, cudaStreamNonBlocking), "stream") ||
+      (hybrid && check_cuda(cudaStreamCreateWithFlags(&ps, cudaStreamNonBlocking), "stream")))
     return 1;
-  cudaEvent_t copied[8], consumed[8], computed[2], read_back[2], begin;
+  cudaEvent_t copied[8], consumed[8], computed[2], read_back[2], begin, pulled[8];
+  if (hybrid)
+    for (int i = 0; i < n_slots; ++i)
+      if (check_cuda(cudaEventCreateWithFlags(&pulled[i], cudaEventDisableTiming), "event")) return 1;
   if (check_cuda(cudaEventCreateWithFlags(&begin, cudaEventDisableTiming), "event")) return 1;
   cudaEventRecord(begin, cs);                              // what the caller queued on the copy
   cudaStreamWaitEvent(hs, begin, 0);                       // stream (index upload) comes first
+  if (hybrid) cudaStreamWaitEvent(ps, begin, 0);
   for (int i = 0; i < n_slots; ++i) {
     if (check_cuda(cudaEventCreateWithFlags(&copied[i], cudaEventDisableTiming), "event") ||
         check_cuda(cudaEventCreateWithFlags(&consumed[i], cudaEventDisableTiming), "event"))
@@ -668,10 +681,21 @@ int scan_host_impl(void* stream, void* copy_stream, const sgmc_glm_spec* spec,
                             dst + (size_t)n * d, src.pull_ctas);
     } else {
       const float* hb = src.host_batches + (k % src.host_batch_count) * host_stride;
-      cudaMemcpyAsync(dst + (size_t)rank * (sharded ? rows_local : 0) * d, hb,
-                      (size_t)rows_local * d * 4, cudaMemcpyHostToDevice, hs);
-      cudaMemcpyAsync(dst + (size_t)n * d, hb + (size_t)rows_local * d, (size_t)n * 4,
+      const int64_t row0 = (int64_t)rank * (sharded ? rows_local : 0);
+      if (hybrid && rows_dma < rows_local) {
+        // the tail of the slice is pulled by the GPU while the DMA engine copies its head
+        cudaStreamWaitEvent(ps, consumed[sl], 0);
+        if (rc == 0)
+          rc = sgmc_pull_rows(ps, src.X_mapped, nullptr, src.idx_all + k * n, n, row0 + rows_dma,
+                              rows_local - rows_dma, d, dst, nullptr, src.pull_ctas);
+        cudaEventRecord(pulled[sl], ps);
+      }
+      if (rows_dma > 0)
+        cudaMemcpyAsync(dst + (size_t)row0 * d, hb, (size_t)rows_dma * d * 4,
+                        cudaMemcpyHostToDevice, hs);
+      cudaMemcpyAsync(dst + (size_t)n * d, hb + (size_t)rows_dma * d, (size_t)n * 4,
                       cudaMemcpyHostToDevice, hs);
+      if (hybrid && rows_dma < rows_local) cudaStreamWaitEvent(hs, pulled[sl], 0);
     }
     if (sharded && rc == 0)
       rc = sgmc_nccl_allgather(nccl_comm, hs, dst + (size_t)rank * rows_local * d, dst,
@@ -747,6 +771,12 @@ int scan_host_impl(void* stream, void* copy_stream, const sgmc_glm_spec* spec,
   // events can go (destruction is deferred by the runtime until they have completed)
   for (int i = 0; i < n_slots; ++i) { cudaEventDestroy(copied[i]); cudaEventDestroy(consumed[i]); }
   for (int i = 0; i < 2; ++i) { cudaEventDestroy(computed[i]); cudaEventDestroy(read_back[i]); }
+  if (hybrid) {
+    cudaEventRecord(begin, ps);
+    cudaStreamWaitEvent(cs, begin, 0);
+    for (int i = 0; i < n_slots; ++i) cudaEventDestroy(pulled[i]);
+    cudaStreamDestroy(ps);
+  }
   cudaEventDestroy(begin);
   cudaStreamDestroy(rs);
   cudaStreamDestroy(hs);
@@ -770,6 +800,33 @@ int sgmc_glm_sgld_scan_host(void* stream, void* copy_stream, const sgmc_glm_spec
   HostSource src;
   src.host_batches = host_batches;
   src.host_batch_count = host_batch_count;
+  return scan_host_impl(stream, copy_stream, spec, theta, v, n_chains, P, src, n_steps,
+                        batch_size, observation_count, device_slots, n_slots,
+                        potential_variance, host_results, grad, keys_a, keys_b, step_sizes,
+                        temperature, alpha, lmbd, workspace, workspace_bytes, path, prng_layout,
+                        nccl_comm, rank, n_ranks, keep, samples_out, scalars_out, capacity, kept);
+}
+
+int sgmc_glm_sgld_scan_hybrid(void* stream, void* copy_stream, const sgmc_glm_spec* spec,
+                              float* theta, float* v, int64_t n_chains, int64_t P,
+                              const float* host_batches, int64_t host_batch_count,
+                              int64_t rows_dma, const float* X_mapped, const int32_t* idx_all,
+                              int pull_ctas, int64_t n_steps, int64_t batch_size,
+                              int64_t observation_count, float* device_slots, int n_slots,
+                              float* potential_variance, float* host_results, float* grad,
+                              uint32_t* keys_a, uint32_t* keys_b, const float* step_sizes,
+                              float temperature, float alpha, float lmbd, void* workspace,
+                              size_t workspace_bytes, int path, int prng_layout,
+                              void* nccl_comm, int rank, int n_ranks, const uint8_t* keep,
+                              float* samples_out, float* scalars_out, int64_t capacity,
+                              int64_t* kept) {
+  HostSource src;
+  src.host_batches = host_batches;
+  src.host_batch_count = host_batch_count;
+  src.rows_dma = rows_dma;
+  src.X_mapped = X_mapped;
+  src.idx_all = idx_all;
+  src.pull_ctas = pull_ctas;
   return scan_host_impl(stream, copy_stream, spec, theta, v, n_chains, P, src, n_steps,
                         batch_size, observation_count, device_slots, n_slots,
                         potential_variance, host_results, grad, keys_a, keys_b, step_sizes,

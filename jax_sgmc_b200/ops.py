@@ -409,6 +409,35 @@ def glm_sgld_scan_pull(spec, theta, X_mapped: int, y_mapped: int, idx_all, n_ste
   return int(cnt.value)
 
 
+def glm_sgld_scan_hybrid(spec, theta, host_batches_ptr, host_batch_count, rows_dma, X_mapped: int,
+                         idx_all, n_steps, batch_size, observation_count, device_slots, n_slots,
+                         potential_variance, host_results_ptr, grad, keys_a, keys_b, step_sizes,
+                         copy_stream, temperature=1.0, v=None, alpha=0.9, lmbd=1e-5,
+                         workspace=None, path=0, layout=0, stream=None, nccl_comm=None, rank=0,
+                         n_ranks=1, keep=None, samples_out=None, scalars_out=None, kept: int = 0,
+                         pull_ctas=0) -> int:
+  """The host scan with both transports (see sgmc_glm_sgld_scan_hybrid): the first
+  ``rows_dma`` rows of every minibatch (slice) from the staged host batches, the rest pulled
+  by the GPU out of the registered data set."""
+  C_, P = theta.shape
+  ss = np.ascontiguousarray(step_sizes, np.float32)
+  assert ss.size >= n_steps
+  kp = None if keep is None else np.ascontiguousarray(keep, np.uint8)
+  cnt = C.c_int64(int(kept))
+  cap = 0 if samples_out is None else samples_out.shape[0]
+  _lib.call("sgmc_glm_sgld_scan_hybrid", _s(stream), copy_stream.handle, C.byref(spec),
+            vp(theta), vp(v), C_, P, C.c_void_p(host_batches_ptr), int(host_batch_count),
+            int(rows_dma), C.c_void_p(X_mapped), vp(idx_all), int(pull_ctas), int(n_steps),
+            int(batch_size), int(observation_count), vp(device_slots), int(n_slots),
+            vp(potential_variance), C.c_void_p(host_results_ptr), vp(grad), vp(keys_a),
+            vp(keys_b), ss.ctypes.data_as(C.c_void_p), float(temperature), float(alpha),
+            float(lmbd), vp(workspace), workspace.nbytes, PATH[path], _layout(layout),
+            None if nccl_comm is None else C.c_void_p(nccl_comm), int(rank), int(n_ranks),
+            None if kp is None else kp.ctypes.data_as(C.c_void_p), vp(samples_out),
+            vp(scalars_out), int(cap), C.byref(cnt))
+  return int(cnt.value)
+
+
 def host_gather_batches(dst_ptr: int, X: np.ndarray, y: np.ndarray, idx: np.ndarray, row0: int,
                         rows: int, n_threads: int):
   """Threaded host gather into a page-locked staging buffer (see

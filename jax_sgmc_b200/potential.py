@@ -220,11 +220,19 @@ class _PotentialFn:
       return None
     rows = n // world
     pull = bool(getattr(loader, "pull", False)) or os.environ.get("SGMC_HOST_PULL", "0") == "1"
-    host_stride, dev_stride = rows * d + n, n * d + n
+    # hybrid: a fraction of every minibatch (slice) is pulled by the GPU while the host
+    # gathers and the DMA engine copies the rest (sgmc_glm_sgld_scan_hybrid)
+    frac = float(os.environ.get("SGMC_HOST_PULL_FRACTION", getattr(loader, "pull_fraction", 0.0)))
+    rows_pull = 0 if pull else min(rows, int(round(frac * rows / 8.0)) * 8)
+    hybrid = rows_pull > 0 and rows_pull < rows
+    if rows_pull >= rows:
+      pull = True
+    rows_dma = rows - rows_pull if hybrid else rows
+    host_stride, dev_stride = rows_dma * d + n, n * d + n
     K = len(step_sizes)
     CH = max(2, min(int(source["chunk"]), 512 if pull else 64, K))
     CH -= CH % 2                       # the chain keys ping-pong once per step
-    key = ("host_stream", C, sample.n_params, n, path, CH, world, pull)
+    key = ("host_stream", C, sample.n_params, n, path, CH, world, pull, rows_dma)
     buf = self._buffers.get(key)
     if buf is None:
       res, res_addr = _pinned_array(CH * 2 * C)
@@ -232,11 +240,11 @@ class _PotentialFn:
              "slots": DeviceArray((3 * dev_stride,), np.float32),
              "uv": DeviceArray((2, 2, C), np.float32), "copy": Stream.create(),
              "ws": ops.glm_workspace(C, n, spec.d, path)}
-      if pull:
+      if pull or hybrid:
         hidx, hidx_addr = _pinned_array(2 * CH * n)
         buf.update(hidx=hidx.view(np.int32).reshape(2, CH, n), hidx_addr=hidx_addr,
                    didx=DeviceArray((2, CH, n), np.int32))
-      else:
+      if not pull:
         ring, ring_addr = _pinned_array(2 * CH * host_stride,
                                         write_combined=os.environ.get("SGMC_RING_WC", "0") == "1")
         buf.update(ring=ring, ring_addr=ring_addr)
@@ -247,18 +255,18 @@ class _PotentialFn:
     threads = max(1, int(os.environ.get("SGMC_GATHER_THREADS", os.cpu_count() or 1)) //
                   max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1"))))
     main = current_stream()
-    Xm = loader.mapped(self.likelihood.x) if pull else 0
+    Xm = loader.mapped(self.likelihood.x) if (pull or hybrid) else 0
     ym = loader.mapped(self.likelihood.y) if pull else 0
 
     def produce(count, half):
       # index draw (the chain's NumPy PCG64 pipeline) of one chunk, then (staged mode) the
       # row gather; runs in a worker thread beside the device's work on the previous chunk
       idx_rows = source["draw"](count)
-      if pull:
+      if pull or hybrid:
         buf["hidx"][half, :count] = idx_rows
-      else:
+      if not pull:
         ops.host_gather_batches(buf["ring_addr"] + half * CH * host_stride * 4, X, y, idx_rows,
-                                rank * rows, rows, threads)
+                                rank * rows, rows_dma, threads)
 
     ss = np.ascontiguousarray(step_sizes, np.float32)
     kp = None if keep is None else np.ascontiguousarray(keep, np.uint8)
@@ -266,7 +274,11 @@ class _PotentialFn:
     done, half, last_k = 0, 0, 0
     produce(min(CH, K), 0)
     trace = []
+    prof = os.environ.get("SGMC_HOST_SCAN_TRACE") == "1"
+    import time as _time
+    t_enq = t_gpu = t_join = t_host = 0.0
     while done < K:
+      t_a = _time.perf_counter()
       k = min(CH, K - done)
       worker = None
       if done + k < K:
@@ -276,9 +288,16 @@ class _PotentialFn:
                     lmbd=lmbd, workspace=buf["ws"], path=path, nccl_comm=nccl, rank=rank,
                     n_ranks=world, keep=None if kp is None else kp[done:done + k],
                     samples_out=samples_out, scalars_out=scalars_out, kept=kept)
-      if pull:
+      if pull or hybrid:
         didx = buf["didx"].row_slice(half, half + 1)
         didx.copy_from_pinned(buf["hidx_addr"] + half * CH * n * 4, k * n * 4, buf["copy"])
+      if hybrid:
+        kept = ops.glm_sgld_scan_hybrid(
+            spec, sample.flat, buf["ring_addr"] + half * CH * host_stride * 4, k, rows_dma, Xm,
+            didx, k, n, N, buf["slots"], 3, buf["uv"], buf["res_addr"], grad_out, keys_a, keys_b,
+            ss[done:done + k], buf["copy"],
+            pull_ctas=int(os.environ.get("SGMC_PULL_CTAS", "0")), **common)
+      elif pull:
         kept = ops.glm_sgld_scan_pull(
             spec, sample.flat, Xm, ym, didx, k, n, N, buf["slots"], 3, buf["uv"],
             buf["res_addr"], grad_out, keys_a, keys_b, ss[done:done + k], buf["copy"],
@@ -288,12 +307,21 @@ class _PotentialFn:
             spec, sample.flat, buf["ring_addr"] + half * CH * host_stride * 4, k, k, n, N,
             buf["slots"], 3, buf["uv"], buf["res_addr"], grad_out, keys_a, keys_b,
             ss[done:done + k], buf["copy"], **common)
+      t_b = _time.perf_counter()
       main.sync()
       buf["copy"].sync()
+      t_c = _time.perf_counter()
       trace.append(buf["res"][:k * 2 * C].reshape(k, 2, C)[:, 0].mean(axis=1))   # host reads U
+      t_d = _time.perf_counter()
       if worker is not None:
         worker.join()
+      t_e = _time.perf_counter()
+      t_enq += t_b - t_a; t_gpu += t_c - t_b; t_host += t_d - t_c; t_join += t_e - t_d
       done, half, last_k = done + k, 1 - half, k
+    if prof:
+      print(f"host scan: {K} steps, chunks of {CH}: enqueue {t_enq * 1e6 / K:.1f} us/step, "
+            f"wait for the device {t_gpu * 1e6 / K:.1f}, host reads {t_host * 1e6 / K:.1f}, "
+            f"wait for the gather worker {t_join * 1e6 / K:.1f}", flush=True)
     self.last_potential_trace = np.concatenate(trace) if trace else np.zeros(0, np.float32)
     if last_k:                          # LangevinState.potential / .variance of the last step
       last = buf["uv"].row_slice((last_k - 1) & 1, ((last_k - 1) & 1) + 1).reshape(2, C)
@@ -301,8 +329,9 @@ class _PotentialFn:
         U_out.copy_from(last.row_slice(0, 1).reshape(C))
       if var_out is not None:
         var_out.copy_from(last.row_slice(1, 2).reshape(C))
-    self.host_link_mode = "pull" if pull else "staged"
-    self.h2d_bytes_per_step = (rows * d + n) * 4 + (n * 4 if pull else 0)   # + the index row
+    self.host_link_mode = "pull" if pull else (f"hybrid({rows_pull}/{rows} rows pulled)" if hybrid
+                                               else "staged")
+    self.h2d_bytes_per_step = (rows * d + n) * 4 + (n * 4 if (pull or hybrid) else 0)   # + the index row
     self.d2h_bytes_per_step = 2 * C * 4
     return kept
 

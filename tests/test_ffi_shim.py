@@ -29,7 +29,8 @@ NOT_CUSTOM_CALLS = {
     "sgmc_get_option", "sgmc_host_register", "sgmc_host_unregister",
     # whole scans: host schedules, several streams, host memory -- they replace lax.scan
     # itself and are driven from Python, not from inside an XLA computation
-    "sgmc_glm_sgld_scan_host", "sgmc_glm_sgld_scan_pull", "sgmc_glm_sgld_scan_device",
+    "sgmc_glm_sgld_scan_host", "sgmc_glm_sgld_scan_pull", "sgmc_glm_sgld_scan_hybrid",
+    "sgmc_glm_sgld_scan_device",
     "sgmc_host_gather_batches", "sgmc_pull_rows", "sgmc_glm_prepare_minibatch",
     # communicator handles / peer memory (set up from Python, one process per GPU)
     "sgmc_nccl_available", "sgmc_nccl_unique_id", "sgmc_nccl_init", "sgmc_nccl_destroy",

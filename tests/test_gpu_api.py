@@ -255,7 +255,7 @@ def test_sample_ring_equals_device_buffer(gpu, direct, monkeypatch):
                             a[0]["samples"]["variables"]["w"][-1])
 
 
-@pytest.mark.parametrize("link", ["pull", "staged"])
+@pytest.mark.parametrize("link", ["pull", "staged", "hybrid"])
 def test_streaming_loader_equals_resident_loader(gpu, monkeypatch, link):
   """StreamingNumpyDataLoader feeds the chains the same minibatches as
   the HBM-resident NumpyDataLoader: identical samples, several cache refills deep --
@@ -263,6 +263,7 @@ def test_streaming_loader_equals_resident_loader(gpu, monkeypatch, link):
   (default) and with the rows pulled by the GPU out of the mapped host arrays."""
   from jax_sgmc_b200 import alias, data, glm, potential
   monkeypatch.setenv("SGMC_HOST_PULL", "1" if link == "pull" else "0")
+  monkeypatch.setenv("SGMC_HOST_PULL_FRACTION", "0.34" if link == "hybrid" else "0")
   X, y, _ = odata.logistic_dataset(700, 16, seed=4)
   pot = potential.minibatch_potential(glm.GaussianPrior(5.0), glm.LogisticRegression(),
                                       strategy="vmap", path="simt")
@@ -278,7 +279,7 @@ def test_streaming_loader_equals_resident_loader(gpu, monkeypatch, link):
   assert a["sample_count"] == b["sample_count"] == 40
   assert np.array_equal(a["samples"]["variables"]["w"], b["samples"]["variables"]["w"])
   assert np.array_equal(a["samples"]["likelihood"], b["samples"]["likelihood"])
-  assert pot.host_link_mode == link
+  assert pot.host_link_mode.startswith(link)
   # many chains share the one stream of minibatches
   loader = data.StreamingNumpyDataLoader(x=X, y=y)
   run = alias.sgld(pot, loader, cache_size=4, batch_size=24, first_step_size=1e-2,
