@@ -38,6 +38,19 @@ class MlpSpec(C.Structure):
               ("temperature", C.c_float)]
 
 
+CNN_MAX_CONV = 4
+
+
+class CnnSpec(C.Structure):
+  """``sgmc_cnn_spec`` (include/sgmc_b200.h)."""
+  _fields_ = [("n_conv", C.c_int32), ("height", C.c_int32), ("width", C.c_int32),
+              ("channels", C.c_int32 * (CNN_MAX_CONV + 1)), ("stride", C.c_int32 * CNN_MAX_CONV),
+              ("n_classes", C.c_int32), ("w_off", C.c_int64 * (CNN_MAX_CONV + 1)),
+              ("b_off", C.c_int64 * (CNN_MAX_CONV + 1)), ("prior", C.c_int32),
+              ("prior_off", C.c_int64), ("prior_size", C.c_int64), ("prior_scale", C.c_float),
+              ("temperature", C.c_float)]
+
+
 _vp, _i64, _i32, _f32, _sz = C.c_void_p, C.c_int64, C.c_int32, C.c_float, C.c_size_t
 _int = C.c_int
 
@@ -125,6 +138,8 @@ PROTOTYPES = {
                                 _vp, _int, _i64, _i64, _i64, _vp, _int, _vp, _vp, _vp, _vp, _vp,
                                 _vp, _f32, _f32, _f32, _vp, _sz, _int, _int, _vp, _int, _int,
                                 _vp, _vp, _vp, _i64, C.POINTER(_i64)],
+    "sgmc_cnn_potential_grad": [_vp, C.POINTER(CnnSpec), _vp, _i64, _i64, _vp, _vp, _vp, _vp, _i64,
+                                _i64, _vp, _vp, _vp, _vp, _vp, _sz],
     "sgmc_glm_potential_grad_row_sharded": [_vp, C.POINTER(GlmSpec), _vp, _i64, _i64, _vp, _vp,
                                             _vp, _i64, _i64, _vp, _vp, _vp, _vp, _sz, _int, _vp,
                                             _int, _int, _vp],
@@ -181,6 +196,7 @@ SPECIAL = {
     "sgmc_p2p_window_bytes": ([_int, _sz], _sz),
     "sgmc_mlp_workspace_bytes": ([C.POINTER(MlpSpec), _i64, _i64], _sz),
     "sgmc_glm_fisher_scratch_floats": ([_i64, _i64, _i64], _sz),
+    "sgmc_cnn_workspace_bytes": ([C.POINTER(CnnSpec), _i64, _i64], _sz),
 }
 
 _lib = None

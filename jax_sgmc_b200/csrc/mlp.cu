@@ -15,6 +15,8 @@
 // micro-tiles, FFMA; operand loads are scalar and bounds-checked so any offset /
 // alignment of the layers inside the raveled sample works (the reference's pytrees put
 // biases of 10 floats between the weight matrices).
+#include <algorithm>
+
 #include "common.cuh"
 #include "glm_math.cuh"
 
@@ -328,11 +330,327 @@ static int mlp_check(const sgmc_mlp_spec* s, int64_t P) {
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------
+// Convolutional classifier (BASELINE.json configs[4]: SGGMC / AMAGOLD on a CIFAR-10-shape
+// CNN): 3x3 convolutions with zero padding 1 and stride 1 or 2, tanh, then one dense layer
+// on the flattened NHWC feature map and the softmax cross entropy of the head above.  Every
+// chain has its own filters, the minibatch is shared: a convolution is im2col (patch index
+// (kh*3 + kw)*Cin + cin, the row-major order of the HWIO filter tensor) followed by the
+// chain-batched GEMM of the dense layers; its reverse pass is the same two GEMMs as a dense
+// layer (dW = patches^T . dZ, dPatches = dZ . W^T) followed by col2im.
+struct ConvGeom {
+  int n, Hi, Wi, Cin, Ho, Wo, stride;
+};
+
+// dst[b][(i, ho, wo)][(kh*3 + kw)*Cin + c] = src[b][i'][ho*s + kh - 1][wo*s + kw - 1][c]
+// (zero outside); i' = idx[i] when the source is the data set itself (first layer).
+__global__ void __launch_bounds__(256) k_im2col(const float* __restrict__ src, int64_t src_batch,
+                                                const int32_t* __restrict__ idx, float* __restrict__ dst,
+                                                const ConvGeom g, int64_t total_per_batch) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int64_t b = blockIdx.y;
+  const int K = 9 * g.Cin;
+  for (int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x; e < total_per_batch;
+       e += (int64_t)gridDim.x * 256) {
+    const int k = (int)(e % K);
+    const int64_t row = e / K;
+    const int c = k % g.Cin, kk = k / g.Cin, kh = kk / 3, kw = kk - kh * 3;
+    const int wo = (int)(row % g.Wo);
+    const int64_t r2 = row / g.Wo;
+    const int ho = (int)(r2 % g.Ho);
+    const int i = (int)(r2 / g.Ho);
+    const int hi = ho * g.stride + kh - 1, wi = wo * g.stride + kw - 1;
+    float v = 0.f;
+    if (hi >= 0 && hi < g.Hi && wi >= 0 && wi < g.Wi) {
+      const int64_t obs = idx ? idx[i] : i;
+      v = __ldg(src + b * src_batch + ((obs * g.Hi + hi) * g.Wi + wi) * g.Cin + c);
+    }
+    dst[b * total_per_batch + e] = v;
+  }
+}
+
+// dZ[b][(i, hi, wi)][c] = (sum over the patches that contain input pixel (hi, wi)) dP * (1 - h^2)
+__global__ void __launch_bounds__(256) k_col2im_dtanh(const float* __restrict__ dP,
+                                                      const float* __restrict__ h,
+                                                      float* __restrict__ dZ, const ConvGeom g,
+                                                      int64_t in_per_batch) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int64_t b = blockIdx.y;
+  const int K = 9 * g.Cin;
+  const int64_t rows = (int64_t)g.n * g.Ho * g.Wo;
+  for (int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x; e < in_per_batch;
+       e += (int64_t)gridDim.x * 256) {
+    const int c = (int)(e % g.Cin);
+    const int64_t r1 = e / g.Cin;
+    const int wi = (int)(r1 % g.Wi);
+    const int64_t r2 = r1 / g.Wi;
+    const int hi = (int)(r2 % g.Hi);
+    const int i = (int)(r2 / g.Hi);
+    float s = 0.f;
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) {
+      const int th = hi + 1 - kh;
+      if (th < 0 || th % g.stride) continue;
+      const int ho = th / g.stride;
+      if (ho >= g.Ho) continue;
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        const int tw = wi + 1 - kw;
+        if (tw < 0 || tw % g.stride) continue;
+        const int wo = tw / g.stride;
+        if (wo >= g.Wo) continue;
+        const int64_t row = ((int64_t)i * g.Ho + ho) * g.Wo + wo;
+        s += dP[(b * rows + row) * K + (kh * 3 + kw) * g.Cin + c];
+      }
+    }
+    const float hv = h[b * in_per_batch + e];
+    dZ[b * in_per_batch + e] = s * (1.0f - hv * hv);
+  }
+}
+
+// db[c][o] = sum over `rows` rows of dZ[c][row][o] (+ prior term): 32 columns x 8 row lanes
+__global__ void __launch_bounds__(256) k_colsum_grad(const float* __restrict__ dZ, int64_t rows,
+                                                     int out, const float* __restrict__ theta,
+                                                     float* __restrict__ grad, int64_t P,
+                                                     int64_t b_off, float coef, int64_t prior_lo,
+                                                     int64_t prior_hi) {
+  pdl_launch_dependents();
+  pdl_wait();
+  __shared__ float red[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int o = blockIdx.x * 32 + tx;
+  const int64_t c = blockIdx.y;
+  float s = 0.f;
+  if (o < out) {
+    const float* src = dZ + c * rows * out + o;
+    for (int64_t r = ty; r < rows; r += 8) s += src[r * out];
+  }
+  red[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0 && o < out) {
+    float t = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) t += red[q][tx];
+    const int64_t p = b_off + o;
+    if (p >= prior_lo && p < prior_hi) t = fmaf(coef, theta[c * P + p], t);
+    grad[c * P + p] = t;
+  }
+}
+
+struct CnnLayer {
+  ConvGeom g;
+  int64_t rows, K;       // rows = n * Ho * Wo, K = 9 * Cin
+  int Cout;
+};
+
+struct CnnWs {
+  float* P[SGMC_CNN_MAX_CONV];       // patches (layer 0: shared by the chains)
+  float* H[SGMC_CNN_MAX_CONV + 1];   // H[l + 1] = tanh output of conv layer l
+  float* dZ[SGMC_CNN_MAX_CONV + 1];  // dZ[l + 1] = gradient w.r.t. the pre-activation of layer l
+  float* dP;                         // largest patch-gradient buffer (layers >= 1)
+  float* logits; float* dlogits; float* ell; float* sumsq;
+};
+
+static int cnn_layers(const sgmc_cnn_spec& s, int64_t n, CnnLayer* L) {
+  int Hi = s.height, Wi = s.width;
+  for (int l = 0; l < s.n_conv; ++l) {
+    const int st = s.stride[l];
+    CnnLayer& q = L[l];
+    q.g.n = (int)n; q.g.Hi = Hi; q.g.Wi = Wi; q.g.Cin = s.channels[l]; q.g.stride = st;
+    q.g.Ho = (Hi + 2 - 3) / st + 1; q.g.Wo = (Wi + 2 - 3) / st + 1;
+    q.rows = n * (int64_t)q.g.Ho * q.g.Wo; q.K = 9 * (int64_t)s.channels[l];
+    q.Cout = s.channels[l + 1];
+    Hi = q.g.Ho; Wi = q.g.Wo;
+  }
+  return Hi * Wi * s.channels[s.n_conv];      // features of the dense head
+}
+
+static size_t cnn_carve(CnnWs* w, uint8_t* base, const sgmc_cnn_spec& s, int64_t C, int64_t n) {
+  CnnLayer L[SGMC_CNN_MAX_CONV];
+  cnn_layers(s, n, L);
+  size_t off = 0;
+  auto take = [&](size_t floats) {
+    float* p = base ? reinterpret_cast<float*>(base + off) : nullptr;
+    off += (floats * 4 + 255) & ~(size_t)255;
+    return p;
+  };
+  size_t dp_max = 0;
+  for (int l = 0; l < s.n_conv; ++l) {
+    float* p = take((size_t)(l == 0 ? 1 : C) * L[l].rows * L[l].K);
+    float* h = take((size_t)C * L[l].rows * L[l].Cout);
+    float* d = take((size_t)C * L[l].rows * L[l].Cout);
+    if (l > 0) dp_max = std::max(dp_max, (size_t)C * L[l].rows * L[l].K);
+    if (w) { w->P[l] = p; w->H[l + 1] = h; w->dZ[l + 1] = d; }
+  }
+  float* dp = take(dp_max ? dp_max : 1);
+  float* lg = take((size_t)C * n * s.n_classes);
+  float* dl = take((size_t)C * n * s.n_classes);
+  float* ell = take((size_t)C * n);
+  float* sq = take((size_t)C * kSumsqParts);
+  if (w) { w->dP = dp; w->logits = lg; w->dlogits = dl; w->ell = ell; w->sumsq = sq; }
+  return off;
+}
+
+static int cnn_check(const sgmc_cnn_spec* s, int64_t P) {
+  SGMC_REQUIRE(s != nullptr, "null spec");
+  SGMC_REQUIRE(s->n_conv >= 1 && s->n_conv <= SGMC_CNN_MAX_CONV, "1..%d conv layers",
+               SGMC_CNN_MAX_CONV);
+  SGMC_REQUIRE(s->height > 0 && s->width > 0 && s->n_classes > 0, "bad geometry");
+  SGMC_REQUIRE(s->prior == kPriorFlat || s->prior == kPriorGaussian, "prior: flat or gaussian");
+  int Hi = s->height, Wi = s->width;
+  for (int l = 0; l < s->n_conv; ++l) {
+    SGMC_REQUIRE(s->channels[l] > 0 && s->channels[l + 1] > 0, "channels must be positive");
+    SGMC_REQUIRE(s->stride[l] == 1 || s->stride[l] == 2, "stride 1 or 2");
+    SGMC_REQUIRE(s->w_off[l] >= 0 && s->w_off[l] + 9ll * s->channels[l] * s->channels[l + 1] <= P &&
+                 s->b_off[l] >= 0 && s->b_off[l] + s->channels[l + 1] <= P,
+                 "conv layer %d lies outside the sample", l);
+    Hi = (Hi - 1) / s->stride[l] + 1; Wi = (Wi - 1) / s->stride[l] + 1;
+  }
+  const int64_t F = (int64_t)Hi * Wi * s->channels[s->n_conv];
+  SGMC_REQUIRE(s->w_off[s->n_conv] >= 0 && s->w_off[s->n_conv] + F * s->n_classes <= P &&
+               s->b_off[s->n_conv] >= 0 && s->b_off[s->n_conv] + s->n_classes <= P,
+               "the dense head lies outside the sample");
+  return 0;
+}
+
 }  // namespace sgmc
 
 using namespace sgmc;
 
 extern "C" {
+
+size_t sgmc_cnn_workspace_bytes(const sgmc_cnn_spec* spec, int64_t n_chains, int64_t batch_size) {
+  if (!spec || spec->n_conv < 1 || spec->n_conv > SGMC_CNN_MAX_CONV) return 0;
+  return cnn_carve(nullptr, nullptr, *spec, n_chains, batch_size) + 256;
+}
+
+int sgmc_cnn_potential_grad(void* stream, const sgmc_cnn_spec* spec, const float* theta,
+                            int64_t n_chains, int64_t P, const float* X, const float* y,
+                            const int32_t* idx, const float* mask, int64_t batch_size,
+                            int64_t observation_count, float* potential, float* variance,
+                            float* grad, float* ell, void* workspace, size_t workspace_bytes) {
+  if (int e = cnn_check(spec, P)) return e;
+  SGMC_REQUIRE(theta && X && y && potential && workspace, "null argument");
+  const int64_t C = n_chains, n = batch_size;
+  SGMC_REQUIRE(C > 0 && C <= 65535 && n > 0 && n <= (1 << 20), "bad sizes");
+  SGMC_REQUIRE(workspace_bytes >= sgmc_cnn_workspace_bytes(spec, C, n), "workspace too small");
+  const sgmc_cnn_spec& sp = *spec;
+  const int NL = sp.n_conv;
+  cudaStream_t s = (cudaStream_t)stream;
+  CnnWs w{};
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(workspace) + 255) &
+                                             ~(uintptr_t)255);
+  cnn_carve(&w, base, sp, C, n);
+  CnnLayer L[SGMC_CNN_MAX_CONV];
+  const int F = cnn_layers(sp, n, L);
+  for (int l = 0; l < NL; ++l)
+    SGMC_REQUIRE(L[l].rows < (1ll << 31) && L[l].rows * L[l].K < (1ll << 40), "layer %d too large", l);
+  const bool gauss = sp.prior == kPriorGaussian;
+  const int64_t prior_lo = gauss ? sp.prior_off : 0, prior_hi = gauss ? sp.prior_off + sp.prior_size : 0;
+  const float inv_T = 1.0f / sp.temperature;
+  const float coef = gauss ? (1.0f / (sp.prior_scale * sp.prior_scale)) / sp.temperature : 0.f;
+  auto blocks = [](int64_t total) { return (unsigned)std::min<int64_t>((total + 255) / 256, 148 * 32); };
+
+  if (gauss && prior_hi > prior_lo) {
+    launch_pdl(k_mlp_sumsq, dim3(kSumsqParts, (unsigned)C), dim3(256), 0, s, theta, P, prior_lo,
+               prior_hi, w.sumsq);
+    if (post_launch("k_mlp_sumsq")) return 1;
+  }
+  // ---- forward ---------------------------------------------------------------------------
+  for (int l = 0; l < NL; ++l) {
+    const int64_t per = L[l].rows * L[l].K;
+    const int64_t in_per = (int64_t)n * L[l].g.Hi * L[l].g.Wi * L[l].g.Cin;
+    if (l == 0)
+      launch_pdl(k_im2col, dim3(blocks(per), 1), dim3(256), 0, s, X, (int64_t)0, idx, w.P[0], L[0].g, per);
+    else
+      launch_pdl(k_im2col, dim3(blocks(per), (unsigned)C), dim3(256), 0, s, (const float*)w.H[l],
+                 in_per, (const int32_t*)nullptr, w.P[l], L[l].g, per);
+    if (post_launch("k_im2col")) return 1;
+    BgemmArgs g{};
+    g.A = w.P[l]; g.a_batch = l == 0 ? 0 : per; g.lda = L[l].K;
+    g.B = theta + sp.w_off[l]; g.b_batch = P; g.ldb = L[l].Cout;
+    g.C = w.H[l + 1]; g.c_batch = L[l].rows * L[l].Cout; g.ldc = L[l].Cout;
+    g.M = (int)L[l].rows; g.N = L[l].Cout; g.K = (int)L[l].K;
+    g.bias = theta + sp.b_off[l]; g.bias_batch = P;
+    if (launch_bgemm<false, false, kEpiBiasTanh>(s, g, C, "k_bgemm<conv,tanh>")) return 1;
+  }
+  {   // dense head on the flattened NHWC map: logits [n, K] = H_L [n, F] . W [F, K] + b
+    BgemmArgs g{};
+    g.A = w.H[NL]; g.a_batch = n * (int64_t)F; g.lda = F;
+    g.B = theta + sp.w_off[NL]; g.b_batch = P; g.ldb = sp.n_classes;
+    g.C = w.logits; g.c_batch = n * (int64_t)sp.n_classes; g.ldc = sp.n_classes;
+    g.M = (int)n; g.N = sp.n_classes; g.K = F;
+    g.bias = theta + sp.b_off[NL]; g.bias_batch = P;
+    if (launch_bgemm<false, false, kEpiBias>(s, g, C, "k_bgemm<head>")) return 1;
+  }
+  HeadArgs h{};
+  h.logits = w.logits; h.dlogits = grad ? w.dlogits : nullptr; h.ell_ws = w.ell; h.ell_out = ell;
+  h.y = y; h.idx = idx; h.mask = mask; h.n = (int)n; h.K = sp.n_classes;
+  h.n_obs = (float)observation_count; h.inv_temperature = inv_T;
+  h.prior_half_inv = gauss ? 0.5f / (sp.prior_scale * sp.prior_scale) : 0.f;
+  h.sumsq_parts = gauss && prior_hi > prior_lo ? w.sumsq : nullptr;
+  h.potential = potential; h.variance = variance;
+  launch_pdl(k_mlp_head, dim3((unsigned)C), dim3(256), 0, s, h);
+  if (post_launch("k_mlp_head")) return 1;
+  if (!grad) return 0;
+  // ---- reverse pass: head ------------------------------------------------------------------
+  launch_pdl(k_colsum_grad, dim3((unsigned)((sp.n_classes + 31) / 32), (unsigned)C), dim3(256), 0, s,
+             (const float*)w.dlogits, n, sp.n_classes, theta, grad, P, (int64_t)sp.b_off[NL], coef,
+             prior_lo, prior_hi);
+  if (post_launch("k_colsum_grad")) return 1;
+  {   // dW_head [F, K] = H_L^T [F, n] . dlogits [n, K]
+    BgemmArgs g{};
+    g.A = w.H[NL]; g.a_batch = n * (int64_t)F; g.lda = F;
+    g.B = w.dlogits; g.b_batch = n * (int64_t)sp.n_classes; g.ldb = sp.n_classes;
+    g.C = grad + sp.w_off[NL]; g.c_batch = P; g.ldc = sp.n_classes;
+    g.M = F; g.N = sp.n_classes; g.K = (int)n;
+    g.aux = theta + sp.w_off[NL]; g.aux_batch = P; g.ldaux = sp.n_classes;
+    g.coef = coef; g.p0 = sp.w_off[NL]; g.prior_lo = prior_lo; g.prior_hi = prior_hi;
+    if (launch_bgemm<true, false, kEpiPrior>(s, g, C, "k_bgemm<dW head>")) return 1;
+  }
+  {   // dZ_L [n, F] = (dlogits [n, K] . W^T [K, F]) * (1 - H_L^2)
+    BgemmArgs g{};
+    g.A = w.dlogits; g.a_batch = n * (int64_t)sp.n_classes; g.lda = sp.n_classes;
+    g.B = theta + sp.w_off[NL]; g.b_batch = P; g.ldb = sp.n_classes;      // stored [F][K] = N x K
+    g.C = w.dZ[NL]; g.c_batch = n * (int64_t)F; g.ldc = F;
+    g.M = (int)n; g.N = F; g.K = sp.n_classes;
+    g.aux = w.H[NL]; g.aux_batch = n * (int64_t)F; g.ldaux = F;
+    if (launch_bgemm<false, true, kEpiDtanh>(s, g, C, "k_bgemm<dH head>")) return 1;
+  }
+  // ---- reverse pass: convolutions ------------------------------------------------------------
+  for (int l = NL - 1; l >= 0; --l) {
+    const int64_t per = L[l].rows * L[l].K;
+    launch_pdl(k_colsum_grad, dim3((unsigned)((L[l].Cout + 31) / 32), (unsigned)C), dim3(256), 0, s,
+               (const float*)w.dZ[l + 1], L[l].rows, L[l].Cout, theta, grad, P,
+               (int64_t)sp.b_off[l], coef, prior_lo, prior_hi);
+    if (post_launch("k_colsum_grad")) return 1;
+    {   // dW_l [9 Cin, Cout] = patches^T [9 Cin, rows] . dZ [rows, Cout]
+      BgemmArgs g{};
+      g.A = w.P[l]; g.a_batch = l == 0 ? 0 : per; g.lda = L[l].K;
+      g.B = w.dZ[l + 1]; g.b_batch = L[l].rows * L[l].Cout; g.ldb = L[l].Cout;
+      g.C = grad + sp.w_off[l]; g.c_batch = P; g.ldc = L[l].Cout;
+      g.M = (int)L[l].K; g.N = L[l].Cout; g.K = (int)L[l].rows;
+      g.aux = theta + sp.w_off[l]; g.aux_batch = P; g.ldaux = L[l].Cout;
+      g.coef = coef; g.p0 = sp.w_off[l]; g.prior_lo = prior_lo; g.prior_hi = prior_hi;
+      if (launch_bgemm<true, false, kEpiPrior>(s, g, C, "k_bgemm<dW conv>")) return 1;
+    }
+    if (l > 0) {   // dPatches [rows, 9 Cin] = dZ [rows, Cout] . W^T, then col2im and tanh'
+      BgemmArgs g{};
+      g.A = w.dZ[l + 1]; g.a_batch = L[l].rows * L[l].Cout; g.lda = L[l].Cout;
+      g.B = theta + sp.w_off[l]; g.b_batch = P; g.ldb = L[l].Cout;     // stored [9 Cin][Cout] = N x K
+      g.C = w.dP; g.c_batch = per; g.ldc = L[l].K;
+      g.M = (int)L[l].rows; g.N = (int)L[l].K; g.K = L[l].Cout;
+      if (launch_bgemm<false, true, kEpiStore>(s, g, C, "k_bgemm<dPatches>")) return 1;
+      const int64_t in_per = (int64_t)n * L[l].g.Hi * L[l].g.Wi * L[l].g.Cin;
+      launch_pdl(k_col2im_dtanh, dim3(blocks(in_per), (unsigned)C), dim3(256), 0, s,
+                 (const float*)w.dP, (const float*)w.H[l], w.dZ[l], L[l].g, in_per);
+      if (post_launch("k_col2im_dtanh")) return 1;
+    }
+  }
+  return 0;
+}
 
 size_t sgmc_mlp_workspace_bytes(const sgmc_mlp_spec* spec, int64_t n_chains, int64_t batch_size) {
   if (!spec || spec->n_layers < 1 || spec->n_layers > SGMC_MLP_MAX_LAYERS) return 0;

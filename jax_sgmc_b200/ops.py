@@ -351,6 +351,47 @@ def mlp_potential_grad(spec, theta, X, y, idx, observation_count, potential, var
   return workspace
 
 
+def cnn_spec(height, width, channels, strides, n_classes, w_off, b_off, prior="flat",
+             prior_off=0, prior_size=0, prior_scale=1.0, temperature=1.0):
+  """``sgmc_cnn_spec``: ``channels`` = [input, conv_0 out, ...], one stride per conv layer,
+  ``w_off`` / ``b_off`` = the conv layers' then the dense head's offsets in the flat sample."""
+  sp = _lib.CnnSpec()
+  n_conv = len(strides)
+  assert 1 <= n_conv <= _lib.CNN_MAX_CONV and len(channels) == n_conv + 1
+  assert len(w_off) == n_conv + 1 and len(b_off) == n_conv + 1
+  sp.n_conv, sp.height, sp.width, sp.n_classes = n_conv, int(height), int(width), int(n_classes)
+  for i, c in enumerate(channels):
+    sp.channels[i] = int(c)
+  for i, st in enumerate(strides):
+    sp.stride[i] = int(st)
+  for i in range(n_conv + 1):
+    sp.w_off[i], sp.b_off[i] = int(w_off[i]), int(b_off[i])
+  sp.prior, sp.prior_off, sp.prior_size = PRIOR[prior], int(prior_off), int(prior_size)
+  sp.prior_scale, sp.temperature = float(prior_scale), float(temperature)
+  return sp
+
+
+def cnn_workspace(spec, n_chains: int, batch_size: int) -> DeviceArray:
+  nbytes = _lib.load().sgmc_cnn_workspace_bytes(C.byref(spec), n_chains, batch_size)
+  return DeviceArray((int(nbytes),), np.uint8)
+
+
+def cnn_potential_grad(spec, theta, X, y, idx, observation_count, potential, variance=None,
+                       grad=None, ell=None, mask=None, workspace=None, batch_size=None,
+                       stream=None):
+  """U, var(ell), dU/dtheta of the CNN classifier for all chains on one shared minibatch
+  (see sgmc_cnn_potential_grad)."""
+  C_, P = theta.shape
+  n = int(batch_size if batch_size is not None
+          else (idx.size if idx is not None else X.shape[0]))
+  if workspace is None:
+    workspace = cnn_workspace(spec, C_, n)
+  _lib.call("sgmc_cnn_potential_grad", _s(stream), C.byref(spec), vp(theta), C_, P, vp(X),
+            vp(y), vp(idx), vp(mask), n, int(observation_count), vp(potential), vp(variance),
+            vp(grad), vp(ell), vp(workspace), workspace.nbytes)
+  return workspace
+
+
 def glm_sgld_scan_host(spec, theta, host_batches_ptr, host_batch_count, n_steps, batch_size,
                        observation_count,
                        device_slots, n_slots, potential_variance, host_results_ptr, grad,

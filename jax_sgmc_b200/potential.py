@@ -371,17 +371,22 @@ class _MlpPotentialFn:
       raise NotImplementedError(
           "the MLP potential evaluates one minibatch shared by all chains (device loader, "
           "or a host loader with shared streams)")
-    spec = nn.resolve(self.likelihood, self.prior, sample, self.temperature)
+    cnn = isinstance(self.likelihood, nn.CNNClassifier)
+    X, y = batch.leaf(self.likelihood.x), batch.leaf(self.likelihood.y)
+    if cnn:
+      spec = nn.resolve_cnn(self.likelihood, self.prior, sample, self.temperature, X.shape[1:])
+    else:
+      spec = nn.resolve(self.likelihood, self.prior, sample, self.temperature)
     C, P, n = sample.n_chains, sample.n_params, batch.n
     N = int(info.observation_count)
-    X, y = batch.leaf(self.likelihood.x), batch.leaf(self.likelihood.y)
     if mask is None:
       mask = batch.mask
     key = (C, P, n)
     buf = self._buffers.get(key)
     if buf is None:
       buf = {"U": DeviceArray((C,), np.float32), "var": DeviceArray((C,), np.float32),
-             "ws": ops.mlp_workspace(spec, C, n), "ell": None}
+             "ws": ops.cnn_workspace(spec, C, n) if cnn else ops.mlp_workspace(spec, C, n),
+             "ell": None}
       self._buffers[key] = buf
     grad = None
     if want_grad:
@@ -393,8 +398,9 @@ class _MlpPotentialFn:
       ell = buf["ell"]
     U_buf = U_out if U_out is not None else buf["U"]
     var_buf = var_out if var_out is not None else buf["var"]
-    ops.mlp_potential_grad(spec, sample.flat, X, y, batch.idx, N, U_buf, var_buf, grad, ell,
-                           mask=mask, workspace=buf["ws"], batch_size=n)
+    evaluate = ops.cnn_potential_grad if cnn else ops.mlp_potential_grad
+    evaluate(spec, sample.flat, X, y, batch.idx, N, U_buf, var_buf, grad, ell,
+             mask=mask, workspace=buf["ws"], batch_size=n)
     return U_buf, var_buf, grad, ell
 
   def __call__(self, sample: ChainTree, reference_data, state: Any = None, mask=None,
@@ -485,9 +491,9 @@ def minibatch_potential(prior, likelihood, strategy: str = "map",
   # they never change a state -- so the state handed in is the state handed back, which
   # is what the reference computes for a likelihood that returns its state unchanged.
   del has_state
-  if isinstance(likelihood, nn.MLPClassifier):
+  if isinstance(likelihood, (nn.MLPClassifier, nn.CNNClassifier)):
     if not isinstance(prior, (glm.FlatPrior, glm.GaussianPrior)):
-      raise TypeError("the MLP potential takes a FlatPrior or a GaussianPrior")
+      raise TypeError("the network potentials take a FlatPrior or a GaussianPrior")
     return _MlpPotentialFn(prior, likelihood, temperature)
   lik_is_spec = isinstance(likelihood, (glm.GaussianRegression, glm.LogisticRegression))
   prior_is_spec = isinstance(prior, (glm.FlatPrior, glm.GaussianPrior, glm.InvSigmaPrior))
@@ -542,7 +548,7 @@ def full_potential(prior, likelihood, strategy: str = "map", has_state: bool = F
     enqueued, nothing synchronises (the MH solvers consume U on the device)."""
     loader = getattr(full_data_map_fn, "loader", None)
     if loader is not None and state is None and not has_state and \
-        not isinstance(likelihood, nn.MLPClassifier):
+        not isinstance(likelihood, (nn.MLPClassifier, nn.CNNClassifier)):
       # the standard full_reference_data pass over an HBM-resident data set: all
       # batches inside one C call (same arithmetic as the loop below)
       return _full_in_one_call(sample, loader, full_data_map_fn.mb_size), (data_state, state)

@@ -201,6 +201,140 @@ def mlp_layout(sizes, order="haiku"):
   return w_off, b_off, off
 
 
+def _im2col(h, stride):
+  """[..., n, H, W, C] -> patches [..., n, Ho, Wo, 9 C] of the 3x3 / zero-padding-1
+  convolution, patch index (kh*3 + kw)*C + c (the row-major order of an HWIO filter)."""
+  H, W = h.shape[-3], h.shape[-2]
+  Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
+  pad = [(0, 0)] * (h.ndim - 3) + [(1, 1), (1, 1), (0, 0)]
+  hp = np.pad(h, pad)
+  cols = []
+  for kh in range(3):
+    for kw in range(3):
+      cols.append(hp[..., kh:kh + (Ho - 1) * stride + 1:stride,
+                     kw:kw + (Wo - 1) * stride + 1:stride, :])
+  return np.concatenate(cols, axis=-1)
+
+
+def _col2im(dP, H, W, C, stride):
+  """Adjoint of :func:`_im2col`: patch gradients [..., n, Ho, Wo, 9 C] -> [..., n, H, W, C]."""
+  Ho, Wo = dP.shape[-3], dP.shape[-2]
+  out = np.zeros(dP.shape[:-3] + (H + 2, W + 2, C), F32)
+  for kh in range(3):
+    for kw in range(3):
+      k = (kh * 3 + kw) * C
+      out[..., kh:kh + (Ho - 1) * stride + 1:stride,
+          kw:kw + (Wo - 1) * stride + 1:stride, :] += dP[..., k:k + C]
+  return out[..., 1:H + 1, 1:W + 1, :].astype(F32)
+
+
+@dataclass
+class CNNClassifier:
+  """Bayesian CNN classifier (BASELINE.json configs[4]: SGGMC / AMAGOLD on CIFAR-10-shape
+  data): the likelihood of examples/cifar.md:196-204 with a small convolutional network,
+  ``ell = -softmax_cross_entropy_with_integer_labels(apply(sample, x), label)``, evaluated
+  per observation under vmap (potential.py:141-156) and differentiated with
+  ``jax.value_and_grad``.  Restated: 3x3 convolutions (zero padding 1, ``strides[l]``,
+  filters HWIO ``[3, 3, cin, cout]``) as im2col + matmul, tanh, a dense head on the
+  flattened NHWC feature map; the gradient is the hand-derived reverse pass
+  (``dW = patches^T dZ``, ``dPatches = dZ W^T``, col2im, ``* (1 - h^2)``).
+
+  ``image``: (H, W, Cin); ``channels``: conv output channels; ``w_off`` / ``b_off``: offsets
+  of the conv layers' then the head's weights / biases in the raveled sample.  ``X`` rows
+  are flattened NHWC images."""
+  image: Sequence[int]
+  channels: Sequence[int]
+  strides: Sequence[int]
+  n_classes: int
+  w_off: Sequence[int]
+  b_off: Sequence[int]
+
+  def geometry(self):
+    H, W, c = self.image
+    out = []
+    for co, st in zip(self.channels, self.strides):
+      Ho, Wo = (H - 1) // st + 1, (W - 1) // st + 1
+      out.append((H, W, c, Ho, Wo, co, st))
+      H, W, c = Ho, Wo, co
+    return out, H * W * c
+
+  def loglik(self, theta, X, y):
+    C, n = theta.shape[0], X.shape[0]
+    geo, Fdim = self.geometry()
+    h = np.broadcast_to(np.asarray(X, F32).reshape((1, n) + tuple(self.image)),
+                        (C, n) + tuple(self.image))
+    hs, Ps = [h], []
+    for l, (H, W, ci, Ho, Wo, co, st) in enumerate(geo):
+      Wl = theta[:, self.w_off[l]:self.w_off[l] + 9 * ci * co].reshape(C, 9 * ci, co)
+      bl = theta[:, self.b_off[l]:self.b_off[l] + co]
+      P = _im2col(h, st).reshape(C, n * Ho * Wo, 9 * ci)
+      a = (np.matmul(P, Wl).astype(F32) + bl[:, None, :]).astype(F32)
+      h = np.tanh(a).astype(F32).reshape(C, n, Ho, Wo, co)
+      Ps.append(P)
+      hs.append(h)
+    L = len(geo)
+    Wh = theta[:, self.w_off[L]:self.w_off[L] + Fdim * self.n_classes].reshape(C, Fdim, -1)
+    bh = theta[:, self.b_off[L]:self.b_off[L] + self.n_classes]
+    flat = h.reshape(C, n, Fdim)
+    logits = (np.matmul(flat, Wh).astype(F32) + bh[:, None, :]).astype(F32)
+    m = logits.max(axis=2, keepdims=True)
+    sh = (logits - m).astype(F32)
+    ex = np.exp(sh).astype(F32)
+    se = np.sum(ex, axis=2, keepdims=True, dtype=F32)
+    lsm = (sh - np.log(se).astype(F32)).astype(F32)
+    lab = np.asarray(y).astype(np.int64)
+    ell = np.take_along_axis(lsm, np.broadcast_to(lab[None, :, None], (C, n, 1)),
+                             axis=2)[..., 0].astype(F32)
+    return ell, (hs, Ps, (ex / se).astype(F32), lab)
+
+  def vjp(self, theta, X, y, aux, cot):
+    hs, Ps, soft, lab = aux
+    C, n = theta.shape[0], len(lab)
+    geo, Fdim = self.geometry()
+    L = len(geo)
+    g = np.zeros_like(theta)
+    onehot = np.zeros(soft.shape[1:], F32)
+    onehot[np.arange(n), lab] = 1
+    dlog = ((onehot[None] - soft).astype(F32) * cot[..., None]).astype(F32)
+    Wh = theta[:, self.w_off[L]:self.w_off[L] + Fdim * self.n_classes].reshape(C, Fdim, -1)
+    flat = hs[L].reshape(C, n, Fdim)
+    g[:, self.w_off[L]:self.w_off[L] + Fdim * self.n_classes] = \
+        np.matmul(np.swapaxes(flat, 1, 2), dlog).astype(F32).reshape(C, -1)
+    g[:, self.b_off[L]:self.b_off[L] + self.n_classes] = np.sum(dlog, axis=1, dtype=F32)
+    dH = np.matmul(dlog, np.swapaxes(Wh, 1, 2)).astype(F32)
+    dZ = (dH * (F32(1.0) - (flat * flat).astype(F32)).astype(F32)).astype(F32)
+    for l in range(L - 1, -1, -1):
+      H, W, ci, Ho, Wo, co, st = geo[l]
+      dZm = dZ.reshape(C, n * Ho * Wo, co)
+      Wl = theta[:, self.w_off[l]:self.w_off[l] + 9 * ci * co].reshape(C, 9 * ci, co)
+      g[:, self.w_off[l]:self.w_off[l] + 9 * ci * co] = \
+          np.matmul(np.swapaxes(Ps[l], 1, 2), dZm).astype(F32).reshape(C, -1)
+      g[:, self.b_off[l]:self.b_off[l] + co] = np.sum(dZm, axis=1, dtype=F32)
+      if l > 0:
+        dP = np.matmul(dZm, np.swapaxes(Wl, 1, 2)).astype(F32).reshape(C, n, Ho, Wo, 9 * ci)
+        dHl = _col2im(dP, H, W, ci, st)
+        dZ = (dHl * (F32(1.0) - (hs[l] * hs[l]).astype(F32)).astype(F32)).astype(F32)
+    return g
+
+
+def cnn_layout(image, channels, strides, n_classes):
+  """Offsets in the raveled sample of the pytree ``{"conv_0": {"b", "w"}, ..., "head":
+  {"b", "w"}}`` (tree_flatten: keys sorted -- conv_* before head, b before w)."""
+  H, W, c = image
+  w_off, b_off, off = [], [], 0
+  for co, st in zip(channels, strides):
+    b_off.append(off)
+    off += co
+    w_off.append(off)
+    off += 9 * c * co
+    H, W, c = (H - 1) // st + 1, (W - 1) // st + 1, co
+  b_off.append(off)
+  off += n_classes
+  w_off.append(off)
+  off += H * W * c * n_classes
+  return w_off, b_off, off
+
+
 @dataclass
 class Prior:
   """Log-priors used by the reference examples.

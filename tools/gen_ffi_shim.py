@@ -25,6 +25,7 @@ Parameter kinds (launcher argument order):
   x:expr            an expression over the buffers (dimensions)
   glm               the sgmc_glm_spec, rebuilt from scalar attributes -> &spec
   mlp               the sgmc_mlp_spec, rebuilt from attributes        -> &spec
+  cnn               the sgmc_cnn_spec, rebuilt from attributes        -> &spec
   null              a NULL pointer argument (a feature the FFI route does not expose)
 """
 import os
@@ -125,6 +126,11 @@ HANDLERS = [
                                       "a:int64:observation_count", "out:F32:potential",
                                       "out:F32:variance", "out:F32:grad", "null", "ws:workspace"]),
     ("mlp_potential_grad", ["S", "mlp", "in:F32:theta", "x:theta.dimensions()[0]",
+                            "x:theta.dimensions()[1]", "in:F32:X", "in:F32:y", "opt:S32:idx",
+                            "opt:F32:mask", "a:int64:batch_size", "a:int64:observation_count",
+                            "out:F32:potential", "out:F32:variance", "out:F32:grad", "null",
+                            "ws:workspace"]),
+    ("cnn_potential_grad", ["S", "cnn", "in:F32:theta", "x:theta.dimensions()[0]",
                             "x:theta.dimensions()[1]", "in:F32:X", "in:F32:y", "opt:S32:idx",
                             "opt:F32:mask", "a:int64:batch_size", "a:int64:observation_count",
                             "out:F32:potential", "out:F32:variance", "out:F32:grad", "null",
@@ -284,6 +290,28 @@ def emit(name, params):
           "  spec.activation = activation; spec.prior = prior; spec.prior_off = prior_off;\n"
           "  spec.prior_size = prior_size; spec.prior_scale = prior_scale;\n"
           "  spec.temperature = potential_temperature;")
+      call.append("&spec")
+    elif k == "cnn":
+      attrs += [("int32_t", "height"), ("int32_t", "width"), ("int32_t", "n_classes"),
+                ("ffi::Span<const int64_t>", "channels"), ("ffi::Span<const int64_t>", "strides"),
+                ("ffi::Span<const int64_t>", "w_off"), ("ffi::Span<const int64_t>", "b_off")]
+      attrs += [(CT[t], n) for t, n in MLP_ATTRS if n != "activation"]
+      pre.append(
+          "  sgmc_cnn_spec spec{};\n"
+          "  spec.n_conv = (int32_t)strides.size();\n"
+          "  if (spec.n_conv < 1 || spec.n_conv > SGMC_CNN_MAX_CONV ||\n"
+          "      channels.size() != strides.size() + 1 || w_off.size() != strides.size() + 1 ||\n"
+          "      b_off.size() != w_off.size())\n"
+          "    return ffi::Error(ffi::ErrorCode::kInvalidArgument, \"bad CNN layout\");\n"
+          "  spec.height = height; spec.width = width; spec.n_classes = n_classes;\n"
+          "  for (int l = 0; l <= spec.n_conv; ++l) {\n"
+          "    spec.channels[l] = (int32_t)channels.begin()[l];\n"
+          "    spec.w_off[l] = w_off.begin()[l];\n"
+          "    spec.b_off[l] = b_off.begin()[l];\n"
+          "  }\n"
+          "  for (int l = 0; l < spec.n_conv; ++l) spec.stride[l] = (int32_t)strides.begin()[l];\n"
+          "  spec.prior = prior; spec.prior_off = prior_off; spec.prior_size = prior_size;\n"
+          "  spec.prior_scale = prior_scale; spec.temperature = potential_temperature;")
       call.append("&spec")
     else:
       raise ValueError(p)
