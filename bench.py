@@ -349,6 +349,54 @@ def bench_row_sharded(args, ctl, nccl, stream, path):
           "potential_path": path}
 
 
+def bench_cnn(args, ctl, nccl, stream):
+  """C5 (configs[4]): the CIFAR-10-shape CNN potential + gradient (conv3x3-32 / 2, conv3x3-64
+  / 2, dense-10; 60 362 parameters per chain) for 8 chains on a minibatch of 1024 images whose
+  rows are sharded over the ranks, gradient and potential all-reduced (the evaluation
+  alias.sggmc / alias.amagold make per leapfrog step).  Strong scaling: the minibatch is
+  the same at every N."""
+  from jax_sgmc_b200 import data, glm, nn, ops, potential
+  from jax_sgmc_b200.device import Event
+  from jax_sgmc_b200.tree_util import ChainTree
+  world = ctl.world
+  C, n, N = 8, 1024, 8192
+  if n % world:
+    return None
+  rng = np.random.default_rng(0)
+  loader = data.DeviceNumpyDataLoader(x=rng.random((N, 32, 32, 3), dtype=np.float32),
+                                      y=rng.integers(0, 10, N).astype(np.float32))
+  sample = ChainTree.from_trees(
+      [nn.init_cnn_params(ops.prng_key(c), (32, 32, 3), (32, 64), (2, 2), 10) for c in range(C)])
+  pot = potential.minibatch_potential(glm.GaussianPrior(10.0), nn.CNNClassifier(strides=(2, 2)))
+  if nccl is not None:
+    pot.shard_rows(nccl)
+  init_fn, get_fn, _ = data.random_reference_data(loader, 1, n)
+  state = init_fn()
+  state, ref = get_fn(state, information=True)
+  for _ in range(2):
+    pot.value_and_grad(sample, ref)
+  stream.sync()
+  ctl.barrier()
+  K = 10
+  e0, e1 = Event(), Event()
+  e0.record(stream)
+  for _ in range(K):
+    state, ref = get_fn(state, information=True)
+    pot.value_and_grad(sample, ref)
+  e1.record(stream)
+  e1.sync()
+  ms = ctl.max(e0.elapsed_ms(e1)) / K
+  # forward + reverse pass: 3 x the forward FLOPs minus the first layer's input gradient
+  f1, f2, f3 = 2.0 * 256 * 27 * 32, 2.0 * 64 * 288 * 64, 2.0 * 4096 * 10
+  flops = C * n * (3 * (f1 + f2 + f3) - f1)
+  return {"workload": "C5: CNN potential + gradient (conv3x3-32/2, conv3x3-64/2, dense-10 on "
+                      "32x32x3), minibatch rows sharded over the ranks, gradient all-reduce",
+          "chains": C, "batch": n, "rows_per_rank": n // world, "n_gpus": world,
+          "parameters_per_chain": int(sample.n_params), "us_per_evaluation": ms * 1e3,
+          "chain_evaluations_per_s": C / (ms * 1e-3), "tflops_fp32": flops / (ms * 1e-3) / 1e12,
+          "scaling": "strong"}
+
+
 def run_b200(args):
   from jax_sgmc_b200 import _lib, alias, data, device, dist, glm, ops, potential
   from jax_sgmc_b200.device import DeviceArray as DA, Event, Stream
@@ -574,6 +622,7 @@ def run_b200(args):
   if not args.no_resgld:
     resgld = bench_resgld(args, ctl, nccl, stream, path)
   row_sharded = bench_row_sharded(args, ctl, nccl, stream, path)
+  cnn = None if args.no_resgld else bench_cnn(args, ctl, nccl, stream)
 
   cpu_base = None
   if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -599,6 +648,7 @@ def run_b200(args):
         "roofline": roofline, "roofline_tensor": roofline_tensor,
         "step_profile": step_profile, "e2e": e2e,
         "cpu_baseline": cpu_base, "resgld": resgld, "row_sharded_gradient": row_sharded,
+        "cnn_sharded_gradient": cnn,
     }
     print(json.dumps(line), flush=True)
   ctl.close()

@@ -37,6 +37,11 @@ struct BgemmArgs {
   const float* aux; int64_t aux_batch, ldaux;                   // kEpiDtanh: * (1 - aux^2); kEpiPrior: + coef * aux
   float coef;
   int64_t p0, prior_lo, prior_hi;                               // kEpiPrior: flat index of C(0,0), prior range
+  // split-K (reductions over hundreds of thousands of rows with a tiny output: the conv
+  // weight gradients): blockIdx.z = batch * n_split + split, a split covers k_chunk of K and
+  // writes its raw accumulators to C + batch * c_batch + split * c_split (k_splitk_reduce adds
+  // them in fixed order).  n_split <= 1: plain GEMM.
+  int n_split, k_chunk; int64_t c_split;
 };
 
 // One operand tile -> registers.  MN_CONTIG: element (k, mn) at base + row(k) * ld + mn
@@ -86,9 +91,15 @@ __global__ void __launch_bounds__(kBThreads, 2) k_bgemm(const BgemmArgs a) {
   __shared__ __align__(16) float Bs[2][kBK][kBN + kBPad];
   const int t = threadIdx.x, tx = t & 15, ty = t >> 4;
   const int m0 = blockIdx.y * kBM, n0 = blockIdx.x * kBN;
-  const int64_t b = blockIdx.z;
-  const float* A = a.A + b * a.a_batch;
-  const float* B = a.B + b * a.b_batch;
+  const int ns = a.n_split > 1 ? a.n_split : 1;
+  const int64_t b = blockIdx.z / ns;
+  const int sp = (int)(blockIdx.z - b * ns);
+  const int k_begin = ns > 1 ? sp * a.k_chunk : 0;
+  const int K = ns > 1 ? min(a.k_chunk, a.K - k_begin) : a.K;
+  // advance both operands along K to the split's range
+  const float* A = a.A + b * a.a_batch + (a.a_idx ? 0 : (A_T ? (int64_t)k_begin * a.lda : k_begin));
+  const float* B = a.B + b * a.b_batch + (B_T ? k_begin : (int64_t)k_begin * a.ldb);
+  const int32_t* a_idx = a.a_idx ? a.a_idx + (A_T ? k_begin : 0) : nullptr;
   pdl_launch_dependents();
   pdl_wait();
 
@@ -99,17 +110,17 @@ __global__ void __launch_bounds__(kBThreads, 2) k_bgemm(const BgemmArgs a) {
     for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
 
   float ra[8], rb[8];
-  const int kt = (a.K + kBK - 1) / kBK;
-  load_tile<A_T>(ra, A, a.lda, a.a_idx, m0, 0, a.M, a.K, t);
-  load_tile<!B_T>(rb, B, a.ldb, nullptr, n0, 0, a.N, a.K, t);
+  const int kt = (K + kBK - 1) / kBK;
+  load_tile<A_T>(ra, A, a.lda, a_idx, m0, 0, a.M, K, t);
+  load_tile<!B_T>(rb, B, a.ldb, nullptr, n0, 0, a.N, K, t);
   store_tile<A_T>(As[0], ra, t);
   store_tile<!B_T>(Bs[0], rb, t);
   __syncthreads();
   for (int it = 0; it < kt; ++it) {
     const int cur = it & 1;
     if (it + 1 < kt) {
-      load_tile<A_T>(ra, A, a.lda, a.a_idx, m0, (it + 1) * kBK, a.M, a.K, t);
-      load_tile<!B_T>(rb, B, a.ldb, nullptr, n0, (it + 1) * kBK, a.N, a.K, t);
+      load_tile<A_T>(ra, A, a.lda, a_idx, m0, (it + 1) * kBK, a.M, K, t);
+      load_tile<!B_T>(rb, B, a.ldb, nullptr, n0, (it + 1) * kBK, a.N, K, t);
     }
 #pragma unroll
     for (int kk = 0; kk < kBK; ++kk) {
@@ -131,7 +142,7 @@ __global__ void __launch_bounds__(kBThreads, 2) k_bgemm(const BgemmArgs a) {
     __syncthreads();
   }
 
-  float* Cb = a.C + b * a.c_batch;
+  float* Cb = a.C + b * a.c_batch + (ns > 1 ? sp * a.c_split : 0);
   const float* bias = (EPI == kEpiBiasTanh || EPI == kEpiBias) ? a.bias + b * a.bias_batch : nullptr;
   const float* aux = (EPI == kEpiDtanh || EPI == kEpiPrior) ? a.aux + b * a.aux_batch : nullptr;
 #pragma unroll
@@ -162,7 +173,9 @@ __global__ void __launch_bounds__(kBThreads, 2) k_bgemm(const BgemmArgs a) {
 template <bool A_T, bool B_T, int EPI>
 static int launch_bgemm(cudaStream_t s, const BgemmArgs& a, int64_t batch, const char* name) {
   SGMC_REQUIRE(batch <= 65535, "%s: more than 65535 chains per call", name);
-  dim3 grid((unsigned)((a.N + kBN - 1) / kBN), (unsigned)((a.M + kBM - 1) / kBM), (unsigned)batch);
+  const int64_t z = batch * (a.n_split > 1 ? a.n_split : 1);
+  SGMC_REQUIRE(z <= 65535, "%s: too many chains x K splits", name);
+  dim3 grid((unsigned)((a.N + kBN - 1) / kBN), (unsigned)((a.M + kBM - 1) / kBM), (unsigned)z);
   launch_pdl(k_bgemm<A_T, B_T, EPI>, grid, dim3(kBThreads), 0, s, a);
   return post_launch(name);
 }
@@ -410,6 +423,55 @@ __global__ void __launch_bounds__(256) k_col2im_dtanh(const float* __restrict__ 
   }
 }
 
+// out[b][m][n] = sum_s part[b][s][m][n] in split order (+ coef * aux on the prior range):
+// the second stage of the split-K GEMMs and of the split column sums
+__global__ void __launch_bounds__(256) k_splitk_reduce(const float* __restrict__ part, int n_split,
+                                                       int64_t MN, int N, float* __restrict__ out,
+                                                       int64_t out_batch, int64_t ldc,
+                                                       const float* __restrict__ aux,
+                                                       int64_t aux_batch, float coef, int64_t p0,
+                                                       int64_t prior_lo, int64_t prior_hi) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int64_t b = blockIdx.y;
+  for (int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x; e < MN; e += (int64_t)gridDim.x * 256) {
+    const float* src = part + b * n_split * MN + e;
+    float s = 0.f;
+    for (int q = 0; q < n_split; ++q) s += src[(int64_t)q * MN];
+    const int64_t m = e / N, n = e - m * N;
+    const int64_t o = m * ldc + n;
+    const int64_t p = p0 + o;
+    if (aux != nullptr && p >= prior_lo && p < prior_hi) s = fmaf(coef, aux[b * aux_batch + o], s);
+    out[b * out_batch + o] = s;
+  }
+}
+
+// part[c][s][o] = sum over the split's rows of dZ[c][row][o]: 32 columns x 8 row lanes
+__global__ void __launch_bounds__(256) k_colsum_part(const float* __restrict__ dZ, int64_t rows,
+                                                     int out, int64_t row_chunk,
+                                                     float* __restrict__ part) {
+  pdl_launch_dependents();
+  pdl_wait();
+  __shared__ float red[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int o = blockIdx.x * 32 + tx;
+  const int64_t c = blockIdx.y, sp = blockIdx.z;
+  const int64_t r0 = sp * row_chunk, r1 = min(rows, r0 + row_chunk);
+  float s = 0.f;
+  if (o < out) {
+    const float* src = dZ + c * rows * out + o;
+    for (int64_t r = r0 + ty; r < r1; r += 8) s += src[r * out];
+  }
+  red[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0 && o < out) {
+    float t = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) t += red[q][tx];
+    part[(c * gridDim.z + sp) * out + o] = t;
+  }
+}
+
 // db[c][o] = sum over `rows` rows of dZ[c][row][o] (+ prior term): 32 columns x 8 row lanes
 __global__ void __launch_bounds__(256) k_colsum_grad(const float* __restrict__ dZ, int64_t rows,
                                                      int out, const float* __restrict__ theta,
@@ -450,8 +512,12 @@ struct CnnWs {
   float* H[SGMC_CNN_MAX_CONV + 1];   // H[l + 1] = tanh output of conv layer l
   float* dZ[SGMC_CNN_MAX_CONV + 1];  // dZ[l + 1] = gradient w.r.t. the pre-activation of layer l
   float* dP;                         // largest patch-gradient buffer (layers >= 1)
+  float* part;                       // split-K partials of the conv weight / bias gradients
   float* logits; float* dlogits; float* ell; float* sumsq;
 };
+
+constexpr int kSplitChunk = 2048;    // rows of K per split of a conv weight gradient
+static int cnn_splits(int64_t rows) { return (int)std::min<int64_t>((rows + kSplitChunk - 1) / kSplitChunk, 512); }
 
 static int cnn_layers(const sgmc_cnn_spec& s, int64_t n, CnnLayer* L) {
   int Hi = s.height, Wi = s.width;
@@ -476,15 +542,18 @@ static size_t cnn_carve(CnnWs* w, uint8_t* base, const sgmc_cnn_spec& s, int64_t
     off += (floats * 4 + 255) & ~(size_t)255;
     return p;
   };
-  size_t dp_max = 0;
+  size_t dp_max = 0, part_max = 1;
   for (int l = 0; l < s.n_conv; ++l) {
     float* p = take((size_t)(l == 0 ? 1 : C) * L[l].rows * L[l].K);
     float* h = take((size_t)C * L[l].rows * L[l].Cout);
     float* d = take((size_t)C * L[l].rows * L[l].Cout);
     if (l > 0) dp_max = std::max(dp_max, (size_t)C * L[l].rows * L[l].K);
+    part_max = std::max(part_max, (size_t)C * std::max(cnn_splits(L[l].rows), 2) * L[l].K * L[l].Cout);
     if (w) { w->P[l] = p; w->H[l + 1] = h; w->dZ[l + 1] = d; }
   }
   float* dp = take(dp_max ? dp_max : 1);
+  float* part = take(part_max);
+  if (w) w->part = part;
   float* lg = take((size_t)C * n * s.n_classes);
   float* dl = take((size_t)C * n * s.n_classes);
   float* ell = take((size_t)C * n);
@@ -622,19 +691,35 @@ int sgmc_cnn_potential_grad(void* stream, const sgmc_cnn_spec* spec, const float
   // ---- reverse pass: convolutions ------------------------------------------------------------
   for (int l = NL - 1; l >= 0; --l) {
     const int64_t per = L[l].rows * L[l].K;
-    launch_pdl(k_colsum_grad, dim3((unsigned)((L[l].Cout + 31) / 32), (unsigned)C), dim3(256), 0, s,
-               (const float*)w.dZ[l + 1], L[l].rows, L[l].Cout, theta, grad, P,
-               (int64_t)sp.b_off[l], coef, prior_lo, prior_hi);
-    if (post_launch("k_colsum_grad")) return 1;
-    {   // dW_l [9 Cin, Cout] = patches^T [9 Cin, rows] . dZ [rows, Cout]
+    const int S = cnn_splits(L[l].rows);
+    const int64_t chunk = (L[l].rows + S - 1) / S;
+    SGMC_REQUIRE(C * (int64_t)S <= 65535, "too many chains x K splits");
+    {   // db_l [Cout] = column sums of dZ over all rows, in S row chunks then in order
+      launch_pdl(k_colsum_part, dim3((unsigned)((L[l].Cout + 31) / 32), (unsigned)C, (unsigned)S),
+                 dim3(256), 0, s, (const float*)w.dZ[l + 1], L[l].rows, L[l].Cout, chunk, w.part);
+      if (post_launch("k_colsum_part")) return 1;
+      launch_pdl(k_splitk_reduce, dim3(1, (unsigned)C), dim3(256), 0, s, (const float*)w.part, S,
+                 (int64_t)L[l].Cout, L[l].Cout, grad + sp.b_off[l], P, (int64_t)L[l].Cout,
+                 theta + sp.b_off[l], P, coef, (int64_t)sp.b_off[l], prior_lo, prior_hi);
+      if (post_launch("k_splitk_reduce")) return 1;
+    }
+    {   // dW_l [9 Cin, Cout] = patches^T [9 Cin, rows] . dZ [rows, Cout]: split over the rows
       BgemmArgs g{};
+      const int64_t MN = L[l].K * L[l].Cout;
       g.A = w.P[l]; g.a_batch = l == 0 ? 0 : per; g.lda = L[l].K;
       g.B = w.dZ[l + 1]; g.b_batch = L[l].rows * L[l].Cout; g.ldb = L[l].Cout;
-      g.C = grad + sp.w_off[l]; g.c_batch = P; g.ldc = L[l].Cout;
+      g.C = w.part; g.c_batch = (int64_t)S * MN; g.ldc = L[l].Cout;
       g.M = (int)L[l].K; g.N = L[l].Cout; g.K = (int)L[l].rows;
-      g.aux = theta + sp.w_off[l]; g.aux_batch = P; g.ldaux = L[l].Cout;
-      g.coef = coef; g.p0 = sp.w_off[l]; g.prior_lo = prior_lo; g.prior_hi = prior_hi;
-      if (launch_bgemm<true, false, kEpiPrior>(s, g, C, "k_bgemm<dW conv>")) return 1;
+      g.n_split = S; g.k_chunk = (int)chunk; g.c_split = MN;
+      if (S == 1) { g.n_split = 2; g.k_chunk = (int)L[l].rows; }      // (one split: same code path)
+      const int S_eff = S == 1 ? 2 : S;
+      g.c_batch = (int64_t)S_eff * MN;
+      if (launch_bgemm<true, false, kEpiStore>(s, g, C, "k_bgemm<dW conv, split-K>")) return 1;
+      launch_pdl(k_splitk_reduce, dim3((unsigned)std::min<int64_t>((MN + 255) / 256, 1024), (unsigned)C),
+                 dim3(256), 0, s, (const float*)w.part, S_eff, MN, L[l].Cout, grad + sp.w_off[l], P,
+                 (int64_t)L[l].Cout, theta + sp.w_off[l], P, coef, (int64_t)sp.w_off[l], prior_lo,
+                 prior_hi);
+      if (post_launch("k_splitk_reduce")) return 1;
     }
     if (l > 0) {   // dPatches [rows, 9 Cin] = dZ [rows, Cout] . W^T, then col2im and tanh'
       BgemmArgs g{};

@@ -359,6 +359,19 @@ class _MlpPotentialFn:
   def __init__(self, prior, likelihood, temperature):
     self.prior, self.likelihood, self.temperature = prior, likelihood, float(temperature)
     self._buffers = {}
+    self.shard_comm = None
+
+  def shard_rows(self, comm):
+    """Minibatch-gradient sharding (BASELINE.json configs[4]; the reference's ``pmap`` batch
+    strategy, potential.py:150): every rank evaluates rows ``[rank n / R, (rank + 1) n / R)``
+    of the shared minibatch for all chains, then the gradient and the potential are
+    all-reduced over ``comm`` (a ``dist.NcclCommunicator``).  With equal slices the mean over
+    the ranks of ``(-N mean_r(ell) - prior) / T`` and of its gradient IS the unsharded value,
+    so one ``ncclAllReduce(sum)`` of ``f32[C][P]`` + ``f32[C]`` and a scale by ``1 / R`` per
+    evaluation; every rank then applies the identical update.  ``var(ell)`` (only
+    ``langevin_diffusion`` / reSGLD read it) stays the rank's own."""
+    self.shard_comm = comm
+    return self
 
   def sgld_step(self, *args, **kwargs) -> bool:
     return False          # no fused whole-step call: the integrator runs potential, then update
@@ -399,8 +412,27 @@ class _MlpPotentialFn:
     U_buf = U_out if U_out is not None else buf["U"]
     var_buf = var_out if var_out is not None else buf["var"]
     evaluate = ops.cnn_potential_grad if cnn else ops.mlp_potential_grad
-    evaluate(spec, sample.flat, X, y, batch.idx, N, U_buf, var_buf, grad, ell,
-             mask=mask, workspace=buf["ws"], batch_size=n)
+    comm = self.shard_comm
+    if comm is None or comm.world == 1:
+      evaluate(spec, sample.flat, X, y, batch.idx, N, U_buf, var_buf, grad, ell,
+               mask=mask, workspace=buf["ws"], batch_size=n)
+      return U_buf, var_buf, grad, ell
+    # ---- rows of the minibatch sharded over the ranks + all-reduce (see shard_rows) ----
+    R, r = comm.world, comm.rank
+    if n % R or batch.idx is None or want_ell:
+      raise ValueError("row sharding needs an indexed minibatch whose size is a multiple of "
+                       "the rank count (per-observation likelihoods are not gathered)")
+    n_r = n // R
+    idx_r = DeviceArray((n_r,), np.int32, ptr=batch.idx.ptr + r * n_r * 4, owner=batch.idx)
+    mask_r = None if mask is None else DeviceArray((n_r,), np.float32, ptr=mask.ptr + r * n_r * 4,
+                                                   owner=mask)
+    evaluate(spec, sample.flat, X, y, idx_r, N, U_buf, var_buf, grad, None,
+             mask=mask_r, workspace=buf["ws"], batch_size=n_r)
+    comm.allreduce_sum(U_buf, U_buf)
+    ops.tree_ewise(0, U_buf, 1.0 / R, U_buf)
+    if grad is not None:
+      comm.allreduce_sum(grad, grad)
+      ops.tree_ewise(0, grad, 1.0 / R, grad)
     return U_buf, var_buf, grad, ell
 
   def __call__(self, sample: ChainTree, reference_data, state: Any = None, mask=None,

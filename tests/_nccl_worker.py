@@ -65,5 +65,33 @@ for path, (C, d, n, N) in (("simt", (6, 24, 64, 400)), ("tc_parity", (128, 64, 2
   np.testing.assert_allclose(var.numpy(), v0.numpy(), rtol=2e-4)
   scale = np.abs(g0.numpy()).max(axis=1, keepdims=True)
   assert (np.abs(g.numpy() - g0.numpy()) / scale).max() < 1e-5, path
+# ---- CNN potential with the minibatch rows sharded over the ranks (configs[4]) -------------
+from jax_sgmc_b200 import data, glm, nn, potential  # noqa: E402
+from jax_sgmc_b200.tree_util import ChainTree  # noqa: E402
+
+rng = np.random.default_rng(11)
+N, n, C = 96, 32, 3
+X = rng.random((N, 8, 8, 3)).astype(np.float32)
+y = rng.integers(0, 5, N).astype(np.float32)
+loader = data.DeviceNumpyDataLoader(x=X, y=y)
+trees = [nn.init_cnn_params(ops.prng_key(c), (8, 8, 3), (4, 6), (2, 1), 5) for c in range(C)]
+sample = ChainTree.from_trees(trees)
+init_fn, get_fn, _ = data.random_reference_data(loader, 1, n)
+_, ref = get_fn(init_fn(), information=True)           # same key on every rank: same minibatch
+lik, prior = nn.CNNClassifier(strides=(2, 1)), glm.GaussianPrior(3.0)
+whole = potential.minibatch_potential(prior, lik)
+(U0, _), g0 = whole.value_and_grad(sample, ref)
+U0, g0 = U0.numpy(), g0.flat.numpy()
+sharded = potential.minibatch_potential(prior, lik).shard_rows(nccl)
+(U1, _), g1 = sharded.value_and_grad(sample, ref)
+device.synchronize()
+np.testing.assert_allclose(U1.numpy(), U0, rtol=1e-5)
+scale = np.abs(g0).max(axis=1, keepdims=True)
+assert (np.abs(g1.flat.numpy() - g0) / scale).max() < 1e-5
+# every rank holds the identical reduced gradient (they apply the identical update)
+both = DA.zeros((world,) + g0.shape)
+nccl.allgather(g1.flat, both)
+device.synchronize()
+assert np.array_equal(both.numpy()[0].view(np.uint32), both.numpy()[1].view(np.uint32))
 ctl.barrier()
 print(f"rank {rank} ok", flush=True)
