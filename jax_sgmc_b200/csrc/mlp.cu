@@ -446,6 +446,55 @@ __global__ void __launch_bounds__(256) k_splitk_reduce(const float* __restrict__
   }
 }
 
+// Tall-skinny weight gradient of a convolution with few channels (M N <= 1024 outputs over
+// hundreds of thousands of rows, e.g. 27 x 32 for the first layer on RGB images), where a
+// 128 x 128 GEMM tile would be 95 % padding: part[c][s][m][n] = sum over the split's rows
+// of P[row][m] dZ[c][row][n].  A CTA stages 64 rows of both operands in shared memory; a
+// thread owns up to four outputs.
+__global__ void __launch_bounds__(256) k_dw_tallskinny(const float* __restrict__ Pm, int64_t p_batch,
+                                                       const float* __restrict__ dZ, int64_t rows,
+                                                       int M, int N, int64_t row_chunk,
+                                                       float* __restrict__ part) {
+  pdl_launch_dependents();
+  pdl_wait();
+  extern __shared__ float ts_smem[];
+  float* sP = ts_smem;                 // [64][M]
+  float* sZ = ts_smem + 64 * M;        // [64][N]
+  const int64_t c = blockIdx.y, sp = blockIdx.x;
+  const int64_t r0 = sp * row_chunk, r1 = min(rows, r0 + row_chunk);
+  const float* P = Pm + c * p_batch;
+  const float* Z = dZ + c * rows * N;
+  const int MN = M * N;
+  int om[4], on[4];
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int o = threadIdx.x + q * 256;
+    om[q] = o < MN ? o / N : 0;
+    on[q] = o < MN ? o - om[q] * N : 0;
+  }
+  for (int64_t r = r0; r < r1; r += 64) {
+    const int nr = (int)min((int64_t)64, r1 - r);
+    __syncthreads();
+    for (int e = threadIdx.x; e < nr * M; e += 256) sP[e] = P[r * M + e];
+    for (int e = threadIdx.x; e < nr * N; e += 256) sZ[e] = Z[r * N + e];
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (threadIdx.x + q * 256 >= MN) break;
+      float a = acc[q];
+      for (int i = 0; i < nr; ++i) a = fmaf(sP[i * M + om[q]], sZ[i * N + on[q]], a);
+      acc[q] = a;
+    }
+  }
+  float* out = part + (c * gridDim.x + sp) * MN;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int o = threadIdx.x + q * 256;
+    if (o < MN) out[o] = acc[q];
+  }
+}
+
 // part[c][s][o] = sum over the split's rows of dZ[c][row][o]: 32 columns x 8 row lanes
 __global__ void __launch_bounds__(256) k_colsum_part(const float* __restrict__ dZ, int64_t rows,
                                                      int out, int64_t row_chunk,
@@ -714,7 +763,16 @@ int sgmc_cnn_potential_grad(void* stream, const sgmc_cnn_spec* spec, const float
       if (S == 1) { g.n_split = 2; g.k_chunk = (int)L[l].rows; }      // (one split: same code path)
       const int S_eff = S == 1 ? 2 : S;
       g.c_batch = (int64_t)S_eff * MN;
-      if (launch_bgemm<true, false, kEpiStore>(s, g, C, "k_bgemm<dW conv, split-K>")) return 1;
+      if (MN <= 1024 && (64 * (L[l].K + L[l].Cout)) * 4 <= 48 * 1024) {
+        // few channels: the tall-skinny kernel instead of 128 x 128 tiles of padding
+        launch_pdl(k_dw_tallskinny, dim3((unsigned)S_eff, (unsigned)C), dim3(256),
+                   (size_t)(64 * (L[l].K + L[l].Cout)) * 4, s, (const float*)w.P[l],
+                   l == 0 ? (int64_t)0 : per, (const float*)w.dZ[l + 1], L[l].rows, (int)L[l].K,
+                   L[l].Cout, S == 1 ? L[l].rows : chunk, w.part);
+        if (post_launch("k_dw_tallskinny")) return 1;
+      } else if (launch_bgemm<true, false, kEpiStore>(s, g, C, "k_bgemm<dW conv, split-K>")) {
+        return 1;
+      }
       launch_pdl(k_splitk_reduce, dim3((unsigned)std::min<int64_t>((MN + 255) / 256, 1024), (unsigned)C),
                  dim3(256), 0, s, (const float*)w.part, S_eff, MN, L[l].Cout, grad + sp.w_off[l], P,
                  (int64_t)L[l].Cout, theta + sp.w_off[l], P, coef, (int64_t)sp.w_off[l], prior_lo,
