@@ -47,11 +47,26 @@ struct BgemmArgs {
 // One operand tile -> registers.  MN_CONTIG: element (k, mn) at base + row(k) * ld + mn
 // (the tile's M / N index is contiguous in memory); otherwise element (mn, k) at
 // base + row(mn) * ld + k (K contiguous).  `row` applies the optional gather.
+// `vec` (uniform per CTA, see operand_vec): two 16-byte loads per thread along the contiguous
+// index instead of eight 4-byte ones; the register / shared-memory mapping differs, the
+// values that land in As / Bs do not.
 template <bool MN_CONTIG>
 __device__ __forceinline__ void load_tile(float (&r)[8], const float* __restrict__ base, int64_t ld,
                                           const int32_t* __restrict__ idx, int mn0, int k0, int MN,
-                                          int K, int t) {
-  if (MN_CONTIG) {
+                                          int K, int t, bool vec) {
+  if (vec) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int mn = MN_CONTIG ? mn0 + (t & 31) * 4 : mn0 + (t >> 2) + 64 * h;
+      const int k = MN_CONTIG ? k0 + (t >> 5) + 8 * h : k0 + (t & 3) * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (mn < MN && k < K) {
+        const int64_t row = MN_CONTIG ? (idx ? idx[k] : k) : (idx ? idx[mn] : mn);
+        v = __ldg(reinterpret_cast<const float4*>(base + row * ld + (MN_CONTIG ? mn : k)));
+      }
+      r[4 * h] = v.x; r[4 * h + 1] = v.y; r[4 * h + 2] = v.z; r[4 * h + 3] = v.w;
+    }
+  } else if (MN_CONTIG) {
     const int mn = mn0 + (t & 127);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -73,14 +88,32 @@ __device__ __forceinline__ void load_tile(float (&r)[8], const float* __restrict
 }
 
 template <bool MN_CONTIG>
-__device__ __forceinline__ void store_tile(float (*s)[kBM + kBPad], const float (&r)[8], int t) {
-  if (MN_CONTIG) {
+__device__ __forceinline__ void store_tile(float (*s)[kBM + kBPad], const float (&r)[8], int t,
+                                           bool vec) {
+  if (vec && MN_CONTIG) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+      *reinterpret_cast<float4*>(&s[(t >> 5) + 8 * h][(t & 31) * 4]) =
+          make_float4(r[4 * h], r[4 * h + 1], r[4 * h + 2], r[4 * h + 3]);
+  } else if (vec) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) s[(t & 3) * 4 + j][(t >> 2) + 64 * h] = r[4 * h + j];
+  } else if (MN_CONTIG) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) s[(t >> 7) + 2 * i][t & 127] = r[i];
   } else {
 #pragma unroll
     for (int i = 0; i < 8; ++i) s[t & 15][(t >> 4) + 16 * i] = r[i];
   }
+}
+
+// 16-byte loads are legal for an operand when its (batch- and split-advanced) base and its
+// leading dimension are 16-byte multiples and the extent along the contiguous index is a
+// multiple of four (a float4 is then entirely inside or entirely outside the matrix).
+__device__ __forceinline__ bool operand_vec(const float* base, int64_t ld, int contig_extent) {
+  return ((reinterpret_cast<uintptr_t>(base) & 15) == 0) && (ld & 3) == 0 && (contig_extent & 3) == 0;
 }
 
 // A_T: A is stored K x M (M contiguous), else M x K (K contiguous).
@@ -103,24 +136,28 @@ __global__ void __launch_bounds__(kBThreads, 2) k_bgemm(const BgemmArgs a) {
   pdl_launch_dependents();
   pdl_wait();
 
-  float acc[8][8];
+  // accumulators as column pairs: one packed fma.rn.f32x2 per pair (same per-element
+  // rounding as 64 scalar FMAs, half the issue slots)
+  float2 acc[8][4];
 #pragma unroll
   for (int i = 0; i < 8; ++i)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < 4; ++j) acc[i][j] = make_float2(0.f, 0.f);
 
   float ra[8], rb[8];
   const int kt = (K + kBK - 1) / kBK;
-  load_tile<A_T>(ra, A, a.lda, a_idx, m0, 0, a.M, K, t);
-  load_tile<!B_T>(rb, B, a.ldb, nullptr, n0, 0, a.N, K, t);
-  store_tile<A_T>(As[0], ra, t);
-  store_tile<!B_T>(Bs[0], rb, t);
+  const bool va = operand_vec(A, a.lda, A_T ? a.M : K);
+  const bool vb = operand_vec(B, a.ldb, B_T ? K : a.N);
+  load_tile<A_T>(ra, A, a.lda, a_idx, m0, 0, a.M, K, t, va);
+  load_tile<!B_T>(rb, B, a.ldb, nullptr, n0, 0, a.N, K, t, vb);
+  store_tile<A_T>(As[0], ra, t, va);
+  store_tile<!B_T>(Bs[0], rb, t, vb);
   __syncthreads();
   for (int it = 0; it < kt; ++it) {
     const int cur = it & 1;
     if (it + 1 < kt) {
-      load_tile<A_T>(ra, A, a.lda, a_idx, m0, (it + 1) * kBK, a.M, K, t);
-      load_tile<!B_T>(rb, B, a.ldb, nullptr, n0, (it + 1) * kBK, a.N, K, t);
+      load_tile<A_T>(ra, A, a.lda, a_idx, m0, (it + 1) * kBK, a.M, K, t, va);
+      load_tile<!B_T>(rb, B, a.ldb, nullptr, n0, (it + 1) * kBK, a.N, K, t, vb);
     }
 #pragma unroll
     for (int kk = 0; kk < kBK; ++kk) {
@@ -129,15 +166,18 @@ __global__ void __launch_bounds__(kBThreads, 2) k_bgemm(const BgemmArgs a) {
       const float4 b0 = *reinterpret_cast<const float4*>(&Bs[cur][kk][tx * 4]);
       const float4 b1 = *reinterpret_cast<const float4*>(&Bs[cur][kk][64 + tx * 4]);
       const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-      const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+      const float2 bv[4] = {make_float2(b0.x, b0.y), make_float2(b0.z, b0.w),
+                            make_float2(b1.x, b1.y), make_float2(b1.z, b1.w)};
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
+      for (int i = 0; i < 8; ++i) {
+        const float2 ai = make_float2(av[i], av[i]);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        for (int j = 0; j < 4; ++j) acc[i][j] = __ffma2_rn(ai, bv[j], acc[i][j]);
+      }
     }
     if (it + 1 < kt) {
-      store_tile<A_T>(As[cur ^ 1], ra, t);
-      store_tile<!B_T>(Bs[cur ^ 1], rb, t);
+      store_tile<A_T>(As[cur ^ 1], ra, t, va);
+      store_tile<!B_T>(Bs[cur ^ 1], rb, t, vb);
     }
     __syncthreads();
   }
@@ -145,27 +185,51 @@ __global__ void __launch_bounds__(kBThreads, 2) k_bgemm(const BgemmArgs a) {
   float* Cb = a.C + b * a.c_batch + (ns > 1 ? sp * a.c_split : 0);
   const float* bias = (EPI == kEpiBiasTanh || EPI == kEpiBias) ? a.bias + b * a.bias_batch : nullptr;
   const float* aux = (EPI == kEpiDtanh || EPI == kEpiPrior) ? a.aux + b * a.aux_batch : nullptr;
+  // four consecutive columns per (row, half): one 16-byte store (and aux load) when the
+  // output / aux rows allow it
+  const bool vc = operand_vec(Cb, a.ldc, a.N);
+  const bool vx = aux != nullptr && operand_vec(aux, a.ldaux, a.N);
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int m = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + i - 4);
     if (m >= a.M) continue;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int n = n0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + j - 4);
-      if (n >= a.N) continue;
-      float v = acc[i][j];
-      if (EPI == kEpiBiasTanh) v = tanhf(v + __ldg(bias + n));
-      if (EPI == kEpiBias) v = v + __ldg(bias + n);
-      if (EPI == kEpiDtanh) {
-        const float h = __ldg(aux + (int64_t)m * a.ldaux + n);
-        v = v * (1.0f - h * h);
+    for (int jh = 0; jh < 2; ++jh) {
+      const int nb = n0 + 64 * jh + tx * 4;
+      if (nb >= a.N) continue;
+      float x[4] = {0.f, 0.f, 0.f, 0.f};
+      if (EPI == kEpiDtanh || EPI == kEpiPrior) {
+        if (vx) {
+          const float4 q = __ldg(reinterpret_cast<const float4*>(aux + (int64_t)m * a.ldaux + nb));
+          x[0] = q.x; x[1] = q.y; x[2] = q.z; x[3] = q.w;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (nb + j < a.N) x[j] = __ldg(aux + (int64_t)m * a.ldaux + nb + j);
+        }
       }
-      if (EPI == kEpiPrior) {
-        const int64_t p = a.p0 + (int64_t)m * a.ldc + n;
-        if (p >= a.prior_lo && p < a.prior_hi)
-          v = fmaf(a.coef, __ldg(aux + (int64_t)m * a.ldaux + n), v);
+      float v[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int n = nb + j;
+        v[j] = (j & 1) ? acc[i][2 * jh + (j >> 1)].y : acc[i][2 * jh + (j >> 1)].x;
+        if (n >= a.N) continue;
+        if (EPI == kEpiBiasTanh) v[j] = tanhf(v[j] + __ldg(bias + n));
+        if (EPI == kEpiBias) v[j] = v[j] + __ldg(bias + n);
+        if (EPI == kEpiDtanh) v[j] = v[j] * (1.0f - x[j] * x[j]);
+        if (EPI == kEpiPrior) {
+          const int64_t p = a.p0 + (int64_t)m * a.ldc + n;
+          if (p >= a.prior_lo && p < a.prior_hi) v[j] = fmaf(a.coef, x[j], v[j]);
+        }
       }
-      Cb[(int64_t)m * a.ldc + n] = v;
+      float* dst = Cb + (int64_t)m * a.ldc + nb;
+      if (vc) {
+        *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (nb + j < a.N) dst[j] = v[j];
+      }
     }
   }
 }
