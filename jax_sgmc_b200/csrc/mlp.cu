@@ -118,12 +118,17 @@ __device__ __forceinline__ bool operand_vec(const float* base, int64_t ld, int c
 
 // A_T: A is stored K x M (M contiguous), else M x K (K contiguous).
 // B_T: B is stored N x K (K contiguous), else K x N (N contiguous).
-template <bool A_T, bool B_T, int EPI>
-__global__ void __launch_bounds__(kBThreads, 2) k_bgemm(const BgemmArgs a) {
+// BN: tile width, 128 or 64 (outputs of at most 64 columns -- the convolutions' channels, the
+// class logits: the thread tile drops its second column half instead of multiplying padding).
+template <bool A_T, bool B_T, int EPI, int BN = kBN>
+__global__ void __launch_bounds__(kBThreads, BN == 64 ? 3 : 2) k_bgemm(const BgemmArgs a) {
+  static_assert(BN == 128 || BN == 64, "tile width");
+  constexpr int NH = BN / 64;          // column halves per thread
   __shared__ __align__(16) float As[2][kBK][kBM + kBPad];
   __shared__ __align__(16) float Bs[2][kBK][kBN + kBPad];
   const int t = threadIdx.x, tx = t & 15, ty = t >> 4;
-  const int m0 = blockIdx.y * kBM, n0 = blockIdx.x * kBN;
+  const int m0 = blockIdx.y * kBM, n0 = blockIdx.x * BN;
+  const int n_end = min(a.N, n0 + BN);   // operand B: columns of this tile only
   const int ns = a.n_split > 1 ? a.n_split : 1;
   const int64_t b = blockIdx.z / ns;
   const int sp = (int)(blockIdx.z - b * ns);
@@ -138,18 +143,18 @@ __global__ void __launch_bounds__(kBThreads, 2) k_bgemm(const BgemmArgs a) {
 
   // accumulators as column pairs: one packed fma.rn.f32x2 per pair (same per-element
   // rounding as 64 scalar FMAs, half the issue slots)
-  float2 acc[8][4];
+  float2 acc[8][2 * NH];
 #pragma unroll
   for (int i = 0; i < 8; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = make_float2(0.f, 0.f);
+    for (int j = 0; j < 2 * NH; ++j) acc[i][j] = make_float2(0.f, 0.f);
 
   float ra[8], rb[8];
   const int kt = (K + kBK - 1) / kBK;
   const bool va = operand_vec(A, a.lda, A_T ? a.M : K);
   const bool vb = operand_vec(B, a.ldb, B_T ? K : a.N);
   load_tile<A_T>(ra, A, a.lda, a_idx, m0, 0, a.M, K, t, va);
-  load_tile<!B_T>(rb, B, a.ldb, nullptr, n0, 0, a.N, K, t, vb);
+  load_tile<!B_T>(rb, B, a.ldb, nullptr, n0, 0, n_end, K, t, vb);
   store_tile<A_T>(As[0], ra, t, va);
   store_tile<!B_T>(Bs[0], rb, t, vb);
   __syncthreads();
@@ -157,22 +162,25 @@ __global__ void __launch_bounds__(kBThreads, 2) k_bgemm(const BgemmArgs a) {
     const int cur = it & 1;
     if (it + 1 < kt) {
       load_tile<A_T>(ra, A, a.lda, a_idx, m0, (it + 1) * kBK, a.M, K, t, va);
-      load_tile<!B_T>(rb, B, a.ldb, nullptr, n0, (it + 1) * kBK, a.N, K, t, vb);
+      load_tile<!B_T>(rb, B, a.ldb, nullptr, n0, (it + 1) * kBK, n_end, K, t, vb);
     }
 #pragma unroll
     for (int kk = 0; kk < kBK; ++kk) {
       const float4 a0 = *reinterpret_cast<const float4*>(&As[cur][kk][ty * 4]);
       const float4 a1 = *reinterpret_cast<const float4*>(&As[cur][kk][64 + ty * 4]);
-      const float4 b0 = *reinterpret_cast<const float4*>(&Bs[cur][kk][tx * 4]);
-      const float4 b1 = *reinterpret_cast<const float4*>(&Bs[cur][kk][64 + tx * 4]);
       const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-      const float2 bv[4] = {make_float2(b0.x, b0.y), make_float2(b0.z, b0.w),
-                            make_float2(b1.x, b1.y), make_float2(b1.z, b1.w)};
+      float2 bv[2 * NH];
+#pragma unroll
+      for (int h = 0; h < NH; ++h) {
+        const float4 q = *reinterpret_cast<const float4*>(&Bs[cur][kk][64 * h + tx * 4]);
+        bv[2 * h] = make_float2(q.x, q.y);
+        bv[2 * h + 1] = make_float2(q.z, q.w);
+      }
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const float2 ai = make_float2(av[i], av[i]);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = __ffma2_rn(ai, bv[j], acc[i][j]);
+        for (int j = 0; j < 2 * NH; ++j) acc[i][j] = __ffma2_rn(ai, bv[j], acc[i][j]);
       }
     }
     if (it + 1 < kt) {
@@ -194,7 +202,7 @@ __global__ void __launch_bounds__(kBThreads, 2) k_bgemm(const BgemmArgs a) {
     const int m = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + i - 4);
     if (m >= a.M) continue;
 #pragma unroll
-    for (int jh = 0; jh < 2; ++jh) {
+    for (int jh = 0; jh < NH; ++jh) {
       const int nb = n0 + 64 * jh + tx * 4;
       if (nb >= a.N) continue;
       float x[4] = {0.f, 0.f, 0.f, 0.f};
@@ -239,8 +247,12 @@ static int launch_bgemm(cudaStream_t s, const BgemmArgs& a, int64_t batch, const
   SGMC_REQUIRE(batch <= 65535, "%s: more than 65535 chains per call", name);
   const int64_t z = batch * (a.n_split > 1 ? a.n_split : 1);
   SGMC_REQUIRE(z <= 65535, "%s: too many chains x K splits", name);
-  dim3 grid((unsigned)((a.N + kBN - 1) / kBN), (unsigned)((a.M + kBM - 1) / kBM), (unsigned)z);
-  launch_pdl(k_bgemm<A_T, B_T, EPI>, grid, dim3(kBThreads), 0, s, a);
+  const unsigned gy = (unsigned)((a.M + kBM - 1) / kBM);
+  if (a.N <= 64)
+    launch_pdl(k_bgemm<A_T, B_T, EPI, 64>, dim3(1, gy, (unsigned)z), dim3(kBThreads), 0, s, a);
+  else
+    launch_pdl(k_bgemm<A_T, B_T, EPI, kBN>, dim3((unsigned)((a.N + kBN - 1) / kBN), gy, (unsigned)z),
+               dim3(kBThreads), 0, s, a);
   return post_launch(name);
 }
 
@@ -487,6 +499,74 @@ __global__ void __launch_bounds__(256) k_col2im_dtanh(const float* __restrict__ 
   }
 }
 
+// The same two kernels for channel counts that are multiples of four (every layer after the
+// first on RGB input): four channels per thread as one 16-byte access, 32-bit index
+// arithmetic (the per-chain extent is checked against 2^31 at the call site).  The sums of
+// col2im run in the same (kh, kw) order, so the results are bit-identical to the scalar form.
+__global__ void __launch_bounds__(256) k_im2col_v4(const float* __restrict__ src, int64_t src_batch,
+                                                   const int32_t* __restrict__ idx, float* __restrict__ dst,
+                                                   const ConvGeom g, uint32_t quads_per_batch) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const float* sb = src + blockIdx.y * src_batch;
+  float4* db = reinterpret_cast<float4*>(dst) + (int64_t)blockIdx.y * quads_per_batch;
+  const uint32_t C4 = (uint32_t)g.Cin >> 2, K4 = 9u * C4;
+  for (uint32_t e = blockIdx.x * 256u + threadIdx.x; e < quads_per_batch; e += gridDim.x * 256u) {
+    const uint32_t k4 = e % K4, row = e / K4;
+    const uint32_t c4 = k4 % C4, kk = k4 / C4, kh = kk / 3u, kw = kk - kh * 3u;
+    const uint32_t wo = row % (uint32_t)g.Wo, r2 = row / (uint32_t)g.Wo;
+    const uint32_t ho = r2 % (uint32_t)g.Ho, i = r2 / (uint32_t)g.Ho;
+    const int hi = (int)(ho * g.stride + kh) - 1, wi = (int)(wo * g.stride + kw) - 1;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (hi >= 0 && hi < g.Hi && wi >= 0 && wi < g.Wi) {
+      const int64_t obs = idx ? idx[i] : (int64_t)i;
+      v = __ldg(reinterpret_cast<const float4*>(sb + ((obs * g.Hi + hi) * g.Wi + wi) * g.Cin) + c4);
+    }
+    db[e] = v;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_col2im_dtanh_v4(const float* __restrict__ dP,
+                                                         const float* __restrict__ h,
+                                                         float* __restrict__ dZ, const ConvGeom g,
+                                                         uint32_t quads_per_batch) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const uint32_t C4 = (uint32_t)g.Cin >> 2, K4 = 9u * C4;
+  const int64_t rows = (int64_t)g.n * g.Ho * g.Wo;
+  const float4* pb = reinterpret_cast<const float4*>(dP) + (int64_t)blockIdx.y * rows * K4;
+  const float4* hb = reinterpret_cast<const float4*>(h) + (int64_t)blockIdx.y * quads_per_batch;
+  float4* zb = reinterpret_cast<float4*>(dZ) + (int64_t)blockIdx.y * quads_per_batch;
+  for (uint32_t e = blockIdx.x * 256u + threadIdx.x; e < quads_per_batch; e += gridDim.x * 256u) {
+    const uint32_t c4 = e % C4, r1 = e / C4;
+    const int wi = (int)(r1 % (uint32_t)g.Wi);
+    const uint32_t r2 = r1 / (uint32_t)g.Wi;
+    const int hi = (int)(r2 % (uint32_t)g.Hi);
+    const uint32_t i = r2 / (uint32_t)g.Hi;
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) {
+      const int th = hi + 1 - kh;
+      if (th < 0 || th % g.stride) continue;
+      const int ho = th / g.stride;
+      if (ho >= g.Ho) continue;
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        const int tw = wi + 1 - kw;
+        if (tw < 0 || tw % g.stride) continue;
+        const int wo = tw / g.stride;
+        if (wo >= g.Wo) continue;
+        const int64_t row = ((int64_t)i * g.Ho + ho) * g.Wo + wo;
+        const float4 q = pb[row * K4 + (uint32_t)(kh * 3 + kw) * C4 + c4];
+        s.x += q.x; s.y += q.y; s.z += q.z; s.w += q.w;
+      }
+    }
+    const float4 hv = hb[e];
+    zb[e] = make_float4(s.x * (1.0f - hv.x * hv.x), s.y * (1.0f - hv.y * hv.y),
+                        s.z * (1.0f - hv.z * hv.z), s.w * (1.0f - hv.w * hv.w));
+  }
+}
+
 // out[b][m][n] = sum_s part[b][s][m][n] in split order (+ coef * aux on the prior range):
 // the second stage of the split-K GEMMs and of the split column sums
 __global__ void __launch_bounds__(256) k_splitk_reduce(const float* __restrict__ part, int n_split,
@@ -494,7 +574,9 @@ __global__ void __launch_bounds__(256) k_splitk_reduce(const float* __restrict__
                                                        int64_t out_batch, int64_t ldc,
                                                        const float* __restrict__ aux,
                                                        int64_t aux_batch, float coef, int64_t p0,
-                                                       int64_t prior_lo, int64_t prior_hi) {
+                                                       int64_t prior_lo, int64_t prior_hi,
+                                                       const float* __restrict__ bias,
+                                                       int64_t bias_batch) {
   pdl_launch_dependents();
   pdl_wait();
   const int64_t b = blockIdx.y;
@@ -506,6 +588,7 @@ __global__ void __launch_bounds__(256) k_splitk_reduce(const float* __restrict__
     const int64_t o = m * ldc + n;
     const int64_t p = p0 + o;
     if (aux != nullptr && p >= prior_lo && p < prior_hi) s = fmaf(coef, aux[b * aux_batch + o], s);
+    if (bias != nullptr) s += bias[b * bias_batch + n];
     out[b * out_batch + o] = s;
   }
 }
@@ -646,9 +729,18 @@ static int cnn_layers(const sgmc_cnn_spec& s, int64_t n, CnnLayer* L) {
   return Hi * Wi * s.channels[s.n_conv];      // features of the dense head
 }
 
+// The dense head has n x n_classes outputs per chain over F features: with few chains that
+// is a handful of tiles with a long serial K loop, so K is split like the weight gradients
+// (512 features per split at least, 16 splits at most) whenever the plain grid would not
+// fill the SMs.
+static int cnn_head_splits(int64_t F, int64_t n, int64_t C) {
+  if (((n + kBM - 1) / kBM) * C >= 2 * 148 || F < 1024) return 1;
+  return (int)std::min<int64_t>(std::min<int64_t>(16, F / 512), 65535 / C);
+}
+
 static size_t cnn_carve(CnnWs* w, uint8_t* base, const sgmc_cnn_spec& s, int64_t C, int64_t n) {
   CnnLayer L[SGMC_CNN_MAX_CONV];
-  cnn_layers(s, n, L);
+  const int64_t F_head = cnn_layers(s, n, L);
   size_t off = 0;
   auto take = [&](size_t floats) {
     float* p = base ? reinterpret_cast<float*>(base + off) : nullptr;
@@ -664,6 +756,7 @@ static size_t cnn_carve(CnnWs* w, uint8_t* base, const sgmc_cnn_spec& s, int64_t
     part_max = std::max(part_max, (size_t)C * std::max(cnn_splits(L[l].rows), 2) * L[l].K * L[l].Cout);
     if (w) { w->P[l] = p; w->H[l + 1] = h; w->dZ[l + 1] = d; }
   }
+  part_max = std::max(part_max, (size_t)C * cnn_head_splits(F_head, n, C) * n * s.n_classes);
   float* dp = take(dp_max ? dp_max : 1);
   float* part = take(part_max);
   if (w) w->part = part;
@@ -744,7 +837,14 @@ int sgmc_cnn_potential_grad(void* stream, const sgmc_cnn_spec* spec, const float
   for (int l = 0; l < NL; ++l) {
     const int64_t per = L[l].rows * L[l].K;
     const int64_t in_per = (int64_t)n * L[l].g.Hi * L[l].g.Wi * L[l].g.Cin;
-    if (l == 0)
+    const float* im_src = l == 0 ? X : (const float*)w.H[l];
+    const bool v4 = L[l].g.Cin % 4 == 0 && per < (1ll << 31) &&
+                    (reinterpret_cast<uintptr_t>(im_src) & 15) == 0;
+    if (v4)
+      launch_pdl(k_im2col_v4, dim3(blocks(per / 4), l == 0 ? 1u : (unsigned)C), dim3(256), 0, s, im_src,
+                 l == 0 ? (int64_t)0 : in_per, l == 0 ? idx : (const int32_t*)nullptr, w.P[l], L[l].g,
+                 (uint32_t)(per / 4));
+    else if (l == 0)
       launch_pdl(k_im2col, dim3(blocks(per), 1), dim3(256), 0, s, X, (int64_t)0, idx, w.P[0], L[0].g, per);
     else
       launch_pdl(k_im2col, dim3(blocks(per), (unsigned)C), dim3(256), 0, s, (const float*)w.H[l],
@@ -765,7 +865,20 @@ int sgmc_cnn_potential_grad(void* stream, const sgmc_cnn_spec* spec, const float
     g.C = w.logits; g.c_batch = n * (int64_t)sp.n_classes; g.ldc = sp.n_classes;
     g.M = (int)n; g.N = sp.n_classes; g.K = F;
     g.bias = theta + sp.b_off[NL]; g.bias_batch = P;
-    if (launch_bgemm<false, false, kEpiBias>(s, g, C, "k_bgemm<head>")) return 1;
+    const int Sh = cnn_head_splits(F, n, C);
+    if (Sh > 1) {
+      const int64_t MN = n * (int64_t)sp.n_classes;
+      g.C = w.part; g.c_batch = Sh * MN; g.c_split = MN;
+      g.n_split = Sh; g.k_chunk = (int)((((int64_t)F + Sh - 1) / Sh + kBK - 1) / kBK * kBK);
+      if (launch_bgemm<false, false, kEpiStore>(s, g, C, "k_bgemm<head, split-K>")) return 1;
+      launch_pdl(k_splitk_reduce, dim3((unsigned)std::min<int64_t>((MN + 255) / 256, 1024), (unsigned)C),
+                 dim3(256), 0, s, (const float*)w.part, Sh, MN, sp.n_classes, w.logits, MN,
+                 (int64_t)sp.n_classes, (const float*)nullptr, (int64_t)0, 0.f, (int64_t)0,
+                 (int64_t)0, (int64_t)0, theta + sp.b_off[NL], P);
+      if (post_launch("k_splitk_reduce<head>")) return 1;
+    } else if (launch_bgemm<false, false, kEpiBias>(s, g, C, "k_bgemm<head>")) {
+      return 1;
+    }
   }
   HeadArgs h{};
   h.logits = w.logits; h.dlogits = grad ? w.dlogits : nullptr; h.ell_ws = w.ell; h.ell_out = ell;
@@ -813,7 +926,8 @@ int sgmc_cnn_potential_grad(void* stream, const sgmc_cnn_spec* spec, const float
       if (post_launch("k_colsum_part")) return 1;
       launch_pdl(k_splitk_reduce, dim3(1, (unsigned)C), dim3(256), 0, s, (const float*)w.part, S,
                  (int64_t)L[l].Cout, L[l].Cout, grad + sp.b_off[l], P, (int64_t)L[l].Cout,
-                 theta + sp.b_off[l], P, coef, (int64_t)sp.b_off[l], prior_lo, prior_hi);
+                 theta + sp.b_off[l], P, coef, (int64_t)sp.b_off[l], prior_lo, prior_hi,
+                 (const float*)nullptr, (int64_t)0);
       if (post_launch("k_splitk_reduce")) return 1;
     }
     {   // dW_l [9 Cin, Cout] = patches^T [9 Cin, rows] . dZ [rows, Cout]: split over the rows
@@ -840,7 +954,7 @@ int sgmc_cnn_potential_grad(void* stream, const sgmc_cnn_spec* spec, const float
       launch_pdl(k_splitk_reduce, dim3((unsigned)std::min<int64_t>((MN + 255) / 256, 1024), (unsigned)C),
                  dim3(256), 0, s, (const float*)w.part, S_eff, MN, L[l].Cout, grad + sp.w_off[l], P,
                  (int64_t)L[l].Cout, theta + sp.w_off[l], P, coef, (int64_t)sp.w_off[l], prior_lo,
-                 prior_hi);
+                 prior_hi, (const float*)nullptr, (int64_t)0);
       if (post_launch("k_splitk_reduce")) return 1;
     }
     if (l > 0) {   // dPatches [rows, 9 Cin] = dZ [rows, Cout] . W^T, then col2im and tanh'
@@ -851,8 +965,12 @@ int sgmc_cnn_potential_grad(void* stream, const sgmc_cnn_spec* spec, const float
       g.M = (int)L[l].rows; g.N = (int)L[l].K; g.K = L[l].Cout;
       if (launch_bgemm<false, true, kEpiStore>(s, g, C, "k_bgemm<dPatches>")) return 1;
       const int64_t in_per = (int64_t)n * L[l].g.Hi * L[l].g.Wi * L[l].g.Cin;
-      launch_pdl(k_col2im_dtanh, dim3(blocks(in_per), (unsigned)C), dim3(256), 0, s,
-                 (const float*)w.dP, (const float*)w.H[l], w.dZ[l], L[l].g, in_per);
+      if (L[l].g.Cin % 4 == 0 && in_per < (1ll << 31) && per < (1ll << 31))
+        launch_pdl(k_col2im_dtanh_v4, dim3(blocks(in_per / 4), (unsigned)C), dim3(256), 0, s,
+                   (const float*)w.dP, (const float*)w.H[l], w.dZ[l], L[l].g, (uint32_t)(in_per / 4));
+      else
+        launch_pdl(k_col2im_dtanh, dim3(blocks(in_per), (unsigned)C), dim3(256), 0, s,
+                   (const float*)w.dP, (const float*)w.H[l], w.dZ[l], L[l].g, in_per);
       if (post_launch("k_col2im_dtanh")) return 1;
     }
   }

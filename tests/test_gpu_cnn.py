@@ -57,6 +57,9 @@ def _close_grad(got, want, tol=1e-5):
     ((9, 8, 3), (5, 6), (2, 2), 10, 4, 19, True),
     ((8, 8, 1), (4,), (1,), 2, 2, 33, False),          # one convolution, stride 1
     ((16, 16, 3), (8, 16), (2, 2), 10, 2, 40, True),   # rows beyond one GEMM tile
+    ((32, 32, 3), (4, 16), (2, 2), 10, 2, 9, True),    # 1024 head features: split-K head
+    ((8, 8, 2), (72,), (1,), 3, 2, 5, False),          # > 64 channels: 128-wide tiles, 9 head splits
+    ((7, 6, 4), (8, 4), (1, 2), 3, 2, 6, True),        # channels % 4 == 0 from the input on: vector im2col / col2im
 ])
 def test_cnn_potential_and_gradient_match_oracle(gpu, image, channels, strides, classes, C, n, masked):
   from jax_sgmc_b200 import ops
