@@ -112,7 +112,8 @@ __device__ __forceinline__ void group_noise(Key lk, uint32_t j0, uint32_t half,
 //                     int64_t iA, int64_t iB, int64_t chain, uint32_t eA,
 //                     uint32_t eB) const;              // returns a partial sum
 //     float apply_one(int64_t i, float noise, int64_t chain, uint32_t e) const;
-//     void reduce(int64_t chain, float warp_sum) const;         // lane 0 only
+//     void reduce(int64_t chain, uint32_t tile_in_chain, uint32_t tiles_per_chain,
+//                 float warp_sum) const;                        // lane 0 only, if kReduce
 //     static constexpr bool kReduce;
 //     static constexpr bool kSplit;   // optional: apply_vec also returns |max| and
 //                                     // reduce2(chain, tile_in_chain, sum, max) is called
@@ -228,11 +229,11 @@ k_noise_pass(const __grid_constant__ LeafTable tab,
         amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, s));
       }
       if (lane == 0) op.reduce2(c, lt, partial, amax);
-    } else if (Op::kReduce) {
+    } else if constexpr (Op::kReduce) {
 #pragma unroll
       for (int s = 16; s > 0; s >>= 1)
         partial += __shfl_xor_sync(0xffffffffu, partial, s);
-      if (lane == 0) op.reduce(c, partial);
+      if (lane == 0) op.reduce(c, lt, tpc, partial);
     }
   }
 }

@@ -22,6 +22,9 @@
 #include <cuda_fp16.h>
 
 #include <cmath>
+#include <map>
+#include <mutex>
+#include <utility>
 
 namespace sgmc {
 
@@ -139,7 +142,6 @@ struct NormalLikeOp {
     out[i] = n;
     return 0.f;
   }
-  __device__ void reduce(int64_t, float) const {}
 };
 
 // ---- SGLD / pSGLD -----------------------------------------------------------
@@ -201,7 +203,6 @@ struct SgldOp {
     if (RMS) v[i] = vv;
     return 0.f;
   }
-  __device__ void reduce(int64_t, float) const {}
 };
 
 // ---- SGLD / pSGLD that also emits the tensor-core operand of the NEXT potential ----
@@ -360,7 +361,6 @@ struct SghmcBeginOp {
     mom[i] = p;
     return 0.f;
   }
-  __device__ void reduce(int64_t, float) const {}
 };
 
 // step: integrator.py:616-655 (+ next position update :610-612 unless last)
@@ -427,7 +427,6 @@ struct SghmcStepOp {
     mom[i] = p;
     return 0.f;
   }
-  __device__ void reduce(int64_t, float) const {}
 };
 
 // ---- OBABO --------------------------------------------------------------------
@@ -496,8 +495,8 @@ struct ObaboAOp {   // integrator.py:210-240
     mom[i] = p;
     return s;
   }
-  __device__ void reduce(int64_t c, float s) const {
-    atomicAdd(&ke[c], 0.5f * s);
+  __device__ void reduce(int64_t c, uint32_t lt, uint32_t tpc, float s) const {
+    ke[c * tpc + lt] = s;         // per-tile partial; k_energy_finish adds them in tile order
   }
 };
 
@@ -555,8 +554,8 @@ struct ObaboBOp {   // integrator.py:248-261
     mom[i] = p;
     return s;
   }
-  __device__ void reduce(int64_t c, float s) const {
-    atomicAdd(&ke[c], 0.5f * s);
+  __device__ void reduce(int64_t c, uint32_t lt, uint32_t tpc, float s) const {
+    ke[c * tpc + lt] = s;         // per-tile partial; k_energy_finish adds them in tile order
   }
 };
 
@@ -630,8 +629,8 @@ struct RevLeapfrogOp {
     mom[i] = p;
     return s;
   }
-  __device__ void reduce(int64_t c, float s) const {
-    atomicAdd(&energy[c], half_eps * s);
+  __device__ void reduce(int64_t c, uint32_t lt, uint32_t tpc, float s) const {
+    energy[c * tpc + lt] = s;     // per-tile partial; k_energy_finish adds them in tile order
   }
 };
 
@@ -644,6 +643,64 @@ struct AdaptedMassScope {
   AdaptedMassScope(const float* inv, const float* sqrt) { g_adapted.inv = inv; g_adapted.sqrt = sqrt; }
   ~AdaptedMassScope() { g_adapted = AdaptedMass{}; }
 };
+
+// ---- per-chain energies in a fixed order ------------------------------------------------
+// The OBABO and reversible-leapfrog passes reduce <p, M^-1 p> / <p + p', M^-1 g> per chain.
+// A chain's warp-tiles run on different CTAs in no particular order, so the pass stores one
+// partial per (chain, tile) and k_energy_finish adds them in tile order: the energy -- and
+// with it every Metropolis-Hastings decision -- is reproducible run to run.  The partials
+// live in a scratch buffer cached per (device, stream): calls on one stream are ordered, so
+// they can share it; it only ever grows.
+__global__ void __launch_bounds__(256) k_energy_finish(const float* __restrict__ part, uint32_t tpc,
+                                                       float* __restrict__ out, float scale,
+                                                       int64_t n_chains) {
+  pdl_wait();
+  const int64_t c = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (c >= n_chains) return;
+  const float* p = part + c * tpc;
+  float s = 0.f;
+  for (uint32_t t = lane; t < tpc; t += 32) s += p[t];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) out[c] += scale * s;
+}
+
+static float* energy_scratch(cudaStream_t stream, size_t floats) {
+  struct Buf { float* p = nullptr; size_t cap = 0; };
+  static std::mutex mu;
+  static std::map<std::pair<int, cudaStream_t>, Buf> cache;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+  std::lock_guard<std::mutex> lock(mu);
+  Buf& b = cache[{dev, stream}];
+  if (b.cap < floats) {
+    if (b.p) {   // earlier passes on this stream may still read the old buffer
+      if (cudaStreamSynchronize(stream) != cudaSuccess) return nullptr;
+      cudaFree(b.p);
+      b = Buf{};
+    }
+    const size_t cap = floats + floats / 4 + 1024;
+    if (cudaMalloc(&b.p, cap * sizeof(float)) != cudaSuccess) { b.p = nullptr; return nullptr; }
+    b.cap = cap;
+  }
+  return b.p;
+}
+
+// Runs `op` (whose energy pointer the caller has set to the scratch) and then the ordered sum
+// out[c] += scale * sum_t part[c][t].
+template <class Op>
+static int launch_energy_pass(cudaStream_t stream, const LeafTable& tab, const uint32_t* keys_in,
+                              uint32_t* keys_out, int64_t n_chains, int key_mode, int layout,
+                              const Op& op, const float* part, float* out, float scale,
+                              const char* name) {
+  if (int e = launch_noise_pass(stream, tab, keys_in, keys_out, n_chains, key_mode, layout, op, name))
+    return e;
+  if (n_chains == 0 || tab.tiles_per_chain == 0) return 0;
+  launch_pdl(k_energy_finish, dim3((unsigned)((n_chains + 7) / 8)), dim3(256), 0, stream, part,
+             tab.tiles_per_chain, out, scale, n_chains);
+  return post_launch(name);
+}
 
 static bool aligned16(std::initializer_list<const void*> ps) {
   for (const void* p : ps)
@@ -1131,13 +1188,14 @@ int sgmc_obabo_pass_a(void* stream, float* theta, float* momentum,
   // integrator.py:195-199
   const float a = (float)exp((double)(-friction * step_size));  // f64 libm, rounded once
   const float o_noise = sqrtf((1.0f - a) * temperature);
-  ObaboAOp op{theta, momentum, grad, ke_start, mass, step_size, sqrtf(a),
+  float* part = energy_scratch((cudaStream_t)stream, (size_t)n_chains * tab.tiles_per_chain);
+  SGMC_REQUIRE(part != nullptr || n_chains == 0, "sgmc_obabo_pass_a: no memory for the energy partials");
+  ObaboAOp op{theta, momentum, grad, part, mass, step_size, sqrtf(a),
               o_noise, -1.0f * (0.5f * step_size)};
   op.mass_inv = g_adapted.inv;
   op.mass_sqrt = g_adapted.sqrt;
-  return launch_noise_pass((cudaStream_t)stream, tab, keys_in, keys_out,
-                           n_chains, kKeySplit3A, prng_layout, op,
-                           "sgmc_obabo_pass_a");
+  return launch_energy_pass((cudaStream_t)stream, tab, keys_in, keys_out, n_chains, kKeySplit3A,
+                            prng_layout, op, part, ke_start, 0.5f, "sgmc_obabo_pass_a");
 }
 
 int sgmc_obabo_pass_b(void* stream, float* momentum, const float* grad,
@@ -1150,13 +1208,14 @@ int sgmc_obabo_pass_b(void* stream, float* momentum, const float* grad,
                                aligned16({momentum, grad}))) return e;
   const float a = (float)exp((double)(-friction * step_size));  // f64 libm, rounded once
   const float o_noise = sqrtf((1.0f - a) * temperature);
-  ObaboBOp op{momentum, grad, ke_end, mass, sqrtf(a), o_noise,
+  float* part = energy_scratch((cudaStream_t)stream, (size_t)n_chains * tab.tiles_per_chain);
+  SGMC_REQUIRE(part != nullptr || n_chains == 0, "sgmc_obabo_pass_b: no memory for the energy partials");
+  ObaboBOp op{momentum, grad, part, mass, sqrtf(a), o_noise,
               -1.0f * (0.5f * step_size)};
   op.mass_inv = g_adapted.inv;
   op.mass_sqrt = g_adapted.sqrt;
-  return launch_noise_pass((cudaStream_t)stream, tab, keys_in, nullptr,
-                           n_chains, kKeySplit3B, prng_layout, op,
-                           "sgmc_obabo_pass_b");
+  return launch_energy_pass((cudaStream_t)stream, tab, keys_in, nullptr, n_chains, kKeySplit3B,
+                            prng_layout, op, part, ke_end, 0.5f, "sgmc_obabo_pass_b");
 }
 
 int sgmc_revleapfrog_step(void* stream, float* theta, float* momentum, const float* grad,
@@ -1170,14 +1229,16 @@ int sgmc_revleapfrog_step(void* stream, float* theta, float* momentum, const flo
                                aligned16({theta, momentum, grad}))) return e;
   // integrator.py:423-446: weak-typed python scalars times the f32 step size
   const float ef = step_size * friction;
-  RevLeapfrogOp op{theta, momentum, grad, energy, mass,
+  float* part = energy_scratch((cudaStream_t)stream, (size_t)n_chains * tab.tiles_per_chain);
+  SGMC_REQUIRE(part != nullptr || n_chains == 0, "sgmc_revleapfrog_step: no memory for the energy partials");
+  RevLeapfrogOp op{theta, momentum, grad, part, mass,
                    1.0f - ef, -1.0f * step_size, sqrtf((4.0f * friction) * step_size),
                    1.0f / (1.0f + ef), 0.5f * step_size,
                    last ? 0.5f * step_size : step_size};
   op.mass_inv = g_adapted.inv;
   op.mass_sqrt = g_adapted.sqrt;
-  return launch_noise_pass((cudaStream_t)stream, tab, keys_in, keys_out, n_chains,
-                           kKeySplit2, prng_layout, op, "sgmc_revleapfrog_step");
+  return launch_energy_pass((cudaStream_t)stream, tab, keys_in, keys_out, n_chains, kKeySplit2,
+                            prng_layout, op, part, energy, 0.5f * step_size, "sgmc_revleapfrog_step");
 }
 
 // The same three passes with an ADAPTED mass matrix (adaption.mass_matrix, diagonal): every

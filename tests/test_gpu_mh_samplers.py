@@ -335,3 +335,44 @@ def test_full_potential_one_call_equals_the_batch_loop(gpu, C, d, N, mb, path):
   ids = np.arange(int(np.ceil(N / mb)) * mb).reshape(-1, mb)
   batches = [(X[i % N], y[i % N], (i < N).astype(np.float32)) for i in ids]
   np.testing.assert_allclose(fast.numpy(), o_full(theta, batches, N), rtol=2e-5)
+
+
+def test_energies_are_reduced_in_a_fixed_order(gpu):
+  """The per-chain energies of the OBABO passes and of the reversible leapfrog are sums over
+  hundreds of warp-tiles that run on different CTAs: repeated runs on the same inputs must
+  give the same bits (one partial per (chain, tile), added in tile order by k_energy_finish),
+  the accumulation onto a non-zero start value included."""
+  from jax_sgmc_b200 import ops
+  from jax_sgmc_b200.device import DeviceArray as DA
+  rng = np.random.default_rng(4)
+  C, sizes = 5, [70001, 3, 130000, 517]        # 785 tiles of 256 parameters per chain, ragged leaves
+  P = sum(sizes)
+  theta = rng.standard_normal((C, P)).astype(np.float32)
+  mom = rng.standard_normal((C, P)).astype(np.float32)
+  grad = (rng.standard_normal((C, P)) * 3).astype(np.float32)
+  keys = _keys(C, 21)
+  start = rng.standard_normal(C).astype(np.float32)
+
+  def run(which):
+    d_t, d_p, d_g = DA.from_numpy(theta), DA.from_numpy(mom), DA.from_numpy(grad)
+    e = DA.from_numpy(start)
+    kin, kout = DA.from_numpy(keys), DA((C, 2), np.uint32)
+    if which == "a":
+      ops.obabo_pass_a(d_t, d_p, d_g, e, kin, kout, sizes, 0.01, 1.2, 0.8)
+    elif which == "b":
+      ops.obabo_pass_b(d_p, d_g, e, kin, sizes, 0.01, 1.2, 0.8)
+    else:
+      ops.revleapfrog_step(d_t, d_p, d_g, e, kin, kout, sizes, 0.01, 0.3)
+    return e.numpy().view(np.uint32), d_p.numpy()
+
+  for which in ("a", "b", "leapfrog"):
+    first, p_after = run(which)
+    for _ in range(4):
+      again, _p = run(which)
+      assert np.array_equal(first, again), which
+    got = first.view(np.float32)
+    assert np.all(np.isfinite(got)) and not np.array_equal(got, start)
+    if which == "b":   # ke_end += 0.5 <p3, p3>, p3 = the momentum before the O step: check by value
+      p3 = (np.float32(-0.005) * grad + mom).astype(np.float32)
+      want = start + 0.5 * (p3.astype(np.float64) ** 2).sum(axis=1)
+      np.testing.assert_allclose(got, want, rtol=1e-5)
