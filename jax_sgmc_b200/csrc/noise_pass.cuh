@@ -38,6 +38,13 @@ struct LeafTable {
   uint32_t size[SGMC_MAX_LEAVES];   // leaf size
   uint32_t gstart[SGMC_MAX_LEAVES + 1];
   uint8_t vec_ok[SGMC_MAX_LEAVES];  // float4 path legal for this leaf
+  // The leaf could take the float4 path but its first element is not 16-byte aligned in every
+  // chain (P or the leaf offset is not a multiple of four: the 669 706-parameter classifier of
+  // C3).  Such a leaf gets ONE EXTRA group: group 0 covers the first s = (4 - misalignment) & 3
+  // pairs of the chain's copy one by one, groups k >= 1 the pairs [s + 4(k-1), s + 4k), which
+  // start 16-byte aligned in that chain.  The noise belongs to the pair index, not to the
+  // group, so the draws are unchanged.
+  uint8_t shifted[SGMC_MAX_LEAVES];
 };
 
 // How the noise key of this pass derives from the chain key (see the op
@@ -197,12 +204,17 @@ k_noise_pass(const __grid_constant__ LeafTable tab,
       while (l + 1 < L && g >= tab.gstart[l + 1]) ++l;
       const uint32_t size = tab.size[l];
       const uint32_t half = (size + 1u) >> 1;
-      const uint32_t j0 = (g - tab.gstart[l]) * 4u;
+      uint32_t j0 = (g - tab.gstart[l]) * 4u, cnt = 4u;
       const Key lk = s_keys[(int)(c - c_lo) * L + l];
       const int64_t base = c * (int64_t)tab.P + tab.off[l];
+      if (tab.shifted[l]) {
+        const uint32_t s = (4u - ((uint32_t)base & 3u)) & 3u;
+        if (j0 == 0u) cnt = s;
+        else j0 = j0 - 4u + s;
+      }
       const uint32_t eA = tab.off[l] + j0, eB = eA + half;
       float nA[4], nB[4];
-      if (tab.vec_ok[l] && j0 + 4u <= half) {
+      if (tab.vec_ok[l] && cnt == 4u && j0 + 4u <= half) {
         typename Op::Regs r;
         op.load_vec(r, base + j0, base + half + j0);   // loads first ...
         group_noise<LAYOUT, true>(lk, j0, half, size, nA, nB);  // ... then ALU work
@@ -214,7 +226,7 @@ k_noise_pass(const __grid_constant__ LeafTable tab,
         group_noise<LAYOUT>(lk, j0, half, size, nA, nB);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          if (j0 + q < half) {
+          if ((uint32_t)q < cnt && j0 + q < half) {
             partial += op.apply_one(base + j0 + q, nA[q], c, eA + q);
             if (j0 + q + half < size)
               partial += op.apply_one(base + half + j0 + q, nB[q], c, eB + q);

@@ -47,9 +47,13 @@ int build_leaf_table(LeafTable* t, const int64_t* leaf_sizes, int n_leaves,
     t->off[l] = (uint32_t)off;
     t->size[l] = (uint32_t)size;
     t->gstart[l] = (uint32_t)g;
-    t->vec_ok[l] = (ptrs_aligned16 && P % 4 == 0 && off % 4 == 0 &&
-                    half % 4 == 0 && size % 2 == 0) ? 1 : 0;
-    g += (half + 3) / 4;
+    // float4 path: both halves of the leaf start 16-byte aligned -- in every chain when P and
+    // the offset are multiples of four, else after a per-chain shift (see LeafTable::shifted)
+    const bool capable = ptrs_aligned16 && half % 4 == 0 && size % 2 == 0 && size > 0;
+    const bool aligned_everywhere = P % 4 == 0 && off % 4 == 0;
+    t->vec_ok[l] = capable ? 1 : 0;
+    t->shifted[l] = (capable && !aligned_everywhere) ? 1 : 0;
+    g += (half + 3) / 4 + t->shifted[l];
     off += size;
   }
   t->gstart[n_leaves] = (uint32_t)g;
@@ -1074,7 +1078,7 @@ int sgld_update_split(cudaStream_t stream, float* theta, float* v, const float* 
   const int64_t sizes[1] = {P};
   if (int e = build_leaf_table(&tab, sizes, 1, n_chains,
                                aligned16({theta, v, grad, so.th_hi, so.th_lo}))) return e;
-  SGMC_REQUIRE(tab.vec_ok[0], "split update needs 16-byte aligned buffers");
+  SGMC_REQUIRE(tab.vec_ok[0] && !tab.shifted[0], "split update needs 16-byte aligned buffers");
   const float eps = step_size;
   const float ns = sqrtf((2.0f * temperature) * eps);
   const bool rms = v != nullptr;

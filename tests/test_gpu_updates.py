@@ -12,7 +12,9 @@ from oracle import sgmc as osgmc
 
 pytestmark = pytest.mark.gpu
 
-SIZES = [[1024], [1, 4], [8, 16, 40], [7, 2, 33], [2048, 10]]
+# [2048, 10] and [6, 64, 3, 136]: float4-capable leaves whose alignment differs from chain to
+# chain (P % 4 = 2 and P odd): the per-chain shifted groups of LeafTable::shifted
+SIZES = [[1024], [1, 4], [8, 16, 40], [7, 2, 33], [2048, 10], [6, 64, 3, 136]]
 LAYOUTS = ["original", "partitionable"]
 
 
