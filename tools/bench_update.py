@@ -26,18 +26,20 @@ def main():
   ap.add_argument("--sets", type=int, default=6)
   ap.add_argument("--kernels", default="sgld,sgld_rms,sghmc,obabo_a,obabo_b,normal_like")
   ap.add_argument("--layout", default="original")
+  ap.add_argument("--sizes", default="", help="comma-separated leaf sizes (overrides --params)")
   a = ap.parse_args()
   device.set_device(0)
   s = Stream.create()
   device.set_current_stream(s)
-  C, P, R = a.chains, a.params, a.sets
+  leaf_sizes = [int(x) for x in a.sizes.split(",")] if a.sizes else [a.params]
+  C, P, R = a.chains, sum(leaf_sizes), a.sets
   pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
   peak = json.load(open(pk)).get("hbm_gbs", 6650.0) if os.path.exists(pk) else 6650.0
   sets = [dict(t=DA.zeros((C, P)), v=DA.full((C, P), 1.0), g=DA.full((C, P), 0.01),
                p=DA.zeros((C, P))) for _ in range(R)]
   ke = DA.zeros((C,))
   kk = [ops.prng_keys(range(C)), DA((C, 2), np.uint32)]
-  sizes = [P]
+  sizes = leaf_sizes
   eps = 1e-3
 
   def run(name, i):
