@@ -597,7 +597,9 @@ __global__ void __launch_bounds__(256) k_splitk_reduce(const float* __restrict__
 // hundreds of thousands of rows, e.g. 27 x 32 for the first layer on RGB images), where a
 // 128 x 128 GEMM tile would be 95 % padding: part[c][s][m][n] = sum over the split's rows
 // of P[row][m] dZ[c][row][n].  A CTA stages 64 rows of both operands in shared memory; a
-// thread owns up to four outputs.
+// thread owns up to four outputs -- four neighbouring columns of one output row when N is a
+// multiple of four (one 16-byte and one 4-byte shared-memory load per four FMAs), any four
+// otherwise.  Every output adds its rows in row order either way.
 __global__ void __launch_bounds__(256) k_dw_tallskinny(const float* __restrict__ Pm, int64_t p_batch,
                                                        const float* __restrict__ dZ, int64_t rows,
                                                        int M, int N, int64_t row_chunk,
@@ -612,11 +614,12 @@ __global__ void __launch_bounds__(256) k_dw_tallskinny(const float* __restrict__
   const float* P = Pm + c * p_batch;
   const float* Z = dZ + c * rows * N;
   const int MN = M * N;
+  const bool quads = (N & 3) == 0;     // M N / 4 <= 256 quads: one per thread
   int om[4], on[4];
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
-    const int o = threadIdx.x + q * 256;
+    const int o = quads ? threadIdx.x * 4 + q : threadIdx.x + q * 256;
     om[q] = o < MN ? o / N : 0;
     on[q] = o < MN ? o - om[q] * N : 0;
   }
@@ -626,6 +629,22 @@ __global__ void __launch_bounds__(256) k_dw_tallskinny(const float* __restrict__
     for (int e = threadIdx.x; e < nr * M; e += 256) sP[e] = P[r * M + e];
     for (int e = threadIdx.x; e < nr * N; e += 256) sZ[e] = Z[r * N + e];
     __syncthreads();
+    if (quads) {
+      if (threadIdx.x * 4 < MN) {
+        const float* p = sP + om[0];
+        const float* z = sZ + on[0];
+#pragma unroll 8
+        for (int i = 0; i < nr; ++i) {
+          const float a = p[i * M];
+          const float4 q = *reinterpret_cast<const float4*>(z + i * N);
+          acc[0] = fmaf(a, q.x, acc[0]);
+          acc[1] = fmaf(a, q.y, acc[1]);
+          acc[2] = fmaf(a, q.z, acc[2]);
+          acc[3] = fmaf(a, q.w, acc[3]);
+        }
+      }
+      continue;
+    }
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       if (threadIdx.x + q * 256 >= MN) break;
@@ -637,7 +656,7 @@ __global__ void __launch_bounds__(256) k_dw_tallskinny(const float* __restrict__
   float* out = part + (c * gridDim.x + sp) * MN;
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
-    const int o = threadIdx.x + q * 256;
+    const int o = quads ? threadIdx.x * 4 + q : threadIdx.x + q * 256;
     if (o < MN) out[o] = acc[q];
   }
 }
